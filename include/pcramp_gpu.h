@@ -1,0 +1,132 @@
+/* pcramp_gpu.h -- C ABI of the B200 (sm_100a) primer-pair scoring path for PCRamp.
+ *
+ * PCRamp (the reference) has no plugin or FFI layer: its hot path is a set of C++ free functions
+ * and PCR methods called from main().  Each entry point below replaces one
+ * of those internal seams with a batch call over plain host pointers; the citation beside it is the
+ * reference code a maintainer would swap for the call (INTEGRATION.md shows the patch).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; pcramp_gpu_last_error(ctx) gives the
+ *    message (the reference throws const char* / std::string, main.cpp:1269-1292 -- the C++ wrapper
+ *    in INTEGRATION.md rethrows it).
+ *  - words are two uint64 {buffer[0], buffer[1]} of the reference's __word<unsigned long,2>
+ *    (word.h:12-17): nibble i sits in limb i/16 at bit (15 - i%16)*4; A=1 C=2 G=4 T=8, 0 = EOS.
+ *  - sequences are the reference's packed nibbles: two bases per byte, even index in the high
+ *    nibble (sequence.h:223-228).
+ *  - strand values: 1 = plus, 2 = minus (sequence.h:27-32).
+ *  - bitsets are uint32 words, bit (i & 31) of word (i >> 5) = sequence i (LSB first).  The
+ *    reference's MPI wire format is MSB-first bytes (mpi_util.cpp:152-233); convert at that edge only.
+ *  - a ctx is bound to ONE GPU and is not thread-safe.  Multi-GPU = one process (rank) per GPU, each
+ *    with its own ctx over its shard of the sequences.
+ *  - there is no CPU fallback: without a CUDA device pcramp_gpu_create fails.
+ */
+#ifndef PCRAMP_GPU_H
+#define PCRAMP_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcramp_gpu_ctx pcramp_gpu_ctx;
+
+/* Which sequence collection a call addresses (main.cpp:244-434 keeps three deques). */
+enum { PCRAMP_TARGET = 0, PCRAMP_BACKGROUND = 1, PCRAMP_MULTIPLEX = 2, PCRAMP_NUM_KINDS = 3 };
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int pcramp_gpu_create(pcramp_gpu_ctx **ctx, int device);
+void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx);
+const char *pcramp_gpu_last_error(const pcramp_gpu_ctx *ctx);
+/* cudaStream_t every kernel of this ctx is launched on (for CUDA-event timing by the caller). */
+void *pcramp_gpu_stream(pcramp_gpu_ctx *ctx);
+int pcramp_gpu_synchronize(pcramp_gpu_ctx *ctx);
+
+/* ---- sequences: replaces the resident std::deque<Sequence> (main.cpp:244-434) ------------------- */
+/* nibbles: concatenated packed sequences; byte_off[i] = first byte of sequence i; len[i] in bases.
+ * weight may be NULL (1.0f each, sequence.h:22).  All sequences start active (sequence.h:143). */
+int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const uint8_t *nibbles,
+	const uint64_t *byte_off, const uint32_t *len, const float *weight);
+/* Sequence::active(bool) for the whole collection (main.cpp:493-495,1116-1121). */
+int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active);
+/* Sequence::split_sequence (sequence.h:231-243; called at main.cpp:1010-1016). */
+int pcramp_gpu_split_sequence(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pos);
+
+/* Sequence::pack (sequence.cpp:92-267) of ONE sequence: every (word, loc, strand) it would insert, in no
+ * particular order.  The scan below never materialises this list; the call exists so that the device-side
+ * model of pack() can be checked entry by entry.  Call with cap = 0 to size, then again with buffers. */
+int pcramp_gpu_pack(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pack_max_degen, float pack_min_gc,
+	float pack_max_gc, uint32_t min_oligo_length, uint64_t cap, uint64_t *words, int32_t *loc, uint32_t *strand,
+	uint64_t *n_out);
+
+/* ---- seed scan: replaces the per-sequence Sequence::pack + select_words loops, the final sort()
+ *      and keys() (main.cpp:579-631 and :644-691; sequence.cpp:92-267; select_words.cpp:8-139;
+ *      pcramp.h:231-256).  f/r: n_pairs x 2 uint64 trial oligos (PCR::oligo(FORWARD/REVERSE)).
+ *      threshold = opt.{target,background}_threshold * opt.*_search_multiplier (main.cpp:601,669).
+ *      The resulting word database stays on the GPU for pcramp_gpu_score_pairs. ------------------- */
+int pcramp_gpu_select_words(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r,
+	uint32_t n_pairs, int optimize_5, int optimize_3, float threshold, uint32_t pack_max_degen,
+	float pack_min_gc, float pack_max_gc, uint32_t min_oligo_length, uint64_t *n_entries, uint64_t *n_keys);
+/* Copy the database out, ordered by (word, index, loc, strand) -- the order read_only_multimap::sort()
+ * (read_only_multimap.h:93-101) leaves, with its unspecified ties made canonical.  key_index[i] is the
+ * position of entry i's word in keys() order.  Any output pointer may be NULL. */
+int pcramp_gpu_db_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *words, uint32_t *index, int32_t *loc,
+	uint32_t *strand, uint32_t *key_index);
+int pcramp_gpu_keys_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *keys);
+
+/* ---- pair scoring: replaces PCR::collect_candidates + update_identity + compute_coverage
+ *      (pcr_assay.cpp:12-69,271-302,338-441; optimize.cpp:209-301) and PCR::find_target_match
+ *      (pcr_assay.cpp:544-578) for a batch of pairs against the database built above.
+ *        optimize()'s first score (optimize.cpp:62-75): search = threshold*multiplier, detect = threshold
+ *        find_target_match:                              search = detect = opt.target_threshold
+ *      coverage[t] (float, may be NULL) = sum of weights of detected sequences, accumulated in double
+ *      in the reference's amplicon order; bitsets (may be NULL) = n_pairs x ceil(n_seq/32) words. --- */
+int pcramp_gpu_score_pairs(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r,
+	uint32_t n_pairs, float search_threshold, float detect_threshold, int amplicon_min, int amplicon_max,
+	int use_taq_mama, float *coverage, uint32_t *bitsets);
+
+/* ---- resident variants: the same two steps with the pairs already staged in HBM and the results
+ *      left in HBM (what a multi-batch driver, the NCCL exchange and bench.py's `value` use). -------- */
+int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs);
+int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int optimize_5, int optimize_3, float threshold,
+	uint32_t pack_max_degen, float pack_min_gc, float pack_max_gc, uint32_t min_oligo_length,
+	uint64_t *n_entries, uint64_t *n_keys);
+int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_threshold, float detect_threshold,
+	int amplicon_min, int amplicon_max, int use_taq_mama);
+/* device pointers of the last staged results: coverage float[n_pairs], bitsets uint32[n_pairs*words] */
+void *pcramp_gpu_device_coverage(pcramp_gpu_ctx *ctx);
+void *pcramp_gpu_device_bitsets(pcramp_gpu_ctx *ctx);
+uint32_t pcramp_gpu_bitset_words(pcramp_gpu_ctx *ctx, int kind);
+int pcramp_gpu_fetch_results(pcramp_gpu_ctx *ctx, float *coverage, uint32_t *bitsets);
+
+/* ---- instrumentation ----------------------------------------------------------------------------- */
+/* Counters of the last select_words / score_pairs call on this ctx. */
+typedef struct pcramp_gpu_stats {
+	uint64_t n_patterns;      /* candidate words x 2 strands scanned */
+	uint64_t n_positions;     /* template positions streamed (active sequences) */
+	uint64_t n_hits;          /* (candidate, window) hits at or above threshold */
+	uint64_t n_entries;       /* database entries */
+	uint64_t n_keys;          /* unique words */
+	uint64_t kernel_launches; /* kernels of this library launched by the call */
+	float ms_scan;            /* CUDA-event time of the full-window scan kernel */
+	float ms_edge;            /* ... of the partial-window kernel */
+	float ms_db;              /* ... of hit filtering, sorting, materialisation */
+	float ms_score;           /* ... of the pair-scoring kernels */
+} pcramp_gpu_stats;
+int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
+
+/* ---- host-side word helpers (word.h / word.cpp), for building candidate lists ------------------- */
+void pcramp_word_from_string(const char *iupac, int centre, uint64_t out[2]);
+int pcramp_word_to_string(const uint64_t w[2], char out[33]);
+uint32_t pcramp_word_and(const uint64_t a[2], const uint64_t b[2]);
+uint32_t pcramp_word_size(const uint64_t a[2]);
+int pcramp_word_start(const uint64_t a[2]);
+int pcramp_word_stop(const uint64_t a[2]);
+void pcramp_word_complement(const uint64_t a[2], uint64_t out[2]);
+void pcramp_word_center(const uint64_t a[2], uint64_t out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCRAMP_GPU_H */

@@ -1,0 +1,259 @@
+"""ctypes mirror of include/pcramp_gpu.h.
+
+One method per C entry point, same names and argument meaning.  numpy arrays in, numpy arrays out;
+words are (n, 2) uint64 arrays of {buffer[0], buffer[1]}.  There is no CPU fallback: if the CUDA
+library is missing or no GPU is present this module raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+TARGET, BACKGROUND, MULTIPLEX = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpcramp_gpu.so")
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+class GpuError(RuntimeError):
+    pass
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("n_patterns", ctypes.c_uint64),
+        ("n_positions", ctypes.c_uint64),
+        ("n_hits", ctypes.c_uint64),
+        ("n_entries", ctypes.c_uint64),
+        ("n_keys", ctypes.c_uint64),
+        ("kernel_launches", ctypes.c_uint64),
+        ("ms_scan", ctypes.c_float),
+        ("ms_edge", ctypes.c_float),
+        ("ms_db", ctypes.c_float),
+        ("ms_score", ctypes.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+# name -> (restype, argtypes); also the list of symbols tests check against include/pcramp_gpu.h
+SIGNATURES = {
+    "pcramp_gpu_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "pcramp_gpu_destroy": (None, [ctypes.c_void_p]),
+    "pcramp_gpu_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "pcramp_gpu_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "pcramp_gpu_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "pcramp_gpu_upload_sequences": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, _u8p, _u64p, _u32p, _f32p]),
+    "pcramp_gpu_set_active": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u8p]),
+    "pcramp_gpu_split_sequence": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]),
+    "pcramp_gpu_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
+                                       ctypes.c_uint32, ctypes.c_uint64, _u64p, _i32p, _u32p, _u64p]),
+    "pcramp_gpu_select_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_float, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_uint32, _u64p, _u64p]),
+    "pcramp_gpu_db_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u32p, _i32p, _u32p, _u32p]),
+    "pcramp_gpu_keys_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p]),
+    "pcramp_gpu_score_pairs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _u32p]),
+    "pcramp_gpu_stage_pairs": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32]),
+    "pcramp_gpu_select_words_staged": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_uint32,
+                                                      ctypes.c_float, ctypes.c_float, ctypes.c_uint32, _u64p, _u64p]),
+    "pcramp_gpu_score_pairs_staged": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_int]),
+    "pcramp_gpu_device_coverage": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "pcramp_gpu_device_bitsets": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "pcramp_gpu_bitset_words": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_int]),
+    "pcramp_gpu_fetch_results": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
+    "pcramp_gpu_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
+    "pcramp_word_from_string": (None, [ctypes.c_char_p, ctypes.c_int, _u64p]),
+    "pcramp_word_to_string": (ctypes.c_int, [_u64p, ctypes.c_char_p]),
+    "pcramp_word_and": (ctypes.c_uint32, [_u64p, _u64p]),
+    "pcramp_word_size": (ctypes.c_uint32, [_u64p]),
+    "pcramp_word_start": (ctypes.c_int, [_u64p]),
+    "pcramp_word_stop": (ctypes.c_int, [_u64p]),
+    "pcramp_word_complement": (None, [_u64p, _u64p]),
+    "pcramp_word_center": (None, [_u64p, _u64p]),
+}
+
+
+def load_library():
+    """dlopen the CUDA library; fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GpuError("%s is missing: run `python -m pcramp_b200.build` (there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def _words(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim != 2 or a.shape[1] != 2:
+        raise ValueError("words must have shape (n, 2)")
+    return a
+
+
+class PcrampGpu:
+    """One context = one GPU (include/pcramp_gpu.h)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.pcramp_gpu_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            raise GpuError("pcramp_gpu_create failed (rc=%d): no usable CUDA device %d; there is no CPU fallback" % (rc, device))
+        self.h = h
+        self.n_seq = {}
+        self.n_pairs = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pcramp_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GpuError(self.lib.pcramp_gpu_last_error(self.h).decode())
+
+    @property
+    def stream(self):
+        return self.lib.pcramp_gpu_stream(self.h)
+
+    def synchronize(self):
+        self._ck(self.lib.pcramp_gpu_synchronize(self.h))
+
+    # ---- sequences ----------------------------------------------------------------------------
+    def upload_sequences(self, kind, nibbles, byte_off, length, weight=None):
+        nibbles = np.ascontiguousarray(nibbles, dtype=np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        if weight is not None:
+            weight = np.ascontiguousarray(weight, dtype=np.float32)
+        n = len(length)
+        self._ck(self.lib.pcramp_gpu_upload_sequences(self.h, kind, n, _ptr(nibbles, _u8p), _ptr(byte_off, _u64p), _ptr(length, _u32p),
+                                                      _ptr(weight, _f32p)))
+        self.n_seq[kind] = n
+
+    def set_active(self, kind, active):
+        active = np.ascontiguousarray(active, dtype=np.uint8)
+        self._ck(self.lib.pcramp_gpu_set_active(self.h, kind, _ptr(active, _u8p)))
+
+    def split_sequence(self, kind, seq, pos):
+        self._ck(self.lib.pcramp_gpu_split_sequence(self.h, kind, int(seq), int(pos)))
+
+    def pack(self, kind, seq, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0, min_oligo_length=18):
+        """Sequence::pack of one sequence -> (words, loc, strand), unordered."""
+        n = ctypes.c_uint64()
+        args = (self.h, kind, int(seq), int(pack_max_degen), float(pack_min_gc), float(pack_max_gc), int(min_oligo_length))
+        self._ck(self.lib.pcramp_gpu_pack(*args, 0, None, None, None, ctypes.byref(n)))
+        words = np.zeros((n.value, 2), np.uint64)
+        loc = np.zeros(n.value, np.int32)
+        strand = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self.lib.pcramp_gpu_pack(*args, n.value, _ptr(words, _u64p), _ptr(loc, _i32p), _ptr(strand, _u32p), ctypes.byref(n)))
+        return words, loc, strand
+
+    # ---- seed scan ----------------------------------------------------------------------------
+    def select_words(self, kind, f, r, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0,
+                     pack_max_gc=1.0, min_oligo_length=18):
+        f, r = _words(f), _words(r)
+        ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
+        self._ck(self.lib.pcramp_gpu_select_words(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), len(f), int(optimize_5), int(optimize_3),
+                                                  float(threshold), int(pack_max_degen), float(pack_min_gc), float(pack_max_gc),
+                                                  int(min_oligo_length), ctypes.byref(ne), ctypes.byref(nk)))
+        self.n_pairs = len(f)
+        self._db = (ne.value, nk.value)
+        return ne.value, nk.value
+
+    def db_copy(self, kind):
+        ne, nk = self._db
+        words = np.zeros((ne, 2), np.uint64)
+        index = np.zeros(ne, np.uint32)
+        loc = np.zeros(ne, np.int32)
+        strand = np.zeros(ne, np.uint32)
+        key = np.zeros(ne, np.uint32)
+        self._ck(self.lib.pcramp_gpu_db_copy(self.h, kind, _ptr(words, _u64p), _ptr(index, _u32p), _ptr(loc, _i32p), _ptr(strand, _u32p),
+                                             _ptr(key, _u32p)))
+        return words, index, loc, strand, key
+
+    def keys_copy(self, kind):
+        ne, nk = self._db
+        keys = np.zeros((nk, 2), np.uint64)
+        self._ck(self.lib.pcramp_gpu_keys_copy(self.h, kind, _ptr(keys, _u64p)))
+        return keys
+
+    # ---- pair scoring -------------------------------------------------------------------------
+    def score_pairs(self, kind, f, r, search_threshold, detect_threshold, amplicon_min=80, amplicon_max=200, use_taq_mama=False):
+        f, r = _words(f), _words(r)
+        n = len(f)
+        nw = (self.n_seq[kind] + 31) // 32
+        cov = np.zeros(n, np.float32)
+        bits = np.zeros((n, nw), np.uint32)
+        self._ck(self.lib.pcramp_gpu_score_pairs(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), n, float(search_threshold),
+                                                 float(detect_threshold), int(amplicon_min), int(amplicon_max), int(use_taq_mama),
+                                                 _ptr(cov, _f32p), _ptr(bits, _u32p)))
+        return cov, bits
+
+    # ---- resident variants --------------------------------------------------------------------
+    def stage_pairs(self, f, r):
+        f, r = _words(f), _words(r)
+        self._ck(self.lib.pcramp_gpu_stage_pairs(self.h, _ptr(f, _u64p), _ptr(r, _u64p), len(f)))
+        self.n_pairs = len(f)
+
+    def select_words_staged(self, kind, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0,
+                            min_oligo_length=18):
+        ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
+        self._ck(self.lib.pcramp_gpu_select_words_staged(self.h, kind, int(optimize_5), int(optimize_3), float(threshold), int(pack_max_degen),
+                                                         float(pack_min_gc), float(pack_max_gc), int(min_oligo_length), ctypes.byref(ne),
+                                                         ctypes.byref(nk)))
+        self._db = (ne.value, nk.value)
+        return ne.value, nk.value
+
+    def score_pairs_staged(self, kind, search_threshold, detect_threshold, amplicon_min=80, amplicon_max=200, use_taq_mama=False):
+        self._ck(self.lib.pcramp_gpu_score_pairs_staged(self.h, kind, float(search_threshold), float(detect_threshold), int(amplicon_min),
+                                                        int(amplicon_max), int(use_taq_mama)))
+
+    def fetch_results(self, kind):
+        nw = (self.n_seq[kind] + 31) // 32
+        cov = np.zeros(self.n_pairs, np.float32)
+        bits = np.zeros((self.n_pairs, nw), np.uint32)
+        self._ck(self.lib.pcramp_gpu_fetch_results(self.h, _ptr(cov, _f32p), _ptr(bits, _u32p)))
+        return cov, bits
+
+    def device_pointers(self):
+        return self.lib.pcramp_gpu_device_coverage(self.h), self.lib.pcramp_gpu_device_bitsets(self.h)
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.pcramp_gpu_get_stats(self.h, ctypes.byref(s)))
+        return s.as_dict()
+
+
+def unpack_bits(bits, n_seq):
+    """(n_pairs, words) uint32, LSB-first -> (n_pairs, n_seq) uint8."""
+    b = np.unpackbits(np.ascontiguousarray(bits).view(np.uint8), axis=1, bitorder="little")
+    return b[:, :n_seq]

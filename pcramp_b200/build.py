@@ -1,0 +1,54 @@
+"""Build the CUDA C-ABI library (pcramp_b200/csrc/libpcramp_gpu.so).
+
+Everything is built in-tree with explicit nvcc / make invocations so that the resulting .so files
+travel with a snapshot of the repository (they are git-ignored, not gpurun-ignored).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "pcramp_b200", "csrc")
+LIB = os.path.join(CSRC, "libpcramp_gpu.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    # identity / coverage arithmetic must round like the reference's scalar x86 code: no FMA contraction,
+    # IEEE division and square root (the defaults, stated here so nobody adds --use_fast_math)
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_cuda(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(ROOT, "include", "pcramp_gpu.h"))
+    if not force and not _stale(LIB, srcs):
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "pcramp_gpu.cu")]
+    env = dict(os.environ)
+    env.pop("CXX", None)  # the image's CXX wrapper is not a usable host compiler for nvcc
+    env.pop("CC", None)
+    subprocess.run(cmd, check=True, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built", LIB)

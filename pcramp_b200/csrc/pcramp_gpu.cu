@@ -1,0 +1,1003 @@
+// pcramp_gpu.cu -- context, HBM residency and the C ABI of include/pcramp_gpu.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false (see build.py).
+// -fmad=false because identity/coverage arithmetic must round exactly like the reference's scalar
+// x86 code (SURVEY.md section 7 "Float bit-exactness"); the hot scan kernel is integer-only.
+#include "../../include/pcramp_gpu.h"
+
+#include "score.cuh"
+
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pcr;
+
+namespace {
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	~DevBuf() { release(); }
+	void release()
+	{
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	cudaError_t ensure(size_t bytes)
+	{
+		if (bytes <= cap) return cudaSuccess;
+		release();
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) { p = nullptr; return e; }
+		cap = want;
+		return cudaSuccess;
+	}
+	template <class T> T *as() const { return (T *)p; }
+};
+
+struct SeqSet {
+	uint32_t n = 0;
+	bool any_degenerate = false;
+	uint64_t total_positions = 0; // sum of clen over all sequences
+	std::vector<uint32_t> len, plen, clen;
+	std::vector<float> weight;
+	std::vector<uint8_t> active;
+	std::vector<uint64_t> raw_off, grp_off;
+	std::vector<std::vector<uint32_t>> eos; // per sequence, sorted raw positions
+	uint64_t raw_bytes = 0, n_groups = 0, n_tiles = 0;
+	DevBuf d_raw, d_raw_off, d_len, d_plen, d_clen, d_planes, d_grp_off, d_eos_pos, d_eos_off, d_weight, d_active, d_tile_seq, d_tile_x0;
+	// database (seq-grouped order = entry-id order) + canonical permutation
+	uint64_t n_entries = 0, n_keys = 0;
+	bool db_valid = false;
+	DevBuf e_hi, e_lo, e_seq, e_loc, e_strand, e_perm, e_keyrank, seq_ent_off;
+
+	SeqDev dev() const
+	{
+		SeqDev sd;
+		sd.n = n;
+		sd.planes = d_planes.as<uint4>();
+		sd.grp_off = d_grp_off.as<uint64_t>();
+		sd.clen = d_clen.as<uint32_t>();
+		sd.len = d_len.as<uint32_t>();
+		sd.plen = d_plen.as<uint32_t>();
+		sd.raw = d_raw.as<uint8_t>();
+		sd.raw_off = d_raw_off.as<uint64_t>();
+		sd.eos_pos = d_eos_pos.as<uint32_t>();
+		sd.eos_off = d_eos_off.as<uint32_t>();
+		sd.weight = d_weight.as<float>();
+		sd.active = d_active.as<uint8_t>();
+		return sd;
+	}
+};
+
+} // namespace
+
+struct pcramp_gpu_ctx {
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[8] = {};
+	std::string err;
+	SeqSet sets[PCRAMP_NUM_KINDS];
+	// staged pairs + results
+	uint32_t n_pairs = 0, res_words = 0;
+	DevBuf d_f, d_r, d_oligos, d_cov, d_bits, d_bits1;
+	// candidates / patterns
+	DevBuf d_cand_cnt, d_cand_off, d_cand_words, d_cand_thr, d_pat_mask, d_pat_meta;
+	// scratch
+	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
+	unsigned long long *h_counters = nullptr; // pinned
+	pcramp_gpu_stats stats = {};
+};
+
+namespace {
+
+#define CK(call)                                                                                      \
+	do {                                                                                              \
+		cudaError_t e__ = (call);                                                                     \
+		if (e__ != cudaSuccess) {                                                                     \
+			char b__[512];                                                                            \
+			snprintf(b__, sizeof(b__), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+			ctx->err = b__;                                                                           \
+			return 1;                                                                                 \
+		}                                                                                             \
+	} while (0)
+
+inline int fail(pcramp_gpu_ctx *ctx, const std::string &m)
+{
+	ctx->err = m;
+	return 1;
+}
+
+inline uint32_t bits_for(uint64_t n)
+{
+	uint32_t b = 1;
+	while ((1ull << b) < n) ++b;
+	return b;
+}
+
+inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+// ---------------------------------------------------------------------------------------------
+// K0: nibbles -> bit-planes
+// ---------------------------------------------------------------------------------------------
+// sequences without EOS: one thread per 32-base group, 16 raw bytes -> one uint4 of planes
+__global__ void planes_direct_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ raw_off, const uint64_t *__restrict__ grp_off,
+	const uint32_t *__restrict__ len, const uint32_t *__restrict__ clen, uint32_t n_seq, uint64_t n_groups, uint4 *planes)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n_groups) return;
+	uint32_t lo = 0, hi = n_seq; // sequence owning group g: last s with grp_off[s] <= g
+	while (hi - lo > 1u) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (grp_off[mid] <= g) lo = mid; else hi = mid;
+	}
+	const uint32_t seq = lo;
+	if (len[seq] != clen[seq]) return; // has EOS: planes_compact_kernel writes it
+	const uint32_t L = len[seq];
+	const uint64_t first = (g - grp_off[seq]) * 32ull;
+	uint4 out = make_uint4(0, 0, 0, 0);
+	const uint8_t *src = raw + raw_off[seq];
+	for (uint32_t b = 0; b < 32u; b += 2u) {
+		const uint64_t pos = first + b;
+		if (pos >= L) break;
+		const uint32_t v = src[pos >> 1];
+		const uint32_t n0 = v >> 4, n1 = (pos + 1 < L) ? (v & 15u) : 0u;
+		out.x |= ((n0 & 1u) << b) | ((n1 & 1u) << (b + 1));
+		out.y |= (((n0 >> 1) & 1u) << b) | (((n1 >> 1) & 1u) << (b + 1));
+		out.z |= (((n0 >> 2) & 1u) << b) | (((n1 >> 2) & 1u) << (b + 1));
+		out.w |= (((n0 >> 3) & 1u) << b) | (((n1 >> 3) & 1u) << (b + 1));
+	}
+	planes[g] = out;
+}
+
+// sequences with EOS: one warp per listed sequence compacts the non-EOS bases in order
+__global__ void planes_compact_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ raw_off, const uint64_t *__restrict__ grp_off,
+	const uint32_t *__restrict__ len, const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *planes_u32)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (warp >= n_list) return;
+	const uint32_t seq = list[warp];
+	const uint32_t L = len[seq];
+	const uint64_t g0 = grp_off[seq], g1 = grp_off[seq + 1];
+	for (uint64_t w = g0 * 4ull + lane; w < g1 * 4ull; w += 32ull) planes_u32[w] = 0u;
+	__syncwarp();
+	const uint8_t *src = raw + raw_off[seq];
+	uint32_t base = 0;
+	for (uint32_t i0 = 0; i0 < L; i0 += 32u) {
+		const uint32_t i = i0 + lane;
+		uint32_t nib = 0;
+		if (i < L) {
+			const uint32_t v = src[i >> 1];
+			nib = (i & 1u) ? (v & 15u) : (v >> 4);
+		}
+		const uint32_t m = __ballot_sync(0xffffffffu, nib != 0u);
+		if (nib != 0u) {
+			const uint32_t j = base + __popc(m & ((1u << lane) - 1u));
+			uint32_t *grp = planes_u32 + (g0 + (j >> 5)) * 4ull;
+			const uint32_t bit = 1u << (j & 31u);
+			if (nib & 1u) atomicOr(grp + 0, bit);
+			if (nib & 2u) atomicOr(grp + 1, bit);
+			if (nib & 4u) atomicOr(grp + 2, bit);
+			if (nib & 8u) atomicOr(grp + 3, bit);
+		}
+		base += __popc(m);
+	}
+}
+
+__global__ void set_raw_nibble_kernel(uint8_t *raw, uint64_t byte, uint32_t low, uint32_t value)
+{
+	uint8_t v = raw[byte];
+	v = low ? (uint8_t)((v & 0xF0u) | value) : (uint8_t)((v & 0x0Fu) | (value << 4));
+	raw[byte] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidates and patterns, built on the device from the staged pairs (select_words.cpp:25-84)
+// ---------------------------------------------------------------------------------------------
+__global__ void cand_count_kernel(const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs, int opt5, int opt3,
+	uint32_t *cnt)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 2u * n_pairs) return;
+	const uint64_t *src = (i & 1u) ? r : f;
+	W128 w;
+	w.hi = src[2 * (i >> 1)];
+	w.lo = src[2 * (i >> 1) + 1];
+	const int start = w_start(w), stop = w_stop(w);
+	uint32_t c = 1;
+	if (opt5 && start > 0 && start < 32) c += (uint32_t)start;       // :50-58
+	if (opt3 && stop >= 0 && stop < 31) c += (uint32_t)(31 - stop);   // :61-70
+	cnt[i] = c;
+}
+
+__device__ inline void emit_candidate(const W128 &w, uint32_t cand, float threshold, uint64_t *cand_words, uint32_t *cand_thr,
+	uint4 *pat_mask, uint32_t *pat_meta)
+{
+	const int start = w_start(w), stop = w_stop(w);
+	const uint32_t thr = (uint32_t)__fmul_rn((float)w_size(w), threshold); // select_words.cpp:83
+	cand_words[2 * cand] = w.hi;
+	cand_words[2 * cand + 1] = w.lo;
+	cand_thr[cand] = thr;
+	uint4 mp = make_uint4(0, 0, 0, 0), mm = make_uint4(0, 0, 0, 0);
+	for (int k = 0; start + k <= stop; ++k) {
+		const uint32_t a = w_get(w, start + k); // plus strand: primer[k]
+		mp.x |= (a & 1u) << k;
+		mp.y |= ((a >> 1) & 1u) << k;
+		mp.z |= ((a >> 2) & 1u) << k;
+		mp.w |= ((a >> 3) & 1u) << k;
+		const uint32_t b = w_get(w, stop - k);  // minus strand: complement of primer read backwards
+		mm.x |= ((b >> 3) & 1u) << k;           // T -> A
+		mm.y |= ((b >> 2) & 1u) << k;           // G -> C
+		mm.z |= ((b >> 1) & 1u) << k;           // C -> G
+		mm.w |= (b & 1u) << k;                  // A -> T
+	}
+	pat_mask[2 * cand] = mp;
+	pat_meta[2 * cand] = pat_meta_pack(thr, (uint32_t)start, 0u, cand);
+	pat_mask[2 * cand + 1] = mm;
+	pat_meta[2 * cand + 1] = pat_meta_pack(thr, (uint32_t)(31 - stop), 1u, cand);
+}
+
+__global__ void cand_build_kernel(const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs, int opt5, int opt3,
+	float threshold, const uint32_t *__restrict__ off, uint64_t *cand_words, uint32_t *cand_thr, uint4 *pat_mask, uint32_t *pat_meta)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 2u * n_pairs) return;
+	const uint64_t *src = (i & 1u) ? r : f;
+	W128 w;
+	w.hi = src[2 * (i >> 1)];
+	w.lo = src[2 * (i >> 1) + 1];
+	uint32_t c = off[i];
+	emit_candidate(w, c++, threshold, cand_words, cand_thr, pat_mask, pat_meta);
+	const int start = w_start(w), stop = w_stop(w);
+	if (opt5 && start > 0 && start < 32)
+		for (int j = 1; j <= start; ++j) emit_candidate(w_shl(w, j), c++, threshold, cand_words, cand_thr, pat_mask, pat_meta);
+	if (opt3 && stop >= 0 && stop < 31)
+		for (int j = 1; j <= 31 - stop; ++j) emit_candidate(w_shr(w, j), c++, threshold, cand_words, cand_thr, pat_mask, pat_meta);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+int rebuild_tiles(pcramp_gpu_ctx *ctx, SeqSet &s)
+{
+	std::vector<uint32_t> tseq, tx0;
+	s.total_positions = 0;
+	for (uint32_t i = 0; i < s.n; ++i) {
+		s.total_positions += s.clen[i];
+		for (uint64_t x = 0; x < s.clen[i]; x += SCAN_TILE) {
+			tseq.push_back(i);
+			tx0.push_back((uint32_t)x);
+		}
+	}
+	s.n_tiles = tseq.size();
+	CK(s.d_tile_seq.ensure(std::max<size_t>(1, tseq.size()) * 4));
+	CK(s.d_tile_x0.ensure(std::max<size_t>(1, tx0.size()) * 4));
+	if (!tseq.empty()) {
+		CK(cudaMemcpyAsync(s.d_tile_seq.p, tseq.data(), tseq.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(s.d_tile_x0.p, tx0.data(), tx0.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int upload_eos(pcramp_gpu_ctx *ctx, SeqSet &s)
+{
+	std::vector<uint32_t> off(s.n + 1, 0), pos;
+	for (uint32_t i = 0; i < s.n; ++i) {
+		off[i] = (uint32_t)pos.size();
+		pos.insert(pos.end(), s.eos[i].begin(), s.eos[i].end());
+	}
+	off[s.n] = (uint32_t)pos.size();
+	CK(s.d_eos_off.ensure(off.size() * 4));
+	CK(s.d_eos_pos.ensure(std::max<size_t>(1, pos.size()) * 4));
+	CK(cudaMemcpyAsync(s.d_eos_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (!pos.empty()) CK(cudaMemcpyAsync(s.d_eos_pos.p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int compact_sequences(pcramp_gpu_ctx *ctx, SeqSet &s, const std::vector<uint32_t> &list)
+{
+	if (list.empty()) return 0;
+	DevBuf d_list;
+	CK(d_list.ensure(list.size() * 4));
+	CK(cudaMemcpyAsync(d_list.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	planes_compact_kernel<<<grid_for(list.size() * 32ull, 256), 256, 0, ctx->stream>>>(s.d_raw.as<uint8_t>(), s.d_raw_off.as<uint64_t>(),
+		s.d_grp_off.as<uint64_t>(), s.d_len.as<uint32_t>(), d_list.as<uint32_t>(), (uint32_t)list.size(), s.d_planes.as<uint32_t>());
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+inline float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+	float ms = 0.0f;
+	cudaEventElapsedTime(&ms, a, b);
+	return ms;
+}
+
+int check_kind(pcramp_gpu_ctx *ctx, int kind)
+{
+	if (!ctx) return 1;
+	if (kind < 0 || kind >= PCRAMP_NUM_KINDS) return fail(ctx, "pcramp_gpu: bad sequence kind");
+	return 0;
+}
+
+} // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int pcramp_gpu_create(pcramp_gpu_ctx **out, int device)
+{
+	if (!out) return 1;
+	*out = nullptr;
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return 2; // no CPU fallback
+	if (device < 0 || device >= n_dev) return 3;
+	pcramp_gpu_ctx *ctx = new pcramp_gpu_ctx();
+	ctx->device = device;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		delete ctx;
+		return 4;
+	}
+	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+	for (auto &e : ctx->ev) cudaEventCreate(&e);
+	cudaMallocHost((void **)&ctx->h_counters, 8 * sizeof(unsigned long long));
+	*out = ctx;
+	return 0;
+}
+
+void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (auto &e : ctx->ev) cudaEventDestroy(e);
+	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+	cudaStream_t s = ctx->stream;
+	delete ctx;
+	cudaStreamDestroy(s);
+}
+
+const char *pcramp_gpu_last_error(const pcramp_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "pcramp_gpu: null context"; }
+void *pcramp_gpu_stream(pcramp_gpu_ctx *ctx) { return (void *)ctx->stream; }
+
+int pcramp_gpu_synchronize(pcramp_gpu_ctx *ctx)
+{
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const uint8_t *nibbles, const uint64_t *byte_off,
+	const uint32_t *len, const float *weight)
+{
+	if (check_kind(ctx, kind)) return 1;
+	if (n >= (1u << 24)) return fail(ctx, "pcramp_gpu_upload_sequences: at most 2^24 - 1 sequences per collection");
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	s.n = n;
+	s.db_valid = false;
+	s.n_entries = s.n_keys = 0;
+	s.len.assign(len, len + n);
+	s.plen.assign(n, 0);
+	s.clen.assign(n, 0);
+	s.weight.assign(n, 1.0f);
+	if (weight) s.weight.assign(weight, weight + n);
+	s.active.assign(n, 1);
+	s.raw_off.assign(byte_off, byte_off + n);
+	s.eos.assign(n, std::vector<uint32_t>());
+	s.grp_off.assign(n + 1, 0);
+	s.any_degenerate = false;
+	s.raw_bytes = 0;
+	std::vector<uint32_t> with_eos;
+	for (uint32_t i = 0; i < n; ++i) {
+		const uint64_t bytes = ((uint64_t)len[i] + 1) / 2;
+		s.raw_bytes = std::max(s.raw_bytes, byte_off[i] + bytes);
+		const uint8_t *src = nibbles + byte_off[i];
+		// host pass: EOS positions and "any degenerate base" (SWAR over 8 bytes = 16 nibbles)
+		uint64_t p = 0;
+		for (; p + 8 <= len[i] / 2; p += 8) {
+			uint64_t v;
+			memcpy(&v, src + p, 8);
+			const uint64_t b0 = v & 0x1111111111111111ull, b1 = (v >> 1) & 0x1111111111111111ull, b2 = (v >> 2) & 0x1111111111111111ull,
+			               b3 = (v >> 3) & 0x1111111111111111ull;
+			if ((b0 & b1) | (b0 & b2) | (b0 & b3) | (b1 & b2) | (b1 & b3) | (b2 & b3)) s.any_degenerate = true;
+			if ((b0 | b1 | b2 | b3) != 0x1111111111111111ull) {
+				for (uint32_t q = 0; q < 16; ++q) {
+					const uint32_t pos = (uint32_t)(2 * p + q);
+					const uint32_t nib = (q & 1u) ? (src[pos >> 1] & 15u) : (src[pos >> 1] >> 4);
+					if (nib == 0u) s.eos[i].push_back(pos);
+				}
+			}
+		}
+		for (uint64_t pos = 2 * p; pos < len[i]; ++pos) {
+			const uint32_t nib = (pos & 1u) ? (src[pos >> 1] & 15u) : (src[pos >> 1] >> 4);
+			if (nib == 0u) s.eos[i].push_back((uint32_t)pos);
+			else if (nib & (nib - 1u)) s.any_degenerate = true;
+		}
+		s.clen[i] = len[i] - (uint32_t)s.eos[i].size();
+		if (!s.eos[i].empty()) with_eos.push_back(i);
+		s.plen[i] = len[i] + (len[i] & 1u);
+		if (len[i] & 1u) s.eos[i].push_back(len[i]); // the pad nibble pack() also pushes (seqdev.cuh)
+		s.grp_off[i + 1] = s.grp_off[i] + ((uint64_t)s.clen[i] + 31) / 32 + 1;
+	}
+	s.n_groups = s.grp_off[n];
+	CK(s.d_raw.ensure(std::max<uint64_t>(16, s.raw_bytes)));
+	CK(s.d_raw_off.ensure(std::max<size_t>(1, n) * 8));
+	CK(s.d_len.ensure(std::max<size_t>(1, n) * 4));
+	CK(s.d_clen.ensure(std::max<size_t>(1, n) * 4));
+	CK(s.d_plen.ensure(std::max<size_t>(1, n) * 4));
+	CK(s.d_weight.ensure(std::max<size_t>(1, n) * 4));
+	CK(s.d_active.ensure(std::max<size_t>(1, n)));
+	CK(s.d_grp_off.ensure((size_t)(n + 1) * 8));
+	CK(s.d_planes.ensure(std::max<uint64_t>(1, s.n_groups) * 16));
+	if (s.raw_bytes) CK(cudaMemcpyAsync(s.d_raw.p, nibbles, s.raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (n) {
+		CK(cudaMemcpyAsync(s.d_raw_off.p, s.raw_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(s.d_len.p, s.len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(s.d_clen.p, s.clen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(s.d_plen.p, s.plen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(s.d_weight.p, s.weight.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(s.d_active.p, s.active.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	CK(cudaMemcpyAsync(s.d_grp_off.p, s.grp_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemsetAsync(s.d_planes.p, 0, std::max<uint64_t>(1, s.n_groups) * 16, ctx->stream));
+	if (s.n_groups) {
+		planes_direct_kernel<<<grid_for(s.n_groups, 256), 256, 0, ctx->stream>>>(s.d_raw.as<uint8_t>(), s.d_raw_off.as<uint64_t>(),
+			s.d_grp_off.as<uint64_t>(), s.d_len.as<uint32_t>(), s.d_clen.as<uint32_t>(), n, s.n_groups, s.d_planes.as<uint4>());
+		CK(cudaGetLastError());
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (upload_eos(ctx, s)) return 1;
+	if (compact_sequences(ctx, s, with_eos)) return 1;
+	return rebuild_tiles(ctx, s);
+}
+
+int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active)
+{
+	if (check_kind(ctx, kind)) return 1;
+	SeqSet &s = ctx->sets[kind];
+	for (uint32_t i = 0; i < s.n; ++i) s.active[i] = active[i] ? 1 : 0;
+	if (s.n) CK(cudaMemcpyAsync(s.d_active.p, s.active.data(), s.n, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int pcramp_gpu_split_sequence(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pos)
+{
+	if (check_kind(ctx, kind)) return 1;
+	SeqSet &s = ctx->sets[kind];
+	if (seq >= s.n || pos >= s.len[seq]) return fail(ctx, "pcramp_gpu_split_sequence: out of range");
+	std::vector<uint32_t> &e = s.eos[seq];
+	auto it = std::lower_bound(e.begin(), e.end(), pos);
+	if (it != e.end() && *it == pos) return 0; // already EOS
+	e.insert(it, pos);
+	s.clen[seq] -= 1;
+	s.db_valid = false;
+	set_raw_nibble_kernel<<<1, 1, 0, ctx->stream>>>(s.d_raw.as<uint8_t>(), s.raw_off[seq] + pos / 2, pos & 1u, 0u);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(s.d_clen.as<uint32_t>() + seq, &s.clen[seq], 4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (upload_eos(ctx, s)) return 1;
+	if (compact_sequences(ctx, s, std::vector<uint32_t>(1, seq))) return 1;
+	return rebuild_tiles(ctx, s);
+}
+
+int pcramp_gpu_pack(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pack_max_degen, float min_gc, float max_gc, uint32_t min_len,
+	uint64_t cap, uint64_t *words, int32_t *loc, uint32_t *strand, uint64_t *n_out)
+{
+	if (check_kind(ctx, kind)) return 1;
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	if (seq >= s.n) return fail(ctx, "pcramp_gpu_pack: sequence out of range");
+	if (min_len == 0) return fail(ctx, "pcramp_gpu_pack: min_oligo_length must be >= 1");
+	PackParams pp;
+	pp.max_degen = pack_max_degen;
+	pp.min_gc = min_gc;
+	pp.max_gc = max_gc;
+	pp.min_len = min_len;
+	pp.gc_filter = (min_gc > 0.0f) || (max_gc < 1.0f);
+	const uint64_t worst = 2ull * ((uint64_t)s.plen[seq] + 64ull + s.eos[seq].size());
+	DevBuf o_words, o_loc, o_strand;
+	CK(o_words.ensure(worst * 16));
+	CK(o_loc.ensure(worst * 4));
+	CK(o_strand.ensure(worst * 4));
+	CK(ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
+	CK(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+	pack_dump_kernel<<<grid_for(worst / 2 + 1, 256), 256, 0, ctx->stream>>>(s.dev(), seq, pp, o_words.as<uint64_t>(), o_loc.as<int32_t>(),
+		o_strand.as<uint32_t>(), ctx->d_counters.as<unsigned long long>());
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	const uint64_t n = ctx->h_counters[0];
+	if (n_out) *n_out = n;
+	if (n > cap || !words) return 0; // caller sizes with cap = 0 first
+	if (n) {
+		CK(cudaMemcpyAsync(words, o_words.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(loc, o_loc.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(strand, o_strand.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	return 0;
+}
+
+int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs)
+{
+	if (!ctx) return 1;
+	CK(cudaSetDevice(ctx->device));
+	ctx->n_pairs = n_pairs;
+	CK(ctx->d_f.ensure(std::max<size_t>(1, n_pairs) * 16));
+	CK(ctx->d_r.ensure(std::max<size_t>(1, n_pairs) * 16));
+	if (n_pairs) {
+		CK(cudaMemcpyAsync(ctx->d_f.p, f, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(ctx->d_r.p, r, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int opt3, float threshold, uint32_t pack_max_degen,
+	float min_gc, float max_gc, uint32_t min_len, uint64_t *n_entries_out, uint64_t *n_keys_out)
+{
+	if (check_kind(ctx, kind)) return 1;
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	cudaStream_t st = ctx->stream;
+	pcramp_gpu_stats &stat = ctx->stats;
+	stat = pcramp_gpu_stats();
+	s.db_valid = false;
+	s.n_entries = s.n_keys = 0;
+	if (n_entries_out) *n_entries_out = 0;
+	if (n_keys_out) *n_keys_out = 0;
+	const uint32_t n_pairs = ctx->n_pairs;
+	if (min_len == 0) return fail(ctx, "pcramp_gpu_select_words: min_oligo_length must be >= 1");
+	PackParams pp;
+	pp.max_degen = pack_max_degen;
+	pp.min_gc = min_gc;
+	pp.max_gc = max_gc;
+	pp.min_len = min_len;
+	pp.gc_filter = (min_gc > 0.0f) || (max_gc < 1.0f); // sequence.cpp:102
+	CK(s.seq_ent_off.ensure((size_t)(s.n + 1) * 4));
+	if (s.n == 0 || n_pairs == 0) { // select_words.cpp:13-15
+		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(s.n + 1) * 4, st));
+		CK(cudaStreamSynchronize(st));
+		s.db_valid = true;
+		return 0;
+	}
+	const SeqDev sd = s.dev();
+	unsigned long long *d_cnt = nullptr;
+	CK(ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
+	d_cnt = ctx->d_counters.as<unsigned long long>();
+
+	// ---- candidates and patterns --------------------------------------------------------------
+	const uint32_t n_oligo = 2u * n_pairs;
+	CK(ctx->d_cand_cnt.ensure((size_t)n_oligo * 4));
+	CK(ctx->d_cand_off.ensure((size_t)n_oligo * 4));
+	cand_count_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->d_f.as<uint64_t>(), ctx->d_r.as<uint64_t>(), n_pairs, opt5, opt3,
+		ctx->d_cand_cnt.as<uint32_t>());
+	CK(cudaGetLastError());
+	stat.kernel_launches++;
+	size_t tmp_bytes = 0;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->d_cand_cnt.as<uint32_t>(), ctx->d_cand_off.as<uint32_t>(), (int)n_oligo, st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->d_cand_cnt.as<uint32_t>(), ctx->d_cand_off.as<uint32_t>(), (int)n_oligo, st));
+	uint32_t last_off = 0, last_cnt = 0;
+	CK(cudaMemcpyAsync(&last_off, ctx->d_cand_off.as<uint32_t>() + (n_oligo - 1), 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&last_cnt, ctx->d_cand_cnt.as<uint32_t>() + (n_oligo - 1), 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const uint32_t n_cand = last_off + last_cnt;
+	if (n_cand > PAT_MAX_CAND) return fail(ctx, "pcramp_gpu_select_words: more than 2^20 candidate words in one batch");
+	const uint32_t n_pat = 2u * n_cand;
+	CK(ctx->d_cand_words.ensure((size_t)n_cand * 16));
+	CK(ctx->d_cand_thr.ensure((size_t)n_cand * 4));
+	CK(ctx->d_pat_mask.ensure((size_t)n_pat * 16));
+	CK(ctx->d_pat_meta.ensure((size_t)n_pat * 4));
+	cand_build_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->d_f.as<uint64_t>(), ctx->d_r.as<uint64_t>(), n_pairs, opt5, opt3, threshold,
+		ctx->d_cand_off.as<uint32_t>(), ctx->d_cand_words.as<uint64_t>(), ctx->d_cand_thr.as<uint32_t>(), ctx->d_pat_mask.as<uint4>(),
+		ctx->d_pat_meta.as<uint32_t>());
+	CK(cudaGetLastError());
+	stat.kernel_launches++;
+	{ // a zero threshold would select every word of every sequence (select_words.cpp:99-117): refuse
+		std::vector<uint32_t> thr(n_cand);
+		CK(cudaMemcpyAsync(thr.data(), ctx->d_cand_thr.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for (uint32_t t : thr)
+			if (t == 0) return fail(ctx, "pcramp_gpu_select_words: a candidate has match threshold 0 (empty oligo or threshold too low)");
+	}
+	const uint32_t cand_bits = bits_for(n_cand), seq_bits = bits_for(s.n);
+	stat.n_patterns = n_pat;
+	stat.n_positions = 0;
+	for (uint32_t i = 0; i < s.n; ++i)
+		if (s.active[i]) stat.n_positions += s.clen[i];
+
+	// ---- scan (re-run with a larger hit buffer if it overflowed) -------------------------------
+	uint64_t n_hits = 0;
+	uint64_t cap = std::max<uint64_t>(ctx->hit_key[0].cap / 8, 1ull << 20);
+	for (int attempt = 0;; ++attempt) {
+		CK(ctx->hit_key[0].ensure(cap * 8));
+		CK(ctx->hit_val[0].ensure(cap * 4));
+		cap = std::min<uint64_t>(ctx->hit_key[0].cap / 8, ctx->hit_val[0].cap / 4);
+		HitSink hs;
+		hs.key = ctx->hit_key[0].as<uint64_t>();
+		hs.val = ctx->hit_val[0].as<uint32_t>();
+		hs.count = d_cnt;
+		hs.cap = cap;
+		CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
+		CK(cudaEventRecord(ctx->ev[0], st));
+		if (s.n_tiles) {
+			const unsigned grid = (unsigned)std::min<uint64_t>(s.n_tiles, (uint64_t)ctx->sm_count * 2);
+			scan_full_kernel<<<grid, SCAN_THREADS, 0, st>>>(sd, s.d_tile_seq.as<uint32_t>(), s.d_tile_x0.as<uint32_t>(), (uint32_t)s.n_tiles,
+				ctx->d_pat_mask.as<uint4>(), ctx->d_pat_meta.as<uint32_t>(), n_pat, cand_bits, hs);
+			CK(cudaGetLastError());
+			stat.kernel_launches++;
+		}
+		CK(cudaEventRecord(ctx->ev[1], st));
+		scan_edge_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n + 7) / 8, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(sd, pp,
+			ctx->d_cand_words.as<uint64_t>(), ctx->d_cand_thr.as<uint32_t>(), n_cand, cand_bits, hs);
+		CK(cudaGetLastError());
+		stat.kernel_launches++;
+		CK(cudaEventRecord(ctx->ev[2], st));
+		CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		n_hits = ctx->h_counters[0];
+		stat.ms_scan += ev_ms(ctx->ev[0], ctx->ev[1]);
+		stat.ms_edge += ev_ms(ctx->ev[1], ctx->ev[2]);
+		if (n_hits <= cap) break;
+		if (attempt >= 2) return fail(ctx, "pcramp_gpu_select_words: hit buffer kept overflowing");
+		cap = n_hits + n_hits / 8 + 1024;
+	}
+	stat.n_hits = n_hits;
+	CK(cudaEventRecord(ctx->ev[3], st));
+	if (n_hits == 0) {
+		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(s.n + 1) * 4, st));
+		CK(cudaStreamSynchronize(st));
+		s.db_valid = true;
+		return 0;
+	}
+
+	// ---- validate, sort, tier ------------------------------------------------------------------
+	if (pp.gc_filter || s.any_degenerate) {
+		validate_hits_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(sd, pp, ctx->hit_key[0].as<uint64_t>(), ctx->hit_val[0].as<uint32_t>(), n_hits,
+			cand_bits);
+		CK(cudaGetLastError());
+		stat.kernel_launches++;
+	}
+	CK(ctx->hit_key[1].ensure(n_hits * 8));
+	CK(ctx->hit_val[1].ensure(n_hits * 4));
+	// all 64 bits when hits may have been invalidated to ~0 (they must sort last), else only the used field
+	const int sort_end = (pp.gc_filter || s.any_degenerate) ? 64 : (int)(HIT_GROUP_SHIFT + cand_bits + seq_bits);
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->hit_key[0].as<uint64_t>(), ctx->hit_key[1].as<uint64_t>(),
+		ctx->hit_val[0].as<uint32_t>(), ctx->hit_val[1].as<uint32_t>(), (int64_t)n_hits, 3, sort_end, st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->hit_key[0].as<uint64_t>(), ctx->hit_key[1].as<uint64_t>(),
+		ctx->hit_val[0].as<uint32_t>(), ctx->hit_val[1].as<uint32_t>(), (int64_t)n_hits, 3, sort_end, st));
+	stat.kernel_launches += 8;
+	CK(ctx->ent_id[0].ensure(n_hits * 8));
+	CK(ctx->ent_id[1].ensure(n_hits * 8));
+	CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
+	tier_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[1].as<uint64_t>(), ctx->hit_val[1].as<uint32_t>(), n_hits, cand_bits,
+		ctx->ent_id[0].as<uint64_t>(), d_cnt);
+	CK(cudaGetLastError());
+	stat.kernel_launches++;
+	CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const uint64_t n_flag = ctx->h_counters[0];
+	if (n_flag == 0) {
+		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(s.n + 1) * 4, st));
+		CK(cudaStreamSynchronize(st));
+		s.db_valid = true;
+		return 0;
+	}
+
+	// ---- unique entries -------------------------------------------------------------------------
+	CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, ctx->ent_id[0].as<uint64_t>(), ctx->ent_id[1].as<uint64_t>(), (int64_t)n_flag, 0,
+		(int)(35 + seq_bits), st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	CK(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp_bytes, ctx->ent_id[0].as<uint64_t>(), ctx->ent_id[1].as<uint64_t>(), (int64_t)n_flag, 0,
+		(int)(35 + seq_bits), st));
+	CK(cub::DeviceSelect::Unique(nullptr, tmp_bytes, ctx->ent_id[1].as<uint64_t>(), ctx->ent_id[0].as<uint64_t>(), d_cnt + 1, (int64_t)n_flag, st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	CK(cub::DeviceSelect::Unique(ctx->cub_tmp.p, tmp_bytes, ctx->ent_id[1].as<uint64_t>(), ctx->ent_id[0].as<uint64_t>(), d_cnt + 1, (int64_t)n_flag, st));
+	stat.kernel_launches += 10;
+	CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const uint64_t n_ent = ctx->h_counters[1];
+	if (n_ent >= (1ull << 32)) return fail(ctx, "pcramp_gpu_select_words: database exceeds 2^32 entries");
+
+	// ---- materialise + canonical order + keys ------------------------------------------------
+	CK(s.e_hi.ensure(n_ent * 8));
+	CK(s.e_lo.ensure(n_ent * 8));
+	CK(s.e_seq.ensure(n_ent * 4));
+	CK(s.e_loc.ensure(n_ent * 4));
+	CK(s.e_strand.ensure(n_ent * 4));
+	CK(s.e_perm.ensure(n_ent * 4));
+	CK(s.e_keyrank.ensure(n_ent * 4));
+	CK(ctx->order_key[0].ensure(n_ent * 8));
+	CK(ctx->order_key[1].ensure(n_ent * 8));
+	CK(ctx->perm[0].ensure(n_ent * 4));
+	CK(ctx->perm[1].ensure(n_ent * 4));
+	CK(ctx->head.ensure(n_ent * 4));
+	const unsigned ge = grid_for(n_ent, 256);
+	materialise_kernel<<<ge, 256, 0, st>>>(sd, pp, ctx->ent_id[0].as<uint64_t>(), n_ent, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(),
+		s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), ctx->order_key[0].as<uint64_t>());
+	CK(cudaGetLastError());
+	seq_offsets_kernel<<<grid_for((uint64_t)s.n + 1, 256), 256, 0, st>>>(s.e_seq.as<uint32_t>(), n_ent, s.n, s.seq_ent_off.as<uint32_t>());
+	CK(cudaGetLastError());
+	iota_kernel<<<ge, 256, 0, st>>>(ctx->perm[0].as<uint32_t>(), n_ent);
+	CK(cudaGetLastError());
+	stat.kernel_launches += 3;
+	// three stable LSD passes: (index, loc, strand), then word.lo, then word.hi
+	auto sort_pass = [&](const uint64_t *key_in, int end_bit, int src, int dst) -> int {
+		size_t tb = 0;
+		CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, key_in, ctx->order_key[1].as<uint64_t>(), ctx->perm[src].as<uint32_t>(),
+			ctx->perm[dst].as<uint32_t>(), (int64_t)n_ent, 0, end_bit, st));
+		CK(ctx->cub_tmp.ensure(tb));
+		CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, key_in, ctx->order_key[1].as<uint64_t>(), ctx->perm[src].as<uint32_t>(),
+			ctx->perm[dst].as<uint32_t>(), (int64_t)n_ent, 0, end_bit, st));
+		stat.kernel_launches += 8;
+		return 0;
+	};
+	if (sort_pass(ctx->order_key[0].as<uint64_t>(), (int)(34 + seq_bits), 0, 1)) return 1;
+	gather_u64_kernel<<<ge, 256, 0, st>>>(s.e_lo.as<uint64_t>(), ctx->perm[1].as<uint32_t>(), ctx->order_key[0].as<uint64_t>(), n_ent);
+	CK(cudaGetLastError());
+	if (sort_pass(ctx->order_key[0].as<uint64_t>(), 64, 1, 0)) return 1;
+	gather_u64_kernel<<<ge, 256, 0, st>>>(s.e_hi.as<uint64_t>(), ctx->perm[0].as<uint32_t>(), ctx->order_key[0].as<uint64_t>(), n_ent);
+	CK(cudaGetLastError());
+	if (sort_pass(ctx->order_key[0].as<uint64_t>(), 64, 0, 1)) return 1;
+	CK(cudaMemcpyAsync(s.e_perm.p, ctx->perm[1].p, n_ent * 4, cudaMemcpyDeviceToDevice, st));
+	key_heads_kernel<<<ge, 256, 0, st>>>(s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), s.e_perm.as<uint32_t>(), ctx->head.as<uint32_t>(), n_ent);
+	CK(cudaGetLastError());
+	CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), (int)n_ent, st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	CK(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), (int)n_ent, st));
+	stat.kernel_launches += 5;
+	uint32_t n_keys = 0;
+	CK(cudaMemcpyAsync(&n_keys, s.e_keyrank.as<uint32_t>() + (n_ent - 1), 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaEventRecord(ctx->ev[4], st));
+	CK(cudaStreamSynchronize(st));
+	stat.ms_db = ev_ms(ctx->ev[3], ctx->ev[4]);
+	s.n_entries = n_ent;
+	s.n_keys = n_keys;
+	s.db_valid = true;
+	stat.n_entries = n_ent;
+	stat.n_keys = n_keys;
+	if (n_entries_out) *n_entries_out = n_ent;
+	if (n_keys_out) *n_keys_out = n_keys;
+	return 0;
+}
+
+int pcramp_gpu_select_words(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, int opt5, int opt3,
+	float threshold, uint32_t pack_max_degen, float min_gc, float max_gc, uint32_t min_len, uint64_t *n_entries, uint64_t *n_keys)
+{
+	if (pcramp_gpu_stage_pairs(ctx, f, r, n_pairs)) return 1;
+	return pcramp_gpu_select_words_staged(ctx, kind, opt5, opt3, threshold, pack_max_degen, min_gc, max_gc, min_len, n_entries, n_keys);
+}
+
+int pcramp_gpu_db_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *words, uint32_t *index, int32_t *loc, uint32_t *strand, uint32_t *key_index)
+{
+	if (check_kind(ctx, kind)) return 1;
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	if (!s.db_valid) return fail(ctx, "pcramp_gpu_db_copy: no database (call pcramp_gpu_select_words first)");
+	const uint64_t n = s.n_entries;
+	if (n == 0) return 0;
+	DevBuf o_words, o_index, o_loc, o_strand, o_key, o_keys;
+	CK(o_words.ensure(n * 16));
+	CK(o_index.ensure(n * 4));
+	CK(o_loc.ensure(n * 4));
+	CK(o_strand.ensure(n * 4));
+	CK(o_key.ensure(n * 4));
+	CK(o_keys.ensure(std::max<uint64_t>(1, s.n_keys) * 16));
+	db_export_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), s.e_seq.as<uint32_t>(),
+		s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), s.e_perm.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), n, o_words.as<uint64_t>(),
+		o_index.as<uint32_t>(), o_loc.as<int32_t>(), o_strand.as<uint32_t>(), o_key.as<uint32_t>(), o_keys.as<uint64_t>());
+	CK(cudaGetLastError());
+	if (words) CK(cudaMemcpyAsync(words, o_words.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	if (index) CK(cudaMemcpyAsync(index, o_index.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (loc) CK(cudaMemcpyAsync(loc, o_loc.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (strand) CK(cudaMemcpyAsync(strand, o_strand.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (key_index) CK(cudaMemcpyAsync(key_index, o_key.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int pcramp_gpu_keys_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *keys)
+{
+	if (check_kind(ctx, kind)) return 1;
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	if (!s.db_valid) return fail(ctx, "pcramp_gpu_keys_copy: no database (call pcramp_gpu_select_words first)");
+	const uint64_t n = s.n_entries;
+	if (n == 0 || !keys) return 0;
+	DevBuf o_words, o_index, o_loc, o_strand, o_key, o_keys;
+	CK(o_words.ensure(n * 16));
+	CK(o_index.ensure(n * 4));
+	CK(o_loc.ensure(n * 4));
+	CK(o_strand.ensure(n * 4));
+	CK(o_key.ensure(n * 4));
+	CK(o_keys.ensure(std::max<uint64_t>(1, s.n_keys) * 16));
+	db_export_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), s.e_seq.as<uint32_t>(),
+		s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), s.e_perm.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), n, o_words.as<uint64_t>(),
+		o_index.as<uint32_t>(), o_loc.as<int32_t>(), o_strand.as<uint32_t>(), o_key.as<uint32_t>(), o_keys.as<uint64_t>());
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(keys, o_keys.p, s.n_keys * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+uint32_t pcramp_gpu_bitset_words(pcramp_gpu_ctx *ctx, int kind) { return (ctx->sets[kind].n + 31u) / 32u; }
+
+int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_threshold, float detect_threshold, int amp_min, int amp_max,
+	int taq)
+{
+	if (check_kind(ctx, kind)) return 1;
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	cudaStream_t st = ctx->stream;
+	if (!s.db_valid) return fail(ctx, "pcramp_gpu_score_pairs: no database (call pcramp_gpu_select_words first)");
+	const uint32_t n_pairs = ctx->n_pairs, n_words = (s.n + 31u) / 32u;
+	ctx->res_words = n_words;
+	const size_t bits_bytes = std::max<size_t>(1, (size_t)n_pairs * n_words) * 4;
+	CK(ctx->d_cov.ensure(std::max<size_t>(1, n_pairs) * 4));
+	CK(ctx->d_bits.ensure(bits_bytes));
+	CK(ctx->d_bits1.ensure(bits_bytes));
+	CK(ctx->d_oligos.ensure(std::max<size_t>(1, n_pairs) * 2 * sizeof(OligoDev)));
+	CK(cudaEventRecord(ctx->ev[5], st));
+	CK(cudaMemsetAsync(ctx->d_bits.p, 0, bits_bytes, st));
+	CK(cudaMemsetAsync(ctx->d_bits1.p, 0, bits_bytes, st));
+	CK(cudaMemsetAsync(ctx->d_cov.p, 0, std::max<size_t>(1, n_pairs) * 4, st));
+	ctx->stats.ms_score = 0.0f;
+	if (n_pairs && s.n) {
+		const float thr2 = search_threshold * search_threshold; // pcr_assay.cpp:31-32 (float product)
+		prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(ctx->d_f.as<uint64_t>(), ctx->d_r.as<uint64_t>(), n_pairs, thr2,
+			ctx->d_oligos.as<OligoDev>());
+		CK(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+		if (s.n_entries) {
+			const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
+			score_kernel<<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), s.e_loc.as<int32_t>(),
+				s.e_strand.as<uint32_t>(), s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>(), n_pairs, detect_threshold, amp_min,
+				amp_max, taq, ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
+			CK(cudaGetLastError());
+			coverage_kernel<<<grid_for(n_pairs, 128), 128, 0, st>>>(ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), s.d_weight.as<float>(),
+				n_pairs, n_words, s.n, ctx->d_cov.as<float>());
+			CK(cudaGetLastError());
+			ctx->stats.kernel_launches += 2;
+		}
+	}
+	CK(cudaEventRecord(ctx->ev[6], st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.ms_score = ev_ms(ctx->ev[5], ctx->ev[6]);
+	return 0;
+}
+
+void *pcramp_gpu_device_coverage(pcramp_gpu_ctx *ctx) { return ctx->d_cov.p; }
+void *pcramp_gpu_device_bitsets(pcramp_gpu_ctx *ctx) { return ctx->d_bits.p; }
+
+int pcramp_gpu_fetch_results(pcramp_gpu_ctx *ctx, float *coverage, uint32_t *bitsets)
+{
+	if (!ctx) return 1;
+	CK(cudaSetDevice(ctx->device));
+	if (coverage && ctx->n_pairs) CK(cudaMemcpyAsync(coverage, ctx->d_cov.p, (size_t)ctx->n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (bitsets && ctx->n_pairs && ctx->res_words)
+		CK(cudaMemcpyAsync(bitsets, ctx->d_bits.p, (size_t)ctx->n_pairs * ctx->res_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int pcramp_gpu_score_pairs(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, float search_threshold,
+	float detect_threshold, int amp_min, int amp_max, int taq, float *coverage, uint32_t *bitsets)
+{
+	if (pcramp_gpu_stage_pairs(ctx, f, r, n_pairs)) return 1;
+	if (pcramp_gpu_score_pairs_staged(ctx, kind, search_threshold, detect_threshold, amp_min, amp_max, taq)) return 1;
+	return pcramp_gpu_fetch_results(ctx, coverage, bitsets);
+}
+
+int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out)
+{
+	if (!ctx || !out) return 1;
+	*out = ctx->stats;
+	return 0;
+}
+
+// ---- host-side word helpers -----------------------------------------------------------------
+static inline uint32_t iupac_to_bits(char c)
+{ // base_table.h:31-76
+	switch (c) {
+	case 'A': case 'a': return 1;
+	case 'C': case 'c': return 2;
+	case 'G': case 'g': return 4;
+	case 'T': case 't': case 'U': case 'u': return 8;
+	case 'M': case 'm': return 3;
+	case 'R': case 'r': return 5;
+	case 'S': case 's': return 6;
+	case 'V': case 'v': return 7;
+	case 'W': case 'w': return 9;
+	case 'Y': case 'y': return 10;
+	case 'H': case 'h': return 11;
+	case 'K': case 'k': return 12;
+	case 'D': case 'd': return 13;
+	case 'B': case 'b': return 14;
+	case 'N': case 'n': case 'I': case 'i': case 'X': case 'x': return 15;
+	default: return 0;
+	}
+}
+
+void pcramp_word_from_string(const char *iupac, int centre, uint64_t out[2])
+{
+	W128 w;
+	w.hi = w.lo = 0;
+	for (int i = 0; iupac[i] && i < WORD_LEN; ++i) w_set(w, i, iupac_to_bits(iupac[i]));
+	if (centre) w = w_center(w);
+	out[0] = w.hi;
+	out[1] = w.lo;
+}
+
+int pcramp_word_to_string(const uint64_t in[2], char out[33])
+{ // word.h:649-657
+	static const char sym[] = "-ACMGRSVTWYHKDBN";
+	W128 w;
+	w.hi = in[0];
+	w.lo = in[1];
+	int n = 0;
+	for (int i = w_start(w); i <= w_stop(w); ++i) out[n++] = sym[w_get(w, i)];
+	out[n] = 0;
+	return n;
+}
+
+uint32_t pcramp_word_and(const uint64_t a[2], const uint64_t b[2])
+{
+	W128 x, y;
+	x.hi = a[0]; x.lo = a[1];
+	y.hi = b[0]; y.lo = b[1];
+	return (uint32_t)w_and_count(x, y);
+}
+uint32_t pcramp_word_size(const uint64_t a[2])
+{
+	W128 x;
+	x.hi = a[0]; x.lo = a[1];
+	return (uint32_t)w_size(x);
+}
+int pcramp_word_start(const uint64_t a[2])
+{
+	W128 x;
+	x.hi = a[0]; x.lo = a[1];
+	return w_start(x);
+}
+int pcramp_word_stop(const uint64_t a[2])
+{
+	W128 x;
+	x.hi = a[0]; x.lo = a[1];
+	return w_stop(x);
+}
+void pcramp_word_complement(const uint64_t a[2], uint64_t out[2])
+{
+	W128 x;
+	x.hi = a[0]; x.lo = a[1];
+	const W128 r = w_complement(x);
+	out[0] = r.hi;
+	out[1] = r.lo;
+}
+void pcramp_word_center(const uint64_t a[2], uint64_t out[2])
+{
+	W128 x;
+	x.hi = a[0]; x.lo = a[1];
+	const W128 r = w_center(x);
+	out[0] = r.hi;
+	out[1] = r.lo;
+}
+
+} // extern "C"

@@ -1,0 +1,199 @@
+// seqdev.cuh -- how a sequence collection lives in HBM, and the closed-form model of
+// Sequence::pack (sequence.cpp:92-267) that every kernel shares.
+//
+// HBM layout per collection (all arrays are struct-of-arrays indexed by sequence):
+//   raw      the reference's packed nibbles as uploaded (2 bases/byte, sequence.h:223-228); only
+//            the GC filter and the slow paths read it.
+//   planes   the COMPRESSED text (EOS nibbles removed -- pack() absorbs them, Appendix A.3 of
+//            SURVEY.md) as four interleaved bit-planes: one uint4 {A,C,G,T} per 32 bases, bit b of
+//            a plane word = base 32*g+b carries that letter.  Same 4 bits/base as the nibbles, but
+//            a 32-base template window for ANY alignment is two 16-byte loads and four funnel
+//            shifts, and "does primer position k match" is a plain AND.  Each sequence owns
+//            ceil(clen/32)+1 groups (one zero halo group), bits past clen are zero.
+//   eos_pos  sorted raw positions of the EOS nibbles of each sequence (CSR via eos_off); empty for
+//            almost every sequence.  Gives raw<->compressed index maps and has_split() by search.
+//
+// Closed form of pack().  Let b_0..b_{clen-1} be the non-EOS bases, c_i the number of bases in
+// raw[0..i].  Entries are emitted at these events (both strands each), subject to the degeneracy
+// and GC filters:
+//   FULL    every compressed index j >= 31: word = b_{j-31..j}; with i = raw index of b_j:
+//           loc+ = i - 31, loc- = i                                   (sequence.cpp:182-194)
+//   FILL    every raw index i with 1 <= c_i < 32 and c_i >= min_len (EOS positions included, which
+//           re-emit the unchanged word): word = b_0..b_{n-1}, n = c_i, centred at st = (33-n)/2;
+//           loc+ = i + 1 - n - st, loc- = i + st                      (:155-181)
+//   EOSEVT  every raw index i holding EOS with c_i >= 32 (31 >= min_len): word = the last 31 bases,
+//           st = 1; loc+ = i - 31, loc- = i + 1                       (:155-181 with size 31)
+//   TAIL    q = 1..s0: the last n = n0 - q bases, counter s = s0 - q >= min_len, st = (33-n)/2;
+//           loc+ = L - s - st, loc- = L - 1 + st                      (:198-263)
+//           where (n0, s0) = (clen, clen) if clen < 32, (31, 31) if the last raw nibble is EOS,
+//           else (32, 31).
+// Odd lengths: pack() iterates BYTES (`iter != seq_buffer.end()`, sequence.cpp:111), so a sequence of
+// odd length also pushes the unused low nibble of its last byte, which Sequence::operator= left zero
+// (sequence.cpp:23): one trailing EOS at raw index len.  plen = len + (len & 1) is the length the
+// model above uses for L, and that virtual EOS is part of eos_pos (has_split never looks that far).
+// tests/test_gpu_parity.py checks this model entry by entry against the reference's state machine.
+#pragma once
+#include "word128.cuh"
+
+namespace pcr {
+
+struct SeqDev {
+	uint32_t n;
+	const uint4 *planes;
+	const uint64_t *grp_off; // n + 1, in groups
+	const uint32_t *clen;    // compressed length (bases)
+	const uint32_t *len;     // raw length (nibbles incl. EOS)
+	const uint32_t *plen;    // length pack() walks: len rounded up to even (see below)
+	const uint8_t *raw;
+	const uint64_t *raw_off; // byte offset of each sequence in raw
+	const uint32_t *eos_pos;
+	const uint32_t *eos_off; // n + 1
+	const float *weight;
+	const uint8_t *active;
+};
+
+enum : uint32_t { ENT_FULL = 0, ENT_FILL = 1, ENT_EOSEVT = 2, ENT_TAIL = 3 };
+
+struct PackParams {
+	uint32_t max_degen;
+	float min_gc, max_gc;
+	uint32_t min_len;
+	int gc_filter;
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ uint32_t comp_nibble_at(const SeqDev &sd, uint32_t seq, uint32_t j)
+{
+	const uint4 g = __ldg(sd.planes + sd.grp_off[seq] + (j >> 5));
+	const uint32_t b = j & 31u;
+	return ((g.x >> b) & 1u) | (((g.y >> b) & 1u) << 1) | (((g.z >> b) & 1u) << 2) | (((g.w >> b) & 1u) << 3);
+}
+
+__device__ __forceinline__ uint32_t raw_nibble_at(const SeqDev &sd, uint32_t seq, uint32_t i)
+{
+	if (i >= sd.len[seq]) return 0u; // the virtual pad nibble of an odd-length sequence
+	const uint8_t v = __ldg(sd.raw + sd.raw_off[seq] + (i >> 1));
+	return (i & 1u) ? (v & 0xFu) : (v >> 4);
+}
+
+// number of EOS k (0-based, raw position e_k) with e_k - k <= j, i.e. that precede base j
+__device__ __forceinline__ uint32_t eos_before_base(const SeqDev &sd, uint32_t seq, uint32_t j)
+{
+	const uint32_t lo0 = sd.eos_off[seq], hi0 = sd.eos_off[seq + 1];
+	uint32_t lo = 0, hi = hi0 - lo0;
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (sd.eos_pos[lo0 + mid] - mid <= j) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+__device__ __forceinline__ uint32_t raw_of_comp(const SeqDev &sd, uint32_t seq, uint32_t j) { return j + eos_before_base(sd, seq, j); }
+
+// number of EOS with raw position <= i
+__device__ __forceinline__ uint32_t eos_upto_raw(const SeqDev &sd, uint32_t seq, int64_t i)
+{
+	const uint32_t lo0 = sd.eos_off[seq], hi0 = sd.eos_off[seq + 1];
+	uint32_t lo = 0, hi = hi0 - lo0;
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if ((int64_t)sd.eos_pos[lo0 + mid] <= i) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+// Sequence::has_split (sequence.cpp:304-330) for an in-range [loc, loc+len)
+__device__ __forceinline__ bool has_split_dev(const SeqDev &sd, uint32_t seq, int loc, int len)
+{
+	if (sd.eos_off[seq + 1] == sd.eos_off[seq] || len <= 0) return false;
+	return eos_upto_raw(sd, seq, (int64_t)loc + len - 1) != eos_upto_raw(sd, seq, (int64_t)loc - 1);
+}
+
+// n bases b_{first..first+n-1} of the compressed text, left-justified in a word
+__device__ inline W128 gather_bases(const SeqDev &sd, uint32_t seq, uint32_t first, uint32_t n)
+{
+	W128 w;
+	w.hi = w.lo = 0;
+	for (uint32_t k = 0; k < n; ++k) w_set(w, (int)k, comp_nibble_at(sd, seq, first + k));
+	return w;
+}
+
+// GC count over raw[i-31..i] clipped at 0 (sequence.cpp:127-141: the last 32 pushed nibbles, EOS included)
+__device__ inline uint32_t gc_window_raw(const SeqDev &sd, uint32_t seq, int64_t i)
+{
+	uint32_t c = 0;
+	for (int64_t p = (i >= 31 ? i - 31 : 0); p <= i; ++p) c += ((raw_nibble_at(sd, seq, (uint32_t)p) & 6u) != 0u);
+	return c;
+}
+__device__ __forceinline__ bool gc_pass(uint32_t num_gc, const PackParams &pp)
+{
+	const float fraction = __fmul_rn((float)num_gc, 1.0f / 32.0f);
+	return !(fraction < pp.min_gc || fraction > pp.max_gc);
+}
+
+// One pack() entry pair, identified by (type, pos).  Returns false when the event emits nothing
+// (too short, filtered).  plus/minus are the two database words, loc_p/loc_m their WordMatch.loc.
+__device__ inline bool pack_entry(const SeqDev &sd, uint32_t seq, uint32_t type, uint32_t pos, const PackParams &pp,
+	W128 &plus, W128 &minus, int &loc_p, int &loc_m)
+{
+	const uint32_t L = sd.plen[seq], Lc = sd.clen[seq];
+	uint32_t n, first;
+	int st;
+	int64_t gc_end = -1; // raw index the GC window ends at; -2 = tail rule
+	if (type == ENT_FULL) {
+		if (pos < 31u || pos >= Lc) return false;
+		n = 32; first = pos - 31u; st = 0;
+		const uint32_t i = raw_of_comp(sd, seq, pos);
+		loc_p = (int)i - 31;
+		loc_m = (int)i;
+		gc_end = i;
+	} else if (type == ENT_FILL) {
+		if (pos >= L) return false;
+		const uint32_t c = pos + 1u - eos_upto_raw(sd, seq, pos);
+		if (c >= 32u || c == 0u || c < pp.min_len) return false;
+		n = c; first = 0; st = (33 - (int)n) / 2;
+		loc_p = (int)pos + 1 - (int)n - st;
+		loc_m = (int)pos + st;
+		gc_end = pos;
+	} else if (type == ENT_EOSEVT) {
+		if (pos >= L || raw_nibble_at(sd, seq, pos) != 0u) return false;
+		const uint32_t c = pos + 1u - eos_upto_raw(sd, seq, pos);
+		if (c < 32u || 31u < pp.min_len) return false;
+		n = 31; first = c - 31u; st = 1;
+		loc_p = (int)pos - 31;
+		loc_m = (int)pos + 1;
+		gc_end = pos;
+	} else {
+		uint32_t n0, s0;
+		if (Lc < 32u) { n0 = Lc; s0 = Lc; }
+		else if (raw_nibble_at(sd, seq, L - 1u) == 0u) { n0 = 31; s0 = 31; }
+		else { n0 = 32; s0 = 31; }
+		if (pos == 0u || pos > s0) return false;
+		const uint32_t s = s0 - pos;
+		n = n0 - pos;
+		if (s < pp.min_len || n == 0u) return false;
+		first = Lc - n; st = (33 - (int)n) / 2;
+		loc_p = (int)L - (int)s - st;
+		loc_m = (int)L - 1 + st;
+		gc_end = -2;
+	}
+	if (pp.gc_filter) {
+		uint32_t num_gc;
+		if (gc_end == -2) { // tail: one pop when 32 nibbles were buffered, then frozen (sequence.cpp:204-222)
+			num_gc = (L >= 32u) ? gc_window_raw(sd, seq, (int64_t)L - 1) - ((raw_nibble_at(sd, seq, L - 32u) & 6u) != 0u)
+			                    : gc_window_raw(sd, seq, (int64_t)L - 1);
+		} else {
+			num_gc = gc_window_raw(sd, seq, gc_end);
+		}
+		if (!gc_pass(num_gc, pp)) return false;
+	}
+	const W128 left = gather_bases(sd, seq, first, n);
+	if (w_degeneracy_sat(left) > (uint64_t)pp.max_degen) return false; // :149-153 (shift-invariant)
+	plus = w_shr(left, st);
+	minus = w_shr(w_complement(left), st); // complement() left-justifies; centring gives the same st
+	return true;
+}
+
+#endif // __CUDACC__
+
+} // namespace pcr

@@ -1,0 +1,94 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/libpcramp_ref.so, built from
+/root/reference by oracle/Makefile) on the seeded scenarios of tests/scenarios.py, plus a table of
+known-answer values of the reference's word and NucCruc primitives.
+
+Run in the dev container only (needs /root/reference):   python tests/golden/make_golden.py
+The fixtures travel with the repository; the GPU box never reads /root/reference.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from tests import scenarios  # noqa: E402
+from tests.harness import RefLib  # noqa: E402
+
+
+def word_kats(ref):
+    """Known answers of Word primitives on a fixed list of oligos (word.h / word.cpp)."""
+    rng = np.random.default_rng(2024)
+    sym = "ACGTMRSVWYHKDBN"
+    oligos = ["CAGCCACTGCACCTCTTCAT", "ACATAGCCTGATACGAGT", "GGGTGTGCATCGAGCGGGCG", "A" * 32, "N", "ACGTN", "RYKMSWBDHVN",
+              "CAGCCTCTGCACCTNTTCAT", "RAGCCACTGCACCTCTTCAT"]
+    for n in (1, 2, 17, 18, 25, 31, 32):
+        for _ in range(4):
+            p = [0.22, 0.22, 0.22, 0.22] + [0.12 / 11] * 11
+            oligos.append("".join(rng.choice(list(sym), size=n, p=p)))
+    rows = []
+    words = []
+    for s in oligos:
+        for centre in (0, 1):
+            w = ref.word_from_string(s, centre)
+            words.append(w)
+    words = np.array(words, dtype=np.uint64)
+    for w in words:
+        w = (int(w[0]), int(w[1]))
+        comp = ref.word_complement(w)
+        cen = ref.word_center(w)
+        sl = ref.word_shift(w, 1)
+        sr = ref.word_shift(w, 0)
+        rows.append([w[0], w[1], ref.word_size(w), ref.word_start(w) & 0xFFFFFFFF, ref.word_stop(w) & 0xFFFFFFFF,
+                     int(min(ref.word_degeneracy(w), 2.0 ** 62)), comp[0], comp[1], cen[0], cen[1], sl[0], sl[1], sr[0], sr[1]])
+    pair = []
+    for i in range(0, len(words), 3):
+        for j in range(1, len(words), 5):
+            a, b = (int(words[i][0]), int(words[i][1])), (int(words[j][0]), int(words[j][1]))
+            pair.append([a[0], a[1], b[0], b[1], ref.word_and(a, b)])
+    taq = np.array([[ref.taq_mama(a, b, c, d) for c in (1, 2, 4, 8, 5) for d in (1, 2, 4, 8, 0)] for a in (1, 2, 4, 8, 15) for b in (1, 2, 4, 8, 3)],
+                   dtype=np.float32)
+    expand = []
+    for s in ("ACGT", "RAGY", "NAN", "ACRTNGB", "SWKM"):
+        w = ref.word_from_string(s, 1)
+        n, ws = ref.word_expand(w)
+        expand.append(np.concatenate([[n], ws.reshape(-1)]).astype(np.uint64))
+    return dict(oligos=np.array(oligos), word_rows=np.array(rows, dtype=np.uint64), and_rows=np.array(pair, dtype=np.uint64), taq=taq,
+                expand=np.concatenate(expand))
+
+
+def thermo_kats(ref):
+    """NucCruc front-ends on fixed oligos (SURVEY.md Appendix B lists a few of these)."""
+    rng = np.random.default_rng(7)
+    seqs = ["CAGCCACTGCACCTCTTCAT", "ACATAGCCTGATACGAGT", "GGGTGTGCATCGAGCGGGCG", "AAAAAAAAAAAAAAAAAAAA", "GCGCGCGCGCGCGCGCGCGC",
+            "ACGTACGTACGTACGTACGTACGTA", "ACAATCATTTCAGGCGCGAG", "ATGAAGAGGTGCAGTGGCTG"]
+    for n in (18, 19, 20, 21, 22, 23, 24, 25):
+        for _ in range(3):
+            seqs.append("".join(rng.choice(list("ACGT"), size=n)))
+    rows = []
+    for s in seqs:
+        for op in (0, 1, 2):
+            rows.append(ref.thermo(op, s))
+    het = []
+    for i in range(0, len(seqs) - 1, 2):
+        for op in (3, 4):
+            het.append(ref.thermo(op, seqs[i], seqs[i + 1]))
+    return dict(thermo_seqs=np.array(seqs), thermo_self=np.array(rows, np.float32), thermo_het=np.array(het, np.float32))
+
+
+def main():
+    ref = RefLib()
+    ref.set_threads(1)
+    for sc in scenarios.all_scenarios():
+        rec = scenarios.run_checker(ref, sc, "ref")
+        np.savez_compressed(os.path.join(HERE, "scenario_%s.npz" % sc.name), **rec)
+        print("%-12s entries %5d keys %5d detected %4d" % (sc.name, len(rec["db_loc"]), len(rec["keys"]), int(rec["bits"].sum())))
+    np.savez_compressed(os.path.join(HERE, "kat_words.npz"), **word_kats(ref))
+    np.savez_compressed(os.path.join(HERE, "kat_thermo.npz"), **thermo_kats(ref))
+    print("wrote fixtures to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,340 @@
+"""ctypes wrappers around the two CPU checkers (test infrastructure only):
+
+  OracleLib  oracle/liboracle.so          -- my restatement of the reference algorithm
+  RefLib     oracle/_ref/libpcramp_ref.so -- the unmodified reference sources + oracle/ref_driver.cpp
+
+Both expose the same Python surface so tests can run one scenario through either.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_PATH = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libpcramp_ref.so")
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _w(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.ndim == 2 and a.shape[1] == 2
+    return a
+
+
+def build_oracle():
+    if not os.path.exists(ORACLE_PATH) or os.path.getmtime(ORACLE_PATH) < os.path.getmtime(os.path.join(ROOT, "oracle", "pcramp_oracle.cpp")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
+
+
+def canonical(words, index, loc, strand):
+    """Sort DB entries by (word, index, loc, strand) -- the reference's order among equal keys is unspecified."""
+    words = np.asarray(words, dtype=np.uint64).reshape(-1, 2)
+    order = np.lexsort((strand, loc, index, words[:, 1], words[:, 0]))
+    return words[order], np.asarray(index)[order], np.asarray(loc)[order], np.asarray(strand)[order]
+
+
+class _Base:
+    prefix = ""
+
+    def _fn(self, name, res, args):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = res
+        f.argtypes = args
+        return f
+
+    def _words_api(self):
+        P = self.prefix
+        self.f_word_from_string = self._fn("word_from_string", None, [ctypes.c_char_p, ctypes.c_int, _u64p])
+        self.f_word_and = self._fn("word_and", ctypes.c_uint32, [_u64p, _u64p])
+        self.f_word_size = self._fn("word_size", ctypes.c_uint32, [_u64p])
+        self.f_word_start = self._fn("word_start", ctypes.c_int, [_u64p])
+        self.f_word_stop = self._fn("word_stop", ctypes.c_int, [_u64p])
+        self.f_word_degeneracy = self._fn("word_degeneracy", ctypes.c_double, [_u64p])
+        self.f_word_complement = self._fn("word_complement", None, [_u64p, _u64p])
+        self.f_word_center = self._fn("word_center", None, [_u64p, _u64p])
+        self.f_word_shift = self._fn("word_shift", None, [_u64p, ctypes.c_int, _u64p])
+        self.f_word_push_back = self._fn("word_push_back", None, [_u64p, ctypes.c_uint8, _u64p])
+        self.f_taq = self._fn("taq_mama", ctypes.c_float, [ctypes.c_uint8] * 4)
+        self.f_word_expand = self._fn("word_expand", ctypes.c_long, [_u64p, ctypes.c_long, _u64p])
+
+    # --- word helpers, value semantics ---
+    @staticmethod
+    def _mk(w):
+        return (ctypes.c_uint64 * 2)(int(w[0]), int(w[1]))
+
+    def word_from_string(self, s, centre=True):
+        out = (ctypes.c_uint64 * 2)()
+        self.f_word_from_string(s.encode(), int(centre), out)
+        return (int(out[0]), int(out[1]))
+
+    def word_and(self, a, b):
+        return int(self.f_word_and(self._mk(a), self._mk(b)))
+
+    def word_size(self, a):
+        return int(self.f_word_size(self._mk(a)))
+
+    def word_start(self, a):
+        return int(self.f_word_start(self._mk(a)))
+
+    def word_stop(self, a):
+        return int(self.f_word_stop(self._mk(a)))
+
+    def word_degeneracy(self, a):
+        return float(self.f_word_degeneracy(self._mk(a)))
+
+    def _unary(self, fn, a, *extra):
+        out = (ctypes.c_uint64 * 2)()
+        fn(self._mk(a), *extra, out)
+        return (int(out[0]), int(out[1]))
+
+    def word_complement(self, a):
+        return self._unary(self.f_word_complement, a)
+
+    def word_center(self, a):
+        return self._unary(self.f_word_center, a)
+
+    def word_shift(self, a, left):
+        return self._unary(self.f_word_shift, a, int(left))
+
+    def word_push_back(self, a, b):
+        return self._unary(self.f_word_push_back, a, int(b))
+
+    def taq_mama(self, p0, p1, t0, t1):
+        return float(self.f_taq(p0, p1, t0, t1))
+
+    def word_expand(self, a, cap=4096):
+        out = np.zeros((cap, 2), np.uint64)
+        n = self.f_word_expand(self._mk(a), cap, _p(out, _u64p))
+        return n, out[:min(n, cap)]
+
+
+class OracleLib(_Base):
+    prefix = "oracle_"
+
+    def __init__(self):
+        build_oracle()
+        self.lib = ctypes.CDLL(ORACLE_PATH)
+        self._words_api()
+        self.lib.oracle_create.restype = ctypes.c_void_p
+        self.h = ctypes.c_void_p(self.lib.oracle_create())
+        vp = ctypes.c_void_p
+        self.f_set = self._fn("set_sequences", ctypes.c_int, [vp, ctypes.c_uint32, _u8p, _u64p, _u32p, _f32p, _u8p])
+        self.f_active = self._fn("set_active", ctypes.c_int, [vp, _u8p])
+        self.f_split = self._fn("split_sequence", ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32])
+        self.f_pack = self._fn("pack", ctypes.c_long, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_uint32,
+                                                      _u64p, _u32p, _i32p, _u32p])
+        self.f_select = self._fn("select_words", ctypes.c_long, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                                ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_uint32])
+        self.f_db_size = self._fn("db_size", ctypes.c_long, [vp])
+        self.f_num_keys = self._fn("num_keys", ctypes.c_long, [vp])
+        self.f_db_copy = self._fn("db_copy", None, [vp, _u64p, _u32p, _i32p, _u32p])
+        self.f_keys_copy = self._fn("keys_copy", None, [vp, _u64p])
+        self.f_db_set = self._fn("db_set", ctypes.c_int, [vp, ctypes.c_long, _u64p, _u32p, _i32p, _u32p])
+        self.f_score = self._fn("score_pairs", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                             ctypes.c_int, ctypes.c_int, _f32p, _u8p])
+        self.f_has_split = self._fn("has_split", ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_int])
+        self.n_seq = 0
+
+    def set_sequences(self, coll, active=None):
+        self.n_seq = coll.n
+        a = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
+        assert self.f_set(self.h, coll.n, _p(coll.nibbles, _u8p), _p(coll.byte_off, _u64p), _p(coll.length, _u32p), _p(coll.weight, _f32p),
+                          _p(a, _u8p)) == 0
+
+    def set_active(self, active):
+        a = np.ascontiguousarray(active, dtype=np.uint8)
+        self.f_active(self.h, _p(a, _u8p))
+
+    def split_sequence(self, seq, pos):
+        self.f_split(self.h, seq, pos)
+
+    def pack(self, seq, pack_max_degen=256, min_gc=0.0, max_gc=1.0, min_len=18):
+        n = self.f_pack(self.h, seq, pack_max_degen, min_gc, max_gc, min_len, None, None, None, None)
+        words = np.zeros((n, 2), np.uint64)
+        index = np.zeros(n, np.uint32)
+        loc = np.zeros(n, np.int32)
+        strand = np.zeros(n, np.uint32)
+        self.f_pack(self.h, seq, pack_max_degen, min_gc, max_gc, min_len, _p(words, _u64p), _p(index, _u32p), _p(loc, _i32p), _p(strand, _u32p))
+        return canonical(words, index, loc, strand)
+
+    def select_words(self, f, r, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0,
+                     min_oligo_length=18):
+        f, r = _w(f), _w(r)
+        n = self.f_select(self.h, len(f), _p(f, _u64p), _p(r, _u64p), int(optimize_5), int(optimize_3), threshold, pack_max_degen, pack_min_gc,
+                          pack_max_gc, min_oligo_length)
+        assert n >= 0
+        return n, self.f_num_keys(self.h)
+
+    def db(self):
+        n = self.f_db_size(self.h)
+        words = np.zeros((n, 2), np.uint64)
+        index = np.zeros(n, np.uint32)
+        loc = np.zeros(n, np.int32)
+        strand = np.zeros(n, np.uint32)
+        if n:
+            self.f_db_copy(self.h, _p(words, _u64p), _p(index, _u32p), _p(loc, _i32p), _p(strand, _u32p))
+        return canonical(words, index, loc, strand)
+
+    def keys(self):
+        n = self.f_num_keys(self.h)
+        k = np.zeros((n, 2), np.uint64)
+        if n:
+            self.f_keys_copy(self.h, _p(k, _u64p))
+        return k
+
+    def db_set(self, words, index, loc, strand):
+        words = _w(words)
+        index = np.ascontiguousarray(index, np.uint32)
+        loc = np.ascontiguousarray(loc, np.int32)
+        strand = np.ascontiguousarray(strand, np.uint32)
+        assert self.f_db_set(self.h, len(index), _p(words, _u64p), _p(index, _u32p), _p(loc, _i32p), _p(strand, _u32p)) == 0
+
+    def score_pairs(self, f, r, search_threshold, detect_threshold, amp_min=80, amp_max=200, taq=False):
+        f, r = _w(f), _w(r)
+        cov = np.zeros(len(f), np.float32)
+        bits = np.zeros((len(f), self.n_seq), np.uint8)
+        assert self.f_score(self.h, len(f), _p(f, _u64p), _p(r, _u64p), search_threshold, detect_threshold, amp_min, amp_max, int(taq),
+                            _p(cov, _f32p), _p(bits, _u8p)) == 0
+        return cov, bits
+
+    def has_split(self, seq, loc, length):
+        return self.f_has_split(self.h, seq, loc, length)
+
+
+class RefLib(_Base):
+    prefix = "ref_"
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(REF_PATH)
+        self._words_api()
+        self.lib.ref_create.restype = ctypes.c_void_p
+        self.h = ctypes.c_void_p(self.lib.ref_create())
+        vp = ctypes.c_void_p
+        self.f_err = self._fn("last_error", ctypes.c_char_p, [vp])
+        self.f_threads = self._fn("set_threads", None, [ctypes.c_int])
+        self.f_max_threads = self._fn("max_threads", ctypes.c_int, [])
+        self.f_set = self._fn("set_sequences", ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_char_p, _u64p, _u32p, _f32p, _u8p])
+        self.f_active = self._fn("set_active", ctypes.c_int, [vp, _u8p])
+        self.f_split = self._fn("split_sequence", ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32])
+        self.f_pack = self._fn("pack", ctypes.c_long, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_uint32,
+                                                      _u64p, _u32p, _i32p, _u32p])
+        self.f_select = self._fn("select_words", ctypes.c_long, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                                ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_uint32])
+        self.f_db_size = self._fn("db_size", ctypes.c_long, [vp])
+        self.f_num_keys = self._fn("num_keys", ctypes.c_long, [vp])
+        self.f_db_copy = self._fn("db_copy", None, [vp, _u64p, _u32p, _i32p, _u32p])
+        self.f_keys_copy = self._fn("keys_copy", None, [vp, _u64p])
+        self.f_db_set = self._fn("db_set", ctypes.c_int, [vp, ctypes.c_long, _u64p, _u32p, _i32p, _u32p])
+        self.f_score = self._fn("score_pairs", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                             ctypes.c_int, ctypes.c_int, _f32p, _u8p])
+        self.f_random = self._fn("random_assays", ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                                ctypes.c_int, ctypes.c_uint32, ctypes.c_float, _u64p, _u64p])
+        self.f_has_split = self._fn("has_split", ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_int])
+        self.f_thermo = self._fn("thermo", ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_float, ctypes.c_float,
+                                                          ctypes.c_float, _f32p])
+        self.n_seq = 0
+
+    def set_threads(self, n):
+        self.f_threads(int(n))
+
+    def max_threads(self):
+        return int(self.f_max_threads())
+
+    def set_sequences(self, coll, active=None):
+        self.n_seq = coll.n
+        texts = [coll.text(i) for i in range(coll.n)]
+        off = np.zeros(coll.n, np.uint64)
+        ln = np.array([len(t) for t in texts], np.uint32)
+        if coll.n:
+            off[1:] = np.cumsum(ln.astype(np.uint64))[:-1]
+        blob = "".join(texts).encode()
+        a = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
+        rc = self.f_set(self.h, coll.n, blob, _p(off, _u64p), _p(ln, _u32p), _p(coll.weight, _f32p), _p(a, _u8p))
+        assert rc == 0, self.f_err(self.h)
+
+    def set_active(self, active):
+        a = np.ascontiguousarray(active, dtype=np.uint8)
+        self.f_active(self.h, _p(a, _u8p))
+
+    def split_sequence(self, seq, pos):
+        self.f_split(self.h, seq, pos)
+
+    def pack(self, seq, pack_max_degen=256, min_gc=0.0, max_gc=1.0, min_len=18):
+        n = self.f_pack(self.h, seq, pack_max_degen, min_gc, max_gc, min_len, None, None, None, None)
+        assert n >= 0, self.f_err(self.h)
+        words = np.zeros((n, 2), np.uint64)
+        index = np.zeros(n, np.uint32)
+        loc = np.zeros(n, np.int32)
+        strand = np.zeros(n, np.uint32)
+        self.f_pack(self.h, seq, pack_max_degen, min_gc, max_gc, min_len, _p(words, _u64p), _p(index, _u32p), _p(loc, _i32p), _p(strand, _u32p))
+        return canonical(words, index, loc, strand)
+
+    def select_words(self, f, r, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0,
+                     min_oligo_length=18):
+        f, r = _w(f), _w(r)
+        n = self.f_select(self.h, len(f), _p(f, _u64p), _p(r, _u64p), int(optimize_5), int(optimize_3), threshold, pack_max_degen, pack_min_gc,
+                          pack_max_gc, min_oligo_length)
+        assert n >= 0, self.f_err(self.h)
+        return n, self.f_num_keys(self.h)
+
+    def db(self):
+        n = self.f_db_size(self.h)
+        words = np.zeros((n, 2), np.uint64)
+        index = np.zeros(n, np.uint32)
+        loc = np.zeros(n, np.int32)
+        strand = np.zeros(n, np.uint32)
+        if n:
+            self.f_db_copy(self.h, _p(words, _u64p), _p(index, _u32p), _p(loc, _i32p), _p(strand, _u32p))
+        return canonical(words, index, loc, strand)
+
+    def keys(self):
+        n = self.f_num_keys(self.h)
+        k = np.zeros((n, 2), np.uint64)
+        if n:
+            self.f_keys_copy(self.h, _p(k, _u64p))
+        return k
+
+    def db_set(self, words, index, loc, strand):
+        words = _w(words)
+        index = np.ascontiguousarray(index, np.uint32)
+        loc = np.ascontiguousarray(loc, np.int32)
+        strand = np.ascontiguousarray(strand, np.uint32)
+        assert self.f_db_set(self.h, len(index), _p(words, _u64p), _p(index, _u32p), _p(loc, _i32p), _p(strand, _u32p)) == 0
+
+    def score_pairs(self, f, r, target_threshold, search_multiplier, amp_min=80, amp_max=200, taq=False, want_cov=True, want_bits=True):
+        """coverage: optimize()'s first score (search = thr*mult, detect = thr); bits: find_target_match (search = detect = thr)."""
+        f, r = _w(f), _w(r)
+        cov = np.zeros(len(f), np.float32)
+        bits = np.zeros((len(f), self.n_seq), np.uint8)
+        rc = self.f_score(self.h, len(f), _p(f, _u64p), _p(r, _u64p), target_threshold, search_multiplier, amp_min, amp_max, int(taq),
+                          _p(cov, _f32p) if want_cov else None, _p(bits, _u8p) if want_bits else None)
+        assert rc == 0, self.f_err(self.h)
+        return cov, bits
+
+    def random_assays(self, n_pairs, seed, primer_range=(18, 25), amp_range=(80, 200), degen=1, salt=0.05):
+        f = np.zeros((n_pairs, 2), np.uint64)
+        r = np.zeros((n_pairs, 2), np.uint64)
+        rc = self.f_random(self.h, n_pairs, seed, primer_range[0], primer_range[1], amp_range[0], amp_range[1], degen, salt, _p(f, _u64p),
+                           _p(r, _u64p))
+        assert rc == 0, self.f_err(self.h)
+        return f, r
+
+    def has_split(self, seq, loc, length):
+        return self.f_has_split(self.h, seq, loc, length)
+
+    def thermo(self, op, a, b="", salt=0.05, strand_a=9e-7, strand_b=9e-7):
+        out = np.zeros(5, np.float32)
+        rc = self.f_thermo(op, a.encode(), b.encode(), salt, strand_a, strand_b, _p(out, _f32p))
+        assert rc == 0
+        return out

@@ -1,0 +1,172 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs and
+against the golden vectors produced by the unmodified reference.  Bit-exact everywhere: binding-site
+databases, keys, amplified-target bitsets and float coverages."""
+import os
+
+import numpy as np
+import pytest
+
+from pcramp_b200 import TARGET, BACKGROUND, synth
+from pcramp_b200.api import unpack_bits
+from tests import scenarios
+from tests.harness import canonical
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SCENARIOS = {fn.__name__[2:]: fn for fn in scenarios.ALL}
+
+
+class GpuChecker:
+    """adapts PcrampGpu to the checker surface scenarios.run_checker drives"""
+
+    def __init__(self, gpu, kind=TARGET):
+        self.g = gpu
+        self.kind = kind
+        self.n_seq = 0
+
+    def set_sequences(self, coll, active=None):
+        self.n_seq = coll.n
+        self.g.upload_sequences(self.kind, coll.nibbles, coll.byte_off, coll.length, coll.weight)
+        if active is not None:
+            self.g.set_active(self.kind, active)
+
+    def split_sequence(self, seq, pos):
+        self.g.split_sequence(self.kind, seq, pos)
+
+    def pack(self, seq, pack_max_degen, min_gc, max_gc, min_len):
+        w, loc, st = self.g.pack(self.kind, seq, pack_max_degen, min_gc, max_gc, min_len)
+        return canonical(w, np.full(len(loc), seq, np.uint32), loc, st)
+
+    def select_words(self, f, r, threshold, **kw):
+        return self.g.select_words(self.kind, f, r, threshold, **kw)
+
+    def db(self):
+        w, idx, loc, st, key = self.g.db_copy(self.kind)
+        self.last_key_index = key
+        return w, idx, loc, st
+
+    def keys(self):
+        return self.g.keys_copy(self.kind)
+
+    def score_pairs(self, f, r, search, detect, amp_min, amp_max, taq):
+        cov, bits = self.g.score_pairs(self.kind, f, r, search, detect, amp_min, amp_max, taq)
+        return cov, unpack_bits(bits, self.n_seq)
+
+
+def compare(got, want, what):
+    assert sorted(got) == sorted(want), what
+    for k in want:
+        a, b = got[k], want[k]
+        assert a.shape == b.shape, "%s: %s shape %s vs %s" % (what, k, a.shape, b.shape)
+        assert np.array_equal(a, b), "%s: %s differs" % (what, k)
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_scenario_vs_oracle_and_golden(gpu, oracle, name):
+    sc = SCENARIOS[name]()
+    got = scenarios.run_checker(GpuChecker(gpu), sc, "gpu")
+    want = scenarios.run_checker(oracle, sc, "oracle")
+    compare(got, want, name + " vs oracle")
+    gold = np.load(os.path.join(GOLD, "scenario_%s.npz" % name))
+    compare(got, {k: gold[k] for k in gold.files}, name + " vs reference golden")
+
+
+@pytest.mark.parametrize("name", ["basic", "repeats", "shift"])
+def test_db_is_sorted_and_keys_are_consistent(gpu, name):
+    sc = SCENARIOS[name]()
+    chk = GpuChecker(gpu)
+    chk.set_sequences(sc.coll, sc.active)
+    chk.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+    w, idx, loc, st, key = gpu.db_copy(TARGET)
+    keys = gpu.keys_copy(TARGET)
+    order = np.lexsort((st, loc, idx, w[:, 1], w[:, 0]))
+    assert np.array_equal(order, np.arange(len(order)))          # delivered in canonical order
+    assert np.array_equal(keys[key], w)                          # key_index points at the entry's word
+    uniq = np.unique(w, axis=0)
+    assert len(uniq) == len(keys) and np.array_equal(np.unique(keys, axis=0), uniq)
+    assert np.all((keys[1:, 0] > keys[:-1, 0]) | ((keys[1:, 0] == keys[:-1, 0]) & (keys[1:, 1] > keys[:-1, 1])))  # keys() order
+
+
+def test_background_kind_and_independent_collections(gpu, oracle):
+    """targets and backgrounds live side by side in one context (main.cpp keeps three deques)"""
+    t = SCENARIOS["basic"]()
+    b = SCENARIOS["lowthr"]()
+    gt, gb = GpuChecker(gpu, TARGET), GpuChecker(gpu, BACKGROUND)
+    gt.set_sequences(t.coll)
+    gb.set_sequences(b.coll)
+    gb.select_words(b.f, b.r, float(b.threshold), **b.select_kwargs())
+    gt.select_words(t.f, t.r, float(t.threshold), **t.select_kwargs())
+    for sc, g in ((t, gt), (b, gb)):
+        oracle.set_sequences(sc.coll)
+        oracle.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+        for a, c in zip(g.db(), oracle.db()):
+            assert np.array_equal(a, c)
+        cov_o, bits_o = oracle.score_pairs(sc.f, sc.r, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+        cov_g, bits_g = g.score_pairs(sc.f, sc.r, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+        assert np.array_equal(cov_g, cov_o) and np.array_equal(bits_g, bits_o)
+
+
+def test_medium_random_vs_oracle(gpu, oracle):
+    """a few hundred kb with several tiles per sequence, more pairs than one pattern chunk holds"""
+    coll = synth.make_targets(501, 40, 5000, n_clades=4, between=0.15, within=0.05)
+    f, r = synth.make_pairs(502, coll, 300)
+    thr = float(np.float32(1.0) * np.float32(0.9))
+    g = GpuChecker(gpu)
+    g.set_sequences(coll)
+    oracle.set_sequences(coll)
+    ne, nk = g.select_words(f, r, thr)
+    no, nko = oracle.select_words(f, r, thr)
+    assert (ne, nk) == (no, nko) and ne > 1000
+    for a, c in zip(g.db(), oracle.db()):
+        assert np.array_equal(a, c)
+    assert np.array_equal(g.keys(), oracle.keys())
+    for search, detect in ((thr, 1.0), (1.0, 1.0), (thr, 0.9)):
+        cov_o, bits_o = oracle.score_pairs(f, r, search, detect, 80, 200, False)
+        cov_g, bits_g = g.score_pairs(f, r, search, detect, 80, 200, False)
+        assert np.array_equal(bits_g, bits_o) and np.array_equal(cov_g, cov_o)
+    st = gpu.stats()
+    assert st["n_patterns"] == 4 * 300 and st["n_positions"] == 40 * 5000 and st["kernel_launches"] > 0
+
+
+def test_staged_path_equals_host_pointer_path(gpu):
+    sc = SCENARIOS["basic"]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll)
+    g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+    cov_a, bits_a = gpu.score_pairs(TARGET, sc.f, sc.r, sc.search_threshold, 1.0)
+    gpu.stage_pairs(sc.f, sc.r)
+    gpu.select_words_staged(TARGET, float(sc.threshold), **sc.select_kwargs())
+    gpu.score_pairs_staged(TARGET, sc.search_threshold, 1.0)
+    cov_b, bits_b = gpu.fetch_results(TARGET)
+    assert np.array_equal(cov_a, cov_b) and np.array_equal(bits_a, bits_b)
+
+
+def test_properties_at_scale(gpu):
+    """size-independent properties on an input too large for the CPU oracle: every pair was cut from one of
+    the targets, so (i) its source sequence must be amplified at threshold 0.9 search / 1.0 detect exactly when
+    the primers match it perfectly -- they do, by construction; (ii) scoring is independent of batch
+    composition for the bitset of find_target_match when the DB is rebuilt per batch from the same pairs;
+    (iii) coverage == popcount(bitset) for unit weights."""
+    n, L, P = 400, 30000, 256
+    coll = synth.make_targets(601, n, L, n_clades=8, between=0.15, within=0.05)
+    f, r = synth.make_pairs(602, coll, P)
+    thr = float(np.float32(1.0) * np.float32(0.9))
+    gpu.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
+    gpu.select_words(TARGET, f, r, thr)
+    cov, bits = gpu.score_pairs(TARGET, f, r, 1.0, 1.0)
+    b = unpack_bits(bits, n)
+    assert np.array_equal(cov, b.sum(axis=1).astype(np.float32))
+    assert (b.sum(axis=1) >= 1).all()            # each pair amplifies at least the sequence it was cut from
+    # the same pairs in reverse order give the same rows
+    gpu.select_words(TARGET, f[::-1].copy(), r[::-1].copy(), thr)
+    cov2, bits2 = gpu.score_pairs(TARGET, f[::-1].copy(), r[::-1].copy(), 1.0, 1.0)
+    assert np.array_equal(bits2[::-1], bits) and np.array_equal(cov2[::-1], cov)
+    # deactivating the sequences a pair amplifies removes exactly those bits
+    active = np.ones(n, np.uint8)
+    active[b[0].astype(bool)] = 0
+    gpu.set_active(TARGET, active)
+    gpu.select_words(TARGET, f, r, thr)
+    cov3, bits3 = gpu.score_pairs(TARGET, f, r, 1.0, 1.0)
+    b3 = unpack_bits(bits3, n)
+    assert b3[0].sum() == 0 and np.array_equal(b3, b * active[None, :])
