@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- primer-pair x target evaluations/s of the B200 scoring path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU code (oracle/_ref) on host cores
+
+Workload (BASELINE.json config 5, the one the headline target is quoted on): fixed candidate primer pairs in
+batches of --pairs (the reference's num_trial, default 1000) against --targets x --length synthetic viral
+targets (20 clades, 15 % between / 5 % within).  One step = one batch through the
+whole hot path: seed scan (Sequence::pack + select_words over every active target, sort, keys) and pair scoring
+(collect_candidates, identity, coverage, amplified-target bitsets).  One evaluation = one (pair, target)
+decision.  With N > 1 the targets are sharded over the ranks (strong scaling: the collection is fixed),
+every rank scores the same batch on its shard, and NCCL all-gathers the shard bitsets, which are spliced
+into global bitsets + coverages on every rank (include/pcramp_gpu.h: pcramp_gpu_merge_shards).
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "primer_pair_x_target_evaluations_per_s"
+UNIT = "evaluations/s"
+SEARCH_MULT = np.float32(0.9)   # DEFAULT_SEARCH_THRESHOLD_MULTIPLIER (pcramp.h:51)
+TARGET_THR = np.float32(1.0)    # DEFAULT_TARGET_THRESHOLD (pcramp.h:36)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--targets", type=int, default=20000)
+    ap.add_argument("--length", type=int, default=30000)
+    ap.add_argument("--clades", type=int, default=20)
+    ap.add_argument("--pairs", type=int, default=1000)
+    ap.add_argument("--cpu-targets", type=int, default=96, help="targets in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("C5 sweep: batches of %d fixed primer pairs (18-25 nt, amplicon 80-200 nt) vs %d x %d nt synthetic viral targets "
+            "(%d clades, 15%%/5%% divergence); step = seed scan + pair scoring of one batch" % (a.pairs, a.targets, a.length, a.clades))
+
+
+def make_factory(a):
+    from pcramp_b200 import synth
+    return synth.TargetFactory(3, a.targets, a.length, n_clades=a.clades, between=0.15, within=0.05)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                power.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle/_ref when the compiled reference travelled, else the port)
+# --------------------------------------------------------------------------------------------------
+def cpu_checker():
+    from tests.harness import RefLib, OracleLib, REF_PATH
+    if os.path.exists(REF_PATH):
+        chk = RefLib()
+        chk.set_threads(0)  # all host threads (the reference's --thread default)
+        return chk, "reference", chk.max_threads()
+    return OracleLib(), "port", 1
+
+
+def cpu_step(chk, kind, sample, f, r):
+    thr = float(TARGET_THR * SEARCH_MULT)
+    chk.select_words(f, r, thr)
+    if kind == "reference":
+        chk.score_pairs(f, r, float(TARGET_THR), float(SEARCH_MULT), 80, 200, False, want_cov=True, want_bits=False)
+    else:
+        chk.score_pairs(f, r, thr, float(TARGET_THR), 80, 200, False)
+
+
+def cpu_sample(a, factory, n_targets):
+    stride = max(1, a.targets // n_targets)
+    idx = [i * stride for i in range(n_targets)]
+    return factory.collection(idx), idx
+
+
+def run_reference(a):
+    from pcramp_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    factory = make_factory(a)
+    chk, kind, cores = cpu_checker()
+    n_t = max(8, a.cpu_targets // 2)
+    sample, _ = cpu_sample(a, factory, n_t)
+    chk.set_sequences(sample)
+    total = a.steps + a.warmup
+    f, r = synth.make_pairs(5, factory, a.pairs * total)
+    for s in range(a.warmup):
+        cpu_step(chk, kind, sample, f[s * a.pairs:(s + 1) * a.pairs], r[s * a.pairs:(s + 1) * a.pairs])
+    t0 = time.perf_counter()
+    for s in range(a.warmup, total):
+        cpu_step(chk, kind, sample, f[s * a.pairs:(s + 1) * a.pairs], r[s * a.pairs:(s + 1) * a.pairs])
+    dt = time.perf_counter() - t0
+    value = a.pairs * n_t * a.steps / dt
+    sample_desc = "%d pairs x %d of the %d targets per step (every %d-th target); throughput is per (pair, target), the loop is linear in targets" % (
+        a.pairs, n_t, a.targets, max(1, a.targets // n_t))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": {"workload": workload_name(a), "targets": a.targets, "target_len": a.length, "pairs_per_step": a.pairs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# --------------------------------------------------------------------------------------------------
+# this repository's CUDA path
+# --------------------------------------------------------------------------------------------------
+class DevArray:
+    """zero-copy torch view of a device pointer owned by the C library"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2}
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from pcramp_b200 import PcrampGpu, TARGET, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (a.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    factory = make_factory(a)
+    bounds = [a.targets * k // world for k in range(world + 1)]   # contiguous shards
+    shard_nseq = np.array([bounds[k + 1] - bounds[k] for k in range(world)], dtype=np.uint32)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    coll = factory.collection(range(lo, hi))
+    total = a.steps + a.warmup
+    n_batches = total + a.steps + 1                                # resident (warm-up + timed) then e2e (1 warm-up + timed)
+    f_all, r_all = synth.make_pairs(5, factory, a.pairs * n_batches)
+    f_pin = torch.from_numpy(f_all.view(np.int64)).pin_memory()
+    r_pin = torch.from_numpy(r_all.view(np.int64)).pin_memory()
+    f_host, r_host = f_pin.numpy().view(np.uint64), r_pin.numpy().view(np.uint64)
+
+    g = PcrampGpu(local)
+    g.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
+    ext = torch.cuda.ExternalStream(g.stream, device=local)
+    thr = float(TARGET_THR * SEARCH_MULT)
+    n_words_local = (int(shard_nseq[rank]) + 31) // 32
+    n_words_global = (a.targets + 31) // 32
+    P = a.pairs
+    if world > 1:
+        max_words = int(max((int(n) + 31) // 32 for n in shard_nseq))
+        gat_any = torch.zeros((world, P * max_words), dtype=torch.int32, device="cuda")
+        gat_p1 = torch.zeros((world, P * max_words), dtype=torch.int32, device="cuda")
+        packed_any = torch.zeros(int(sum(P * ((int(n) + 31) // 32) for n in shard_nseq)), dtype=torch.int32, device="cuda")
+        packed_p1 = torch.zeros_like(packed_any)
+        out_bits = torch.zeros((P, n_words_global), dtype=torch.int32, device="cuda")
+        out_cov = torch.zeros(P, dtype=torch.float32, device="cuda")
+    host_cov = torch.zeros(P, dtype=torch.float32).pin_memory()
+    host_bits = torch.zeros((P, n_words_global), dtype=torch.int32).pin_memory()
+    launches = [0]
+    stats_acc = {"ms_scan": 0.0, "ms_edge": 0.0, "ms_db": 0.0, "ms_score": 0.0, "n_entries": 0, "n_hits": 0, "scan_launches": 0}
+    last = {}
+
+    def exchange():
+        """NCCL: all-gather the shard bitsets, then splice + re-sum on every rank"""
+        d_cov, d_any, d_p1 = g.device_pointers()
+        my_any = torch.as_tensor(DevArray(d_any, (P * n_words_local,), "<i4"), device="cuda")
+        my_p1 = torch.as_tensor(DevArray(d_p1, (P * n_words_local,), "<i4"), device="cuda")
+        gat_any[rank, :P * n_words_local].copy_(my_any)
+        gat_p1[rank, :P * n_words_local].copy_(my_p1)
+        dist.all_gather_into_tensor(gat_any.view(-1), gat_any[rank].clone())
+        dist.all_gather_into_tensor(gat_p1.view(-1), gat_p1[rank].clone())
+        o = 0
+        for s in range(world):   # drop the padding so shard s holds exactly P x words_s words
+            n = P * ((int(shard_nseq[s]) + 31) // 32)
+            packed_any[o:o + n].copy_(gat_any[s, :n])
+            packed_p1[o:o + n].copy_(gat_p1[s, :n])
+            o += n
+        torch.cuda.current_stream().synchronize()
+        g.merge_shards(packed_any.data_ptr(), packed_p1.data_ptr(), shard_nseq, P, out_bits.data_ptr(), out_cov.data_ptr())
+        launches[0] += 1
+
+    def account(timed):
+        st = g.stats()
+        last.update(st)
+        if timed:
+            launches[0] += st["kernel_launches"]
+            for k in ("ms_scan", "ms_edge", "ms_db", "ms_score"):
+                stats_acc[k] += st[k]
+            stats_acc["n_entries"] += st["n_entries"]
+            stats_acc["n_hits"] += st["n_hits"]
+            stats_acc["scan_launches"] += 1
+
+    def step_resident(b, timed):
+        g.set_batch(b * P, P)
+        g.select_words_staged(TARGET, thr)
+        g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
+        account(timed)
+        if world > 1:
+            exchange()
+
+    def step_e2e(b, timed):
+        fb, rb = f_host[b * P:(b + 1) * P], r_host[b * P:(b + 1) * P]
+        if world == 1:
+            g.select_words(TARGET, fb, rb, thr)
+            cov, bits = g.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR))
+            host_cov.numpy()[:] = cov
+            host_bits.numpy().view(np.uint32)[:] = bits
+        else:
+            g.stage_pairs(fb, rb)
+            g.select_words_staged(TARGET, thr)
+            g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
+            exchange()
+            host_cov.copy_(out_cov, non_blocking=True)
+            host_bits.copy_(out_bits, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, first_batch, n_steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for s in range(n_steps):
+            fn(first_batch + s, True)
+        e1.record(ext)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.cuda.stream(ext):
+        g.stage_pairs(f_all, r_all)                      # every batch resident in HBM before the timed region
+        for s in range(a.warmup):
+            step_resident(s, False)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms_resident = timed_region(step_resident, a.warmup, a.steps)
+        launches_resident = launches[0]
+        step_e2e(total, False)
+        launches[0] = 0
+        ms_e2e = timed_region(step_e2e, total + 1, a.steps)
+        clocks = sampler.stop() if rank == 0 else None
+        int_peak = g.measure_int_peak() if rank == 0 else 0.0
+
+    evals_per_step = float(P) * a.targets
+    value = evals_per_step * a.steps / (ms_resident * 1e-3)
+    e2e_value = evals_per_step * a.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        n_scan = max(1, stats_acc["scan_launches"])
+        scan_ms = stats_acc["ms_scan"] / n_scan
+        n_cand = last["n_patterns"] // 2
+        # nibbles of the active sequences + 16 B per candidate + 28 B per emitted entry
+        alg_bytes = float(sum((int(L) + 1) // 2 for L in coll.length)) + 16.0 * n_cand + 28.0 * stats_acc["n_entries"] / n_scan
+        achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        align_per_launch = float(last["n_patterns"]) * float(last["n_positions"])
+        align_rate = align_per_launch / (scan_ms * 1e-3) if scan_ms > 0 else 0.0
+        roofline = {
+            "kernel": "scan_full_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": None,
+            "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms, "share_of_step": stats_acc["ms_scan"] / ms_resident,
+            "note": "the scan is integer-issue bound (4 LOP3 + POPC + ISETP per alignment x %d patterns per template position), not HBM "
+                    "bound: see `issue`" % last["n_patterns"],
+            "issue": {"unit": "alignments/s", "achieved": align_rate, "peak": int_peak,
+                      "frac": (align_rate / int_peak) if int_peak else None,
+                      "peak_source": "measured live (pcramp_gpu_measure_int_peak: the scan's own instruction mix from registers)",
+                      "alignments_per_launch": align_per_launch},
+        }
+        cpu_baseline = None
+        if world == 1 and not a.no_cpu_baseline:
+            chk, kind, cores = cpu_checker()
+            sample, _ = cpu_sample(a, factory, a.cpu_targets)
+            chk.set_sequences(sample)
+            fb, rb = f_all[:P], r_all[:P]
+            t0 = time.perf_counter()
+            cpu_step(chk, kind, sample, fb, rb)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": P * a.cpu_targets / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
+                            "sample": "one step of %d pairs x %d of the %d targets (every %d-th target)" % (
+                                P, a.cpu_targets, a.targets, max(1, a.targets // a.cpu_targets))}
+        h2d = 2 * P * 16
+        d2h = P * 4 + P * n_words_global * 4
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_resident / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "targets": a.targets, "target_len": a.length, "pairs_per_step": P,
+                       "seed_threshold": thr, "detect_threshold": float(TARGET_THR), "sharding": "targets, contiguous, %d shard(s)" % world,
+                       "l2": "inputs larger than L2 (%.0f MB of bit-planes per GPU)" % (coll.length.sum() / 2e6),
+                       "db_entries_per_step": stats_acc["n_entries"] / n_scan, "hits_per_step": stats_acc["n_hits"] / n_scan},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_resident,
+            "breakdown_ms_per_step": {k: stats_acc[k] / n_scan for k in ("ms_scan", "ms_edge", "ms_db", "ms_score")},
+            "roofline": roofline, "cpu_baseline": cpu_baseline}))
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,9 @@ int pcramp_gpu_score_pairs(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, con
 /* ---- resident variants: the same two steps with the pairs already staged in HBM and the results
  *      left in HBM (what a multi-batch driver, the NCCL exchange and bench.py's `value` use). -------- */
 int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs);
+/* Select the window [first, first+count) of the staged pairs as the current batch (a "design iteration" worth
+ * of trials, main.cpp:523-558) without touching the host. */
+int pcramp_gpu_set_batch(pcramp_gpu_ctx *ctx, uint32_t first, uint32_t count);
 int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int optimize_5, int optimize_3, float threshold,
 	uint32_t pack_max_degen, float pack_min_gc, float pack_max_gc, uint32_t min_oligo_length,
 	uint64_t *n_entries, uint64_t *n_keys);
@@ -97,8 +100,20 @@ int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_th
 /* device pointers of the last staged results: coverage float[n_pairs], bitsets uint32[n_pairs*words] */
 void *pcramp_gpu_device_coverage(pcramp_gpu_ctx *ctx);
 void *pcramp_gpu_device_bitsets(pcramp_gpu_ctx *ctx);
+/* bitsets of the sequences detected by the {F(+), R(-)} pass alone (pcr_assay.cpp:37-47); with the bitsets above
+ * they fix the order compute_coverage sums weights in, which the multi-GPU merge needs to stay bit-exact */
+void *pcramp_gpu_device_bitsets_pass1(pcramp_gpu_ctx *ctx);
 uint32_t pcramp_gpu_bitset_words(pcramp_gpu_ctx *ctx, int kind);
 int pcramp_gpu_fetch_results(pcramp_gpu_ctx *ctx, float *coverage, uint32_t *bitsets);
+
+/* ---- multi-GPU: replaces reduce_best_assay's gather of BitSets (main.cpp:1421-1601) --------------------
+ * Sequences are sharded across ranks in contiguous index ranges; every rank scores the same pairs on its
+ * shard.  After the caller has all-gathered the shards' device bitsets (NCCL, rank-major), this splices
+ * them into global bitsets (n_pairs x ceil(sum(shard_nseq)/32)) and re-sums the coverage over all
+ * sequences in the reference's order.  All d_* are device pointers; shard_nseq/weight_all are host. */
+int pcramp_gpu_merge_shards(pcramp_gpu_ctx *ctx, const void *d_any_gathered, const void *d_pass1_gathered,
+	uint32_t n_shards, const uint32_t *shard_nseq, const float *weight_all, uint32_t n_pairs, void *d_out_bits,
+	void *d_out_cov);
 
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* Counters of the last select_words / score_pairs call on this ctx. */
@@ -115,6 +130,8 @@ typedef struct pcramp_gpu_stats {
 	float ms_score;           /* ... of the pair-scoring kernels */
 } pcramp_gpu_stats;
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
+/* Issue-bound ceiling of the scan's own instruction mix on this GPU (alignments/s), measured live. */
+int pcramp_gpu_measure_int_peak(pcramp_gpu_ctx *ctx, double *alignments_per_s);
 
 /* ---- host-side word helpers (word.h / word.cpp), for building candidate lists ------------------- */
 void pcramp_word_from_string(const char *iupac, int centre, uint64_t out[2]);

@@ -64,12 +64,17 @@ SIGNATURES = {
     "pcramp_gpu_score_pairs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _u32p]),
     "pcramp_gpu_stage_pairs": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32]),
+    "pcramp_gpu_set_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]),
     "pcramp_gpu_select_words_staged": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_uint32,
                                                       ctypes.c_float, ctypes.c_float, ctypes.c_uint32, _u64p, _u64p]),
     "pcramp_gpu_score_pairs_staged": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                      ctypes.c_int]),
     "pcramp_gpu_device_coverage": (ctypes.c_void_p, [ctypes.c_void_p]),
     "pcramp_gpu_device_bitsets": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "pcramp_gpu_device_bitsets_pass1": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "pcramp_gpu_merge_shards": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, _u32p, _f32p, ctypes.c_uint32,
+                                               ctypes.c_void_p, ctypes.c_void_p]),
+    "pcramp_gpu_measure_int_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "pcramp_gpu_bitset_words": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_int]),
     "pcramp_gpu_fetch_results": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
     "pcramp_gpu_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
@@ -123,6 +128,7 @@ class PcrampGpu:
         self.h = h
         self.n_seq = {}
         self.n_pairs = 0
+        self._db = {}
 
     def close(self):
         if getattr(self, "h", None):
@@ -186,11 +192,11 @@ class PcrampGpu:
                                                   float(threshold), int(pack_max_degen), float(pack_min_gc), float(pack_max_gc),
                                                   int(min_oligo_length), ctypes.byref(ne), ctypes.byref(nk)))
         self.n_pairs = len(f)
-        self._db = (ne.value, nk.value)
+        self._db[kind] = (ne.value, nk.value)
         return ne.value, nk.value
 
     def db_copy(self, kind):
-        ne, nk = self._db
+        ne, nk = self._db[kind]
         words = np.zeros((ne, 2), np.uint64)
         index = np.zeros(ne, np.uint32)
         loc = np.zeros(ne, np.int32)
@@ -201,7 +207,7 @@ class PcrampGpu:
         return words, index, loc, strand, key
 
     def keys_copy(self, kind):
-        ne, nk = self._db
+        ne, nk = self._db[kind]
         keys = np.zeros((nk, 2), np.uint64)
         self._ck(self.lib.pcramp_gpu_keys_copy(self.h, kind, _ptr(keys, _u64p)))
         return keys
@@ -224,13 +230,17 @@ class PcrampGpu:
         self._ck(self.lib.pcramp_gpu_stage_pairs(self.h, _ptr(f, _u64p), _ptr(r, _u64p), len(f)))
         self.n_pairs = len(f)
 
+    def set_batch(self, first, count):
+        self._ck(self.lib.pcramp_gpu_set_batch(self.h, int(first), int(count)))
+        self.n_pairs = int(count)
+
     def select_words_staged(self, kind, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0,
                             min_oligo_length=18):
         ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
         self._ck(self.lib.pcramp_gpu_select_words_staged(self.h, kind, int(optimize_5), int(optimize_3), float(threshold), int(pack_max_degen),
                                                          float(pack_min_gc), float(pack_max_gc), int(min_oligo_length), ctypes.byref(ne),
                                                          ctypes.byref(nk)))
-        self._db = (ne.value, nk.value)
+        self._db[kind] = (ne.value, nk.value)
         return ne.value, nk.value
 
     def score_pairs_staged(self, kind, search_threshold, detect_threshold, amplicon_min=80, amplicon_max=200, use_taq_mama=False):
@@ -245,7 +255,21 @@ class PcrampGpu:
         return cov, bits
 
     def device_pointers(self):
-        return self.lib.pcramp_gpu_device_coverage(self.h), self.lib.pcramp_gpu_device_bitsets(self.h)
+        """(coverage, bitsets, pass-1 bitsets) device addresses of the last staged scoring call"""
+        return (self.lib.pcramp_gpu_device_coverage(self.h), self.lib.pcramp_gpu_device_bitsets(self.h),
+                self.lib.pcramp_gpu_device_bitsets_pass1(self.h))
+
+    def merge_shards(self, d_any, d_pass1, shard_nseq, n_pairs, d_out_bits, d_out_cov, weight_all=None):
+        shard_nseq = np.ascontiguousarray(shard_nseq, dtype=np.uint32)
+        if weight_all is not None:
+            weight_all = np.ascontiguousarray(weight_all, dtype=np.float32)
+        self._ck(self.lib.pcramp_gpu_merge_shards(self.h, d_any, d_pass1, len(shard_nseq), _ptr(shard_nseq, _u32p), _ptr(weight_all, _f32p),
+                                                  int(n_pairs), d_out_bits, d_out_cov))
+
+    def measure_int_peak(self):
+        v = ctypes.c_double()
+        self._ck(self.lib.pcramp_gpu_measure_int_peak(self.h, ctypes.byref(v)))
+        return v.value
 
     def stats(self):
         s = Stats()

@@ -88,7 +88,10 @@ struct pcramp_gpu_ctx {
 	std::string err;
 	SeqSet sets[PCRAMP_NUM_KINDS];
 	// staged pairs + results
-	uint32_t n_pairs = 0, res_words = 0;
+	uint32_t n_pairs = 0, res_words = 0; // n_pairs = size of the current batch window
+	uint32_t n_staged = 0, batch_first = 0;
+	const uint64_t *pf() const { return d_f.as<uint64_t>() + 2ull * batch_first; }
+	const uint64_t *pr() const { return d_r.as<uint64_t>() + 2ull * batch_first; }
 	DevBuf d_f, d_r, d_oligos, d_cov, d_bits, d_bits1;
 	// candidates / patterns
 	DevBuf d_cand_cnt, d_cand_off, d_cand_words, d_cand_thr, d_pat_mask, d_pat_meta;
@@ -538,7 +541,8 @@ int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_
 {
 	if (!ctx) return 1;
 	CK(cudaSetDevice(ctx->device));
-	ctx->n_pairs = n_pairs;
+	ctx->n_pairs = ctx->n_staged = n_pairs;
+	ctx->batch_first = 0;
 	CK(ctx->d_f.ensure(std::max<size_t>(1, n_pairs) * 16));
 	CK(ctx->d_r.ensure(std::max<size_t>(1, n_pairs) * 16));
 	if (n_pairs) {
@@ -546,6 +550,15 @@ int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_
 		CK(cudaMemcpyAsync(ctx->d_r.p, r, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int pcramp_gpu_set_batch(pcramp_gpu_ctx *ctx, uint32_t first, uint32_t count)
+{
+	if (!ctx) return 1;
+	if ((uint64_t)first + count > ctx->n_staged) return fail(ctx, "pcramp_gpu_set_batch: window exceeds the staged pairs");
+	ctx->batch_first = first;
+	ctx->n_pairs = count;
 	return 0;
 }
 
@@ -586,7 +599,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	const uint32_t n_oligo = 2u * n_pairs;
 	CK(ctx->d_cand_cnt.ensure((size_t)n_oligo * 4));
 	CK(ctx->d_cand_off.ensure((size_t)n_oligo * 4));
-	cand_count_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->d_f.as<uint64_t>(), ctx->d_r.as<uint64_t>(), n_pairs, opt5, opt3,
+	cand_count_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->pf(), ctx->pr(), n_pairs, opt5, opt3,
 		ctx->d_cand_cnt.as<uint32_t>());
 	CK(cudaGetLastError());
 	stat.kernel_launches++;
@@ -605,7 +618,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(ctx->d_cand_thr.ensure((size_t)n_cand * 4));
 	CK(ctx->d_pat_mask.ensure((size_t)n_pat * 16));
 	CK(ctx->d_pat_meta.ensure((size_t)n_pat * 4));
-	cand_build_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->d_f.as<uint64_t>(), ctx->d_r.as<uint64_t>(), n_pairs, opt5, opt3, threshold,
+	cand_build_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->pf(), ctx->pr(), n_pairs, opt5, opt3, threshold,
 		ctx->d_cand_off.as<uint32_t>(), ctx->d_cand_words.as<uint64_t>(), ctx->d_cand_thr.as<uint32_t>(), ctx->d_pat_mask.as<uint4>(),
 		ctx->d_pat_meta.as<uint32_t>());
 	CK(cudaGetLastError());
@@ -862,7 +875,7 @@ int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_th
 	ctx->stats.ms_score = 0.0f;
 	if (n_pairs && s.n) {
 		const float thr2 = search_threshold * search_threshold; // pcr_assay.cpp:31-32 (float product)
-		prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(ctx->d_f.as<uint64_t>(), ctx->d_r.as<uint64_t>(), n_pairs, thr2,
+		prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(ctx->pf(), ctx->pr(), n_pairs, thr2,
 			ctx->d_oligos.as<OligoDev>());
 		CK(cudaGetLastError());
 		ctx->stats.kernel_launches++;
@@ -886,6 +899,130 @@ int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_th
 
 void *pcramp_gpu_device_coverage(pcramp_gpu_ctx *ctx) { return ctx->d_cov.p; }
 void *pcramp_gpu_device_bitsets(pcramp_gpu_ctx *ctx) { return ctx->d_bits.p; }
+void *pcramp_gpu_device_bitsets_pass1(pcramp_gpu_ctx *ctx) { return ctx->d_bits1.p; }
+
+// ---- multi-GPU: combine per-shard results -----------------------------------
+// Each rank scored the same pairs against its own contiguous shard of the sequences.  After the
+// all-gather of the shards' bitsets (rank-major: shard s holds n_pairs x words_s words), splice them
+// into one global LSB-first bitset per pair and recompute the coverage over ALL sequences in the
+// reference's order (pass-1 detections ascending, then pass-2-only ascending) from the global weights.
+__global__ void merge_shards_kernel(const uint32_t *__restrict__ any, const uint32_t *__restrict__ p1, uint32_t n_shards,
+	const uint32_t *__restrict__ shard_nseq, const uint64_t *__restrict__ shard_word_off, const uint32_t *__restrict__ shard_seq_off,
+	const float *__restrict__ weight, uint32_t n_pairs, uint32_t out_words, uint32_t *out_bits, float *out_cov)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_pairs) return;
+	uint32_t *ob = out_bits + (size_t)p * out_words;
+	for (uint32_t w = 0; w < out_words; ++w) ob[w] = 0u;
+	double acc = 0.0;
+	for (int pass = 0; pass < 2; ++pass) {
+		for (uint32_t s = 0; s < n_shards; ++s) {
+			const uint32_t ns = shard_nseq[s], ws = (ns + 31u) / 32u;
+			const uint32_t *a = any + shard_word_off[s] + (size_t)p * ws, *b = p1 + shard_word_off[s] + (size_t)p * ws;
+			for (uint32_t w = 0; w < ws; ++w) {
+				uint32_t m = pass == 0 ? b[w] : (a[w] & ~b[w]);
+				while (m) {
+					const uint32_t local = w * 32u + (uint32_t)(__ffs(m) - 1);
+					m &= m - 1u;
+					if (local >= ns) continue;
+					const uint32_t g = shard_seq_off[s] + local;
+					ob[g >> 5] |= 1u << (g & 31u);
+					acc = __dadd_rn(acc, (double)weight[g]);
+				}
+			}
+		}
+	}
+	out_cov[p] = (float)acc;
+}
+
+int pcramp_gpu_merge_shards(pcramp_gpu_ctx *ctx, const void *d_any_gathered, const void *d_pass1_gathered, uint32_t n_shards,
+	const uint32_t *shard_nseq, const float *weight_all, uint32_t n_pairs, void *d_out_bits, void *d_out_cov)
+{
+	if (!ctx) return 1;
+	CK(cudaSetDevice(ctx->device));
+	std::vector<uint64_t> woff(n_shards);
+	std::vector<uint32_t> soff(n_shards);
+	uint64_t wo = 0;
+	uint32_t so = 0;
+	for (uint32_t s = 0; s < n_shards; ++s) {
+		woff[s] = wo;
+		soff[s] = so;
+		wo += (uint64_t)n_pairs * ((shard_nseq[s] + 31u) / 32u);
+		so += shard_nseq[s];
+	}
+	DevBuf d_ns, d_wo, d_so, d_w;
+	CK(d_ns.ensure(n_shards * 4));
+	CK(d_wo.ensure(n_shards * 8));
+	CK(d_so.ensure(n_shards * 4));
+	CK(d_w.ensure(std::max<size_t>(1, so) * 4));
+	CK(cudaMemcpyAsync(d_ns.p, shard_nseq, n_shards * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(d_wo.p, woff.data(), n_shards * 8, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(d_so.p, soff.data(), n_shards * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (weight_all) CK(cudaMemcpyAsync(d_w.p, weight_all, (size_t)so * 4, cudaMemcpyHostToDevice, ctx->stream));
+	else {
+		std::vector<float> ones(so, 1.0f);
+		CK(cudaMemcpyAsync(d_w.p, ones.data(), (size_t)so * 4, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	merge_shards_kernel<<<grid_for(n_pairs, 128), 128, 0, ctx->stream>>>((const uint32_t *)d_any_gathered, (const uint32_t *)d_pass1_gathered,
+		n_shards, d_ns.as<uint32_t>(), d_wo.as<uint64_t>(), d_so.as<uint32_t>(), d_w.as<float>(), n_pairs, (so + 31u) / 32u,
+		(uint32_t *)d_out_bits, (float *)d_out_cov);
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->stats.kernel_launches++;
+	return 0;
+}
+
+// ---- measured integer-pipe peak: the denominator of the scan kernel's issue roofline ----------------
+// Each thread runs 8 independent chains of the scan's own instruction mix (4 LOP3 + POPC + compare per
+// alignment) on register-resident data, so the figure is "alignments/s if nothing but issue limits it".
+__global__ void __launch_bounds__(256, 2) int_peak_kernel(uint32_t iters, uint32_t seed, uint32_t *sink)
+{
+	uint32_t wa[8], wc[8], wg[8], wt[8];
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	#pragma unroll
+	for (int r = 0; r < 8; ++r) {
+		wa[r] = (t * 2654435761u) ^ (seed + r);
+		wc[r] = ~wa[r] & (t * 40503u + r);
+		wg[r] = (wa[r] >> 3) ^ 0x5a5a5a5au;
+		wt[r] = ~(wa[r] | wc[r] | wg[r]);
+	}
+	uint4 b = make_uint4(seed * 3u + 1u, seed * 5u + 2u, seed * 7u + 3u, seed * 11u + 4u);
+	uint32_t hits = 0;
+	for (uint32_t i = 0; i < iters; ++i) {
+		bool any = false;
+		#pragma unroll
+		for (int r = 0; r < 8; ++r) {
+			const uint32_t m = (b.x & wa[r]) | (b.y & wc[r]) | (b.z & wg[r]) | (b.w & wt[r]);
+			any |= (__popc(m) >= 31);
+		}
+		if (any) ++hits;
+		b.x = b.x * 1664525u + 1013904223u; // a new pattern every iteration (cheap, on the FMA pipe)
+		b.y += b.x;
+		b.z ^= b.y;
+		b.w -= b.z;
+	}
+	if (hits == 0xffffffffu) sink[t] = hits;
+}
+
+int pcramp_gpu_measure_int_peak(pcramp_gpu_ctx *ctx, double *alignments_per_s)
+{
+	if (!ctx || !alignments_per_s) return 1;
+	CK(cudaSetDevice(ctx->device));
+	DevBuf sink;
+	CK(sink.ensure(4));
+	const uint32_t iters = 200000;
+	const unsigned grid = (unsigned)ctx->sm_count * 2;
+	int_peak_kernel<<<grid, 256, 0, ctx->stream>>>(1000, 1u, sink.as<uint32_t>()); // warm-up
+	CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+	int_peak_kernel<<<grid, 256, 0, ctx->stream>>>(iters, 2u, sink.as<uint32_t>());
+	CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(ctx->stream));
+	const double s = ev_ms(ctx->ev[0], ctx->ev[1]) * 1e-3;
+	*alignments_per_s = (double)grid * 256.0 * 8.0 * (double)iters / s;
+	return 0;
+}
 
 int pcramp_gpu_fetch_results(pcramp_gpu_ctx *ctx, float *coverage, uint32_t *bitsets)
 {

@@ -61,16 +61,27 @@ class Collection:
         return Collection([self.codes(int(i)) for i in idx], w)
 
 
-def make_targets(seed, n, length, n_clades=1, between=0.0, within=0.03):
+class TargetFactory:
     """n sequences of `length` nt: a random root, `n_clades` clade ancestors at `between` divergence from it,
-    every sequence at `within` divergence from its clade ancestor (sequence i belongs to clade i % n_clades)."""
-    root = np.random.default_rng([seed, 0]).integers(0, 4, size=length, dtype=np.uint8)
-    clades = [_mutate(np.random.default_rng([seed, 1, c]), root, between) for c in range(n_clades)]
-    seqs = []
-    for i in range(n):
-        letters = _mutate(np.random.default_rng([seed, 2, i]), clades[i % n_clades], within)
-        seqs.append(CODE[letters])
-    return Collection(seqs)
+    every sequence at `within` divergence from its clade ancestor (sequence i belongs to clade i % n_clades).
+    Sequence i is a pure function of (seed, i), so shards and samples can be generated independently."""
+
+    def __init__(self, seed, n, length, n_clades=1, between=0.0, within=0.03):
+        self.seed, self.n, self.seq_len, self.n_clades, self.within = seed, n, length, n_clades, within
+        root = np.random.default_rng([seed, 0]).integers(0, 4, size=length, dtype=np.uint8)
+        self.clades = [_mutate(np.random.default_rng([seed, 1, c]), root, between) for c in range(n_clades)]
+        self.length = np.full(n, length, dtype=np.uint32)
+
+    def codes(self, i):
+        return CODE[_mutate(np.random.default_rng([self.seed, 2, int(i)]), self.clades[int(i) % self.n_clades], self.within)]
+
+    def collection(self, indices=None):
+        idx = range(self.n) if indices is None else indices
+        return Collection([self.codes(i) for i in idx])
+
+
+def make_targets(seed, n, length, n_clades=1, between=0.0, within=0.03):
+    return TargetFactory(seed, n, length, n_clades, between, within).collection()
 
 
 def word_from_codes(codes, centre=True):
@@ -106,6 +117,8 @@ def make_pairs(seed, coll, n_pairs, primer_range=(18, 25), amplicon_range=(80, 2
     such that the amplicon is 80-200 nt.  `degenerate_fraction` of the primers get one position widened to a
     two-letter IUPAC code (config C3's "degenerate primers")."""
     rng = np.random.default_rng([seed, 3])
+    if not isinstance(coll.length, np.ndarray):
+        raise TypeError("coll must be a Collection or a TargetFactory")
     f = np.zeros((n_pairs, 2), dtype=np.uint64)
     r = np.zeros((n_pairs, 2), dtype=np.uint64)
     t = 0
@@ -119,13 +132,7 @@ def make_pairs(seed, coll, n_pairs, primer_range=(18, 25), amplicon_range=(80, 2
             continue
         f_start = int(rng.integers(0, L - amp + 1))
         r_start = f_start + amp - r_len
-        o = int(coll.byte_off[i])
-        lo_b, hi_b = (f_start // 2), (f_start + amp + 1) // 2 + 1
-        b = coll.nibbles[o + lo_b:o + hi_b]
-        c = np.empty(2 * len(b), dtype=np.uint8)
-        c[0::2] = b >> 4
-        c[1::2] = b & 15
-        c = c[f_start - 2 * lo_b:f_start - 2 * lo_b + amp]
+        c = coll.codes(i)[f_start:f_start + amp]
         fc = c[:f_len].copy()
         rc = revcomp_codes(c[amp - r_len:]).copy()
         if (fc == 0).any() or (rc == 0).any():
