@@ -33,6 +33,9 @@ class Stats(ctypes.Structure):
         ("n_entries", ctypes.c_uint64),
         ("n_keys", ctypes.c_uint64),
         ("kernel_launches", ctypes.c_uint64),
+        ("n_seeded", ctypes.c_uint64),
+        ("n_seed_entries", ctypes.c_uint64),
+        ("ms_seed", ctypes.c_float),
         ("ms_scan", ctypes.c_float),
         ("ms_edge", ctypes.c_float),
         ("ms_db", ctypes.c_float),
@@ -77,6 +80,7 @@ SIGNATURES = {
     "pcramp_gpu_measure_int_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "pcramp_gpu_bitset_words": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_int]),
     "pcramp_gpu_fetch_results": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
+    "pcramp_gpu_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "pcramp_gpu_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
     "pcramp_word_from_string": (None, [ctypes.c_char_p, ctypes.c_int, _u64p]),
     "pcramp_word_to_string": (ctypes.c_int, [_u64p, ctypes.c_char_p]),
@@ -270,6 +274,9 @@ class PcrampGpu:
         v = ctypes.c_double()
         self._ck(self.lib.pcramp_gpu_measure_int_peak(self.h, ctypes.byref(v)))
         return v.value
+
+    def set_option(self, name, value):
+        self._ck(self.lib.pcramp_gpu_set_option(self.h, name.encode(), int(value)))
 
     def stats(self):
         s = Stats()

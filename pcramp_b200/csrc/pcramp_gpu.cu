@@ -54,6 +54,8 @@ struct SeqSet {
 	std::vector<std::vector<uint32_t>> eos; // per sequence, sorted raw positions
 	uint64_t raw_bytes = 0, n_groups = 0, n_tiles = 0;
 	DevBuf d_raw, d_raw_off, d_len, d_plen, d_clen, d_planes, d_grp_off, d_eos_pos, d_eos_off, d_weight, d_active, d_tile_seq, d_tile_x0;
+	DevBuf d_dirty_bits, d_dirty_seq, d_dirty_grp; // groups whose alignments read a degenerate base (scan.cuh)
+	uint32_t n_dirty = 0;
 	// database (seq-grouped order = entry-id order) + canonical permutation
 	uint64_t n_entries = 0, n_keys = 0;
 	bool db_valid = false;
@@ -94,7 +96,11 @@ struct pcramp_gpu_ctx {
 	const uint64_t *pr() const { return d_r.as<uint64_t>() + 2ull * batch_first; }
 	DevBuf d_f, d_r, d_oligos, d_cov, d_bits, d_bits1;
 	// candidates / patterns
-	DevBuf d_cand_cnt, d_cand_off, d_cand_words, d_cand_thr, d_pat_mask, d_pat_meta;
+	DevBuf d_cand_cnt, d_cand_off, d_cand_words, d_cand_thr, d_pat_mask, d_pat_meta, d_pat_meta2, d_pat_seeded, d_pat_sbefore;
+	DevBuf d_part_mask, d_part_meta, d_part_meta2; // seeded patterns first, brute-force patterns after
+	DevBuf d_seed_cnt, d_seed_start, d_seed_bucket, d_seed_entries, d_tile_counter;
+	int max_smem_optin = 0;
+	int force_brute = 0;
 	// scratch
 	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
 	unsigned long long *h_counters = nullptr; // pinned
@@ -223,35 +229,11 @@ __global__ void cand_count_kernel(const uint64_t *__restrict__ f, const uint64_t
 	cnt[i] = c;
 }
 
-__device__ inline void emit_candidate(const W128 &w, uint32_t cand, float threshold, uint64_t *cand_words, uint32_t *cand_thr,
-	uint4 *pat_mask, uint32_t *pat_meta)
-{
-	const int start = w_start(w), stop = w_stop(w);
-	const uint32_t thr = (uint32_t)__fmul_rn((float)w_size(w), threshold); // select_words.cpp:83
-	cand_words[2 * cand] = w.hi;
-	cand_words[2 * cand + 1] = w.lo;
-	cand_thr[cand] = thr;
-	uint4 mp = make_uint4(0, 0, 0, 0), mm = make_uint4(0, 0, 0, 0);
-	for (int k = 0; start + k <= stop; ++k) {
-		const uint32_t a = w_get(w, start + k); // plus strand: primer[k]
-		mp.x |= (a & 1u) << k;
-		mp.y |= ((a >> 1) & 1u) << k;
-		mp.z |= ((a >> 2) & 1u) << k;
-		mp.w |= ((a >> 3) & 1u) << k;
-		const uint32_t b = w_get(w, stop - k);  // minus strand: complement of primer read backwards
-		mm.x |= ((b >> 3) & 1u) << k;           // T -> A
-		mm.y |= ((b >> 2) & 1u) << k;           // G -> C
-		mm.z |= ((b >> 1) & 1u) << k;           // C -> G
-		mm.w |= (b & 1u) << k;                  // A -> T
-	}
-	pat_mask[2 * cand] = mp;
-	pat_meta[2 * cand] = pat_meta_pack(thr, (uint32_t)start, 0u, cand);
-	pat_mask[2 * cand + 1] = mm;
-	pat_meta[2 * cand + 1] = pat_meta_pack(thr, (uint32_t)(31 - stop), 1u, cand);
-}
-
+// one oligo -> its candidate family (cand_words / cand_thr, used by the partial-word kernel and for the hit
+// keys) and ONE pattern per strand (masks + meta), classified for the seed filter
 __global__ void cand_build_kernel(const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs, int opt5, int opt3,
-	float threshold, const uint32_t *__restrict__ off, uint64_t *cand_words, uint32_t *cand_thr, uint4 *pat_mask, uint32_t *pat_meta)
+	float threshold, const uint32_t *__restrict__ off, uint64_t *cand_words, uint32_t *cand_thr, uint4 *pat_mask, uint32_t *pat_meta,
+	uint32_t *pat_meta2, uint32_t *pat_seeded)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= 2u * n_pairs) return;
@@ -259,13 +241,69 @@ __global__ void cand_build_kernel(const uint64_t *__restrict__ f, const uint64_t
 	W128 w;
 	w.hi = src[2 * (i >> 1)];
 	w.lo = src[2 * (i >> 1) + 1];
-	uint32_t c = off[i];
-	emit_candidate(w, c++, threshold, cand_words, cand_thr, pat_mask, pat_meta);
-	const int start = w_start(w), stop = w_stop(w);
-	if (opt5 && start > 0 && start < 32)
-		for (int j = 1; j <= start; ++j) emit_candidate(w_shl(w, j), c++, threshold, cand_words, cand_thr, pat_mask, pat_meta);
-	if (opt3 && stop >= 0 && stop < 31)
-		for (int j = 1; j <= 31 - stop; ++j) emit_candidate(w_shr(w, j), c++, threshold, cand_words, cand_thr, pat_mask, pat_meta);
+	const int start = w_start(w), stop = w_stop(w), size = w_size(w);
+	const uint32_t thr = (uint32_t)__fmul_rn((float)size, threshold); // select_words.cpp:83 (same for the whole family)
+	const uint32_t base = off[i];
+	uint32_t c = base;
+	cand_words[2 * c] = w.hi; cand_words[2 * c + 1] = w.lo; cand_thr[c] = thr; ++c;
+	uint32_t nl = 0, nr = 0;
+	if (opt5 && start > 0 && start < 32) { // select_words.cpp:50-58
+		nl = (uint32_t)start;
+		for (int j = 1; j <= start; ++j, ++c) { const W128 v = w_shl(w, j); cand_words[2 * c] = v.hi; cand_words[2 * c + 1] = v.lo; cand_thr[c] = thr; }
+	}
+	if (opt3 && stop >= 0 && stop < 31) { // :61-70
+		nr = (uint32_t)(31 - stop);
+		for (int j = 1; j <= 31 - stop; ++j, ++c) { const W128 v = w_shr(w, j); cand_words[2 * c] = v.hi; cand_words[2 * c + 1] = v.lo; cand_thr[c] = thr; }
+	}
+	uint4 mp = make_uint4(0, 0, 0, 0), mm = make_uint4(0, 0, 0, 0);
+	for (int k = 0; start + k <= stop; ++k) {
+		const uint32_t a = w_get(w, start + k); // plus strand: primer[k]
+		mp.x |= (a & 1u) << k;
+		mp.y |= ((a >> 1) & 1u) << k;
+		mp.z |= ((a >> 2) & 1u) << k;
+		mp.w |= ((a >> 3) & 1u) << k;
+		const uint32_t b = w_get(w, stop - k);  // minus strand: complement of the primer read backwards
+		mm.x |= ((b >> 3) & 1u) << k;           // T -> A
+		mm.y |= ((b >> 2) & 1u) << k;           // G -> C
+		mm.z |= ((b >> 1) & 1u) << k;           // C -> G
+		mm.w |= (b & 1u) << k;                  // A -> T
+	}
+	// seed class: count >= thr leaves e = size - thr mismatches; e + 1 pieces of >= 5 (6) bases each
+	const uint32_t n = stop >= start ? (uint32_t)(stop - start + 1) : 0u;
+	uint32_t e = 0, cls = 0;
+	if (thr >= 1u && thr <= (uint32_t)size && (uint32_t)size == n) {
+		e = (uint32_t)size - thr;
+		const uint32_t piece = n / (e + 1u);
+		cls = piece >= 6u ? 6u : (piece >= 5u ? 5u : 0u);
+		if (cls && (seed_entries_needed(mp, n, e + 1u, cls) == 0u || seed_entries_needed(mm, n, e + 1u, cls) == 0u)) cls = 0u;
+	}
+	pat_mask[2 * i] = mp;
+	pat_meta[2 * i] = pat_meta_pack(thr, (uint32_t)start, 0u, base);
+	pat_meta2[2 * i] = pat_meta2_pack(nl, nr, n, e, cls);
+	pat_seeded[2 * i] = cls ? 1u : 0u;
+	pat_mask[2 * i + 1] = mm;
+	pat_meta[2 * i + 1] = pat_meta_pack(thr, (uint32_t)(31 - stop), 1u, base);
+	pat_meta2[2 * i + 1] = pat_meta2_pack(nl, nr, n, e, cls);
+	pat_seeded[2 * i + 1] = cls ? 1u : 0u;
+}
+
+// seeded patterns first (in order), brute-force patterns after them
+__global__ void pat_partition_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ meta2,
+	const uint32_t *__restrict__ seeded, const uint32_t *__restrict__ seeded_before, uint32_t n_pat, uint32_t n_seeded, uint4 *o_mask,
+	uint32_t *o_meta, uint32_t *o_meta2)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_pat) return;
+	const uint32_t d = seeded[p] ? seeded_before[p] : n_seeded + (p - seeded_before[p]);
+	o_mask[d] = mask[p];
+	o_meta[d] = meta[p];
+	o_meta2[d] = meta2[p];
+}
+
+__global__ void seed_overflow_kernel(const uint32_t *__restrict__ cnt, unsigned int *flag)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < SEED_BUCKETS && cnt[i] > 4095u) atomicExch(flag, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -306,6 +344,32 @@ int upload_eos(pcramp_gpu_ctx *ctx, SeqSet &s)
 	CK(cudaMemcpyAsync(s.d_eos_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	if (!pos.empty()) CK(cudaMemcpyAsync(s.d_eos_pos.p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int rebuild_dirty(pcramp_gpu_ctx *ctx, SeqSet &s)
+{
+	s.n_dirty = 0;
+	if (!s.any_degenerate || s.n_groups == 0) return 0;
+	const uint64_t n_words = (s.n_groups + 31) / 32;
+	CK(s.d_dirty_bits.ensure(n_words * 4));
+	CK(ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
+	unsigned int *d_n = (unsigned int *)ctx->d_counters.p;
+	for (int pass = 0; pass < 2; ++pass) { // count, then fill
+		CK(cudaMemsetAsync(d_n, 0, 8 * sizeof(unsigned long long), ctx->stream));
+		dirty_bits_kernel<<<grid_for(n_words, 128), 128, 0, ctx->stream>>>(s.dev(), s.n_groups, s.d_dirty_bits.as<uint32_t>(),
+			s.d_dirty_seq.as<uint32_t>(), s.d_dirty_grp.as<uint32_t>(), d_n, pass == 0 ? 0u : s.n_dirty);
+		CK(cudaGetLastError());
+		unsigned int n = 0;
+		CK(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (pass == 0) {
+			s.n_dirty = n;
+			if (n == 0) break;
+			CK(s.d_dirty_seq.ensure((size_t)n * 4));
+			CK(s.d_dirty_grp.ensure((size_t)n * 4));
+		}
+	}
 	return 0;
 }
 
@@ -357,6 +421,14 @@ int pcramp_gpu_create(pcramp_gpu_ctx **out, int device)
 		return 4;
 	}
 	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+	cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+	ctx->max_smem_optin -= 2048; // room for the kernel's static shared memory and the runtime's reservation
+	if (cudaFuncSetAttribute(scan_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin) != cudaSuccess) {
+		cudaGetLastError();
+		cudaStreamDestroy(ctx->stream);
+		delete ctx;
+		return 5;
+	}
 	for (auto &e : ctx->ev) cudaEventCreate(&e);
 	cudaMallocHost((void **)&ctx->h_counters, 8 * sizeof(unsigned long long));
 	*out = ctx;
@@ -466,6 +538,7 @@ int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const
 	CK(cudaStreamSynchronize(ctx->stream));
 	if (upload_eos(ctx, s)) return 1;
 	if (compact_sequences(ctx, s, with_eos)) return 1;
+	if (rebuild_dirty(ctx, s)) return 1;
 	return rebuild_tiles(ctx, s);
 }
 
@@ -496,6 +569,7 @@ int pcramp_gpu_split_sequence(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint3
 	CK(cudaStreamSynchronize(ctx->stream));
 	if (upload_eos(ctx, s)) return 1;
 	if (compact_sequences(ctx, s, std::vector<uint32_t>(1, seq))) return 1;
+	if (rebuild_dirty(ctx, s)) return 1; // the compressed text moved by one base
 	return rebuild_tiles(ctx, s);
 }
 
@@ -613,30 +687,62 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(cudaStreamSynchronize(st));
 	const uint32_t n_cand = last_off + last_cnt;
 	if (n_cand > PAT_MAX_CAND) return fail(ctx, "pcramp_gpu_select_words: more than 2^20 candidate words in one batch");
-	const uint32_t n_pat = 2u * n_cand;
+	const uint32_t n_pat = 2u * n_oligo; // one pattern per (oligo, strand); shift families ride on it
 	CK(ctx->d_cand_words.ensure((size_t)n_cand * 16));
 	CK(ctx->d_cand_thr.ensure((size_t)n_cand * 4));
 	CK(ctx->d_pat_mask.ensure((size_t)n_pat * 16));
 	CK(ctx->d_pat_meta.ensure((size_t)n_pat * 4));
+	CK(ctx->d_pat_meta2.ensure((size_t)n_pat * 4));
+	CK(ctx->d_pat_seeded.ensure((size_t)n_pat * 4));
+	CK(ctx->d_pat_sbefore.ensure((size_t)n_pat * 4));
+	CK(ctx->d_part_mask.ensure((size_t)n_pat * 16));
+	CK(ctx->d_part_meta.ensure((size_t)n_pat * 4));
+	CK(ctx->d_part_meta2.ensure((size_t)n_pat * 4));
 	cand_build_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->pf(), ctx->pr(), n_pairs, opt5, opt3, threshold,
 		ctx->d_cand_off.as<uint32_t>(), ctx->d_cand_words.as<uint64_t>(), ctx->d_cand_thr.as<uint32_t>(), ctx->d_pat_mask.as<uint4>(),
-		ctx->d_pat_meta.as<uint32_t>());
+		ctx->d_pat_meta.as<uint32_t>(), ctx->d_pat_meta2.as<uint32_t>(), ctx->d_pat_seeded.as<uint32_t>());
 	CK(cudaGetLastError());
 	stat.kernel_launches++;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->d_pat_seeded.as<uint32_t>(), ctx->d_pat_sbefore.as<uint32_t>(), (int)n_pat, st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->d_pat_seeded.as<uint32_t>(), ctx->d_pat_sbefore.as<uint32_t>(), (int)n_pat, st));
+	uint32_t n_seeded = 0;
 	{ // a zero threshold would select every word of every sequence (select_words.cpp:99-117): refuse
 		std::vector<uint32_t> thr(n_cand);
+		uint32_t sb = 0, sl = 0;
 		CK(cudaMemcpyAsync(thr.data(), ctx->d_cand_thr.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&sb, ctx->d_pat_sbefore.as<uint32_t>() + (n_pat - 1), 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&sl, ctx->d_pat_seeded.as<uint32_t>() + (n_pat - 1), 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 		for (uint32_t t : thr)
 			if (t == 0) return fail(ctx, "pcramp_gpu_select_words: a candidate has match threshold 0 (empty oligo or threshold too low)");
+		n_seeded = sb + sl;
+	}
+	if (ctx->force_brute) n_seeded = 0; // testing hook: everything through the brute-force kernel
+	const uint32_t n_brute = n_pat - n_seeded;
+	if (ctx->force_brute) {
+		CK(cudaMemcpyAsync(ctx->d_part_mask.p, ctx->d_pat_mask.p, (size_t)n_pat * 16, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(ctx->d_part_meta.p, ctx->d_pat_meta.p, (size_t)n_pat * 4, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(ctx->d_part_meta2.p, ctx->d_pat_meta2.p, (size_t)n_pat * 4, cudaMemcpyDeviceToDevice, st));
+	} else {
+		pat_partition_kernel<<<grid_for(n_pat, 256), 256, 0, st>>>(ctx->d_pat_mask.as<uint4>(), ctx->d_pat_meta.as<uint32_t>(),
+			ctx->d_pat_meta2.as<uint32_t>(), ctx->d_pat_seeded.as<uint32_t>(), ctx->d_pat_sbefore.as<uint32_t>(), n_pat, n_seeded,
+			ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>());
+		CK(cudaGetLastError());
+		stat.kernel_launches++;
 	}
 	const uint32_t cand_bits = bits_for(n_cand), seq_bits = bits_for(s.n);
-	stat.n_patterns = n_pat;
+	stat.n_patterns = 2ull * n_cand; // brute-force-equivalent pattern count (every family member, both strands)
+	stat.n_seeded = n_seeded;
 	stat.n_positions = 0;
 	for (uint32_t i = 0; i < s.n; ++i)
 		if (s.active[i]) stat.n_positions += s.clen[i];
 
 	// ---- scan (re-run with a larger hit buffer if it overflowed) -------------------------------
+	CK(ctx->d_seed_cnt.ensure(SEED_BUCKETS * 4));
+	CK(ctx->d_seed_start.ensure(SEED_BUCKETS * 4));
+	CK(ctx->d_seed_bucket.ensure(SEED_BUCKETS * 4));
+	CK(ctx->d_tile_counter.ensure(16));
 	uint64_t n_hits = 0;
 	uint64_t cap = std::max<uint64_t>(ctx->hit_key[0].cap / 8, 1ull << 20);
 	for (int attempt = 0;; ++attempt) {
@@ -650,10 +756,80 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		hs.cap = cap;
 		CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
 		CK(cudaEventRecord(ctx->ev[0], st));
-		if (s.n_tiles) {
+		// (a) seeded patterns, in chunks that fit shared memory
+		if (s.n_tiles && n_seeded) {
+			uint32_t chunk = std::min<uint32_t>(n_seeded, 4096u);
+			uint32_t done = 0;
+			while (done < n_seeded) {
+				const uint32_t cn = std::min<uint32_t>(chunk, n_seeded - done);
+				const uint4 *c_mask = ctx->d_part_mask.as<uint4>() + done;
+				const uint32_t *c_meta = ctx->d_part_meta.as<uint32_t>() + done, *c_meta2 = ctx->d_part_meta2.as<uint32_t>() + done;
+				// count -> exclusive scan -> fill
+				CK(cudaMemsetAsync(ctx->d_seed_cnt.p, 0, SEED_BUCKETS * 4, st));
+				seed_count_kernel<<<grid_for(cn, 128), 128, 0, st>>>(c_mask, c_meta2, cn, ctx->d_seed_cnt.as<uint32_t>());
+				CK(cudaGetLastError());
+				CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->d_seed_cnt.as<uint32_t>(), ctx->d_seed_start.as<uint32_t>(), (int)SEED_BUCKETS, st));
+				CK(ctx->cub_tmp.ensure(tmp_bytes));
+				CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->d_seed_cnt.as<uint32_t>(), ctx->d_seed_start.as<uint32_t>(), (int)SEED_BUCKETS, st));
+				unsigned int *d_flag = ctx->d_tile_counter.as<unsigned int>() + 1;
+				CK(cudaMemsetAsync(ctx->d_tile_counter.p, 0, 16, st));
+				seed_overflow_kernel<<<grid_for(SEED_BUCKETS, 256), 256, 0, st>>>(ctx->d_seed_cnt.as<uint32_t>(), d_flag);
+				CK(cudaGetLastError());
+				uint32_t last_start = 0, last_cnt2 = 0, overflow = 0;
+				CK(cudaMemcpyAsync(&last_start, ctx->d_seed_start.as<uint32_t>() + (SEED_BUCKETS - 1), 4, cudaMemcpyDeviceToHost, st));
+				CK(cudaMemcpyAsync(&last_cnt2, ctx->d_seed_cnt.as<uint32_t>() + (SEED_BUCKETS - 1), 4, cudaMemcpyDeviceToHost, st));
+				CK(cudaMemcpyAsync(&overflow, d_flag, 4, cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				stat.kernel_launches += 4;
+				const uint32_t n_ent = last_start + last_cnt2;
+				const uint32_t ecap = (n_ent + 3u) & ~3u, pcap = (cn + 3u) & ~3u;
+				const size_t smem = seed_smem_bytes(ecap, pcap);
+				if (overflow || smem > (size_t)ctx->max_smem_optin || n_ent >= (1u << 20)) {
+					if (cn <= 16) return fail(ctx, "pcramp_gpu_select_words: seed table does not fit shared memory");
+					chunk = cn / 2; // fewer patterns per pass
+					continue;
+				}
+				CK(ctx->d_seed_entries.ensure(std::max<size_t>(1, ecap) * 4));
+				seed_bucket_pack_kernel<<<grid_for(SEED_BUCKETS, 256), 256, 0, st>>>(ctx->d_seed_start.as<uint32_t>(), ctx->d_seed_cnt.as<uint32_t>(),
+					ctx->d_seed_bucket.as<uint32_t>());
+				CK(cudaGetLastError());
+				seed_fill_kernel<<<grid_for(cn, 128), 128, 0, st>>>(c_mask, c_meta2, cn, ctx->d_seed_start.as<uint32_t>(),
+					ctx->d_seed_entries.as<uint32_t>(), ecap);
+				CK(cudaGetLastError());
+				SeedChunk ch;
+				ch.bucket = ctx->d_seed_bucket.as<uint32_t>();
+				ch.entries = ctx->d_seed_entries.as<uint32_t>();
+				ch.mask = c_mask;
+				ch.meta = c_meta;
+				ch.meta2 = c_meta2;
+				ch.n_entries = n_ent;
+				ch.n_pat = cn;
+				ch.ecap = ecap;
+				ch.pcap = pcap;
+				const unsigned grid = (unsigned)std::min<uint64_t>(s.n_tiles, (uint64_t)ctx->sm_count);
+				scan_seed_kernel<<<grid, SEED_THREADS, smem, st>>>(sd, s.d_tile_seq.as<uint32_t>(), s.d_tile_x0.as<uint32_t>(), (uint32_t)s.n_tiles,
+					ctx->d_tile_counter.as<unsigned int>(), ch, s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, cand_bits, hs);
+				CK(cudaGetLastError());
+				stat.kernel_launches += 3;
+				stat.n_seed_entries += n_ent;
+				done += cn;
+			}
+			// (b) the seeded patterns, brute force, on the groups whose text holds a degenerate base
+			if (s.n_dirty) {
+				scan_groups_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n_dirty + 7) / 8, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(sd,
+					s.d_dirty_seq.as<uint32_t>(), s.d_dirty_grp.as<uint32_t>(), s.n_dirty, ctx->d_part_mask.as<uint4>(),
+					ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(), n_seeded, cand_bits, hs);
+				CK(cudaGetLastError());
+				stat.kernel_launches++;
+			}
+		}
+		CK(cudaEventRecord(ctx->ev[7], st));
+		// (c) patterns that cannot be seeded: brute force over every alignment
+		if (s.n_tiles && n_brute) {
 			const unsigned grid = (unsigned)std::min<uint64_t>(s.n_tiles, (uint64_t)ctx->sm_count * 2);
 			scan_full_kernel<<<grid, SCAN_THREADS, 0, st>>>(sd, s.d_tile_seq.as<uint32_t>(), s.d_tile_x0.as<uint32_t>(), (uint32_t)s.n_tiles,
-				ctx->d_pat_mask.as<uint4>(), ctx->d_pat_meta.as<uint32_t>(), n_pat, cand_bits, hs);
+				ctx->d_part_mask.as<uint4>() + n_seeded, ctx->d_part_meta.as<uint32_t>() + n_seeded, ctx->d_part_meta2.as<uint32_t>() + n_seeded,
+				n_brute, cand_bits, hs);
 			CK(cudaGetLastError());
 			stat.kernel_launches++;
 		}
@@ -666,7 +842,8 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 		n_hits = ctx->h_counters[0];
-		stat.ms_scan += ev_ms(ctx->ev[0], ctx->ev[1]);
+		stat.ms_seed += ev_ms(ctx->ev[0], ctx->ev[7]);
+		stat.ms_scan += ev_ms(ctx->ev[7], ctx->ev[1]);
 		stat.ms_edge += ev_ms(ctx->ev[1], ctx->ev[2]);
 		if (n_hits <= cap) break;
 		if (attempt >= 2) return fail(ctx, "pcramp_gpu_select_words: hit buffer kept overflowing");
@@ -1041,6 +1218,13 @@ int pcramp_gpu_score_pairs(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, con
 	if (pcramp_gpu_stage_pairs(ctx, f, r, n_pairs)) return 1;
 	if (pcramp_gpu_score_pairs_staged(ctx, kind, search_threshold, detect_threshold, amp_min, amp_max, taq)) return 1;
 	return pcramp_gpu_fetch_results(ctx, coverage, bitsets);
+}
+
+int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
+{
+	if (!ctx || !name) return 1;
+	if (strcmp(name, "force_brute_scan") == 0) { ctx->force_brute = value; return 0; }
+	return fail(ctx, std::string("pcramp_gpu_set_option: unknown option ") + name);
 }
 
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out)

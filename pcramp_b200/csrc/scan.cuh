@@ -7,19 +7,29 @@
 //     cand & window_at(p)   ==   #{k < n : primer[k] n text[p + start + k] != {} }
 // and against the minus-strand word of the same window (its reverse complement, sequence.cpp:188)
 //     cand & rc(window_at(p)) == #{k < n : rc(primer)[k] n text[p + 31 - stop + k] != {} }.
-// Both are "count matching positions of an n-letter pattern laid on the text at x", so a pattern is
-// four 32-bit masks B_A,B_C,B_G,B_T (bit k: pattern[k] admits that letter) and with the text held
-// as bit-planes (seqdev.cuh) the per-alignment work is
+// Both are "count matching positions of an n-letter PATTERN laid on the text at alignment x", so a
+// pattern is four 32-bit masks B_A,B_C,B_G,B_T (bit k: pattern[k] admits that letter) and with the
+// text held as bit-planes (seqdev.cuh)
 //     m = (B_A & W_A(x)) | (B_C & W_C(x)) | (B_G & W_G(x)) | (B_T & W_T(x));  count = popc(m)
 // = 4 LOP3 + 1 POPC + 1 ISETP, against ~24 integer ops for the reference's 128-bit nibble fold.
-// W_l(x) (the 32 plane bits from x) is pattern-independent: each thread funnel-shifts its R
-// alignments out of shared memory once per tile and keeps them in registers for ALL patterns, so
-// HBM is read once per tile and the kernel is bound by the integer pipes, not by memory.
 //
-// Output: a flat list of hits (candidate, strand, sequence, window, count) with count >= the
-// candidate's threshold.  The per-(candidate, sequence) "best tier only" rule of select_words
-// (select_words.cpp:99-117) is a max over ALL words of a sequence, so it is applied afterwards on
-// the (tiny) hit list, not inside the scan (db.cuh).
+// The 5'/3' shift family select_words adds per oligo (select_words.cpp:38-72) lays the SAME primer on
+// the SAME text alignments, seen through neighbouring windows: one pattern per (oligo, strand) is
+// scanned and a hit is fanned out to every family member whose window exists (emit_family).
+//
+// Three kernels produce the same flat hit list (candidate, strand, sequence, window, count >= thr):
+//   scan_seed_kernel   the fast path.  count >= thr allows e = n - thr mismatches, so of e+1 disjoint
+//                      pieces of the primer one must match exactly (pigeonhole).  Piece seeds of q = 5
+//                      or 6 bases (all IUPAC expansions) are indexed by their 2-bit code in shared memory;
+//                      each text position looks up the primers having that seed and only those
+//                      alignments are counted.  Exact, ~10^2-10^3 x fewer alignments than brute force.
+//   scan_full_kernel   brute force over all alignments, for patterns whose pieces would be < 5 bases
+//                      (low thresholds, e.g. backgrounds at 0.72) or too degenerate to expand.
+//   scan_groups_kernel brute force of the seeded patterns over the few 32-base groups whose text
+//                      contains a degenerate base (a 2-bit code cannot represent it); the seed kernel
+//                      skips exactly those alignments.
+// The per-(candidate, sequence) "best tier only" rule of select_words (select_words.cpp:99-117) is a
+// max over ALL words of a sequence, so it is applied afterwards on the hit list (db.cuh).
 #pragma once
 #include "seqdev.cuh"
 
@@ -31,11 +41,16 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_R;  // 2048 template positions per
 constexpr int SCAN_TILE_GROUPS = SCAN_TILE / 32;  // 64 plane groups (+1 halo)
 constexpr int SCAN_PAT_CHUNK = 1024;              // patterns staged in shared memory at a time
 
-// pattern meta word: thr[5:0] | frame_offset[10:6] | minus[11] | cand[31:12]
+// pattern meta word: thr[5:0] | frame_offset[10:6] | minus[11] | base candidate id[31:12]
 constexpr uint32_t PAT_MAX_CAND = 1u << 20;
 __host__ __device__ __forceinline__ uint32_t pat_meta_pack(uint32_t thr, uint32_t off, uint32_t minus, uint32_t cand)
 {
 	return (thr & 63u) | ((off & 31u) << 6) | ((minus & 1u) << 11) | (cand << 12);
+}
+// second meta word: n_left[4:0] | n_right[9:5] | n[15:10] | e[21:16] | seed class q[24:22] (0 = brute force)
+__host__ __device__ __forceinline__ uint32_t pat_meta2_pack(uint32_t nl, uint32_t nr, uint32_t n, uint32_t e, uint32_t cls)
+{
+	return (nl & 31u) | ((nr & 31u) << 5) | ((n & 63u) << 10) | ((e & 63u) << 16) | ((cls & 7u) << 22);
 }
 
 // hit key, low to high: minus[0] | type[2:1] | 63-count[8:3] | cand[9 .. 9+cand_bits) | seq[...]
@@ -63,15 +78,35 @@ __device__ __forceinline__ void hit_append(const HitSink &hs, uint64_t key, uint
 	}
 }
 
+// A pattern matched `cnt` positions at alignment x (text index of primer base 0).  Report it for the
+// base candidate and for every 5'/3'-shifted copy whose 32-base window lies inside the sequence:
+// the copy shifted j slots toward 5' sees the same alignment through the window starting j later.
+__device__ __forceinline__ void emit_family(const HitSink &hs, uint32_t seq, uint32_t clen, uint32_t cand_bits, uint32_t meta, uint32_t meta2,
+	int64_t x, uint32_t cnt)
+{
+	const int off = (int)((meta >> 6) & 31u);
+	const uint32_t minus = (meta >> 11) & 1u, base = meta >> 12;
+	const int nl = (int)(meta2 & 31u), nr = (int)((meta2 >> 5) & 31u);
+	for (int v = 0; v <= nl + nr; ++v) {
+		int o;
+		if (v == 0) o = off;
+		else if (v <= nl) o = minus ? off + v : off - v;               // shift_left v times (select_words.cpp:50-58)
+		else o = minus ? off - (v - nl) : off + (v - nl);              // shift_right (v - nl) times (:61-70)
+		const int64_t wstart = x - o;
+		if (wstart >= 0 && wstart + 32 <= (int64_t)clen)
+			hit_append(hs, hit_key_pack(seq, base + (uint32_t)v, cand_bits, cnt, ENT_FULL, minus), (uint32_t)wstart + 31u);
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
-// K1a: full windows.  One CTA per tile of 2048 template positions (persistent, strided), all
-// patterns per tile.  __launch_bounds__(256, 2): ~64 registers, 16 warps/SM -- the loop is pure
-// register arithmetic with 8 independent chains per thread, so occupancy only has to cover the
-// 4-cycle ALU latency and the shared-memory pattern broadcast.
+// K1 brute force: one CTA per tile of 2048 alignments (persistent, strided), all given patterns
+// per tile.  Each thread funnel-shifts its 8 alignments' plane windows out of shared memory once
+// per tile and keeps them in registers for every pattern.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS, 2)
 scan_full_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_t *__restrict__ tile_x0, uint32_t n_tiles,
-	const uint4 *__restrict__ pat_mask, const uint32_t *__restrict__ pat_meta, uint32_t n_pat, uint32_t cand_bits, HitSink hs)
+	const uint4 *__restrict__ pat_mask, const uint32_t *__restrict__ pat_meta, const uint32_t *__restrict__ pat_meta2, uint32_t n_pat,
+	uint32_t cand_bits, HitSink hs)
 {
 	__shared__ uint4 s_grp[SCAN_TILE_GROUPS + 1];
 	__shared__ uint4 s_mask[SCAN_PAT_CHUNK];
@@ -125,17 +160,191 @@ scan_full_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_
 					any |= (__popc(m) >= thr);
 				}
 				if (any) { // rare: a real binding site (or a chance hit at a low threshold)
-					const int off = (int)((meta >> 6) & 31u);
-					const uint32_t minus = (meta >> 11) & 1u, cand = meta >> 12;
+					const uint32_t meta2 = __ldg(pat_meta2 + c0 + p);
 					#pragma unroll
 					for (int r = 0; r < SCAN_R; ++r) {
 						const uint32_t m = (b.x & wa[r]) | (b.y & wc[r]) | (b.z & wg[r]) | (b.w & wt[r]);
 						const int cnt = __popc(m);
-						if (cnt >= thr) {
-							const int64_t wstart = (int64_t)x0 + r * SCAN_THREADS + tid - off; // window start p
-							if (wstart >= 0 && wstart + 32 <= (int64_t)clen)
-								hit_append(hs, hit_key_pack(seq, cand, cand_bits, (uint32_t)cnt, ENT_FULL, minus), (uint32_t)wstart + 31u);
+						if (cnt >= thr) emit_family(hs, seq, clen, cand_bits, meta, meta2, (int64_t)x0 + r * SCAN_THREADS + tid, (uint32_t)cnt);
+					}
+				}
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 brute force over listed 32-alignment groups (the "dirty" groups whose windows touch a
+// degenerate text base).  One warp per group, lane = alignment, patterns streamed through smem.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scan_groups_kernel(SeqDev sd, const uint32_t *__restrict__ grp_seq, const uint32_t *__restrict__ grp_idx, uint32_t n_groups,
+	const uint4 *__restrict__ pat_mask, const uint32_t *__restrict__ pat_meta, const uint32_t *__restrict__ pat_meta2, uint32_t n_pat,
+	uint32_t cand_bits, HitSink hs)
+{
+	__shared__ uint4 s_mask[SCAN_PAT_CHUNK];
+	__shared__ uint32_t s_meta[SCAN_PAT_CHUNK];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	for (uint32_t g0 = blockIdx.x * 8u; g0 < n_groups; g0 += gridDim.x * 8u) {
+		const uint32_t gi = g0 + warp;
+		bool live = gi < n_groups;
+		uint32_t seq = 0, grp = 0, clen = 0;
+		uint32_t wa = 0, wc = 0, wg = 0, wt = 0;
+		if (live) {
+			seq = grp_seq[gi];
+			grp = grp_idx[gi];
+			live = sd.active[seq] != 0;
+		}
+		if (live) {
+			clen = sd.clen[seq];
+			const uint64_t gbase = sd.grp_off[seq];
+			const uint32_t ngrp = (uint32_t)(sd.grp_off[seq + 1] - gbase);
+			const uint4 lo = __ldg(sd.planes + gbase + grp);
+			const uint4 hi = (grp + 1u < ngrp) ? __ldg(sd.planes + gbase + grp + 1u) : make_uint4(0, 0, 0, 0);
+			wa = __funnelshift_r(lo.x, hi.x, lane);
+			wc = __funnelshift_r(lo.y, hi.y, lane);
+			wg = __funnelshift_r(lo.z, hi.z, lane);
+			wt = __funnelshift_r(lo.w, hi.w, lane);
+		}
+		for (uint32_t c0 = 0; c0 < n_pat; c0 += SCAN_PAT_CHUNK) {
+			const uint32_t cn = min((uint32_t)SCAN_PAT_CHUNK, n_pat - c0);
+			__syncthreads();
+			for (uint32_t i = threadIdx.x; i < cn; i += blockDim.x) {
+				s_mask[i] = __ldg(pat_mask + c0 + i);
+				s_meta[i] = __ldg(pat_meta + c0 + i);
+			}
+			__syncthreads();
+			if (!live) continue;
+			for (uint32_t p = 0; p < cn; ++p) {
+				const uint4 b = s_mask[p];
+				const uint32_t meta = s_meta[p];
+				const uint32_t m = (b.x & wa) | (b.y & wc) | (b.z & wg) | (b.w & wt);
+				const int cnt = __popc(m);
+				if (cnt >= (int)(meta & 63u))
+					emit_family(hs, seq, clen, cand_bits, meta, __ldg(pat_meta2 + c0 + p), (int64_t)grp * 32 + lane, (uint32_t)cnt);
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 fast path: pigeonhole seed filter.
+//
+// Shared memory (one CTA of 1024 threads per SM, everything hot is on chip):
+//   bucket[1024 + 4096]  per 2-bit seed code (q = 5, then q = 6): first entry | count << 20
+//   entries[]            seed -> (pattern << 5 | offset of the seed inside the pattern)
+//   mask[], meta[]       the chunk's pattern masks and thresholds
+//   grp[66], b0[66], b1[66]  the tile's planes with one halo group on each side, and the two code
+//                        planes b0 = C|T, b1 = G|T (A=00 C=01 G=10 T=11)
+// A thread takes 2 of the tile's 2048 text positions; the seed code at x is five / six low bits of
+// each code plane window.  For every (pattern, offset) in the bucket the alignment x - offset is
+// counted with the same 4 LOP3 + POPC as the brute-force kernel, planes funnel-shifted from smem.
+// An alignment found through several of its pieces is reported by the leftmost matching one only.
+// ---------------------------------------------------------------------------------------------
+constexpr int SEED_THREADS = 1024;
+constexpr int SEED_R = SCAN_TILE / SEED_THREADS;       // 2
+constexpr int SEED_GROUPS = SCAN_TILE_GROUPS + 2;      // 66: halo group on both sides
+constexpr uint32_t SEED_BUCKETS = 1024u + 4096u;
+constexpr uint32_t SEED_MAX_EXPANSIONS = 64u;          // per pattern, over all its pieces
+
+struct SeedChunk {
+	const uint32_t *bucket;  // SEED_BUCKETS words
+	const uint32_t *entries; // n_entries words
+	const uint4 *mask;       // n_pat
+	const uint32_t *meta;    // n_pat
+	const uint32_t *meta2;   // n_pat (read on hits only, stays in global memory)
+	uint32_t n_entries, n_pat;
+	uint32_t ecap, pcap;     // shared-memory capacities the launch was sized for (multiples of 4)
+};
+
+__host__ __device__ __forceinline__ size_t seed_smem_bytes(uint32_t ecap, uint32_t pcap)
+{
+	return (size_t)SEED_BUCKETS * 4 + (size_t)ecap * 4 + (size_t)pcap * 16 + (size_t)pcap * 4 + (size_t)SEED_GROUPS * 16 + 2 * (size_t)SEED_GROUPS * 4;
+}
+
+__global__ void __launch_bounds__(SEED_THREADS, 1)
+scan_seed_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_t *__restrict__ tile_x0, uint32_t n_tiles,
+	unsigned int *tile_counter, SeedChunk ch, const uint32_t *__restrict__ dirty_bits, uint32_t cand_bits, HitSink hs)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	uint32_t *s_bucket = smem;
+	uint32_t *s_entries = s_bucket + SEED_BUCKETS;
+	uint4 *s_mask = (uint4 *)(s_entries + ch.ecap);
+	uint32_t *s_meta = (uint32_t *)(s_mask + ch.pcap);
+	uint4 *s_grp = (uint4 *)(s_meta + ch.pcap);
+	uint32_t *s_b0 = (uint32_t *)(s_grp + SEED_GROUPS);
+	uint32_t *s_b1 = s_b0 + SEED_GROUPS;
+	__shared__ uint32_t s_tile;
+
+	const uint32_t tid = threadIdx.x;
+	for (uint32_t i = tid; i < SEED_BUCKETS; i += SEED_THREADS) s_bucket[i] = __ldg(ch.bucket + i);
+	for (uint32_t i = tid; i < ch.n_entries; i += SEED_THREADS) s_entries[i] = __ldg(ch.entries + i);
+	for (uint32_t i = tid; i < ch.n_pat; i += SEED_THREADS) {
+		s_mask[i] = __ldg(ch.mask + i);
+		s_meta[i] = __ldg(ch.meta + i);
+	}
+
+	for (;;) {
+		__syncthreads(); // tables loaded / previous tile consumed
+		if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+		__syncthreads();
+		const uint32_t tile = s_tile;
+		if (tile >= n_tiles) break;
+		const uint32_t seq = tile_seq[tile];
+		if (!sd.active[seq]) continue;
+		const uint32_t x0 = tile_x0[tile];
+		const uint64_t gbase = sd.grp_off[seq];
+		const uint32_t ngrp = (uint32_t)(sd.grp_off[seq + 1] - gbase);
+		const uint32_t clen = sd.clen[seq];
+		if (tid < SEED_GROUPS) {
+			const int64_t g = (int64_t)(x0 >> 5) - 1 + tid;
+			const uint4 v = (g >= 0 && g < (int64_t)ngrp) ? __ldg(sd.planes + gbase + g) : make_uint4(0, 0, 0, 0);
+			s_grp[tid] = v;
+			s_b0[tid] = v.y | v.w;
+			s_b1[tid] = v.z | v.w;
+		}
+		__syncthreads();
+
+		#pragma unroll
+		for (int r = 0; r < SEED_R; ++r) {
+			const uint32_t xl = r * SEED_THREADS + tid;
+			if (x0 + xl >= clen) continue;
+			const uint32_t bit = 32u + xl; // bit index inside the haloed tile
+			const uint32_t w0 = __funnelshift_r(s_b0[bit >> 5], s_b0[(bit >> 5) + 1], bit & 31u);
+			const uint32_t w1 = __funnelshift_r(s_b1[bit >> 5], s_b1[(bit >> 5) + 1], bit & 31u);
+			#pragma unroll
+			for (int t = 0; t < 2; ++t) {
+				const uint32_t code = t == 0 ? ((w0 & 31u) | ((w1 & 31u) << 5)) : (1024u + ((w0 & 63u) | ((w1 & 63u) << 6)));
+				const uint32_t bk = s_bucket[code];
+				const uint32_t first = bk & 0xFFFFFu, count = bk >> 20;
+				for (uint32_t j = 0; j < count; ++j) {
+					const uint32_t en = s_entries[first + j];
+					const uint32_t pid = en >> 5, off = en & 31u;
+					const uint32_t bit2 = bit - off;
+					const uint4 lo = s_grp[bit2 >> 5], hi = s_grp[(bit2 >> 5) + 1];
+					const uint32_t sh = bit2 & 31u;
+					const uint4 b = s_mask[pid];
+					const uint32_t m = (b.x & __funnelshift_r(lo.x, hi.x, sh)) | (b.y & __funnelshift_r(lo.y, hi.y, sh)) |
+					                   (b.z & __funnelshift_r(lo.z, hi.z, sh)) | (b.w & __funnelshift_r(lo.w, hi.w, sh));
+					const int cnt = __popc(m);
+					const uint32_t meta = s_meta[pid];
+					if (cnt >= (int)(meta & 63u)) { // a binding site
+						const int64_t x = (int64_t)x0 + xl - off;
+						if (x < 0) continue;
+						if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
+							const uint64_t G = gbase + (uint64_t)(x >> 5);
+							if (((dirty_bits[G >> 5] >> (G & 31u)) & 1u)) continue;
 						}
+						const uint32_t meta2 = __ldg(ch.meta2 + pid);
+						const uint32_t n = (meta2 >> 10) & 63u, pieces = ((meta2 >> 16) & 63u) + 1u, q = (meta2 >> 22) & 7u;
+						const uint32_t qmask = (1u << q) - 1u;
+						bool first_piece = true; // report through the leftmost exactly-matching piece only
+						for (uint32_t i = 0; i < pieces; ++i) {
+							const uint32_t o = (i * n) / pieces;
+							if (o >= off) break;
+							if (((m >> o) & qmask) == qmask) { first_piece = false; break; }
+						}
+						if (first_piece) emit_family(hs, seq, clen, cand_bits, meta, meta2, x, (uint32_t)cnt);
 					}
 				}
 			}
@@ -201,6 +410,131 @@ scan_edge_kernel(SeqDev sd, PackParams pp, const uint64_t *__restrict__ cand_wor
 			}
 		}
 	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// dirty groups: a 32-base group is "dirty" when it or its right neighbour holds a degenerate base,
+// i.e. when some alignment starting in it reads a base that is not exactly one letter.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool group_degenerate(const uint4 g)
+{
+	return ((g.x & g.y) | (g.x & g.z) | (g.x & g.w) | (g.y & g.z) | (g.y & g.w) | (g.z & g.w)) != 0u;
+}
+
+// one thread per 32 consecutive GLOBAL groups -> one word of dirty_bits; sequences are found by search
+__global__ void dirty_bits_kernel(SeqDev sd, uint64_t n_groups, uint32_t *dirty_bits, uint32_t *list_seq, uint32_t *list_grp,
+	unsigned int *n_list, uint32_t list_cap)
+{
+	const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w * 32ull >= n_groups) return;
+	uint32_t lo = 0, hi = sd.n; // sequence owning the first group of this word
+	while (hi - lo > 1u) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (sd.grp_off[mid] <= w * 32ull) lo = mid; else hi = mid;
+	}
+	uint32_t seq = lo, bits = 0;
+	for (uint32_t b = 0; b < 32u; ++b) {
+		const uint64_t G = w * 32ull + b;
+		if (G >= n_groups) break;
+		while (seq + 1u < sd.n && sd.grp_off[seq + 1] <= G) ++seq;
+		const bool last = (G + 1 == sd.grp_off[seq + 1]); // the zero halo group of this sequence
+		const bool d = group_degenerate(__ldg(sd.planes + G)) || (!last && group_degenerate(__ldg(sd.planes + G + 1)));
+		if (d) {
+			bits |= 1u << b;
+			const unsigned int o = atomicAdd(n_list, 1u);
+			if (o < list_cap) {
+				list_seq[o] = seq;
+				list_grp[o] = (uint32_t)(G - sd.grp_off[seq]);
+			}
+		}
+	}
+	dirty_bits[w] = bits;
+}
+
+// ---------------------------------------------------------------------------------------------
+// seed tables (per chunk of seeded patterns), built on the device
+// ---------------------------------------------------------------------------------------------
+// Enumerate the IUPAC expansions of the q-base seed of piece `i` of a pattern and call f(code).
+template <class F>
+__device__ __forceinline__ void for_each_seed(const uint4 &mask, uint32_t n, uint32_t pieces, uint32_t q, uint32_t i, F f)
+{
+	const uint32_t o = (i * n) / pieces;
+	// per-position letter sets as 4-bit {A,C,G,T}; letter codes A=0 C=1 G=2 T=3 -> b0 = code & 1, b1 = code >> 1
+	uint32_t sets[6];
+	uint32_t total = 1;
+	for (uint32_t k = 0; k < q; ++k) {
+		const uint32_t s = ((mask.x >> (o + k)) & 1u) | (((mask.y >> (o + k)) & 1u) << 1) | (((mask.z >> (o + k)) & 1u) << 2) |
+		                   (((mask.w >> (o + k)) & 1u) << 3);
+		sets[k] = s;
+		total *= (uint32_t)__popc(s);
+	}
+	for (uint32_t t = 0; t < total; ++t) { // mixed-radix counter over the sets
+		uint32_t rem = t, b0 = 0, b1 = 0;
+		for (uint32_t k = 0; k < q; ++k) {
+			const uint32_t cnt = (uint32_t)__popc(sets[k]);
+			uint32_t pick = rem % cnt;
+			rem /= cnt;
+			uint32_t s = sets[k], letter = 0;
+			for (;;) { // pick-th set bit
+				letter = (uint32_t)(__ffs(s) - 1);
+				if (pick == 0) break;
+				--pick;
+				s &= s - 1u;
+			}
+			b0 |= (letter & 1u) << k;
+			b1 |= (letter >> 1) << k;
+		}
+		f((q == 5u ? 0u : 1024u) + (b0 | (b1 << q)), o);
+	}
+}
+
+// number of seed-table entries a pattern needs, or 0 when it cannot be seeded
+__device__ __forceinline__ uint32_t seed_entries_needed(const uint4 &mask, uint32_t n, uint32_t pieces, uint32_t q)
+{
+	uint32_t sum = 0;
+	for (uint32_t i = 0; i < pieces; ++i) {
+		const uint32_t o = (i * n) / pieces;
+		uint32_t total = 1;
+		for (uint32_t k = 0; k < q; ++k) {
+			const uint32_t c = ((mask.x >> (o + k)) & 1u) + ((mask.y >> (o + k)) & 1u) + ((mask.z >> (o + k)) & 1u) + ((mask.w >> (o + k)) & 1u);
+			if (c == 0u) return 0u; // an EOS inside the primer: leave it to brute force
+			total *= c;
+			if (total > SEED_MAX_EXPANSIONS) return 0u;
+		}
+		sum += total;
+		if (sum > SEED_MAX_EXPANSIONS) return 0u;
+	}
+	return sum;
+}
+
+__global__ void seed_count_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta2, uint32_t n_pat, uint32_t *bucket_cnt)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_pat) return;
+	const uint4 m = mask[p];
+	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u, q = (m2 >> 22) & 7u;
+	for (uint32_t i = 0; i < pieces; ++i) for_each_seed(m, n, pieces, q, i, [&](uint32_t code, uint32_t) { atomicAdd(bucket_cnt + code, 1u); });
+}
+
+// bucket_cnt holds the exclusive start of every bucket on entry and is advanced as a cursor
+__global__ void seed_fill_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta2, uint32_t n_pat, uint32_t *cursor,
+	uint32_t *entries, uint32_t ecap)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_pat) return;
+	const uint4 m = mask[p];
+	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u, q = (m2 >> 22) & 7u;
+	for (uint32_t i = 0; i < pieces; ++i)
+		for_each_seed(m, n, pieces, q, i, [&](uint32_t code, uint32_t o) {
+			const uint32_t slot = atomicAdd(cursor + code, 1u);
+			if (slot < ecap) entries[slot] = (p << 5) | o;
+		});
+}
+
+__global__ void seed_bucket_pack_kernel(const uint32_t *__restrict__ start, const uint32_t *__restrict__ cnt, uint32_t *bucket)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < SEED_BUCKETS) bucket[i] = (start[i] & 0xFFFFFu) | (min(cnt[i], 4095u) << 20);
 }
 
 } // namespace pcr

@@ -170,3 +170,78 @@ def test_properties_at_scale(gpu):
     cov3, bits3 = gpu.score_pairs(TARGET, f, r, 1.0, 1.0)
     b3 = unpack_bits(bits3, n)
     assert b3[0].sum() == 0 and np.array_equal(b3, b * active[None, :])
+
+
+def _db_tuple(gpu, kind=TARGET):
+    w, idx, loc, st, key = gpu.db_copy(kind)
+    return w, idx, loc, st, key, gpu.keys_copy(kind)
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_seed_filter_equals_brute_force(gpu, name):
+    """the pigeonhole seed path and the brute-force path are two CUDA implementations of the same scan"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    try:
+        gpu.set_option("force_brute_scan", 1)
+        g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+        assert gpu.stats()["n_seeded"] == 0
+        brute = _db_tuple(gpu)
+    finally:
+        gpu.set_option("force_brute_scan", 0)
+    g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+    st = gpu.stats()
+    fast = _db_tuple(gpu)
+    for a, b in zip(fast, brute):
+        assert np.array_equal(a, b)
+    if name in ("lowthr", "taq_weights"):
+        assert st["n_seeded"] == 0          # 0.72 n / 0.81 n leave pieces shorter than 5 bases: brute force
+    elif name not in ("repeats",):
+        assert st["n_seeded"] > 0
+
+
+def test_seed_filter_with_degenerate_text_vs_oracle(gpu, oracle):
+    """IUPAC codes and N runs in the targets (dirty groups), degenerate primers (seed expansion), several tiles"""
+    rng = np.random.default_rng(77)
+    base = synth.make_targets(701, 24, 9000, n_clades=3, between=0.12, within=0.05)
+    codes = [base.codes(i).copy() for i in range(base.n)]
+    for c in codes:
+        k = rng.integers(0, len(c), size=25)
+        c[k] |= synth.CODE[rng.integers(0, 4, size=25)]
+        s = int(rng.integers(0, len(c) - 40))
+        c[s:s + int(rng.integers(1, 12))] = 15
+    codes[3][2040:2056] = 15      # an N run across a tile boundary
+    codes[5][4000] = 0            # and one EOS
+    coll = synth.Collection(codes)
+    f, r = synth.make_pairs(702, base, 200, degenerate_fraction=0.5)
+    thr = float(np.float32(1.0) * np.float32(0.9))
+    g = GpuChecker(gpu)
+    g.set_sequences(coll)
+    oracle.set_sequences(coll)
+    for kw in (dict(), dict(optimize_5=True, optimize_3=True)):
+        ne, nk = g.select_words(f[:60] if kw else f, r[:60] if kw else r, thr, **kw)
+        no, nko = oracle.select_words(f[:60] if kw else f, r[:60] if kw else r, thr, **kw)
+        assert (ne, nk) == (no, nko)
+        for a, c in zip(g.db(), oracle.db()):
+            assert np.array_equal(a, c)
+        assert gpu.stats()["n_seeded"] > 0
+    cov_o, bits_o = oracle.score_pairs(f[:60], r[:60], thr, 0.9, 80, 200, False)
+    cov_g, bits_g = g.score_pairs(f[:60], r[:60], thr, 0.9, 80, 200, False)
+    assert np.array_equal(bits_g, bits_o) and np.array_equal(cov_g, cov_o)
+
+
+def test_exact_threshold_and_mixed_classes(gpu, oracle):
+    """threshold 1.0 (one piece = the whole primer) and 0.8 (pieces of 4-5: mixed seeded / brute-force batch)"""
+    coll = synth.make_targets(801, 16, 6000, n_clades=2, between=0.1, within=0.04)
+    f, r = synth.make_pairs(802, coll, 120)
+    g = GpuChecker(gpu)
+    g.set_sequences(coll)
+    oracle.set_sequences(coll)
+    for thr in (1.0, 0.95, 0.8, 0.75):
+        ne, nk = g.select_words(f, r, thr)
+        assert (ne, nk) == oracle.select_words(f, r, thr)
+        for a, c in zip(g.db(), oracle.db()):
+            assert np.array_equal(a, c)
