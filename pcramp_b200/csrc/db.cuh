@@ -15,10 +15,11 @@
 
 namespace pcr {
 
-// entry id, low to high: pos[31:0] | minus[32] | type[34:33] | seq[35 ...]
+// entry id, low to high: pos[31:0] | type[33:32] | minus[34] | seq[35 ...]: sorted ids group a sequence's
+// plus-strand entries before its minus-strand entries (what pair scoring iterates over)
 __host__ __device__ __forceinline__ uint64_t entry_id_pack(uint32_t seq, uint32_t type, uint32_t minus, uint32_t pos)
 {
-	return ((uint64_t)seq << 35) | ((uint64_t)type << 33) | ((uint64_t)minus << 32) | pos;
+	return ((uint64_t)seq << 35) | ((uint64_t)minus << 34) | ((uint64_t)type << 32) | pos;
 }
 
 __global__ void validate_hits_kernel(SeqDev sd, PackParams pp, uint64_t *hit_key, const uint32_t *hit_val, uint64_t n_hits,
@@ -56,12 +57,12 @@ __global__ void tier_kernel(const uint64_t *__restrict__ hit_key, const uint32_t
 
 // word, loc, strand, seq of each unique entry (entry ids sorted => grouped by sequence)
 __global__ void materialise_kernel(SeqDev sd, PackParams pp, const uint64_t *__restrict__ entry_id, uint64_t n, uint64_t *w_hi,
-	uint64_t *w_lo, uint32_t *e_seq, int32_t *e_loc, uint32_t *e_strand, uint64_t *order_key)
+	uint64_t *w_lo, uint4 *e_planes, uint32_t *e_seq, int32_t *e_loc, uint32_t *e_strand, uint64_t *order_key)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint64_t id = entry_id[i];
-	const uint32_t seq = (uint32_t)(id >> 35), type = (uint32_t)(id >> 33) & 3u, minus = (uint32_t)(id >> 32) & 1u;
+	const uint32_t seq = (uint32_t)(id >> 35), type = (uint32_t)(id >> 32) & 3u, minus = (uint32_t)(id >> 34) & 1u;
 	W128 wp, wm;
 	int lp = 0, lm = 0;
 	wp.hi = wp.lo = wm.hi = wm.lo = 0;
@@ -70,6 +71,8 @@ __global__ void materialise_kernel(SeqDev sd, PackParams pp, const uint64_t *__r
 	const int loc = minus ? lm : lp;
 	w_hi[i] = w.hi;
 	w_lo[i] = w.lo;
+	const Planes4 pl = w_planes(w); // what pair scoring compares against (score.cuh)
+	e_planes[i] = make_uint4(pl.a, pl.c, pl.g, pl.t);
 	e_seq[i] = seq;
 	e_loc[i] = loc;
 	e_strand[i] = minus ? STRAND_MINUS : STRAND_PLUS;
@@ -126,17 +129,19 @@ __global__ void key_heads_kernel(const uint64_t *__restrict__ w_hi, const uint64
 	head[i] = (w_hi[a] != w_hi[b] || w_lo[a] != w_lo[b]) ? 1u : 0u;
 }
 
-// first entry of each sequence in the seq-grouped arrays: off[s] = lower_bound(e_seq, s)
-__global__ void seq_offsets_kernel(const uint32_t *__restrict__ e_seq, uint64_t n, uint32_t n_seq, uint32_t *off)
+// first entry of each (sequence, strand) run in the grouped arrays: off[2*s + minus] = lower_bound; off[2*n_seq] = n
+__global__ void seq_offsets_kernel(const uint32_t *__restrict__ e_seq, const uint32_t *__restrict__ e_strand, uint64_t n, uint32_t n_seq,
+	uint32_t *off)
 {
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s > n_seq) return;
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k > 2u * n_seq) return;
 	uint64_t lo = 0, hi = n;
 	while (lo < hi) {
 		const uint64_t mid = (lo + hi) >> 1;
-		if (e_seq[mid] < s) lo = mid + 1; else hi = mid;
+		const uint32_t key = 2u * e_seq[mid] + (e_strand[mid] == STRAND_MINUS ? 1u : 0u);
+		if (key < k) lo = mid + 1; else hi = mid;
 	}
-	off[s] = (uint32_t)lo;
+	off[k] = (uint32_t)lo;
 }
 
 __global__ void db_export_kernel(const uint64_t *__restrict__ w_hi, const uint64_t *__restrict__ w_lo, const uint32_t *__restrict__ e_seq,

@@ -59,7 +59,7 @@ struct SeqSet {
 	// database (seq-grouped order = entry-id order) + canonical permutation
 	uint64_t n_entries = 0, n_keys = 0;
 	bool db_valid = false;
-	DevBuf e_hi, e_lo, e_seq, e_loc, e_strand, e_perm, e_keyrank, seq_ent_off;
+	DevBuf e_hi, e_lo, e_planes, e_seq, e_loc, e_strand, e_perm, e_keyrank, seq_ent_off;
 
 	SeqDev dev() const
 	{
@@ -232,7 +232,7 @@ __global__ void cand_count_kernel(const uint64_t *__restrict__ f, const uint64_t
 // one oligo -> its candidate family (cand_words / cand_thr, used by the partial-word kernel and for the hit
 // keys) and ONE pattern per strand (masks + meta), classified for the seed filter
 __global__ void cand_build_kernel(const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs, int opt5, int opt3,
-	float threshold, const uint32_t *__restrict__ off, uint64_t *cand_words, uint32_t *cand_thr, uint4 *pat_mask, uint32_t *pat_meta,
+	float threshold, const uint32_t *__restrict__ off, uint4 *cand_planes, uint32_t *cand_thr, uint4 *pat_mask, uint32_t *pat_meta,
 	uint32_t *pat_meta2, uint32_t *pat_seeded)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,15 +245,16 @@ __global__ void cand_build_kernel(const uint64_t *__restrict__ f, const uint64_t
 	const uint32_t thr = (uint32_t)__fmul_rn((float)size, threshold); // select_words.cpp:83 (same for the whole family)
 	const uint32_t base = off[i];
 	uint32_t c = base;
-	cand_words[2 * c] = w.hi; cand_words[2 * c + 1] = w.lo; cand_thr[c] = thr; ++c;
+	const Planes4 fp = w_planes(w); // frame planes; a copy shifted j slots toward 5' is the planes shifted right by j bits
+	cand_planes[c] = make_uint4(fp.a, fp.c, fp.g, fp.t); cand_thr[c] = thr; ++c;
 	uint32_t nl = 0, nr = 0;
 	if (opt5 && start > 0 && start < 32) { // select_words.cpp:50-58
 		nl = (uint32_t)start;
-		for (int j = 1; j <= start; ++j, ++c) { const W128 v = w_shl(w, j); cand_words[2 * c] = v.hi; cand_words[2 * c + 1] = v.lo; cand_thr[c] = thr; }
+		for (int j = 1; j <= start; ++j, ++c) { cand_planes[c] = make_uint4(fp.a >> j, fp.c >> j, fp.g >> j, fp.t >> j); cand_thr[c] = thr; }
 	}
 	if (opt3 && stop >= 0 && stop < 31) { // :61-70
 		nr = (uint32_t)(31 - stop);
-		for (int j = 1; j <= 31 - stop; ++j, ++c) { const W128 v = w_shr(w, j); cand_words[2 * c] = v.hi; cand_words[2 * c + 1] = v.lo; cand_thr[c] = thr; }
+		for (int j = 1; j <= 31 - stop; ++j, ++c) { cand_planes[c] = make_uint4(fp.a << j, fp.c << j, fp.g << j, fp.t << j); cand_thr[c] = thr; }
 	}
 	uint4 mp = make_uint4(0, 0, 0, 0), mm = make_uint4(0, 0, 0, 0);
 	for (int k = 0; start + k <= stop; ++k) {
@@ -657,9 +658,9 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	pp.max_gc = max_gc;
 	pp.min_len = min_len;
 	pp.gc_filter = (min_gc > 0.0f) || (max_gc < 1.0f); // sequence.cpp:102
-	CK(s.seq_ent_off.ensure((size_t)(s.n + 1) * 4));
+	CK(s.seq_ent_off.ensure((size_t)(2 * s.n + 1) * 4));
 	if (s.n == 0 || n_pairs == 0) { // select_words.cpp:13-15
-		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(s.n + 1) * 4, st));
+		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(2 * s.n + 1) * 4, st));
 		CK(cudaStreamSynchronize(st));
 		s.db_valid = true;
 		return 0;
@@ -699,7 +700,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(ctx->d_part_meta.ensure((size_t)n_pat * 4));
 	CK(ctx->d_part_meta2.ensure((size_t)n_pat * 4));
 	cand_build_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->pf(), ctx->pr(), n_pairs, opt5, opt3, threshold,
-		ctx->d_cand_off.as<uint32_t>(), ctx->d_cand_words.as<uint64_t>(), ctx->d_cand_thr.as<uint32_t>(), ctx->d_pat_mask.as<uint4>(),
+		ctx->d_cand_off.as<uint32_t>(), ctx->d_cand_words.as<uint4>(), ctx->d_cand_thr.as<uint32_t>(), ctx->d_pat_mask.as<uint4>(),
 		ctx->d_pat_meta.as<uint32_t>(), ctx->d_pat_meta2.as<uint32_t>(), ctx->d_pat_seeded.as<uint32_t>());
 	CK(cudaGetLastError());
 	stat.kernel_launches++;
@@ -793,7 +794,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				seed_bucket_pack_kernel<<<grid_for(SEED_BUCKETS, 256), 256, 0, st>>>(ctx->d_seed_start.as<uint32_t>(), ctx->d_seed_cnt.as<uint32_t>(),
 					ctx->d_seed_bucket.as<uint32_t>());
 				CK(cudaGetLastError());
-				seed_fill_kernel<<<grid_for(cn, 128), 128, 0, st>>>(c_mask, c_meta2, cn, ctx->d_seed_start.as<uint32_t>(),
+				seed_fill_kernel<<<grid_for(cn, 128), 128, 0, st>>>(c_mask, c_meta, c_meta2, cn, ctx->d_seed_start.as<uint32_t>(),
 					ctx->d_seed_entries.as<uint32_t>(), ecap);
 				CK(cudaGetLastError());
 				SeedChunk ch;
@@ -835,7 +836,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		}
 		CK(cudaEventRecord(ctx->ev[1], st));
 		scan_edge_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n + 7) / 8, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(sd, pp,
-			ctx->d_cand_words.as<uint64_t>(), ctx->d_cand_thr.as<uint32_t>(), n_cand, cand_bits, hs);
+			ctx->d_cand_words.as<uint4>(), ctx->d_cand_thr.as<uint32_t>(), n_cand, cand_bits, hs);
 		CK(cudaGetLastError());
 		stat.kernel_launches++;
 		CK(cudaEventRecord(ctx->ev[2], st));
@@ -852,7 +853,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	stat.n_hits = n_hits;
 	CK(cudaEventRecord(ctx->ev[3], st));
 	if (n_hits == 0) {
-		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(s.n + 1) * 4, st));
+		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(2 * s.n + 1) * 4, st));
 		CK(cudaStreamSynchronize(st));
 		s.db_valid = true;
 		return 0;
@@ -886,7 +887,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(cudaStreamSynchronize(st));
 	const uint64_t n_flag = ctx->h_counters[0];
 	if (n_flag == 0) {
-		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(s.n + 1) * 4, st));
+		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(2 * s.n + 1) * 4, st));
 		CK(cudaStreamSynchronize(st));
 		s.db_valid = true;
 		return 0;
@@ -910,6 +911,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	// ---- materialise + canonical order + keys ------------------------------------------------
 	CK(s.e_hi.ensure(n_ent * 8));
 	CK(s.e_lo.ensure(n_ent * 8));
+	CK(s.e_planes.ensure(n_ent * 16));
 	CK(s.e_seq.ensure(n_ent * 4));
 	CK(s.e_loc.ensure(n_ent * 4));
 	CK(s.e_strand.ensure(n_ent * 4));
@@ -922,9 +924,10 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(ctx->head.ensure(n_ent * 4));
 	const unsigned ge = grid_for(n_ent, 256);
 	materialise_kernel<<<ge, 256, 0, st>>>(sd, pp, ctx->ent_id[0].as<uint64_t>(), n_ent, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(),
-		s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), ctx->order_key[0].as<uint64_t>());
+		s.e_planes.as<uint4>(), s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), ctx->order_key[0].as<uint64_t>());
 	CK(cudaGetLastError());
-	seq_offsets_kernel<<<grid_for((uint64_t)s.n + 1, 256), 256, 0, st>>>(s.e_seq.as<uint32_t>(), n_ent, s.n, s.seq_ent_off.as<uint32_t>());
+	seq_offsets_kernel<<<grid_for(2ull * s.n + 1, 256), 256, 0, st>>>(s.e_seq.as<uint32_t>(), s.e_strand.as<uint32_t>(), n_ent, s.n,
+		s.seq_ent_off.as<uint32_t>());
 	CK(cudaGetLastError());
 	iota_kernel<<<ge, 256, 0, st>>>(ctx->perm[0].as<uint32_t>(), n_ent);
 	CK(cudaGetLastError());
@@ -1058,7 +1061,7 @@ int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_th
 		ctx->stats.kernel_launches++;
 		if (s.n_entries) {
 			const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
-			score_kernel<<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), s.e_loc.as<int32_t>(),
+			score_kernel<<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(),
 				s.e_strand.as<uint32_t>(), s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>(), n_pairs, detect_threshold, amp_min,
 				amp_max, taq, ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
 			CK(cudaGetLastError());

@@ -232,13 +232,12 @@ scan_groups_kernel(SeqDev sd, const uint32_t *__restrict__ grp_seq, const uint32
 //
 // Shared memory (one CTA of 1024 threads per SM, everything hot is on chip):
 //   bucket[1024 + 4096]  per 2-bit seed code (q = 5, then q = 6): first entry | count << 20
-//   entries[]            seed -> (pattern << 5 | offset of the seed inside the pattern)
-//   mask[], meta[]       the chunk's pattern masks and thresholds
-//   grp[66], b0[66], b1[66]  the tile's planes with one halo group on each side, and the two code
-//                        planes b0 = C|T, b1 = G|T (A=00 C=01 G=10 T=11)
+//   entries[]            seed -> pattern << 11 | threshold << 5 | offset of the seed inside the pattern
+//   mask[]               the chunk's pattern masks
+//   grp[66]              the tile's planes with one halo group on each side
 // A thread takes 2 of the tile's 2048 text positions; the seed code at x is five / six low bits of
-// each code plane window.  For every (pattern, offset) in the bucket the alignment x - offset is
-// counted with the same 4 LOP3 + POPC as the brute-force kernel, planes funnel-shifted from smem.
+// the code planes b0 = C|T, b1 = G|T (A=00 C=01 G=10 T=11).  For every (pattern, offset) in the bucket
+// the alignment x - offset is counted with the same 4 LOP3 + POPC as the brute-force kernel.
 // An alignment found through several of its pieces is reported by the leftmost matching one only.
 // ---------------------------------------------------------------------------------------------
 constexpr int SEED_THREADS = 1024;
@@ -246,22 +245,28 @@ constexpr int SEED_R = SCAN_TILE / SEED_THREADS;       // 2
 constexpr int SEED_GROUPS = SCAN_TILE_GROUPS + 2;      // 66: halo group on both sides
 constexpr uint32_t SEED_BUCKETS = 1024u + 4096u;
 constexpr uint32_t SEED_MAX_EXPANSIONS = 64u;          // per pattern, over all its pieces
+constexpr uint32_t SEED_MAX_PATTERNS = 1u << 21;       // entry word: pattern[31:11] | thr[10:5] | offset[4:0]
 
 struct SeedChunk {
 	const uint32_t *bucket;  // SEED_BUCKETS words
 	const uint32_t *entries; // n_entries words
 	const uint4 *mask;       // n_pat
-	const uint32_t *meta;    // n_pat
-	const uint32_t *meta2;   // n_pat (read on hits only, stays in global memory)
+	const uint32_t *meta;    // n_pat (read on hits only, stays in global memory)
+	const uint32_t *meta2;   // n_pat (ditto)
 	uint32_t n_entries, n_pat;
 	uint32_t ecap, pcap;     // shared-memory capacities the launch was sized for (multiples of 4)
 };
 
 __host__ __device__ __forceinline__ size_t seed_smem_bytes(uint32_t ecap, uint32_t pcap)
 {
-	return (size_t)SEED_BUCKETS * 4 + (size_t)ecap * 4 + (size_t)pcap * 16 + (size_t)pcap * 4 + (size_t)SEED_GROUPS * 16 + 2 * (size_t)SEED_GROUPS * 4;
+	return (size_t)SEED_BUCKETS * 4 + (size_t)ecap * 4 + (size_t)pcap * 16 + (size_t)SEED_GROUPS * 16;
 }
 
+// Shared memory holds bucket[] | entries[] | mask[] | the tile's 66 plane groups.  A warp owns 32 consecutive
+// text positions per step, so every alignment it verifies (x - offset, offset <= 27) reads plane bits out of
+// the same three groups: they are broadcast-loaded once into registers and each verification is pure
+// register arithmetic plus ONE 16-byte shared load (the pattern masks) -- the kernel is bound by the
+// shared-memory pipe, so loads per verification are what counts (profiles/r01_summary.md).
 __global__ void __launch_bounds__(SEED_THREADS, 1)
 scan_seed_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_t *__restrict__ tile_x0, uint32_t n_tiles,
 	unsigned int *tile_counter, SeedChunk ch, const uint32_t *__restrict__ dirty_bits, uint32_t cand_bits, HitSink hs)
@@ -270,19 +275,13 @@ scan_seed_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_
 	uint32_t *s_bucket = smem;
 	uint32_t *s_entries = s_bucket + SEED_BUCKETS;
 	uint4 *s_mask = (uint4 *)(s_entries + ch.ecap);
-	uint32_t *s_meta = (uint32_t *)(s_mask + ch.pcap);
-	uint4 *s_grp = (uint4 *)(s_meta + ch.pcap);
-	uint32_t *s_b0 = (uint32_t *)(s_grp + SEED_GROUPS);
-	uint32_t *s_b1 = s_b0 + SEED_GROUPS;
+	uint4 *s_grp = s_mask + ch.pcap;
 	__shared__ uint32_t s_tile;
 
-	const uint32_t tid = threadIdx.x;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
 	for (uint32_t i = tid; i < SEED_BUCKETS; i += SEED_THREADS) s_bucket[i] = __ldg(ch.bucket + i);
 	for (uint32_t i = tid; i < ch.n_entries; i += SEED_THREADS) s_entries[i] = __ldg(ch.entries + i);
-	for (uint32_t i = tid; i < ch.n_pat; i += SEED_THREADS) {
-		s_mask[i] = __ldg(ch.mask + i);
-		s_meta[i] = __ldg(ch.meta + i);
-	}
+	for (uint32_t i = tid; i < ch.n_pat; i += SEED_THREADS) s_mask[i] = __ldg(ch.mask + i);
 
 	for (;;) {
 		__syncthreads(); // tables loaded / previous tile consumed
@@ -298,20 +297,19 @@ scan_seed_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_
 		const uint32_t clen = sd.clen[seq];
 		if (tid < SEED_GROUPS) {
 			const int64_t g = (int64_t)(x0 >> 5) - 1 + tid;
-			const uint4 v = (g >= 0 && g < (int64_t)ngrp) ? __ldg(sd.planes + gbase + g) : make_uint4(0, 0, 0, 0);
-			s_grp[tid] = v;
-			s_b0[tid] = v.y | v.w;
-			s_b1[tid] = v.z | v.w;
+			s_grp[tid] = (g >= 0 && g < (int64_t)ngrp) ? __ldg(sd.planes + gbase + g) : make_uint4(0, 0, 0, 0);
 		}
 		__syncthreads();
 
-		#pragma unroll
+		#pragma unroll 1
 		for (int r = 0; r < SEED_R; ++r) {
-			const uint32_t xl = r * SEED_THREADS + tid;
+			const uint32_t xl = r * SEED_THREADS + tid; // lane-consecutive, warp-aligned to a group
+			const uint32_t gi = 1u + (xl >> 5);          // the warp's own group inside the haloed tile
+			const uint4 gm = s_grp[gi - 1], gc = s_grp[gi], gp = s_grp[gi + 1]; // warp-uniform: broadcast loads
 			if (x0 + xl >= clen) continue;
-			const uint32_t bit = 32u + xl; // bit index inside the haloed tile
-			const uint32_t w0 = __funnelshift_r(s_b0[bit >> 5], s_b0[(bit >> 5) + 1], bit & 31u);
-			const uint32_t w1 = __funnelshift_r(s_b1[bit >> 5], s_b1[(bit >> 5) + 1], bit & 31u);
+			// seed codes at x: low q bits of the code planes b0 = C|T, b1 = G|T (A=00 C=01 G=10 T=11)
+			const uint32_t w0 = __funnelshift_r(gc.y | gc.w, gp.y | gp.w, lane);
+			const uint32_t w1 = __funnelshift_r(gc.z | gc.w, gp.z | gp.w, lane);
 			#pragma unroll
 			for (int t = 0; t < 2; ++t) {
 				const uint32_t code = t == 0 ? ((w0 & 31u) | ((w1 & 31u) << 5)) : (1024u + ((w0 & 63u) | ((w1 & 63u) << 6)));
@@ -319,23 +317,24 @@ scan_seed_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_
 				const uint32_t first = bk & 0xFFFFFu, count = bk >> 20;
 				for (uint32_t j = 0; j < count; ++j) {
 					const uint32_t en = s_entries[first + j];
-					const uint32_t pid = en >> 5, off = en & 31u;
-					const uint32_t bit2 = bit - off;
-					const uint4 lo = s_grp[bit2 >> 5], hi = s_grp[(bit2 >> 5) + 1];
-					const uint32_t sh = bit2 & 31u;
+					const uint32_t pid = en >> 11, off = en & 31u;
+					const int d = (int)lane - (int)off; // alignment start relative to the warp's group, in [-27, 31]
+					const bool left = d < 0;
+					const uint32_t sh = (uint32_t)d & 31u;
 					const uint4 b = s_mask[pid];
-					const uint32_t m = (b.x & __funnelshift_r(lo.x, hi.x, sh)) | (b.y & __funnelshift_r(lo.y, hi.y, sh)) |
-					                   (b.z & __funnelshift_r(lo.z, hi.z, sh)) | (b.w & __funnelshift_r(lo.w, hi.w, sh));
+					const uint32_t m = (b.x & __funnelshift_r(left ? gm.x : gc.x, left ? gc.x : gp.x, sh)) |
+					                   (b.y & __funnelshift_r(left ? gm.y : gc.y, left ? gc.y : gp.y, sh)) |
+					                   (b.z & __funnelshift_r(left ? gm.z : gc.z, left ? gc.z : gp.z, sh)) |
+					                   (b.w & __funnelshift_r(left ? gm.w : gc.w, left ? gc.w : gp.w, sh));
 					const int cnt = __popc(m);
-					const uint32_t meta = s_meta[pid];
-					if (cnt >= (int)(meta & 63u)) { // a binding site
+					if (cnt >= (int)((en >> 5) & 63u)) { // a binding site
 						const int64_t x = (int64_t)x0 + xl - off;
 						if (x < 0) continue;
 						if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
 							const uint64_t G = gbase + (uint64_t)(x >> 5);
 							if (((dirty_bits[G >> 5] >> (G & 31u)) & 1u)) continue;
 						}
-						const uint32_t meta2 = __ldg(ch.meta2 + pid);
+						const uint32_t meta = __ldg(ch.meta + pid), meta2 = __ldg(ch.meta2 + pid);
 						const uint32_t n = (meta2 >> 10) & 63u, pieces = ((meta2 >> 16) & 63u) + 1u, q = (meta2 >> 22) & 7u;
 						const uint32_t qmask = (1u << q) - 1u;
 						bool first_piece = true; // report through the leftmost exactly-matching piece only
@@ -355,7 +354,7 @@ scan_seed_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_
 // ---------------------------------------------------------------------------------------------
 // K1b: the partial words pack() emits at sequence starts, ends and EOS events (FILL / EOSEVT /
 // TAIL, seqdev.cuh).  A few dozen per sequence; they are built explicitly and compared with the
-// reference's own 128-bit formulation.  One warp per sequence, lanes = events, loop over candidates.
+// same letter-plane count as everywhere else.  One warp per sequence, lanes = events, loop over candidates.
 // ---------------------------------------------------------------------------------------------
 struct EdgeCounts {
 	uint32_t n_fill, n_eos, n_tail;
@@ -373,7 +372,7 @@ __device__ inline EdgeCounts edge_counts(const SeqDev &sd, uint32_t seq, const P
 }
 
 __global__ void __launch_bounds__(256)
-scan_edge_kernel(SeqDev sd, PackParams pp, const uint64_t *__restrict__ cand_words, const uint32_t *__restrict__ cand_thr,
+scan_edge_kernel(SeqDev sd, PackParams pp, const uint4 *__restrict__ cand_planes, const uint32_t *__restrict__ cand_thr,
 	uint32_t n_cand, uint32_t cand_bits, HitSink hs)
 {
 	const uint32_t lane = threadIdx.x & 31u;
@@ -397,13 +396,14 @@ scan_edge_kernel(SeqDev sd, PackParams pp, const uint64_t *__restrict__ cand_wor
 			wp.hi = wp.lo = wm.hi = wm.lo = 0;
 			ok = ok && pack_entry(sd, seq, type, pos, pp, wp, wm, lp, lm);
 			if (!__any_sync(0xffffffffu, ok)) continue;
+			const Planes4 pp4 = w_planes(wp), pm4 = w_planes(wm);
+			#pragma unroll 4
 			for (uint32_t c = 0; c < n_cand; ++c) {
-				W128 cw;
-				cw.hi = __ldg(cand_words + 2 * c);
-				cw.lo = __ldg(cand_words + 2 * c + 1);
+				const uint4 cv = __ldg(cand_planes + c); // uniform address: one broadcast load per warp
 				const int thr = (int)__ldg(cand_thr + c);
-				if (ok) {
-					const int np = w_and_count(cw, wp), nm = w_and_count(cw, wm);
+				const int np = __popc((cv.x & pp4.a) | (cv.y & pp4.c) | (cv.z & pp4.g) | (cv.w & pp4.t));
+				const int nm = __popc((cv.x & pm4.a) | (cv.y & pm4.c) | (cv.z & pm4.g) | (cv.w & pm4.t));
+				if (ok && (np >= thr || nm >= thr)) {
 					if (np >= thr) hit_append(hs, hit_key_pack(seq, c, cand_bits, (uint32_t)np, type, 0u), pos);
 					if (nm >= thr) hit_append(hs, hit_key_pack(seq, c, cand_bits, (uint32_t)nm, type, 1u), pos);
 				}
@@ -517,17 +517,18 @@ __global__ void seed_count_kernel(const uint4 *__restrict__ mask, const uint32_t
 }
 
 // bucket_cnt holds the exclusive start of every bucket on entry and is advanced as a cursor
-__global__ void seed_fill_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta2, uint32_t n_pat, uint32_t *cursor,
-	uint32_t *entries, uint32_t ecap)
+__global__ void seed_fill_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ meta2,
+	uint32_t n_pat, uint32_t *cursor, uint32_t *entries, uint32_t ecap)
 {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n_pat) return;
 	const uint4 m = mask[p];
+	const uint32_t thr = meta[p] & 63u;
 	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u, q = (m2 >> 22) & 7u;
 	for (uint32_t i = 0; i < pieces; ++i)
 		for_each_seed(m, n, pieces, q, i, [&](uint32_t code, uint32_t o) {
 			const uint32_t slot = atomicAdd(cursor + code, 1u);
-			if (slot < ecap) entries[slot] = (p << 5) | o;
+			if (slot < ecap) entries[slot] = (p << 11) | (thr << 5) | o;
 		});
 }
 

@@ -15,7 +15,7 @@
 namespace pcr {
 
 struct OligoDev {
-	uint64_t hi, lo;
+	uint32_t a, c, g, t; // letter planes over the frame (word128.cuh)
 	float norm;      // float(1.0 / len), optimize.cpp:221
 	uint32_t packed; // thr[7:0] | start[15:8] | stop[23:16] | penultimate nibble[27:24] | last nibble[31:28]
 };
@@ -57,8 +57,8 @@ __global__ void prep_oligos_kernel(const uint64_t *__restrict__ f, const uint64_
 	w.lo = src[2 * (i >> 1) + 1];
 	const int size = w_size(w), start = w_start(w), stop = w_stop(w);
 	OligoDev o;
-	o.hi = w.hi;
-	o.lo = w.lo;
+	const Planes4 pl = w_planes(w);
+	o.a = pl.a; o.c = pl.c; o.g = pl.g; o.t = pl.t;
 	o.norm = size > 0 ? (float)(1.0 / (double)size) : 0.0f;
 	const uint32_t thr = (uint32_t)__fmul_rn((float)size, thr2);
 	const uint32_t pen = stop >= 1 ? w_get(w, stop - 1) : 0u, last = stop >= 0 ? w_get(w, stop) : 0u;
@@ -67,13 +67,18 @@ __global__ void prep_oligos_kernel(const uint64_t *__restrict__ f, const uint64_
 }
 
 struct ScoreEntry {
-	uint64_t hi, lo;
+	uint32_t a, c, g, t; // letter planes of the database word
 	int32_t loc;
 	uint32_t strand;
 };
 
+__device__ __forceinline__ int oligo_count(const OligoDev &o, const ScoreEntry &e)
+{ // Word::operator& (word.cpp:111-154) on letter planes: 4 LOP3 + POPC
+	return __popc((o.a & e.a) | (o.c & e.c) | (o.g & e.g) | (o.t & e.t));
+}
+
 // identity of an oligo against one database word (optimize.cpp:221-259)
-__device__ __forceinline__ float oligo_identity(const OligoDev &o, int count, uint64_t e_hi, uint64_t e_lo, int taq)
+__device__ __forceinline__ float oligo_identity(const OligoDev &o, int count, const ScoreEntry &e, int taq)
 {
 	float v = __fmul_rn((float)count, o.norm);
 	if (taq) {
@@ -81,10 +86,9 @@ __device__ __forceinline__ float oligo_identity(const OligoDev &o, int count, ui
 		const int a = taq_index(p0), b = taq_index(p1);
 		if (a >= 0 && b >= 0) { // neither primer base degenerate
 			const int stop = (int)((o.packed >> 16) & 255u);
-			W128 e;
-			e.hi = e_hi;
-			e.lo = e_lo;
-			const int c = stop >= 1 ? taq_index(w_get(e, stop - 1)) : -1, d = taq_index(w_get(e, stop));
+			Planes4 ep;
+			ep.a = e.a; ep.c = e.c; ep.g = e.g; ep.t = e.t;
+			const int c = stop >= 1 ? taq_index(planes_nibble(ep, stop - 1)) : -1, d = taq_index(planes_nibble(ep, stop));
 			if (c >= 0 && d >= 0) v = __fmul_rn(v, fminf(1.0f, c_taq_mama[16 * (4 * d + c) + (4 * b + a)]));
 		}
 	}
@@ -94,60 +98,62 @@ __device__ __forceinline__ float oligo_identity(const OligoDev &o, int count, ui
 constexpr int SCORE_THREADS = 256;
 constexpr int SCORE_SMEM_ENTRIES = 1024; // 24 KB; longer per-sequence lists spill to L2 reads
 
-// one pass of collect_candidates: oligo P binds the plus strand, oligo M the minus strand
-__device__ inline bool amplicon_pass(const SeqDev &sd, uint32_t seq, const ScoreEntry *s_ent, const uint64_t *__restrict__ g_hi,
-	const uint64_t *__restrict__ g_lo, const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand, uint32_t e0, uint32_t E,
-	const OligoDev &P, const OligoDev &M, float detect, int amp_min, int amp_max, int taq, uint32_t lane)
+__device__ __forceinline__ ScoreEntry load_entry(const ScoreEntry *s_ent, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc,
+	const uint32_t *__restrict__ g_strand, uint32_t e0, uint32_t e)
+{
+	if (e < (uint32_t)SCORE_SMEM_ENTRIES) return s_ent[e];
+	ScoreEntry en;
+	const uint4 v = g_pl[e0 + e];
+	en.a = v.x; en.c = v.y; en.g = v.z; en.t = v.w;
+	en.loc = g_loc[e0 + e];
+	en.strand = g_strand[e0 + e];
+	return en;
+}
+
+// one pass of collect_candidates: oligo P binds the plus strand (entries [0, Ep)), oligo M the minus strand
+// (entries [Ep, E)).  Warp-cooperative: lanes take entries.
+__device__ inline bool amplicon_pass(const SeqDev &sd, uint32_t seq, const ScoreEntry *s_ent, const uint4 *__restrict__ g_pl,
+	const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand, uint32_t e0, uint32_t Ep, uint32_t E, const OligoDev &P,
+	const OligoDev &M, float detect, int amp_min, int amp_max, int taq, uint32_t lane)
 {
 	const int p_thr = (int)(P.packed & 255u), p_start = (int)((P.packed >> 8) & 255u), p_stop = (int)((P.packed >> 16) & 255u);
 	const int m_thr = (int)(M.packed & 255u), m_start = (int)((M.packed >> 8) & 255u), m_stop = (int)((M.packed >> 16) & 255u);
 	const int L = (int)sd.len[seq];
-	W128 pw, mw;
-	pw.hi = P.hi; pw.lo = P.lo;
-	mw.hi = M.hi; mw.lo = M.lo;
-	for (uint32_t base = 0; base < E; base += 32u) {
+	for (uint32_t base = 0; base < Ep; base += 32u) {
 		const uint32_t e = base + lane;
 		ScoreEntry en;
-		en.hi = en.lo = 0; en.loc = 0; en.strand = 0;
-		if (e < E) {
-			if (e < (uint32_t)SCORE_SMEM_ENTRIES) en = s_ent[e];
-			else { en.hi = g_hi[e0 + e]; en.lo = g_lo[e0 + e]; en.loc = g_loc[e0 + e]; en.strand = g_strand[e0 + e]; }
-		}
-		W128 ew;
-		ew.hi = en.hi; ew.lo = en.lo;
-		const int cp = w_and_count(pw, ew);
-		uint32_t plus_mask = __ballot_sync(0xffffffffu, e < E && en.strand == STRAND_PLUS && cp >= p_thr);
+		en.a = en.c = en.g = en.t = 0u; en.loc = 0; en.strand = 0u;
+		if (e < Ep) en = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e);
+		const int cp = oligo_count(P, en);
+		uint32_t plus_mask = __ballot_sync(0xffffffffu, e < Ep && cp >= p_thr);
 		while (plus_mask) {
 			const int src = __ffs(plus_mask) - 1;
 			plus_mask &= plus_mask - 1u;
-			const int loc_p = __shfl_sync(0xffffffffu, en.loc, src);
+			ScoreEntry pe;
+			pe.a = __shfl_sync(0xffffffffu, en.a, src); pe.c = __shfl_sync(0xffffffffu, en.c, src);
+			pe.g = __shfl_sync(0xffffffffu, en.g, src); pe.t = __shfl_sync(0xffffffffu, en.t, src);
+			pe.loc = __shfl_sync(0xffffffffu, en.loc, src);
+			pe.strand = STRAND_PLUS;
 			const int cnt_p = __shfl_sync(0xffffffffu, cp, src);
-			const uint64_t hi_p = __shfl_sync(0xffffffffu, en.hi, src), lo_p = __shfl_sync(0xffffffffu, en.lo, src);
-			const float ident_p = oligo_identity(P, cnt_p, hi_p, lo_p, taq);
-			const int plus_loc3 = loc_p + p_stop; // sequence.h:67-75, plus strand
-			for (uint32_t base2 = 0; base2 < E; base2 += 32u) {
+			const float ident_p = oligo_identity(P, cnt_p, pe, taq);
+			const int plus_loc3 = pe.loc + p_stop; // sequence.h:67-75, plus strand
+			for (uint32_t base2 = Ep; base2 < E; base2 += 32u) {
 				const uint32_t e2 = base2 + lane;
 				bool ok = false;
 				if (e2 < E) {
-					ScoreEntry m2;
-					if (e2 < (uint32_t)SCORE_SMEM_ENTRIES) m2 = s_ent[e2];
-					else { m2.hi = g_hi[e0 + e2]; m2.lo = g_lo[e0 + e2]; m2.loc = g_loc[e0 + e2]; m2.strand = g_strand[e0 + e2]; }
-					if (m2.strand == STRAND_MINUS) {
-						W128 w2;
-						w2.hi = m2.hi; w2.lo = m2.lo;
-						const int cm = w_and_count(mw, w2);
-						if (cm >= m_thr) {
-							const int minus_loc5 = m2.loc - m_stop; // sequence.h:57-65, minus strand
-							if (plus_loc3 < minus_loc5) {             // pcr_assay.cpp:368-371
-								int amp_start = loc_p + p_start;
-								const int amp_stop = min(m2.loc - m_start, L - 1);
-								int amp_len = amp_stop - amp_start + 1;
-								if (amp_len >= amp_min && amp_len <= amp_max) { // :383-392
-									if (amp_start < 0) { amp_len += amp_start; amp_start = 0; } // :412-416
-									if (amp_len >= 0 && !has_split_dev(sd, seq, amp_start, amp_len)) { // :418
-										const float ident_m = oligo_identity(M, cm, m2.hi, m2.lo, taq);
-										ok = __fsqrt_rn(__fmul_rn(ident_p, ident_m)) >= detect; // :292-294
-									}
+					const ScoreEntry m2 = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e2);
+					const int cm = oligo_count(M, m2);
+					if (cm >= m_thr) {
+						const int minus_loc5 = m2.loc - m_stop; // sequence.h:57-65, minus strand
+						if (plus_loc3 < minus_loc5) {             // pcr_assay.cpp:368-371
+							int amp_start = pe.loc + p_start;
+							const int amp_stop = min(m2.loc - m_start, L - 1);
+							int amp_len = amp_stop - amp_start + 1;
+							if (amp_len >= amp_min && amp_len <= amp_max) { // :383-392
+								if (amp_start < 0) { amp_len += amp_start; amp_start = 0; } // :412-416
+								if (amp_len >= 0 && !has_split_dev(sd, seq, amp_start, amp_len)) { // :418
+									const float ident_m = oligo_identity(M, cm, m2, taq);
+									ok = __fsqrt_rn(__fmul_rn(ident_p, ident_m)) >= detect; // :292-294
 								}
 							}
 						}
@@ -160,32 +166,66 @@ __device__ inline bool amplicon_pass(const SeqDev &sd, uint32_t seq, const Score
 	return false;
 }
 
+// One CTA per sequence; its database entries (plus strand first) sit in shared memory.
+//   filter: a warp takes 32 pairs, ONE PAIR PER LANE with both oligos' planes in registers, and sweeps the
+//           entries (broadcast loads): does F (R) reach its match_words threshold on any plus entry, on any
+//           minus entry?  A pair can only amplify this sequence if F+ & R- or R+ & F- (pcr_assay.cpp:37-59).
+//           ~14 instructions per (32 pairs x entry); all but ~1 in 10^3 (pair, sequence) combinations end here.
+//   exact:  the surviving pairs of the warp are scored one after the other by the whole warp
+//           (amplicon_pass: geometry, has_split, identities).
 __global__ void __launch_bounds__(SCORE_THREADS)
-score_kernel(SeqDev sd, const uint64_t *__restrict__ g_hi, const uint64_t *__restrict__ g_lo, const int32_t *__restrict__ g_loc,
-	const uint32_t *__restrict__ g_strand, const uint32_t *__restrict__ seq_off, const OligoDev *__restrict__ oligos, uint32_t n_pairs,
-	float detect, int amp_min, int amp_max, int taq, uint32_t *bits_any, uint32_t *bits_pass1, uint32_t n_words)
+score_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand,
+	const uint32_t *__restrict__ seq_off2, const OligoDev *__restrict__ oligos, uint32_t n_pairs, float detect, int amp_min, int amp_max,
+	int taq, uint32_t *bits_any, uint32_t *bits_pass1, uint32_t n_words)
 {
 	__shared__ ScoreEntry s_ent[SCORE_SMEM_ENTRIES];
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = SCORE_THREADS / 32;
+	const uint32_t n_chunks = (n_pairs + 31u) / 32u;
 	for (uint32_t seq = blockIdx.x; seq < sd.n; seq += gridDim.x) {
-		const uint32_t e0 = seq_off[seq], E = seq_off[seq + 1] - e0;
-		if (E == 0u || !sd.active[seq]) continue; // optimize.cpp:280-283
+		const uint32_t e0 = seq_off2[2 * seq], Ep = seq_off2[2 * seq + 1] - e0, E = seq_off2[2 * seq + 2] - e0;
+		if (Ep == 0u || Ep == E || !sd.active[seq]) continue; // needs both strands; inactive: optimize.cpp:280-283
 		__syncthreads();
 		for (uint32_t i = threadIdx.x; i < min(E, (uint32_t)SCORE_SMEM_ENTRIES); i += SCORE_THREADS) {
 			ScoreEntry en;
-			en.hi = g_hi[e0 + i]; en.lo = g_lo[e0 + i]; en.loc = g_loc[e0 + i]; en.strand = g_strand[e0 + i];
+			const uint4 v = g_pl[e0 + i];
+			en.a = v.x; en.c = v.y; en.g = v.z; en.t = v.w;
+			en.loc = g_loc[e0 + i]; en.strand = g_strand[e0 + i];
 			s_ent[i] = en;
 		}
 		__syncthreads();
-		for (uint32_t p = warp; p < n_pairs; p += n_warps) {
-			const OligoDev F = oligos[2 * p], R = oligos[2 * p + 1];
-			// {F(+), R(-)} then {R(+), F(-)}  (pcr_assay.cpp:37-59)
-			const bool d1 = amplicon_pass(sd, seq, s_ent, g_hi, g_lo, g_loc, g_strand, e0, E, F, R, detect, amp_min, amp_max, taq, lane);
-			const bool d2 = d1 ? false : amplicon_pass(sd, seq, s_ent, g_hi, g_lo, g_loc, g_strand, e0, E, R, F, detect, amp_min, amp_max, taq, lane);
-			if (lane == 0u && (d1 || d2)) {
-				const uint32_t bit = 1u << (seq & 31u);
-				atomicOr(bits_any + (size_t)p * n_words + (seq >> 5), bit);
-				if (d1) atomicOr(bits_pass1 + (size_t)p * n_words + (seq >> 5), bit);
+		for (uint32_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+			const uint32_t p = chunk * 32u + lane;
+			OligoDev F, R;
+			F.a = F.c = F.g = F.t = R.a = R.c = R.g = R.t = 0u;
+			F.norm = R.norm = 0.0f;
+			F.packed = R.packed = 255u; // threshold nothing reaches
+			if (p < n_pairs) { F = oligos[2 * p]; R = oligos[2 * p + 1]; }
+			const int f_thr = (int)(F.packed & 255u), r_thr = (int)(R.packed & 255u);
+			bool fp = false, rp = false, fm = false, rm = false;
+			for (uint32_t e = 0; e < Ep; ++e) { // plus-strand entries
+				const ScoreEntry en = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e);
+				fp |= oligo_count(F, en) >= f_thr;
+				rp |= oligo_count(R, en) >= r_thr;
+			}
+			for (uint32_t e = Ep; e < E; ++e) { // minus-strand entries
+				const ScoreEntry en = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e);
+				fm |= oligo_count(F, en) >= f_thr;
+				rm |= oligo_count(R, en) >= r_thr;
+			}
+			uint32_t todo = __ballot_sync(0xffffffffu, (fp && rm) || (rp && fm));
+			while (todo) {
+				const uint32_t src = (uint32_t)__ffs(todo) - 1u;
+				todo &= todo - 1u;
+				const uint32_t q = chunk * 32u + src;
+				const OligoDev Fq = oligos[2 * q], Rq = oligos[2 * q + 1];
+				// {F(+), R(-)} then {R(+), F(-)}  (pcr_assay.cpp:37-59)
+				const bool d1 = amplicon_pass(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Fq, Rq, detect, amp_min, amp_max, taq, lane);
+				const bool d2 = d1 ? false : amplicon_pass(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Rq, Fq, detect, amp_min, amp_max, taq, lane);
+				if (lane == 0u && (d1 || d2)) {
+					const uint32_t bit = 1u << (seq & 31u);
+					atomicOr(bits_any + (size_t)q * n_words + (seq >> 5), bit);
+					if (d1) atomicOr(bits_pass1 + (size_t)q * n_words + (seq >> 5), bit);
+				}
 			}
 		}
 	}

@@ -162,6 +162,38 @@ PCR_HD uint64_t w_degeneracy_sat(const W128 &a)
 	return d;
 }
 
+// The word as four 32-bit letter planes over the FRAME: bit k of plane l set iff nibble k admits letter l.
+// With both operands in this form Word::operator& is popc((a.A&b.A)|(a.C&b.C)|(a.G&b.G)|(a.T&b.T)).
+struct Planes4 {
+	uint32_t a, c, g, t;
+};
+PCR_HD Planes4 w_planes(const W128 &w)
+{
+	Planes4 p;
+	p.a = p.c = p.g = p.t = 0u;
+	for (int k = 0; k < WORD_LEN; ++k) {
+		const uint32_t b = w_get(w, k);
+		p.a |= (b & 1u) << k;
+		p.c |= ((b >> 1) & 1u) << k;
+		p.g |= ((b >> 2) & 1u) << k;
+		p.t |= ((b >> 3) & 1u) << k;
+	}
+	return p;
+}
+PCR_HD int planes_and_count(const Planes4 &x, const Planes4 &y)
+{
+	const uint32_t m = (x.a & y.a) | (x.c & y.c) | (x.g & y.g) | (x.t & y.t);
+#if defined(__CUDA_ARCH__)
+	return __popc(m);
+#else
+	return __builtin_popcount(m);
+#endif
+}
+PCR_HD uint32_t planes_nibble(const Planes4 &p, int k)
+{
+	return ((p.a >> k) & 1u) | (((p.c >> k) & 1u) << 1) | (((p.g >> k) & 1u) << 2) | (((p.t >> k) & 1u) << 3);
+}
+
 PCR_HD bool is_degen_nibble(uint32_t b) { return !(b == 1u || b == 2u || b == 4u || b == 8u); } // base_table.h:124-137
 
 } // namespace pcr
