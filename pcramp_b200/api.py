@@ -12,7 +12,7 @@ import numpy as np
 TARGET, BACKGROUND, MULTIPLEX = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpcramp_gpu.so")
+LIB_PATH = os.environ.get("PCRAMP_GPU_LIB") or os.path.join(_HERE, "csrc", "libpcramp_gpu.so")
 
 _u64p = ctypes.POINTER(ctypes.c_uint64)
 _u32p = ctypes.POINTER(ctypes.c_uint32)

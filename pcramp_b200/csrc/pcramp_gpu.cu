@@ -274,9 +274,8 @@ __global__ void cand_build_kernel(const uint64_t *__restrict__ f, const uint64_t
 	uint32_t e = 0, cls = 0;
 	if (thr >= 1u && thr <= (uint32_t)size && (uint32_t)size == n) {
 		e = (uint32_t)size - thr;
-		const uint32_t piece = n / (e + 1u);
-		cls = piece >= 6u ? 6u : (piece >= 5u ? 5u : 0u);
-		if (cls && (seed_entries_needed(mp, n, e + 1u, cls) == 0u || seed_entries_needed(mm, n, e + 1u, cls) == 0u)) cls = 0u;
+		cls = (n / (e + 1u) >= SEED_QMIN) ? 1u : 0u; // every piece of the even split has at least 5 bases
+		if (cls && (seed_entries_needed(mp, n, e + 1u) == 0u || seed_entries_needed(mm, n, e + 1u) == 0u)) cls = 0u;
 	}
 	pat_mask[2 * i] = mp;
 	pat_meta[2 * i] = pat_meta_pack(thr, (uint32_t)start, 0u, base);

@@ -19,8 +19,8 @@
 //
 // Three kernels produce the same flat hit list (candidate, strand, sequence, window, count >= thr):
 //   scan_seed_kernel   the fast path.  count >= thr allows e = n - thr mismatches, so of e+1 disjoint
-//                      pieces of the primer one must match exactly (pigeonhole).  Piece seeds of q = 5
-//                      or 6 bases (all IUPAC expansions) are indexed by their 2-bit code in shared memory;
+//                      pieces of the primer one must match exactly (pigeonhole).  Piece seeds of q = 5,
+//                      6 or 7 bases (all IUPAC expansions) are indexed by their 2-bit code in shared memory;
 //                      each text position looks up the primers having that seed and only those
 //                      alignments are counted.  Exact, ~10^2-10^3 x fewer alignments than brute force.
 //   scan_full_kernel   brute force over all alignments, for patterns whose pieces would be < 5 bases
@@ -231,21 +231,29 @@ scan_groups_kernel(SeqDev sd, const uint32_t *__restrict__ grp_seq, const uint32
 // K1 fast path: pigeonhole seed filter.
 //
 // Shared memory (one CTA of 1024 threads per SM, everything hot is on chip):
-//   bucket[1024 + 4096]  per 2-bit seed code (q = 5, then q = 6): first entry | count << 20
-//   entries[]            seed -> pattern << 11 | threshold << 5 | offset of the seed inside the pattern
+//   bucket[1024 + 4096 + 8192]  per 2-bit seed code (q = 5, 6, 7): first entry | count << 20
+//   entries[]            seed -> pattern << 11 | threshold << 5 | 27 - offset of the seed inside the pattern
 //   mask[]               the chunk's pattern masks
-//   grp[66]              the tile's planes with one halo group on each side
-// A thread takes 2 of the tile's 2048 text positions; the seed code at x is five / six low bits of
-// the code planes b0 = C|T, b1 = G|T (A=00 C=01 G=10 T=11).  For every (pattern, offset) in the bucket
-// the alignment x - offset is counted with the same 4 LOP3 + POPC as the brute-force kernel.
-// An alignment found through several of its pieces is reported by the leftmost matching one only.
+// The seed code at text position x is the q low bits of the code planes b0 = C|T, b1 = G|T (A=00 C=01 G=10
+// T=11).  For every (pattern, offset) in the bucket the alignment x - offset is counted with the same
+// 4 LOP3 + POPC as the brute-force kernel.  A primer's e+1 pieces are the even split of its n bases; a
+// piece's seed is its first min(len, 7) bases.  An alignment found through several of its pieces is
+// reported by the leftmost matching one only.
 // ---------------------------------------------------------------------------------------------
 constexpr int SEED_THREADS = 1024;
-constexpr int SEED_R = SCAN_TILE / SEED_THREADS;       // 2
-constexpr int SEED_GROUPS = SCAN_TILE_GROUPS + 2;      // 66: halo group on both sides
-constexpr uint32_t SEED_BUCKETS = 1024u + 4096u;
+constexpr uint32_t SEED_B5 = 0u, SEED_B6 = 1024u, SEED_B7 = 1024u + 4096u; // bucket table offsets per seed length
+constexpr uint32_t SEED_BUCKETS = 1024u + 4096u + 8192u;                    // q = 7 codes (14 bits) are folded to 13
 constexpr uint32_t SEED_MAX_EXPANSIONS = 64u;          // per pattern, over all its pieces
-constexpr uint32_t SEED_MAX_PATTERNS = 1u << 21;       // entry word: pattern[31:11] | thr[10:5] | offset[4:0]
+constexpr uint32_t SEED_MAX_PATTERNS = 1u << 21;       // entry word: pattern[31:11] | thr[10:5] | 27 - offset[4:0]
+constexpr uint32_t SEED_QMIN = 5u, SEED_QMAX = 7u;
+
+__host__ __device__ __forceinline__ uint32_t seed_bucket_index(uint32_t q, uint32_t b0, uint32_t b1)
+{ // b0 / b1 = the q low bits of the two code planes
+	if (q == 5u) return SEED_B5 + (b0 | (b1 << 5));
+	if (q == 6u) return SEED_B6 + (b0 | (b1 << 6));
+	const uint32_t c = b0 | (b1 << 7);
+	return SEED_B7 + ((c ^ (c >> 13)) & 8191u); // two codes per bucket; verification discards the stranger
+}
 
 struct SeedChunk {
 	const uint32_t *bucket;  // SEED_BUCKETS words
@@ -259,94 +267,145 @@ struct SeedChunk {
 
 __host__ __device__ __forceinline__ size_t seed_smem_bytes(uint32_t ecap, uint32_t pcap)
 {
-	return (size_t)SEED_BUCKETS * 4 + (size_t)ecap * 4 + (size_t)pcap * 16 + (size_t)SEED_GROUPS * 16;
+	return (size_t)SEED_BUCKETS * 4 + (size_t)ecap * 4 + (size_t)pcap * 16;
 }
 
-// Shared memory holds bucket[] | entries[] | mask[] | the tile's 66 plane groups.  A warp owns 32 consecutive
-// text positions per step, so every alignment it verifies (x - offset, offset <= 27) reads plane bits out of
-// the same three groups: they are broadcast-loaded once into registers and each verification is pure
-// register arithmetic plus ONE 16-byte shared load (the pattern masks) -- the kernel is bound by the
-// shared-memory pipe, so loads per verification are what counts (profiles/r01_summary.md).
+// piece i of a pattern of n bases cut into `pieces`: [o, o + len); its seed is the first q = min(len, 7) bases
+__host__ __device__ __forceinline__ void seed_piece(uint32_t n, uint32_t pieces, uint32_t i, uint32_t &o, uint32_t &q)
+{
+	o = (i * n) / pieces;
+	const uint32_t len = ((i + 1u) * n) / pieces - o;
+	q = len < SEED_QMAX ? len : SEED_QMAX;
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+	uint4 v;
+	asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+
+// bits [start, start + 64) of the 96-bit string lo:mid:hi (bit 0 = LSB of lo), zero beyond; start in [0, 63]
+__device__ __forceinline__ void take64(uint32_t lo, uint32_t mid, uint32_t hi, uint32_t start, uint32_t &o_lo, uint32_t &o_hi)
+{
+	const bool up = start >= 32u;
+	const uint32_t sh = start & 31u;
+	o_lo = __funnelshift_r(up ? mid : lo, up ? hi : mid, sh);
+	o_hi = __funnelshift_r(up ? hi : mid, up ? 0u : hi, sh);
+}
+
+__device__ __forceinline__ void seed_hit(uint32_t en, uint32_t m, uint32_t xpos, uint64_t gbase, const uint32_t *__restrict__ dirty_bits,
+	const uint32_t *__restrict__ g_meta, const uint32_t *__restrict__ g_meta2, uint32_t seq, uint32_t clen, uint32_t cand_bits, const HitSink &hs)
+{
+	const uint32_t off = 27u - (en & 31u), pid = en >> 11;
+	const int64_t x = (int64_t)xpos - off;
+	if (x < 0) return;
+	if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
+		const uint64_t G = gbase + (uint64_t)(x >> 5);
+		if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) return;
+	}
+	const uint32_t meta = __ldg(g_meta + pid), meta2 = __ldg(g_meta2 + pid);
+	const uint32_t n = (meta2 >> 10) & 63u, pieces = ((meta2 >> 16) & 63u) + 1u;
+	for (uint32_t i = 0; i < pieces; ++i) { // report through the leftmost exactly-matching piece only
+		uint32_t o, pq;
+		seed_piece(n, pieces, i, o, pq);
+		if (o >= off) break;
+		const uint32_t pm = (1u << pq) - 1u;
+		if (((m >> o) & pm) == pm) return;
+	}
+	emit_family(hs, seq, clen, cand_bits, meta, meta2, x, (uint32_t)__popc(m));
+}
+
+// one table entry: count the alignment it proposes (1 shared load + 4 SHF + 4 LOP3 + POPC + compare)
+#define seed_verify(EN, A_MASK, CA0, CA1, CC0, CC1, CG0, CG1, CT0, CT1, XPOS, GBASE, DIRTY, CH, SEQ, CLEN, CBITS, HS)                     \
+	do {                                                                                                                              \
+		const uint32_t en__ = (EN);                                                                                                   \
+		const uint4 b__ = lds128((A_MASK) + ((en__ >> 7) & 0x1FFFFF0u));                                                            \
+		const uint32_t sh__ = en__ & 31u;                                                                                             \
+		const uint32_t m__ = (b__.x & __funnelshift_r(CA0, CA1, sh__)) | (b__.y & __funnelshift_r(CC0, CC1, sh__)) |                  \
+		                     (b__.z & __funnelshift_r(CG0, CG1, sh__)) | (b__.w & __funnelshift_r(CT0, CT1, sh__));                  \
+		if ((uint32_t)__popc(m__) << 5 >= (en__ & 0x7E0u)) /* count >= thr: a binding site (rare) */                                  \
+			seed_hit(en__, m__, XPOS, GBASE, DIRTY, (CH).meta, (CH).meta2, SEQ, CLEN, CBITS, HS);                                    \
+	} while (0)
+
+// The seed table and the pattern masks are staged once per CTA in shared memory (the only barrier).  After
+// that every WARP works alone: it pulls a tile (64 groups = 2048 text positions of one sequence) from a
+// global counter and slides over it one group at a time -- lane = text position, the group's planes and its
+// two neighbours arrive as warp-uniform 16-byte loads straight from L2 (each base is read once; there is no
+// shared-memory tile and no block barrier to wait at).  Per step a lane cuts, for each letter plane, the 64
+// bits that every alignment it may have to verify falls into (x - offset, offset <= 27), so a verification is
+// ONE 16-byte shared load (pattern masks) + 4 funnel shifts + 4 LOP3 + POPC.
 __global__ void __launch_bounds__(SEED_THREADS, 1)
 scan_seed_kernel(SeqDev sd, const uint32_t *__restrict__ tile_seq, const uint32_t *__restrict__ tile_x0, uint32_t n_tiles,
 	unsigned int *tile_counter, SeedChunk ch, const uint32_t *__restrict__ dirty_bits, uint32_t cand_bits, HitSink hs)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
-	uint32_t *s_bucket = smem;
-	uint32_t *s_entries = s_bucket + SEED_BUCKETS;
-	uint4 *s_mask = (uint4 *)(s_entries + ch.ecap);
-	uint4 *s_grp = s_mask + ch.pcap;
-	__shared__ uint32_t s_tile;
-
-	const uint32_t tid = threadIdx.x, lane = tid & 31u;
-	for (uint32_t i = tid; i < SEED_BUCKETS; i += SEED_THREADS) s_bucket[i] = __ldg(ch.bucket + i);
-	for (uint32_t i = tid; i < ch.n_entries; i += SEED_THREADS) s_entries[i] = __ldg(ch.entries + i);
-	for (uint32_t i = tid; i < ch.n_pat; i += SEED_THREADS) s_mask[i] = __ldg(ch.mask + i);
+	{
+		uint32_t *s_bucket = smem;
+		uint32_t *s_entries = s_bucket + SEED_BUCKETS;
+		uint4 *s_mask = (uint4 *)(s_entries + ch.ecap);
+		for (uint32_t i = threadIdx.x; i < SEED_BUCKETS; i += SEED_THREADS) s_bucket[i] = __ldg(ch.bucket + i);
+		for (uint32_t i = threadIdx.x; i < ch.n_entries; i += SEED_THREADS) s_entries[i] = __ldg(ch.entries + i);
+		for (uint32_t i = threadIdx.x; i < ch.n_pat; i += SEED_THREADS) s_mask[i] = __ldg(ch.mask + i);
+	}
+	__syncthreads();
+	const uint32_t a_bucket = (uint32_t)__cvta_generic_to_shared(smem);
+	const uint32_t a_entries = a_bucket + SEED_BUCKETS * 4u;
+	const uint32_t a_mask = a_entries + ch.ecap * 4u;
+	const uint32_t lane = threadIdx.x & 31u;
 
 	for (;;) {
-		__syncthreads(); // tables loaded / previous tile consumed
-		if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-		__syncthreads();
-		const uint32_t tile = s_tile;
+		uint32_t tile = 0;
+		if (lane == 0u) tile = atomicAdd(tile_counter, 1u);
+		tile = __shfl_sync(0xffffffffu, tile, 0);
 		if (tile >= n_tiles) break;
-		const uint32_t seq = tile_seq[tile];
+		const uint32_t seq = __ldg(tile_seq + tile);
 		if (!sd.active[seq]) continue;
-		const uint32_t x0 = tile_x0[tile];
+		const uint32_t x0 = __ldg(tile_x0 + tile);
 		const uint64_t gbase = sd.grp_off[seq];
-		const uint32_t ngrp = (uint32_t)(sd.grp_off[seq + 1] - gbase);
+		const uint32_t ngrp = (uint32_t)(sd.grp_off[seq + 1] - gbase); // includes the zero halo group
 		const uint32_t clen = sd.clen[seq];
-		if (tid < SEED_GROUPS) {
-			const int64_t g = (int64_t)(x0 >> 5) - 1 + tid;
-			s_grp[tid] = (g >= 0 && g < (int64_t)ngrp) ? __ldg(sd.planes + gbase + g) : make_uint4(0, 0, 0, 0);
-		}
-		__syncthreads();
-
-		#pragma unroll 1
-		for (int r = 0; r < SEED_R; ++r) {
-			const uint32_t xl = r * SEED_THREADS + tid; // lane-consecutive, warp-aligned to a group
-			const uint32_t gi = 1u + (xl >> 5);          // the warp's own group inside the haloed tile
-			const uint4 gm = s_grp[gi - 1], gc = s_grp[gi], gp = s_grp[gi + 1]; // warp-uniform: broadcast loads
-			if (x0 + xl >= clen) continue;
-			// seed codes at x: low q bits of the code planes b0 = C|T, b1 = G|T (A=00 C=01 G=10 T=11)
-			const uint32_t w0 = __funnelshift_r(gc.y | gc.w, gp.y | gp.w, lane);
-			const uint32_t w1 = __funnelshift_r(gc.z | gc.w, gp.z | gp.w, lane);
-			#pragma unroll
-			for (int t = 0; t < 2; ++t) {
-				const uint32_t code = t == 0 ? ((w0 & 31u) | ((w1 & 31u) << 5)) : (1024u + ((w0 & 63u) | ((w1 & 63u) << 6)));
-				const uint32_t bk = s_bucket[code];
-				const uint32_t first = bk & 0xFFFFFu, count = bk >> 20;
-				for (uint32_t j = 0; j < count; ++j) {
-					const uint32_t en = s_entries[first + j];
-					const uint32_t pid = en >> 11, off = en & 31u;
-					const int d = (int)lane - (int)off; // alignment start relative to the warp's group, in [-27, 31]
-					const bool left = d < 0;
-					const uint32_t sh = (uint32_t)d & 31u;
-					const uint4 b = s_mask[pid];
-					const uint32_t m = (b.x & __funnelshift_r(left ? gm.x : gc.x, left ? gc.x : gp.x, sh)) |
-					                   (b.y & __funnelshift_r(left ? gm.y : gc.y, left ? gc.y : gp.y, sh)) |
-					                   (b.z & __funnelshift_r(left ? gm.z : gc.z, left ? gc.z : gp.z, sh)) |
-					                   (b.w & __funnelshift_r(left ? gm.w : gc.w, left ? gc.w : gp.w, sh));
-					const int cnt = __popc(m);
-					if (cnt >= (int)((en >> 5) & 63u)) { // a binding site
-						const int64_t x = (int64_t)x0 + xl - off;
-						if (x < 0) continue;
-						if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
-							const uint64_t G = gbase + (uint64_t)(x >> 5);
-							if (((dirty_bits[G >> 5] >> (G & 31u)) & 1u)) continue;
-						}
-						const uint32_t meta = __ldg(ch.meta + pid), meta2 = __ldg(ch.meta2 + pid);
-						const uint32_t n = (meta2 >> 10) & 63u, pieces = ((meta2 >> 16) & 63u) + 1u, q = (meta2 >> 22) & 7u;
-						const uint32_t qmask = (1u << q) - 1u;
-						bool first_piece = true; // report through the leftmost exactly-matching piece only
-						for (uint32_t i = 0; i < pieces; ++i) {
-							const uint32_t o = (i * n) / pieces;
-							if (o >= off) break;
-							if (((m >> o) & qmask) == qmask) { first_piece = false; break; }
-						}
-						if (first_piece) emit_family(hs, seq, clen, cand_bits, meta, meta2, x, (uint32_t)cnt);
-					}
-				}
+		const uint32_t g0 = x0 >> 5;
+		const uint32_t g_end = min(g0 + (uint32_t)SCAN_TILE_GROUPS, (clen + 31u) >> 5);
+		const uint4 zero4 = make_uint4(0, 0, 0, 0);
+		uint4 gm = g0 > 0u ? __ldg(sd.planes + gbase + g0 - 1u) : zero4;
+		uint4 gc = __ldg(sd.planes + gbase + g0);
+		uint4 gp = (g0 + 1u < ngrp) ? __ldg(sd.planes + gbase + g0 + 1u) : zero4;
+		for (uint32_t g = g0; g < g_end; ++g) {
+			__syncwarp(); // lanes leave the entry loops at different times: re-form the warp for the uniform part
+			const uint4 gn = (g + 2u < ngrp) ? __ldg(sd.planes + gbase + g + 2u) : zero4; // prefetch for the next step
+			const uint32_t xpos = (g << 5) + lane;
+			if (xpos < clen) {
+				// 64-bit cuts of the four letter planes starting 27 bases left of this lane's position
+				uint32_t ca0, ca1, cc0, cc1, cg0, cg1, ct0, ct1;
+				take64(gm.x, gc.x, gp.x, lane + 5u, ca0, ca1);
+				take64(gm.y, gc.y, gp.y, lane + 5u, cc0, cc1);
+				take64(gm.z, gc.z, gp.z, lane + 5u, cg0, cg1);
+				take64(gm.w, gc.w, gp.w, lane + 5u, ct0, ct1);
+				// seed codes at x: low q bits of the code planes b0 = C|T, b1 = G|T (A=00 C=01 G=10 T=11)
+				const uint32_t w0 = __funnelshift_r(gc.y | gc.w, gp.y | gp.w, lane);
+				const uint32_t w1 = __funnelshift_r(gc.z | gc.w, gp.z | gp.w, lane);
+				// one loop over the position's three buckets: a lane's trip count is the SUM of its three bucket
+				// sizes, whose spread across the warp is smaller than the three spreads added up
+				const uint32_t b5 = lds32(a_bucket + 4u * seed_bucket_index(5u, w0 & 31u, w1 & 31u));
+				const uint32_t b6 = lds32(a_bucket + 4u * seed_bucket_index(6u, w0 & 63u, w1 & 63u));
+				const uint32_t b7 = lds32(a_bucket + 4u * seed_bucket_index(7u, w0 & 127u, w1 & 127u));
+				const uint32_t n5 = b5 >> 20, n56 = n5 + (b6 >> 20), n567 = n56 + (b7 >> 20);
+				const uint32_t e5 = a_entries + 4u * (b5 & 0xFFFFFu), e6 = a_entries + 4u * ((b6 & 0xFFFFFu) - n5),
+				               e7 = a_entries + 4u * ((b7 & 0xFFFFFu) - n56);
+				for (uint32_t j = 0; j < n567; ++j)
+					seed_verify(lds32((j < n5 ? e5 : (j < n56 ? e6 : e7)) + 4u * j), a_mask, ca0, ca1, cc0, cc1, cg0, cg1, ct0, ct1, xpos, gbase,
+						dirty_bits, ch, seq, clen, cand_bits, hs);
 			}
+			gm = gc;
+			gc = gp;
+			gp = gn;
 		}
 	}
 }
@@ -454,13 +513,14 @@ __global__ void dirty_bits_kernel(SeqDev sd, uint64_t n_groups, uint32_t *dirty_
 // ---------------------------------------------------------------------------------------------
 // seed tables (per chunk of seeded patterns), built on the device
 // ---------------------------------------------------------------------------------------------
-// Enumerate the IUPAC expansions of the q-base seed of piece `i` of a pattern and call f(code).
+// Enumerate the IUPAC expansions of the seed of piece `i` of a pattern and call f(bucket, offset).
 template <class F>
-__device__ __forceinline__ void for_each_seed(const uint4 &mask, uint32_t n, uint32_t pieces, uint32_t q, uint32_t i, F f)
+__device__ __forceinline__ void for_each_seed(const uint4 &mask, uint32_t n, uint32_t pieces, uint32_t i, F f)
 {
-	const uint32_t o = (i * n) / pieces;
+	uint32_t o, q;
+	seed_piece(n, pieces, i, o, q);
 	// per-position letter sets as 4-bit {A,C,G,T}; letter codes A=0 C=1 G=2 T=3 -> b0 = code & 1, b1 = code >> 1
-	uint32_t sets[6];
+	uint32_t sets[SEED_QMAX];
 	uint32_t total = 1;
 	for (uint32_t k = 0; k < q; ++k) {
 		const uint32_t s = ((mask.x >> (o + k)) & 1u) | (((mask.y >> (o + k)) & 1u) << 1) | (((mask.z >> (o + k)) & 1u) << 2) |
@@ -484,16 +544,18 @@ __device__ __forceinline__ void for_each_seed(const uint4 &mask, uint32_t n, uin
 			b0 |= (letter & 1u) << k;
 			b1 |= (letter >> 1) << k;
 		}
-		f((q == 5u ? 0u : 1024u) + (b0 | (b1 << q)), o);
+		f(seed_bucket_index(q, b0, b1), o);
 	}
 }
 
 // number of seed-table entries a pattern needs, or 0 when it cannot be seeded
-__device__ __forceinline__ uint32_t seed_entries_needed(const uint4 &mask, uint32_t n, uint32_t pieces, uint32_t q)
+__device__ __forceinline__ uint32_t seed_entries_needed(const uint4 &mask, uint32_t n, uint32_t pieces)
 {
 	uint32_t sum = 0;
 	for (uint32_t i = 0; i < pieces; ++i) {
-		const uint32_t o = (i * n) / pieces;
+		uint32_t o, q;
+		seed_piece(n, pieces, i, o, q);
+		if (q < SEED_QMIN) return 0u;
 		uint32_t total = 1;
 		for (uint32_t k = 0; k < q; ++k) {
 			const uint32_t c = ((mask.x >> (o + k)) & 1u) + ((mask.y >> (o + k)) & 1u) + ((mask.z >> (o + k)) & 1u) + ((mask.w >> (o + k)) & 1u);
@@ -512,8 +574,8 @@ __global__ void seed_count_kernel(const uint4 *__restrict__ mask, const uint32_t
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n_pat) return;
 	const uint4 m = mask[p];
-	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u, q = (m2 >> 22) & 7u;
-	for (uint32_t i = 0; i < pieces; ++i) for_each_seed(m, n, pieces, q, i, [&](uint32_t code, uint32_t) { atomicAdd(bucket_cnt + code, 1u); });
+	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u;
+	for (uint32_t i = 0; i < pieces; ++i) for_each_seed(m, n, pieces, i, [&](uint32_t code, uint32_t) { atomicAdd(bucket_cnt + code, 1u); });
 }
 
 // bucket_cnt holds the exclusive start of every bucket on entry and is advanced as a cursor
@@ -524,11 +586,11 @@ __global__ void seed_fill_kernel(const uint4 *__restrict__ mask, const uint32_t 
 	if (p >= n_pat) return;
 	const uint4 m = mask[p];
 	const uint32_t thr = meta[p] & 63u;
-	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u, q = (m2 >> 22) & 7u;
+	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u;
 	for (uint32_t i = 0; i < pieces; ++i)
-		for_each_seed(m, n, pieces, q, i, [&](uint32_t code, uint32_t o) {
+		for_each_seed(m, n, pieces, i, [&](uint32_t code, uint32_t o) {
 			const uint32_t slot = atomicAdd(cursor + code, 1u);
-			if (slot < ecap) entries[slot] = (p << 11) | (thr << 5) | o;
+			if (slot < ecap) entries[slot] = (p << 11) | (thr << 5) | (27u - o);
 		});
 }
 
