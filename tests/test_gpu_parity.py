@@ -245,3 +245,43 @@ def test_exact_threshold_and_mixed_classes(gpu, oracle):
         assert (ne, nk) == oracle.select_words(f, r, thr)
         for a, c in zip(g.db(), oracle.db()):
             assert np.array_equal(a, c)
+
+
+def test_merge_shards_equals_unsharded(gpu):
+    """the N>1 exchange on one GPU: score three shards one after the other, concatenate their (any, pass-1) bitsets as an
+    all-gather would, splice with pcramp_gpu_merge_shards -> identical bitsets and (weighted) coverage as the unsharded call"""
+    import torch
+    from pcramp_b200.sharding import shard_bounds, shard_sizes, shard_words
+    coll = synth.make_targets(951, 70, 3000, n_clades=3, between=0.12, within=0.05)
+    coll.weight = np.random.default_rng(5).uniform(0.1, 3.0, size=coll.n).astype(np.float32)
+    f, r = synth.make_pairs(952, coll, 50)
+    thr = float(np.float32(1.0) * np.float32(0.9))
+    gpu.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length, coll.weight)
+    gpu.select_words(TARGET, f, r, thr)
+    cov_all, bits_all = gpu.score_pairs(TARGET, f, r, thr, 0.9)
+    world = 3
+    b = shard_bounds(coll.n, world)
+    words = shard_words(coll.n, world)
+    any_parts, p1_parts = [], []
+    for k in range(world):
+        sh = coll.subset(range(b[k], b[k + 1]))
+        gpu.upload_sequences(TARGET, sh.nibbles, sh.byte_off, sh.length, sh.weight)
+        gpu.stage_pairs(f, r)
+        gpu.select_words_staged(TARGET, thr)
+        gpu.score_pairs_staged(TARGET, thr, 0.9)
+        d_cov, d_any, d_p1 = gpu.device_pointers()
+        n = len(f) * words[k]
+
+        class Dev:
+            def __init__(self, ptr):
+                self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": (n,), "typestr": "<i4", "version": 2}
+        any_parts.append(torch.as_tensor(Dev(d_any), device="cuda").clone())
+        p1_parts.append(torch.as_tensor(Dev(d_p1), device="cuda").clone())
+    g_any, g_p1 = torch.cat(any_parts), torch.cat(p1_parts)
+    out_bits = torch.zeros((len(f), (coll.n + 31) // 32), dtype=torch.int32, device="cuda")
+    out_cov = torch.zeros(len(f), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    gpu.merge_shards(g_any.data_ptr(), g_p1.data_ptr(), shard_sizes(coll.n, world), len(f), out_bits.data_ptr(), out_cov.data_ptr(), coll.weight)
+    assert np.array_equal(out_bits.cpu().numpy().view(np.uint32), bits_all)
+    assert np.array_equal(out_cov.cpu().numpy(), cov_all)
+    assert bits_all.any()
