@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=1000)
     ap.add_argument("--cpu-targets", type=int, default=96, help="targets in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp-problems", type=int, default=262144, help="NucCruc problems per step of the DP GCUPS leg (0 = skip the leg)")
+    ap.add_argument("--dp-cpu-problems", type=int, default=60000, help="problems in the bounded CPU sample of the DP leg")
     return ap.parse_args()
 
 
@@ -164,6 +166,109 @@ def run_reference(a):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+# --------------------------------------------------------------------------------------------------
+# DP GCUPS leg (the second half of BASELINE.json's metric): batches of gapped heterodimer problems
+# (NucCruc::approximate_tm_heterodimer on primer pairs, what PCR::max_dimer_tm / multiplex_compatible run)
+# --------------------------------------------------------------------------------------------------
+DP_INT_OPS_PER_CELL = 45.0   # 3 states, 7 delta_g look-ups per gapped nearest-neighbour cell
+
+
+def dp_problems(seed, n):
+    """primer-like oligo pairs: 18-25-mers, uniform ACGT (random_assay geometry, pcr_assay.cpp:636-688)"""
+    rng = np.random.default_rng(seed)
+    la = rng.integers(18, 26, size=n)
+    lb = rng.integers(18, 26, size=n)
+    sym = np.frombuffer(b"ACGT", dtype=np.uint8)
+    a = np.zeros((n, 33), np.uint8)
+    b = np.zeros((n, 33), np.uint8)
+    ra = sym[rng.integers(0, 4, size=(n, 32))]
+    rb = sym[rng.integers(0, 4, size=(n, 32))]
+    col = np.arange(32)[None, :]
+    a[:, :32] = np.where(col < la[:, None], ra, 0)
+    b[:, :32] = np.where(col < lb[:, None], rb, 0)
+    return a, b, int((la * lb).sum())
+
+
+def dp_leg(a, g, torch, ext, rank, world, dist):
+    """-> dict for the JSON line (rank 0) or None"""
+    import ctypes
+    n = a.dp_problems
+    sa, sb, cells = dp_problems(1000 + rank, n)
+    strand = np.float32(9e-7)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(k):
+            fn()
+        e1.record(ext)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    g.thermo_stage(3, sa, sb, 0.05, strand, strand)
+    for _ in range(max(3, a.warmup)):
+        g.thermo_run_staged()
+    kernel_ms = []
+
+    def resident():
+        g.thermo_run_staged()
+
+    ms_res = timed(resident, a.steps)
+    g.synchronize()
+    st = g.thermo_stats()
+    assert st["dp_cells"] == cells and st["n_problems"] == n
+    g.thermo_batch(3, sa, sb, 0.05, strand, strand)
+    ms_e2e = timed(lambda: g.thermo_batch(3, sa, sb, 0.05, strand, strand), a.steps)
+    kernel_ms = g.thermo_stats()["ms_kernel"]
+    if rank != 0:
+        return None
+    total_cells = float(cells) * world   # every rank runs its own batch of the same shape (replicas)
+    gcups = total_cells * a.steps / (ms_res * 1e-3) / 1e9
+    gcups_e2e = total_cells * a.steps / (ms_e2e * 1e-3) / 1e9
+    sm_clock = 1.965e9
+    int_peak = 148 * 128 * sm_clock   # one INT32 op per lane per clock on the unified FP32/INT32 pipe
+    out = {
+        "metric": "dp_gcups", "value": gcups, "unit": "GCUPS (1e9 DP cells/s, cells = q x t)", "ms_per_step": ms_res / a.steps,
+        "problems_per_step_per_gpu": n, "cells_per_step_per_gpu": cells, "scaling": "weak (replicas: every rank runs its own batch)",
+        "op": "approximate_tm_heterodimer, gapped (align_dimer + enumeration + evaluation), 18-25-mer pairs",
+        "e2e": {"value": gcups_e2e, "unit": "GCUPS", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": n * (32 + 32 + 1 + 1 + 4),
+                "d2h_bytes_per_step": n * 16},
+        "gpu_launches": a.steps,
+        "roofline": {"kernel": "thermo_kernel", "bound": "int32 issue", "achieved": total_cells / world * DP_INT_OPS_PER_CELL / (kernel_ms * 1e-3) / 1e12,
+                     "peak": int_peak / 1e12, "unit": "Tops/s (INT32)", "frac": (total_cells / world * DP_INT_OPS_PER_CELL / (kernel_ms * 1e-3)) / int_peak,
+                     "avg_launch_ms": kernel_ms,
+                     "note": "algorithmic cost 45 INT32 ops per gapped cell (SURVEY.md 8d) against 148 SM x 128 lanes x 1.965 GHz; the "
+                             "kernel also runs the traceback / enumeration / float evaluation epilogue, which this model does not credit"},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        from tests.harness import RefLib, REF_PATH
+        if os.path.exists(REF_PATH):
+            ref = RefLib()
+            ref.set_threads(0)
+            m = min(n, a.dp_cpu_problems)
+            A = [bytes(r[:int(np.argmax(r == 0))]).decode() for r in sa[:m]]
+            B = [bytes(r[:int(np.argmax(r == 0))]).decode() for r in sb[:m]]
+            ref.thermo_batch(3, A[:2000], B[:2000], 0.05, strand, strand)
+            t0 = time.perf_counter()
+            ref.thermo_batch(3, A, B, 0.05, strand, strand)
+            dt = time.perf_counter() - t0
+            c = float(sum(len(x) * len(y) for x, y in zip(A, B)))
+            out["cpu_baseline"] = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": ref.max_threads(), "kind": "reference", "seconds": dt,
+                                   "sample": "the first %d problems of the step, one NucCruc per OpenMP thread" % m}
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -314,6 +419,7 @@ def run_b200(a):
         ms_e2e = timed_region(step_e2e, total + 1, a.steps)
         clocks = sampler.stop() if rank == 0 else None
         int_peak = g.measure_int_peak() if rank == 0 else 0.0
+        dp = dp_leg(a, g, torch, ext, rank, world, dist if world > 1 else None) if a.dp_problems > 0 else None
 
     evals_per_step = float(P) * a.targets
     value = evals_per_step * a.steps / (ms_resident * 1e-3)
@@ -378,7 +484,7 @@ def run_b200(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_resident,
             "breakdown_ms_per_step": {k: stats_acc[k] / n_scan for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score")},
-            "roofline": roofline, "cpu_baseline": cpu_baseline}))
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp}))
     # teardown order matters: torch tensors that were used on the library's stream must die before the stream does
     sys.stdout.flush()
     torch.cuda.synchronize()

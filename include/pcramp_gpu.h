@@ -115,6 +115,63 @@ int pcramp_gpu_merge_shards(pcramp_gpu_ctx *ctx, const void *d_any_gathered, con
 	uint32_t n_shards, const uint32_t *shard_nseq, const float *weight_all, uint32_t n_pairs, void *d_out_bits,
 	void *d_out_cov);
 
+/* ---- K3: SantaLucia nearest-neighbour thermodynamics: replaces the NucCruc call surface pcramp uses
+ *      (nuc_cruc.h:696-763 tm_pm_duplex / approximate_tm_hairpin, :775-838 salt / strand, :875-994 set_query /
+ *      set_target; nuc_cruc.cpp:2236-2455 approximate_tm_{heterodimer,homodimer,hairpin}) for a BATCH of
+ *      oligos / oligo pairs.  One NucCruc object per OpenMP thread (main.cpp:528-535, optimize.cpp:49-52)
+ *      becomes one call per batch.
+ *        seq_a / seq_b : n strings of bases (ACGT, and I except for PM_DUPLEX), NUL terminated, at a fixed
+ *                        stride (bytes); at most 32 bases (Word length, options.cpp:854-860).  seq_b is read by
+ *                        the heterodimer ops only (query = a, target = b).
+ *        salt          : NucCruc::salt(), [Na+] in mol/l, 1e-6 .. 1
+ *        strand_a      : n total strand concentrations as NucCruc::strand(c) takes them; for the heterodimer
+ *                        ops strand_b (n) is required and the pair goes through NucCruc::strand(c_a, c_b)
+ *        tm, dH, dS, dG_dp : n floats each, any may be NULL: the return value of the Tm call, delta_H(),
+ *                        delta_S(), delta_G_dp() (nuc_cruc.h:1361-1383).
+ *      Errors mirror the reference's throws (illegal base, empty hairpin query, sequence too long). ------- */
+enum {
+	PCRAMP_TM_PM_DUPLEX = 0,        /* tm_pm_duplex(a)                                   nuc_cruc.h:723-759 */
+	PCRAMP_TM_HAIRPIN = 1,          /* set_query(a); approximate_tm_hairpin()            nuc_cruc.cpp:2381-2455 */
+	PCRAMP_TM_HOMODIMER = 2,        /* set_query(a); approximate_tm_homodimer()          nuc_cruc.cpp:2296-2354 */
+	PCRAMP_TM_HETERODIMER = 3,      /* set_query(a); set_target(b); approximate_tm_heterodimer()  :2236-2294 */
+	PCRAMP_TM_HETERODIMER_DIAG = 4, /* the same with fast_alignment(true) (optimize.cpp:51)         :546-612 */
+	PCRAMP_TM_HOMODIMER_DIAG = 5,   /* approximate_tm_homodimer() with fast_alignment(true) */
+	PCRAMP_TM_NUM_OPS = 6
+};
+int pcramp_gpu_thermo_batch(pcramp_gpu_ctx *ctx, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
+	float salt, const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp);
+/* Resident variant: stage a batch in HBM once, run the kernel on it any number of times, fetch when wanted. */
+int pcramp_gpu_thermo_stage(pcramp_gpu_ctx *ctx, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
+	float salt, const float *strand_a, const float *strand_b);
+int pcramp_gpu_thermo_run_staged(pcramp_gpu_ctx *ctx);
+int pcramp_gpu_thermo_fetch(pcramp_gpu_ctx *ctx, float *tm, float *dH, float *dS, float *dG_dp);
+
+/* PCR::is_valid (valid_pcr.cpp:5-45) for n trial oligos (words, n x 2 uint64): every concrete expansion of a
+ * degenerate oligo (Word::begin/next, word.h:525-647) must have tm_pm_duplex in [tm_min, tm_max],
+ * approximate_tm_hairpin <= max_hairpin and, if check_homo_dimer, approximate_tm_homodimer <= max_dimer, at strand
+ * concentration primer_strand / degeneracy.  fast_alignment = the NucCruc::fast_alignment() flag of the caller's
+ * object (true inside optimize(), optimize.cpp:51).  valid[i] = 1 / 0. */
+int pcramp_gpu_is_valid(pcramp_gpu_ctx *ctx, const uint64_t *words, uint32_t n, float salt, float primer_strand, float tm_min,
+	float tm_max, float max_hairpin, float max_dimer, int check_homo_dimer, int fast_alignment, uint8_t *valid);
+/* PCR::max_dimer_tm (pcr_assay.cpp:232-269): the highest heterodimer Tm over all expansions of F x R. */
+int pcramp_gpu_max_dimer_tm(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, float salt,
+	float primer_strand, int fast_alignment, float *tm);
+/* PCR::multiplex_compatible (pcr_assay.cpp:815-852) as main.cpp:748-752 calls it: for trial assay i (f[i], r[i]),
+ * ok[i] = AND over the pool of pool_assay.multiplex_compatible(melt, opt, trial_i), i.e. no heterodimer
+ * (query = an expansion of a pool oligo, target = an expansion of a trial oligo) reaches max_dimer. */
+int pcramp_gpu_multiplex_compatible(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs,
+	const uint64_t *pool_f, const uint64_t *pool_r, uint32_t n_pool, float salt, float primer_strand, float max_dimer,
+	int fast_alignment, uint8_t *ok);
+/* Counters of the last K3 call: problems, DP cells (q*t gapped dimer, (n-4)(n-3)/2 hairpin, min(q,t) diagonal;
+ * SURVEY.md section 8d), kernel launches, CUDA-event time of the kernels. */
+typedef struct pcramp_gpu_thermo_stats {
+	uint64_t n_problems;
+	uint64_t dp_cells;
+	uint64_t kernel_launches;
+	float ms_kernel;
+} pcramp_gpu_thermo_stats;
+int pcramp_gpu_get_thermo_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_thermo_stats *out);
+
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* Counters of the last select_words / score_pairs call on this ctx. */
 typedef struct pcramp_gpu_stats {

@@ -15,16 +15,26 @@
 //   PCR::find_target_match       pcr_assay.cpp:544-578
 //   PCR::random_assay            pcr_assay.cpp:580-734
 //   NucCruc front-ends           nuc_cruc.h:696-763, nuc_cruc.cpp:2236-2455
+//   PCR::is_valid / max_dimer_tm / multiplex_compatible    valid_pcr.cpp:5-45, pcr_assay.cpp:232-269,815-852
 //   Word helpers                 word.h / word.cpp
-#include "assay.h"
-#include "seq_overlap.h"
-
 #include <omp.h>
 #include <stdint.h>
+#include <algorithm>
+#include <deque>
+#include <iostream>
+#include <map>
+#include <set>
 #include <sstream>
 #include <string>
+#include <unordered_map>
 #include <vector>
-#include <deque>
+
+// PCR::is_valid is a private member (assay.h:237); the driver needs to call it as optimize_pcr.cpp does.  Access
+// specifiers do not change the class layout, so the objects compiled from the unmodified sources stay compatible.
+#define private public
+#include "assay.h"
+#undef private
+#include "seq_overlap.h"
 
 // Globals the reference expects main.cpp to define (main.cpp:33-34).
 int mpi_numtasks = 1;
@@ -312,45 +322,161 @@ int ref_has_split(void *h, uint32_t seq, int loc, int len)
 
 // ---- NucCruc front-ends (nuc_cruc.h:696-763) ------------------------------------------------
 // op: 0 tm_pm_duplex(a), 1 approximate_tm_hairpin(a), 2 approximate_tm_homodimer(a),
-//     3 approximate_tm_heterodimer(query=a, target=b) gapped, 4 same with fast_alignment(true).
+//     3 approximate_tm_heterodimer(query=a, target=b) gapped, 4 same with fast_alignment(true),
+//     5 approximate_tm_homodimer(a) with fast_alignment(true).
 // out = {tm, dH, dS, dG, dG_dp}
+// The reference reads one or two slots past the end of its query ring buffer when a trace reaches row 0
+// (nuc_cruc.cpp:1375 with last_i == 0; circle_buffer.h:136-139 has no bounds check), i.e. whatever an earlier,
+// longer query left there (or uninitialised memory).  To make its answers reproducible the driver first loads
+// 256 x 'A' through the public set_query / set_target, so those slots hold base A.
+static void thermo_one(NucCruc &melt, int op, const char *a, const char *b, float strand_a, float strand_b, float *out)
+{
+	static const std::string fill(MAX_SEQUENCE_LENGTH, 'A');
+	melt.set_query(fill);
+	melt.set_target(fill);
+	float tm = 0.0f;
+	switch (op) {
+	case 0:
+		melt.strand(strand_a);
+		tm = melt.tm_pm_duplex(a);
+		break;
+	case 1:
+		melt.strand(strand_a);
+		melt.set_query(a);
+		tm = melt.approximate_tm_hairpin();
+		break;
+	case 2:
+	case 5:
+		melt.fast_alignment(op == 5);
+		melt.strand(strand_a);
+		melt.set_query(a);
+		tm = melt.approximate_tm_homodimer();
+		break;
+	case 3:
+	case 4:
+		melt.fast_alignment(op == 4);
+		melt.strand(strand_a, strand_b);
+		melt.set_query(a);
+		melt.set_target(b);
+		tm = melt.approximate_tm_heterodimer();
+		break;
+	default:
+		throw "bad op";
+	}
+	out[0] = tm;
+	out[1] = melt.delta_H();
+	out[2] = melt.delta_S();
+	out[3] = melt.delta_G();
+	out[4] = melt.delta_G_dp();
+}
+
 int ref_thermo(int op, const char *a, const char *b, float salt, float strand_a, float strand_b, float *out)
 {
 	return guarded(NULL, [&]() {
 		NucCruc melt;
 		melt.salt(salt);
-		float tm = 0.0f;
-		switch (op) {
-		case 0:
-			melt.strand(strand_a);
-			tm = melt.tm_pm_duplex(a);
-			break;
-		case 1:
-			melt.strand(strand_a);
-			melt.set_query(a);
-			tm = melt.approximate_tm_hairpin();
-			break;
-		case 2:
-			melt.strand(strand_a);
-			melt.set_query(a);
-			tm = melt.approximate_tm_homodimer();
-			break;
-		case 3:
-		case 4:
-			melt.fast_alignment(op == 4);
-			melt.strand(strand_a, strand_b);
-			melt.set_query(a);
-			melt.set_target(b);
-			tm = melt.approximate_tm_heterodimer();
-			break;
-		default:
-			throw "bad op";
+		thermo_one(melt, op, a, b, strand_a, strand_b, out);
+	});
+}
+
+// n problems; a / b: strings of stride 33 bytes (NUL padded); strand: n x 2 floats; out: n x 5 floats.
+// One NucCruc per OpenMP thread, as main.cpp:528-535 does.
+int ref_thermo_batch(int op, int n, const char *a, const char *b, float salt, const float *strand, float *out)
+{
+	int bad = 0;
+#pragma omp parallel
+	{
+		try {
+			NucCruc melt;
+			melt.salt(salt);
+#pragma omp for schedule(dynamic, 64)
+			for (int p = 0; p < n; ++p)
+				thermo_one(melt, op, a + (size_t)p * 33, b ? b + (size_t)p * 33 : a + (size_t)p * 33, strand[2 * p], strand[2 * p + 1],
+					out + 5 * (size_t)p);
+		} catch (...) {
+#pragma omp atomic write
+			bad = 1;
 		}
-		out[0] = tm;
-		out[1] = melt.delta_H();
-		out[2] = melt.delta_S();
-		out[3] = melt.delta_G();
-		out[4] = melt.delta_G_dp();
+	}
+	return bad ? -1 : 0;
+}
+
+// ---- the thermodynamic filters of PCR (valid_pcr.cpp:5-45, pcr_assay.cpp:232-269,815-852) ---------------
+static void fill_melt(NucCruc &melt)
+{
+	static const std::string fill(MAX_SEQUENCE_LENGTH, 'A');
+	melt.set_query(fill);
+	melt.set_target(fill);
+}
+
+static Options thermo_options(float salt, float primer_strand, float tm_min, float tm_max, float max_hairpin, float max_dimer)
+{
+	Options opt;
+	opt.salt = salt;
+	opt.primer_strand = primer_strand;
+	opt.primer_tm_range = make_pair(tm_min, tm_max);
+	opt.max_hairpin = max_hairpin;
+	opt.max_dimer = max_dimer;
+	return opt;
+}
+
+int ref_is_valid(uint32_t n, const uint64_t *words, float salt, float primer_strand, float tm_min, float tm_max, float max_hairpin,
+	float max_dimer, int check_homo_dimer, int fast_alignment, uint8_t *valid)
+{
+	return guarded(NULL, [&]() {
+		const Options opt = thermo_options(salt, primer_strand, tm_min, tm_max, max_hairpin, max_dimer);
+		NucCruc melt;
+		melt.fast_alignment(fast_alignment != 0);
+		melt.salt(salt);
+		PCR p;
+		for (uint32_t i = 0; i < n; ++i) {
+			fill_melt(melt);
+			valid[i] = p.is_valid(FORWARD, make_word(words + 2 * i), melt, opt, check_homo_dimer != 0) ? 1 : 0;
+		}
+	});
+}
+
+int ref_max_dimer_tm(uint32_t n, const uint64_t *f, const uint64_t *r, float salt, float primer_strand, int fast_alignment, float *tm)
+{
+	return guarded(NULL, [&]() {
+		const Options opt = thermo_options(salt, primer_strand, 0.0f, 0.0f, 0.0f, 0.0f);
+		NucCruc melt;
+		melt.fast_alignment(fast_alignment != 0);
+		melt.salt(salt);
+		for (uint32_t i = 0; i < n; ++i) {
+			PCR p;
+			p.oligo(FORWARD, make_word(f + 2 * i));
+			p.oligo(REVERSE, make_word(r + 2 * i));
+			fill_melt(melt);
+			tm[i] = p.max_dimer_tm(melt, opt);
+		}
+	});
+}
+
+// NOTE: multiplex_compatible loads FORWARD then REVERSE of the POOL assay as the query; when FORWARD is the longer
+// one the reference's off-the-end read sees FORWARD's bases, not the 'A' fill -- callers keep len(F) <= len(R) in the pool.
+int ref_multiplex_compatible(uint32_t n, const uint64_t *f, const uint64_t *r, uint32_t n_pool, const uint64_t *pf, const uint64_t *pr,
+	float salt, float primer_strand, float max_dimer, int fast_alignment, uint8_t *ok)
+{
+	return guarded(NULL, [&]() {
+		const Options opt = thermo_options(salt, primer_strand, 0.0f, 0.0f, 0.0f, max_dimer);
+		NucCruc melt;
+		melt.fast_alignment(fast_alignment != 0);
+		melt.salt(salt);
+		for (uint32_t i = 0; i < n; ++i) {
+			PCR p;
+			p.oligo(FORWARD, make_word(f + 2 * i));
+			p.oligo(REVERSE, make_word(r + 2 * i));
+			bool all = true;
+			for (uint32_t j = 0; j < n_pool && all; ++j) {
+				PCR q;
+				q.oligo(FORWARD, make_word(pf + 2 * j));
+				q.oligo(REVERSE, make_word(pr + 2 * j));
+				fill_melt(melt);
+				all = q.multiplex_compatible(melt, opt, p); // main.cpp:748-752: the pool assay is `this`
+			}
+			ok[i] = all ? 1 : 0;
+		}
 	});
 }
 

@@ -46,6 +46,22 @@ class Stats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ThermoStats(ctypes.Structure):
+    _fields_ = [
+        ("n_problems", ctypes.c_uint64),
+        ("dp_cells", ctypes.c_uint64),
+        ("kernel_launches", ctypes.c_uint64),
+        ("ms_kernel", ctypes.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# op codes of pcramp_gpu_thermo_batch (include/pcramp_gpu.h)
+TM_PM_DUPLEX, TM_HAIRPIN, TM_HOMODIMER, TM_HETERODIMER, TM_HETERODIMER_DIAG, TM_HOMODIMER_DIAG = range(6)
+THERMO_STRIDE = 33  # bytes per string slot used by this wrapper (32 bases + NUL)
+
 _lib = None
 
 # name -> (restype, argtypes); also the list of symbols tests check against include/pcramp_gpu.h
@@ -82,6 +98,19 @@ SIGNATURES = {
     "pcramp_gpu_fetch_results": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
     "pcramp_gpu_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "pcramp_gpu_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
+    "pcramp_gpu_thermo_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32,
+                                               ctypes.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]),
+    "pcramp_gpu_thermo_stage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32,
+                                               ctypes.c_float, _f32p, _f32p]),
+    "pcramp_gpu_thermo_run_staged": (ctypes.c_int, [ctypes.c_void_p]),
+    "pcramp_gpu_thermo_fetch": (ctypes.c_int, [ctypes.c_void_p, _f32p, _f32p, _f32p, _f32p]),
+    "pcramp_gpu_is_valid": (ctypes.c_int, [ctypes.c_void_p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                           ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, _u8p]),
+    "pcramp_gpu_max_dimer_tm": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                               _f32p]),
+    "pcramp_gpu_multiplex_compatible": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32, _u64p, _u64p, ctypes.c_uint32,
+                                                       ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, _u8p]),
+    "pcramp_gpu_get_thermo_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ThermoStats)]),
     "pcramp_word_from_string": (None, [ctypes.c_char_p, ctypes.c_int, _u64p]),
     "pcramp_word_to_string": (ctypes.c_int, [_u64p, ctypes.c_char_p]),
     "pcramp_word_and": (ctypes.c_uint32, [_u64p, _u64p]),
@@ -270,6 +299,70 @@ class PcrampGpu:
         self._ck(self.lib.pcramp_gpu_merge_shards(self.h, d_any, d_pass1, len(shard_nseq), _ptr(shard_nseq, _u32p), _ptr(weight_all, _f32p),
                                                   int(n_pairs), d_out_bits, d_out_cov))
 
+    # ---- K3: nearest-neighbour thermodynamics -------------------------------------------------------
+    def _thermo_args(self, op, seq_a, seq_b, strand_a, strand_b):
+        a = seq_a if isinstance(seq_a, np.ndarray) else pack_strings(seq_a)
+        n = len(a)
+        b = None
+        if seq_b is not None:
+            b = seq_b if isinstance(seq_b, np.ndarray) else pack_strings(seq_b, a.shape[1])
+        sa = None if strand_a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(strand_a, dtype=np.float32), (n,)))
+        sb = None if strand_b is None else np.ascontiguousarray(np.broadcast_to(np.asarray(strand_b, dtype=np.float32), (n,)))
+        return n, a, b, sa, sb
+
+    def thermo_batch(self, op, seq_a, seq_b=None, salt=0.05, strand_a=9e-7, strand_b=None):
+        """-> (tm, dH, dS, dG_dp) float32 arrays; seq_* are lists of str or (n, stride) uint8 arrays"""
+        n, a, b, sa, sb = self._thermo_args(op, seq_a, seq_b, strand_a, strand_b)
+        out = [np.zeros(n, np.float32) for _ in range(4)]
+        self._ck(self.lib.pcramp_gpu_thermo_batch(self.h, int(op), n, a.ctypes.data_as(ctypes.c_char_p),
+                                                  None if b is None else b.ctypes.data_as(ctypes.c_char_p), a.shape[1], float(salt),
+                                                  _ptr(sa, _f32p), _ptr(sb, _f32p), *[_ptr(o, _f32p) for o in out]))
+        return tuple(out)
+
+    def thermo_stage(self, op, seq_a, seq_b=None, salt=0.05, strand_a=9e-7, strand_b=None):
+        n, a, b, sa, sb = self._thermo_args(op, seq_a, seq_b, strand_a, strand_b)
+        self._ck(self.lib.pcramp_gpu_thermo_stage(self.h, int(op), n, a.ctypes.data_as(ctypes.c_char_p),
+                                                  None if b is None else b.ctypes.data_as(ctypes.c_char_p), a.shape[1], float(salt),
+                                                  _ptr(sa, _f32p), _ptr(sb, _f32p)))
+        self._thermo_n = n
+
+    def thermo_run_staged(self):
+        self._ck(self.lib.pcramp_gpu_thermo_run_staged(self.h))
+
+    def thermo_fetch(self):
+        out = [np.zeros(self._thermo_n, np.float32) for _ in range(4)]
+        self._ck(self.lib.pcramp_gpu_thermo_fetch(self.h, *[_ptr(o, _f32p) for o in out]))
+        return tuple(out)
+
+    def is_valid(self, words, salt=0.05, primer_strand=9e-7, tm_range=(50.0, 75.0), max_hairpin=40.0, max_dimer=40.0,
+                 check_homo_dimer=True, fast_alignment=False):
+        words = _words(words)
+        valid = np.zeros(len(words), np.uint8)
+        self._ck(self.lib.pcramp_gpu_is_valid(self.h, _ptr(words, _u64p), len(words), float(salt), float(primer_strand), float(tm_range[0]),
+                                              float(tm_range[1]), float(max_hairpin), float(max_dimer), int(check_homo_dimer),
+                                              int(fast_alignment), _ptr(valid, _u8p)))
+        return valid
+
+    def max_dimer_tm(self, f, r, salt=0.05, primer_strand=9e-7, fast_alignment=False):
+        f, r = _words(f), _words(r)
+        tm = np.zeros(len(f), np.float32)
+        self._ck(self.lib.pcramp_gpu_max_dimer_tm(self.h, _ptr(f, _u64p), _ptr(r, _u64p), len(f), float(salt), float(primer_strand),
+                                                  int(fast_alignment), _ptr(tm, _f32p)))
+        return tm
+
+    def multiplex_compatible(self, f, r, pool_f, pool_r, salt=0.05, primer_strand=9e-7, max_dimer=40.0, fast_alignment=False):
+        f, r, pool_f, pool_r = _words(f), _words(r), _words(pool_f), _words(pool_r)
+        ok = np.zeros(len(f), np.uint8)
+        self._ck(self.lib.pcramp_gpu_multiplex_compatible(self.h, _ptr(f, _u64p), _ptr(r, _u64p), len(f), _ptr(pool_f, _u64p),
+                                                          _ptr(pool_r, _u64p), len(pool_f), float(salt), float(primer_strand),
+                                                          float(max_dimer), int(fast_alignment), _ptr(ok, _u8p)))
+        return ok
+
+    def thermo_stats(self):
+        s = ThermoStats()
+        self._ck(self.lib.pcramp_gpu_get_thermo_stats(self.h, ctypes.byref(s)))
+        return s.as_dict()
+
     def measure_int_peak(self):
         v = ctypes.c_double()
         self._ck(self.lib.pcramp_gpu_measure_int_peak(self.h, ctypes.byref(v)))
@@ -282,6 +375,17 @@ class PcrampGpu:
         s = Stats()
         self._ck(self.lib.pcramp_gpu_get_stats(self.h, ctypes.byref(s)))
         return s.as_dict()
+
+
+def pack_strings(strs, stride=THERMO_STRIDE):
+    """list of str -> (n, stride) uint8, NUL padded (the fixed-stride string layout of pcramp_gpu_thermo_batch)"""
+    buf = np.zeros((len(strs), stride), dtype=np.uint8)
+    for i, s in enumerate(strs):
+        b = s.encode() if isinstance(s, str) else bytes(s)
+        if len(b) >= stride:
+            raise ValueError("sequence longer than %d bases" % (stride - 1))
+        buf[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    return buf
 
 
 def unpack_bits(bits, n_seq):

@@ -41,7 +41,8 @@ def build_cuda(force=False, verbose=False):
     srcs.append(os.path.join(ROOT, "include", "pcramp_gpu.h"))
     if not force and not _stale(LIB, srcs):
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "pcramp_gpu.cu")]
+    units = [s for s in srcs if s.endswith(".cu")]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["--threads", str(len(units))] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + units
     env = dict(os.environ)
     env.pop("CXX", None)  # the image's CXX wrapper is not a usable host compiler for nvcc
     env.pop("CC", None)

@@ -5,6 +5,7 @@
 // x86 code (SURVEY.md section 7 "Float bit-exactness"); the hot scan kernel is integer-only.
 #include "../../include/pcramp_gpu.h"
 
+#include "ctx.cuh"
 #include "score.cuh"
 
 #include <cub/cub.cuh>
@@ -19,121 +20,6 @@
 using namespace pcr;
 
 namespace {
-
-struct DevBuf {
-	void *p = nullptr;
-	size_t cap = 0;
-	~DevBuf() { release(); }
-	void release()
-	{
-		if (p) cudaFree(p);
-		p = nullptr;
-		cap = 0;
-	}
-	cudaError_t ensure(size_t bytes)
-	{
-		if (bytes <= cap) return cudaSuccess;
-		release();
-		size_t want = bytes + bytes / 4 + 256;
-		cudaError_t e = cudaMalloc(&p, want);
-		if (e != cudaSuccess) { p = nullptr; return e; }
-		cap = want;
-		return cudaSuccess;
-	}
-	template <class T> T *as() const { return (T *)p; }
-};
-
-struct SeqSet {
-	uint32_t n = 0;
-	bool any_degenerate = false;
-	uint64_t total_positions = 0; // sum of clen over all sequences
-	std::vector<uint32_t> len, plen, clen;
-	std::vector<float> weight;
-	std::vector<uint8_t> active;
-	std::vector<uint64_t> raw_off, grp_off;
-	std::vector<std::vector<uint32_t>> eos; // per sequence, sorted raw positions
-	uint64_t raw_bytes = 0, n_groups = 0, n_tiles = 0;
-	DevBuf d_raw, d_raw_off, d_len, d_plen, d_clen, d_planes, d_grp_off, d_eos_pos, d_eos_off, d_weight, d_active, d_tile_seq, d_tile_x0;
-	DevBuf d_dirty_bits, d_dirty_seq, d_dirty_grp; // groups whose alignments read a degenerate base (scan.cuh)
-	uint32_t n_dirty = 0;
-	// database (seq-grouped order = entry-id order) + canonical permutation
-	uint64_t n_entries = 0, n_keys = 0;
-	bool db_valid = false;
-	DevBuf e_hi, e_lo, e_planes, e_seq, e_loc, e_strand, e_perm, e_keyrank, seq_ent_off;
-
-	SeqDev dev() const
-	{
-		SeqDev sd;
-		sd.n = n;
-		sd.planes = d_planes.as<uint4>();
-		sd.grp_off = d_grp_off.as<uint64_t>();
-		sd.clen = d_clen.as<uint32_t>();
-		sd.len = d_len.as<uint32_t>();
-		sd.plen = d_plen.as<uint32_t>();
-		sd.raw = d_raw.as<uint8_t>();
-		sd.raw_off = d_raw_off.as<uint64_t>();
-		sd.eos_pos = d_eos_pos.as<uint32_t>();
-		sd.eos_off = d_eos_off.as<uint32_t>();
-		sd.weight = d_weight.as<float>();
-		sd.active = d_active.as<uint8_t>();
-		return sd;
-	}
-};
-
-} // namespace
-
-struct pcramp_gpu_ctx {
-	int device = 0;
-	int sm_count = 148;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[8] = {};
-	std::string err;
-	SeqSet sets[PCRAMP_NUM_KINDS];
-	// staged pairs + results
-	uint32_t n_pairs = 0, res_words = 0; // n_pairs = size of the current batch window
-	uint32_t n_staged = 0, batch_first = 0;
-	const uint64_t *pf() const { return d_f.as<uint64_t>() + 2ull * batch_first; }
-	const uint64_t *pr() const { return d_r.as<uint64_t>() + 2ull * batch_first; }
-	DevBuf d_f, d_r, d_oligos, d_cov, d_bits, d_bits1;
-	// candidates / patterns
-	DevBuf d_cand_cnt, d_cand_off, d_cand_words, d_cand_thr, d_pat_mask, d_pat_meta, d_pat_meta2, d_pat_seeded, d_pat_sbefore;
-	DevBuf d_part_mask, d_part_meta, d_part_meta2; // seeded patterns first, brute-force patterns after
-	DevBuf d_seed_cnt, d_seed_start, d_seed_bucket, d_seed_entries, d_tile_counter;
-	int max_smem_optin = 0;
-	int force_brute = 0;
-	// scratch
-	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
-	unsigned long long *h_counters = nullptr; // pinned
-	pcramp_gpu_stats stats = {};
-};
-
-namespace {
-
-#define CK(call)                                                                                      \
-	do {                                                                                              \
-		cudaError_t e__ = (call);                                                                     \
-		if (e__ != cudaSuccess) {                                                                     \
-			char b__[512];                                                                            \
-			snprintf(b__, sizeof(b__), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-			ctx->err = b__;                                                                           \
-			return 1;                                                                                 \
-		}                                                                                             \
-	} while (0)
-
-inline int fail(pcramp_gpu_ctx *ctx, const std::string &m)
-{
-	ctx->err = m;
-	return 1;
-}
-
-inline uint32_t bits_for(uint64_t n)
-{
-	uint32_t b = 1;
-	while ((1ull << b) < n) ++b;
-	return b;
-}
-
-inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 // ---------------------------------------------------------------------------------------------
 // K0: nibbles -> bit-planes
@@ -442,6 +328,8 @@ void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	for (auto &e : ctx->ev) cudaEventDestroy(e);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+	nc::thermo_state_free(ctx->thermo);
+	ctx->thermo = nullptr;
 	cudaStream_t s = ctx->stream;
 	delete ctx;
 	cudaStreamDestroy(s);

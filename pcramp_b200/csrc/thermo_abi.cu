@@ -1,0 +1,492 @@
+// thermo_abi.cu -- K3 host side: batches NucCruc problems onto the GPU and mirrors the thermodynamic filters
+// PCR::is_valid / max_dimer_tm / multiplex_compatible (valid_pcr.cpp:5-45, pcr_assay.cpp:232-269,815-852).
+// Part of libpcramp_gpu.so; no CPU evaluation path exists here: every Tm comes from thermo_kernel.
+#include "ctx.cuh"
+#include "thermo.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+using namespace pcr;
+using namespace pcr::nc;
+
+namespace pcr {
+namespace nc {
+
+struct PinnedBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	~PinnedBuf() { release(); }
+	void release()
+	{
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+	cudaError_t ensure(size_t bytes)
+	{
+		if (bytes <= cap) return cudaSuccess;
+		release();
+		const size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMallocHost(&p, want);
+		if (e != cudaSuccess) { p = nullptr; return e; }
+		cap = want;
+		return cudaSuccess;
+	}
+	template <class T> T *as() const { return (T *)p; }
+};
+
+struct ThermoState {
+	bool tables_ready = false;
+	Tables h_tables;
+	DpTable h_dp;
+	float dp_salt = -1.0f;
+	DevBuf d_tables, d_dp, d_a, d_b, d_la, d_lb, d_ls, d_out;
+	PinnedBuf h_a, h_b, h_la, h_lb, h_ls, h_out;
+	int op = -1;
+	uint32_t n = 0;
+	uint64_t cells = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	pcramp_gpu_thermo_stats stats = {};
+};
+
+void thermo_state_free(ThermoState *t)
+{
+	if (!t) return;
+	if (t->ev0) cudaEventDestroy(t->ev0);
+	if (t->ev1) cudaEventDestroy(t->ev1);
+	delete t;
+}
+
+} // namespace nc
+} // namespace pcr
+
+namespace {
+
+int thermo_get(pcramp_gpu_ctx *ctx, ThermoState **out)
+{
+	if (!ctx->thermo) {
+		ThermoState *t = new ThermoState();
+		build_tables(t->h_tables);
+		ctx->thermo = t;
+		CK(cudaEventCreate(&t->ev0));
+		CK(cudaEventCreate(&t->ev1));
+	}
+	ThermoState *t = ctx->thermo;
+	if (!t->tables_ready) {
+		CK(t->d_tables.ensure(sizeof(Tables)));
+		CK(cudaMemcpyAsync(t->d_tables.p, &t->h_tables, sizeof(Tables), cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		t->tables_ready = true;
+	}
+	*out = t;
+	return 0;
+}
+
+int thermo_set_salt(pcramp_gpu_ctx *ctx, ThermoState *t, float salt)
+{ // NucCruc::salt (nuc_cruc.h:779-794)
+	if (!(salt >= 1.0e-6f)) return fail(ctx, ":salt: [Na+] < 1.0e-6f");
+	if (salt > 1.0f) return fail(ctx, ":salt: [Na+] > 1.0f");
+	if (salt == t->dp_salt) return 0;
+	CK(cudaStreamSynchronize(ctx->stream)); // a previous launch may still read the table
+	build_dp(t->h_tables, salt, 310.15f, t->h_dp);
+	CK(t->d_dp.ensure(sizeof(DpTable)));
+	CK(cudaMemcpyAsync(t->d_dp.p, &t->h_dp, sizeof(DpTable), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	t->dp_salt = salt;
+	return 0;
+}
+
+inline bool two_sequences(int op) { return op == OP_HETERODIMER || op == OP_HETERODIMER_DIAG; }
+inline bool needs_strand(int op) { return op != OP_HAIRPIN; }
+
+// reserve pinned staging for n problems
+int thermo_reserve(pcramp_gpu_ctx *ctx, ThermoState *t, uint32_t n)
+{
+	const size_t m = n ? n : 1;
+	CK(t->h_a.ensure(m * THERMO_SEQ_STRIDE));
+	CK(t->h_b.ensure(m * THERMO_SEQ_STRIDE));
+	CK(t->h_la.ensure(m));
+	CK(t->h_lb.ensure(m));
+	CK(t->h_ls.ensure(m * sizeof(float)));
+	CK(t->h_out.ensure(m * sizeof(float4)));
+	CK(t->d_a.ensure(m * THERMO_SEQ_STRIDE));
+	CK(t->d_b.ensure(m * THERMO_SEQ_STRIDE));
+	CK(t->d_la.ensure(m));
+	CK(t->d_lb.ensure(m));
+	CK(t->d_ls.ensure(m * sizeof(float)));
+	CK(t->d_out.ensure(m * sizeof(float4)));
+	return 0;
+}
+
+// problems already encoded in the pinned staging buffers -> HBM
+int thermo_upload(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n)
+{
+	t->op = op;
+	t->n = n;
+	uint64_t cells = 0;
+	const uint8_t *la = t->h_la.as<uint8_t>(), *lb = t->h_lb.as<uint8_t>();
+	for (uint32_t p = 0; p < n; ++p) cells += (uint64_t)problem_cells(op, la[p], two_sequences(op) ? lb[p] : la[p]);
+	t->cells = cells;
+	if (!n) return 0;
+	CK(cudaMemcpyAsync(t->d_a.p, t->h_a.p, (size_t)n * THERMO_SEQ_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(t->d_la.p, t->h_la.p, n, cudaMemcpyHostToDevice, ctx->stream));
+	if (two_sequences(op)) {
+		CK(cudaMemcpyAsync(t->d_b.p, t->h_b.p, (size_t)n * THERMO_SEQ_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(t->d_lb.p, t->h_lb.p, n, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	CK(cudaMemcpyAsync(t->d_ls.p, t->h_ls.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	return 0;
+}
+
+int thermo_launch(pcramp_gpu_ctx *ctx, ThermoState *t)
+{
+	t->stats.n_problems = t->n;
+	t->stats.dp_cells = t->cells;
+	t->stats.kernel_launches = 0;
+	t->stats.ms_kernel = 0.0f;
+	if (!t->n) return 0;
+	CK(cudaEventRecord(t->ev0, ctx->stream));
+	thermo_kernel<<<grid_for(t->n, THERMO_BLOCK), THERMO_BLOCK, 0, ctx->stream>>>(t->op, t->n, t->d_a.as<uint8_t>(), t->d_b.as<uint8_t>(),
+		t->d_la.as<uint8_t>(), t->d_lb.as<uint8_t>(), t->d_ls.as<float>(), t->d_tables.as<Tables>(), t->d_dp.as<DpTable>(), t->d_out.as<float4>());
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(t->ev1, ctx->stream));
+	t->stats.kernel_launches = 1;
+	return 0;
+}
+
+int thermo_download(pcramp_gpu_ctx *ctx, ThermoState *t)
+{
+	if (t->n) CK(cudaMemcpyAsync(t->h_out.p, t->d_out.p, (size_t)t->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (t->n && t->stats.kernel_launches) {
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, t->ev0, t->ev1);
+		t->stats.ms_kernel = ms;
+	}
+	return 0;
+}
+
+// ASCII -> base codes into slot p of a staging buffer; mirrors set_query's / tm_pm_duplex's throws
+int encode_seq(pcramp_gpu_ctx *ctx, const char *s, uint32_t stride, bool allow_inosine, uint8_t *dst, uint8_t *len_out)
+{
+	memset(dst, 0, THERMO_SEQ_STRIDE);
+	uint32_t len = 0;
+	while (len < stride && s[len]) {
+		if (len >= (uint32_t)NC_MAX_LEN) return fail(ctx, "pcramp_gpu_thermo: sequence longer than 32 bases (Word length)");
+		const int c = base_code(s[len]);
+		if (c < 0 || (c == bI && !allow_inosine))
+			return fail(ctx, allow_inosine ? ":set_query: Illegal base" : "Unknown base in tm_pm_duplex");
+		dst[len] = (uint8_t)c;
+		++len;
+	}
+	*len_out = (uint8_t)len;
+	return 0;
+}
+
+inline float hetero_strand(float c_a, float c_b)
+{ // NucCruc::strand(c_a, c_b), nuc_cruc.h:818-838
+	return (c_a > c_b) ? c_a - 0.5f * c_b : c_b - 0.5f * c_a;
+}
+
+int thermo_stage_strings(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
+	const float *strand_a, const float *strand_b)
+{
+	if (op < 0 || op >= OP_COUNT) return fail(ctx, "pcramp_gpu_thermo: unknown op");
+	if (n && (!seq_a || stride == 0)) return fail(ctx, "pcramp_gpu_thermo: null sequences");
+	if (n && two_sequences(op) && (!seq_b || !strand_b)) return fail(ctx, "pcramp_gpu_thermo: heterodimer ops need seq_b and strand_b");
+	if (n && needs_strand(op) && !strand_a) return fail(ctx, "pcramp_gpu_thermo: null strand concentration");
+	if (thermo_reserve(ctx, t, n)) return 1;
+	uint8_t *ha = t->h_a.as<uint8_t>(), *hb = t->h_b.as<uint8_t>(), *la = t->h_la.as<uint8_t>(), *lb = t->h_lb.as<uint8_t>();
+	float *ls = t->h_ls.as<float>();
+	for (uint32_t p = 0; p < n; ++p) {
+		if (encode_seq(ctx, seq_a + (size_t)p * stride, stride, op != OP_PM_DUPLEX, ha + (size_t)p * THERMO_SEQ_STRIDE, la + p)) return 1;
+		if (op == OP_HAIRPIN && la[p] == 0) return fail(ctx, ":NucCruc::align_hairpin: Empty query sequence");
+		float strand = 1.0f;
+		if (two_sequences(op)) {
+			if (encode_seq(ctx, seq_b + (size_t)p * stride, stride, true, hb + (size_t)p * THERMO_SEQ_STRIDE, lb + p)) return 1;
+			if (strand_a[p] < 0.0f) return fail(ctx, ":strand: m_c_a < 0.0f");
+			if (strand_b[p] < 0.0f) return fail(ctx, ":strand: m_c_b < 0.0f");
+			strand = hetero_strand(strand_a[p], strand_b[p]);
+		} else {
+			lb[p] = 0;
+			if (needs_strand(op)) {
+				if (strand_a[p] < 0.0f) return fail(ctx, ":strand: strand_concentration < 0.0f");
+				strand = strand_a[p];
+			}
+		}
+		if (op != OP_PM_DUPLEX && op != OP_HAIRPIN && !(strand > 0.0f)) return fail(ctx, ":NucCruc::tm_dimer: Invalid strand_concentration");
+		ls[p] = logf(strand); // the float overload the reference's log() resolves to (nuc_cruc.cpp:2129)
+	}
+	return thermo_upload(ctx, t, op, n);
+}
+
+// ---- degenerate oligo expansion (Word::begin / Word::next, word.h:525-647; Word::str, :649-666) -----------------
+struct Expansion {
+	int len = 0;
+	int n_letters[32];
+	uint8_t letters[32][4];
+	uint64_t count = 1;
+};
+
+int expand_word(pcramp_gpu_ctx *ctx, const uint64_t w[2], Expansion &e)
+{
+	W128 x;
+	x.hi = w[0];
+	x.lo = w[1];
+	const int first = w_start(x), last = w_stop(x);
+	e.len = 0;
+	e.count = 1;
+	if (last < first || last < 0) return fail(ctx, "pcramp_gpu_thermo: empty oligo");
+	static const uint8_t code_of_bit[4] = {bA, bC, bG, bT}; // nibble bits A=1 C=2 G=4 T=8 (base_table.h:6-29)
+	for (int i = first; i <= last; ++i) {
+		const uint32_t nib = w_get(x, i);
+		if (nib == 0) return fail(ctx, "Unknown base in tm_pm_duplex"); // str() writes '-' for an internal EOS
+		int k = 0;
+		for (int b = 0; b < 4; ++b)
+			if (nib & (1u << b)) e.letters[e.len][k++] = code_of_bit[b];
+		e.n_letters[e.len] = k;
+		e.count *= (uint64_t)k;
+		if (e.count > (1ull << 24)) return fail(ctx, "pcramp_gpu_thermo: oligo degeneracy above 2^24");
+		++e.len;
+	}
+	return 0;
+}
+
+// the idx-th expansion (mixed radix, position 0 fastest) as base codes
+inline void expansion_at(const Expansion &e, uint64_t idx, uint8_t *dst)
+{
+	memset(dst, 0, THERMO_SEQ_STRIDE);
+	for (int i = 0; i < e.len; ++i) {
+		const int k = e.n_letters[i];
+		dst[i] = e.letters[i][idx % k];
+		idx /= k;
+	}
+}
+
+int run_and_fetch(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n)
+{
+	if (thermo_upload(ctx, t, op, n)) return 1;
+	if (thermo_launch(ctx, t)) return 1;
+	return thermo_download(ctx, t);
+}
+
+} // namespace
+
+extern "C" {
+
+int pcramp_gpu_thermo_stage(pcramp_gpu_ctx *ctx, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride, float salt,
+	const float *strand_a, const float *strand_b)
+{
+	if (!ctx) return 1;
+	CK(cudaSetDevice(ctx->device));
+	ThermoState *t = nullptr;
+	if (thermo_get(ctx, &t)) return 1;
+	if (thermo_set_salt(ctx, t, salt)) return 1;
+	return thermo_stage_strings(ctx, t, op, n, seq_a, seq_b, stride, strand_a, strand_b);
+}
+
+int pcramp_gpu_thermo_run_staged(pcramp_gpu_ctx *ctx)
+{
+	if (!ctx) return 1;
+	CK(cudaSetDevice(ctx->device));
+	if (!ctx->thermo || ctx->thermo->op < 0) return fail(ctx, "pcramp_gpu_thermo_run_staged: nothing staged");
+	return thermo_launch(ctx, ctx->thermo);
+}
+
+int pcramp_gpu_thermo_fetch(pcramp_gpu_ctx *ctx, float *tm, float *dH, float *dS, float *dG_dp)
+{
+	if (!ctx) return 1;
+	CK(cudaSetDevice(ctx->device));
+	ThermoState *t = ctx->thermo;
+	if (!t || t->op < 0) return fail(ctx, "pcramp_gpu_thermo_fetch: nothing staged");
+	if (thermo_download(ctx, t)) return 1;
+	const float4 *o = t->h_out.as<float4>();
+	for (uint32_t p = 0; p < t->n; ++p) {
+		if (tm) tm[p] = o[p].x;
+		if (dH) dH[p] = o[p].y;
+		if (dS) dS[p] = o[p].z;
+		if (dG_dp) dG_dp[p] = o[p].w;
+	}
+	return 0;
+}
+
+int pcramp_gpu_thermo_batch(pcramp_gpu_ctx *ctx, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride, float salt,
+	const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp)
+{
+	if (pcramp_gpu_thermo_stage(ctx, op, n, seq_a, seq_b, stride, salt, strand_a, strand_b)) return 1;
+	if (pcramp_gpu_thermo_run_staged(ctx)) return 1;
+	return pcramp_gpu_thermo_fetch(ctx, tm, dH, dS, dG_dp);
+}
+
+int pcramp_gpu_get_thermo_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_thermo_stats *out)
+{
+	if (!ctx || !out) return 1;
+	if (ctx->thermo) *out = ctx->thermo->stats;
+	else memset(out, 0, sizeof(*out));
+	return 0;
+}
+
+// PCR::is_valid for a batch.  The reference stops at the first failing expansion / test; the verdict is the AND over all
+// of them, so the batch runs in three rounds -- duplex Tm of every expansion, then hairpins of the oligos still
+// alive, then homodimers -- each round one kernel launch.
+int pcramp_gpu_is_valid(pcramp_gpu_ctx *ctx, const uint64_t *words, uint32_t n, float salt, float primer_strand, float tm_min, float tm_max,
+	float max_hairpin, float max_dimer, int check_homo_dimer, int fast_alignment, uint8_t *valid)
+{
+	if (!ctx) return 1;
+	if (n && (!words || !valid)) return fail(ctx, "pcramp_gpu_is_valid: null argument");
+	CK(cudaSetDevice(ctx->device));
+	ThermoState *t = nullptr;
+	if (thermo_get(ctx, &t)) return 1;
+	if (thermo_set_salt(ctx, t, salt)) return 1;
+	std::vector<Expansion> ex(n);
+	std::vector<float> log_strand(n);
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (expand_word(ctx, words + 2 * (size_t)i, ex[i])) return 1;
+		const double degen = (double)ex[i].count; // Word::degeneracy (word.h:97-138)
+		const float strand = (float)((double)primer_strand / degen); // valid_pcr.cpp:13 -> NucCruc::strand(const float &)
+		if (strand < 0.0f) return fail(ctx, ":strand: strand_concentration < 0.0f");
+		if (check_homo_dimer && !(strand > 0.0f)) return fail(ctx, ":NucCruc::tm_dimer: Invalid strand_concentration");
+		log_strand[i] = logf(strand);
+		total += ex[i].count;
+		valid[i] = 1;
+	}
+	if (total > 0xffffffffull) return fail(ctx, "pcramp_gpu_is_valid: too many expansions in one batch");
+	uint64_t launches = 0, cells = 0, problems = 0;
+	float ms = 0.0f;
+	const int ops[3] = {OP_PM_DUPLEX, OP_HAIRPIN, fast_alignment ? OP_HOMODIMER_DIAG : OP_HOMODIMER};
+	std::vector<uint32_t> owner;
+	for (int round = 0; round < (check_homo_dimer ? 3 : 2); ++round) {
+		uint64_t m = 0;
+		for (uint32_t i = 0; i < n; ++i)
+			if (valid[i]) m += ex[i].count;
+		if (!m) break;
+		if (thermo_reserve(ctx, t, (uint32_t)m)) return 1;
+		owner.resize(m);
+		uint8_t *ha = t->h_a.as<uint8_t>(), *la = t->h_la.as<uint8_t>(), *lb = t->h_lb.as<uint8_t>();
+		float *ls = t->h_ls.as<float>();
+		uint32_t p = 0;
+		for (uint32_t i = 0; i < n; ++i) {
+			if (!valid[i]) continue;
+			for (uint64_t k = 0; k < ex[i].count; ++k, ++p) {
+				expansion_at(ex[i], k, ha + (size_t)p * THERMO_SEQ_STRIDE);
+				la[p] = (uint8_t)ex[i].len;
+				lb[p] = 0;
+				ls[p] = log_strand[i];
+				owner[p] = i;
+			}
+		}
+		if (run_and_fetch(ctx, t, ops[round], (uint32_t)m)) return 1;
+		launches += t->stats.kernel_launches;
+		cells += t->stats.dp_cells;
+		problems += m;
+		ms += t->stats.ms_kernel;
+		const float4 *o = t->h_out.as<float4>();
+		for (uint32_t q = 0; q < (uint32_t)m; ++q) {
+			const float tm = o[q].x;
+			bool ok;
+			if (round == 0) ok = !((tm < tm_min) || (tm > tm_max)); // valid_pcr.cpp:20
+			else if (round == 1) ok = !(tm > max_hairpin);           // :28
+			else ok = !(tm > max_dimer);                             // :37
+			if (!ok) valid[owner[q]] = 0;
+		}
+	}
+	t->stats.kernel_launches = launches;
+	t->stats.dp_cells = cells;
+	t->stats.n_problems = problems;
+	t->stats.ms_kernel = ms;
+	return 0;
+}
+
+namespace {
+// heterodimer problems for every expansion pair of (a x b); appends to the staging buffers starting at slot p
+void stage_pair_products(ThermoState *t, const Expansion &a, const Expansion &b, float log_strand, uint32_t owner_id, std::vector<uint32_t> &owner,
+	uint32_t &p)
+{
+	uint8_t *ha = t->h_a.as<uint8_t>(), *hb = t->h_b.as<uint8_t>(), *la = t->h_la.as<uint8_t>(), *lb = t->h_lb.as<uint8_t>();
+	float *ls = t->h_ls.as<float>();
+	for (uint64_t i = 0; i < a.count; ++i)
+		for (uint64_t j = 0; j < b.count; ++j, ++p) {
+			expansion_at(a, i, ha + (size_t)p * THERMO_SEQ_STRIDE);
+			expansion_at(b, j, hb + (size_t)p * THERMO_SEQ_STRIDE);
+			la[p] = (uint8_t)a.len;
+			lb[p] = (uint8_t)b.len;
+			ls[p] = log_strand;
+			owner[p] = owner_id;
+		}
+}
+} // namespace
+
+int pcramp_gpu_max_dimer_tm(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, float salt, float primer_strand,
+	int fast_alignment, float *tm)
+{
+	if (!ctx) return 1;
+	if (n_pairs && (!f || !r || !tm)) return fail(ctx, "pcramp_gpu_max_dimer_tm: null argument");
+	CK(cudaSetDevice(ctx->device));
+	ThermoState *t = nullptr;
+	if (thermo_get(ctx, &t)) return 1;
+	if (thermo_set_salt(ctx, t, salt)) return 1;
+	std::vector<Expansion> ef(n_pairs), er(n_pairs);
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n_pairs; ++i) {
+		if (expand_word(ctx, f + 2 * (size_t)i, ef[i]) || expand_word(ctx, r + 2 * (size_t)i, er[i])) return 1;
+		total += ef[i].count * er[i].count;
+	}
+	if (total > 0xffffffffull) return fail(ctx, "pcramp_gpu_max_dimer_tm: too many expansions in one batch");
+	if (thermo_reserve(ctx, t, (uint32_t)total)) return 1;
+	std::vector<uint32_t> owner(total);
+	uint32_t p = 0;
+	for (uint32_t i = 0; i < n_pairs; ++i) {
+		// pcr_assay.cpp:244: strand(primer_strand / degen_f, primer_strand / degen_r), each narrowed to float
+		const float ca = (float)((double)primer_strand / (double)ef[i].count), cb = (float)((double)primer_strand / (double)er[i].count);
+		if (ca < 0.0f || cb < 0.0f) return fail(ctx, ":strand: m_c_a < 0.0f");
+		const float strand = hetero_strand(ca, cb);
+		if (!(strand > 0.0f)) return fail(ctx, ":NucCruc::tm_dimer: Invalid strand_concentration");
+		stage_pair_products(t, ef[i], er[i], logf(strand), i, owner, p);
+		tm[i] = 0.0f;
+	}
+	if (run_and_fetch(ctx, t, fast_alignment ? OP_HETERODIMER_DIAG : OP_HETERODIMER, (uint32_t)total)) return 1;
+	const float4 *o = t->h_out.as<float4>();
+	for (uint32_t q = 0; q < (uint32_t)total; ++q) tm[owner[q]] = std::max(tm[owner[q]], o[q].x);
+	return 0;
+}
+
+int pcramp_gpu_multiplex_compatible(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, const uint64_t *pool_f,
+	const uint64_t *pool_r, uint32_t n_pool, float salt, float primer_strand, float max_dimer, int fast_alignment, uint8_t *ok)
+{
+	if (!ctx) return 1;
+	if (n_pairs && (!f || !r || !ok)) return fail(ctx, "pcramp_gpu_multiplex_compatible: null argument");
+	if (n_pool && (!pool_f || !pool_r)) return fail(ctx, "pcramp_gpu_multiplex_compatible: null pool");
+	CK(cudaSetDevice(ctx->device));
+	ThermoState *t = nullptr;
+	if (thermo_get(ctx, &t)) return 1;
+	if (thermo_set_salt(ctx, t, salt)) return 1;
+	for (uint32_t i = 0; i < n_pairs; ++i) ok[i] = 1;
+	if (!n_pairs || !n_pool) return 0;
+	if (primer_strand < 0.0f) return fail(ctx, ":strand: strand_concentration < 0.0f");
+	if (!(primer_strand > 0.0f)) return fail(ctx, ":NucCruc::tm_dimer: Invalid strand_concentration");
+	const float log_strand = logf(primer_strand); // pcr_assay.cpp:819-821: no degeneracy correction
+	std::vector<Expansion> trial(2 * (size_t)n_pairs), pool(2 * (size_t)n_pool);
+	for (uint32_t i = 0; i < n_pairs; ++i)
+		if (expand_word(ctx, f + 2 * (size_t)i, trial[2 * i]) || expand_word(ctx, r + 2 * (size_t)i, trial[2 * i + 1])) return 1;
+	for (uint32_t i = 0; i < n_pool; ++i)
+		if (expand_word(ctx, pool_f + 2 * (size_t)i, pool[2 * i]) || expand_word(ctx, pool_r + 2 * (size_t)i, pool[2 * i + 1])) return 1;
+	uint64_t pool_count = 0, total = 0;
+	for (const Expansion &e : pool) pool_count += e.count;
+	for (const Expansion &e : trial) total += e.count * pool_count;
+	if (total > 0xffffffffull) return fail(ctx, "pcramp_gpu_multiplex_compatible: too many expansions in one batch");
+	if (thermo_reserve(ctx, t, (uint32_t)total)) return 1;
+	std::vector<uint32_t> owner(total);
+	uint32_t p = 0;
+	for (uint32_t i = 0; i < n_pairs; ++i)
+		for (const Expansion &q : pool) // main.cpp:748-752: pool_assay.multiplex_compatible(melt, opt, trial) -> the pool oligo is the query
+			for (int so = 0; so < 2; ++so) stage_pair_products(t, q, trial[2 * i + so], log_strand, i, owner, p);
+	if (run_and_fetch(ctx, t, fast_alignment ? OP_HETERODIMER_DIAG : OP_HETERODIMER, (uint32_t)total)) return 1;
+	const float4 *o = t->h_out.as<float4>();
+	for (uint32_t q = 0; q < (uint32_t)total; ++q)
+		if (o[q].x >= max_dimer) ok[owner[q]] = 0; // pcr_assay.cpp:842
+	return 0;
+}
+
+} // extern "C"

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from tests import scenarios  # noqa: E402
+from tests import thermo_cases  # noqa: E402
 from tests.harness import RefLib  # noqa: E402
 
 
@@ -78,6 +79,44 @@ def thermo_kats(ref):
     return dict(thermo_seqs=np.array(seqs), thermo_self=np.array(rows, np.float32), thermo_het=np.array(het, np.float32))
 
 
+THERMO_N = 160          # problems per (op, salt) in the committed fixture
+FILTER_N = 96           # trial oligos / pairs in the is_valid, max_dimer_tm and multiplex_compatible fixtures
+
+
+def thermo_filter_inputs(word_from_string):
+    """the words used by the is_valid / max_dimer_tm / multiplex_compatible fixtures (shared with the tests)"""
+    words = thermo_cases.primer_words(11, FILTER_N, word_from_string)
+    f = thermo_cases.primer_words(12, FILTER_N, word_from_string)
+    r = thermo_cases.primer_words(13, FILTER_N, word_from_string)
+    # pool assays keep len(F) <= len(R): see the note above ref_multiplex_compatible in oracle/ref_driver.cpp
+    pool_f = thermo_cases.primer_words(14, 3, word_from_string, lo=18, hi=20)
+    pool_r = thermo_cases.primer_words(15, 3, word_from_string, lo=21, hi=25)
+    # a few trials that do dimerise with the pool: reverse complements of pool oligos with a mismatch
+    return words, f, r, pool_f, pool_r
+
+
+def thermo_batch_kats(ref):
+    """Batches of NucCruc problems per op and salt (tests/thermo_cases.py) + the three PCR-level thermodynamic filters."""
+    rec = {}
+    for op in thermo_cases.OPS:
+        for si, salt in enumerate(thermo_cases.SALTS):
+            A, B, sa, sb = thermo_cases.problems(100 + si, THERMO_N, op)
+            rec["op%d_salt%d" % (op, si)] = ref.thermo_batch(op, A, B, salt, sa, sb)
+    words, f, r, pool_f, pool_r = thermo_filter_inputs(ref.word_from_string)
+    rec["filter_words"] = words
+    rec["filter_f"], rec["filter_r"], rec["pool_f"], rec["pool_r"] = f, r, pool_f, pool_r
+    for fast in (0, 1):
+        for homo in (0, 1):
+            rec["is_valid_fast%d_homo%d" % (fast, homo)] = ref.is_valid(words, check_homo_dimer=bool(homo), fast_alignment=bool(fast))
+        rec["is_valid_wide_fast%d" % fast] = ref.is_valid(words, tm_range=(40.0, 90.0), max_hairpin=60.0, max_dimer=60.0, check_homo_dimer=True,
+                                                           fast_alignment=bool(fast))
+        rec["is_valid_dimer_fast%d" % fast] = ref.is_valid(words, tm_range=(30.0, 95.0), max_hairpin=95.0, max_dimer=30.0, check_homo_dimer=True,
+                                                            fast_alignment=bool(fast))
+        rec["max_dimer_fast%d" % fast] = ref.max_dimer_tm(f, r, fast_alignment=bool(fast))
+        rec["multiplex_fast%d" % fast] = ref.multiplex_compatible(f, r, pool_f, pool_r, max_dimer=10.0, fast_alignment=bool(fast))
+    return rec
+
+
 def main():
     ref = RefLib()
     ref.set_threads(1)
@@ -87,6 +126,7 @@ def main():
         print("%-12s entries %5d keys %5d detected %4d" % (sc.name, len(rec["db_loc"]), len(rec["keys"]), int(rec["bits"].sum())))
     np.savez_compressed(os.path.join(HERE, "kat_words.npz"), **word_kats(ref))
     np.savez_compressed(os.path.join(HERE, "kat_thermo.npz"), **thermo_kats(ref))
+    np.savez_compressed(os.path.join(HERE, "kat_thermo_batch.npz"), **thermo_batch_kats(ref))
     print("wrote fixtures to", HERE)
 
 

@@ -243,6 +243,13 @@ class RefLib(_Base):
         self.f_has_split = self._fn("has_split", ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_int])
         self.f_thermo = self._fn("thermo", ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_float, ctypes.c_float,
                                                           ctypes.c_float, _f32p])
+        cp = ctypes.c_char_p
+        self.f_thermo_batch = self._fn("thermo_batch", ctypes.c_int, [ctypes.c_int, ctypes.c_int, cp, cp, ctypes.c_float, _f32p, _f32p])
+        self.f_is_valid = self._fn("is_valid", ctypes.c_int, [ctypes.c_uint32, _u64p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                                               ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, _u8p])
+        self.f_max_dimer = self._fn("max_dimer_tm", ctypes.c_int, [ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, ctypes.c_float, ctypes.c_int, _f32p])
+        self.f_multiplex = self._fn("multiplex_compatible", ctypes.c_int, [ctypes.c_uint32, _u64p, _u64p, ctypes.c_uint32, _u64p, _u64p,
+                                                                             ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, _u8p])
         self.n_seq = 0
 
     def set_threads(self, n):
@@ -338,3 +345,90 @@ class RefLib(_Base):
         rc = self.f_thermo(op, a.encode(), b.encode(), salt, strand_a, strand_b, _p(out, _f32p))
         assert rc == 0
         return out
+
+    def thermo_batch(self, op, seq_a, seq_b=None, salt=0.05, strand_a=9e-7, strand_b=9e-7):
+        """-> (n, 5) float32 {tm, dH, dS, dG, dG_dp}; one NucCruc per OpenMP thread, stale ring-buffer slots pinned to 'A'"""
+        a = pack_strings(seq_a)
+        b = pack_strings(seq_b) if seq_b is not None else None
+        n = len(a)
+        strand = np.stack([np.broadcast_to(np.asarray(strand_a, np.float32), (n,)), np.broadcast_to(np.asarray(strand_b, np.float32), (n,))], 1)
+        strand = np.ascontiguousarray(strand, dtype=np.float32)
+        out = np.zeros((n, 5), np.float32)
+        rc = self.f_thermo_batch(int(op), n, a.ctypes.data_as(ctypes.c_char_p), None if b is None else b.ctypes.data_as(ctypes.c_char_p),
+                                 float(salt), _p(strand, _f32p), _p(out, _f32p))
+        assert rc == 0
+        return out
+
+    def is_valid(self, words, salt=0.05, primer_strand=9e-7, tm_range=(50.0, 75.0), max_hairpin=40.0, max_dimer=40.0, check_homo_dimer=True,
+                 fast_alignment=False):
+        w = _w(words)
+        out = np.zeros(len(w), np.uint8)
+        rc = self.f_is_valid(len(w), _p(w, _u64p), salt, primer_strand, tm_range[0], tm_range[1], max_hairpin, max_dimer, int(check_homo_dimer),
+                             int(fast_alignment), _p(out, _u8p))
+        assert rc == 0
+        return out
+
+    def max_dimer_tm(self, f, r, salt=0.05, primer_strand=9e-7, fast_alignment=False):
+        f, r = _w(f), _w(r)
+        out = np.zeros(len(f), np.float32)
+        rc = self.f_max_dimer(len(f), _p(f, _u64p), _p(r, _u64p), salt, primer_strand, int(fast_alignment), _p(out, _f32p))
+        assert rc == 0
+        return out
+
+    def multiplex_compatible(self, f, r, pool_f, pool_r, salt=0.05, primer_strand=9e-7, max_dimer=40.0, fast_alignment=False):
+        f, r, pf, pr = _w(f), _w(r), _w(pool_f), _w(pool_r)
+        out = np.zeros(len(f), np.uint8)
+        rc = self.f_multiplex(len(f), _p(f, _u64p), _p(r, _u64p), len(pf), _p(pf, _u64p), _p(pr, _u64p), salt, primer_strand, max_dimer,
+                              int(fast_alignment), _p(out, _u8p))
+        assert rc == 0
+        return out
+
+
+def pack_strings(strs, stride=33):
+    buf = np.zeros((len(strs), stride), dtype=np.uint8)
+    for i, s in enumerate(strs):
+        b = str(s).encode()
+        assert len(b) < stride
+        buf[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    return buf
+
+
+HOST_THERMO_SRC = os.path.join(ROOT, "tests", "native", "host_thermo_harness.cpp")
+HOST_THERMO_LIB = os.path.join(ROOT, "build", "libhost_thermo.so")
+
+
+class HostThermo:
+    """The product's NucCruc device functions (pcramp_b200/csrc/nuccruc.cuh, all __host__ __device__) compiled for the
+    host by tests/native/host_thermo_harness.cpp -- lets the CPU tier check the K3 arithmetic without a GPU."""
+
+    def __init__(self):
+        csrc = os.path.join(ROOT, "pcramp_b200", "csrc")
+        deps = [HOST_THERMO_SRC, os.path.join(csrc, "nuccruc.cuh"), os.path.join(csrc, "word128.cuh"), os.path.join(csrc, "santalucia_tables.inc")]
+        if not os.path.exists(HOST_THERMO_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOST_THERMO_LIB) for d in deps):
+            os.makedirs(os.path.dirname(HOST_THERMO_LIB), exist_ok=True)
+            subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", "-o", HOST_THERMO_LIB,
+                            HOST_THERMO_SRC], check=True)
+        self.lib = ctypes.CDLL(HOST_THERMO_LIB)
+        self.lib.host_thermo_batch.restype = ctypes.c_int
+        self.lib.host_thermo_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_float, _f32p, _f32p,
+                                               ctypes.POINTER(ctypes.c_longlong)]
+
+    def thermo_batch(self, op, seq_a, seq_b=None, salt=0.05, strand=9e-7):
+        """strand = the effective total strand concentration (what NucCruc::strand() holds); -> (n, 4) {tm, dH, dS, dG_dp}, cells"""
+        a = pack_strings(seq_a)
+        b = pack_strings(seq_b) if seq_b is not None else None
+        n = len(a)
+        st = np.ascontiguousarray(np.broadcast_to(np.asarray(strand, np.float32), (n,)))
+        out = np.zeros((n, 4), np.float32)
+        cells = ctypes.c_longlong(0)
+        rc = self.lib.host_thermo_batch(int(op), n, a.ctypes.data_as(ctypes.c_char_p), None if b is None else b.ctypes.data_as(ctypes.c_char_p),
+                                        float(salt), _p(st, _f32p), _p(out, _f32p), ctypes.byref(cells))
+        assert rc == 0
+        return out, cells.value
+
+
+def hetero_strand(c_a, c_b):
+    """NucCruc::strand(c_a, c_b) (nuc_cruc.h:818-838) in float32"""
+    c_a = np.asarray(c_a, np.float32)
+    c_b = np.asarray(c_b, np.float32)
+    return np.where(c_a > c_b, c_a - np.float32(0.5) * c_b, c_b - np.float32(0.5) * c_a).astype(np.float32)
