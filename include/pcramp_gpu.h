@@ -172,6 +172,31 @@ typedef struct pcramp_gpu_thermo_stats {
 } pcramp_gpu_thermo_stats;
 int pcramp_gpu_get_thermo_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_thermo_stats *out);
 
+/* ---- K4: SO::SeqOverlap Smith-Waterman (seq_overlap.h, seq_overlap.cpp:347-609; nucleic-acid SmithWaterman mode,
+ *      +2 / -3 / -5 / -2) and the background tests built on it (background_match.cpp:7-295). ------------------ */
+/* Raw alignments of n (query word, target word) pairs: what pack_query_slots(Word) + pack_target_slots(Word) +
+ * align() + score() / alignment_range_query() / alignment_range_target() / target_last_two_aligned() return for one
+ * slot (seq_overlap.h:828-869,1102-1136,1265-1330).  Coordinates are -1 when no cell reaches the initial maximum
+ * (0): the reference then reports stale values of an earlier alignment.  last_two: 2 bytes per problem (4-bit codes,
+ * 15 = N).  Any output may be NULL. */
+int pcramp_gpu_sw_batch(pcramp_gpu_ctx *ctx, uint32_t n, const uint64_t *query, const uint64_t *target, int32_t *score,
+	int32_t *q_start, int32_t *q_stop, int32_t *t_start, int32_t *t_stop, uint8_t *last_two);
+/* PCR::find_background_match (background_match.cpp:7-166) for n_pairs assays against the database built by
+ * pcramp_gpu_select_words on `kind` (normally PCRAMP_BACKGROUND): collect_background_candidates with
+ * search_threshold = opt.background_threshold * opt.background_search_multiplier and the background amplicon range
+ * (assay.h:411-421), then four alignments per candidate amplicon and sqrt(S_F S_R / (2|F| 2|R|)) >= detect_threshold
+ * (= opt.background_threshold).  bitsets: n_pairs x ceil(n_seq/32), written (not OR-ed).  n_amplicons (may be NULL)
+ * receives the number of candidate amplicons.  The reference's guard `(i + 1) >= num_seq` (:122) is reproduced: a
+ * candidate at an odd position of a pair's list is scored only while that position is below the number of sequences. */
+int pcramp_gpu_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r, uint32_t n_pairs,
+	float search_threshold, float detect_threshold, int amplicon_min, int amplicon_max, int use_taq_mama,
+	uint32_t *bitsets, uint64_t *n_amplicons);
+/* PCR::find_multiplex_background_match (background_match.cpp:168-295): every sequence of `kind` (normally
+ * PCRAMP_MULTIPLEX, the amplicons of the assays already chosen, main.cpp:989-1008) against F, rc(F), R, rc(R) of
+ * every pair; a sequence is matched when any of the four normalised scores reaches threshold. */
+int pcramp_gpu_multiplex_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r,
+	uint32_t n_pairs, float threshold, int use_taq_mama, uint32_t *bitsets);
+
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* Counters of the last select_words / score_pairs call on this ctx. */
 typedef struct pcramp_gpu_stats {

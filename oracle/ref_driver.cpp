@@ -480,4 +480,100 @@ int ref_multiplex_compatible(uint32_t n, const uint64_t *f, const uint64_t *r, u
 	});
 }
 
+// ---- SO::SeqOverlap (seq_overlap.h / seq_overlap.cpp:347-609), eight problems per align() as the reference runs it ----
+// out: n x 6 int32 {score, query start, query stop, target start, target stop, (last_two.first << 4) | last_two.second}
+int ref_sw_batch(uint32_t n, const uint64_t *query, const uint64_t *target, int32_t *out)
+{
+	return guarded(NULL, [&]() {
+		SO::SeqOverlap align(SO::SeqOverlap::SmithWaterman, true);
+		for (uint32_t base = 0; base < n; base += SO_LEN) {
+			const uint32_t m = std::min<uint32_t>(SO_LEN, n - base);
+			for (uint32_t s = 0; s < SO_LEN; ++s) { // unused slots repeat the last problem so that every slot holds valid data
+				const uint32_t p = base + std::min(s, m - 1);
+				align.pack_query_slots((unsigned char)(1u << s), make_word(query + 2 * p));
+				align.pack_target_slots((unsigned char)(1u << s), make_word(target + 2 * p));
+			}
+			align.align();
+			for (uint32_t s = 0; s < m; ++s) {
+				int32_t *o = out + 6 * (size_t)(base + s);
+				o[0] = align.score(s);
+				const pair<int, int> q = align.alignment_range_query(s), t = align.alignment_range_target(s);
+				o[1] = q.first; o[2] = q.second; o[3] = t.first; o[4] = t.second;
+				const pair<unsigned char, unsigned char> l = align.target_last_two_aligned(s);
+				o[5] = ((int)l.first << 4) | (int)l.second;
+			}
+		}
+	});
+}
+
+// PCR::find_background_match (background_match.cpp:7-166) of every pair against the context's database and sequences
+// n_candidates[t] (may be NULL) = |background_amplicons| of pair t.  When that count is odd and below the number of
+// sequences the reference reads one element past the end of the list (background_match.cpp:122):
+// the driver does not call the reference for such pairs (it was seen to crash) and reports their bits as 255.
+int ref_background_match(void *h, uint32_t n_pairs, const uint64_t *f, const uint64_t *r, float background_threshold, float search_multiplier,
+	int amp_min, int amp_max, int taq_mama, uint8_t *bits, uint32_t *n_candidates)
+{
+	RefCtx *c = (RefCtx *)h;
+	Options opt;
+	opt.background_threshold = background_threshold;
+	opt.background_search_multiplier = search_multiplier;
+	opt.background_amplicon_range = make_pair(amp_min, amp_max);
+	opt.use_taq_mama = (taq_mama != 0);
+	const size_t n_seq = c->seq.size();
+	int fail = 0;
+	#pragma omp parallel for schedule(dynamic)
+	for (uint32_t t = 0; t < n_pairs; ++t) {
+		try {
+			PCR p;
+			p.oligo(FORWARD, make_word(f + 2 * t));
+			p.oligo(REVERSE, make_word(r + 2 * t));
+			BitSet m(n_seq, false);
+			ostringstream sink;
+			p.collect_background_candidates(c->db_keys, c->db, c->seq, opt);
+			const size_t n_amp = p.background_amplicons.size();
+			if (n_candidates) n_candidates[t] = (uint32_t)n_amp;
+			if ((n_amp & 1) && n_amp < n_seq) { // the reference would index background_amplicons[n_amp] (it crashes on some inputs)
+				for (size_t i = 0; i < n_seq; ++i) bits[(size_t)t * n_seq + i] = 255;
+				continue;
+			}
+			p.find_background_match(m, c->db_keys, c->db, c->seq, opt, sink);
+			for (size_t i = 0; i < n_seq; ++i) bits[(size_t)t * n_seq + i] = m[i] ? 1 : 0;
+		} catch (...) {
+			#pragma omp critical
+			fail = 1;
+		}
+	}
+	if (fail) c->err = "exception inside ref_background_match";
+	return fail;
+}
+
+// PCR::find_multiplex_background_match (background_match.cpp:168-295) against the context's sequences
+int ref_multiplex_background_match(void *h, uint32_t n_pairs, const uint64_t *f, const uint64_t *r, float background_threshold, int taq_mama,
+	uint8_t *bits)
+{
+	RefCtx *c = (RefCtx *)h;
+	Options opt;
+	opt.background_threshold = background_threshold;
+	opt.use_taq_mama = (taq_mama != 0);
+	const size_t n_seq = c->seq.size();
+	int fail = 0;
+	#pragma omp parallel for schedule(dynamic)
+	for (uint32_t t = 0; t < n_pairs; ++t) {
+		try {
+			PCR p;
+			p.oligo(FORWARD, make_word(f + 2 * t));
+			p.oligo(REVERSE, make_word(r + 2 * t));
+			BitSet m(n_seq, false);
+			ostringstream sink;
+			p.find_multiplex_background_match(m, c->seq, opt, sink);
+			for (size_t i = 0; i < n_seq; ++i) bits[(size_t)t * n_seq + i] = m[i] ? 1 : 0;
+		} catch (...) {
+			#pragma omp critical
+			fail = 1;
+		}
+	}
+	if (fail) c->err = "exception inside ref_multiplex_background_match";
+	return fail;
+}
+
 } // extern "C"

@@ -110,6 +110,11 @@ SIGNATURES = {
                                                _f32p]),
     "pcramp_gpu_multiplex_compatible": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32, _u64p, _u64p, ctypes.c_uint32,
                                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, _u8p]),
+    "pcramp_gpu_sw_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, _u64p, _u64p, _i32p, _i32p, _i32p, _i32p, _i32p, _u8p]),
+    "pcramp_gpu_background_match": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
+                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, _u32p, _u64p]),
+    "pcramp_gpu_multiplex_background_match": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float,
+                                                             ctypes.c_int, _u32p]),
     "pcramp_gpu_get_thermo_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ThermoStats)]),
     "pcramp_word_from_string": (None, [ctypes.c_char_p, ctypes.c_int, _u64p]),
     "pcramp_word_to_string": (ctypes.c_int, [_u64p, ctypes.c_char_p]),
@@ -357,6 +362,35 @@ class PcrampGpu:
                                                           _ptr(pool_r, _u64p), len(pool_f), float(salt), float(primer_strand),
                                                           float(max_dimer), int(fast_alignment), _ptr(ok, _u8p)))
         return ok
+
+    # ---- K4: Smith-Waterman and the background tests ------------------------------------------------
+    def sw_batch(self, query, target):
+        """-> (n, 6) int32 {score, q_start, q_stop, t_start, t_stop, (last_two.first << 4) | last_two.second}"""
+        q, t = _words(query), _words(target)
+        n = len(q)
+        cols = [np.zeros(n, np.int32) for _ in range(5)]
+        l2 = np.zeros((n, 2), np.uint8)
+        self._ck(self.lib.pcramp_gpu_sw_batch(self.h, n, _ptr(q, _u64p), _ptr(t, _u64p), *[_ptr(c, _i32p) for c in cols], _ptr(l2, _u8p)))
+        return np.stack(cols + [(l2[:, 0].astype(np.int32) << 4) | l2[:, 1]], 1)
+
+    def background_match(self, kind, f, r, search_threshold, detect_threshold, amplicon_min=0, amplicon_max=2000, use_taq_mama=False):
+        """-> (bitsets (n_pairs, words) uint32, number of candidate amplicons)"""
+        f, r = _words(f), _words(r)
+        nw = (self.n_seq[kind] + 31) // 32
+        bits = np.zeros((len(f), nw), np.uint32)
+        n_amp = ctypes.c_uint64()
+        self._ck(self.lib.pcramp_gpu_background_match(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), len(f), float(search_threshold),
+                                                      float(detect_threshold), int(amplicon_min), int(amplicon_max), int(use_taq_mama),
+                                                      _ptr(bits, _u32p), ctypes.byref(n_amp)))
+        return bits, n_amp.value
+
+    def multiplex_background_match(self, kind, f, r, threshold, use_taq_mama=False):
+        f, r = _words(f), _words(r)
+        nw = (self.n_seq[kind] + 31) // 32
+        bits = np.zeros((len(f), nw), np.uint32)
+        self._ck(self.lib.pcramp_gpu_multiplex_background_match(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), len(f), float(threshold),
+                                                                int(use_taq_mama), _ptr(bits, _u32p)))
+        return bits
 
     def thermo_stats(self):
         s = ThermoStats()

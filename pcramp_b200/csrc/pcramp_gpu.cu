@@ -1212,3 +1212,5 @@ void pcramp_word_center(const uint64_t a[2], uint64_t out[2])
 }
 
 } // extern "C"
+
+#include "sw_abi.cuh" // K4: Smith-Waterman batches, find_background_match, find_multiplex_background_match

@@ -1,0 +1,449 @@
+// sw_abi.cuh -- K4 (included at the end of pcramp_gpu.cu: it shares score.cuh's kernels with K2): SO::SeqOverlap Smith-Waterman batches and the two background tests built on it,
+// PCR::find_background_match and PCR::find_multiplex_background_match (background_match.cpp:7-295).
+//
+//   sw_words_kernel         one thread = one (query word, target word) alignment, with start coordinates
+//   amplicon_list_kernel    PCR::collect_candidates + find_amplicon_match for the background thresholds
+//                           (pcr_assay.cpp:12-69,338-441): every geometric candidate amplicon of every pair, as
+//                           (pair, pass, sequence, plus loc, minus loc) records; CTA per sequence, the same
+//                           lane-per-pair filter as score_kernel
+//   two stable radix sorts  -> the reference's background_amplicons order: pass {F+,R-} then {R+,F-}, each by
+//                           (sequence, plus loc, minus loc)
+//   background_sw_kernel    one thread = one candidate amplicon: the four alignments F / rc(F) vs the forward key,
+//                           R / rc(R) vs the reverse key, the normalised product score and the sequence's bit
+//   multiplex_sw_kernel     one thread = one (pair, sequence, primer strand) alignment against a whole sequence
+#pragma once
+#include "ctx.cuh"
+#include "score.cuh"
+#include "sw.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
+namespace {
+
+int check_kind2(pcramp_gpu_ctx *ctx, int kind)
+{
+	if (!ctx) return 1;
+	if (kind < 0 || kind >= PCRAMP_NUM_KINDS) return fail(ctx, "pcramp_gpu: bad sequence kind");
+	return 0;
+}
+
+__device__ __forceinline__ float taq_correction(unsigned p0, unsigned p1, unsigned t0, unsigned t1)
+{ // taq_mama_correction (word.cpp:249-294)
+	const int a = taq_index(p0), b = taq_index(p1), c = taq_index(t0), d = taq_index(t1);
+	if (a < 0 || b < 0 || c < 0 || d < 0) return 1.0f;
+	return fminf(1.0f, c_taq_mama[16 * (4 * d + c) + (4 * b + a)]);
+}
+
+__device__ __forceinline__ void word_last_two(const W128 &w, unsigned &p0, unsigned &p1)
+{ // Word::get_last_two (word.h:299-305)
+	const int last = w_stop(w);
+	p0 = last >= 1 ? w_get(w, last - 1) : 0u;
+	p1 = last >= 0 ? w_get(w, last) : 0u;
+}
+
+// ---- raw SeqOverlap batch -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sw_words_kernel(uint32_t n, const uint64_t *__restrict__ query, const uint64_t *__restrict__ target, int *out)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	W128 qw, tw;
+	qw.hi = query[2 * p]; qw.lo = query[2 * p + 1];
+	tw.hi = target[2 * p]; tw.lo = target[2 * p + 1];
+	sw::Query q;
+	sw::query_from_word(qw, q);
+	const sw::WordTarget t(tw);
+	const sw::Result r = sw::align<true>(q, t);
+	unsigned a, b;
+	sw::last_two(r, t, a, b);
+	int *o = out + 6 * (size_t)p;
+	o[0] = r.score;
+	o[1] = r.any ? r.q_start : -1;
+	o[2] = r.any ? r.q_stop : -1;
+	o[3] = r.any ? r.t_start : -1;
+	o[4] = r.any ? r.t_stop : -1;
+	o[5] = (int)((a << 4) | b);
+}
+
+// ---- candidate amplicons --------------------------------------------------------------------------------
+struct AmpliconOut {
+	uint64_t *key1;   // pair[63:33] | pass[32] | sequence[31:0]
+	uint64_t *key2;   // (plus loc + 2^31)[63:32] | (minus loc + 2^31)[31:0]
+	uint32_t *plus_id, *minus_id; // database entry ids
+	unsigned long long *count;
+	uint64_t cap;
+};
+
+__device__ inline void amplicon_emit_pass(const SeqDev &sd, uint32_t seq, const ScoreEntry *s_ent, const uint4 *__restrict__ g_pl,
+	const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand, uint32_t e0, uint32_t Ep, uint32_t E, const OligoDev &P,
+	const OligoDev &M, int amp_min, int amp_max, uint32_t lane, uint32_t pair, uint32_t pass, const AmpliconOut &out)
+{
+	const int p_thr = (int)(P.packed & 255u), p_start = (int)((P.packed >> 8) & 255u), p_stop = (int)((P.packed >> 16) & 255u);
+	const int m_thr = (int)(M.packed & 255u), m_start = (int)((M.packed >> 8) & 255u), m_stop = (int)((M.packed >> 16) & 255u);
+	const int L = (int)sd.len[seq];
+	for (uint32_t base = 0; base < Ep; base += 32u) {
+		const uint32_t e = base + lane;
+		ScoreEntry en;
+		en.a = en.c = en.g = en.t = 0u; en.loc = 0; en.strand = 0u;
+		if (e < Ep) en = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e);
+		uint32_t plus_mask = __ballot_sync(0xffffffffu, e < Ep && oligo_count(P, en) >= p_thr);
+		while (plus_mask) {
+			const int src = __ffs(plus_mask) - 1;
+			plus_mask &= plus_mask - 1u;
+			const int ploc = __shfl_sync(0xffffffffu, en.loc, src);
+			const int plus_loc3 = ploc + p_stop;
+			for (uint32_t base2 = Ep; base2 < E; base2 += 32u) {
+				const uint32_t e2 = base2 + lane;
+				bool ok = false;
+				int mloc = 0;
+				if (e2 < E) {
+					const ScoreEntry m2 = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e2);
+					mloc = m2.loc;
+					if (oligo_count(M, m2) >= m_thr && plus_loc3 < m2.loc - m_stop) { // pcr_assay.cpp:368-371
+						int amp_start = ploc + p_start;
+						const int amp_stop = min(m2.loc - m_start, L - 1);
+						int amp_len = amp_stop - amp_start + 1;
+						if (amp_len >= amp_min && amp_len <= amp_max) { // :383-392 (the `break` only prunes: length grows with the minus loc)
+							if (amp_start < 0) { amp_len += amp_start; amp_start = 0; }
+							// :418 (a split also stays inside every longer amplicon; a negative length throws in the reference)
+							ok = amp_len >= 0 && !has_split_dev(sd, seq, amp_start, amp_len);
+						}
+					}
+				}
+				const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+				if (okm) {
+					unsigned long long pos = 0;
+					if (lane == 0u) pos = atomicAdd(out.count, (unsigned long long)__popc(okm));
+					pos = __shfl_sync(0xffffffffu, pos, 0);
+					if (ok) {
+						const uint64_t o = pos + (uint64_t)__popc(okm & ((1u << lane) - 1u));
+						if (o < out.cap) {
+							out.key1[o] = ((uint64_t)pair << 33) | ((uint64_t)pass << 32) | seq;
+							out.key2[o] = ((uint64_t)(uint32_t)(ploc + 0x40000000) << 32) | (uint32_t)(mloc + 0x40000000);
+							out.plus_id[o] = e0 + (base + (uint32_t)src);
+							out.minus_id[o] = e0 + e2;
+						}
+					}
+				}
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(SCORE_THREADS)
+amplicon_list_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand,
+	const uint32_t *__restrict__ seq_off2, const OligoDev *__restrict__ oligos, uint32_t n_pairs, int amp_min, int amp_max, AmpliconOut out)
+{
+	__shared__ ScoreEntry s_ent[SCORE_SMEM_ENTRIES];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = SCORE_THREADS / 32;
+	const uint32_t n_chunks = (n_pairs + 31u) / 32u;
+	for (uint32_t seq = blockIdx.x; seq < sd.n; seq += gridDim.x) {
+		const uint32_t e0 = seq_off2[2 * seq], Ep = seq_off2[2 * seq + 1] - e0, E = seq_off2[2 * seq + 2] - e0;
+		if (Ep == 0u || Ep == E || !sd.active[seq]) continue;
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < min(E, (uint32_t)SCORE_SMEM_ENTRIES); i += SCORE_THREADS) {
+			ScoreEntry en;
+			const uint4 v = g_pl[e0 + i];
+			en.a = v.x; en.c = v.y; en.g = v.z; en.t = v.w;
+			en.loc = g_loc[e0 + i]; en.strand = g_strand[e0 + i];
+			s_ent[i] = en;
+		}
+		__syncthreads();
+		for (uint32_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+			const uint32_t p = chunk * 32u + lane;
+			OligoDev F, R;
+			F.a = F.c = F.g = F.t = R.a = R.c = R.g = R.t = 0u;
+			F.norm = R.norm = 0.0f;
+			F.packed = R.packed = 255u;
+			if (p < n_pairs) { F = oligos[2 * p]; R = oligos[2 * p + 1]; }
+			const int f_thr = (int)(F.packed & 255u), r_thr = (int)(R.packed & 255u);
+			bool fp = false, rp = false, fm = false, rm = false;
+			for (uint32_t e = 0; e < Ep; ++e) {
+				const ScoreEntry en = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e);
+				fp |= oligo_count(F, en) >= f_thr;
+				rp |= oligo_count(R, en) >= r_thr;
+			}
+			for (uint32_t e = Ep; e < E; ++e) {
+				const ScoreEntry en = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e);
+				fm |= oligo_count(F, en) >= f_thr;
+				rm |= oligo_count(R, en) >= r_thr;
+			}
+			uint32_t todo1 = __ballot_sync(0xffffffffu, fp && rm), todo2 = __ballot_sync(0xffffffffu, rp && fm);
+			uint32_t todo = todo1 | todo2;
+			while (todo) {
+				const uint32_t src = (uint32_t)__ffs(todo) - 1u;
+				todo &= todo - 1u;
+				const uint32_t q = chunk * 32u + src;
+				const OligoDev Fq = oligos[2 * q], Rq = oligos[2 * q + 1];
+				if ((todo1 >> src) & 1u)
+					amplicon_emit_pass(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Fq, Rq, amp_min, amp_max, lane, q, 0u, out);
+				if ((todo2 >> src) & 1u)
+					amplicon_emit_pass(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Rq, Fq, amp_min, amp_max, lane, q, 1u, out);
+			}
+		}
+	}
+}
+
+__global__ void iota32_kernel(uint32_t *p, uint64_t n)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = (uint32_t)i;
+}
+__global__ void gather64_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ perm, uint64_t *dst, uint64_t n)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = src[perm[i]];
+}
+
+// find_background_match's scoring loop (background_match.cpp:66-165) for the amplicon at sorted position i.
+// The reference walks the list two at a time and guards the second of each pair with `(i + 1) >= num_seq`
+// (:122): an odd-indexed candidate is scored only while its index is below the number of
+// SEQUENCES.  Reproduced as written.  (Its other effect -- reading one candidate past the end of an odd-length
+// list -- is undefined behaviour in the reference and has no counterpart here.)
+__global__ void __launch_bounds__(128) background_sw_kernel(uint64_t n, const uint64_t *__restrict__ key1_sorted, const uint32_t *__restrict__ perm,
+	const uint32_t *__restrict__ plus_id, const uint32_t *__restrict__ minus_id, const uint64_t *__restrict__ e_hi, const uint64_t *__restrict__ e_lo,
+	const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_seq, float threshold, int taq, uint32_t *bits, uint32_t n_words)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t k1 = key1_sorted[i];
+	const uint32_t pair = (uint32_t)(k1 >> 33), pass = (uint32_t)(k1 >> 32) & 1u, seq = (uint32_t)k1;
+	const uint64_t first_key = (uint64_t)pair << 33;
+	uint64_t lo = 0, hi = i; // first record of this pair
+	while (lo < hi) {
+		const uint64_t mid = (lo + hi) >> 1;
+		if (key1_sorted[mid] < first_key) lo = mid + 1; else hi = mid;
+	}
+	const uint64_t idx = i - lo;
+	if ((idx & 1ull) && idx >= (uint64_t)n_seq) return;
+	const uint32_t rec = perm[i];
+	const uint32_t pe = plus_id[rec], me = minus_id[rec];
+	// pass 0: F on the plus entry, R on the minus entry; pass 1: R on plus, F on minus (pcr_assay.cpp:421-435)
+	const uint32_t fe = pass ? me : pe, re = pass ? pe : me;
+	W128 fw, rw, fk, rk;
+	fw.hi = f[2 * pair]; fw.lo = f[2 * pair + 1];
+	rw.hi = r[2 * pair]; rw.lo = r[2 * pair + 1];
+	fk.hi = e_hi[fe]; fk.lo = e_lo[fe];
+	rk.hi = e_hi[re]; rk.lo = e_lo[re];
+	const W128 fc = w_complement(fw), rc = w_complement(rw);
+	const sw::WordTarget tf(fk), tr(rk);
+	sw::Query q;
+	sw::query_from_word(fw, q);
+	const sw::Result s0 = sw::align<false>(q, tf); // slot 0: F   + f
+	sw::query_from_word(fc, q);
+	const sw::Result s1 = sw::align<false>(q, tf); // slot 1: (F) + f
+	sw::query_from_word(rw, q);
+	const sw::Result s2 = sw::align<false>(q, tr); // slot 2: R   + r
+	sw::query_from_word(rc, q);
+	const sw::Result s3 = sw::align<false>(q, tr); // slot 3: (R) + r
+	float f_norm = __fmul_rn(2.0f, (float)w_size(fw)), r_norm = __fmul_rn(2.0f, (float)w_size(rw));
+	if (f_norm > 0.0f) f_norm = __fdiv_rn(1.0f, f_norm);
+	if (r_norm > 0.0f) r_norm = __fdiv_rn(1.0f, r_norm);
+	float FpRm = __fmul_rn(__fmul_rn((float)(s0.score * s3.score), f_norm), r_norm);
+	float RpFm = __fmul_rn(__fmul_rn((float)(s1.score * s2.score), f_norm), r_norm);
+	if (taq) {
+		unsigned p0, p1, t0, t1, u0, u1, v0, v1;
+		word_last_two(fw, p0, p1); // Fp
+		sw::last_two(s0, tf, t0, t1);
+		word_last_two(rc, u0, u1); // Rm
+		sw::last_two(s3, tr, v0, v1);
+		FpRm = __fmul_rn(FpRm, __fmul_rn(taq_correction(p0, p1, t0, t1), taq_correction(u0, u1, v0, v1)));
+		word_last_two(rw, p0, p1); // Rp
+		sw::last_two(s2, tr, t0, t1);
+		word_last_two(fc, u0, u1); // Fm
+		sw::last_two(s1, tf, v0, v1);
+		RpFm = __fmul_rn(RpFm, __fmul_rn(taq_correction(p0, p1, t0, t1), taq_correction(u0, u1, v0, v1)));
+	}
+	const float score = (FpRm > RpFm) ? __fsqrt_rn(FpRm) : __fsqrt_rn(RpFm);
+	if (score >= threshold) atomicOr(bits + (size_t)pair * n_words + (seq >> 5), 1u << (seq & 31u));
+}
+
+// find_multiplex_background_match (background_match.cpp:168-295): thread = (pair, sequence, slot); slots 0..3 =
+// F, rc(F), R, rc(R) against the whole sequence.  Consecutive threads share the sequence, so the loop length is
+// uniform in a warp and the target nibbles are broadcast loads.
+__global__ void __launch_bounds__(128) multiplex_sw_kernel(SeqDev sd, const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs,
+	float threshold, int taq, uint32_t *bits, uint32_t n_words)
+{
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t total = (uint64_t)n_pairs * 4ull * sd.n;
+	if (tid >= total) return;
+	const uint32_t pair = (uint32_t)(tid % n_pairs);
+	const uint64_t rest = tid / n_pairs;
+	const uint32_t slot = (uint32_t)(rest & 3ull), seq = (uint32_t)(rest >> 2);
+	W128 w;
+	const uint64_t *src = (slot & 2u) ? r : f;
+	w.hi = src[2 * pair]; w.lo = src[2 * pair + 1];
+	const int size = w_size(w);
+	if (slot & 1u) w = w_complement(w);
+	sw::Query q;
+	sw::query_from_word(w, q);
+	const sw::NibbleTarget t(sd.raw + sd.raw_off[seq], (int)sd.len[seq]);
+	const sw::Result s = sw::align<false>(q, t);
+	float norm = __fmul_rn(2.0f, (float)size);
+	if (norm > 0.0f) norm = __fdiv_rn(1.0f, norm);
+	float score = __fmul_rn((float)s.score, norm);
+	if (taq) {
+		unsigned p0, p1, t0, t1;
+		word_last_two(w, p0, p1);
+		sw::last_two(s, t, t0, t1);
+		score = __fmul_rn(score, taq_correction(p0, p1, t0, t1));
+	}
+	if (score >= threshold) atomicOr(bits + (size_t)pair * n_words + (seq >> 5), 1u << (seq & 31u));
+}
+
+} // namespace
+
+extern "C" {
+
+int pcramp_gpu_sw_batch(pcramp_gpu_ctx *ctx, uint32_t n, const uint64_t *query, const uint64_t *target, int32_t *score, int32_t *q_start,
+	int32_t *q_stop, int32_t *t_start, int32_t *t_stop, uint8_t *last_two)
+{
+	if (!ctx) return 1;
+	if (n && (!query || !target)) return fail(ctx, "pcramp_gpu_sw_batch: null argument");
+	CK(cudaSetDevice(ctx->device));
+	if (!n) return 0;
+	for (uint32_t p = 0; p < n; ++p) { // pack_query_slots throws on an empty query (seq_overlap.h:832-834)
+		if ((query[2 * p] | query[2 * p + 1]) == 0) return fail(ctx, ":SeqOverlap::pack_query_slots: len == 0");
+	}
+	DevBuf dq, dt, dout;
+	CK(dq.ensure((size_t)n * 16));
+	CK(dt.ensure((size_t)n * 16));
+	CK(dout.ensure((size_t)n * 24));
+	CK(cudaMemcpyAsync(dq.p, query, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(dt.p, target, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+	sw_words_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, dq.as<uint64_t>(), dt.as<uint64_t>(), dout.as<int>());
+	CK(cudaGetLastError());
+	std::vector<int> h((size_t)n * 6);
+	CK(cudaMemcpyAsync(h.data(), dout.p, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	for (uint32_t p = 0; p < n; ++p) {
+		const int *o = h.data() + 6 * (size_t)p;
+		if (score) score[p] = o[0];
+		if (q_start) q_start[p] = o[1];
+		if (q_stop) q_stop[p] = o[2];
+		if (t_start) t_start[p] = o[3];
+		if (t_stop) t_stop[p] = o[4];
+		if (last_two) { last_two[2 * p] = (uint8_t)((o[5] >> 4) & 15); last_two[2 * p + 1] = (uint8_t)(o[5] & 15); }
+	}
+	ctx->stats.kernel_launches = 1;
+	return 0;
+}
+
+int pcramp_gpu_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, float search_threshold,
+	float detect_threshold, int amp_min, int amp_max, int taq, uint32_t *bitsets, uint64_t *n_amplicons)
+{
+	if (check_kind2(ctx, kind)) return 1;
+	if (n_pairs && (!f || !r || !bitsets)) return fail(ctx, "pcramp_gpu_background_match: null argument");
+	if (n_pairs >= (1u << 30)) return fail(ctx, "pcramp_gpu_background_match: too many pairs in one batch");
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	cudaStream_t st = ctx->stream;
+	if (!s.db_valid) return fail(ctx, "pcramp_gpu_background_match: no database (call pcramp_gpu_select_words first)");
+	if (n_amplicons) *n_amplicons = 0;
+	const uint32_t n_words = (s.n + 31u) / 32u;
+	const size_t bits_bytes = std::max<size_t>(1, (size_t)n_pairs * n_words) * 4;
+	ctx->stats.kernel_launches = 0;
+	if (!n_pairs || !s.n) return 0;
+	memset(bitsets, 0, (size_t)n_pairs * n_words * 4);
+	if (!s.n_entries) return 0; // collect_background_candidates does nothing on an empty database (assay.h:411-421)
+	DevBuf d_f, d_r, d_ol, d_bits, d_cnt, k1[2], k2[2], pid, mid, perm[2], tmp;
+	CK(d_f.ensure((size_t)n_pairs * 16));
+	CK(d_r.ensure((size_t)n_pairs * 16));
+	CK(d_ol.ensure((size_t)n_pairs * 2 * sizeof(OligoDev)));
+	CK(d_bits.ensure(bits_bytes));
+	CK(d_cnt.ensure(8));
+	CK(cudaMemcpyAsync(d_f.p, f, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_r.p, r, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, st));
+	CK(cudaMemsetAsync(d_bits.p, 0, bits_bytes, st));
+	const float thr2 = search_threshold * search_threshold; // pcr_assay.cpp:31-32
+	prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(d_f.as<uint64_t>(), d_r.as<uint64_t>(), n_pairs, thr2, d_ol.as<OligoDev>());
+	CK(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	uint64_t cap = std::max<uint64_t>(1u << 16, (uint64_t)n_pairs * 64), n = 0;
+	const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		CK(k1[0].ensure(cap * 8));
+		CK(k2[0].ensure(cap * 8));
+		CK(pid.ensure(cap * 4));
+		CK(mid.ensure(cap * 4));
+		CK(cudaMemsetAsync(d_cnt.p, 0, 8, st));
+		AmpliconOut out;
+		out.key1 = k1[0].as<uint64_t>();
+		out.key2 = k2[0].as<uint64_t>();
+		out.plus_id = pid.as<uint32_t>();
+		out.minus_id = mid.as<uint32_t>();
+		out.count = d_cnt.as<unsigned long long>();
+		out.cap = cap;
+		amplicon_list_kernel<<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+			s.seq_ent_off.as<uint32_t>(), d_ol.as<OligoDev>(), n_pairs, amp_min, amp_max, out);
+		CK(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+		unsigned long long h_n = 0;
+		CK(cudaMemcpyAsync(&h_n, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		n = h_n;
+		if (n <= cap) break;
+		if (attempt == 1) return fail(ctx, "pcramp_gpu_background_match: candidate list kept growing");
+		cap = n; // the list is deterministic: the second run fits exactly
+	}
+	if (n_amplicons) *n_amplicons = n;
+	if (n >= (1ull << 32)) return fail(ctx, "pcramp_gpu_background_match: more than 2^32 candidate amplicons in one batch");
+	if (n) {
+		// order = (pair, pass, sequence, plus loc, minus loc): LSD, two stable radix sorts carrying a permutation
+		CK(k1[1].ensure(n * 8));
+		CK(k2[1].ensure(n * 8));
+		CK(perm[0].ensure(n * 4));
+		CK(perm[1].ensure(n * 4));
+		iota32_kernel<<<grid_for(n, 256), 256, 0, st>>>(perm[0].as<uint32_t>(), n);
+		size_t tmp_bytes = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k2[0].as<uint64_t>(), k2[1].as<uint64_t>(), perm[0].as<uint32_t>(), perm[1].as<uint32_t>(),
+			(int)n, 0, 64, st);
+		CK(tmp.ensure(tmp_bytes));
+		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k2[0].as<uint64_t>(), k2[1].as<uint64_t>(), perm[0].as<uint32_t>(), perm[1].as<uint32_t>(),
+			(int)n, 0, 64, st));
+		gather64_kernel<<<grid_for(n, 256), 256, 0, st>>>(k1[0].as<uint64_t>(), perm[1].as<uint32_t>(), k1[1].as<uint64_t>(), n);
+		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k1[1].as<uint64_t>(), k1[0].as<uint64_t>(), perm[1].as<uint32_t>(), perm[0].as<uint32_t>(),
+			(int)n, 0, 64, st));
+		background_sw_kernel<<<grid_for(n, 128), 128, 0, st>>>(n, k1[0].as<uint64_t>(), perm[0].as<uint32_t>(), pid.as<uint32_t>(), mid.as<uint32_t>(),
+			s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), d_f.as<uint64_t>(), d_r.as<uint64_t>(), s.n, detect_threshold, taq, d_bits.as<uint32_t>(), n_words);
+		CK(cudaGetLastError());
+		ctx->stats.kernel_launches += 5;
+	}
+	CK(cudaMemcpyAsync(bitsets, d_bits.p, (size_t)n_pairs * n_words * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int pcramp_gpu_multiplex_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, float threshold,
+	int taq, uint32_t *bitsets)
+{
+	if (check_kind2(ctx, kind)) return 1;
+	if (n_pairs && (!f || !r || !bitsets)) return fail(ctx, "pcramp_gpu_multiplex_background_match: null argument");
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	cudaStream_t st = ctx->stream;
+	const uint32_t n_words = (s.n + 31u) / 32u;
+	ctx->stats.kernel_launches = 0;
+	if (!n_pairs || !s.n) return 0;
+	for (uint32_t p = 0; p < n_pairs; ++p)
+		if ((f[2 * p] | f[2 * p + 1]) == 0 || (r[2 * p] | r[2 * p + 1]) == 0) return fail(ctx, ":SeqOverlap::pack_query_slots: len == 0");
+	const size_t bits_bytes = (size_t)n_pairs * n_words * 4;
+	DevBuf d_f, d_r, d_bits;
+	CK(d_f.ensure((size_t)n_pairs * 16));
+	CK(d_r.ensure((size_t)n_pairs * 16));
+	CK(d_bits.ensure(bits_bytes));
+	CK(cudaMemcpyAsync(d_f.p, f, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_r.p, r, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, st));
+	CK(cudaMemsetAsync(d_bits.p, 0, bits_bytes, st));
+	const uint64_t total = (uint64_t)n_pairs * 4ull * s.n;
+	multiplex_sw_kernel<<<grid_for(total, 128), 128, 0, st>>>(s.dev(), d_f.as<uint64_t>(), d_r.as<uint64_t>(), n_pairs, threshold, taq,
+		d_bits.as<uint32_t>(), n_words);
+	CK(cudaGetLastError());
+	ctx->stats.kernel_launches = 1;
+	CK(cudaMemcpyAsync(bitsets, d_bits.p, bits_bytes, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+} // extern "C"

@@ -16,6 +16,7 @@ sys.path.insert(0, ROOT)
 
 from tests import scenarios  # noqa: E402
 from tests import thermo_cases  # noqa: E402
+from tests import background_cases  # noqa: E402
 from tests.harness import RefLib  # noqa: E402
 
 
@@ -117,6 +118,32 @@ def thermo_batch_kats(ref):
     return rec
 
 
+SW_N = 4000
+
+
+def background_kats(ref):
+    """K4: raw SeqOverlap alignments, find_background_match per case, find_multiplex_background_match"""
+    rec = {}
+    q, t = background_cases.sw_problems(71, SW_N, ref.word_from_string)
+    rec["sw_query"], rec["sw_target"], rec["sw_out"] = q, t, ref.sw_batch(q, t)
+    for case in background_cases.bg_cases():
+        ref.set_sequences(case.coll)
+        for seq, pos in case.splits:
+            ref.split_sequence(seq, pos)
+        ref.select_words(case.f, case.r, case.search_threshold, min_oligo_length=background_cases.BG_MIN_LEN)
+        bits, cnt = ref.background_match(case.f, case.r, float(background_cases.BG_THRESHOLD), float(background_cases.BG_MULT),
+                                         background_cases.BG_AMP[0], background_cases.BG_AMP[1], case.taq)
+        rec["bg_%s_bits" % case.name], rec["bg_%s_count" % case.name] = bits, cnt
+        print("background %-10s candidates %6d  max/pair %4d  detected %4d  sequences %d" % (case.name, int(cnt.sum()), int(cnt.max()),
+                                                                                            int(bits.sum()), case.coll.n))
+    coll, f, r = background_cases.multiplex_case()
+    ref.set_sequences(coll)
+    for taq in (0, 1):
+        rec["multiplex_bits_taq%d" % taq] = ref.multiplex_background_match(f, r, float(background_cases.BG_THRESHOLD), bool(taq))
+    print("multiplex detected", int(rec["multiplex_bits_taq0"].sum()), int(rec["multiplex_bits_taq1"].sum()))
+    return rec
+
+
 def main():
     ref = RefLib()
     ref.set_threads(1)
@@ -127,6 +154,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_words.npz"), **word_kats(ref))
     np.savez_compressed(os.path.join(HERE, "kat_thermo.npz"), **thermo_kats(ref))
     np.savez_compressed(os.path.join(HERE, "kat_thermo_batch.npz"), **thermo_batch_kats(ref))
+    np.savez_compressed(os.path.join(HERE, "kat_background.npz"), **background_kats(ref))
     print("wrote fixtures to", HERE)
 
 

@@ -250,6 +250,10 @@ class RefLib(_Base):
         self.f_max_dimer = self._fn("max_dimer_tm", ctypes.c_int, [ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, ctypes.c_float, ctypes.c_int, _f32p])
         self.f_multiplex = self._fn("multiplex_compatible", ctypes.c_int, [ctypes.c_uint32, _u64p, _u64p, ctypes.c_uint32, _u64p, _u64p,
                                                                              ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, _u8p])
+        self.f_sw = self._fn("sw_batch", ctypes.c_int, [ctypes.c_uint32, _u64p, _u64p, _i32p])
+        self.f_bg = self._fn("background_match", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                                ctypes.c_int, ctypes.c_int, _u8p, _u32p])
+        self.f_mbg = self._fn("multiplex_background_match", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, ctypes.c_int, _u8p])
         self.n_seq = 0
 
     def set_threads(self, n):
@@ -384,6 +388,32 @@ class RefLib(_Base):
         return out
 
 
+    def sw_batch(self, query, target):
+        """SO::SeqOverlap, 8 problems per align(): -> (n, 6) int32 {score, q_start, q_stop, t_start, t_stop, last_two}"""
+        q, t = _w(query), _w(target)
+        out = np.zeros((len(q), 6), np.int32)
+        rc = self.f_sw(len(q), _p(q, _u64p), _p(t, _u64p), _p(out, _i32p))
+        assert rc == 0
+        return out
+
+    def background_match(self, f, r, background_threshold, search_multiplier, amp_min=0, amp_max=2000, taq=False):
+        """PCR::find_background_match per pair -> (bits (n_pairs, n_seq) uint8, candidate amplicon counts)"""
+        f, r = _w(f), _w(r)
+        bits = np.zeros((len(f), self.n_seq), np.uint8)
+        cnt = np.zeros(len(f), np.uint32)
+        rc = self.f_bg(self.h, len(f), _p(f, _u64p), _p(r, _u64p), background_threshold, search_multiplier, amp_min, amp_max, int(taq),
+                       _p(bits, _u8p), _p(cnt, _u32p))
+        assert rc == 0, self.f_err(self.h)
+        return bits, cnt
+
+    def multiplex_background_match(self, f, r, background_threshold, taq=False):
+        f, r = _w(f), _w(r)
+        bits = np.zeros((len(f), self.n_seq), np.uint8)
+        rc = self.f_mbg(self.h, len(f), _p(f, _u64p), _p(r, _u64p), background_threshold, int(taq), _p(bits, _u8p))
+        assert rc == 0, self.f_err(self.h)
+        return bits
+
+
 def pack_strings(strs, stride=33):
     buf = np.zeros((len(strs), stride), dtype=np.uint8)
     for i, s in enumerate(strs):
@@ -432,3 +462,27 @@ def hetero_strand(c_a, c_b):
     c_a = np.asarray(c_a, np.float32)
     c_b = np.asarray(c_b, np.float32)
     return np.where(c_a > c_b, c_a - np.float32(0.5) * c_b, c_b - np.float32(0.5) * c_a).astype(np.float32)
+
+
+HOST_SW_SRC = os.path.join(ROOT, "tests", "native", "host_sw_harness.cpp")
+HOST_SW_LIB = os.path.join(ROOT, "build", "libhost_sw.so")
+
+
+class HostSw:
+    """pcramp_b200/csrc/sw.cuh (the K4 Smith-Waterman core, __host__ __device__) compiled for the host"""
+
+    def __init__(self):
+        csrc = os.path.join(ROOT, "pcramp_b200", "csrc")
+        deps = [HOST_SW_SRC, os.path.join(csrc, "sw.cuh"), os.path.join(csrc, "word128.cuh")]
+        if not os.path.exists(HOST_SW_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOST_SW_LIB) for d in deps):
+            os.makedirs(os.path.dirname(HOST_SW_LIB), exist_ok=True)
+            subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", HOST_SW_LIB, HOST_SW_SRC], check=True)
+        self.lib = ctypes.CDLL(HOST_SW_LIB)
+        self.lib.host_sw_batch.restype = ctypes.c_int
+        self.lib.host_sw_batch.argtypes = [ctypes.c_uint32, _u64p, _u64p, ctypes.c_int, _i32p]
+
+    def sw_batch(self, query, target, with_start=True):
+        q, t = _w(query), _w(target)
+        out = np.zeros((len(q), 6), np.int32)
+        self.lib.host_sw_batch(len(q), _p(q, _u64p), _p(t, _u64p), int(with_start), _p(out, _i32p))
+        return out
