@@ -86,6 +86,38 @@ int pcramp_gpu_score_pairs(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, con
 	uint32_t n_pairs, float search_threshold, float detect_threshold, int amplicon_min, int amplicon_max,
 	int use_taq_mama, float *coverage, uint32_t *bitsets);
 
+/* The scoring step of an optimisation move (optimize_pcr.cpp:8-989; every one of the six moves is "mutate one oligo ->
+ * is_valid -> update_identity -> compute_coverage", optimize.cpp:209-261, pcr_assay.cpp:271-302): trial assay
+ * (var_f[i], var_r[i]) is scored against the candidate amplicons collect_candidates found for the UNMOVED assay
+ * (base_f[i], base_r[i]) -- same database words, same amplicon geometry, identities of the trial oligos.  With
+ * var == base this equals pcramp_gpu_score_pairs.  coverage / bitsets as there (either may be NULL). */
+int pcramp_gpu_score_variants(pcramp_gpu_ctx *ctx, int kind, const uint64_t *base_f, const uint64_t *base_r,
+	const uint64_t *var_f, const uint64_t *var_r, uint32_t n, float search_threshold, float detect_threshold,
+	int amplicon_min, int amplicon_max, int use_taq_mama, float *coverage, uint32_t *bitsets);
+
+/* optimize() (optimize.cpp:14-207) with its moves (optimize_pcr.cpp:8-989) for n_trials assays at once: what the
+ * OpenMP trial loop of main.cpp:697-729 does one assay at a time.  f / r are updated in place to the best assay found
+ * (m_assay.copy_oligos(best)); the three score arrays (any may be NULL) receive the returned Score (pcramp.h:158-215).
+ * moves: the reference's list in its order (main.cpp:77-96): values 0..5 = IncreaseDegeneracy, DecreaseDegeneracy,
+ * Trim5, Trim3, Grow5, Grow3 (assay.h:21-29).  Needs the TARGET database (and uses the BACKGROUND database when one was
+ * built); the multiplex terms (optimize.cpp:76-91: a non-empty multiplex database / assay pool) are not implemented yet
+ * and are refused. */
+typedef struct pcramp_gpu_optimize_options {
+	float target_threshold, target_search_multiplier;         /* opt.target_threshold, opt.target_search_multiplier */
+	int target_amplicon_min, target_amplicon_max;             /* opt.target_amplicon_range */
+	float background_threshold, background_search_multiplier; /* opt.background_threshold, opt.background_search_multiplier */
+	int background_amplicon_min, background_amplicon_max;     /* opt.background_amplicon_range */
+	int use_taq_mama;                                         /* opt.use_taq_mama */
+	int use_multiplex;                                        /* opt.use_multiplex (hard-wired true, options.cpp:72) */
+	uint32_t degen;                                           /* opt.degen */
+	int primer_min, primer_max;                               /* opt.primer_range */
+	float salt, primer_strand;                                /* opt.salt, opt.primer_strand */
+	float primer_tm_min, primer_tm_max, max_hairpin;          /* opt.primer_tm_range, opt.max_hairpin */
+} pcramp_gpu_optimize_options;
+int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r, uint32_t n_trials, const int *moves, uint32_t n_moves,
+	const pcramp_gpu_optimize_options *options, float *target_coverage, float *background_coverage, float *oligo_overlap,
+	uint32_t *iterations);
+
 /* ---- resident variants: the same two steps with the pairs already staged in HBM and the results
  *      left in HBM (what a multi-batch driver, the NCCL exchange and bench.py's `value` use). -------- */
 int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs);

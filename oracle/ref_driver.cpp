@@ -576,4 +576,102 @@ int ref_multiplex_background_match(void *h, uint32_t n_pairs, const uint64_t *f,
 	return fail;
 }
 
+// ---- move scoring and the local search (optimize.cpp, optimize_pcr.cpp) -----------------------------------------------------
+// What every move does to score a trial oligo (optimize_pcr.cpp: update_identity -> compute_coverage) against the candidate
+// amplicons collect_candidates built for the unmoved assay.
+int ref_score_variants(void *h, uint32_t n, const uint64_t *base_f, const uint64_t *base_r, const uint64_t *var_f, const uint64_t *var_r,
+	float target_threshold, float search_multiplier, int amp_min, int amp_max, int taq_mama, float *coverage)
+{
+	RefCtx *c = (RefCtx *)h;
+	Options opt;
+	opt.target_threshold = target_threshold;
+	opt.target_search_multiplier = search_multiplier;
+	opt.target_amplicon_range = make_pair(amp_min, amp_max);
+	opt.use_taq_mama = (taq_mama != 0);
+	int fail = 0;
+	#pragma omp parallel for schedule(dynamic)
+	for (uint32_t t = 0; t < n; ++t) {
+		try {
+			PCR p;
+			p.oligo(FORWARD, make_word(base_f + 2 * t));
+			p.oligo(REVERSE, make_word(base_r + 2 * t));
+			p.collect_target_candidates(c->db_keys, c->db, c->seq, opt);
+			update_identity(p.target_f_identity, make_word(var_f + 2 * t), c->db_keys, opt.use_taq_mama);
+			update_identity(p.target_r_identity, make_word(var_r + 2 * t), c->db_keys, opt.use_taq_mama);
+			coverage[t] = p.compute_target_coverage(opt.target_threshold);
+		} catch (...) {
+			#pragma omp critical
+			fail = 1;
+		}
+	}
+	if (fail) c->err = "exception inside ref_score_variants";
+	return fail;
+}
+
+// optimize() creates its own NucCruc on the stack (optimize.cpp:49) and the hairpin evaluation reads past the end of its
+// query buffer (see thermo_one above), so the answer depends on what the stack held.  Zero the stack region below us first:
+// the object then starts as if zero-filled (stale slots = base A), which is the convention the goldens are pinned to.
+static void __attribute__((noinline)) paint_stack()
+{
+	volatile char buf[1 << 21];
+	for (size_t i = 0; i < sizeof(buf); ++i) buf[i] = 0;
+}
+
+struct RefOptimizeOptions { // mirrors pcramp_gpu_optimize_options (include/pcramp_gpu.h)
+	float target_threshold, target_search_multiplier;
+	int target_amplicon_min, target_amplicon_max;
+	float background_threshold, background_search_multiplier;
+	int background_amplicon_min, background_amplicon_max;
+	int use_taq_mama, use_multiplex;
+	uint32_t degen;
+	int primer_min, primer_max;
+	float salt, primer_strand, primer_tm_min, primer_tm_max, max_hairpin;
+};
+
+// optimize() (optimize.cpp:14-207) of each trial, serially, against the target context h_t and (if not NULL) the background
+// context h_b; empty multiplex database and pool.  f / r are updated in place; score: n x 3 floats.
+int ref_optimize(void *h_t, void *h_b, uint32_t n, uint64_t *f, uint64_t *r, const int *moves, uint32_t n_moves, const RefOptimizeOptions *o,
+	float *score)
+{
+	RefCtx *ct = (RefCtx *)h_t, *cb = (RefCtx *)h_b;
+	return guarded(ct, [&]() {
+		Options opt;
+		opt.target_threshold = o->target_threshold;
+		opt.target_search_multiplier = o->target_search_multiplier;
+		opt.target_amplicon_range = make_pair(o->target_amplicon_min, o->target_amplicon_max);
+		opt.background_threshold = o->background_threshold;
+		opt.background_search_multiplier = o->background_search_multiplier;
+		opt.background_amplicon_range = make_pair(o->background_amplicon_min, o->background_amplicon_max);
+		opt.use_taq_mama = (o->use_taq_mama != 0);
+		opt.use_multiplex = (o->use_multiplex != 0);
+		opt.degen = o->degen;
+		opt.primer_range = make_pair(o->primer_min, o->primer_max);
+		opt.salt = o->salt;
+		opt.primer_strand = o->primer_strand;
+		opt.primer_tm_range = make_pair(o->primer_tm_min, o->primer_tm_max);
+		opt.max_hairpin = o->max_hairpin;
+		opt.output_filter = Options::SILENT;
+		vector<Move> mv;
+		for (uint32_t i = 0; i < n_moves; ++i) mv.push_back((Move)moves[i]);
+		const vector<Word> no_keys;
+		const MULTIMAP<Word, WordMatch> no_db;
+		const deque<Sequence> no_seq;
+		const deque<PCR> pool;
+		ostringstream sink;
+		for (uint32_t t = 0; t < n; ++t) {
+			PCR p;
+			p.oligo(FORWARD, make_word(f + 2 * t));
+			p.oligo(REVERSE, make_word(r + 2 * t));
+			paint_stack();
+			const Score s = optimize(p, mv, ct->db_keys, ct->db, ct->seq, cb ? cb->db_keys : no_keys, cb ? cb->db : no_db, cb ? cb->seq : no_seq,
+				no_keys, no_db, no_seq, pool, opt, sink);
+			put_word(f + 2 * t, p.oligo(FORWARD));
+			put_word(r + 2 * t, p.oligo(REVERSE));
+			score[3 * t] = s.target_coverage;
+			score[3 * t + 1] = s.background_coverage;
+			score[3 * t + 2] = s.oligo_overlap;
+		}
+	});
+}
+
 } // extern "C"

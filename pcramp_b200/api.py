@@ -58,6 +58,30 @@ class ThermoStats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class OptimizeOptions(ctypes.Structure):
+    """pcramp_gpu_optimize_options; defaults = the reference's (pcramp.h:14-51)"""
+    _fields_ = [
+        ("target_threshold", ctypes.c_float), ("target_search_multiplier", ctypes.c_float),
+        ("target_amplicon_min", ctypes.c_int), ("target_amplicon_max", ctypes.c_int),
+        ("background_threshold", ctypes.c_float), ("background_search_multiplier", ctypes.c_float),
+        ("background_amplicon_min", ctypes.c_int), ("background_amplicon_max", ctypes.c_int),
+        ("use_taq_mama", ctypes.c_int), ("use_multiplex", ctypes.c_int), ("degen", ctypes.c_uint32),
+        ("primer_min", ctypes.c_int), ("primer_max", ctypes.c_int),
+        ("salt", ctypes.c_float), ("primer_strand", ctypes.c_float),
+        ("primer_tm_min", ctypes.c_float), ("primer_tm_max", ctypes.c_float), ("max_hairpin", ctypes.c_float),
+    ]
+
+    def __init__(self, **kw):
+        d = dict(target_threshold=1.0, target_search_multiplier=0.9, target_amplicon_min=80, target_amplicon_max=200,
+                 background_threshold=0.8, background_search_multiplier=0.9, background_amplicon_min=0, background_amplicon_max=2000,
+                 use_taq_mama=0, use_multiplex=1, degen=1, primer_min=18, primer_max=25, salt=0.05, primer_strand=900.0e-9,
+                 primer_tm_min=50.0, primer_tm_max=75.0, max_hairpin=40.0)
+        d.update(kw)
+        super().__init__(**d)
+
+
+MOVES = {"IncreaseDegeneracy": 0, "DecreaseDegeneracy": 1, "Trim5": 2, "Trim3": 3, "Grow5": 4, "Grow3": 5}
+
 # op codes of pcramp_gpu_thermo_batch (include/pcramp_gpu.h)
 TM_PM_DUPLEX, TM_HAIRPIN, TM_HOMODIMER, TM_HETERODIMER, TM_HETERODIMER_DIAG, TM_HOMODIMER_DIAG = range(6)
 THERMO_STRIDE = 33  # bytes per string slot used by this wrapper (32 bases + NUL)
@@ -82,6 +106,10 @@ SIGNATURES = {
     "pcramp_gpu_keys_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p]),
     "pcramp_gpu_score_pairs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _u32p]),
+    "pcramp_gpu_score_variants": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float,
+                                                 ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _u32p]),
+    "pcramp_gpu_optimize": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32, _i32p, ctypes.c_uint32, ctypes.c_void_p, _f32p, _f32p,
+                                           _f32p, _u32p]),
     "pcramp_gpu_stage_pairs": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32]),
     "pcramp_gpu_set_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]),
     "pcramp_gpu_select_words_staged": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_uint32,
@@ -261,6 +289,30 @@ class PcrampGpu:
                                                  float(detect_threshold), int(amplicon_min), int(amplicon_max), int(use_taq_mama),
                                                  _ptr(cov, _f32p), _ptr(bits, _u32p)))
         return cov, bits
+
+    def score_variants(self, kind, base_f, base_r, var_f, var_r, search_threshold, detect_threshold, amplicon_min=80, amplicon_max=200,
+                       use_taq_mama=False):
+        """move scoring: trial oligos (var_*) against the candidate amplicons of the unmoved assays (base_*)"""
+        bf, br, vf, vr = _words(base_f), _words(base_r), _words(var_f), _words(var_r)
+        n = len(bf)
+        nw = (self.n_seq[kind] + 31) // 32
+        cov = np.zeros(n, np.float32)
+        bits = np.zeros((n, nw), np.uint32)
+        self._ck(self.lib.pcramp_gpu_score_variants(self.h, kind, _ptr(bf, _u64p), _ptr(br, _u64p), _ptr(vf, _u64p), _ptr(vr, _u64p), n,
+                                                    float(search_threshold), float(detect_threshold), int(amplicon_min), int(amplicon_max),
+                                                    int(use_taq_mama), _ptr(cov, _f32p), _ptr(bits, _u32p)))
+        return cov, bits
+
+    def optimize(self, f, r, moves, options):
+        """optimize() for a batch of trials -> (f, r, target_coverage, background_coverage, oligo_overlap, iterations)"""
+        f, r = _words(f).copy(), _words(r).copy()
+        n = len(f)
+        mv = np.ascontiguousarray([MOVES[m] if isinstance(m, str) else int(m) for m in moves], dtype=np.int32)
+        tc, bc, ov = (np.zeros(n, np.float32) for _ in range(3))
+        it = np.zeros(n, np.uint32)
+        self._ck(self.lib.pcramp_gpu_optimize(self.h, _ptr(f, _u64p), _ptr(r, _u64p), n, _ptr(mv, _i32p), len(mv), ctypes.byref(options),
+                                              _ptr(tc, _f32p), _ptr(bc, _f32p), _ptr(ov, _f32p), _ptr(it, _u32p)))
+        return f, r, tc, bc, ov, it
 
     # ---- resident variants --------------------------------------------------------------------
     def stage_pairs(self, f, r):

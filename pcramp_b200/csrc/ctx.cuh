@@ -9,10 +9,13 @@
 #include <string>
 #include <vector>
 
+struct pcramp_gpu_ctx;
 namespace pcr {
 namespace nc {
 struct ThermoState; // thermo_abi.cu
 void thermo_state_free(ThermoState *);
+int thermo_run_codes(pcramp_gpu_ctx *ctx, int op, uint32_t n, const uint8_t *codes, const uint8_t *len, const float *strand, float salt,
+	float *tm_out);
 }
 }
 
@@ -94,7 +97,7 @@ struct pcramp_gpu_ctx {
 	uint32_t n_staged = 0, batch_first = 0;
 	const uint64_t *pf() const { return d_f.as<uint64_t>() + 2ull * batch_first; }
 	const uint64_t *pr() const { return d_r.as<uint64_t>() + 2ull * batch_first; }
-	DevBuf d_f, d_r, d_oligos, d_cov, d_bits, d_bits1;
+	DevBuf d_f, d_r, d_oligos, d_oligos_base, d_variants, d_cov, d_bits, d_bits1;
 	// candidates / patterns
 	DevBuf d_cand_cnt, d_cand_off, d_cand_words, d_cand_thr, d_pat_mask, d_pat_meta, d_pat_meta2, d_pat_seeded, d_pat_sbefore;
 	DevBuf d_part_mask, d_part_meta, d_part_meta2; // seeded patterns first, brute-force patterns after

@@ -920,21 +920,23 @@ int pcramp_gpu_keys_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *keys)
 
 uint32_t pcramp_gpu_bitset_words(pcramp_gpu_ctx *ctx, int kind) { return (ctx->sets[kind].n + 31u) / 32u; }
 
-int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_threshold, float detect_threshold, int amp_min, int amp_max,
-	int taq)
+// K2 launch sequence shared by pair scoring and move-variant scoring.  d_f / d_r: the oligos whose identities are
+// computed; d_bf / d_br (variant scoring only, else null): the base assays whose candidate amplicon lists are used.
+static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, const uint64_t *d_r, const uint64_t *d_bf, const uint64_t *d_br,
+	uint32_t n_pairs, float search_threshold, float detect_threshold, int amp_min, int amp_max, int taq)
 {
-	if (check_kind(ctx, kind)) return 1;
-	CK(cudaSetDevice(ctx->device));
 	SeqSet &s = ctx->sets[kind];
 	cudaStream_t st = ctx->stream;
 	if (!s.db_valid) return fail(ctx, "pcramp_gpu_score_pairs: no database (call pcramp_gpu_select_words first)");
-	const uint32_t n_pairs = ctx->n_pairs, n_words = (s.n + 31u) / 32u;
+	const uint32_t n_words = (s.n + 31u) / 32u;
+	const bool variant = d_bf != nullptr;
 	ctx->res_words = n_words;
 	const size_t bits_bytes = std::max<size_t>(1, (size_t)n_pairs * n_words) * 4;
 	CK(ctx->d_cov.ensure(std::max<size_t>(1, n_pairs) * 4));
 	CK(ctx->d_bits.ensure(bits_bytes));
 	CK(ctx->d_bits1.ensure(bits_bytes));
 	CK(ctx->d_oligos.ensure(std::max<size_t>(1, n_pairs) * 2 * sizeof(OligoDev)));
+	if (variant) CK(ctx->d_oligos_base.ensure(std::max<size_t>(1, n_pairs) * 2 * sizeof(OligoDev)));
 	CK(cudaEventRecord(ctx->ev[5], st));
 	CK(cudaMemsetAsync(ctx->d_bits.p, 0, bits_bytes, st));
 	CK(cudaMemsetAsync(ctx->d_bits1.p, 0, bits_bytes, st));
@@ -942,15 +944,24 @@ int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_th
 	ctx->stats.ms_score = 0.0f;
 	if (n_pairs && s.n) {
 		const float thr2 = search_threshold * search_threshold; // pcr_assay.cpp:31-32 (float product)
-		prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(ctx->pf(), ctx->pr(), n_pairs, thr2,
-			ctx->d_oligos.as<OligoDev>());
+		prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(d_f, d_r, n_pairs, thr2, ctx->d_oligos.as<OligoDev>());
 		CK(cudaGetLastError());
 		ctx->stats.kernel_launches++;
+		if (variant) {
+			prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(d_bf, d_br, n_pairs, thr2, ctx->d_oligos_base.as<OligoDev>());
+			CK(cudaGetLastError());
+			ctx->stats.kernel_launches++;
+		}
 		if (s.n_entries) {
 			const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
-			score_kernel<<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(),
-				s.e_strand.as<uint32_t>(), s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>(), n_pairs, detect_threshold, amp_min,
-				amp_max, taq, ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
+			if (variant)
+				score_kernel<true><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+					s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>(), ctx->d_oligos_base.as<OligoDev>(), n_pairs, detect_threshold, amp_min,
+					amp_max, taq, ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
+			else
+				score_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+					s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>(), nullptr, n_pairs, detect_threshold, amp_min, amp_max, taq,
+					ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
 			CK(cudaGetLastError());
 			coverage_kernel<<<grid_for(n_pairs, 128), 128, 0, st>>>(ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), s.d_weight.as<float>(),
 				n_pairs, n_words, s.n, ctx->d_cov.as<float>());
@@ -962,6 +973,42 @@ int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_th
 	CK(cudaStreamSynchronize(st));
 	ctx->stats.ms_score = ev_ms(ctx->ev[5], ctx->ev[6]);
 	return 0;
+}
+
+int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_threshold, float detect_threshold, int amp_min, int amp_max,
+	int taq)
+{
+	if (check_kind(ctx, kind)) return 1;
+	CK(cudaSetDevice(ctx->device));
+	return score_launch(ctx, kind, ctx->pf(), ctx->pr(), nullptr, nullptr, ctx->n_pairs, search_threshold, detect_threshold, amp_min, amp_max, taq);
+}
+
+// The scoring step of an optimisation move for a batch of trial oligos (optimize_pcr.cpp:8-989: every move is
+// "mutate one oligo -> is_valid -> update_identity -> compute_coverage" against the candidate amplicons that
+// collect_candidates built for the UNMOVED assay): variant i is scored against the candidate list of base assay i.
+int pcramp_gpu_score_variants(pcramp_gpu_ctx *ctx, int kind, const uint64_t *base_f, const uint64_t *base_r, const uint64_t *var_f,
+	const uint64_t *var_r, uint32_t n, float search_threshold, float detect_threshold, int amp_min, int amp_max, int taq, float *coverage,
+	uint32_t *bitsets)
+{
+	if (check_kind(ctx, kind)) return 1;
+	if (n && (!base_f || !base_r || !var_f || !var_r)) return fail(ctx, "pcramp_gpu_score_variants: null argument");
+	CK(cudaSetDevice(ctx->device));
+	DevBuf &d = ctx->d_variants;
+	CK(d.ensure(std::max<size_t>(1, n) * 64));
+	uint64_t *p = d.as<uint64_t>();
+	if (n) {
+		CK(cudaMemcpyAsync(p, base_f, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(p + 2ull * n, base_r, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(p + 4ull * n, var_f, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(p + 6ull * n, var_r, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	ctx->stats.kernel_launches = 0;
+	if (score_launch(ctx, kind, p + 4ull * n, p + 6ull * n, p, p + 2ull * n, n, search_threshold, detect_threshold, amp_min, amp_max, taq)) return 1;
+	const uint32_t save = ctx->n_pairs;
+	ctx->n_pairs = n;
+	const int rc = pcramp_gpu_fetch_results(ctx, coverage, bitsets);
+	ctx->n_pairs = save;
+	return rc;
 }
 
 void *pcramp_gpu_device_coverage(pcramp_gpu_ctx *ctx) { return ctx->d_cov.p; }
@@ -1214,3 +1261,4 @@ void pcramp_word_center(const uint64_t a[2], uint64_t out[2])
 } // extern "C"
 
 #include "sw_abi.cuh" // K4: Smith-Waterman batches, find_background_match, find_multiplex_background_match
+#include "optimize_abi.cuh" // optimize() and its moves for a batch of trials

@@ -112,12 +112,18 @@ __device__ __forceinline__ ScoreEntry load_entry(const ScoreEntry *s_ent, const 
 
 // one pass of collect_candidates: oligo P binds the plus strand (entries [0, Ep)), oligo M the minus strand
 // (entries [Ep, E)).  Warp-cooperative: lanes take entries.
+//
+// VARIANT = true is the scoring an optimisation move does (optimize_pcr.cpp: is_valid -> update_identity -> compute_coverage):
+// the candidate amplicons -- which database words take part, and the amplicon geometry -- are those of the BASE assay
+// (Pb, Mb: collect_candidates ran on it, pcr_assay.cpp:12-69), while the identities are recomputed for the trial oligos
+// (P, M: update_identity, optimize.cpp:209-261).
+template <bool VARIANT>
 __device__ inline bool amplicon_pass(const SeqDev &sd, uint32_t seq, const ScoreEntry *s_ent, const uint4 *__restrict__ g_pl,
 	const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand, uint32_t e0, uint32_t Ep, uint32_t E, const OligoDev &P,
-	const OligoDev &M, float detect, int amp_min, int amp_max, int taq, uint32_t lane)
+	const OligoDev &M, const OligoDev &Pb, const OligoDev &Mb, float detect, int amp_min, int amp_max, int taq, uint32_t lane)
 {
-	const int p_thr = (int)(P.packed & 255u), p_start = (int)((P.packed >> 8) & 255u), p_stop = (int)((P.packed >> 16) & 255u);
-	const int m_thr = (int)(M.packed & 255u), m_start = (int)((M.packed >> 8) & 255u), m_stop = (int)((M.packed >> 16) & 255u);
+	const int p_thr = (int)(Pb.packed & 255u), p_start = (int)((Pb.packed >> 8) & 255u), p_stop = (int)((Pb.packed >> 16) & 255u);
+	const int m_thr = (int)(Mb.packed & 255u), m_start = (int)((Mb.packed >> 8) & 255u), m_stop = (int)((Mb.packed >> 16) & 255u);
 	const int L = (int)sd.len[seq];
 	for (uint32_t base = 0; base < Ep; base += 32u) {
 		const uint32_t e = base + lane;
@@ -125,7 +131,7 @@ __device__ inline bool amplicon_pass(const SeqDev &sd, uint32_t seq, const Score
 		en.a = en.c = en.g = en.t = 0u; en.loc = 0; en.strand = 0u;
 		if (e < Ep) en = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e);
 		const int cp = oligo_count(P, en);
-		uint32_t plus_mask = __ballot_sync(0xffffffffu, e < Ep && cp >= p_thr);
+		uint32_t plus_mask = __ballot_sync(0xffffffffu, e < Ep && (VARIANT ? oligo_count(Pb, en) : cp) >= p_thr);
 		while (plus_mask) {
 			const int src = __ffs(plus_mask) - 1;
 			plus_mask &= plus_mask - 1u;
@@ -143,7 +149,7 @@ __device__ inline bool amplicon_pass(const SeqDev &sd, uint32_t seq, const Score
 				if (e2 < E) {
 					const ScoreEntry m2 = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e2);
 					const int cm = oligo_count(M, m2);
-					if (cm >= m_thr) {
+					if ((VARIANT ? oligo_count(Mb, m2) : cm) >= m_thr) {
 						const int minus_loc5 = m2.loc - m_stop; // sequence.h:57-65, minus strand
 						if (plus_loc3 < minus_loc5) {             // pcr_assay.cpp:368-371
 							int amp_start = pe.loc + p_start;
@@ -173,10 +179,12 @@ __device__ inline bool amplicon_pass(const SeqDev &sd, uint32_t seq, const Score
 //           ~14 instructions per (32 pairs x entry); all but ~1 in 10^3 (pair, sequence) combinations end here.
 //   exact:  the surviving pairs of the warp are scored one after the other by the whole warp
 //           (amplicon_pass: geometry, has_split, identities).
+//   VARIANT: `base` holds the assays whose candidate lists are used (filter + membership), `oligos` the trial oligos.
+template <bool VARIANT>
 __global__ void __launch_bounds__(SCORE_THREADS)
 score_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand,
-	const uint32_t *__restrict__ seq_off2, const OligoDev *__restrict__ oligos, uint32_t n_pairs, float detect, int amp_min, int amp_max,
-	int taq, uint32_t *bits_any, uint32_t *bits_pass1, uint32_t n_words)
+	const uint32_t *__restrict__ seq_off2, const OligoDev *__restrict__ oligos, const OligoDev *__restrict__ base, uint32_t n_pairs,
+	float detect, int amp_min, int amp_max, int taq, uint32_t *bits_any, uint32_t *bits_pass1, uint32_t n_words)
 {
 	__shared__ ScoreEntry s_ent[SCORE_SMEM_ENTRIES];
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = SCORE_THREADS / 32;
@@ -199,7 +207,7 @@ score_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restric
 			F.a = F.c = F.g = F.t = R.a = R.c = R.g = R.t = 0u;
 			F.norm = R.norm = 0.0f;
 			F.packed = R.packed = 255u; // threshold nothing reaches
-			if (p < n_pairs) { F = oligos[2 * p]; R = oligos[2 * p + 1]; }
+			if (p < n_pairs) { F = (VARIANT ? base : oligos)[2 * p]; R = (VARIANT ? base : oligos)[2 * p + 1]; }
 			const int f_thr = (int)(F.packed & 255u), r_thr = (int)(R.packed & 255u);
 			bool fp = false, rp = false, fm = false, rm = false;
 			for (uint32_t e = 0; e < Ep; ++e) { // plus-strand entries
@@ -218,9 +226,11 @@ score_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restric
 				todo &= todo - 1u;
 				const uint32_t q = chunk * 32u + src;
 				const OligoDev Fq = oligos[2 * q], Rq = oligos[2 * q + 1];
+				const OligoDev Fb = VARIANT ? base[2 * q] : Fq, Rb = VARIANT ? base[2 * q + 1] : Rq;
 				// {F(+), R(-)} then {R(+), F(-)}  (pcr_assay.cpp:37-59)
-				const bool d1 = amplicon_pass(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Fq, Rq, detect, amp_min, amp_max, taq, lane);
-				const bool d2 = d1 ? false : amplicon_pass(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Rq, Fq, detect, amp_min, amp_max, taq, lane);
+				const bool d1 = amplicon_pass<VARIANT>(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Fq, Rq, Fb, Rb, detect, amp_min, amp_max, taq, lane);
+				const bool d2 = d1 ? false
+				                   : amplicon_pass<VARIANT>(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Rq, Fq, Rb, Fb, detect, amp_min, amp_max, taq, lane);
 				if (lane == 0u && (d1 || d2)) {
 					const uint32_t bit = 1u << (seq & 31u);
 					atomicOr(bits_any + (size_t)q * n_words + (seq >> 5), bit);

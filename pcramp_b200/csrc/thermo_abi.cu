@@ -273,6 +273,34 @@ int run_and_fetch(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n)
 
 } // namespace
 
+namespace pcr {
+namespace nc {
+// Internal entry for the other translation units of the library (the optimisation loop): problems already in base
+// codes.  codes: n x 32 bytes, the bytes past a sequence's length are what the caller wants the reference's ring
+// buffer to hold there (nuccruc.cuh header) -- zero (= A) unless a longer query was loaded before.
+int thermo_run_codes(pcramp_gpu_ctx *ctx, int op, uint32_t n, const uint8_t *codes, const uint8_t *len, const float *strand, float salt,
+	float *tm_out)
+{
+	ThermoState *t = nullptr;
+	if (thermo_get(ctx, &t)) return 1;
+	if (thermo_set_salt(ctx, t, salt)) return 1;
+	if (two_sequences(op)) return fail(ctx, "thermo_run_codes: single-sequence ops only");
+	if (thermo_reserve(ctx, t, n)) return 1;
+	if (n) {
+		memcpy(t->h_a.p, codes, (size_t)n * THERMO_SEQ_STRIDE);
+		memcpy(t->h_la.p, len, n);
+		memset(t->h_lb.p, 0, n);
+		float *ls = t->h_ls.as<float>();
+		for (uint32_t p = 0; p < n; ++p) ls[p] = logf(strand[p]);
+	}
+	if (run_and_fetch(ctx, t, op, n)) return 1;
+	const float4 *o = t->h_out.as<float4>();
+	for (uint32_t p = 0; p < n; ++p) tm_out[p] = o[p].x;
+	return 0;
+}
+} // namespace nc
+} // namespace pcr
+
 extern "C" {
 
 int pcramp_gpu_thermo_stage(pcramp_gpu_ctx *ctx, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride, float salt,

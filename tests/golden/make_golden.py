@@ -17,6 +17,7 @@ sys.path.insert(0, ROOT)
 from tests import scenarios  # noqa: E402
 from tests import thermo_cases  # noqa: E402
 from tests import background_cases  # noqa: E402
+from tests import optimize_cases  # noqa: E402
 from tests.harness import RefLib  # noqa: E402
 
 
@@ -144,6 +145,30 @@ def background_kats(ref):
     return rec
 
 
+def optimize_kats(ref_factory):
+    """the local search: score_variants (one move evaluation) and optimize() end to end, per case"""
+    rec = {}
+    for case in optimize_cases.cases():
+        ref = ref_factory()
+        ref.set_sequences(case.targets)
+        ref.select_words(case.f, case.r, case.target_search, optimize_5=case.optimize_5, optimize_3=case.optimize_3)
+        bg = None
+        if case.background is not None:
+            bg = ref_factory()
+            bg.set_sequences(case.background)
+            bg.select_words(case.f, case.r, case.background_search, optimize_5=case.optimize_5, optimize_3=case.optimize_3,
+                            min_oligo_length=background_cases.BG_MIN_LEN)
+        f, r, score = ref.optimize(case.f, case.r, case.moves, case.options, bg)
+        rec["opt_%s_f" % case.name], rec["opt_%s_r" % case.name], rec["opt_%s_score" % case.name] = f, r, score
+        # one move evaluation: the optimised oligos scored against the candidate lists of the starting assays
+        rec["var_%s_cov" % case.name] = ref.score_variants(case.f, case.r, f, r, float(case.options.target_threshold),
+                                                          float(case.options.target_search_multiplier), case.options.target_amplicon_min,
+                                                          case.options.target_amplicon_max, bool(case.options.use_taq_mama))
+        changed = int(((f != case.f).any(1) | (r != case.r).any(1)).sum())
+        print("optimize %-18s changed %3d of %3d  mean score %s" % (case.name, changed, len(f), score.mean(0)))
+    return rec
+
+
 def main():
     ref = RefLib()
     ref.set_threads(1)
@@ -155,6 +180,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_thermo.npz"), **thermo_kats(ref))
     np.savez_compressed(os.path.join(HERE, "kat_thermo_batch.npz"), **thermo_batch_kats(ref))
     np.savez_compressed(os.path.join(HERE, "kat_background.npz"), **background_kats(ref))
+    np.savez_compressed(os.path.join(HERE, "kat_optimize.npz"), **optimize_kats(RefLib))
     print("wrote fixtures to", HERE)
 
 

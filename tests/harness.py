@@ -254,6 +254,9 @@ class RefLib(_Base):
         self.f_bg = self._fn("background_match", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                                                 ctypes.c_int, ctypes.c_int, _u8p, _u32p])
         self.f_mbg = self._fn("multiplex_background_match", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, ctypes.c_int, _u8p])
+        self.f_variants = self._fn("score_variants", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, _u64p, _u64p, ctypes.c_float, ctypes.c_float,
+                                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p])
+        self.f_optimize = self._fn("optimize", ctypes.c_int, [vp, vp, ctypes.c_uint32, _u64p, _u64p, _i32p, ctypes.c_uint32, ctypes.c_void_p, _f32p])
         self.n_seq = 0
 
     def set_threads(self, n):
@@ -387,6 +390,24 @@ class RefLib(_Base):
         assert rc == 0
         return out
 
+
+    def score_variants(self, base_f, base_r, var_f, var_r, target_threshold, search_multiplier, amp_min=80, amp_max=200, taq=False):
+        bf, br, vf, vr = _w(base_f), _w(base_r), _w(var_f), _w(var_r)
+        cov = np.zeros(len(bf), np.float32)
+        rc = self.f_variants(self.h, len(bf), _p(bf, _u64p), _p(br, _u64p), _p(vf, _u64p), _p(vr, _u64p), target_threshold, search_multiplier,
+                             amp_min, amp_max, int(taq), _p(cov, _f32p))
+        assert rc == 0, self.f_err(self.h)
+        return cov
+
+    def optimize(self, f, r, moves, options, background=None):
+        """the reference's optimize() per trial (serial); options = pcramp_b200.api.OptimizeOptions; background = another RefLib"""
+        f, r = _w(f).copy(), _w(r).copy()
+        mv = np.ascontiguousarray(moves, dtype=np.int32)
+        score = np.zeros((len(f), 3), np.float32)
+        rc = self.f_optimize(self.h, background.h if background is not None else None, len(f), _p(f, _u64p), _p(r, _u64p), _p(mv, _i32p), len(mv),
+                             ctypes.byref(options), _p(score, _f32p))
+        assert rc == 0, self.f_err(self.h)
+        return f, r, score
 
     def sw_batch(self, query, target):
         """SO::SeqOverlap, 8 problems per align(): -> (n, 6) int32 {score, q_start, q_stop, t_start, t_stop, last_two}"""

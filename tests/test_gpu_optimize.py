@@ -1,0 +1,72 @@
+"""GPU (-m gpu): the local search -- one move evaluation (pcramp_gpu_score_variants) and optimize() with the six moves
+(pcramp_gpu_optimize) -- against goldens of the UNMODIFIED reference's optimize() (tests/golden/make_golden.py) and the
+live reference when it travelled.  Selected oligos bit-exact, scores bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from pcramp_b200 import BACKGROUND, TARGET
+from tests import background_cases as bc
+from tests import optimize_cases as oc
+from tests.harness import REF_PATH, RefLib
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def prepare(gpu, case):
+    gpu.upload_sequences(TARGET, case.targets.nibbles, case.targets.byte_off, case.targets.length, case.targets.weight)
+    gpu.select_words(TARGET, case.f, case.r, case.target_search, optimize_5=case.optimize_5, optimize_3=case.optimize_3)
+    if case.background is not None:
+        b = case.background
+        gpu.upload_sequences(BACKGROUND, b.nibbles, b.byte_off, b.length, b.weight)
+        gpu.select_words(BACKGROUND, case.f, case.r, case.background_search, optimize_5=case.optimize_5, optimize_3=case.optimize_3,
+                         min_oligo_length=bc.BG_MIN_LEN)
+    else:
+        empty = np.zeros(0, np.uint8)
+        gpu.upload_sequences(BACKGROUND, empty, np.zeros(0, np.uint64), np.zeros(0, np.uint32))
+        gpu.select_words(BACKGROUND, case.f, case.r, case.background_search)
+
+
+@pytest.mark.parametrize("case", oc.cases(), ids=lambda c: c.name)
+def test_optimize_matches_reference_golden(gpu, case):
+    g = np.load(os.path.join(GOLD, "kat_optimize.npz"))
+    prepare(gpu, case)
+    o = case.options
+    cov, _ = gpu.score_variants(TARGET, case.f, case.r, g["opt_%s_f" % case.name], g["opt_%s_r" % case.name], case.target_search,
+                                float(o.target_threshold), o.target_amplicon_min, o.target_amplicon_max, bool(o.use_taq_mama))
+    assert np.array_equal(cov.view(np.uint32), g["var_%s_cov" % case.name].view(np.uint32))
+    f, r, tc, bcov, ov, it = gpu.optimize(case.f, case.r, case.moves, o)
+    want = g["opt_%s_score" % case.name]
+    bad = np.where((f != g["opt_%s_f" % case.name]).any(1) | (r != g["opt_%s_r" % case.name]).any(1))[0]
+    assert len(bad) == 0, "trials with different oligos: %s" % bad[:10]
+    got = np.stack([tc, bcov, ov], 1)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert it.min() >= 1
+
+
+def test_variants_with_base_equal_score_pairs(gpu):
+    case = oc.cases()[0]
+    prepare(gpu, case)
+    o = case.options
+    cov_a, bits_a = gpu.score_pairs(TARGET, case.f, case.r, case.target_search, float(o.target_threshold))
+    cov_b, bits_b = gpu.score_variants(TARGET, case.f, case.r, case.f, case.r, case.target_search, float(o.target_threshold))
+    assert np.array_equal(cov_a, cov_b) and np.array_equal(bits_a, bits_b)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PATH), reason="compiled reference did not travel with the snapshot")
+def test_optimize_matches_live_reference(gpu):
+    case = oc.cases()[2]
+    ref = RefLib()
+    ref.set_sequences(case.targets)
+    ref.select_words(case.f, case.r, case.target_search, optimize_5=case.optimize_5, optimize_3=case.optimize_3)
+    bg = RefLib()
+    bg.set_sequences(case.background)
+    bg.select_words(case.f, case.r, case.background_search, optimize_5=case.optimize_5, optimize_3=case.optimize_3, min_oligo_length=bc.BG_MIN_LEN)
+    wf, wr, wscore = ref.optimize(case.f, case.r, case.moves, case.options, bg)
+    prepare(gpu, case)
+    f, r, tc, bcov, ov, it = gpu.optimize(case.f, case.r, case.moves, case.options)
+    assert np.array_equal(f, wf) and np.array_equal(r, wr)
+    assert np.array_equal(np.stack([tc, bcov, ov], 1).view(np.uint32), wscore.view(np.uint32))
