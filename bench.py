@@ -262,12 +262,16 @@ def dp_leg(a, g, torch, ext, rank, world, dist):
             A = [bytes(r[:int(np.argmax(r == 0))]).decode() for r in sa[:m]]
             B = [bytes(r[:int(np.argmax(r == 0))]).decode() for r in sb[:m]]
             ref.thermo_batch(3, A[:2000], B[:2000], 0.05, strand, strand)
+            c1 = float(sum(len(x) * len(y) for x, y in zip(A, B)))
+            reps, c = 0, 0.0
             t0 = time.perf_counter()
-            ref.thermo_batch(3, A, B, 0.05, strand, strand)
+            while reps < 64 and (reps == 0 or time.perf_counter() - t0 < 8.0):
+                ref.thermo_batch(3, A, B, 0.05, strand, strand)
+                reps += 1
+                c += c1
             dt = time.perf_counter() - t0
-            c = float(sum(len(x) * len(y) for x, y in zip(A, B)))
             out["cpu_baseline"] = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": ref.max_threads(), "kind": "reference", "seconds": dt,
-                                   "sample": "the first %d problems of the step, one NucCruc per OpenMP thread" % m}
+                                   "sample": "the first %d problems of the step x %d passes, one NucCruc per OpenMP thread" % (m, reps)}
     return out
 
 

@@ -98,20 +98,20 @@ struct Ctx {
 	const unsigned char *q, *t; // 5'-3' bases, NC_SEQ_CAP entries each, slots past the length hold bA
 	int qlen, tlen;
 	float log_strand; // logf(strand concentration), host libm
-	// DP storage
-	int *M;                 // NC_CELLS match scores
-	unsigned short *info;   // NC_CELLS: M_trace[3:0] | Iq_trace[7:4] | It_trace[11:8] | Iq<0 [12] | It<0 [13]
+	// DP storage: one 16-bit word per cell is all the enumeration needs --
+	//   M_trace[3:0] | Iq_trace[7:4] | It_trace[11:8] | Iq<0 [12] | It<0 [13] | M<0 [14] | M==0 [15]
+	// (the scores themselves only matter for "is this a maximal cell", kept as a short list, see dp_fill)
+	unsigned short *info;   // NC_CELLS
+	int max_cell[8];        // the first NC_MAX_CELLS cells whose M equals the maximum, in row-major order
+	int n_max_cell;         // how many cells equal the maximum (may exceed NC_MAX_CELLS)
 };
+constexpr int NC_MAX_CELLS = 8;
 
 PCR_HD int seq_at(const unsigned char *s, int i) { return (i >= 0 && i < NC_SEQ_CAP) ? s[i] : bA; }
 
 // ---------------------------------------------------------------------------------------------
 // DP fill (nuc_cruc.cpp:347-541 dimer, :546-612 diagonal, :616-816 hairpin)
 // ---------------------------------------------------------------------------------------------
-struct RowState {
-	int M[NC_STRIDE], Iq[NC_STRIDE], It[NC_STRIDE];
-};
-
 PCR_HD int dp_step(int prev_score, int dg) { return (0 < prev_score) ? prev_score - dg : -dg; }
 
 // one interior cell; A = (i-1, j-1), B = (i-1, j), C = (i, j-1)
@@ -167,79 +167,114 @@ PCR_HD void dp_cell(const DpTable *D, int tb, int ptb, int qb, int pqb, int aM, 
 		xIt = ext;
 		ttr = TR_UP;
 	}
-	info = (unsigned short)(mtr | (qtr << 4) | (ttr << 8) | ((xIq < 0) ? 0x1000 : 0) | ((xIt < 0) ? 0x2000 : 0));
+	info = (unsigned short)(mtr | (qtr << 4) | (ttr << 8) | ((xIq < 0) ? 0x1000 : 0) | ((xIt < 0) ? 0x2000 : 0) | ((xM < 0) ? 0x4000 : 0) |
+	                        ((xM == 0) ? 0x8000 : 0));
 }
 
 PCR_HD void dp_border(Ctx &c)
 { // NC_Elem() : scores -1, traces invalid (nuc_cruc.h:427-433); row 0 and column 0 are never written
-	const unsigned short b = (unsigned short)(TR_INVALID | (TR_INVALID << 4) | (TR_INVALID << 8) | 0x3000);
+	const unsigned short b = (unsigned short)(TR_INVALID | (TR_INVALID << 4) | (TR_INVALID << 8) | 0x7000);
 	for (int k = 0; k < NC_STRIDE; ++k) {
-		c.M[k] = -1;
 		c.info[k] = b;
-		c.M[k * NC_STRIDE] = -1;
 		c.info[k * NC_STRIDE] = b;
 	}
 }
 
-// gapped dimer (hairpin = false) or hairpin triangle (hairpin = true, target = query); returns max score
-PCR_HD int dp_fill(Ctx &c, bool hairpin, long long *cells_out)
+// max_ptr bookkeeping (nuc_cruc.cpp:517-537): cells that equal the running maximum, reset when it rises
+PCR_HD void note_cell(Ctx &c, int cell, int xM, int &max_score)
 {
-	dp_border(c);
+	if (xM > max_score) {
+		max_score = xM;
+		c.n_max_cell = 1;
+		c.max_cell[0] = cell;
+	} else if (xM == max_score) {
+		if (c.n_max_cell < NC_MAX_CELLS) c.max_cell[c.n_max_cell] = cell;
+		++c.n_max_cell;
+	}
+}
+
+struct Aln;
+PCR_HD void enumerate_dimer(Ctx &c, int cell, Aln &best, int mode);
+PCR_HD void enumerate_hairpin(Ctx &c, int cell, Aln &best);
+
+// gapped dimer (hairpin = false) or hairpin triangle (hairpin = true, target = query); returns the maximum score.
+// One row of (M, Iq, It) is kept: cell (i-1, j) is read from it and overwritten by (i, j); (i-1, j-1) and (i, j-1) ride
+// along in registers.  REPLAY = true is the rare second pass for problems with more than NC_MAX_CELLS maximal cells: the
+// trace bits are complete, the scores are recomputed and every cell equal to `replay_max` is enumerated in row-major order.
+template <bool REPLAY>
+PCR_HD int dp_fill_t(Ctx &c, bool hairpin, long long *cells_out, int replay_max, Aln *best, int mode)
+{
+	if (!REPLAY) {
+		dp_border(c);
+		c.n_max_cell = 0;
+	}
 	const int qlen = c.qlen, tlen = hairpin ? c.qlen : c.tlen;
 	const unsigned char *tq = hairpin ? c.q : c.t;
 	const int max_stem = qlen - 4; // steric limit 3 + 1 (nuc_cruc.cpp:627-635)
 	const int rows = hairpin ? max_stem : qlen;
-	RowState prev, cur;
-	for (int j = 0; j < NC_STRIDE; ++j) prev.M[j] = prev.Iq[j] = prev.It[j] = -1;
+	int rM[NC_STRIDE], rIq[NC_STRIDE], rIt[NC_STRIDE];
+	for (int j = 0; j < NC_STRIDE; ++j) rM[j] = rIq[j] = rIt[j] = -1;
 	int max_score = -1;
 	long long cells = 0;
 	for (int i = 1; i <= rows; ++i) {
 		const int qb = seq_at(c.q, qlen - i);
 		const int pqb = (i == 1) ? bGAP : seq_at(c.q, qlen - (i - 1));
 		const int cols = hairpin ? (max_stem - (i - 1)) : tlen;
-		cur.M[0] = cur.Iq[0] = cur.It[0] = -1;
+		int aM = -1, aIq = -1, aIt = -1; // (i-1, j-1): column 0 is the border
+		int cM = -1, cIq = -1;           // (i, j-1)
+		int ptb = bGAP;
 		for (int j = 1; j <= cols; ++j) {
 			const int tb = seq_at(tq, j - 1);
-			const int ptb = (j == 1) ? bGAP : seq_at(tq, j - 2);
+			const int bM = rM[j], bIq = rIq[j], bIt = rIt[j]; // (i-1, j)
 			int xM, xIq, xIt;
 			unsigned short inf;
-			dp_cell(c.D, tb, ptb, qb, pqb, prev.M[j - 1], prev.Iq[j - 1], prev.It[j - 1], prev.M[j], prev.It[j], cur.M[j - 1], cur.Iq[j - 1], xM,
-				xIq, xIt, inf);
-			cur.M[j] = xM;
-			cur.Iq[j] = xIq;
-			cur.It[j] = xIt;
-			c.M[i * NC_STRIDE + j] = xM;
-			c.info[i * NC_STRIDE + j] = inf;
-			if (xM > max_score) max_score = xM;
+			dp_cell(c.D, tb, ptb, qb, pqb, aM, aIq, aIt, bM, bIt, cM, cIq, xM, xIq, xIt, inf);
+			rM[j] = xM;
+			rIq[j] = xIq;
+			rIt[j] = xIt;
+			const int cell = i * NC_STRIDE + j;
+			if (!REPLAY) {
+				c.info[cell] = inf;
+				note_cell(c, cell, xM, max_score);
+			} else if (xM == replay_max) {
+				if (hairpin) enumerate_hairpin(c, cell, *best);
+				else enumerate_dimer(c, cell, *best, mode);
+			}
+			aM = bM; aIq = bIq; aIt = bIt;
+			cM = xM; cIq = xIq;
+			ptb = tb;
 		}
 		cells += cols;
-		for (int j = 0; j <= cols; ++j) {
-			prev.M[j] = cur.M[j];
-			prev.Iq[j] = cur.Iq[j];
-			prev.It[j] = cur.It[j];
-		}
 	}
 	if (cells_out) *cells_out = cells;
-	return max_score;
+	return REPLAY ? replay_max : max_score;
 }
 
 // gap-free main diagonal only (fast_alignment(true))
-PCR_HD int dp_fill_diagonal(Ctx &c, long long *cells_out)
+template <bool REPLAY>
+PCR_HD int dp_fill_diagonal_t(Ctx &c, long long *cells_out, int replay_max, Aln *best, int mode)
 {
-	dp_border(c);
+	if (!REPLAY) {
+		dp_border(c);
+		c.n_max_cell = 0;
+	}
 	const int len = c.qlen < c.tlen ? c.qlen : c.tlen;
 	int max_score = -1, prev_pair = bpair(bGAP, bGAP), aM = -1;
 	for (int i = 1; i <= len; ++i) {
 		const int cur_pair = bpair(seq_at(c.t, i - 1), seq_at(c.q, c.qlen - i));
 		const int xM = dp_step(aM, c.D->dg[prev_pair * NPAIR + cur_pair]);
-		c.M[i * NC_STRIDE + i] = xM;
-		c.info[i * NC_STRIDE + i] = (unsigned short)(TR_DIAG | (TR_INVALID << 4) | (TR_INVALID << 8) | 0x3000);
-		if (xM > max_score) max_score = xM;
+		const int cell = i * NC_STRIDE + i;
+		if (!REPLAY) {
+			c.info[cell] = (unsigned short)(TR_DIAG | (TR_INVALID << 4) | (TR_INVALID << 8) | 0x3000 | ((xM < 0) ? 0x4000 : 0) | ((xM == 0) ? 0x8000 : 0));
+			note_cell(c, cell, xM, max_score);
+		} else if (xM == replay_max) {
+			enumerate_dimer(c, cell, *best, mode);
+		}
 		aM = xM;
 		prev_pair = cur_pair;
 	}
 	if (cells_out) *cells_out = len;
-	return max_score;
+	return REPLAY ? replay_max : max_score;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -312,9 +347,8 @@ PCR_HD void trace_back(Ctx &c, int cell, TraceStack &st, int &zero_count, Aln &a
 			if (last_i > query_len || last_j < 1) {
 				valid = false;
 			} else {
-				const int m = c.M[cell];
-				if (m < 0) valid = false;
-				else if (m == 0) {
+				if (inf & 0x4000) valid = false; // M < 0
+				else if (inf & 0x8000) {         // M == 0
 					if (count_zeros) zero_count++;
 					else {
 						truncate_at_zero--;
@@ -736,25 +770,20 @@ PCR_HD Result run_problem(Ctx &c, int op)
 		return r;
 	}
 	int max_score;
-	if (op == OP_HAIRPIN) {
-		max_score = dp_fill(c, true, &r.cells);
-		const int max_stem = c.qlen - 4;
-		for (int i = 1; i <= max_stem; ++i)
-			for (int j = 1; j <= max_stem - (i - 1); ++j)
-				if (c.M[i * NC_STRIDE + j] == max_score) enumerate_hairpin(c, i * NC_STRIDE + j, best);
-	} else {
-		const int mode = (op == OP_HOMODIMER || op == OP_HOMODIMER_DIAG) ? MODE_HOMO : MODE_HETERO;
-		if (op == OP_HETERODIMER_DIAG || op == OP_HOMODIMER_DIAG) {
-			max_score = dp_fill_diagonal(c, &r.cells);
-			const int len = c.qlen < c.tlen ? c.qlen : c.tlen;
-			for (int i = 1; i <= len; ++i)
-				if (c.M[i * NC_STRIDE + i] == max_score) enumerate_dimer(c, i * NC_STRIDE + i, best, mode);
-		} else {
-			max_score = dp_fill(c, false, &r.cells);
-			for (int i = 1; i <= c.qlen; ++i)
-				for (int j = 1; j <= c.tlen; ++j)
-					if (c.M[i * NC_STRIDE + j] == max_score) enumerate_dimer(c, i * NC_STRIDE + j, best, mode);
+	const bool hairpin = (op == OP_HAIRPIN);
+	const bool diagonal = (op == OP_HETERODIMER_DIAG || op == OP_HOMODIMER_DIAG);
+	const int mode = hairpin ? MODE_HAIRPIN : ((op == OP_HOMODIMER || op == OP_HOMODIMER_DIAG) ? MODE_HOMO : MODE_HETERO);
+	if (diagonal) max_score = dp_fill_diagonal_t<false>(c, &r.cells, 0, nullptr, mode);
+	else max_score = dp_fill_t<false>(c, hairpin, &r.cells, 0, nullptr, mode);
+	if (c.n_max_cell <= NC_MAX_CELLS) { // tm_dimer / approximate_tm_hairpin: every maximal cell, in row-major order
+		for (int k = 0; k < c.n_max_cell; ++k) {
+			if (hairpin) enumerate_hairpin(c, c.max_cell[k], best);
+			else enumerate_dimer(c, c.max_cell[k], best, mode);
 		}
+	} else if (diagonal) {
+		dp_fill_diagonal_t<true>(c, nullptr, max_score, &best, mode);
+	} else {
+		dp_fill_t<true>(c, hairpin, nullptr, max_score, &best, mode);
 	}
 	r.tm = best.tm;
 	r.dH = best.dH;

@@ -8,8 +8,8 @@
 //   out             n x float4 {Tm, dH, dS, dG_dp}
 // The integer DP table (49 x 49 int32 = 9.6 KB, update_dp_param) is staged in shared memory once per CTA; the
 // float parameter tables (58 KB, read sparsely by the evaluation epilogue) stay in global memory behind the
-// read-only cache.  The DP matrix of a problem lives in the owning thread's local memory; all lanes of a warp
-// walk the cells in the same (row, column) order, so those accesses coalesce.
+// read-only cache.  The DP matrix of a problem (one 16-bit word of trace bits and sign flags per cell, 2.2 KB) lives in the owning thread's
+// local memory; all lanes of a warp walk the cells in the same (row, column) order, so those accesses coalesce.
 #pragma once
 #include "nuccruc.cuh"
 
@@ -51,7 +51,6 @@ __global__ void __launch_bounds__(THERMO_BLOCK) thermo_kernel(int op, uint32_t n
 		*(uint4 *)(t + 16) = tb[1];
 		*(uint32_t *)(t + 32) = 0u;
 	}
-	int M[NC_CELLS];
 	unsigned short info[NC_CELLS];
 	Ctx c;
 	c.T = tables;
@@ -61,7 +60,6 @@ __global__ void __launch_bounds__(THERMO_BLOCK) thermo_kernel(int op, uint32_t n
 	c.qlen = len_a[p];
 	c.tlen = two ? len_b[p] : c.qlen;
 	c.log_strand = log_strand[p];
-	c.M = M;
 	c.info = info;
 	const Result r = run_problem(c, op);
 	out[p] = make_float4(r.tm, r.dH, r.dS, r.dp_dg);

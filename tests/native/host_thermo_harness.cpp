@@ -24,7 +24,6 @@ int host_thermo_batch(int op, int n, const char *a, const char *b, float salt, c
 	}
 	DpTable dp;
 	build_dp(g_tables, salt, 310.15f, dp);
-	std::vector<int> M(NC_CELLS);
 	std::vector<unsigned short> info(NC_CELLS);
 	long long total = 0;
 	for (int p = 0; p < n; ++p) {
@@ -51,7 +50,6 @@ int host_thermo_batch(int op, int n, const char *a, const char *b, float salt, c
 		c.qlen = qlen;
 		c.tlen = (op == OP_HETERODIMER || op == OP_HETERODIMER_DIAG) ? tlen : qlen;
 		c.log_strand = logf(strand[p]);
-		c.M = M.data();
 		c.info = info.data();
 		Result r = run_problem(c, op);
 		out[4 * p + 0] = r.tm;
