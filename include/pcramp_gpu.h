@@ -240,15 +240,20 @@ typedef struct pcramp_gpu_stats {
 	uint64_t kernel_launches; /* kernels of this library launched by the call */
 	uint64_t n_seeded;        /* patterns (oligo x strand) that went through the seed filter; the rest were brute-forced */
 	uint64_t n_seed_entries;  /* seed-table entries built for them */
-	float ms_seed;            /* CUDA-event time of seed-table build + scan_seed_kernel (+ dirty groups) */
+	uint64_t n_indexed;       /* of those, patterns taken by the indexed scan (index.cuh) */
+	uint64_t n_index_queries; /* k-mer neighbour queries issued against the text index */
+	uint64_t n_index_entries; /* index entries those queries cover (16 bytes each: the scan's HBM traffic) */
+	float ms_seed;            /* CUDA-event time of the seeded scan: index queries + scan_index_kernel, seed-table build + scan_seed_kernel, dirty groups */
 	float ms_scan;            /* ... of the brute-force scan kernel (patterns that cannot be seeded) */
 	float ms_edge;            /* ... of the partial-window kernel */
 	float ms_db;              /* ... of hit filtering, sorting, materialisation */
 	float ms_score;           /* ... of the pair-scoring kernels */
 } pcramp_gpu_stats;
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
-/* Tuning / testing switches.  "force_brute_scan" = 1 sends every pattern through the brute-force scan kernel
- * (both paths are CUDA and give identical results; the tests compare them). */
+/* Tuning / testing switches.  "force_brute_scan" = 1 sends every pattern through the brute-force scan kernel;
+ * "use_index" = 0 keeps the seeded patterns on scan_seed_kernel instead of the indexed scan (default 1: the text index
+ * is built on first use, ~32 bytes per base of device memory).  All paths are CUDA and give identical results; the
+ * tests compare them. */
 int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value);
 /* Issue-bound ceiling of the scan's own instruction mix on this GPU (alignments/s), measured live. */
 int pcramp_gpu_measure_int_peak(pcramp_gpu_ctx *ctx, double *alignments_per_s);

@@ -35,6 +35,9 @@ class Stats(ctypes.Structure):
         ("kernel_launches", ctypes.c_uint64),
         ("n_seeded", ctypes.c_uint64),
         ("n_seed_entries", ctypes.c_uint64),
+        ("n_indexed", ctypes.c_uint64),
+        ("n_index_queries", ctypes.c_uint64),
+        ("n_index_entries", ctypes.c_uint64),
         ("ms_seed", ctypes.c_float),
         ("ms_scan", ctypes.c_float),
         ("ms_edge", ctypes.c_float),

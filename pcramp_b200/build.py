@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     # identity / coverage arithmetic must round like the reference's scalar x86 code: no FMA contraction,
     # IEEE division and square root (the defaults, stated here so nobody adds --use_fast_math)
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-lpthread",
 ]
 
 

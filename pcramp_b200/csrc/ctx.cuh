@@ -57,6 +57,10 @@ struct SeqSet {
 	DevBuf d_raw, d_raw_off, d_len, d_plen, d_clen, d_planes, d_grp_off, d_eos_pos, d_eos_off, d_weight, d_active, d_tile_seq, d_tile_x0;
 	DevBuf d_dirty_bits, d_dirty_seq, d_dirty_grp; // groups whose alignments read a degenerate base (scan.cuh)
 	uint32_t n_dirty = 0;
+	// text index for the indexed seed scan (index.cuh): built lazily, dropped when the text changes
+	DevBuf idx_entries, idx_off, idx_cum;
+	bool idx_valid = false, idx_failed = false;
+	uint32_t idx_n = 0;
 	// database (seq-grouped order = entry-id order) + canonical permutation
 	uint64_t n_entries = 0, n_keys = 0;
 	bool db_valid = false;
@@ -104,6 +108,8 @@ struct pcramp_gpu_ctx {
 	DevBuf d_seed_cnt, d_seed_start, d_seed_bucket, d_seed_entries, d_tile_counter;
 	int max_smem_optin = 0;
 	int force_brute = 0;
+	int use_index = 1;
+	DevBuf d_idx_queries, d_idx_counters;
 	// scratch
 	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
 	unsigned long long *h_counters = nullptr; // pinned

@@ -1,0 +1,244 @@
+// index.cuh -- K1, indexed seed scan: the text side of the pigeonhole filter turned around.
+//
+// scan_seed_kernel (scan.cuh) walks every text position and asks "which primers have a seed here?" -- ~5 candidate
+// verifications per position, 3 x 10^9 per batch of 4000 patterns on 6 x 10^8 positions, all of them integer work on an
+// SM-resident table.  This path asks the opposite question.  The collection is indexed ONCE (per upload / split): every
+// text position sorted by the 2-bit code of the 12 bases that start there, each entry carrying its position and the code
+// bit-planes of the 48 bases around it (16 before, 32 from the position on).  A pattern with e allowed mismatches is cut
+// into s = e/2 + 1 segments; one of them has at most ONE mismatch (pigeonhole), hence so has its k-base prefix
+// (k = min(segment length, 12)).  For every segment the 1 + 3k k-mers within Hamming distance 1 of the prefix are looked
+// up as prefix ranges of the sorted index, and every entry in range is verified from its own 16 bytes: shift the context
+// planes to the alignment, one LOP3 per letter plane, POPC, compare -- no table in shared memory, no text access, a
+// coalesced 16-byte stream.  k = 9..12 makes the ranges 10^2..10^3 x more selective than the 5/6/7-base exact seeds
+// (4^-10 against 4^-6 per lookup), so a batch touches a few GB of index instead of issuing 10^10 warp instructions, and
+// the kernel is bound by HBM bandwidth, not by integer issue.
+//
+// Exactness: (i) pigeonhole as above; (ii) the text k-mer of a true alignment is itself one of the enumerated
+// neighbours, exactly one, so an alignment is found once per qualifying segment and reported through the leftmost
+// qualifying segment only; (iii) alignments that start in a "dirty" 32-base group (text with a degenerate base nearby)
+// are left to scan_groups_kernel, exactly as in scan_seed_kernel; (iv) patterns whose segment prefixes contain a
+// degenerate base or are shorter than 8 stay on scan_seed_kernel / scan_full_kernel.  Hits leave through the same
+// emit_family / HitSink as the other scan kernels.
+#pragma once
+#include "scan.cuh"
+
+namespace pcr {
+
+constexpr uint32_t IDX_K = 12u;                     // bases per index key
+constexpr uint32_t IDX_KMIN = 8u;                   // shortest usable segment prefix
+constexpr uint32_t IDX_CODES = 1u << (2u * IDX_K);  // 16 M prefix offsets
+constexpr uint32_t IDX_MAX_SEG = 4u;                // e <= 7
+constexpr uint32_t IDX_SLOTS = IDX_MAX_SEG * (1u + 3u * IDX_K);
+constexpr uint32_t IDX_CTX_BEFORE = 16u;
+
+struct TextIndex {
+	const uint4 *entries;   // sorted by 12-mer code: {global position, plane0[31:0], plane1[31:0], plane0[47:32] | plane1[47:32] << 16}
+	const uint32_t *off;    // IDX_CODES + 1: first entry whose code is >= c
+	const uint32_t *cum;    // n_seq + 1: global position of each sequence's first base
+	uint32_t n;             // entries
+};
+
+// segments of a pattern of n bases with e allowed mismatches
+__host__ __device__ __forceinline__ uint32_t idx_segments(uint32_t e) { return e / 2u + 1u; }
+__host__ __device__ __forceinline__ void idx_segment(uint32_t n, uint32_t segs, uint32_t i, uint32_t &o, uint32_t &k)
+{
+	o = (i * n) / segs;
+	const uint32_t len = ((i + 1u) * n) / segs - o;
+	k = len < IDX_K ? len : IDX_K;
+}
+
+// letter code (A=0 C=1 G=2 T=3) of pattern position j, or 4 when the position is degenerate / empty
+__device__ __forceinline__ uint32_t idx_letter(const uint4 &m, uint32_t j)
+{
+	const uint32_t a = (m.x >> j) & 1u, c = (m.y >> j) & 1u, g = (m.z >> j) & 1u, t = (m.w >> j) & 1u;
+	if (a + c + g + t != 1u) return 4u;
+	return c | (g << 1) | (t * 3u);
+}
+
+// can this (seedable) pattern go through the index?  every segment prefix >= IDX_KMIN single-letter bases
+__device__ __forceinline__ bool idx_indexable(const uint4 &m, uint32_t meta2)
+{
+	const uint32_t n = (meta2 >> 10) & 63u, e = (meta2 >> 16) & 63u, cls = (meta2 >> 22) & 7u;
+	if (cls == 0u || n == 0u || n > 32u) return false;
+	const uint32_t segs = idx_segments(e);
+	if (segs > IDX_MAX_SEG) return false;
+	for (uint32_t i = 0; i < segs; ++i) {
+		uint32_t o, k;
+		idx_segment(n, segs, i, o, k);
+		if (k < IDX_KMIN || o > IDX_CTX_BEFORE) return false; // the entry's context reaches 16 bases back
+		for (uint32_t j = 0; j < k; ++j)
+			if (idx_letter(m, o + j) > 3u) return false;
+	}
+	return true;
+}
+
+__device__ __forceinline__ uint32_t idx_spread12(uint32_t v)
+{ // 12 bits -> even bit positions
+	v = (v | (v << 8)) & 0x00FF00FFu;
+	v = (v | (v << 4)) & 0x0F0F0F0Fu;
+	v = (v | (v << 2)) & 0x33333333u;
+	v = (v | (v << 1)) & 0x55555555u;
+	return v;
+}
+
+// code bit-planes b0 = C|T, b1 = G|T of bases [x - 16, x + 32) of one sequence (zero outside the sequence)
+__device__ __forceinline__ void idx_context(const SeqDev &sd, uint32_t seq, uint32_t x, uint64_t &c0, uint64_t &c1)
+{
+	const uint64_t gbase = sd.grp_off[seq];
+	const uint32_t ngrp = (uint32_t)(sd.grp_off[seq + 1] - gbase);
+	const uint32_t g = x >> 5;
+	const uint4 z = make_uint4(0, 0, 0, 0);
+	const uint4 pm = g > 0u ? __ldg(sd.planes + gbase + g - 1u) : z;
+	const uint4 pc = __ldg(sd.planes + gbase + g);
+	const uint4 pp = (g + 1u < ngrp) ? __ldg(sd.planes + gbase + g + 1u) : z;
+	const uint32_t start = (x & 31u) + 32u - IDX_CTX_BEFORE; // bit of base x - 16 in the 96-bit string pm:pc:pp
+	uint32_t lo, hi;
+	take64(pm.y | pm.w, pc.y | pc.w, pp.y | pp.w, start, lo, hi);
+	c0 = ((uint64_t)(hi & 0xFFFFu) << 32) | lo;
+	take64(pm.z | pm.w, pc.z | pc.w, pp.z | pp.w, start, lo, hi);
+	c1 = ((uint64_t)(hi & 0xFFFFu) << 32) | lo;
+}
+
+__device__ __forceinline__ uint32_t idx_seq_of(const uint32_t *__restrict__ cum, uint32_t n_seq, uint32_t gpos)
+{ // last sequence with cum[s] <= gpos (empty sequences share an offset with their successor: take the last)
+	uint32_t lo = 0, hi = n_seq;
+	while (hi - lo > 1u) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (__ldg(cum + mid) <= gpos) lo = mid; else hi = mid;
+	}
+	return lo;
+}
+
+// ---- build ---------------------------------------------------------------------------------------------------
+__global__ void index_key_kernel(SeqDev sd, const uint32_t *__restrict__ cum, uint32_t n_pos, uint32_t *key, uint32_t *val)
+{
+	const uint32_t gpos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (gpos >= n_pos) return;
+	const uint32_t seq = idx_seq_of(cum, sd.n, gpos);
+	uint64_t c0, c1;
+	idx_context(sd, seq, gpos - __ldg(cum + seq), c0, c1);
+	const uint32_t b0 = (uint32_t)(c0 >> IDX_CTX_BEFORE) & 0xFFFu, b1 = (uint32_t)(c1 >> IDX_CTX_BEFORE) & 0xFFFu;
+	// first base most significant: reverse the 12 bits, then interleave (b1 above b0)
+	const uint32_t r0 = __brev(b0) >> 20, r1 = __brev(b1) >> 20;
+	key[gpos] = idx_spread12(r0) | (idx_spread12(r1) << 1);
+	val[gpos] = gpos;
+}
+
+__global__ void index_offsets_kernel(const uint32_t *__restrict__ key_sorted, uint32_t n, uint32_t *off)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n) return;
+	const int64_t prev = (i == 0u) ? -1 : (int64_t)key_sorted[i - 1u];
+	const int64_t cur = (i == n) ? (int64_t)IDX_CODES : (int64_t)key_sorted[i];
+	for (int64_t c = prev + 1; c <= cur; ++c) off[c] = i;
+}
+
+__global__ void index_entry_kernel(SeqDev sd, const uint32_t *__restrict__ cum, const uint32_t *__restrict__ pos_sorted, uint32_t n, uint4 *entries)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t gpos = pos_sorted[i];
+	const uint32_t seq = idx_seq_of(cum, sd.n, gpos);
+	uint64_t c0, c1;
+	idx_context(sd, seq, gpos - __ldg(cum + seq), c0, c1);
+	entries[i] = make_uint4(gpos, (uint32_t)c0, (uint32_t)c1, (uint32_t)(c0 >> 32) | ((uint32_t)(c1 >> 32) << 16));
+}
+
+// ---- per batch: the neighbour queries of every indexable pattern -----------------------------------------------------
+struct IdxQuery {
+	uint32_t lo, hi;   // entry range
+	uint32_t pid;      // pattern (index into the seeded part of the partitioned pattern arrays)
+	uint32_t seg;      // segment offset o[7:0] | prefix length k[15:8] | segment number[23:16]
+};
+
+__global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta2, uint32_t n_pat, const uint32_t *__restrict__ off,
+	IdxQuery *queries, unsigned int *n_queries, unsigned int *n_indexed, unsigned long long *n_entries)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t p = t / IDX_SLOTS, slot = t % IDX_SLOTS;
+	if (p >= n_pat) return;
+	const uint4 m = mask[p];
+	const uint32_t m2 = meta2[p];
+	if (!idx_indexable(m, m2)) return;
+	if (slot == 0u) atomicAdd(n_indexed, 1u);
+	const uint32_t n = (m2 >> 10) & 63u, e = (m2 >> 16) & 63u, segs = idx_segments(e);
+	const uint32_t per = 1u + 3u * IDX_K;
+	const uint32_t si = slot / per, j = slot % per;
+	if (si >= segs) return;
+	uint32_t o, k;
+	idx_segment(n, segs, si, o, k);
+	uint32_t sub_pos = 0xFFFFFFFFu, sub_alt = 0u;
+	if (j > 0u) {
+		sub_pos = (j - 1u) / 3u;
+		sub_alt = (j - 1u) % 3u;
+		if (sub_pos >= k) return;
+	}
+	uint32_t code = 0;
+	for (uint32_t q = 0; q < k; ++q) {
+		uint32_t l = idx_letter(m, o + q);
+		if (q == sub_pos) l = (l + 1u + sub_alt) & 3u;
+		code = (code << 2) | l;
+	}
+	const uint32_t sh = 2u * (IDX_K - k);
+	const uint32_t lo = __ldg(off + (code << sh)), hi = __ldg(off + ((code + 1u) << sh));
+	if (lo >= hi) return;
+	const unsigned int w = atomicAdd(n_queries, 1u);
+	atomicAdd(n_entries, (unsigned long long)(hi - lo));
+	IdxQuery qy;
+	qy.lo = lo;
+	qy.hi = hi;
+	qy.pid = p;
+	qy.seg = o | (k << 8) | (si << 16);
+	queries[w] = qy;
+}
+
+// a verified candidate: place it in its sequence, drop what other kernels own, report once
+__device__ __noinline__ void index_hit(const SeqDev &sd, const TextIndex &ix, uint32_t gpos, uint32_t m, uint32_t pid, uint32_t seg,
+	const uint32_t *__restrict__ g_meta, const uint32_t *__restrict__ g_meta2, const uint32_t *__restrict__ dirty_bits, uint32_t cand_bits,
+	const HitSink &hs)
+{
+	const uint32_t o = seg & 255u, si = seg >> 16;
+	const uint32_t seq = idx_seq_of(ix.cum, sd.n, gpos);
+	const int64_t x = (int64_t)(gpos - __ldg(ix.cum + seq)) - (int64_t)o; // text index of primer base 0
+	if (x < 0 || !sd.active[seq]) return;
+	if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
+		const uint64_t G = sd.grp_off[seq] + (uint64_t)(x >> 5);
+		if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) return;
+	}
+	const uint32_t meta = __ldg(g_meta + pid), meta2 = __ldg(g_meta2 + pid);
+	const uint32_t n = (meta2 >> 10) & 63u, segs = idx_segments((meta2 >> 16) & 63u);
+	for (uint32_t i = 0; i < si; ++i) { // an earlier segment whose prefix is within one mismatch reports this alignment
+		uint32_t oo, kk;
+		idx_segment(n, segs, i, oo, kk);
+		if ((uint32_t)__popc((m >> oo) & ((1u << kk) - 1u)) + 1u >= kk) return;
+	}
+	emit_family(hs, seq, sd.clen[seq], cand_bits, meta, meta2, x, (uint32_t)__popc(m));
+}
+
+constexpr int IDX_THREADS = 256;
+
+// one warp per query; lanes stride over the entry range (coalesced 16-byte loads), the pattern sits in registers
+__global__ void __launch_bounds__(IDX_THREADS)
+scan_index_kernel(SeqDev sd, TextIndex ix, const IdxQuery *__restrict__ queries, const unsigned int *__restrict__ n_queries,
+	const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ meta2, const uint32_t *__restrict__ dirty_bits,
+	uint32_t cand_bits, HitSink hs)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t nq = *n_queries;
+	for (uint32_t q = warp; q < nq; q += n_warps) {
+		const IdxQuery qy = queries[q];
+		const uint4 B = __ldg(mask + qy.pid);
+		const uint32_t thr = __ldg(meta + qy.pid) & 63u;
+		const uint32_t sh = IDX_CTX_BEFORE - (qy.seg & 255u); // context bit of primer base 0 (idx_indexable: offset <= 16)
+		for (uint32_t i = qy.lo + lane; i < qy.hi; i += 32u) {
+			const uint4 en = __ldg(ix.entries + i);
+			const uint64_t c0 = ((uint64_t)(en.w & 0xFFFFu) << 32) | en.y, c1 = ((uint64_t)(en.w >> 16) << 32) | en.z;
+			const uint32_t t0 = (uint32_t)(c0 >> sh), t1 = (uint32_t)(c1 >> sh);
+			const uint32_t m = (B.x & ~t1 & ~t0) | (B.y & ~t1 & t0) | (B.z & t1 & ~t0) | (B.w & t1 & t0);
+			if ((uint32_t)__popc(m) >= thr) index_hit(sd, ix, en.x, m, qy.pid, qy.seg, meta, meta2, dirty_bits, cand_bits, hs);
+		}
+	}
+}
+
+} // namespace pcr

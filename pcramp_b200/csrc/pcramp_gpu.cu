@@ -7,6 +7,7 @@
 
 #include "ctx.cuh"
 #include "score.cuh"
+#include "index.cuh"
 
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
@@ -279,6 +280,52 @@ inline float ev_ms(cudaEvent_t a, cudaEvent_t b)
 	return ms;
 }
 
+// The text index of the indexed seed scan (index.cuh): every position of the collection sorted by its 12-mer code, with the
+// 48-base context planes.  One-time cost per upload / split (a radix sort of the positions); ~32 bytes per base while it is
+// built, 16 afterwards.  Collections of 2^31 positions or more, or a failed allocation, stay on scan_seed_kernel.
+int build_index(pcramp_gpu_ctx *ctx, SeqSet &s)
+{
+	s.idx_valid = false;
+	s.idx_n = 0;
+	const uint64_t N = s.total_positions;
+	if (N == 0 || N >= (1ull << 31)) {
+		s.idx_failed = true;
+		return 0;
+	}
+	cudaStream_t st = ctx->stream;
+	std::vector<uint32_t> cum(s.n + 1, 0);
+	for (uint32_t i = 0; i < s.n; ++i) cum[i + 1] = cum[i] + s.clen[i];
+	DevBuf key[2], val[2], tmp;
+	size_t tmp_bytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+		(int64_t)N, 0, (int)(2 * IDX_K), st);
+	const bool ok = s.idx_cum.ensure((size_t)(s.n + 1) * 4) == cudaSuccess && key[0].ensure(N * 4) == cudaSuccess &&
+	                key[1].ensure(N * 4) == cudaSuccess && val[0].ensure(N * 4) == cudaSuccess && val[1].ensure(N * 4) == cudaSuccess &&
+	                tmp.ensure(tmp_bytes) == cudaSuccess && s.idx_off.ensure((size_t)(IDX_CODES + 1) * 4) == cudaSuccess &&
+	                s.idx_entries.ensure(N * 16) == cudaSuccess;
+	if (!ok) { // not enough device memory: keep the table-based scan
+		cudaGetLastError();
+		s.idx_entries.release();
+		s.idx_off.release();
+		s.idx_failed = true;
+		return 0;
+	}
+	CK(cudaMemcpyAsync(s.idx_cum.p, cum.data(), (size_t)(s.n + 1) * 4, cudaMemcpyHostToDevice, st));
+	const SeqDev sd = s.dev();
+	index_key_kernel<<<grid_for(N, 256), 256, 0, st>>>(sd, s.idx_cum.as<uint32_t>(), (uint32_t)N, key[0].as<uint32_t>(), val[0].as<uint32_t>());
+	CK(cudaGetLastError());
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key[0].as<uint32_t>(), key[1].as<uint32_t>(), val[0].as<uint32_t>(), val[1].as<uint32_t>(),
+		(int64_t)N, 0, (int)(2 * IDX_K), st));
+	index_offsets_kernel<<<grid_for(N + 1, 256), 256, 0, st>>>(key[1].as<uint32_t>(), (uint32_t)N, s.idx_off.as<uint32_t>());
+	CK(cudaGetLastError());
+	index_entry_kernel<<<grid_for(N, 256), 256, 0, st>>>(sd, s.idx_cum.as<uint32_t>(), val[1].as<uint32_t>(), (uint32_t)N, s.idx_entries.as<uint4>());
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
+	s.idx_valid = true;
+	s.idx_n = (uint32_t)N;
+	return 0;
+}
+
 int check_kind(pcramp_gpu_ctx *ctx, int kind)
 {
 	if (!ctx) return 1;
@@ -353,6 +400,7 @@ int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const
 	SeqSet &s = ctx->sets[kind];
 	s.n = n;
 	s.db_valid = false;
+	s.idx_valid = s.idx_failed = false; // the text index (index.cuh) is rebuilt on the next seeded scan
 	s.n_entries = s.n_keys = 0;
 	s.len.assign(len, len + n);
 	s.plen.assign(n, 0);
@@ -451,6 +499,7 @@ int pcramp_gpu_split_sequence(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint3
 	e.insert(it, pos);
 	s.clen[seq] -= 1;
 	s.db_valid = false;
+	s.idx_valid = s.idx_failed = false;
 	set_raw_nibble_kernel<<<1, 1, 0, ctx->stream>>>(s.d_raw.as<uint8_t>(), s.raw_off[seq] + pos / 2, pos & 1u, 0u);
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(s.d_clen.as<uint32_t>() + seq, &s.clen[seq], 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -644,17 +693,51 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		hs.cap = cap;
 		CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
 		CK(cudaEventRecord(ctx->ev[0], st));
-		// (a) seeded patterns, in chunks that fit shared memory
+		// (a0) seeded patterns whose segment prefixes are plain k-mers: the indexed scan (index.cuh)
+		bool use_idx = ctx->use_index && !ctx->force_brute && s.n_tiles && n_seeded;
+		if (use_idx && !s.idx_valid && !s.idx_failed) {
+			if (build_index(ctx, s)) return 1;
+			CK(cudaEventRecord(ctx->ev[0], st)); // the one-time build is not part of the scan's time
+		}
+		use_idx = use_idx && s.idx_valid;
+		if (use_idx) {
+			CK(ctx->d_idx_queries.ensure((size_t)n_seeded * IDX_SLOTS * sizeof(IdxQuery)));
+			CK(ctx->d_idx_counters.ensure(32));
+			CK(cudaMemsetAsync(ctx->d_idx_counters.p, 0, 32, st));
+			unsigned int *d_nq = ctx->d_idx_counters.as<unsigned int>();
+			index_query_kernel<<<grid_for((uint64_t)n_seeded * IDX_SLOTS, 256), 256, 0, st>>>(ctx->d_part_mask.as<uint4>(),
+				ctx->d_part_meta2.as<uint32_t>(), n_seeded, s.idx_off.as<uint32_t>(), ctx->d_idx_queries.as<IdxQuery>(), d_nq, d_nq + 1,
+				(unsigned long long *)(d_nq + 2));
+			CK(cudaGetLastError());
+			TextIndex ix;
+			ix.entries = s.idx_entries.as<uint4>();
+			ix.off = s.idx_off.as<uint32_t>();
+			ix.cum = s.idx_cum.as<uint32_t>();
+			ix.n = s.idx_n;
+			scan_index_kernel<<<(unsigned)ctx->sm_count * 8u, IDX_THREADS, 0, st>>>(sd, ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq,
+				ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(),
+				s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, cand_bits, hs);
+			CK(cudaGetLastError());
+			stat.kernel_launches += 2;
+			unsigned int h_idx[4] = {0, 0, 0, 0};
+			CK(cudaMemcpyAsync(h_idx, d_nq, 16, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			stat.n_index_queries = h_idx[0];
+			stat.n_indexed = h_idx[1];
+			stat.n_index_entries = (uint64_t)h_idx[2] | ((uint64_t)h_idx[3] << 32);
+		}
+		const int skip_idx = use_idx ? 1 : 0;
+		// (a) the remaining seeded patterns, in chunks that fit shared memory
 		if (s.n_tiles && n_seeded) {
 			uint32_t chunk = std::min<uint32_t>(n_seeded, 4096u);
-			uint32_t done = 0;
+			uint32_t done = (use_idx && stat.n_indexed == n_seeded) ? n_seeded : 0u; // nothing left for the table-based scan
 			while (done < n_seeded) {
 				const uint32_t cn = std::min<uint32_t>(chunk, n_seeded - done);
 				const uint4 *c_mask = ctx->d_part_mask.as<uint4>() + done;
 				const uint32_t *c_meta = ctx->d_part_meta.as<uint32_t>() + done, *c_meta2 = ctx->d_part_meta2.as<uint32_t>() + done;
 				// count -> exclusive scan -> fill
 				CK(cudaMemsetAsync(ctx->d_seed_cnt.p, 0, SEED_BUCKETS * 4, st));
-				seed_count_kernel<<<grid_for(cn, 128), 128, 0, st>>>(c_mask, c_meta2, cn, ctx->d_seed_cnt.as<uint32_t>());
+				seed_count_kernel<<<grid_for(cn, 128), 128, 0, st>>>(c_mask, c_meta2, cn, ctx->d_seed_cnt.as<uint32_t>(), skip_idx);
 				CK(cudaGetLastError());
 				CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->d_seed_cnt.as<uint32_t>(), ctx->d_seed_start.as<uint32_t>(), (int)SEED_BUCKETS, st));
 				CK(ctx->cub_tmp.ensure(tmp_bytes));
@@ -670,6 +753,10 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				CK(cudaStreamSynchronize(st));
 				stat.kernel_launches += 4;
 				const uint32_t n_ent = last_start + last_cnt2;
+				if (n_ent == 0u) { // every pattern of this chunk went through the index
+					done += cn;
+					continue;
+				}
 				const uint32_t ecap = (n_ent + 3u) & ~3u, pcap = (cn + 3u) & ~3u;
 				const size_t smem = seed_smem_bytes(ecap, pcap);
 				if (overflow || smem > (size_t)ctx->max_smem_optin || n_ent >= (1u << 20)) {
@@ -682,7 +769,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 					ctx->d_seed_bucket.as<uint32_t>());
 				CK(cudaGetLastError());
 				seed_fill_kernel<<<grid_for(cn, 128), 128, 0, st>>>(c_mask, c_meta, c_meta2, cn, ctx->d_seed_start.as<uint32_t>(),
-					ctx->d_seed_entries.as<uint32_t>(), ecap);
+					ctx->d_seed_entries.as<uint32_t>(), ecap, skip_idx);
 				CK(cudaGetLastError());
 				SeedChunk ch;
 				ch.bucket = ctx->d_seed_bucket.as<uint32_t>();
@@ -1161,6 +1248,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 {
 	if (!ctx || !name) return 1;
 	if (strcmp(name, "force_brute_scan") == 0) { ctx->force_brute = value; return 0; }
+	if (strcmp(name, "use_index") == 0) { ctx->use_index = value; return 0; }
 	return fail(ctx, std::string("pcramp_gpu_set_option: unknown option ") + name);
 }
 

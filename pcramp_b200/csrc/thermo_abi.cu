@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 using namespace pcr;
 using namespace pcr::nc;
@@ -167,26 +169,66 @@ int thermo_download(pcramp_gpu_ctx *ctx, ThermoState *t)
 	return 0;
 }
 
-// ASCII -> base codes into slot p of a staging buffer; mirrors set_query's / tm_pm_duplex's throws
-int encode_seq(pcramp_gpu_ctx *ctx, const char *s, uint32_t stride, bool allow_inosine, uint8_t *dst, uint8_t *len_out)
+// ASCII -> base codes into slot p of a staging buffer; mirrors set_query's / tm_pm_duplex's throws (message returned)
+const char *encode_seq(const char *s, uint32_t stride, bool allow_inosine, uint8_t *dst, uint8_t *len_out)
 {
-	memset(dst, 0, THERMO_SEQ_STRIDE);
+	static const struct Lut {
+		int8_t v[256];
+		Lut()
+		{
+			for (int i = 0; i < 256; ++i) v[i] = (int8_t)base_code((char)i);
+		}
+	} lut;
+	uint64_t *d64 = (uint64_t *)dst;
+	d64[0] = d64[1] = d64[2] = d64[3] = 0;
 	uint32_t len = 0;
 	while (len < stride && s[len]) {
-		if (len >= (uint32_t)NC_MAX_LEN) return fail(ctx, "pcramp_gpu_thermo: sequence longer than 32 bases (Word length)");
-		const int c = base_code(s[len]);
-		if (c < 0 || (c == bI && !allow_inosine))
-			return fail(ctx, allow_inosine ? ":set_query: Illegal base" : "Unknown base in tm_pm_duplex");
+		if (len >= (uint32_t)NC_MAX_LEN) return "pcramp_gpu_thermo: sequence longer than 32 bases (Word length)";
+		const int c = lut.v[(unsigned char)s[len]];
+		if (c < 0 || (c == bI && !allow_inosine)) return allow_inosine ? ":set_query: Illegal base" : "Unknown base in tm_pm_duplex";
 		dst[len] = (uint8_t)c;
 		++len;
 	}
 	*len_out = (uint8_t)len;
-	return 0;
+	return nullptr;
 }
 
 inline float hetero_strand(float c_a, float c_b)
 { // NucCruc::strand(c_a, c_b), nuc_cruc.h:818-838
 	return (c_a > c_b) ? c_a - 0.5f * c_b : c_b - 0.5f * c_a;
+}
+
+// problems [lo, hi): encode, validate, take logf of the strand concentration; returns the first error message or null
+const char *stage_range(ThermoState *t, int op, uint32_t lo, uint32_t hi, const char *seq_a, const char *seq_b, uint32_t stride,
+	const float *strand_a, const float *strand_b)
+{
+	uint8_t *ha = t->h_a.as<uint8_t>(), *hb = t->h_b.as<uint8_t>(), *la = t->h_la.as<uint8_t>(), *lb = t->h_lb.as<uint8_t>();
+	float *ls = t->h_ls.as<float>();
+	float last_strand = -1.0f, last_log = 0.0f;
+	for (uint32_t p = lo; p < hi; ++p) {
+		if (const char *e = encode_seq(seq_a + (size_t)p * stride, stride, op != OP_PM_DUPLEX, ha + (size_t)p * THERMO_SEQ_STRIDE, la + p)) return e;
+		if (op == OP_HAIRPIN && la[p] == 0) return ":NucCruc::align_hairpin: Empty query sequence";
+		float strand = 1.0f;
+		if (two_sequences(op)) {
+			if (const char *e = encode_seq(seq_b + (size_t)p * stride, stride, true, hb + (size_t)p * THERMO_SEQ_STRIDE, lb + p)) return e;
+			if (strand_a[p] < 0.0f) return ":strand: m_c_a < 0.0f";
+			if (strand_b[p] < 0.0f) return ":strand: m_c_b < 0.0f";
+			strand = hetero_strand(strand_a[p], strand_b[p]);
+		} else {
+			lb[p] = 0;
+			if (needs_strand(op)) {
+				if (strand_a[p] < 0.0f) return ":strand: strand_concentration < 0.0f";
+				strand = strand_a[p];
+			}
+		}
+		if (op != OP_PM_DUPLEX && op != OP_HAIRPIN && !(strand > 0.0f)) return ":NucCruc::tm_dimer: Invalid strand_concentration";
+		if (strand != last_strand) { // the float overload the reference's log() resolves to (nuc_cruc.cpp:2129)
+			last_strand = strand;
+			last_log = logf(strand);
+		}
+		ls[p] = last_log;
+	}
+	return nullptr;
 }
 
 int thermo_stage_strings(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
@@ -197,27 +239,22 @@ int thermo_stage_strings(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n
 	if (n && two_sequences(op) && (!seq_b || !strand_b)) return fail(ctx, "pcramp_gpu_thermo: heterodimer ops need seq_b and strand_b");
 	if (n && needs_strand(op) && !strand_a) return fail(ctx, "pcramp_gpu_thermo: null strand concentration");
 	if (thermo_reserve(ctx, t, n)) return 1;
-	uint8_t *ha = t->h_a.as<uint8_t>(), *hb = t->h_b.as<uint8_t>(), *la = t->h_la.as<uint8_t>(), *lb = t->h_lb.as<uint8_t>();
-	float *ls = t->h_ls.as<float>();
-	for (uint32_t p = 0; p < n; ++p) {
-		if (encode_seq(ctx, seq_a + (size_t)p * stride, stride, op != OP_PM_DUPLEX, ha + (size_t)p * THERMO_SEQ_STRIDE, la + p)) return 1;
-		if (op == OP_HAIRPIN && la[p] == 0) return fail(ctx, ":NucCruc::align_hairpin: Empty query sequence");
-		float strand = 1.0f;
-		if (two_sequences(op)) {
-			if (encode_seq(ctx, seq_b + (size_t)p * stride, stride, true, hb + (size_t)p * THERMO_SEQ_STRIDE, lb + p)) return 1;
-			if (strand_a[p] < 0.0f) return fail(ctx, ":strand: m_c_a < 0.0f");
-			if (strand_b[p] < 0.0f) return fail(ctx, ":strand: m_c_b < 0.0f");
-			strand = hetero_strand(strand_a[p], strand_b[p]);
-		} else {
-			lb[p] = 0;
-			if (needs_strand(op)) {
-				if (strand_a[p] < 0.0f) return fail(ctx, ":strand: strand_concentration < 0.0f");
-				strand = strand_a[p];
-			}
+	// host staging is a plain byte loop: split it over a few threads for large batches
+	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+	const uint32_t n_thr = n < 65536u ? 1u : std::min<uint32_t>(8u, hw);
+	std::vector<const char *> err(n_thr, nullptr);
+	if (n_thr == 1) {
+		err[0] = stage_range(t, op, 0, n, seq_a, seq_b, stride, strand_a, strand_b);
+	} else {
+		std::vector<std::thread> pool;
+		for (uint32_t k = 0; k < n_thr; ++k) {
+			const uint32_t lo = (uint32_t)((uint64_t)n * k / n_thr), hi = (uint32_t)((uint64_t)n * (k + 1) / n_thr);
+			pool.emplace_back([&, k, lo, hi]() { err[k] = stage_range(t, op, lo, hi, seq_a, seq_b, stride, strand_a, strand_b); });
 		}
-		if (op != OP_PM_DUPLEX && op != OP_HAIRPIN && !(strand > 0.0f)) return fail(ctx, ":NucCruc::tm_dimer: Invalid strand_concentration");
-		ls[p] = logf(strand); // the float overload the reference's log() resolves to (nuc_cruc.cpp:2129)
+		for (std::thread &th : pool) th.join();
 	}
+	for (const char *e : err)
+		if (e) return fail(ctx, e);
 	return thermo_upload(ctx, t, op, n);
 }
 

@@ -203,6 +203,60 @@ def test_seed_filter_equals_brute_force(gpu, name):
         assert st["n_seeded"] > 0
 
 
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_indexed_scan_equals_table_scan(gpu, name):
+    """the indexed seed scan (text index + 1-mismatch k-mer neighbours) and the table-based seed scan are two CUDA
+    implementations of the same filter: identical databases, and the index really is used where it applies"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    try:
+        gpu.set_option("use_index", 0)
+        g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+        assert gpu.stats()["n_indexed"] == 0
+        table = _db_tuple(gpu)
+    finally:
+        gpu.set_option("use_index", 1)
+    g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+    st = gpu.stats()
+    indexed = _db_tuple(gpu)
+    for a, b in zip(indexed, table):
+        assert np.array_equal(a, b)
+    if st["n_seeded"] > 0 and name not in ("degenerate",):
+        assert st["n_indexed"] > 0 and st["n_index_queries"] > 0
+
+
+def test_indexed_scan_large_vs_table_scan(gpu):
+    """a collection of several tiles per sequence with degenerate text, EOS and degenerate primers: index path == table path
+    (both also equal the oracle in the next test), and most patterns take the index"""
+    rng = np.random.default_rng(79)
+    base = synth.make_targets(711, 40, 12000, n_clades=4, between=0.12, within=0.05)
+    codes = [base.codes(i).copy() for i in range(base.n)]
+    for c in codes[:20]:
+        k = rng.integers(0, len(c), size=10)
+        c[k] |= synth.CODE[rng.integers(0, 4, size=10)]
+    codes[7][5000] = 0
+    coll = synth.Collection(codes)
+    f, r = synth.make_pairs(712, base, 500, degenerate_fraction=0.3)
+    thr = float(np.float32(1.0) * np.float32(0.9))
+    g = GpuChecker(gpu)
+    g.set_sequences(coll)
+    out = []
+    for use in (0, 1):
+        gpu.set_option("use_index", use)
+        try:
+            g.select_words(f, r, thr, optimize_5=True, optimize_3=True)
+            out.append((_db_tuple(gpu), gpu.stats()))
+        finally:
+            gpu.set_option("use_index", 1)
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.array_equal(a, b)
+    assert out[1][1]["n_indexed"] > 0.5 * out[1][1]["n_seeded"]
+    assert out[1][1]["n_hits"] == out[0][1]["n_hits"]
+
+
 def test_seed_filter_with_degenerate_text_vs_oracle(gpu, oracle):
     """IUPAC codes and N runs in the targets (dirty groups), degenerate primers (seed expansion), several tiles"""
     rng = np.random.default_rng(77)
