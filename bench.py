@@ -332,7 +332,8 @@ def run_b200(a):
     host_cov = torch.zeros(P, dtype=torch.float32).pin_memory()
     host_bits = torch.zeros((P, n_words_global), dtype=torch.int32).pin_memory()
     launches = [0]
-    stats_acc = {"ms_seed": 0.0, "ms_scan": 0.0, "ms_edge": 0.0, "ms_db": 0.0, "ms_score": 0.0, "n_entries": 0, "n_hits": 0, "scan_launches": 0}
+    stats_acc = {"ms_seed": 0.0, "ms_scan": 0.0, "ms_edge": 0.0, "ms_db": 0.0, "ms_score": 0.0, "n_entries": 0, "n_hits": 0, "scan_launches": 0,
+                 "n_index_entries": 0, "n_index_queries": 0, "n_indexed": 0, "n_seeded": 0}
     last = {}
 
     def exchange():
@@ -361,8 +362,8 @@ def run_b200(a):
             launches[0] += st["kernel_launches"]
             for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score"):
                 stats_acc[k] += st[k]
-            stats_acc["n_entries"] += st["n_entries"]
-            stats_acc["n_hits"] += st["n_hits"]
+            for k in ("n_entries", "n_hits", "n_index_entries", "n_index_queries", "n_indexed", "n_seeded"):
+                stats_acc[k] += st[k]
             stats_acc["scan_launches"] += 1
 
     def step_resident(b, timed):
@@ -444,23 +445,31 @@ def run_b200(a):
         achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
         align_per_launch = float(last["n_patterns"]) * float(last["n_positions"])
         align_rate = align_per_launch / (scan_ms * 1e-3) if scan_ms > 0 else 0.0
+        indexed = stats_acc["n_indexed"] > 0
         seeded = stats_acc["ms_seed"] >= stats_acc["ms_scan"]
+        kernel = ("scan_index_kernel" if indexed else "scan_seed_kernel") if seeded else "scan_full_kernel"
+        stream_bytes = 16.0 * (stats_acc["n_index_entries"] + stats_acc["n_index_queries"]) / n_scan   # 16-byte entries + 16-byte queries
         roofline = {
-            "kernel": "scan_seed_kernel" if seeded else "scan_full_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": None,
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms, "share_of_step": (stats_acc["ms_seed"] + stats_acc["ms_scan"]) / ms_resident,
-            "note": "required HBM roofline of the scan (algorithmic bytes = nibbles of the active targets + 16 B/candidate + 28 B/entry, "
-                    "SURVEY.md 8d).  The scan is NOT HBM bound: %d patterns are laid on every template position, each base is read once "
-                    "(ncu traffic = algorithmic bytes, profiles/), and the time goes to shared-memory seed lookups and integer counting; "
-                    "see `brute_force_equivalent`" % last["n_patterns"],
+            "note": "algorithmic bytes = SURVEY.md 8d (nibbles of the active targets + 16 B/candidate + 28 B/entry): what ONE pass over the text "
+                    "would move.  The seeded scan does not stream the text: %d patterns are resolved through a text index (index.cuh), "
+                    "whose entries (16 B each) are the kernel's real HBM stream -- see `index_stream`; avg_launch_ms is the CUDA-event time of "
+                    "the whole seeded scan (query generation + scan_index_kernel + table scan of the remaining patterns)" % last["n_patterns"],
+            "index_stream": {
+                "unit": "GB/s", "bytes_per_launch": stream_bytes, "achieved": stream_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0,
+                "frac_of_hbm_peak": (stream_bytes / (scan_ms * 1e-3) / 1e9 / hbm_peak) if scan_ms > 0 else 0.0,
+                "queries_per_launch": stats_acc["n_index_queries"] / n_scan, "entries_per_launch": stats_acc["n_index_entries"] / n_scan,
+                "patterns_indexed": stats_acc["n_indexed"] / n_scan, "patterns_seeded": stats_acc["n_seeded"] / n_scan},
             "brute_force_equivalent": {
                 "unit": "alignments/s", "achieved": align_rate, "issue_peak": int_peak,
                 "ratio": (align_rate / int_peak) if int_peak else None,
                 "alignments_per_launch": align_per_launch,
                 "note": "alignments the reference's select_words loop would count (patterns x positions) per second, against the measured "
                         "issue-bound ceiling of the brute-force instruction mix (4 LOP3 + POPC + ISETP, pcramp_gpu_measure_int_peak).  "
-                        "The brute-force kernel sits at ~1.0 of it; the exact seed filter exceeds 1.0 because it skips alignments."},
+                        "The brute-force kernel sits at ~1.0 of it; the exact filters exceed 1.0 because they skip alignments."},
         }
         cpu_baseline = None
         if world == 1 and not a.no_cpu_baseline:

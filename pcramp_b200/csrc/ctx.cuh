@@ -109,7 +109,7 @@ struct pcramp_gpu_ctx {
 	int max_smem_optin = 0;
 	int force_brute = 0;
 	int use_index = 1;
-	DevBuf d_idx_queries, d_idx_counters;
+	DevBuf d_idx_queries, d_idx_counters, d_idx_cand;
 	// scratch
 	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
 	unsigned long long *h_counters = nullptr; // pinned

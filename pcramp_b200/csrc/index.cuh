@@ -192,52 +192,103 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 	queries[w] = qy;
 }
 
-// a verified candidate: place it in its sequence, drop what other kernels own, report once
-__device__ __noinline__ void index_hit(const SeqDev &sd, const TextIndex &ix, uint32_t gpos, uint32_t m, uint32_t pid, uint32_t seg,
-	const uint32_t *__restrict__ g_meta, const uint32_t *__restrict__ g_meta2, const uint32_t *__restrict__ dirty_bits, uint32_t cand_bits,
-	const HitSink &hs)
-{
-	const uint32_t o = seg & 255u, si = seg >> 16;
-	const uint32_t seq = idx_seq_of(ix.cum, sd.n, gpos);
-	const int64_t x = (int64_t)(gpos - __ldg(ix.cum + seq)) - (int64_t)o; // text index of primer base 0
-	if (x < 0 || !sd.active[seq]) return;
-	if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
-		const uint64_t G = sd.grp_off[seq] + (uint64_t)(x >> 5);
-		if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) return;
-	}
-	const uint32_t meta = __ldg(g_meta + pid), meta2 = __ldg(g_meta2 + pid);
-	const uint32_t n = (meta2 >> 10) & 63u, segs = idx_segments((meta2 >> 16) & 63u);
-	for (uint32_t i = 0; i < si; ++i) { // an earlier segment whose prefix is within one mismatch reports this alignment
-		uint32_t oo, kk;
-		idx_segment(n, segs, i, oo, kk);
-		if ((uint32_t)__popc((m >> oo) & ((1u << kk) - 1u)) + 1u >= kk) return;
-	}
-	emit_family(hs, seq, sd.clen[seq], cand_bits, meta, meta2, x, (uint32_t)__popc(m));
-}
+// A verified candidate.  Resolving it (which sequence, is that one active, is the alignment somebody else's, which family
+// members see it) costs a chain of dependent loads, and ~2 % of the streamed entries are candidates -- done inline it
+// stalls the streaming warps.  So the scan only appends 16 bytes per candidate and index_hits_kernel resolves them
+// afterwards, one thread each.
+struct IdxCand {
+	uint32_t gpos, m, pid, seg;
+};
+
+struct IdxCandSink {
+	IdxCand *buf;
+	unsigned int *count; // total produced (may exceed cap: the host grows the buffer and re-runs)
+	uint32_t cap;
+};
 
 constexpr int IDX_THREADS = 256;
 
-// one warp per query; lanes stride over the entry range (coalesced 16-byte loads), the pattern sits in registers
+__device__ __forceinline__ void index_verify(const uint4 &en, const uint4 &B, uint32_t thr, uint32_t sh, const IdxQuery &qy, const IdxCandSink &cs)
+{
+	const uint64_t c0 = ((uint64_t)(en.w & 0xFFFFu) << 32) | en.y, c1 = ((uint64_t)(en.w >> 16) << 32) | en.z;
+	const uint32_t t0 = (uint32_t)(c0 >> sh), t1 = (uint32_t)(c1 >> sh);
+	const uint32_t m = (B.x & ~t1 & ~t0) | (B.y & ~t1 & t0) | (B.z & t1 & ~t0) | (B.w & t1 & t0);
+	if ((uint32_t)__popc(m) >= thr) {
+		const unsigned int w = atomicAdd(cs.count, 1u);
+		if (w < cs.cap) {
+			IdxCand c;
+			c.gpos = en.x;
+			c.m = m;
+			c.pid = qy.pid;
+			c.seg = qy.seg;
+			cs.buf[w] = c;
+		}
+	}
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{ // read-once stream: do not keep it in L1
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+
+// one warp per query; lanes stride over the entry range (coalesced 16-byte loads, four in flight per lane), the pattern
+// sits in registers
 __global__ void __launch_bounds__(IDX_THREADS)
-scan_index_kernel(SeqDev sd, TextIndex ix, const IdxQuery *__restrict__ queries, const unsigned int *__restrict__ n_queries,
-	const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ meta2, const uint32_t *__restrict__ dirty_bits,
-	uint32_t cand_bits, HitSink hs)
+scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsigned int *__restrict__ n_queries, const uint4 *__restrict__ mask,
+	const uint32_t *__restrict__ meta, IdxCandSink cs)
 {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
 	const uint32_t nq = *n_queries;
+	if (warp >= nq) return;
+	IdxQuery qy = queries[warp];
 	for (uint32_t q = warp; q < nq; q += n_warps) {
-		const IdxQuery qy = queries[q];
-		const uint4 B = __ldg(mask + qy.pid);
-		const uint32_t thr = __ldg(meta + qy.pid) & 63u;
-		const uint32_t sh = IDX_CTX_BEFORE - (qy.seg & 255u); // context bit of primer base 0 (idx_indexable: offset <= 16)
-		for (uint32_t i = qy.lo + lane; i < qy.hi; i += 32u) {
-			const uint4 en = __ldg(ix.entries + i);
-			const uint64_t c0 = ((uint64_t)(en.w & 0xFFFFu) << 32) | en.y, c1 = ((uint64_t)(en.w >> 16) << 32) | en.z;
-			const uint32_t t0 = (uint32_t)(c0 >> sh), t1 = (uint32_t)(c1 >> sh);
-			const uint32_t m = (B.x & ~t1 & ~t0) | (B.y & ~t1 & t0) | (B.z & t1 & ~t0) | (B.w & t1 & t0);
-			if ((uint32_t)__popc(m) >= thr) index_hit(sd, ix, en.x, m, qy.pid, qy.seg, meta, meta2, dirty_bits, cand_bits, hs);
+		const IdxQuery cur = qy;
+		if (q + n_warps < nq) qy = queries[q + n_warps]; // next descriptor in flight while this range streams
+		const uint4 B = __ldg(mask + cur.pid);
+		const uint32_t thr = __ldg(meta + cur.pid) & 63u;
+		const uint32_t sh = IDX_CTX_BEFORE - (cur.seg & 255u); // context bit of primer base 0 (idx_indexable: offset <= 16)
+		uint32_t i = cur.lo + lane;
+		for (; i + 96u < cur.hi; i += 128u) {
+			const uint4 e0 = ldg_stream(ix.entries + i), e1 = ldg_stream(ix.entries + i + 32u), e2 = ldg_stream(ix.entries + i + 64u),
+			            e3 = ldg_stream(ix.entries + i + 96u);
+			index_verify(e0, B, thr, sh, cur, cs);
+			index_verify(e1, B, thr, sh, cur, cs);
+			index_verify(e2, B, thr, sh, cur, cs);
+			index_verify(e3, B, thr, sh, cur, cs);
 		}
+		for (; i < cur.hi; i += 32u) index_verify(ldg_stream(ix.entries + i), B, thr, sh, cur, cs);
+	}
+}
+
+// place each candidate in its sequence, drop what other kernels own, report once
+__global__ void __launch_bounds__(256)
+index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__restrict__ g_meta, const uint32_t *__restrict__ g_meta2,
+	const uint32_t *__restrict__ dirty_bits, uint32_t cand_bits, HitSink hs)
+{
+	const uint32_t total = min(*cs.count, cs.cap);
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+		const IdxCand c = cs.buf[i];
+		const uint32_t o = c.seg & 255u, si = c.seg >> 16;
+		const uint32_t seq = idx_seq_of(ix.cum, sd.n, c.gpos);
+		const int64_t x = (int64_t)(c.gpos - __ldg(ix.cum + seq)) - (int64_t)o; // text index of primer base 0
+		if (x < 0 || !sd.active[seq]) continue;
+		if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
+			const uint64_t G = sd.grp_off[seq] + (uint64_t)(x >> 5);
+			if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) continue;
+		}
+		const uint32_t meta = __ldg(g_meta + c.pid), meta2 = __ldg(g_meta2 + c.pid);
+		const uint32_t n = (meta2 >> 10) & 63u, segs = idx_segments((meta2 >> 16) & 63u);
+		bool earlier = false;
+		for (uint32_t k = 0; k < si; ++k) { // an earlier segment whose prefix is within one mismatch reports this alignment
+			uint32_t oo, kk;
+			idx_segment(n, segs, k, oo, kk);
+			if ((uint32_t)__popc((c.m >> oo) & ((1u << kk) - 1u)) + 1u >= kk) earlier = true;
+		}
+		if (earlier) continue;
+		emit_family(hs, seq, sd.clen[seq], cand_bits, meta, meta2, x, (uint32_t)__popc(c.m));
 	}
 }
 

@@ -714,8 +714,26 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 			ix.off = s.idx_off.as<uint32_t>();
 			ix.cum = s.idx_cum.as<uint32_t>();
 			ix.n = s.idx_n;
-			scan_index_kernel<<<(unsigned)ctx->sm_count * 8u, IDX_THREADS, 0, st>>>(sd, ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq,
-				ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(),
+			IdxCandSink cs;
+			for (int grow = 0;; ++grow) { // candidates awaiting resolution: sized like the hit buffer, grown if they overflow
+				const uint64_t ccap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_cand.cap / sizeof(IdxCand), cap), 0xFFFFFFF0ull);
+				CK(ctx->d_idx_cand.ensure(ccap * sizeof(IdxCand)));
+				cs.buf = ctx->d_idx_cand.as<IdxCand>();
+				cs.count = d_nq + 4;
+				cs.cap = (uint32_t)ccap;
+				CK(cudaMemsetAsync(d_nq + 4, 0, 4, st));
+				scan_index_kernel<<<(unsigned)ctx->sm_count * 8u, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq,
+					ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
+				CK(cudaGetLastError());
+				stat.kernel_launches++;
+				unsigned int n_c = 0;
+				CK(cudaMemcpyAsync(&n_c, d_nq + 4, 4, cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				if (n_c <= cs.cap) break;
+				if (grow >= 2) return fail(ctx, "pcramp_gpu_select_words: index candidate buffer kept overflowing");
+				CK(ctx->d_idx_cand.ensure(((size_t)n_c + n_c / 8 + 1024) * sizeof(IdxCand)));
+			}
+			index_hits_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, st>>>(sd, ix, cs, ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(),
 				s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, cand_bits, hs);
 			CK(cudaGetLastError());
 			stat.kernel_launches += 2;
