@@ -65,6 +65,7 @@ struct SeqSet {
 	uint64_t n_entries = 0, n_keys = 0;
 	bool db_valid = false;
 	DevBuf e_hi, e_lo, e_planes, e_seq, e_loc, e_strand, e_perm, e_keyrank, seq_ent_off;
+	DevBuf e_key, key_planes; // key index per entry (entry-id order), letter planes per unique word
 
 	SeqDev dev() const
 	{
@@ -102,6 +103,9 @@ struct pcramp_gpu_ctx {
 	const uint64_t *pf() const { return d_f.as<uint64_t>() + 2ull * batch_first; }
 	const uint64_t *pr() const { return d_r.as<uint64_t>() + 2ull * batch_first; }
 	DevBuf d_f, d_r, d_oligos, d_oligos_base, d_variants, d_cov, d_bits, d_bits1;
+	DevBuf d_keybits, d_items, d_item_count; // K2 filter: key matrix / work list
+	DevBuf d_fst_planes, d_fst_thr, d_fst_cnt, d_fst_start, d_fst_cursor, d_fst_ids, d_fst_combo, d_fst_brute, d_fst_nbrute, d_seqbits; // fst.cuh
+	int use_fst = 1;
 	// candidates / patterns
 	DevBuf d_cand_cnt, d_cand_off, d_cand_words, d_cand_thr, d_pat_mask, d_pat_meta, d_pat_meta2, d_pat_seeded, d_pat_sbefore;
 	DevBuf d_part_mask, d_part_meta, d_part_meta2; // seeded patterns first, brute-force patterns after

@@ -129,6 +129,17 @@ __global__ void key_heads_kernel(const uint64_t *__restrict__ w_hi, const uint64
 	head[i] = (w_hi[a] != w_hi[b] || w_lo[a] != w_lo[b]) ? 1u : 0u;
 }
 
+// key index of every entry (in entry-id order) and the letter planes of every unique word, for the key-matrix form of K2
+__global__ void key_index_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ head, const uint32_t *__restrict__ keyrank,
+	const uint4 *__restrict__ e_planes, uint64_t n, uint32_t *e_key, uint4 *key_planes)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t e = perm[i], k = keyrank[i] - 1u;
+	e_key[e] = k;
+	if (head[i]) key_planes[k] = e_planes[e];
+}
+
 // first entry of each (sequence, strand) run in the grouped arrays: off[2*s + minus] = lower_bound; off[2*n_seq] = n
 __global__ void seq_offsets_kernel(const uint32_t *__restrict__ e_seq, const uint32_t *__restrict__ e_strand, uint64_t n, uint32_t n_seq,
 	uint32_t *off)

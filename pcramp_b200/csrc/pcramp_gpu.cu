@@ -951,6 +951,12 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	stat.kernel_launches += 5;
 	uint32_t n_keys = 0;
 	CK(cudaMemcpyAsync(&n_keys, s.e_keyrank.as<uint32_t>() + (n_ent - 1), 4, cudaMemcpyDeviceToHost, st));
+	CK(s.e_key.ensure(n_ent * 4));
+	CK(s.key_planes.ensure(n_ent * 16)); // at most one key per entry
+	key_index_kernel<<<ge, 256, 0, st>>>(s.e_perm.as<uint32_t>(), ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), s.e_planes.as<uint4>(), n_ent,
+		s.e_key.as<uint32_t>(), s.key_planes.as<uint4>());
+	CK(cudaGetLastError());
+	stat.kernel_launches++;
 	CK(cudaEventRecord(ctx->ev[4], st));
 	CK(cudaStreamSynchronize(st));
 	stat.ms_db = ev_ms(ctx->ev[3], ctx->ev[4]);
@@ -1025,6 +1031,48 @@ int pcramp_gpu_keys_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *keys)
 
 uint32_t pcramp_gpu_bitset_words(pcramp_gpu_ctx *ctx, int kind) { return (ctx->sets[kind].n + 31u) / 32u; }
 
+// frame-aligned seed table (fst.cuh) over n oligos given as letter planes + thresholds (device arrays)
+static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t *d_thr, uint32_t n, Fst &t, uint32_t &n_brute_out)
+{
+	cudaStream_t st = ctx->stream;
+	CK(ctx->d_fst_cnt.ensure((size_t)(FST_BUCKETS + 1) * 4));
+	CK(ctx->d_fst_start.ensure((size_t)(FST_BUCKETS + 1) * 4));
+	CK(ctx->d_fst_cursor.ensure((size_t)(FST_BUCKETS + 1) * 4));
+	CK(ctx->d_fst_combo.ensure(FST_COMBOS * 4));
+	CK(ctx->d_fst_brute.ensure(std::max<size_t>(1, n) * 4));
+	CK(ctx->d_fst_nbrute.ensure(16));
+	CK(cudaMemsetAsync(ctx->d_fst_cnt.p, 0, (size_t)(FST_BUCKETS + 1) * 4, st));
+	CK(cudaMemsetAsync(ctx->d_fst_combo.p, 0, FST_COMBOS * 4, st));
+	CK(cudaMemsetAsync(ctx->d_fst_nbrute.p, 0, 16, st));
+	fst_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(d_planes, d_thr, n, ctx->d_fst_cnt.as<uint32_t>(), ctx->d_fst_combo.as<uint32_t>(),
+		ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), nullptr);
+	CK(cudaGetLastError());
+	size_t tb = 0;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_fst_cnt.as<uint32_t>(), ctx->d_fst_start.as<uint32_t>(), (int)(FST_BUCKETS + 1), st));
+	CK(ctx->cub_tmp.ensure(tb));
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, ctx->d_fst_cnt.as<uint32_t>(), ctx->d_fst_start.as<uint32_t>(), (int)(FST_BUCKETS + 1), st));
+	uint32_t total = 0, nb = 0;
+	CK(cudaMemcpyAsync(&total, ctx->d_fst_start.as<uint32_t>() + FST_BUCKETS, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&nb, ctx->d_fst_nbrute.p, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(ctx->d_fst_cursor.p, ctx->d_fst_start.p, (size_t)(FST_BUCKETS + 1) * 4, cudaMemcpyDeviceToDevice, st));
+	CK(cudaStreamSynchronize(st));
+	CK(ctx->d_fst_ids.ensure(std::max<size_t>(1, total) * 4));
+	fst_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(d_planes, d_thr, n, ctx->d_fst_cursor.as<uint32_t>(), ctx->d_fst_combo.as<uint32_t>(),
+		ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), ctx->d_fst_ids.as<uint32_t>());
+	CK(cudaGetLastError());
+	ctx->stats.kernel_launches += 4;
+	t.planes = d_planes;
+	t.thr = d_thr;
+	t.start = ctx->d_fst_start.as<uint32_t>();
+	t.ids = ctx->d_fst_ids.as<uint32_t>();
+	t.combo = ctx->d_fst_combo.as<uint32_t>();
+	t.brute = ctx->d_fst_brute.as<uint32_t>();
+	t.n_brute = ctx->d_fst_nbrute.as<uint32_t>();
+	t.n = n;
+	n_brute_out = nb;
+	return 0;
+}
+
 // K2 launch sequence shared by pair scoring and move-variant scoring.  d_f / d_r: the oligos whose identities are
 // computed; d_bf / d_br (variant scoring only, else null): the base assays whose candidate amplicon lists are used.
 static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, const uint64_t *d_r, const uint64_t *d_bf, const uint64_t *d_br,
@@ -1058,20 +1106,93 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 			ctx->stats.kernel_launches++;
 		}
 		if (s.n_entries) {
-			const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
-			if (variant)
-				score_kernel<true><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
-					s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>(), ctx->d_oligos_base.as<OligoDev>(), n_pairs, detect_threshold, amp_min,
-					amp_max, taq, ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
-			else
-				score_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
-					s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>(), nullptr, n_pairs, detect_threshold, amp_min, amp_max, taq,
-					ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
-			CK(cudaGetLastError());
+			// key-matrix filter (score.cuh), in chunks of pairs so that the (key x oligo) bit matrix stays below ~1 GB
+			const OligoDev *d_member = variant ? ctx->d_oligos_base.as<OligoDev>() : ctx->d_oligos.as<OligoDev>();
+			const uint64_t n_keys = std::max<uint64_t>(1, s.n_keys);
+			uint32_t chunk_pairs = (uint32_t)std::min<uint64_t>(n_pairs, std::max<uint64_t>(16, ((1ull << 30) / (n_keys * 4)) * 16));
+			chunk_pairs = std::max<uint32_t>(16u, chunk_pairs & ~15u); // whole 32-oligo words
+			CK(ctx->d_item_count.ensure(16));
+			uint64_t item_cap = std::max<uint64_t>(ctx->d_items.cap / sizeof(ScoreItem), 1ull << 20);
+			// seed-table filter (fst.cuh) unless too many oligos cannot be seeded (low thresholds: backgrounds at 0.72^2)
+			Fst fst;
+			bool use_fst = ctx->use_fst != 0;
+			if (use_fst) {
+				CK(ctx->d_fst_planes.ensure((size_t)n_pairs * 2 * 16));
+				CK(ctx->d_fst_thr.ensure((size_t)n_pairs * 2 * 4));
+				oligo_split_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(d_member, 2u * n_pairs, ctx->d_fst_planes.as<uint4>(),
+					ctx->d_fst_thr.as<uint32_t>());
+				CK(cudaGetLastError());
+				ctx->stats.kernel_launches++;
+			}
+			if (use_fst) { // rows of 2 x n_seq x words bits: keep them below ~1 GB per chunk of pairs
+				const uint64_t rows = 2ull * std::max<uint32_t>(1u, s.n);
+				const uint32_t fit = (uint32_t)std::min<uint64_t>(n_pairs, std::max<uint64_t>(16, ((1ull << 30) / (rows * 4)) * 16));
+				chunk_pairs = std::max<uint32_t>(16u, fit & ~15u);
+			}
+			for (uint32_t p0 = 0; p0 < n_pairs; p0 += chunk_pairs) {
+				const uint32_t pc = std::min<uint32_t>(chunk_pairs, n_pairs - p0), nw = (2u * pc + 31u) / 32u;
+				bool chunk_fst = use_fst;
+				if (chunk_fst) {
+					uint32_t n_brute = 0;
+					if (fst_build(ctx, ctx->d_fst_planes.as<uint4>() + 2ull * p0, ctx->d_fst_thr.as<uint32_t>() + 2ull * p0, 2u * pc, fst, n_brute)) return 1;
+					if ((uint64_t)n_brute * 4u > 2ull * pc) chunk_fst = false; // mostly unseedable: the key matrix is the better brute force
+				}
+				if (chunk_fst) {
+					const size_t row_bytes = (size_t)2 * s.n * nw * 4;
+					CK(ctx->d_seqbits.ensure(std::max<size_t>(4, row_bytes)));
+					CK(cudaMemsetAsync(ctx->d_seqbits.p, 0, row_bytes, st));
+					entry_match_kernel<<<grid_for(s.n_entries, 128), 128, 0, st>>>(fst, s.e_planes.as<uint4>(), s.e_seq.as<uint32_t>(),
+						s.e_strand.as<uint32_t>(), s.n_entries, nw, ctx->d_seqbits.as<uint32_t>());
+					CK(cudaGetLastError());
+					ctx->stats.kernel_launches++;
+				} else {
+					CK(ctx->d_keybits.ensure((size_t)n_keys * nw * 4));
+					key_match_kernel<<<dim3(grid_for(s.n_keys, KEYM_THREADS), nw), KEYM_THREADS, 0, st>>>(s.key_planes.as<uint4>(), (uint32_t)s.n_keys,
+						d_member + 2ull * p0, 2u * pc, nw, ctx->d_keybits.as<uint32_t>());
+					CK(cudaGetLastError());
+					ctx->stats.kernel_launches++;
+				}
+				for (int attempt = 0;; ++attempt) {
+					CK(ctx->d_items.ensure(item_cap * sizeof(ScoreItem)));
+					CK(cudaMemsetAsync(ctx->d_item_count.p, 0, 16, st));
+					if (chunk_fst) {
+						seq_pairs_kernel<<<grid_for((uint64_t)s.n * nw, 256), 256, 0, st>>>(s.dev(), s.seq_ent_off.as<uint32_t>(),
+							ctx->d_seqbits.as<uint32_t>(), nw, pc, ctx->d_items.as<ScoreItem>(), ctx->d_item_count.as<unsigned int>(),
+							(uint32_t)std::min<uint64_t>(item_cap, 0xFFFFFFF0ull));
+					} else {
+						const unsigned fthreads = std::min<uint32_t>(256u, (nw + 31u) & ~31u);
+						seq_filter_kernel<<<(unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 16), fthreads, 0, st>>>(s.dev(),
+							s.seq_ent_off.as<uint32_t>(), s.e_key.as<uint32_t>(), ctx->d_keybits.as<uint32_t>(), nw, pc, ctx->d_items.as<ScoreItem>(),
+							ctx->d_item_count.as<unsigned int>(), (uint32_t)std::min<uint64_t>(item_cap, 0xFFFFFFF0ull));
+					}
+					CK(cudaGetLastError());
+					ctx->stats.kernel_launches++;
+					unsigned int n_items = 0;
+					CK(cudaMemcpyAsync(&n_items, ctx->d_item_count.p, 4, cudaMemcpyDeviceToHost, st));
+					CK(cudaStreamSynchronize(st));
+					if (n_items <= item_cap) break;
+					if (attempt >= 2) return fail(ctx, "pcramp_gpu_score_pairs: work list kept overflowing");
+					item_cap = (uint64_t)n_items + n_items / 8 + 1024;
+				}
+				const unsigned grid = (unsigned)ctx->sm_count * 8u;
+				const uint32_t icap = (uint32_t)std::min<uint64_t>(item_cap, 0xFFFFFFF0ull);
+				if (variant)
+					score_items_kernel<true><<<grid, 256, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+						s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>() + 2ull * p0, ctx->d_oligos_base.as<OligoDev>() + 2ull * p0,
+						ctx->d_items.as<ScoreItem>(), ctx->d_item_count.as<unsigned int>(), icap, detect_threshold, amp_min, amp_max, taq,
+						ctx->d_bits.as<uint32_t>() + (size_t)p0 * n_words, ctx->d_bits1.as<uint32_t>() + (size_t)p0 * n_words, n_words);
+				else
+					score_items_kernel<false><<<grid, 256, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+						s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>() + 2ull * p0, nullptr, ctx->d_items.as<ScoreItem>(),
+						ctx->d_item_count.as<unsigned int>(), icap, detect_threshold, amp_min, amp_max, taq,
+						ctx->d_bits.as<uint32_t>() + (size_t)p0 * n_words, ctx->d_bits1.as<uint32_t>() + (size_t)p0 * n_words, n_words);
+				CK(cudaGetLastError());
+				ctx->stats.kernel_launches++;
+			}
 			coverage_kernel<<<grid_for(n_pairs, 128), 128, 0, st>>>(ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), s.d_weight.as<float>(),
 				n_pairs, n_words, s.n, ctx->d_cov.as<float>());
 			CK(cudaGetLastError());
-			ctx->stats.kernel_launches += 2;
+			ctx->stats.kernel_launches += 1;
 		}
 	}
 	CK(cudaEventRecord(ctx->ev[6], st));
@@ -1267,6 +1388,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (!ctx || !name) return 1;
 	if (strcmp(name, "force_brute_scan") == 0) { ctx->force_brute = value; return 0; }
 	if (strcmp(name, "use_index") == 0) { ctx->use_index = value; return 0; }
+	if (strcmp(name, "use_seed_table") == 0) { ctx->use_fst = value; return 0; }
 	return fail(ctx, std::string("pcramp_gpu_set_option: unknown option ") + name);
 }
 

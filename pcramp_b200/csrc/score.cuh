@@ -11,6 +11,7 @@
 // shared memory, a warp takes a pair, lanes take entries.
 #pragma once
 #include "db.cuh"
+#include "fst.cuh"
 
 namespace pcr {
 
@@ -101,7 +102,7 @@ constexpr int SCORE_SMEM_ENTRIES = 1024; // 24 KB; longer per-sequence lists spi
 __device__ __forceinline__ ScoreEntry load_entry(const ScoreEntry *s_ent, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc,
 	const uint32_t *__restrict__ g_strand, uint32_t e0, uint32_t e)
 {
-	if (e < (uint32_t)SCORE_SMEM_ENTRIES) return s_ent[e];
+	if (s_ent && e < (uint32_t)SCORE_SMEM_ENTRIES) return s_ent[e]; // s_ent == nullptr: no staged copy, read the database in place
 	ScoreEntry en;
 	const uint4 v = g_pl[e0 + e];
 	en.a = v.x; en.c = v.y; en.g = v.z; en.t = v.w;
@@ -237,6 +238,173 @@ score_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restric
 					if (d1) atomicOr(bits_pass1 + (size_t)q * n_words + (seq >> 5), bit);
 				}
 			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K2, key-matrix form (the default): the filter question "does oligo o reach its match_words threshold on some plus
+// (minus) entry of sequence s?" is answered per UNIQUE database word instead of per entry.  Sequences of a collection
+// share most of their words (the database of 2.7 M entries of the bench holds ~10x fewer keys), and match_words itself
+// runs over keys (optimize.cpp:291-301):
+//   key_match_kernel   bit (key, oligo) = (oligo & key) >= unsigned(size * thr^2)         one compare per (key, oligo)
+//   seq_filter_kernel  per sequence, OR the key rows of its plus entries and of its minus entries; a pair can only amplify
+//                      the sequence if F(+) & R(-) or R(+) & F(-) (pcr_assay.cpp:37-59): those (sequence, pair) items
+//                      go to a work list (~1 in 10^3 of all combinations)
+//   score_items_kernel one warp per item: the exact amplicon test of amplicon_pass (geometry, has_split, identities)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int KEYM_THREADS = 128;
+
+// grid: (ceil(n_keys / KEYM_THREADS), n_words); block: one 32-oligo word against KEYM_THREADS keys
+__global__ void __launch_bounds__(KEYM_THREADS)
+key_match_kernel(const uint4 *__restrict__ key_planes, uint32_t n_keys, const OligoDev *__restrict__ member, uint32_t n_oligos, uint32_t n_words,
+	uint32_t *keybits)
+{
+	__shared__ OligoDev s_ol[32];
+	const uint32_t w = blockIdx.y;
+	if (threadIdx.x < 32u) {
+		const uint32_t o = w * 32u + threadIdx.x;
+		OligoDev d;
+		d.a = d.c = d.g = d.t = 0u;
+		d.norm = 0.0f;
+		d.packed = 255u; // a threshold nothing reaches
+		if (o < n_oligos) d = member[o];
+		s_ol[threadIdx.x] = d;
+	}
+	__syncthreads();
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_keys) return;
+	const uint4 kp = __ldg(key_planes + k);
+	ScoreEntry en;
+	en.a = kp.x; en.c = kp.y; en.g = kp.z; en.t = kp.w;
+	en.loc = 0; en.strand = 0u;
+	uint32_t bits = 0u;
+	#pragma unroll 8
+	for (uint32_t b = 0; b < 32u; ++b) {
+		const OligoDev &o = s_ol[b];
+		bits |= (uint32_t)(oligo_count(o, en) >= (int)(o.packed & 255u)) << b;
+	}
+	keybits[(size_t)k * n_words + w] = bits;
+}
+
+// --- seed-table form of the same filter (fst.cuh): one thread per database entry finds the few oligos that reach their
+//     threshold on its word and sets (sequence, strand, oligo) bits; pairs are then read off those rows directly
+__global__ void oligo_split_kernel(const OligoDev *__restrict__ o, uint32_t n, uint4 *planes, uint32_t *thr)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const OligoDev d = o[i];
+	planes[i] = make_uint4(d.a, d.c, d.g, d.t);
+	thr[i] = d.packed & 255u;
+}
+
+__global__ void __launch_bounds__(128)
+entry_match_kernel(Fst t, const uint4 *__restrict__ e_planes, const uint32_t *__restrict__ e_seq, const uint32_t *__restrict__ e_strand, uint64_t n_ent,
+	uint32_t n_words, uint32_t *seqbits)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_ent) return;
+	const uint4 kp = __ldg(e_planes + e);
+	const FstWord w = fst_word(kp.x, kp.y, kp.z, kp.w);
+	uint32_t *row = seqbits + ((size_t)__ldg(e_seq + e) * 2u + (__ldg(e_strand + e) == STRAND_MINUS ? 1u : 0u)) * n_words;
+	fst_match<false>(t, w, [&](uint32_t id, uint32_t) { atomicOr(row + (id >> 5), 1u << (id & 31u)); });
+}
+
+struct ScoreItem;
+__global__ void seq_pairs_kernel(SeqDev sd, const uint32_t *__restrict__ seq_off2, const uint32_t *__restrict__ seqbits, uint32_t n_words, uint32_t n_pairs,
+	ScoreItem *items, unsigned int *n_items, uint32_t cap);
+
+struct ScoreItem {
+	uint32_t seq, pair; // pair[29:0] | try pass 1 [30] | try pass 2 [31]
+};
+
+// grid: sequences (strided); block: n_words threads (rounded up to a warp), thread w ORs word w over the sequence's entries
+__global__ void seq_filter_kernel(SeqDev sd, const uint32_t *__restrict__ seq_off2, const uint32_t *__restrict__ e_key, const uint32_t *__restrict__ keybits,
+	uint32_t n_words, uint32_t n_pairs, ScoreItem *items, unsigned int *n_items, uint32_t cap)
+{
+	for (uint32_t seq = blockIdx.x; seq < sd.n; seq += gridDim.x) {
+		const uint32_t e0 = seq_off2[2 * seq], ep = seq_off2[2 * seq + 1], e1 = seq_off2[2 * seq + 2];
+		if (ep == e0 || ep == e1 || !sd.active[seq]) continue; // needs both strands; inactive: optimize.cpp:280-283
+		for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+			uint32_t plus = 0u, minus = 0u;
+			for (uint32_t e = e0; e < ep; ++e) plus |= __ldg(keybits + (size_t)__ldg(e_key + e) * n_words + w);
+			for (uint32_t e = ep; e < e1; ++e) minus |= __ldg(keybits + (size_t)__ldg(e_key + e) * n_words + w);
+			// oligo 2p = F of pair p, 2p + 1 = R: even bits F, odd bits R
+			const uint32_t pass1 = (plus & 0x55555555u) & ((minus >> 1) & 0x55555555u);   // F(+) & R(-)
+			const uint32_t pass2 = ((plus >> 1) & 0x55555555u) & (minus & 0x55555555u);   // R(+) & F(-)
+			uint32_t any = pass1 | pass2;
+			while (any) {
+				const uint32_t b = (uint32_t)__ffs(any) - 1u;
+				any &= any - 1u;
+				const uint32_t pair = (w * 32u + b) >> 1;
+				if (pair < n_pairs) {
+					const unsigned int i = atomicAdd(n_items, 1u);
+					if (i < cap) {
+						ScoreItem it;
+						it.seq = seq;
+						it.pair = pair | (((pass1 >> b) & 1u) << 30) | (((pass2 >> b) & 1u) << 31);
+						items[i] = it;
+					}
+				}
+			}
+		}
+	}
+}
+
+__global__ void seq_pairs_kernel(SeqDev sd, const uint32_t *__restrict__ seq_off2, const uint32_t *__restrict__ seqbits, uint32_t n_words, uint32_t n_pairs,
+	ScoreItem *items, unsigned int *n_items, uint32_t cap)
+{
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= (uint64_t)sd.n * n_words) return;
+	const uint32_t seq = (uint32_t)(tid / n_words), w = (uint32_t)(tid % n_words);
+	const uint32_t e0 = seq_off2[2 * seq], ep = seq_off2[2 * seq + 1], e1 = seq_off2[2 * seq + 2];
+	if (ep == e0 || ep == e1 || !sd.active[seq]) return; // needs both strands; inactive: optimize.cpp:280-283
+	const uint32_t plus = seqbits[(size_t)(2u * seq) * n_words + w], minus = seqbits[(size_t)(2u * seq + 1u) * n_words + w];
+	const uint32_t pass1 = (plus & 0x55555555u) & ((minus >> 1) & 0x55555555u); // F(+) & R(-): even bits F, odd bits R
+	const uint32_t pass2 = ((plus >> 1) & 0x55555555u) & (minus & 0x55555555u); // R(+) & F(-)
+	uint32_t any = pass1 | pass2;
+	while (any) {
+		const uint32_t b = (uint32_t)__ffs(any) - 1u;
+		any &= any - 1u;
+		const uint32_t pair = (w * 32u + b) >> 1;
+		if (pair < n_pairs) {
+			const unsigned int i = atomicAdd(n_items, 1u);
+			if (i < cap) {
+				ScoreItem it;
+				it.seq = seq;
+				it.pair = pair | (((pass1 >> b) & 1u) << 30) | (((pass2 >> b) & 1u) << 31);
+				items[i] = it;
+			}
+		}
+	}
+}
+
+template <bool VARIANT>
+__global__ void __launch_bounds__(256)
+score_items_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand,
+	const uint32_t *__restrict__ seq_off2, const OligoDev *__restrict__ oligos, const OligoDev *__restrict__ base, const ScoreItem *__restrict__ items,
+	const unsigned int *__restrict__ n_items, uint32_t cap, float detect, int amp_min, int amp_max, int taq, uint32_t *bits_any, uint32_t *bits_pass1,
+	uint32_t n_words_seq)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t total = min(*n_items, cap);
+	for (uint32_t i = warp; i < total; i += n_warps) {
+		const ScoreItem it = items[i];
+		const uint32_t seq = it.seq, q = it.pair & 0x3FFFFFFFu;
+		const uint32_t e0 = seq_off2[2 * seq], Ep = seq_off2[2 * seq + 1] - e0, E = seq_off2[2 * seq + 2] - e0;
+		const OligoDev Fq = oligos[2 * q], Rq = oligos[2 * q + 1];
+		const OligoDev Fb = VARIANT ? base[2 * q] : Fq, Rb = VARIANT ? base[2 * q + 1] : Rq;
+		const bool d1 = ((it.pair >> 30) & 1u)
+		                    ? amplicon_pass<VARIANT>(sd, seq, nullptr, g_pl, g_loc, g_strand, e0, Ep, E, Fq, Rq, Fb, Rb, detect, amp_min, amp_max, taq, lane)
+		                    : false;
+		const bool d2 = (d1 || !((it.pair >> 31) & 1u))
+		                    ? false
+		                    : amplicon_pass<VARIANT>(sd, seq, nullptr, g_pl, g_loc, g_strand, e0, Ep, E, Rq, Fq, Rb, Fb, detect, amp_min, amp_max, taq, lane);
+		if (lane == 0u && (d1 || d2)) {
+			const uint32_t bit = 1u << (seq & 31u);
+			atomicOr(bits_any + (size_t)q * n_words_seq + (seq >> 5), bit);
+			if (d1) atomicOr(bits_pass1 + (size_t)q * n_words_seq + (seq >> 5), bit);
 		}
 	}
 }

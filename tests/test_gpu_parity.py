@@ -228,6 +228,30 @@ def test_indexed_scan_equals_table_scan(gpu, name):
         assert st["n_indexed"] > 0 and st["n_index_queries"] > 0
 
 
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_seed_table_filter_equals_compare_all(gpu, name):
+    """pair scoring and the partial-word scan through the frame-aligned seed table (fst.cuh) == comparing every word with
+    every oligo: databases, coverages and bitsets identical"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    out = []
+    for use in (0, 1):
+        gpu.set_option("use_seed_table", use)
+        try:
+            g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+            db = _db_tuple(gpu)
+            cov, bits = gpu.score_pairs(TARGET, sc.f, sc.r, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+            out.append((db, cov, bits))
+        finally:
+            gpu.set_option("use_seed_table", 1)
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32)) and np.array_equal(out[0][2], out[1][2])
+
+
 def test_indexed_scan_large_vs_table_scan(gpu):
     """a collection of several tiles per sequence with degenerate text, EOS and degenerate primers: index path == table path
     (both also equal the oracle in the next test), and most patterns take the index"""
