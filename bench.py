@@ -368,7 +368,7 @@ def run_b200(a):
 
     def step_resident(b, timed):
         g.set_batch(b * P, P)
-        g.select_words_staged(TARGET, thr)
+        g.select_words_staged(TARGET, thr, want_keys=False)   # keys() is only for hosts that walk the database themselves
         g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
         account(timed)
         if world > 1:
@@ -377,13 +377,13 @@ def run_b200(a):
     def step_e2e(b, timed):
         fb, rb = f_host[b * P:(b + 1) * P], r_host[b * P:(b + 1) * P]
         if world == 1:
-            g.select_words(TARGET, fb, rb, thr)
+            g.select_words(TARGET, fb, rb, thr, want_keys=False)
             cov, bits = g.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR))
             host_cov.numpy()[:] = cov
             host_bits.numpy().view(np.uint32)[:] = bits
         else:
             g.stage_pairs(fb, rb)
-            g.select_words_staged(TARGET, thr)
+            g.select_words_staged(TARGET, thr, want_keys=False)
             g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
             exchange()
             host_cov.copy_(out_cov, non_blocking=True)

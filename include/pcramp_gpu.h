@@ -68,6 +68,10 @@ int pcramp_gpu_pack(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pack_m
 int pcramp_gpu_select_words(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r,
 	uint32_t n_pairs, int optimize_5, int optimize_3, float threshold, uint32_t pack_max_degen,
 	float pack_min_gc, float pack_max_gc, uint32_t min_oligo_length, uint64_t *n_entries, uint64_t *n_keys);
+/* n_keys may be NULL in the two calls above: the canonical order of the database and its keys() numbering are only
+ * needed by a host that still walks the database itself; pair scoring on the GPU does not use them, and they are then
+ * built on demand (by the calls below). */
+int pcramp_gpu_db_size(pcramp_gpu_ctx *ctx, int kind, uint64_t *n_entries, uint64_t *n_keys);
 /* Copy the database out, ordered by (word, index, loc, strand) -- the order read_only_multimap::sort()
  * (read_only_multimap.h:93-101) leaves, with its unspecified ties made canonical.  key_index[i] is the
  * position of entry i's word in keys() order.  Any output pointer may be NULL. */

@@ -105,6 +105,7 @@ SIGNATURES = {
                                        ctypes.c_uint32, ctypes.c_uint64, _u64p, _i32p, _u32p, _u64p]),
     "pcramp_gpu_select_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_float, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_uint32, _u64p, _u64p]),
+    "pcramp_gpu_db_size": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p]),
     "pcramp_gpu_db_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u32p, _i32p, _u32p, _u32p]),
     "pcramp_gpu_keys_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p]),
     "pcramp_gpu_score_pairs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
@@ -254,18 +255,23 @@ class PcrampGpu:
 
     # ---- seed scan ----------------------------------------------------------------------------
     def select_words(self, kind, f, r, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0,
-                     pack_max_gc=1.0, min_oligo_length=18):
+                     pack_max_gc=1.0, min_oligo_length=18, want_keys=True):
+        """-> (entries, keys); want_keys=False skips the canonical order / keys() numbering (keys = None)"""
         f, r = _words(f), _words(r)
         ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
         self._ck(self.lib.pcramp_gpu_select_words(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), len(f), int(optimize_5), int(optimize_3),
                                                   float(threshold), int(pack_max_degen), float(pack_min_gc), float(pack_max_gc),
-                                                  int(min_oligo_length), ctypes.byref(ne), ctypes.byref(nk)))
+                                                  int(min_oligo_length), ctypes.byref(ne), ctypes.byref(nk) if want_keys else None))
         self.n_pairs = len(f)
-        self._db[kind] = (ne.value, nk.value)
+        return ne.value, (nk.value if want_keys else None)
+
+    def db_size(self, kind):
+        ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
+        self._ck(self.lib.pcramp_gpu_db_size(self.h, kind, ctypes.byref(ne), ctypes.byref(nk)))
         return ne.value, nk.value
 
     def db_copy(self, kind):
-        ne, nk = self._db[kind]
+        ne, nk = self.db_size(kind)
         words = np.zeros((ne, 2), np.uint64)
         index = np.zeros(ne, np.uint32)
         loc = np.zeros(ne, np.int32)
@@ -276,7 +282,7 @@ class PcrampGpu:
         return words, index, loc, strand, key
 
     def keys_copy(self, kind):
-        ne, nk = self._db[kind]
+        ne, nk = self.db_size(kind)
         keys = np.zeros((nk, 2), np.uint64)
         self._ck(self.lib.pcramp_gpu_keys_copy(self.h, kind, _ptr(keys, _u64p)))
         return keys
@@ -328,13 +334,12 @@ class PcrampGpu:
         self.n_pairs = int(count)
 
     def select_words_staged(self, kind, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0,
-                            min_oligo_length=18):
+                            min_oligo_length=18, want_keys=True):
         ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
         self._ck(self.lib.pcramp_gpu_select_words_staged(self.h, kind, int(optimize_5), int(optimize_3), float(threshold), int(pack_max_degen),
                                                          float(pack_min_gc), float(pack_max_gc), int(min_oligo_length), ctypes.byref(ne),
-                                                         ctypes.byref(nk)))
-        self._db[kind] = (ne.value, nk.value)
-        return ne.value, nk.value
+                                                         ctypes.byref(nk) if want_keys else None))
+        return ne.value, (nk.value if want_keys else None)
 
     def score_pairs_staged(self, kind, search_threshold, detect_threshold, amplicon_min=80, amplicon_max=200, use_taq_mama=False):
         self._ck(self.lib.pcramp_gpu_score_pairs_staged(self.h, kind, float(search_threshold), float(detect_threshold), int(amplicon_min),

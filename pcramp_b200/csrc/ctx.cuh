@@ -47,6 +47,7 @@ struct DevBuf {
 struct SeqSet {
 	uint32_t n = 0;
 	bool any_degenerate = false;
+	bool unit_weights = true; // every weight == 1.0f: coverage = population count
 	uint64_t total_positions = 0; // sum of clen over all sequences
 	std::vector<uint32_t> len, plen, clen;
 	std::vector<float> weight;
@@ -66,6 +67,9 @@ struct SeqSet {
 	bool db_valid = false;
 	DevBuf e_hi, e_lo, e_planes, e_seq, e_loc, e_strand, e_perm, e_keyrank, seq_ent_off;
 	DevBuf e_key, key_planes; // key index per entry (entry-id order), letter planes per unique word
+	DevBuf e_order;           // (index, loc, strand) sort key per entry: input of the canonical order, built on demand
+	bool keys_valid = false;
+	uint32_t seq_bits = 1;
 
 	SeqDev dev() const
 	{

@@ -407,6 +407,8 @@ int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const
 	s.clen.assign(n, 0);
 	s.weight.assign(n, 1.0f);
 	if (weight) s.weight.assign(weight, weight + n);
+	s.unit_weights = true;
+	for (float w : s.weight) s.unit_weights = s.unit_weights && (w == 1.0f);
 	s.active.assign(n, 1);
 	s.raw_off.assign(byte_off, byte_off + n);
 	s.eos.assign(n, std::vector<uint32_t>());
@@ -570,6 +572,74 @@ int pcramp_gpu_set_batch(pcramp_gpu_ctx *ctx, uint32_t first, uint32_t count)
 	if ((uint64_t)first + count > ctx->n_staged) return fail(ctx, "pcramp_gpu_set_batch: window exceeds the staged pairs");
 	ctx->batch_first = first;
 	ctx->n_pairs = count;
+	return 0;
+}
+
+static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t *d_thr, uint32_t n, Fst &t, uint32_t &n_brute_out);
+
+// The canonical (word, index, loc, strand) order of the database and its keys() numbering (read_only_multimap::sort,
+// pcramp.h:231-256).  Pair scoring on the GPU does not need it, so it is built on demand: by db_copy / keys_copy, by
+// select_words when the caller asks for the key count, and by the key-matrix fallback of pair scoring.
+static int db_finalize_keys(pcramp_gpu_ctx *ctx, SeqSet &s)
+{
+	if (s.keys_valid || !s.db_valid) return 0;
+	cudaStream_t st = ctx->stream;
+	const uint64_t n_ent = s.n_entries;
+	if (n_ent == 0) {
+		s.n_keys = 0;
+		s.keys_valid = true;
+		return 0;
+	}
+	pcramp_gpu_stats &stat = ctx->stats;
+	const uint32_t seq_bits = s.seq_bits;
+	size_t tmp_bytes = 0;
+	CK(s.e_perm.ensure(n_ent * 4));
+	CK(s.e_keyrank.ensure(n_ent * 4));
+	CK(ctx->order_key[0].ensure(n_ent * 8));
+	CK(ctx->order_key[1].ensure(n_ent * 8));
+	CK(ctx->perm[0].ensure(n_ent * 4));
+	CK(ctx->perm[1].ensure(n_ent * 4));
+	CK(ctx->head.ensure(n_ent * 4));
+	const unsigned ge = grid_for(n_ent, 256);
+	iota_kernel<<<ge, 256, 0, st>>>(ctx->perm[0].as<uint32_t>(), n_ent);
+	CK(cudaGetLastError());
+	stat.kernel_launches += 1;
+	// three stable LSD passes: (index, loc, strand), then word.lo, then word.hi
+	auto sort_pass = [&](const uint64_t *key_in, int end_bit, int src, int dst) -> int {
+		size_t tb = 0;
+		CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, key_in, ctx->order_key[1].as<uint64_t>(), ctx->perm[src].as<uint32_t>(),
+			ctx->perm[dst].as<uint32_t>(), (int64_t)n_ent, 0, end_bit, st));
+		CK(ctx->cub_tmp.ensure(tb));
+		CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, key_in, ctx->order_key[1].as<uint64_t>(), ctx->perm[src].as<uint32_t>(),
+			ctx->perm[dst].as<uint32_t>(), (int64_t)n_ent, 0, end_bit, st));
+		stat.kernel_launches += 8;
+		return 0;
+	};
+	if (sort_pass(s.e_order.as<uint64_t>(), (int)(34 + seq_bits), 0, 1)) return 1;
+	gather_u64_kernel<<<ge, 256, 0, st>>>(s.e_lo.as<uint64_t>(), ctx->perm[1].as<uint32_t>(), ctx->order_key[0].as<uint64_t>(), n_ent);
+	CK(cudaGetLastError());
+	if (sort_pass(ctx->order_key[0].as<uint64_t>(), 64, 1, 0)) return 1;
+	gather_u64_kernel<<<ge, 256, 0, st>>>(s.e_hi.as<uint64_t>(), ctx->perm[0].as<uint32_t>(), ctx->order_key[0].as<uint64_t>(), n_ent);
+	CK(cudaGetLastError());
+	if (sort_pass(ctx->order_key[0].as<uint64_t>(), 64, 0, 1)) return 1;
+	CK(cudaMemcpyAsync(s.e_perm.p, ctx->perm[1].p, n_ent * 4, cudaMemcpyDeviceToDevice, st));
+	key_heads_kernel<<<ge, 256, 0, st>>>(s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), s.e_perm.as<uint32_t>(), ctx->head.as<uint32_t>(), n_ent);
+	CK(cudaGetLastError());
+	CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), (int)n_ent, st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	CK(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), (int)n_ent, st));
+	stat.kernel_launches += 5;
+	uint32_t n_keys = 0;
+	CK(cudaMemcpyAsync(&n_keys, s.e_keyrank.as<uint32_t>() + (n_ent - 1), 4, cudaMemcpyDeviceToHost, st));
+	CK(s.e_key.ensure(n_ent * 4));
+	CK(s.key_planes.ensure(n_ent * 16)); // at most one key per entry
+	key_index_kernel<<<ge, 256, 0, st>>>(s.e_perm.as<uint32_t>(), ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), s.e_planes.as<uint4>(), n_ent,
+		s.e_key.as<uint32_t>(), s.key_planes.as<uint4>());
+	CK(cudaGetLastError());
+	stat.kernel_launches++;
+	CK(cudaStreamSynchronize(st));
+	s.n_keys = n_keys;
+	s.keys_valid = true;
 	return 0;
 }
 
@@ -827,10 +897,23 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 			stat.kernel_launches++;
 		}
 		CK(cudaEventRecord(ctx->ev[1], st));
-		scan_edge_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n + 7) / 8, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(sd, pp,
-			ctx->d_cand_words.as<uint4>(), ctx->d_cand_thr.as<uint32_t>(), n_cand, cand_bits, hs);
-		CK(cudaGetLastError());
-		stat.kernel_launches++;
+		{
+			bool edge_fst = ctx->use_fst != 0;
+			Fst fst;
+			if (edge_fst) { // the candidate words as a frame-aligned seed table; mostly unseedable candidates: compare with all
+				uint32_t n_brute = 0;
+				if (fst_build(ctx, ctx->d_cand_words.as<uint4>(), ctx->d_cand_thr.as<uint32_t>(), n_cand, fst, n_brute)) return 1;
+				if ((uint64_t)n_brute * 4u > n_cand) edge_fst = false;
+			}
+			if (edge_fst)
+				scan_edge_fst_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n + 3) / 4, (uint64_t)ctx->sm_count * 16), 128, 0, st>>>(sd, pp, fst,
+					cand_bits, hs);
+			else
+				scan_edge_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n + 7) / 8, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(sd, pp,
+					ctx->d_cand_words.as<uint4>(), ctx->d_cand_thr.as<uint32_t>(), n_cand, cand_bits, hs);
+			CK(cudaGetLastError());
+			stat.kernel_launches++;
+		}
 		CK(cudaEventRecord(ctx->ev[2], st));
 		CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
@@ -907,66 +990,30 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(s.e_seq.ensure(n_ent * 4));
 	CK(s.e_loc.ensure(n_ent * 4));
 	CK(s.e_strand.ensure(n_ent * 4));
-	CK(s.e_perm.ensure(n_ent * 4));
-	CK(s.e_keyrank.ensure(n_ent * 4));
-	CK(ctx->order_key[0].ensure(n_ent * 8));
-	CK(ctx->order_key[1].ensure(n_ent * 8));
-	CK(ctx->perm[0].ensure(n_ent * 4));
-	CK(ctx->perm[1].ensure(n_ent * 4));
-	CK(ctx->head.ensure(n_ent * 4));
+	CK(s.e_order.ensure(n_ent * 8));
 	const unsigned ge = grid_for(n_ent, 256);
 	materialise_kernel<<<ge, 256, 0, st>>>(sd, pp, ctx->ent_id[0].as<uint64_t>(), n_ent, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(),
-		s.e_planes.as<uint4>(), s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), ctx->order_key[0].as<uint64_t>());
+		s.e_planes.as<uint4>(), s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), s.e_order.as<uint64_t>());
 	CK(cudaGetLastError());
 	seq_offsets_kernel<<<grid_for(2ull * s.n + 1, 256), 256, 0, st>>>(s.e_seq.as<uint32_t>(), s.e_strand.as<uint32_t>(), n_ent, s.n,
 		s.seq_ent_off.as<uint32_t>());
 	CK(cudaGetLastError());
-	iota_kernel<<<ge, 256, 0, st>>>(ctx->perm[0].as<uint32_t>(), n_ent);
-	CK(cudaGetLastError());
-	stat.kernel_launches += 3;
-	// three stable LSD passes: (index, loc, strand), then word.lo, then word.hi
-	auto sort_pass = [&](const uint64_t *key_in, int end_bit, int src, int dst) -> int {
-		size_t tb = 0;
-		CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, key_in, ctx->order_key[1].as<uint64_t>(), ctx->perm[src].as<uint32_t>(),
-			ctx->perm[dst].as<uint32_t>(), (int64_t)n_ent, 0, end_bit, st));
-		CK(ctx->cub_tmp.ensure(tb));
-		CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, key_in, ctx->order_key[1].as<uint64_t>(), ctx->perm[src].as<uint32_t>(),
-			ctx->perm[dst].as<uint32_t>(), (int64_t)n_ent, 0, end_bit, st));
-		stat.kernel_launches += 8;
-		return 0;
-	};
-	if (sort_pass(ctx->order_key[0].as<uint64_t>(), (int)(34 + seq_bits), 0, 1)) return 1;
-	gather_u64_kernel<<<ge, 256, 0, st>>>(s.e_lo.as<uint64_t>(), ctx->perm[1].as<uint32_t>(), ctx->order_key[0].as<uint64_t>(), n_ent);
-	CK(cudaGetLastError());
-	if (sort_pass(ctx->order_key[0].as<uint64_t>(), 64, 1, 0)) return 1;
-	gather_u64_kernel<<<ge, 256, 0, st>>>(s.e_hi.as<uint64_t>(), ctx->perm[0].as<uint32_t>(), ctx->order_key[0].as<uint64_t>(), n_ent);
-	CK(cudaGetLastError());
-	if (sort_pass(ctx->order_key[0].as<uint64_t>(), 64, 0, 1)) return 1;
-	CK(cudaMemcpyAsync(s.e_perm.p, ctx->perm[1].p, n_ent * 4, cudaMemcpyDeviceToDevice, st));
-	key_heads_kernel<<<ge, 256, 0, st>>>(s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), s.e_perm.as<uint32_t>(), ctx->head.as<uint32_t>(), n_ent);
-	CK(cudaGetLastError());
-	CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), (int)n_ent, st));
-	CK(ctx->cub_tmp.ensure(tmp_bytes));
-	CK(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), (int)n_ent, st));
-	stat.kernel_launches += 5;
-	uint32_t n_keys = 0;
-	CK(cudaMemcpyAsync(&n_keys, s.e_keyrank.as<uint32_t>() + (n_ent - 1), 4, cudaMemcpyDeviceToHost, st));
-	CK(s.e_key.ensure(n_ent * 4));
-	CK(s.key_planes.ensure(n_ent * 16)); // at most one key per entry
-	key_index_kernel<<<ge, 256, 0, st>>>(s.e_perm.as<uint32_t>(), ctx->head.as<uint32_t>(), s.e_keyrank.as<uint32_t>(), s.e_planes.as<uint4>(), n_ent,
-		s.e_key.as<uint32_t>(), s.key_planes.as<uint4>());
-	CK(cudaGetLastError());
-	stat.kernel_launches++;
+	stat.kernel_launches += 2;
 	CK(cudaEventRecord(ctx->ev[4], st));
 	CK(cudaStreamSynchronize(st));
 	stat.ms_db = ev_ms(ctx->ev[3], ctx->ev[4]);
 	s.n_entries = n_ent;
-	s.n_keys = n_keys;
+	s.n_keys = 0;
+	s.keys_valid = false;
+	s.seq_bits = seq_bits;
 	s.db_valid = true;
 	stat.n_entries = n_ent;
-	stat.n_keys = n_keys;
 	if (n_entries_out) *n_entries_out = n_ent;
-	if (n_keys_out) *n_keys_out = n_keys;
+	if (n_keys_out) { // keys() is only materialised for callers that ask for it (db_copy / keys_copy / this count)
+		if (db_finalize_keys(ctx, s)) return 1;
+		stat.n_keys = s.n_keys;
+		*n_keys_out = s.n_keys;
+	}
 	return 0;
 }
 
@@ -983,6 +1030,7 @@ int pcramp_gpu_db_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *words, uint32_t 
 	CK(cudaSetDevice(ctx->device));
 	SeqSet &s = ctx->sets[kind];
 	if (!s.db_valid) return fail(ctx, "pcramp_gpu_db_copy: no database (call pcramp_gpu_select_words first)");
+	if (db_finalize_keys(ctx, s)) return 1;
 	const uint64_t n = s.n_entries;
 	if (n == 0) return 0;
 	DevBuf o_words, o_index, o_loc, o_strand, o_key, o_keys;
@@ -1005,12 +1053,27 @@ int pcramp_gpu_db_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *words, uint32_t 
 	return 0;
 }
 
+int pcramp_gpu_db_size(pcramp_gpu_ctx *ctx, int kind, uint64_t *n_entries, uint64_t *n_keys)
+{
+	if (check_kind(ctx, kind)) return 1;
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	if (!s.db_valid) return fail(ctx, "pcramp_gpu_db_size: no database (call pcramp_gpu_select_words first)");
+	if (n_entries) *n_entries = s.n_entries;
+	if (n_keys) {
+		if (db_finalize_keys(ctx, s)) return 1;
+		*n_keys = s.n_keys;
+	}
+	return 0;
+}
+
 int pcramp_gpu_keys_copy(pcramp_gpu_ctx *ctx, int kind, uint64_t *keys)
 {
 	if (check_kind(ctx, kind)) return 1;
 	CK(cudaSetDevice(ctx->device));
 	SeqSet &s = ctx->sets[kind];
 	if (!s.db_valid) return fail(ctx, "pcramp_gpu_keys_copy: no database (call pcramp_gpu_select_words first)");
+	if (db_finalize_keys(ctx, s)) return 1;
 	const uint64_t n = s.n_entries;
 	if (n == 0 || !keys) return 0;
 	DevBuf o_words, o_index, o_loc, o_strand, o_key, o_keys;
@@ -1108,9 +1171,12 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 		if (s.n_entries) {
 			// key-matrix filter (score.cuh), in chunks of pairs so that the (key x oligo) bit matrix stays below ~1 GB
 			const OligoDev *d_member = variant ? ctx->d_oligos_base.as<OligoDev>() : ctx->d_oligos.as<OligoDev>();
-			const uint64_t n_keys = std::max<uint64_t>(1, s.n_keys);
-			uint32_t chunk_pairs = (uint32_t)std::min<uint64_t>(n_pairs, std::max<uint64_t>(16, ((1ull << 30) / (n_keys * 4)) * 16));
-			chunk_pairs = std::max<uint32_t>(16u, chunk_pairs & ~15u); // whole 32-oligo words
+			// chunks of pairs (whole 32-oligo words) such that `rows` bit rows of the filter matrix stay below ~1 GB
+			auto chunk_for = [&](uint64_t rows) -> uint32_t {
+				const uint64_t fit = std::max<uint64_t>(16, ((1ull << 30) / (std::max<uint64_t>(1, rows) * 4)) * 16);
+				return fit >= n_pairs ? n_pairs : (uint32_t)(fit & ~15ull);
+			};
+			uint32_t chunk_pairs = chunk_for(s.n_entries); // key matrix: at most one key per entry
 			CK(ctx->d_item_count.ensure(16));
 			uint64_t item_cap = std::max<uint64_t>(ctx->d_items.cap / sizeof(ScoreItem), 1ull << 20);
 			// seed-table filter (fst.cuh) unless too many oligos cannot be seeded (low thresholds: backgrounds at 0.72^2)
@@ -1124,11 +1190,7 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 				CK(cudaGetLastError());
 				ctx->stats.kernel_launches++;
 			}
-			if (use_fst) { // rows of 2 x n_seq x words bits: keep them below ~1 GB per chunk of pairs
-				const uint64_t rows = 2ull * std::max<uint32_t>(1u, s.n);
-				const uint32_t fit = (uint32_t)std::min<uint64_t>(n_pairs, std::max<uint64_t>(16, ((1ull << 30) / (rows * 4)) * 16));
-				chunk_pairs = std::max<uint32_t>(16u, fit & ~15u);
-			}
+			if (use_fst) chunk_pairs = std::min(chunk_pairs, chunk_for(2ull * s.n)); // seed table: two rows per sequence
 			for (uint32_t p0 = 0; p0 < n_pairs; p0 += chunk_pairs) {
 				const uint32_t pc = std::min<uint32_t>(chunk_pairs, n_pairs - p0), nw = (2u * pc + 31u) / 32u;
 				bool chunk_fst = use_fst;
@@ -1146,6 +1208,8 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 					CK(cudaGetLastError());
 					ctx->stats.kernel_launches++;
 				} else {
+					if (db_finalize_keys(ctx, s)) return 1;
+					const uint64_t n_keys = std::max<uint64_t>(1, s.n_keys);
 					CK(ctx->d_keybits.ensure((size_t)n_keys * nw * 4));
 					key_match_kernel<<<dim3(grid_for(s.n_keys, KEYM_THREADS), nw), KEYM_THREADS, 0, st>>>(s.key_planes.as<uint4>(), (uint32_t)s.n_keys,
 						d_member + 2ull * p0, 2u * pc, nw, ctx->d_keybits.as<uint32_t>());
@@ -1189,8 +1253,11 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 				CK(cudaGetLastError());
 				ctx->stats.kernel_launches++;
 			}
-			coverage_kernel<<<grid_for(n_pairs, 128), 128, 0, st>>>(ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), s.d_weight.as<float>(),
-				n_pairs, n_words, s.n, ctx->d_cov.as<float>());
+			if (s.unit_weights)
+				coverage_count_kernel<<<grid_for(32ull * n_pairs, 256), 256, 0, st>>>(ctx->d_bits.as<uint32_t>(), n_pairs, n_words, ctx->d_cov.as<float>());
+			else
+				coverage_kernel<<<grid_for(n_pairs, 128), 128, 0, st>>>(ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), s.d_weight.as<float>(),
+					n_pairs, n_words, s.n, ctx->d_cov.as<float>());
 			CK(cudaGetLastError());
 			ctx->stats.kernel_launches += 1;
 		}

@@ -32,6 +32,7 @@
 // max over ALL words of a sequence, so it is applied afterwards on the hit list (db.cuh).
 #pragma once
 #include "seqdev.cuh"
+#include "fst.cuh"
 
 namespace pcr {
 
@@ -430,6 +431,14 @@ __device__ inline EdgeCounts edge_counts(const SeqDev &sd, uint32_t seq, const P
 	return ec;
 }
 
+// event d of a sequence's partial-word list: FILL events, then EOS events, then TAIL events
+__device__ __forceinline__ void edge_event(const SeqDev &sd, uint32_t seq, const EdgeCounts &ec, uint32_t d, uint32_t &type, uint32_t &pos)
+{
+	if (d < ec.n_fill) { type = ENT_FILL; pos = d; }
+	else if (d < ec.n_fill + ec.n_eos) { type = ENT_EOSEVT; pos = sd.eos_pos[sd.eos_off[seq] + (d - ec.n_fill)]; }
+	else { type = ENT_TAIL; pos = d - ec.n_fill - ec.n_eos + 1u; }
+}
+
 __global__ void __launch_bounds__(256)
 scan_edge_kernel(SeqDev sd, PackParams pp, const uint4 *__restrict__ cand_planes, const uint32_t *__restrict__ cand_thr,
 	uint32_t n_cand, uint32_t cand_bits, HitSink hs)
@@ -445,11 +454,7 @@ scan_edge_kernel(SeqDev sd, PackParams pp, const uint4 *__restrict__ cand_planes
 			const uint32_t d = d0 + lane;
 			uint32_t type = 0, pos = 0;
 			bool ok = d < total;
-			if (ok) {
-				if (d < ec.n_fill) { type = ENT_FILL; pos = d; }
-				else if (d < ec.n_fill + ec.n_eos) { type = ENT_EOSEVT; pos = sd.eos_pos[sd.eos_off[seq] + (d - ec.n_fill)]; }
-				else { type = ENT_TAIL; pos = d - ec.n_fill - ec.n_eos + 1u; }
-			}
+			if (ok) edge_event(sd, seq, ec, d, type, pos);
 			W128 wp, wm;
 			int lp, lm;
 			wp.hi = wp.lo = wm.hi = wm.lo = 0;
@@ -467,6 +472,37 @@ scan_edge_kernel(SeqDev sd, PackParams pp, const uint4 *__restrict__ cand_planes
 					if (nm >= thr) hit_append(hs, hit_key_pack(seq, c, cand_bits, (uint32_t)nm, type, 1u), pos);
 				}
 			}
+		}
+	}
+}
+
+// the same scan through the frame-aligned seed table (fst.cuh): one thread per partial word, which only meets the
+// candidates that share a seed with it
+__global__ void __launch_bounds__(128)
+scan_edge_fst_kernel(SeqDev sd, PackParams pp, Fst t, uint32_t cand_bits, HitSink hs)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t seq = warp; seq < sd.n; seq += n_warps) {
+		if (!sd.active[seq]) continue;
+		const EdgeCounts ec = edge_counts(sd, seq, pp);
+		const uint32_t total = ec.n_fill + ec.n_eos + ec.n_tail;
+		for (uint32_t d0 = 0; d0 < total; d0 += 32u) {
+			const uint32_t d = d0 + lane;
+			uint32_t type = 0, pos = 0;
+			bool ok = d < total;
+			if (ok) edge_event(sd, seq, ec, d, type, pos);
+			W128 wp, wm;
+			int lp, lm;
+			wp.hi = wp.lo = wm.hi = wm.lo = 0;
+			ok = ok && pack_entry(sd, seq, type, pos, pp, wp, wm, lp, lm);
+			if (!ok) continue;
+			const Planes4 pp4 = w_planes(wp), pm4 = w_planes(wm);
+			fst_match<true>(t, fst_word(pp4.a, pp4.c, pp4.g, pp4.t),
+				[&](uint32_t c, uint32_t m) { hit_append(hs, hit_key_pack(seq, c, cand_bits, (uint32_t)__popc(m), type, 0u), pos); });
+			fst_match<true>(t, fst_word(pm4.a, pm4.c, pm4.g, pm4.t),
+				[&](uint32_t c, uint32_t m) { hit_append(hs, hit_key_pack(seq, c, cand_bits, (uint32_t)__popc(m), type, 1u), pos); });
 		}
 	}
 }
