@@ -27,7 +27,8 @@ struct Fst {
 	const uint32_t *thr;       // per oligo: slots that must match
 	const uint32_t *start;     // FST_BUCKETS + 1
 	const uint32_t *ids;       // oligo ids grouped by bucket
-	const uint32_t *combo;     // FST_COMBOS flags: is any seed stored under (position, q)?
+	const uint32_t *combo;     // FST_COMBOS flags: is any seed stored under (position, q)?  then (fst_combo_list_kernel)
+	                           // combo[FST_COMBOS] = number of combinations in use, combo[FST_COMBOS + 1 ...] = their list
 	const uint32_t *brute;     // oligos that are compared with every word
 	const uint32_t *n_brute;
 	uint32_t n;
@@ -113,6 +114,20 @@ __global__ void fst_build_kernel(const uint4 *__restrict__ planes, const uint32_
 	}
 }
 
+// one warp: compact the combo flags into a list behind them
+__global__ void fst_combo_list_kernel(uint32_t *combo)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t n = 0;
+	for (uint32_t base = 0; base < FST_COMBOS; base += 32u) {
+		const bool used = combo[base + lane] != 0u;
+		const uint32_t m = __ballot_sync(0xffffffffu, used);
+		if (used) combo[FST_COMBOS + 1u + n + (uint32_t)__popc(m & ((1u << lane) - 1u))] = base + lane;
+		n += (uint32_t)__popc(m);
+	}
+	if (lane == 0u) combo[FST_COMBOS] = n;
+}
+
 // letter planes of a word -> (single-letter slots, code planes)
 struct FstWord {
 	uint32_t a, c, g, t, single, b0, b1;
@@ -160,8 +175,9 @@ __device__ __forceinline__ void fst_match(const Fst &t, const FstWord &w, F hit)
 	}
 	const uint32_t nb = __ldg(t.n_brute);
 	for (uint32_t k = 0; k < nb; ++k) verify(__ldg(t.brute + k), 0u, false);
-	for (uint32_t cb = 0; cb < FST_COMBOS; ++cb) {
-		if (!__ldg(t.combo + cb)) continue;
+	const uint32_t n_combo = __ldg(t.combo + FST_COMBOS);
+	for (uint32_t ci = 0; ci < n_combo; ++ci) {
+		const uint32_t cb = __ldg(t.combo + FST_COMBOS + 1u + ci);
 		const uint32_t p0 = cb >> 2, q = (cb & 3u) + FST_QMIN, qm = (1u << q) - 1u;
 		if (p0 + q > 32u || ((w.single >> p0) & qm) != qm) continue;
 		const uint32_t b = (cb << 12) | ((w.b0 >> p0) & qm) | (((w.b1 >> p0) & qm) << 6);

@@ -207,23 +207,51 @@ struct IdxCandSink {
 };
 
 constexpr int IDX_THREADS = 256;
+constexpr int IDX_BLOCKS_PER_SM = 4; // one resident wave of persistent warps, eight 16-byte loads in flight per lane
 
-__device__ __forceinline__ void index_verify(const uint4 &en, const uint4 &B, uint32_t thr, uint32_t sh, const IdxQuery &qy, const IdxCandSink &cs)
+__device__ __forceinline__ uint32_t index_mask(const uint4 &en, const uint4 &B, uint32_t sh)
 {
 	const uint64_t c0 = ((uint64_t)(en.w & 0xFFFFu) << 32) | en.y, c1 = ((uint64_t)(en.w >> 16) << 32) | en.z;
 	const uint32_t t0 = (uint32_t)(c0 >> sh), t1 = (uint32_t)(c1 >> sh);
-	const uint32_t m = (B.x & ~t1 & ~t0) | (B.y & ~t1 & t0) | (B.z & t1 & ~t0) | (B.w & t1 & t0);
-	if ((uint32_t)__popc(m) >= thr) {
-		const unsigned int w = atomicAdd(cs.count, 1u);
-		if (w < cs.cap) {
-			IdxCand c;
-			c.gpos = en.x;
-			c.m = m;
-			c.pid = qy.pid;
-			c.seg = qy.seg;
-			cs.buf[w] = c;
-		}
+	return (B.x & ~t1 & ~t0) | (B.y & ~t1 & t0) | (B.z & t1 & ~t0) | (B.w & t1 & t0);
+}
+
+// Append the candidates among N entries per lane with ONE atomic per warp: candidates are sparse (~2 % of the entries), so
+// per-candidate atomics on the single counter arrive one lane at a time and serialise in L2 -- that, not HBM, was the
+// kernel's limit.  All 32 lanes must call this together.
+template <int N>
+__device__ __forceinline__ void index_append(const uint4 (&e)[N], uint32_t valid, const uint4 &B, uint32_t thr, uint32_t sh, const IdxQuery &qy,
+	const IdxCandSink &cs, uint32_t lane)
+{
+	uint32_t hits = 0u; // bit u: entry u of this lane is a candidate
+	#pragma unroll
+	for (int u = 0; u < N; ++u)
+		if (((valid >> u) & 1u) && (uint32_t)__popc(index_mask(e[u], B, sh)) >= thr) hits |= 1u << u;
+	if (!__any_sync(0xffffffffu, hits != 0u)) return;
+	const uint32_t mine = (uint32_t)__popc(hits);
+	uint32_t incl = mine; // inclusive prefix sum over the lanes
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((int)lane >= o) incl += v;
 	}
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	unsigned int base = 0;
+	if (lane == 0u) base = atomicAdd(cs.count, total);
+	base = __shfl_sync(0xffffffffu, base, 0) + (incl - mine);
+	#pragma unroll
+	for (int u = 0; u < N; ++u)
+		if ((hits >> u) & 1u) {
+			if (base < cs.cap) {
+				IdxCand c;
+				c.gpos = e[u].x;
+				c.m = index_mask(e[u], B, sh);
+				c.pid = qy.pid;
+				c.seg = qy.seg;
+				cs.buf[base] = c;
+			}
+			++base;
+		}
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
@@ -235,7 +263,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 
 // one warp per query; lanes stride over the entry range (coalesced 16-byte loads, four in flight per lane), the pattern
 // sits in registers
-__global__ void __launch_bounds__(IDX_THREADS)
+__global__ void __launch_bounds__(IDX_THREADS, IDX_BLOCKS_PER_SM)
 scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsigned int *__restrict__ n_queries, const uint4 *__restrict__ mask,
 	const uint32_t *__restrict__ meta, IdxCandSink cs)
 {
@@ -250,16 +278,28 @@ scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsi
 		const uint4 B = __ldg(mask + cur.pid);
 		const uint32_t thr = __ldg(meta + cur.pid) & 63u;
 		const uint32_t sh = IDX_CTX_BEFORE - (cur.seg & 255u); // context bit of primer base 0 (idx_indexable: offset <= 16)
-		uint32_t i = cur.lo + lane;
-		for (; i + 96u < cur.hi; i += 128u) {
-			const uint4 e0 = ldg_stream(ix.entries + i), e1 = ldg_stream(ix.entries + i + 32u), e2 = ldg_stream(ix.entries + i + 64u),
-			            e3 = ldg_stream(ix.entries + i + 96u);
-			index_verify(e0, B, thr, sh, cur, cs);
-			index_verify(e1, B, thr, sh, cur, cs);
-			index_verify(e2, B, thr, sh, cur, cs);
-			index_verify(e3, B, thr, sh, cur, cs);
+		// whole rows of 32 entries, eight rows (then one row) at a time; lanes past the end of the range carry no entry
+		uint32_t i = cur.lo;
+		for (; i + 256u <= cur.hi; i += 256u) {
+			uint4 e[8];
+			#pragma unroll
+			for (int u = 0; u < 8; ++u) e[u] = ldg_stream(ix.entries + i + 32u * u + lane);
+			index_append<8>(e, 0xFFu, B, thr, sh, cur, cs, lane);
 		}
-		for (; i < cur.hi; i += 32u) index_verify(ldg_stream(ix.entries + i), B, thr, sh, cur, cs);
+		for (; i < cur.hi; i += 128u) {
+			uint4 e[4];
+			uint32_t valid = 0u;
+			#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				const uint32_t j = i + 32u * u + lane;
+				e[u] = make_uint4(0, 0, 0, 0);
+				if (j < cur.hi) {
+					e[u] = ldg_stream(ix.entries + j);
+					valid |= 1u << u;
+				}
+			}
+			index_append<4>(e, valid, B, thr, sh, cur, cs, lane);
+		}
 	}
 }
 

@@ -792,7 +792,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				cs.count = d_nq + 4;
 				cs.cap = (uint32_t)ccap;
 				CK(cudaMemsetAsync(d_nq + 4, 0, 4, st));
-				scan_index_kernel<<<(unsigned)ctx->sm_count * 8u, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq,
+				scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq,
 					ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
 				CK(cudaGetLastError());
 				stat.kernel_launches++;
@@ -1101,7 +1101,7 @@ static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t 
 	CK(ctx->d_fst_cnt.ensure((size_t)(FST_BUCKETS + 1) * 4));
 	CK(ctx->d_fst_start.ensure((size_t)(FST_BUCKETS + 1) * 4));
 	CK(ctx->d_fst_cursor.ensure((size_t)(FST_BUCKETS + 1) * 4));
-	CK(ctx->d_fst_combo.ensure(FST_COMBOS * 4));
+	CK(ctx->d_fst_combo.ensure((2 * FST_COMBOS + 1) * 4));
 	CK(ctx->d_fst_brute.ensure(std::max<size_t>(1, n) * 4));
 	CK(ctx->d_fst_nbrute.ensure(16));
 	CK(cudaMemsetAsync(ctx->d_fst_cnt.p, 0, (size_t)(FST_BUCKETS + 1) * 4, st));
@@ -1109,6 +1109,8 @@ static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t 
 	CK(cudaMemsetAsync(ctx->d_fst_nbrute.p, 0, 16, st));
 	fst_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(d_planes, d_thr, n, ctx->d_fst_cnt.as<uint32_t>(), ctx->d_fst_combo.as<uint32_t>(),
 		ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), nullptr);
+	CK(cudaGetLastError());
+	fst_combo_list_kernel<<<1, 32, 0, st>>>(ctx->d_fst_combo.as<uint32_t>());
 	CK(cudaGetLastError());
 	size_t tb = 0;
 	CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_fst_cnt.as<uint32_t>(), ctx->d_fst_start.as<uint32_t>(), (int)(FST_BUCKETS + 1), st));
@@ -1123,7 +1125,7 @@ static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t 
 	fst_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(d_planes, d_thr, n, ctx->d_fst_cursor.as<uint32_t>(), ctx->d_fst_combo.as<uint32_t>(),
 		ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), ctx->d_fst_ids.as<uint32_t>());
 	CK(cudaGetLastError());
-	ctx->stats.kernel_launches += 4;
+	ctx->stats.kernel_launches += 5;
 	t.planes = d_planes;
 	t.thr = d_thr;
 	t.start = ctx->d_fst_start.as<uint32_t>();
