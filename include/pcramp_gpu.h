@@ -252,6 +252,7 @@ typedef struct pcramp_gpu_stats {
 	float ms_edge;            /* ... of the partial-window kernel */
 	float ms_db;              /* ... of hit filtering, sorting, materialisation */
 	float ms_score;           /* ... of the pair-scoring kernels */
+	float ms_index_kernel;    /* ... of scan_index_kernel alone (last launch) */
 } pcramp_gpu_stats;
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
 /* Tuning / testing switches.  "force_brute_scan" = 1 sends every pattern through the brute-force scan kernel;

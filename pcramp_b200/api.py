@@ -43,6 +43,7 @@ class Stats(ctypes.Structure):
         ("ms_edge", ctypes.c_float),
         ("ms_db", ctypes.c_float),
         ("ms_score", ctypes.c_float),
+        ("ms_index_kernel", ctypes.c_float),
     ]
 
     def as_dict(self):

@@ -98,7 +98,7 @@ struct pcramp_gpu_ctx {
 	int device = 0;
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[8] = {};
+	cudaEvent_t ev[10] = {};
 	std::string err;
 	SeqSet sets[PCRAMP_NUM_KINDS];
 	// staged pairs + results

@@ -792,13 +792,16 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				cs.count = d_nq + 4;
 				cs.cap = (uint32_t)ccap;
 				CK(cudaMemsetAsync(d_nq + 4, 0, 4, st));
+				CK(cudaEventRecord(ctx->ev[8], st));
 				scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq,
 					ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
 				CK(cudaGetLastError());
+				CK(cudaEventRecord(ctx->ev[9], st));
 				stat.kernel_launches++;
 				unsigned int n_c = 0;
 				CK(cudaMemcpyAsync(&n_c, d_nq + 4, 4, cudaMemcpyDeviceToHost, st));
 				CK(cudaStreamSynchronize(st));
+				stat.ms_index_kernel = ev_ms(ctx->ev[8], ctx->ev[9]);
 				if (n_c <= cs.cap) break;
 				if (grow >= 2) return fail(ctx, "pcramp_gpu_select_words: index candidate buffer kept overflowing");
 				CK(ctx->d_idx_cand.ensure(((size_t)n_c + n_c / 8 + 1024) * sizeof(IdxCand)));
