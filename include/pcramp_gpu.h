@@ -103,9 +103,11 @@ int pcramp_gpu_score_variants(pcramp_gpu_ctx *ctx, int kind, const uint64_t *bas
  * OpenMP trial loop of main.cpp:697-729 does one assay at a time.  f / r are updated in place to the best assay found
  * (m_assay.copy_oligos(best)); the three score arrays (any may be NULL) receive the returned Score (pcramp.h:158-215).
  * moves: the reference's list in its order (main.cpp:77-96): values 0..5 = IncreaseDegeneracy, DecreaseDegeneracy,
- * Trim5, Trim3, Grow5, Grow3 (assay.h:21-29).  Needs the TARGET database (and uses the BACKGROUND database when one was
- * built); the multiplex terms (optimize.cpp:76-91: a non-empty multiplex database / assay pool) are not implemented yet
- * and are refused. */
+ * Trim5, Trim3, Grow5, Grow3 (assay.h:21-29).  Needs the TARGET database and uses the BACKGROUND database when one was
+ * built.  With options->use_multiplex the multiplex terms (optimize.cpp:76-96 and the same terms inside every move) are
+ * included: the key list of the multiplex background (pcramp_gpu_multiplex_keys) adds
+ * compute_multiplex_background_coverage to the background coverage, and the assay pool (pcramp_gpu_set_pool) gives
+ * Score::oligo_overlap; either may be empty (the first assay of a run). */
 typedef struct pcramp_gpu_optimize_options {
 	float target_threshold, target_search_multiplier;         /* opt.target_threshold, opt.target_search_multiplier */
 	int target_amplicon_min, target_amplicon_max;             /* opt.target_amplicon_range */
@@ -121,6 +123,25 @@ typedef struct pcramp_gpu_optimize_options {
 int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r, uint32_t n_trials, const int *moves, uint32_t n_moves,
 	const pcramp_gpu_optimize_options *options, float *target_coverage, float *background_coverage, float *oligo_overlap,
 	uint32_t *iterations);
+
+/* ---- the multiplex terms of optimize() ---------------------------------------------------------------------
+ * pcramp_gpu_multiplex_keys: main.cpp:989-1003 -- every sequence of the PCRAMP_MULTIPLEX collection (the amplicons of
+ * the assays chosen so far) is pack()ed whole (no select_words, no G+C filter) and keys() (pcramp.h:231-256) of the
+ * result is kept in HBM; n_keys (may be NULL) receives their number, keys_copy their words (n_keys x 2 uint64) in the
+ * reference's key order.  Rebuild after every upload to PCRAMP_MULTIPLEX. */
+int pcramp_gpu_multiplex_keys(pcramp_gpu_ctx *ctx, uint32_t pack_max_degen, uint32_t min_oligo_length, uint64_t *n_keys);
+int pcramp_gpu_multiplex_keys_copy(pcramp_gpu_ctx *ctx, uint64_t *words);
+/* The assay pool (`assay_pool`, main.cpp:744-752,958-985; m_pool of optimize()): the oligos of the assays already chosen. */
+int pcramp_gpu_set_pool(pcramp_gpu_ctx *ctx, const uint64_t *pool_f, const uint64_t *pool_r, uint32_t n_pool);
+/* collect_multiplex_background_candidates (pcr_assay.cpp:71-104) for the assay (base_f[i], base_r[i]), then
+ * update_multiplex_background_candidates (assay.h:449-453) with the trial oligos (var_f[i], var_r[i]) and
+ * compute_multiplex_background_coverage(threshold) (pcr_assay.cpp:304-336): the number of multiplex keys either oligo
+ * reaches the threshold on.  threshold = opt.background_threshold. */
+int pcramp_gpu_multiplex_coverage(pcramp_gpu_ctx *ctx, const uint64_t *base_f, const uint64_t *base_r, const uint64_t *var_f,
+	const uint64_t *var_r, uint32_t n, float threshold, int use_taq_mama, float *coverage);
+/* PCR::compute_oligo_overlap (pcr_assay.cpp:736-754) of n_pairs assays against the pool: Word::max_overlap
+ * (word.h:38-92) of each oligo with every pool oligo, MULTIPLEX_OLIGO_REUSE_BONUS for an exact reuse. */
+int pcramp_gpu_oligo_overlap(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, float *overlap);
 
 /* ---- resident variants: the same two steps with the pairs already staged in HBM and the results
  *      left in HBM (what a multi-batch driver, the NCCL exchange and bench.py's `value` use). -------- */
@@ -273,6 +294,8 @@ int pcramp_word_start(const uint64_t a[2]);
 int pcramp_word_stop(const uint64_t a[2]);
 void pcramp_word_complement(const uint64_t a[2], uint64_t out[2]);
 void pcramp_word_center(const uint64_t a[2], uint64_t out[2]);
+/* Word::max_overlap (word.h:38-92): the largest number of equal nibbles on one diagonal over max(size, size) */
+float pcramp_word_max_overlap(const uint64_t a[2], const uint64_t b[2]);
 
 #ifdef __cplusplus
 }

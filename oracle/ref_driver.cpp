@@ -178,6 +178,21 @@ long ref_select_words(void *h, uint32_t n_pairs, const uint64_t *f, const uint64
 	return n;
 }
 
+// The multiplex background database of main.cpp:989-1003: every sequence pack()ed WHOLE into the database (running index, no
+// select_words, no G+C filter), keys() recomputed.  Returns |db|.
+long ref_pack_all(void *h, uint32_t pack_max_degen, uint32_t min_len)
+{
+	RefCtx *c = (RefCtx *)h;
+	long n = -1;
+	guarded(c, [&]() {
+		c->db = MULTIMAP<Word, WordMatch>();
+		for (uint32_t i = 0; i < c->seq.size(); ++i) c->seq[i].pack(c->db, i, pack_max_degen, 0.0, 1.0, min_len);
+		c->db_keys = keys(c->db);
+		n = (long)c->db.size();
+	});
+	return n;
+}
+
 long ref_db_size(void *h) { return (long)((RefCtx *)h)->db.size(); }
 long ref_num_keys(void *h) { return (long)((RefCtx *)h)->db_keys.size(); }
 
@@ -628,12 +643,13 @@ struct RefOptimizeOptions { // mirrors pcramp_gpu_optimize_options (include/pcra
 	float salt, primer_strand, primer_tm_min, primer_tm_max, max_hairpin;
 };
 
-// optimize() (optimize.cpp:14-207) of each trial, serially, against the target context h_t and (if not NULL) the background
-// context h_b; empty multiplex database and pool.  f / r are updated in place; score: n x 3 floats.
-int ref_optimize(void *h_t, void *h_b, uint32_t n, uint64_t *f, uint64_t *r, const int *moves, uint32_t n_moves, const RefOptimizeOptions *o,
-	float *score)
+// optimize() (optimize.cpp:14-207) of each trial, serially, against the target context h_t, (if not NULL) the background
+// context h_b, (if not NULL) the multiplex background context h_m (ref_pack_all) and the assay pool.  f / r are updated in
+// place; score: n x 3 floats.
+int ref_optimize_multiplex(void *h_t, void *h_b, void *h_m, uint32_t n, uint64_t *f, uint64_t *r, const int *moves, uint32_t n_moves,
+	const RefOptimizeOptions *o, uint32_t n_pool, const uint64_t *pool_f, const uint64_t *pool_r, float *score)
 {
-	RefCtx *ct = (RefCtx *)h_t, *cb = (RefCtx *)h_b;
+	RefCtx *ct = (RefCtx *)h_t, *cb = (RefCtx *)h_b, *cm = (RefCtx *)h_m;
 	return guarded(ct, [&]() {
 		Options opt;
 		opt.target_threshold = o->target_threshold;
@@ -656,7 +672,13 @@ int ref_optimize(void *h_t, void *h_b, uint32_t n, uint64_t *f, uint64_t *r, con
 		const vector<Word> no_keys;
 		const MULTIMAP<Word, WordMatch> no_db;
 		const deque<Sequence> no_seq;
-		const deque<PCR> pool;
+		deque<PCR> pool;
+		for (uint32_t i = 0; i < n_pool; ++i) {
+			PCR q;
+			q.oligo(FORWARD, make_word(pool_f + 2 * i));
+			q.oligo(REVERSE, make_word(pool_r + 2 * i));
+			pool.push_back(q);
+		}
 		ostringstream sink;
 		for (uint32_t t = 0; t < n; ++t) {
 			PCR p;
@@ -664,7 +686,7 @@ int ref_optimize(void *h_t, void *h_b, uint32_t n, uint64_t *f, uint64_t *r, con
 			p.oligo(REVERSE, make_word(r + 2 * t));
 			paint_stack();
 			const Score s = optimize(p, mv, ct->db_keys, ct->db, ct->seq, cb ? cb->db_keys : no_keys, cb ? cb->db : no_db, cb ? cb->seq : no_seq,
-				no_keys, no_db, no_seq, pool, opt, sink);
+				cm ? cm->db_keys : no_keys, cm ? cm->db : no_db, cm ? cm->seq : no_seq, pool, opt, sink);
 			put_word(f + 2 * t, p.oligo(FORWARD));
 			put_word(r + 2 * t, p.oligo(REVERSE));
 			score[3 * t] = s.target_coverage;
@@ -672,6 +694,55 @@ int ref_optimize(void *h_t, void *h_b, uint32_t n, uint64_t *f, uint64_t *r, con
 			score[3 * t + 2] = s.oligo_overlap;
 		}
 	});
+}
+
+int ref_optimize(void *h_t, void *h_b, uint32_t n, uint64_t *f, uint64_t *r, const int *moves, uint32_t n_moves, const RefOptimizeOptions *o,
+	float *score)
+{
+	return ref_optimize_multiplex(h_t, h_b, NULL, n, f, r, moves, n_moves, o, 0, NULL, NULL, score);
+}
+
+// collect_multiplex_background_candidates (pcr_assay.cpp:71-104) for the base assay, update_multiplex_background_candidates
+// (assay.h:449-453) with the trial oligos, compute_multiplex_background_coverage (pcr_assay.cpp:304-336); h = a ref_pack_all context
+int ref_multiplex_coverage(void *h, uint32_t n, const uint64_t *base_f, const uint64_t *base_r, const uint64_t *var_f, const uint64_t *var_r,
+	float background_threshold, int taq_mama, float *coverage)
+{
+	RefCtx *c = (RefCtx *)h;
+	return guarded(c, [&]() {
+		Options opt;
+		opt.background_threshold = background_threshold;
+		opt.use_taq_mama = (taq_mama != 0);
+		for (uint32_t t = 0; t < n; ++t) {
+			PCR p;
+			p.oligo(FORWARD, make_word(base_f + 2 * t));
+			p.oligo(REVERSE, make_word(base_r + 2 * t));
+			p.collect_multiplex_background_candidates(c->db_keys, c->db, c->seq, opt);
+			p.oligo(FORWARD, make_word(var_f + 2 * t));
+			p.oligo(REVERSE, make_word(var_r + 2 * t));
+			p.update_multiplex_background_candidates(c->db_keys, opt.use_taq_mama);
+			coverage[t] = p.compute_multiplex_background_coverage(opt.background_threshold);
+		}
+	});
+}
+
+// PCR::compute_oligo_overlap (pcr_assay.cpp:736-754)
+int ref_oligo_overlap(uint32_t n, const uint64_t *f, const uint64_t *r, uint32_t n_pool, const uint64_t *pool_f, const uint64_t *pool_r,
+	float *overlap)
+{
+	deque<PCR> pool;
+	for (uint32_t i = 0; i < n_pool; ++i) {
+		PCR q;
+		q.oligo(FORWARD, make_word(pool_f + 2 * i));
+		q.oligo(REVERSE, make_word(pool_r + 2 * i));
+		pool.push_back(q);
+	}
+	for (uint32_t t = 0; t < n; ++t) {
+		PCR p;
+		p.oligo(FORWARD, make_word(f + 2 * t));
+		p.oligo(REVERSE, make_word(r + 2 * t));
+		overlap[t] = p.compute_oligo_overlap(pool);
+	}
+	return 0;
 }
 
 } // extern "C"

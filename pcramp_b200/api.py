@@ -115,6 +115,12 @@ SIGNATURES = {
                                                  ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _u32p]),
     "pcramp_gpu_optimize": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32, _i32p, ctypes.c_uint32, ctypes.c_void_p, _f32p, _f32p,
                                            _f32p, _u32p]),
+    "pcramp_gpu_multiplex_keys": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, _u64p]),
+    "pcramp_gpu_multiplex_keys_copy": (ctypes.c_int, [ctypes.c_void_p, _u64p]),
+    "pcramp_gpu_set_pool": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32]),
+    "pcramp_gpu_multiplex_coverage": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int,
+                                                     _f32p]),
+    "pcramp_gpu_oligo_overlap": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32, _f32p]),
     "pcramp_gpu_stage_pairs": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32]),
     "pcramp_gpu_set_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]),
     "pcramp_gpu_select_words_staged": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_uint32,
@@ -157,6 +163,7 @@ SIGNATURES = {
     "pcramp_word_stop": (ctypes.c_int, [_u64p]),
     "pcramp_word_complement": (None, [_u64p, _u64p]),
     "pcramp_word_center": (None, [_u64p, _u64p]),
+    "pcramp_word_max_overlap": (ctypes.c_float, [_u64p, _u64p]),
 }
 
 
@@ -323,6 +330,32 @@ class PcrampGpu:
         self._ck(self.lib.pcramp_gpu_optimize(self.h, _ptr(f, _u64p), _ptr(r, _u64p), n, _ptr(mv, _i32p), len(mv), ctypes.byref(options),
                                               _ptr(tc, _f32p), _ptr(bc, _f32p), _ptr(ov, _f32p), _ptr(it, _u32p)))
         return f, r, tc, bc, ov, it
+
+    # ---- the multiplex terms of optimize() ---------------------------------------------------
+    def multiplex_keys(self, pack_max_degen=256, min_oligo_length=18):
+        """keys() of the whole-sequence pack of the MULTIPLEX collection (main.cpp:989-1003) -> (n_keys, 2) uint64"""
+        n = np.zeros(1, np.uint64)
+        self._ck(self.lib.pcramp_gpu_multiplex_keys(self.h, int(pack_max_degen), int(min_oligo_length), _ptr(n, _u64p)))
+        words = np.zeros((int(n[0]), 2), np.uint64)
+        self._ck(self.lib.pcramp_gpu_multiplex_keys_copy(self.h, _ptr(words, _u64p)))
+        return words
+
+    def set_pool(self, pool_f, pool_r):
+        pf, pr = _words(pool_f), _words(pool_r)
+        self._ck(self.lib.pcramp_gpu_set_pool(self.h, _ptr(pf, _u64p), _ptr(pr, _u64p), len(pf)))
+
+    def multiplex_coverage(self, base_f, base_r, var_f, var_r, threshold, use_taq_mama=False):
+        bf, br, vf, vr = _words(base_f), _words(base_r), _words(var_f), _words(var_r)
+        cov = np.zeros(len(bf), np.float32)
+        self._ck(self.lib.pcramp_gpu_multiplex_coverage(self.h, _ptr(bf, _u64p), _ptr(br, _u64p), _ptr(vf, _u64p), _ptr(vr, _u64p), len(bf),
+                                                        float(threshold), int(use_taq_mama), _ptr(cov, _f32p)))
+        return cov
+
+    def oligo_overlap(self, f, r):
+        f, r = _words(f), _words(r)
+        ov = np.zeros(len(f), np.float32)
+        self._ck(self.lib.pcramp_gpu_oligo_overlap(self.h, _ptr(f, _u64p), _ptr(r, _u64p), len(f), _ptr(ov, _f32p)))
+        return ov
 
     # ---- resident variants --------------------------------------------------------------------
     def stage_pairs(self, f, r):

@@ -123,6 +123,11 @@ struct pcramp_gpu_ctx {
 	unsigned long long *h_counters = nullptr; // pinned
 	pcramp_gpu_stats stats = {};
 	pcr::nc::ThermoState *thermo = nullptr; // K3 state, created on first use (thermo_abi.cu)
+	// multiplex terms of optimize() (multiplex.cuh): unique words of the multiplex background, the assay pool
+	DevBuf mpx_words, mpx_planes, mpx_items, mpx_item_off, mpx_base, mpx_var, mpx_bidx, mpx_cov, mpx_pool, mpx_ov_words, mpx_ov;
+	uint64_t mpx_n_keys = 0;
+	bool mpx_valid = false;
+	std::vector<uint64_t> pool_words; // F0 R0 F1 R1 ... (2 x uint64 each)
 };
 
 namespace pcr {

@@ -68,6 +68,7 @@ struct Variant {
 	// filled in as the batch proceeds
 	bool valid = false;
 	float cov_t = 0.0f, cov_b = 0.0f;
+	float cov_m = 0.0f, ov = 0.0f; // multiplex background coverage; max over the pool of max_overlap(trial oligo, .)
 	uint32_t first_exp = 0, n_exp = 0; // its expansions in the thermo batch
 };
 
@@ -176,9 +177,16 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 	CK(cudaSetDevice(ctx->device));
 	SeqSet &T = ctx->sets[PCRAMP_TARGET], &B = ctx->sets[PCRAMP_BACKGROUND], &M = ctx->sets[PCRAMP_MULTIPLEX];
 	if (!T.db_valid) return fail(ctx, "pcramp_gpu_optimize: no target database (call pcramp_gpu_select_words first)");
-	if (M.db_valid && M.n_entries)
-		return fail(ctx, "pcramp_gpu_optimize: a multiplex background database is present; the multiplex terms of optimize() "
-		                 "(optimize.cpp:76-91) are not implemented yet");
+	// the multiplex terms (optimize.cpp:76-96): the key list of the multiplex background (pcramp_gpu_multiplex_keys) and the
+	// assay pool (pcramp_gpu_set_pool); both may be empty, which is the first assay of a run
+	const bool mpx = o->use_multiplex != 0;
+	if (mpx && M.n && !ctx->mpx_valid)
+		return fail(ctx, "pcramp_gpu_optimize: multiplex background sequences are loaded but their key list was not built "
+		                 "(call pcramp_gpu_multiplex_keys)");
+	const bool have_mkeys = mpx && ctx->mpx_valid && ctx->mpx_n_keys > 0;
+	const bool have_pool = mpx && !ctx->pool_words.empty();
+	auto bonus = [](float v) { return v == 1.0f ? 10.0f : v; }; // MULTIPLEX_OLIGO_REUSE_BONUS (assay.h:19)
+	std::vector<float> best_f(n_trials, 0.0f), best_r(n_trials, 0.0f); // max over the pool of max_overlap(F / R of the trial's assay, .)
 	for (uint32_t m = 0; m < n_moves; ++m)
 		if (moves[m] < 0 || moves[m] >= MV_COUNT) return fail(ctx, ":optimization_move: Unknown move");
 	const bool have_bg = B.db_valid && B.n_entries > 0; // collect_background_candidates skips an empty key list (assay.h:415)
@@ -197,7 +205,7 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 		previous[t].insert(packed(af[t]) + "|" + packed(ar[t]));
 	}
 	std::vector<uint64_t> pf, pr, vf, vr;
-	std::vector<float> cov_t, cov_b;
+	std::vector<float> cov_t, cov_b, cov_m, ovl;
 	std::vector<uint32_t> idx;
 	std::vector<Variant> vars;
 	std::vector<W128> tmp;
@@ -227,13 +235,33 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 					o->background_amplicon_min, o->background_amplicon_max, o->use_taq_mama, cov_b.data(), nullptr)) return 1;
 			launches += ctx->stats.kernel_launches;
 		}
+		cov_m.assign(na, 0.0f);
+		if (have_mkeys && pcr::mpx::coverage_run(ctx, pf.data(), pr.data(), pf.data(), pr.data(), na, o->background_threshold, o->use_taq_mama,
+				cov_m.data(), launches)) return 1;
+		if (have_pool) { // compute_oligo_overlap (pcr_assay.cpp:736-754)
+			vf.resize(4ull * na);
+			for (uint32_t k = 0; k < na; ++k) {
+				vf[4 * k] = pf[2 * k]; vf[4 * k + 1] = pf[2 * k + 1];
+				vf[4 * k + 2] = pr[2 * k]; vf[4 * k + 3] = pr[2 * k + 1];
+			}
+			ovl.assign(2ull * na, 0.0f);
+			if (pcr::mpx::overlap_run(ctx, vf.data(), 2u * na, ovl.data(), launches)) return 1;
+			for (uint32_t k = 0; k < na; ++k) {
+				best_f[idx[k]] = ovl[2 * k];
+				best_r[idx[k]] = ovl[2 * k + 1];
+			}
+		}
 		vars.clear();
 		for (uint32_t k = 0; k < na; ++k) {
 			const uint32_t t = idx[k];
 			++iters[t];
 			approx[t].target = cov_t[k];
 			approx[t].background = cov_b[k];
-			approx[t].overlap = 0.0f; // compute_oligo_overlap over an empty pool (pcr_assay.cpp:736-754)
+			approx[t].overlap = 0.0f;
+			if (mpx) { // optimize.cpp:76-96
+				approx[t].background += cov_m[k];
+				approx[t].overlap = bonus(best_f[t]) + bonus(best_r[t]);
+			}
 			if (approx[t].lt(best[t])) { // optimize.cpp:97-103
 				live[t] = 0;
 				continue;
@@ -350,9 +378,23 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 				launches += ctx->stats.kernel_launches;
 			}
 		}
+		cov_m.assign(nv, 0.0f);
+		ovl.assign(nv, 0.0f);
+		if (nv && have_mkeys && pcr::mpx::coverage_run(ctx, pf.data(), pr.data(), vf.data(), vr.data(), nv, o->background_threshold,
+				o->use_taq_mama, cov_m.data(), launches)) return 1;
+		if (nv && have_pool) {
+			std::vector<uint64_t> vw(2ull * nv);
+			for (uint32_t k = 0; k < nv; ++k) {
+				vw[2 * k] = vars[vi[k]].w.hi;
+				vw[2 * k + 1] = vars[vi[k]].w.lo;
+			}
+			if (pcr::mpx::overlap_run(ctx, vw.data(), nv, ovl.data(), launches)) return 1;
+		}
 		for (uint32_t k = 0; k < nv; ++k) {
 			vars[vi[k]].cov_t = cov_t[k];
 			vars[vi[k]].cov_b = cov_b[k];
+			vars[vi[k]].cov_m = cov_m[k];
+			vars[vi[k]].ov = ovl[k];
 		}
 		// ---- selection, per trial, in the reference's order ------------------------------------------------------------
 		size_t pos = 0;
@@ -375,8 +417,17 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 						trial.target = v.cov_t;
 						const float bound = trial.target + local.background - local.target;
 						if ((o->use_multiplex && bound < 0.0f) || (!o->use_multiplex && bound <= 0.0f)) continue; // background not evaluated
-						trial.background = v.cov_b; // + compute_multiplex_background_coverage = 0 (no multiplex database)
-						trial.overlap = 0.0f;       // no pool
+						trial.background = v.cov_b;
+						if (mpx) {
+							trial.background += v.cov_m; // compute_multiplex_background_coverage (pcr_assay.cpp:304-336)
+							// the oligo that is not being moved contributes its own best overlap with the pool
+							const float other = bonus(og == 0 ? best_r[t] : best_f[t]);
+							// increase_degeneracy never resets trial_score.oligo_overlap (optimize_pcr.cpp:135-144; the other moves
+							// do, :315,765,931, or start from fresh best_f / best_r, :466-491): the maximum carries over from the
+							// previous trial oligo's TOTAL
+							const float own = moves[m] == MV_INC_DEGEN ? std::max(trial.overlap, v.ov) : v.ov;
+							trial.overlap = bonus(own) + other;
+						}
 						if (trial.gt(ret)) {
 							ret = trial;
 							ret_w = v.w;

@@ -400,6 +400,7 @@ int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const
 	SeqSet &s = ctx->sets[kind];
 	s.n = n;
 	s.db_valid = false;
+	if (kind == PCRAMP_MULTIPLEX) ctx->mpx_valid = false;
 	s.idx_valid = s.idx_failed = false; // the text index (index.cuh) is rebuilt on the next seeded scan
 	s.n_entries = s.n_keys = 0;
 	s.len.assign(len, len + n);
@@ -501,6 +502,7 @@ int pcramp_gpu_split_sequence(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint3
 	e.insert(it, pos);
 	s.clen[seq] -= 1;
 	s.db_valid = false;
+	if (kind == PCRAMP_MULTIPLEX) ctx->mpx_valid = false;
 	s.idx_valid = s.idx_failed = false;
 	set_raw_nibble_kernel<<<1, 1, 0, ctx->stream>>>(s.d_raw.as<uint8_t>(), s.raw_off[seq] + pos / 2, pos & 1u, 0u);
 	CK(cudaGetLastError());
@@ -1557,8 +1559,16 @@ void pcramp_word_center(const uint64_t a[2], uint64_t out[2])
 	out[0] = r.hi;
 	out[1] = r.lo;
 }
+float pcramp_word_max_overlap(const uint64_t a[2], const uint64_t b[2])
+{
+	W128 x, y;
+	x.hi = a[0]; x.lo = a[1];
+	y.hi = b[0]; y.lo = b[1];
+	return w_max_overlap(x, y);
+}
 
 } // extern "C"
 
 #include "sw_abi.cuh" // K4: Smith-Waterman batches, find_background_match, find_multiplex_background_match
+#include "multiplex.cuh" // the multiplex terms of optimize(): multiplex background keys / coverage, pool overlap
 #include "optimize_abi.cuh" // optimize() and its moves for a batch of trials

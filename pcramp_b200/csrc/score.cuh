@@ -47,6 +47,19 @@ __device__ __forceinline__ int taq_index(uint32_t b)
 }
 
 // per-oligo constants: match_words threshold unsigned(size * thr^2) (optimize.cpp:293), identity norm
+__device__ __forceinline__ OligoDev make_oligo(const W128 &w, float thr2)
+{
+	const int size = w_size(w), start = w_start(w), stop = w_stop(w);
+	OligoDev o;
+	const Planes4 pl = w_planes(w);
+	o.a = pl.a; o.c = pl.c; o.g = pl.g; o.t = pl.t;
+	o.norm = size > 0 ? (float)(1.0 / (double)size) : 0.0f;
+	const uint32_t thr = (uint32_t)__fmul_rn((float)size, thr2);
+	const uint32_t pen = stop >= 1 ? w_get(w, stop - 1) : 0u, last = stop >= 0 ? w_get(w, stop) : 0u;
+	o.packed = (thr & 255u) | ((uint32_t)(start & 255) << 8) | ((uint32_t)(stop & 255) << 16) | (pen << 24) | (last << 28);
+	return o;
+}
+
 __global__ void prep_oligos_kernel(const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs, float thr2,
 	OligoDev *out)
 {
@@ -56,15 +69,7 @@ __global__ void prep_oligos_kernel(const uint64_t *__restrict__ f, const uint64_
 	W128 w;
 	w.hi = src[2 * (i >> 1)];
 	w.lo = src[2 * (i >> 1) + 1];
-	const int size = w_size(w), start = w_start(w), stop = w_stop(w);
-	OligoDev o;
-	const Planes4 pl = w_planes(w);
-	o.a = pl.a; o.c = pl.c; o.g = pl.g; o.t = pl.t;
-	o.norm = size > 0 ? (float)(1.0 / (double)size) : 0.0f;
-	const uint32_t thr = (uint32_t)__fmul_rn((float)size, thr2);
-	const uint32_t pen = stop >= 1 ? w_get(w, stop - 1) : 0u, last = stop >= 0 ? w_get(w, stop) : 0u;
-	o.packed = (thr & 255u) | ((uint32_t)(start & 255) << 8) | ((uint32_t)(stop & 255) << 16) | (pen << 24) | (last << 28);
-	out[i] = o;
+	out[i] = make_oligo(w, thr2);
 }
 
 struct ScoreEntry {

@@ -120,6 +120,38 @@ PCR_HD W128 w_center(const W128 &a)
 	return delta > 0 ? w_shr(a, delta) : w_shl(a, -delta);
 }
 
+// Word::max_overlap (word.h:38-92): dp[i][j] = dp[i-1][j-1] + (q[i] == s[j]) never resets, so the result is the largest
+// number of EQUAL nibbles on one diagonal of [start, stop] x [start, stop], over max(size, size).
+PCR_HD float w_max_overlap(const W128 &q, const W128 &s)
+{
+	const int qs = w_start(q), qe = w_stop(q), ss = w_start(s), se = w_stop(s);
+	if (qs > qe || ss > se) { // an empty word: no cell is visited; 0 / max(size, size) (0/0 = NaN when both are empty)
+		const int d = w_size(q) > w_size(s) ? w_size(q) : w_size(s);
+		return 0.0f / (float)d;
+	}
+	const int nq = qe - qs + 1, ns = se - ss + 1;
+	const W128 a = w_shl(q, qs), b = w_shl(s, ss);
+	W128 ones;
+	ones.hi = ones.lo = 0x8888888888888888ull;
+	int best = 0;
+	for (int d = -(ns - 1); d <= nq - 1; ++d) { // q position i faces s position i - d
+		const W128 y = d >= 0 ? w_shr(b, d) : w_shl(b, -d);
+		const int lo = d > 0 ? d : 0;
+		int hi = ns + d < nq ? ns + d : nq; // exclusive
+		if (hi <= lo) continue;
+		const W128 m = w_shr(w_shl(ones, 32 - (hi - lo)), lo);
+		const uint64_t eh = ~nibble_nonzero(a.hi ^ y.hi) & m.hi, el = ~nibble_nonzero(a.lo ^ y.lo) & m.lo;
+		const int c = popc64(eh) + popc64(el);
+		best = c > best ? c : best;
+	}
+	const int den = w_size(q) > w_size(s) ? w_size(q) : w_size(s);
+#ifdef __CUDA_ARCH__
+	return __fdiv_rn((float)best, (float)den);
+#else
+	return (float)best / (float)den;
+#endif
+}
+
 // complement of every nibble: A<->T (bits 0,3), C<->G (bits 1,2) -- i.e. reverse the 4 bits.
 PCR_HD uint64_t comp_nibbles(uint64_t v)
 {

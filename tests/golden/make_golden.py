@@ -169,7 +169,41 @@ def optimize_kats(ref_factory):
     return rec
 
 
+def multiplex_optimize_kats(ref_factory):
+    """optimize() with the multiplex terms (multiplex background keys + assay pool), and the three pieces on their own:
+    keys of the whole-sequence pack, compute_multiplex_background_coverage of trial oligos, compute_oligo_overlap"""
+    rec = {}
+    wa, wb = optimize_cases.overlap_words()
+    rec["maxov"] = ref_factory().word_max_overlap(wa, wb)
+    print("max_overlap: %d pairs, %d exact re-uses" % (len(wa), int((rec["maxov"] == 1.0).sum())))
+    for case in optimize_cases.multiplex_cases():
+        ref = ref_factory()
+        ref.set_sequences(case.targets)
+        ref.select_words(case.f, case.r, case.target_search, optimize_5=case.optimize_5, optimize_3=case.optimize_3)
+        mp = None
+        if case.multiplex is not None:
+            mp = ref_factory()
+            mp.set_sequences(case.multiplex)
+            rec["mpx_%s_keys" % case.name] = mp.pack_all()
+        pf, pr = case.pool
+        f, r, score = ref.optimize_multiplex(case.f, case.r, case.moves, case.options, None, mp, pf, pr)
+        rec["opt_%s_f" % case.name], rec["opt_%s_r" % case.name], rec["opt_%s_score" % case.name] = f, r, score
+        if mp is not None:
+            for taq in (0, 1):
+                rec["mpx_%s_cov_taq%d" % (case.name, taq)] = mp.multiplex_coverage(case.f, case.r, f, r, float(case.options.background_threshold),
+                                                                                 bool(taq))
+        rec["mpx_%s_overlap" % case.name] = ref.oligo_overlap(f, r, pf, pr)
+        changed = int(((f != case.f).any(1) | (r != case.r).any(1)).sum())
+        print("multiplex optimize %-18s changed %3d of %3d  mean score %s  keys %d  cov>0: %d" % (
+            case.name, changed, len(f), score.mean(0), len(rec.get("mpx_%s_keys" % case.name, [])),
+            int((rec.get("mpx_%s_cov_taq0" % case.name, np.zeros(1)) > 0).sum())))
+    return rec
+
+
 def main():
+    if "--multiplex-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "kat_optimize_multiplex.npz"), **multiplex_optimize_kats(RefLib))
+        return
     ref = RefLib()
     ref.set_threads(1)
     for sc in scenarios.all_scenarios():
@@ -181,6 +215,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_thermo_batch.npz"), **thermo_batch_kats(ref))
     np.savez_compressed(os.path.join(HERE, "kat_background.npz"), **background_kats(ref))
     np.savez_compressed(os.path.join(HERE, "kat_optimize.npz"), **optimize_kats(RefLib))
+    np.savez_compressed(os.path.join(HERE, "kat_optimize_multiplex.npz"), **multiplex_optimize_kats(RefLib))
     print("wrote fixtures to", HERE)
 
 

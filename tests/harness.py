@@ -257,6 +257,12 @@ class RefLib(_Base):
         self.f_variants = self._fn("score_variants", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, _u64p, _u64p, ctypes.c_float, ctypes.c_float,
                                                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p])
         self.f_optimize = self._fn("optimize", ctypes.c_int, [vp, vp, ctypes.c_uint32, _u64p, _u64p, _i32p, ctypes.c_uint32, ctypes.c_void_p, _f32p])
+        self.f_pack_all = self._fn("pack_all", ctypes.c_long, [vp, ctypes.c_uint32, ctypes.c_uint32])
+        self.f_optimize_mpx = self._fn("optimize_multiplex", ctypes.c_int, [vp, vp, vp, ctypes.c_uint32, _u64p, _u64p, _i32p, ctypes.c_uint32,
+                                                                            ctypes.c_void_p, ctypes.c_uint32, _u64p, _u64p, _f32p])
+        self.f_mpx_cov = self._fn("multiplex_coverage", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, _u64p, _u64p, ctypes.c_float, ctypes.c_int,
+                                                                       _f32p])
+        self.f_overlap = self._fn("oligo_overlap", ctypes.c_int, [ctypes.c_uint32, _u64p, _u64p, ctypes.c_uint32, _u64p, _u64p, _f32p])
         self.n_seq = 0
 
     def set_threads(self, n):
@@ -408,6 +414,44 @@ class RefLib(_Base):
                              ctypes.byref(options), _p(score, _f32p))
         assert rc == 0, self.f_err(self.h)
         return f, r, score
+
+    def word_max_overlap(self, a, b):
+        fn = self._fn("word_max_overlap", ctypes.c_float, [_u64p, _u64p])
+        a, b = _w(a), _w(b)
+        return np.array([fn(_p(a[i], _u64p), _p(b[i], _u64p)) for i in range(len(a))], np.float32)
+
+    def pack_all(self, pack_max_degen=256, min_oligo_length=18):
+        """the multiplex background database of main.cpp:989-1003 (every sequence packed whole) -> its keys"""
+        n = self.f_pack_all(self.h, pack_max_degen, min_oligo_length)
+        assert n >= 0, self.f_err(self.h)
+        return self.keys()
+
+    def optimize_multiplex(self, f, r, moves, options, background=None, multiplex=None, pool_f=None, pool_r=None):
+        """optimize() with a multiplex background context (pack_all) and an assay pool"""
+        f, r = _w(f).copy(), _w(r).copy()
+        mv = np.ascontiguousarray(moves, dtype=np.int32)
+        score = np.zeros((len(f), 3), np.float32)
+        pf = _w(pool_f) if pool_f is not None else np.zeros((0, 2), np.uint64)
+        pr = _w(pool_r) if pool_r is not None else np.zeros((0, 2), np.uint64)
+        rc = self.f_optimize_mpx(self.h, background.h if background is not None else None, multiplex.h if multiplex is not None else None,
+                                 len(f), _p(f, _u64p), _p(r, _u64p), _p(mv, _i32p), len(mv), ctypes.byref(options), len(pf), _p(pf, _u64p),
+                                 _p(pr, _u64p), _p(score, _f32p))
+        assert rc == 0, self.f_err(self.h)
+        return f, r, score
+
+    def multiplex_coverage(self, base_f, base_r, var_f, var_r, threshold, taq=False):
+        bf, br, vf, vr = _w(base_f), _w(base_r), _w(var_f), _w(var_r)
+        cov = np.zeros(len(bf), np.float32)
+        rc = self.f_mpx_cov(self.h, len(bf), _p(bf, _u64p), _p(br, _u64p), _p(vf, _u64p), _p(vr, _u64p), threshold, int(taq), _p(cov, _f32p))
+        assert rc == 0, self.f_err(self.h)
+        return cov
+
+    def oligo_overlap(self, f, r, pool_f, pool_r):
+        f, r, pf, pr = _w(f), _w(r), _w(pool_f), _w(pool_r)
+        ov = np.zeros(len(f), np.float32)
+        rc = self.f_overlap(len(f), _p(f, _u64p), _p(r, _u64p), len(pf), _p(pf, _u64p), _p(pr, _u64p), _p(ov, _f32p))
+        assert rc == 0
+        return ov
 
     def sw_batch(self, query, target):
         """SO::SeqOverlap, 8 problems per align(): -> (n, 6) int32 {score, q_start, q_stop, t_start, t_stop, last_two}"""

@@ -89,3 +89,20 @@ def test_synth_word_packing_matches_library(lib):
         codes = synth.CODE[rng.integers(0, 4, size=n)]
         s = "".join("ACGT"[int(np.log2(c))] for c in codes)
         assert synth.word_from_codes(codes) == synth.word_from_string(s)
+
+
+def test_word_max_overlap_matches_reference_golden(lib):
+    """Word::max_overlap (word.h:38-92) of the host helper (the same function the pool-overlap kernel runs) vs the reference"""
+    import os
+    from tests import optimize_cases as oc
+    from tests.harness import REF_PATH, RefLib
+    a, b = oc.overlap_words()
+    got = np.array([lib.pcramp_word_max_overlap(a[i].ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                                b[i].ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))) for i in range(len(a))], np.float32)
+    want = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_optimize_multiplex.npz"))["maxov"]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    if os.path.exists(REF_PATH):
+        a2, b2 = oc.overlap_words(seed=23, n=3000)
+        got = np.array([lib.pcramp_word_max_overlap(a2[i].ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                                    b2[i].ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))) for i in range(len(a2))], np.float32)
+        assert np.array_equal(got.view(np.uint32), RefLib().word_max_overlap(a2, b2).view(np.uint32))
