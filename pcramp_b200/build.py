@@ -42,7 +42,8 @@ def build_cuda(force=False, verbose=False):
     if not force and not _stale(LIB, srcs):
         return LIB
     units = [s for s in srcs if s.endswith(".cu")]
-    cmd = [_nvcc()] + NVCC_FLAGS + ["--threads", str(len(units))] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + units
+    extra = os.environ.get("PCRAMP_NVCC_EXTRA", "").split()   # tuning experiments only (e.g. -DTHERMO_MIN_BLOCKS=6)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["--threads", str(len(units))] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + units
     env = dict(os.environ)
     env.pop("CXX", None)  # the image's CXX wrapper is not a usable host compiler for nvcc
     env.pop("CC", None)

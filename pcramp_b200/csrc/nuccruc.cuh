@@ -37,8 +37,14 @@ enum : int { P_AT = 3, P_TA = 21, P_CG = 9, P_GC = 15, P_GT = 17, P_TG = 23, P_N
 enum : int { SUPP_LOOP_H = 0, SUPP_LOOP_S, SUPP_BULGE_H, SUPP_BULGE_S, SUPP_TM_AT_H, SUPP_TM_AT_S, SUPP_TM_GC_H, SUPP_TM_GC_S, SUPP_TM_I_H,
 	SUPP_TM_I_S, SUPP_TMM_H, SUPP_TMM_S };
 constexpr int NC_MAX_LEN = 32;              // WORD_LENGTH: the longest oligo pcramp can hold (options.cpp:854-860)
-constexpr int NC_STRIDE = NC_MAX_LEN + 1;
-constexpr int NC_CELLS = NC_STRIDE * NC_STRIDE;
+constexpr int NC_STRIDE = 40;               // row pitch of the DP matrix (cell id = i * NC_STRIDE + j, 0 <= i, j <= 32): a multiple of 8 so
+                                            // that the eight cells a strip writes per row are one aligned 16-byte store
+constexpr int NC_INFO_PAD = 7;              // Ctx::info = storage + NC_INFO_PAD: column 1 of every row lands on a 16-byte boundary
+constexpr int NC_CELLS = (NC_MAX_LEN + 1) * NC_STRIDE + 8; // storage, in 16-bit words (16-byte aligned)
+#ifndef NC_STRIP_W
+#define NC_STRIP_W 8
+#endif
+constexpr int NC_STRIP = NC_STRIP_W;        // columns per register strip of the DP fill (8 or 16)
 constexpr int NC_SEQ_CAP = NC_MAX_LEN + 4;  // room for the stale slots past the end
 constexpr int NC_ALN_CAP = 96;
 constexpr int NC_ALN_HEAD = 8;
@@ -101,7 +107,7 @@ struct Ctx {
 	// DP storage: one 16-bit word per cell is all the enumeration needs --
 	//   M_trace[3:0] | Iq_trace[7:4] | It_trace[11:8] | Iq<0 [12] | It<0 [13] | M<0 [14] | M==0 [15]
 	// (the scores themselves only matter for "is this a maximal cell", kept as a short list, see dp_fill)
-	unsigned short *info;   // NC_CELLS
+	unsigned short *info;   // storage (NC_CELLS words, 16-byte aligned) + NC_INFO_PAD
 	int max_cell[8];        // the first NC_MAX_CELLS cells whose M equals the maximum, in row-major order
 	int n_max_cell;         // how many cells equal the maximum (may exceed NC_MAX_CELLS)
 };
@@ -174,7 +180,7 @@ PCR_HD void dp_cell(const DpTable *D, int tb, int ptb, int qb, int pqb, int aM, 
 PCR_HD void dp_border(Ctx &c)
 { // NC_Elem() : scores -1, traces invalid (nuc_cruc.h:427-433); row 0 and column 0 are never written
 	const unsigned short b = (unsigned short)(TR_INVALID | (TR_INVALID << 4) | (TR_INVALID << 8) | 0x7000);
-	for (int k = 0; k < NC_STRIDE; ++k) {
+	for (int k = 0; k <= NC_MAX_LEN; ++k) {
 		c.info[k] = b;
 		c.info[k * NC_STRIDE] = b;
 	}
@@ -248,6 +254,123 @@ PCR_HD int dp_fill_t(Ctx &c, bool hairpin, long long *cells_out, int replay_max,
 	}
 	if (cells_out) *cells_out = cells;
 	return REPLAY ? replay_max : max_score;
+}
+
+// The same fill (first pass only), strip-mined for a thread that owns the whole problem: NC_STRIP columns at a time, all
+// rows.  The previous row of the strip (clamped M, Iq, It per column), the column constants and the running (i, j-1) cell
+// stay in registers with static indices; only the strip's right-hand boundary column goes through a small per-thread
+// array (3 loads + 3 stores per row per STRIP instead of per cell), and the eight 16-bit info words of a row leave as one
+// 16-byte store.  Table addresses split into a column term and a row term (index = prev * 49 + cur with prev / cur =
+// 7 * target base + query base), so a lookup is one add + one shared-memory load; the two lookups that depend on the
+// column alone / the row alone are hoisted.  dp_step(prev, dg) = max(prev, 0) - dg, so the state is kept clamped.
+// Cells are visited strip-major; the list of maximal cells is put back into row-major order at the end (it is only used
+// when it is complete, i.e. at most NC_MAX_CELLS entries; otherwise the row-major replay pass takes over).
+PCR_HD int imax(int a, int b) { return a > b ? a : b; }
+
+struct alignas(16) InfoRow8 {
+	unsigned int w[4];
+};
+
+PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
+{
+	constexpr int W = NC_STRIP;
+	dp_border(c);
+	c.n_max_cell = 0;
+	const int qlen = c.qlen, tlen = hairpin ? c.qlen : c.tlen;
+	const unsigned char *tq = hairpin ? c.q : c.t;
+	const int max_stem = qlen - 4; // steric limit 3 + 1 (nuc_cruc.cpp:627-635)
+	const int rows = hairpin ? max_stem : qlen;
+	const int max_cols = hairpin ? max_stem : tlen;
+	const int *__restrict__ dg = c.D->dg;
+	int eM[NC_MAX_LEN + 1], eIq[NC_MAX_LEN + 1], eIt[NC_MAX_LEN + 1]; // clamped state of column j0 - 1, per row (column 0: the border)
+	for (int i = 0; i <= NC_MAX_LEN; ++i) eM[i] = eIq[i] = eIt[i] = 0;
+	int max_score = -1;
+	long long cells = 0;
+	for (int j0 = 1; j0 <= max_cols; j0 += W) {
+		int cA[W], cB[W], cC[W];              // column terms: ptb * 343 + tb * 7, tb * 7, tb * 343
+		int pM[W], pIq[W], pIt[W];            // row i - 1 of the strip, clamped (row 0: the border)
+		{
+			int ptb = (j0 == 1) ? (int)bGAP : seq_at(tq, j0 - 2);
+#pragma unroll
+			for (int k = 0; k < W; ++k) {
+				const int tb = seq_at(tq, j0 + k - 1); // past the end: padding (a valid code); those columns are computed and ignored
+				cB[k] = tb * NBASE;
+				cC[k] = tb * (NBASE * NPAIR);
+				cA[k] = ptb * (NBASE * NPAIR) + cB[k];
+				ptb = tb;
+				pM[k] = pIq[k] = pIt[k] = 0;
+			}
+		}
+		int a0M = 0, a0Iq = 0, a0It = 0; // (i - 1, j0 - 1)
+		int pqb = bGAP;
+		for (int i = 1; i <= rows; ++i) {
+			const int cols = hairpin ? (max_stem - (i - 1)) : tlen;
+			if (j0 > cols) break; // hairpin triangle: the rows only get shorter
+			const int nv = cols - j0 + 1; // columns of this strip that exist in this row (the rest is computed and ignored)
+			const int qb = seq_at(c.q, qlen - i);
+			const int rA = pqb * NPAIR + qb;                 // L1 = dg[cA + rA]
+			const int rB = bGAP * NPAIR + qb;                // L2 = dg[cA + rB]
+			const int rC = bGAP * NBASE * NPAIR + rA;        // L3 = dg[cB + rC]
+			const int rD = qb * NPAIR + bGAP;                // L4 = dg[cA + rD]
+			const int rE = rA + bGAP * NBASE;                // L6 = dg[cC + rE]
+			const int dg7 = dg[rC + bGAP * NBASE];           // (GAP, pqb) -> (GAP, qb): the row alone
+			int aM = a0M, aIq = a0Iq, aIt = a0It;            // (i - 1, j - 1)
+			int cM = eM[i], cIq = eIq[i];                    // (i, j - 1)
+			a0M = cM; a0Iq = cIq; a0It = eIt[i];
+			InfoRow8 out[W / 8 > 0 ? W / 8 : 1];
+			int xm[W];
+			int row_max = -0x7fffffff;
+			unsigned int pack = 0u;
+#pragma unroll
+			for (int k = 0; k < W; ++k) {
+				const int d1 = aM - dg[cA[k] + rA];
+				const int d2 = aIq - dg[cA[k] + rB];
+				const int d3 = aIt - dg[cB[k] + rC];
+				const int xM = imax(d1, imax(d2, d3));
+				const unsigned int mtr = (d1 == xM ? (unsigned)TR_DIAG : 0u) | (d2 == xM ? (unsigned)TR_LEFT : 0u) | (d3 == xM ? (unsigned)TR_UP : 0u);
+				const int qi = cM - dg[cA[k] + rD];
+				const int qe = cIq - dg[cA[k] + bGAP * NPAIR + bGAP]; // (ptb, GAP) -> (tb, GAP): the column alone
+				const int xIq = imax(qi, qe);
+				const unsigned int qtr = (qi == xIq ? (unsigned)TR_DIAG : 0u) | (qe == xIq ? (unsigned)TR_LEFT : 0u);
+				const int ti = pM[k] - dg[cC[k] + rE];
+				const int te = pIt[k] - dg7;
+				const int xIt = imax(ti, te);
+				const unsigned int ttr = (ti == xIt ? (unsigned)TR_DIAG : 0u) | (te == xIt ? (unsigned)TR_UP : 0u);
+				const unsigned int inf = mtr | (qtr << 4) | (ttr << 8) | (((unsigned)xIq >> 31) << 12) | (((unsigned)xIt >> 31) << 13) |
+				                         (((unsigned)xM >> 31) << 14) | (xM == 0 ? 0x8000u : 0u);
+				if (k & 1) out[k >> 3].w[(k >> 1) & 3] = pack | (inf << 16);
+				else pack = inf;
+				xm[k] = xM;
+				row_max = imax(row_max, xM);
+				aM = pM[k]; aIq = pIq[k]; aIt = pIt[k];
+				cM = imax(xM, 0); cIq = imax(xIq, 0);
+				pM[k] = cM; pIq[k] = cIq; pIt[k] = imax(xIt, 0);
+			}
+#pragma unroll
+			for (int v = 0; v < W / 8; ++v) *(InfoRow8 *)(c.info + i * NC_STRIDE + j0 + 8 * v) = out[v]; // cells past `cols` are never read
+			if (row_max >= max_score) { // a maximal cell may be in this row of the strip (or in its ignored part): look
+#pragma unroll
+				for (int k = 0; k < W; ++k)
+					if (k < nv) note_cell(c, i * NC_STRIDE + j0 + k, xm[k], max_score);
+			}
+			eM[i] = pM[W - 1]; eIq[i] = pIq[W - 1]; eIt[i] = pIt[W - 1]; // only read by the next strip when column j0 + W - 1 exists in this row
+			cells += nv < W ? nv : W;
+			pqb = qb;
+		}
+	}
+	// row-major order of the maximal cells (insertion sort of at most NC_MAX_CELLS ids)
+	if (c.n_max_cell <= NC_MAX_CELLS)
+		for (int a = 1; a < c.n_max_cell; ++a) {
+			const int v = c.max_cell[a];
+			int b = a - 1;
+			while (b >= 0 && c.max_cell[b] > v) {
+				c.max_cell[b + 1] = c.max_cell[b];
+				--b;
+			}
+			c.max_cell[b + 1] = v;
+		}
+	if (cells_out) *cells_out = cells;
+	return max_score;
 }
 
 // gap-free main diagonal only (fast_alignment(true))
@@ -774,7 +897,7 @@ PCR_HD Result run_problem(Ctx &c, int op)
 	const bool diagonal = (op == OP_HETERODIMER_DIAG || op == OP_HOMODIMER_DIAG);
 	const int mode = hairpin ? MODE_HAIRPIN : ((op == OP_HOMODIMER || op == OP_HOMODIMER_DIAG) ? MODE_HOMO : MODE_HETERO);
 	if (diagonal) max_score = dp_fill_diagonal_t<false>(c, &r.cells, 0, nullptr, mode);
-	else max_score = dp_fill_t<false>(c, hairpin, &r.cells, 0, nullptr, mode);
+	else max_score = dp_fill_strips(c, hairpin, &r.cells);
 	if (c.n_max_cell <= NC_MAX_CELLS) { // tm_dimer / approximate_tm_hairpin: every maximal cell, in row-major order
 		for (int k = 0; k < c.n_max_cell; ++k) {
 			if (hairpin) enumerate_hairpin(c, c.max_cell[k], best);

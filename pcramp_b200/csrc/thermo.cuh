@@ -6,6 +6,8 @@
 //   len_a / len_b   n bytes
 //   log_strand      n floats: logf(total strand concentration), taken on the host with the reference's libm
 //   out             n x float4 {Tm, dH, dS, dG_dp}
+//   order           optional permutation: thread `slot` works on problem order[slot] (problems binned by size, so that the lanes
+//                   of a warp run DP fills of the same shape)
 // The integer DP table (49 x 49 int32 = 9.6 KB, update_dp_param) is staged in shared memory once per CTA; the
 // float parameter tables (58 KB, read sparsely by the evaluation epilogue) stay in global memory behind the
 // read-only cache.  The DP matrix of a problem (one 16-bit word of trace bits and sign flags per cell, 2.2 KB) lives in the owning thread's
@@ -19,13 +21,16 @@ namespace pcr {
 namespace nc {
 
 constexpr int THERMO_BLOCK = 128;
+#ifndef THERMO_MIN_BLOCKS
+#define THERMO_MIN_BLOCKS 5 // register budget of the strip-mined fill (nuccruc.cuh): 96 regs / thread
+#endif
 constexpr int THERMO_SEQ_STRIDE = 32;
 
 struct DpShared {
 	int dg[NPAIR * NPAIR];
 };
 
-__global__ void __launch_bounds__(THERMO_BLOCK) thermo_kernel(int op, uint32_t n, const uint8_t *__restrict__ seq_a, const uint8_t *__restrict__ seq_b,
+__global__ void __launch_bounds__(THERMO_BLOCK, THERMO_MIN_BLOCKS) thermo_kernel(int op, uint32_t n, const uint32_t *__restrict__ order, const uint8_t *__restrict__ seq_a, const uint8_t *__restrict__ seq_b,
 	const uint8_t *__restrict__ len_a, const uint8_t *__restrict__ len_b, const float *__restrict__ log_strand, const Tables *__restrict__ tables,
 	const DpTable *__restrict__ dp, float4 *__restrict__ out)
 {
@@ -36,8 +41,9 @@ __global__ void __launch_bounds__(THERMO_BLOCK) thermo_kernel(int op, uint32_t n
 		for (int k = threadIdx.x; k < (int)(sizeof(DpTable) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
 	}
 	__syncthreads();
-	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= n) return;
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= n) return;
+	const uint32_t p = order ? order[slot] : slot; // size-binned launch order (thermo_abi.cu thermo_order)
 	__align__(16) unsigned char q[NC_SEQ_CAP];
 	__align__(16) unsigned char t[NC_SEQ_CAP];
 	const uint4 *qa = (const uint4 *)(seq_a + (size_t)p * THERMO_SEQ_STRIDE);
@@ -51,7 +57,7 @@ __global__ void __launch_bounds__(THERMO_BLOCK) thermo_kernel(int op, uint32_t n
 		*(uint4 *)(t + 16) = tb[1];
 		*(uint32_t *)(t + 32) = 0u;
 	}
-	unsigned short info[NC_CELLS];
+	__align__(16) unsigned short info[NC_CELLS];
 	Ctx c;
 	c.T = tables;
 	c.D = &s_dp;
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(THERMO_BLOCK) thermo_kernel(int op, uint32_t n
 	c.qlen = len_a[p];
 	c.tlen = two ? len_b[p] : c.qlen;
 	c.log_strand = log_strand[p];
-	c.info = info;
+	c.info = info + NC_INFO_PAD;
 	const Result r = run_problem(c, op);
 	out[p] = make_float4(r.tm, r.dH, r.dS, r.dp_dg);
 }

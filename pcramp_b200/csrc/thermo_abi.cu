@@ -4,6 +4,8 @@
 #include "ctx.cuh"
 #include "thermo.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cstring>
 #include <thread>
@@ -44,6 +46,8 @@ struct ThermoState {
 	DpTable h_dp;
 	float dp_salt = -1.0f;
 	DevBuf d_tables, d_dp, d_a, d_b, d_la, d_lb, d_ls, d_out;
+	DevBuf d_key[2], d_ord[2], d_sort_tmp; // size-binned launch order (thermo_order)
+	const uint32_t *order = nullptr;
 	PinnedBuf h_a, h_b, h_la, h_lb, h_ls, h_out;
 	int op = -1;
 	uint32_t n = 0;
@@ -121,11 +125,14 @@ int thermo_reserve(pcramp_gpu_ctx *ctx, ThermoState *t, uint32_t n)
 	return 0;
 }
 
+int thermo_order(pcramp_gpu_ctx *ctx, ThermoState *t);
+
 // problems already encoded in the pinned staging buffers -> HBM
 int thermo_upload(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n)
 {
 	t->op = op;
 	t->n = n;
+	t->order = nullptr;
 	uint64_t cells = 0;
 	const uint8_t *la = t->h_la.as<uint8_t>(), *lb = t->h_lb.as<uint8_t>();
 	for (uint32_t p = 0; p < n; ++p) cells += (uint64_t)problem_cells(op, la[p], two_sequences(op) ? lb[p] : la[p]);
@@ -138,6 +145,41 @@ int thermo_upload(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n)
 		CK(cudaMemcpyAsync(t->d_lb.p, t->h_lb.p, n, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	CK(cudaMemcpyAsync(t->d_ls.p, t->h_ls.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	return thermo_order(ctx, t);
+}
+
+// Launch order: a warp pays for its longest problem (rows x column strips of the DP fill), so problems of equal size are
+// put next to each other: slot s of the launch works on problem order[s] (results still land in out[problem]).
+constexpr uint32_t THERMO_ORDER_MIN = 2048; // below this the launch is a handful of warps anyway
+
+__global__ void thermo_key_kernel(int op, uint32_t n, const uint8_t *__restrict__ len_a, const uint8_t *__restrict__ len_b, uint16_t *key, uint32_t *ord)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	const uint32_t q = len_a[p], t = (op == OP_HETERODIMER || op == OP_HETERODIMER_DIAG) ? len_b[p] : q;
+	key[p] = (uint16_t)((t << 6) | q); // columns (strips) first, then rows
+	ord[p] = p;
+}
+
+int thermo_order(pcramp_gpu_ctx *ctx, ThermoState *t)
+{
+	t->order = nullptr;
+	const uint32_t n = t->n;
+	if (n < THERMO_ORDER_MIN || t->op == OP_PM_DUPLEX) return 0;
+	for (int k = 0; k < 2; ++k) {
+		CK(t->d_key[k].ensure((size_t)n * 2));
+		CK(t->d_ord[k].ensure((size_t)n * 4));
+	}
+	thermo_key_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(t->op, n, t->d_la.as<uint8_t>(), t->d_lb.as<uint8_t>(), t->d_key[0].as<uint16_t>(),
+		t->d_ord[0].as<uint32_t>());
+	CK(cudaGetLastError());
+	size_t tb = 0;
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, t->d_key[0].as<uint16_t>(), t->d_key[1].as<uint16_t>(), t->d_ord[0].as<uint32_t>(),
+		t->d_ord[1].as<uint32_t>(), (int)n, 0, 12, ctx->stream));
+	CK(t->d_sort_tmp.ensure(tb));
+	CK(cub::DeviceRadixSort::SortPairs(t->d_sort_tmp.p, tb, t->d_key[0].as<uint16_t>(), t->d_key[1].as<uint16_t>(), t->d_ord[0].as<uint32_t>(),
+		t->d_ord[1].as<uint32_t>(), (int)n, 0, 12, ctx->stream));
+	t->order = t->d_ord[1].as<uint32_t>();
 	return 0;
 }
 
@@ -149,7 +191,7 @@ int thermo_launch(pcramp_gpu_ctx *ctx, ThermoState *t)
 	t->stats.ms_kernel = 0.0f;
 	if (!t->n) return 0;
 	CK(cudaEventRecord(t->ev0, ctx->stream));
-	thermo_kernel<<<grid_for(t->n, THERMO_BLOCK), THERMO_BLOCK, 0, ctx->stream>>>(t->op, t->n, t->d_a.as<uint8_t>(), t->d_b.as<uint8_t>(),
+	thermo_kernel<<<grid_for(t->n, THERMO_BLOCK), THERMO_BLOCK, 0, ctx->stream>>>(t->op, t->n, t->order, t->d_a.as<uint8_t>(), t->d_b.as<uint8_t>(),
 		t->d_la.as<uint8_t>(), t->d_lb.as<uint8_t>(), t->d_ls.as<float>(), t->d_tables.as<Tables>(), t->d_dp.as<DpTable>(), t->d_out.as<float4>());
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(t->ev1, ctx->stream));

@@ -50,7 +50,7 @@ int host_thermo_batch(int op, int n, const char *a, const char *b, float salt, c
 		c.qlen = qlen;
 		c.tlen = (op == OP_HETERODIMER || op == OP_HETERODIMER_DIAG) ? tlen : qlen;
 		c.log_strand = logf(strand[p]);
-		c.info = info.data();
+		c.info = info.data() + NC_INFO_PAD;
 		Result r = run_problem(c, op);
 		out[4 * p + 0] = r.tm;
 		out[4 * p + 1] = r.dH;
