@@ -274,6 +274,8 @@ struct alignas(16) InfoRow8 {
 PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 {
 	constexpr int W = NC_STRIP;
+	constexpr int NS = (NC_MAX_LEN + W - 1) / W;
+	constexpr int NEG = -0x7fffffff;
 	dp_border(c);
 	c.n_max_cell = 0;
 	const int qlen = c.qlen, tlen = hairpin ? c.qlen : c.tlen;
@@ -282,11 +284,16 @@ PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 	const int rows = hairpin ? max_stem : qlen;
 	const int max_cols = hairpin ? max_stem : tlen;
 	const int *__restrict__ dg = c.D->dg;
-	int eM[NC_MAX_LEN + 1], eIq[NC_MAX_LEN + 1], eIt[NC_MAX_LEN + 1]; // clamped state of column j0 - 1, per row (column 0: the border)
-	for (int i = 0; i <= NC_MAX_LEN; ++i) eM[i] = eIq[i] = eIt[i] = 0;
+	int eM[NC_MAX_LEN + 2], eIq[NC_MAX_LEN + 2], eIt[NC_MAX_LEN + 2]; // clamped state of column j0 - 1, per row (column 0: the border)
+	for (int i = 0; i < NC_MAX_LEN + 2; ++i) eM[i] = eIq[i] = eIt[i] = 0;
+	// per (strip, row): the largest M among the row's cells of the strip and which of them reach it; the maximal cells of the
+	// matrix are read back from these in row-major order after the fill (no per-cell bookkeeping inside it)
+	int rmax[NS][NC_MAX_LEN + 1];
+	unsigned char rmask[NS][NC_MAX_LEN + 1];
 	int max_score = -1;
 	long long cells = 0;
-	for (int j0 = 1; j0 <= max_cols; j0 += W) {
+	int n_strips = 0;
+	for (int j0 = 1; j0 <= max_cols; j0 += W, ++n_strips) {
 		int cA[W], cB[W], cC[W];              // column terms: ptb * 343 + tb * 7, tb * 7, tb * 343
 		int pM[W], pIq[W], pIt[W];            // row i - 1 of the strip, clamped (row 0: the border)
 		{
@@ -303,11 +310,17 @@ PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 		}
 		int a0M = 0, a0Iq = 0, a0It = 0; // (i - 1, j0 - 1)
 		int pqb = bGAP;
+		// the loads of a row (query base, boundary column) are issued one row ahead of their use
+		int n_qb = seq_at(c.q, qlen - 1), n_eM = eM[1], n_eIq = eIq[1], n_eIt = eIt[1];
 		for (int i = 1; i <= rows; ++i) {
 			const int cols = hairpin ? (max_stem - (i - 1)) : tlen;
 			if (j0 > cols) break; // hairpin triangle: the rows only get shorter
 			const int nv = cols - j0 + 1; // columns of this strip that exist in this row (the rest is computed and ignored)
-			const int qb = seq_at(c.q, qlen - i);
+			const int qb = n_qb;
+			int cM = n_eM, cIq = n_eIq;                      // (i, j - 1)
+			const int cIt0 = n_eIt;
+			n_qb = seq_at(c.q, qlen - (i + 1));
+			n_eM = eM[i + 1]; n_eIq = eIq[i + 1]; n_eIt = eIt[i + 1];
 			const int rA = pqb * NPAIR + qb;                 // L1 = dg[cA + rA]
 			const int rB = bGAP * NPAIR + qb;                // L2 = dg[cA + rB]
 			const int rC = bGAP * NBASE * NPAIR + rA;        // L3 = dg[cB + rC]
@@ -315,11 +328,9 @@ PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 			const int rE = rA + bGAP * NBASE;                // L6 = dg[cC + rE]
 			const int dg7 = dg[rC + bGAP * NBASE];           // (GAP, pqb) -> (GAP, qb): the row alone
 			int aM = a0M, aIq = a0Iq, aIt = a0It;            // (i - 1, j - 1)
-			int cM = eM[i], cIq = eIq[i];                    // (i, j - 1)
-			a0M = cM; a0Iq = cIq; a0It = eIt[i];
+			a0M = cM; a0Iq = cIq; a0It = cIt0;
 			InfoRow8 out[W / 8 > 0 ? W / 8 : 1];
 			int xm[W];
-			int row_max = -0x7fffffff;
 			unsigned int pack = 0u;
 #pragma unroll
 			for (int k = 0; k < W; ++k) {
@@ -341,34 +352,46 @@ PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 				if (k & 1) out[k >> 3].w[(k >> 1) & 3] = pack | (inf << 16);
 				else pack = inf;
 				xm[k] = xM;
-				row_max = imax(row_max, xM);
 				aM = pM[k]; aIq = pIq[k]; aIt = pIt[k];
 				cM = imax(xM, 0); cIq = imax(xIq, 0);
 				pM[k] = cM; pIq[k] = cIq; pIt[k] = imax(xIt, 0);
 			}
 #pragma unroll
 			for (int v = 0; v < W / 8; ++v) *(InfoRow8 *)(c.info + i * NC_STRIDE + j0 + 8 * v) = out[v]; // cells past `cols` are never read
-			if (row_max >= max_score) { // a maximal cell may be in this row of the strip (or in its ignored part): look
-#pragma unroll
-				for (int k = 0; k < W; ++k)
-					if (k < nv) note_cell(c, i * NC_STRIDE + j0 + k, xm[k], max_score);
-			}
 			eM[i] = pM[W - 1]; eIq[i] = pIq[W - 1]; eIt[i] = pIt[W - 1]; // only read by the next strip when column j0 + W - 1 exists in this row
+			int row_max = NEG;
+			if (nv < W) {
+#pragma unroll
+				for (int k = 0; k < W; ++k) xm[k] = (k < nv) ? xm[k] : NEG;
+			}
+#pragma unroll
+			for (int k = 0; k < W; ++k) row_max = imax(row_max, xm[k]);
+			unsigned int eq = 0u;
+#pragma unroll
+			for (int k = 0; k < W; ++k) eq |= (xm[k] == row_max ? 1u : 0u) << k;
+			rmax[n_strips][i] = row_max;
+			rmask[n_strips][i] = (unsigned char)eq;
+			max_score = imax(max_score, row_max);
 			cells += nv < W ? nv : W;
 			pqb = qb;
 		}
 	}
-	// row-major order of the maximal cells (insertion sort of at most NC_MAX_CELLS ids)
-	if (c.n_max_cell <= NC_MAX_CELLS)
-		for (int a = 1; a < c.n_max_cell; ++a) {
-			const int v = c.max_cell[a];
-			int b = a - 1;
-			while (b >= 0 && c.max_cell[b] > v) {
-				c.max_cell[b + 1] = c.max_cell[b];
-				--b;
+	// max_ptr bookkeeping (nuc_cruc.cpp:517-537) after the fact: the cells that equal the maximum, in row-major order
+	for (int i = 1; i <= rows; ++i) {
+		const int cols = hairpin ? (max_stem - (i - 1)) : tlen;
+		for (int s = 0; s < n_strips; ++s) {
+			if (s * W + 1 > cols) break;
+			if (rmax[s][i] != max_score) continue;
+			unsigned int eq = rmask[s][i];
+			while (eq) {
+				int k = 0;
+				while (!((eq >> k) & 1u)) ++k;
+				eq &= eq - 1u;
+				if (c.n_max_cell < NC_MAX_CELLS) c.max_cell[c.n_max_cell] = i * NC_STRIDE + s * W + 1 + k;
+				++c.n_max_cell;
 			}
-			c.max_cell[b + 1] = v;
 		}
+	}
 	if (cells_out) *cells_out = cells;
 	return max_score;
 }

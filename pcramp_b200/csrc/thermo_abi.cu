@@ -157,7 +157,7 @@ __global__ void thermo_key_kernel(int op, uint32_t n, const uint8_t *__restrict_
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n) return;
 	const uint32_t q = len_a[p], t = (op == OP_HETERODIMER || op == OP_HETERODIMER_DIAG) ? len_b[p] : q;
-	key[p] = (uint16_t)((t << 6) | q); // columns (strips) first, then rows
+	key[p] = (uint16_t)(0xfffu - ((t << 6) | q)); // columns (strips) first, then rows; largest first, so that the last wave of CTAs is the cheapest
 	ord[p] = p;
 }
 
