@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=1000)
     ap.add_argument("--cpu-targets", type=int, default=96, help="targets in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: how the shards' bitsets are merged -- p2p = peer stores over NVLink fused into the tail of pair scoring "
+                         "(xchg.cuh, the product path); nccl = all-gather + pcramp_gpu_merge_shards (the baseline it replaces)")
     ap.add_argument("--dp-problems", type=int, default=262144, help="NucCruc problems per step of the DP GCUPS leg (0 = skip the leg)")
     ap.add_argument("--dp-cpu-problems", type=int, default=60000, help="problems in the bounded CPU sample of the DP leg")
     return ap.parse_args()
@@ -303,7 +306,9 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     factory = make_factory(a)
-    bounds = [a.targets * k // world for k in range(world + 1)]   # contiguous shards
+    from pcramp_b200.sharding import shard_bounds
+    p2p = world > 1 and a.exchange == "p2p"
+    bounds = shard_bounds(a.targets, world, align=32 if p2p else 1)   # contiguous shards; p2p: on bitset words
     shard_nseq = np.array([bounds[k + 1] - bounds[k] for k in range(world)], dtype=np.uint32)
     lo, hi = bounds[rank], bounds[rank + 1]
     coll = factory.collection(range(lo, hi))
@@ -321,7 +326,13 @@ def run_b200(a):
     n_words_local = (int(shard_nseq[rank]) + 31) // 32
     n_words_global = (a.targets + 31) // 32
     P = a.pairs
-    if world > 1:
+    if p2p:
+        g.exchange_create(rank, world, shard_nseq, P, None)
+        handles = [None] * world
+        dist.all_gather_object(handles, g.exchange_ipc_handle())
+        g.exchange_connect_ipc(handles)
+        dist.barrier()
+    elif world > 1:
         max_words = int(max((int(n) + 31) // 32 for n in shard_nseq))
         gat_any = torch.zeros((world, P * max_words), dtype=torch.int32, device="cuda")
         gat_p1 = torch.zeros((world, P * max_words), dtype=torch.int32, device="cuda")
@@ -372,7 +383,10 @@ def run_b200(a):
         g.select_words_staged(TARGET, thr, want_keys=False)   # keys() is only for hosts that walk the database themselves
         g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
         account(timed)
-        if world > 1:
+        if p2p:
+            g.exchange_step(TARGET)
+            launches[0] += 3 if timed else 0
+        elif world > 1:
             exchange()
 
     def step_e2e(b, timed):
@@ -380,6 +394,14 @@ def run_b200(a):
         if world == 1:
             g.select_words(TARGET, fb, rb, thr, want_keys=False)
             cov, bits = g.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR))
+            host_cov.numpy()[:] = cov
+            host_bits.numpy().view(np.uint32)[:] = bits
+        elif p2p:
+            g.stage_pairs(fb, rb)
+            g.select_words_staged(TARGET, thr, want_keys=False)
+            g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
+            g.exchange_step(TARGET)
+            cov, bits = g.exchange_fetch(P)
             host_cov.numpy()[:] = cov
             host_bits.numpy().view(np.uint32)[:] = bits
         else:
@@ -504,6 +526,8 @@ def run_b200(a):
             "data": "synthetic",
             "config": {"workload": workload_name(a), "targets": a.targets, "target_len": a.length, "pairs_per_step": P,
                        "seed_threshold": thr, "detect_threshold": float(TARGET_THR), "sharding": "targets, contiguous, %d shard(s)" % world,
+                       "exchange": ("none" if world == 1 else "peer stores over NVLink from the scoring stream + flag wait (xchg.cuh), no NCCL "
+                                    "on the data path" if p2p else "NCCL all-gather + pcramp_gpu_merge_shards"),
                        "l2": "inputs larger than L2 (%.0f MB of bit-planes per GPU)" % (coll.length.sum() / 2e6),
                        "db_entries_per_step": stats_acc["n_entries"] / n_scan, "hits_per_step": stats_acc["n_hits"] / n_scan},
             "clocks": clocks,
@@ -515,12 +539,15 @@ def run_b200(a):
     sys.stdout.flush()
     torch.cuda.synchronize()
     if world > 1:
-        del gat_any, gat_p1, packed_any, packed_p1, out_bits, out_cov
-        dist.barrier()
-        dist.destroy_process_group()
+        if not p2p:
+            del gat_any, gat_p1, packed_any, packed_p1, out_bits, out_cov
+        dist.barrier()                      # p2p: nobody frees its exchange buffer while a peer could still store into it
     del ext
     torch.cuda.empty_cache()
     g.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     os._exit(0)
 
 

@@ -172,6 +172,28 @@ int pcramp_gpu_merge_shards(pcramp_gpu_ctx *ctx, const void *d_any_gathered, con
 	uint32_t n_shards, const uint32_t *shard_nseq, const float *weight_all, uint32_t n_pairs, void *d_out_bits,
 	void *d_out_cov);
 
+/* The same exchange without NCCL and without leaving the library's stream (xchg.cuh): every rank owns a double-buffered
+ * global result (n_pairs x ceil(N/32) words) that its peers address over NVLink.  After pair scoring, one kernel stores the
+ * shard's bitset words into every rank's buffer and publishes a step flag, one waits for all ranks' flags, and the coverage
+ * kernels run on the merged bitsets.  Shards: contiguous, every shard but the last a multiple of 32 sequences.
+ *   create   once per run (rank, world <= 16, shard_nseq[world], largest batch, weights of ALL sequences or NULL = 1.0)
+ *   buffer / ipc_handle   this rank's buffer as a device pointer (contexts of one process) or a 64-byte cudaIpcMemHandle_t
+ *   connect  peers = world pointers (from_ipc = 0) or world x 64 bytes of handles gathered from all ranks (from_ipc = 1)
+ *   step     after pcramp_gpu_score_pairs_staged on this rank's shard; asynchronous
+ *   coverage / bitsets / words   device pointers + row pitch of the merged result;  fetch = host copies (synchronises, and
+ *            reports a rank that did not arrive within ~2 s instead of hanging) */
+int pcramp_gpu_exchange_create(pcramp_gpu_ctx *ctx, uint32_t rank, uint32_t world, const uint32_t *shard_nseq, uint32_t max_pairs,
+	const float *weight_all);
+void *pcramp_gpu_exchange_buffer(pcramp_gpu_ctx *ctx);
+int pcramp_gpu_exchange_ipc_handle(pcramp_gpu_ctx *ctx, void *handle64);
+int pcramp_gpu_exchange_connect(pcramp_gpu_ctx *ctx, const void *peers, int from_ipc);
+int pcramp_gpu_exchange_step(pcramp_gpu_ctx *ctx, int kind);
+void *pcramp_gpu_exchange_coverage(pcramp_gpu_ctx *ctx);
+void *pcramp_gpu_exchange_bitsets(pcramp_gpu_ctx *ctx);
+uint32_t pcramp_gpu_exchange_words(pcramp_gpu_ctx *ctx);
+int pcramp_gpu_exchange_fetch(pcramp_gpu_ctx *ctx, float *coverage, uint32_t *bitsets);
+int pcramp_gpu_exchange_destroy(pcramp_gpu_ctx *ctx);
+
 /* ---- K3: SantaLucia nearest-neighbour thermodynamics: replaces the NucCruc call surface pcramp uses
  *      (nuc_cruc.h:696-763 tm_pm_duplex / approximate_tm_hairpin, :775-838 salt / strand, :875-994 set_query /
  *      set_target; nuc_cruc.cpp:2236-2455 approximate_tm_{heterodimer,homodimer,hairpin}) for a BATCH of

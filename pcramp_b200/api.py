@@ -132,6 +132,16 @@ SIGNATURES = {
     "pcramp_gpu_device_bitsets_pass1": (ctypes.c_void_p, [ctypes.c_void_p]),
     "pcramp_gpu_merge_shards": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, _u32p, _f32p, ctypes.c_uint32,
                                                ctypes.c_void_p, ctypes.c_void_p]),
+    "pcramp_gpu_exchange_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.c_uint32, _f32p]),
+    "pcramp_gpu_exchange_buffer": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "pcramp_gpu_exchange_ipc_handle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pcramp_gpu_exchange_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "pcramp_gpu_exchange_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "pcramp_gpu_exchange_coverage": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "pcramp_gpu_exchange_bitsets": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "pcramp_gpu_exchange_words": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "pcramp_gpu_exchange_fetch": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
+    "pcramp_gpu_exchange_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pcramp_gpu_measure_int_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "pcramp_gpu_bitset_words": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_int]),
     "pcramp_gpu_fetch_results": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
@@ -397,6 +407,45 @@ class PcrampGpu:
             weight_all = np.ascontiguousarray(weight_all, dtype=np.float32)
         self._ck(self.lib.pcramp_gpu_merge_shards(self.h, d_any, d_pass1, len(shard_nseq), _ptr(shard_nseq, _u32p), _ptr(weight_all, _f32p),
                                                   int(n_pairs), d_out_bits, d_out_cov))
+
+    # ---- multi-GPU exchange over peer memory (xchg.cuh) ----------------------------------------
+    def exchange_create(self, rank, world, shard_nseq, max_pairs, weight_all=None):
+        sn = np.ascontiguousarray(shard_nseq, dtype=np.uint32)
+        w = None if weight_all is None else np.ascontiguousarray(weight_all, dtype=np.float32)
+        self._ck(self.lib.pcramp_gpu_exchange_create(self.h, int(rank), int(world), _ptr(sn, _u32p), int(max_pairs), _ptr(w, _f32p)))
+        self._xchg_world = int(world)
+
+    def exchange_buffer(self):
+        return self.lib.pcramp_gpu_exchange_buffer(self.h)
+
+    def exchange_ipc_handle(self):
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self.lib.pcramp_gpu_exchange_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def exchange_connect_pointers(self, pointers):
+        arr = (ctypes.c_void_p * len(pointers))(*[int(p) for p in pointers])
+        self._ck(self.lib.pcramp_gpu_exchange_connect(self.h, arr, 0))
+
+    def exchange_connect_ipc(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self._xchg_world
+        self._ck(self.lib.pcramp_gpu_exchange_connect(self.h, ctypes.create_string_buffer(blob, len(blob)), 1))
+
+    def exchange_step(self, kind):
+        self._ck(self.lib.pcramp_gpu_exchange_step(self.h, kind))
+
+    def exchange_pointers(self):
+        """(coverage, bitsets, words per row) of the merged result of the last step"""
+        return (self.lib.pcramp_gpu_exchange_coverage(self.h), self.lib.pcramp_gpu_exchange_bitsets(self.h),
+                int(self.lib.pcramp_gpu_exchange_words(self.h)))
+
+    def exchange_fetch(self, n_pairs):
+        words = int(self.lib.pcramp_gpu_exchange_words(self.h))
+        cov = np.zeros(n_pairs, np.float32)
+        bits = np.zeros((n_pairs, words), np.uint32)
+        self._ck(self.lib.pcramp_gpu_exchange_fetch(self.h, _ptr(cov, _f32p), _ptr(bits, _u32p)))
+        return cov, bits
 
     # ---- K3: nearest-neighbour thermodynamics -------------------------------------------------------
     def _thermo_args(self, op, seq_a, seq_b, strand_a, strand_b):

@@ -10,6 +10,7 @@
 #include <vector>
 
 struct pcramp_gpu_ctx;
+struct pcramp_gpu_xchg; // xchg.cuh
 namespace pcr {
 namespace nc {
 struct ThermoState; // thermo_abi.cu
@@ -123,6 +124,7 @@ struct pcramp_gpu_ctx {
 	unsigned long long *h_counters = nullptr; // pinned
 	pcramp_gpu_stats stats = {};
 	pcr::nc::ThermoState *thermo = nullptr; // K3 state, created on first use (thermo_abi.cu)
+	pcramp_gpu_xchg *xchg = nullptr;        // multi-GPU exchange state (xchg.cuh)
 	// multiplex terms of optimize() (multiplex.cuh): unique words of the multiplex background, the assay pool
 	DevBuf mpx_words, mpx_planes, mpx_items, mpx_item_off, mpx_base, mpx_var, mpx_bidx, mpx_cov, mpx_pool, mpx_ov_words, mpx_ov;
 	uint64_t mpx_n_keys = 0;

@@ -377,6 +377,7 @@ void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx)
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	nc::thermo_state_free(ctx->thermo);
 	ctx->thermo = nullptr;
+	pcramp_gpu_exchange_destroy(ctx);
 	cudaStream_t s = ctx->stream;
 	delete ctx;
 	cudaStreamDestroy(s);
@@ -1570,5 +1571,6 @@ float pcramp_word_max_overlap(const uint64_t a[2], const uint64_t b[2])
 } // extern "C"
 
 #include "sw_abi.cuh" // K4: Smith-Waterman batches, find_background_match, find_multiplex_background_match
+#include "xchg.cuh" // multi-GPU: peer-memory exchange of the shards' bitsets fused into the tail of pair scoring
 #include "multiplex.cuh" // the multiplex terms of optimize(): multiplex background keys / coverage, pool overlap
 #include "optimize_abi.cuh" // optimize() and its moves for a batch of trials
