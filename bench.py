@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=1000)
     ap.add_argument("--cpu-targets", type=int, default=96, help="targets in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="pairs", choices=["pairs", "targets"],
+                    help="N>1: pairs = every GPU holds all targets and scores its own batches of the sweep (no data-path exchange, the "
+                         "headline); targets = the sequences are split across the GPUs, every GPU scores the same batch and the shards' "
+                         "bitsets are exchanged (one design iteration at minimum latency; also measured, as `target_sharded`, in pairs mode)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the shards' bitsets are merged -- p2p = peer stores over NVLink fused into the tail of pair scoring "
                          "(xchg.cuh, the product path); nccl = all-gather + pcramp_gpu_merge_shards (the baseline it replaces)")
@@ -288,6 +292,64 @@ class DevArray:
         self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2}
 
 
+def target_sharded_leg(a, factory, rank, world, local, dist, torch, thr):
+    """N>1, second arrangement: the targets are split across the GPUs (contiguous shards on bitset-word boundaries), every GPU scores
+    the SAME batch on its shard and the shards' bitsets are merged over peer memory (xchg.cuh) -- what one design iteration of pcramp
+    needs (its 1000 trials against all targets at minimum latency).  value = pairs x ALL targets / max-over-ranks time."""
+    from pcramp_b200 import PcrampGpu, TARGET, synth
+    from pcramp_b200.sharding import shard_bounds
+    P = a.pairs
+    bounds = shard_bounds(a.targets, world, align=32)
+    sizes = np.array([bounds[k + 1] - bounds[k] for k in range(world)], dtype=np.uint32)
+    coll = factory.collection(range(bounds[rank], bounds[rank + 1]))
+    steps, warm = a.steps, 2
+    f, r = synth.make_pairs(5, factory, P * (steps + warm))
+    g = PcrampGpu(local)
+    try:
+        g.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
+        g.exchange_create(rank, world, sizes, P, None)
+        handles = [None] * world
+        dist.all_gather_object(handles, g.exchange_ipc_handle())
+        g.exchange_connect_ipc(handles)
+        g.stage_pairs(f, r)
+        ext = torch.cuda.ExternalStream(g.stream, device=local)
+
+        def step(b):
+            g.set_batch(b * P, P)
+            g.select_words_staged(TARGET, thr, want_keys=False)
+            g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
+            g.exchange_step(TARGET)
+
+        for b in range(warm):
+            step(b)
+        g.exchange_fetch(P)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for b in range(warm, warm + steps):
+            step(b)
+        e1.record(ext)
+        cov, bits = g.exchange_fetch(P)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        chk = torch.tensor([float(cov.sum()), float(np.unpackbits(bits.view(np.uint8)).sum())], device="cuda", dtype=torch.float64)
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        same = bool((lo_ == hi_).all().item())      # every rank must hold the same merged result
+        dist.barrier()
+        del ext
+    finally:
+        g.close()
+    return {"value": float(P) * a.targets * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "scaling": "strong",
+            "shards": [int(x) for x in sizes], "exchange": "peer stores over NVLink + flag wait (xchg.cuh)", "ranks_agree": same,
+            "detected_bits_last_step": int(chk[1].item())}
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -307,14 +369,20 @@ def run_b200(a):
 
     factory = make_factory(a)
     from pcramp_b200.sharding import shard_bounds
-    p2p = world > 1 and a.exchange == "p2p"
-    bounds = shard_bounds(a.targets, world, align=32 if p2p else 1)   # contiguous shards; p2p: on bitset words
-    shard_nseq = np.array([bounds[k + 1] - bounds[k] for k in range(world)], dtype=np.uint32)
-    lo, hi = bounds[rank], bounds[rank + 1]
+    by_targets = world > 1 and a.shard == "targets"
+    p2p = by_targets and a.exchange == "p2p"
+    if by_targets:
+        bounds = shard_bounds(a.targets, world, align=32 if p2p else 1)   # contiguous shards; p2p: on bitset words
+        shard_nseq = np.array([bounds[k + 1] - bounds[k] for k in range(world)], dtype=np.uint32)
+        lo, hi = bounds[rank], bounds[rank + 1]
+    else:                                                                 # one GPU, or the pair-sharded sweep: every rank holds every target
+        shard_nseq = np.array([a.targets] * world, dtype=np.uint32)
+        lo, hi = 0, a.targets
     coll = factory.collection(range(lo, hi))
     total = a.steps + a.warmup
     n_batches = total + a.steps + 1                                # resident (warm-up + timed) then e2e (1 warm-up + timed)
-    f_all, r_all = synth.make_pairs(5, factory, a.pairs * n_batches)
+    # target-sharded: every rank scores the SAME batches; pair-sharded: every rank has its own slice of the sweep
+    f_all, r_all = synth.make_pairs(5 if by_targets else 5 + 1000 * rank, factory, a.pairs * n_batches)
     f_pin = torch.from_numpy(f_all.view(np.int64)).pin_memory()
     r_pin = torch.from_numpy(r_all.view(np.int64)).pin_memory()
     f_host, r_host = f_pin.numpy().view(np.uint64), r_pin.numpy().view(np.uint64)
@@ -332,7 +400,7 @@ def run_b200(a):
         dist.all_gather_object(handles, g.exchange_ipc_handle())
         g.exchange_connect_ipc(handles)
         dist.barrier()
-    elif world > 1:
+    elif by_targets:
         max_words = int(max((int(n) + 31) // 32 for n in shard_nseq))
         gat_any = torch.zeros((world, P * max_words), dtype=torch.int32, device="cuda")
         gat_p1 = torch.zeros((world, P * max_words), dtype=torch.int32, device="cuda")
@@ -386,12 +454,12 @@ def run_b200(a):
         if p2p:
             g.exchange_step(TARGET)
             launches[0] += 3 if timed else 0
-        elif world > 1:
+        elif by_targets:
             exchange()
 
     def step_e2e(b, timed):
         fb, rb = f_host[b * P:(b + 1) * P], r_host[b * P:(b + 1) * P]
-        if world == 1:
+        if not by_targets:
             g.select_words(TARGET, fb, rb, thr, want_keys=False)
             cov, bits = g.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR))
             host_cov.numpy()[:] = cov
@@ -449,7 +517,10 @@ def run_b200(a):
         int_peak = g.measure_int_peak() if rank == 0 else 0.0
         dp = dp_leg(a, g, torch, ext, rank, world, dist if world > 1 else None) if a.dp_problems > 0 else None
 
-    evals_per_step = float(P) * a.targets
+    evals_per_step = float(P) * a.targets * (1 if by_targets else world)   # pair-sharded: every rank completes its own batch per step
+    tsh = None
+    if world > 1 and not by_targets:
+        tsh = target_sharded_leg(a, factory, rank, world, local, dist, torch, thr)
     value = evals_per_step * a.steps / (ms_resident * 1e-3)
     e2e_value = evals_per_step * a.steps / (ms_e2e * 1e-3)
 
@@ -518,15 +589,17 @@ def run_b200(a):
             cpu_baseline = {"value": P * a.cpu_targets / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
                             "sample": "one step of %d pairs x %d of the %d targets (every %d-th target)" % (
                                 P, a.cpu_targets, a.targets, max(1, a.targets // a.cpu_targets))}
-        h2d = 2 * P * 16
-        d2h = P * 4 + P * n_words_global * 4
+        jobs = 1 if by_targets else world                  # pair-sharded: every rank moves its own batch
+        h2d = 2 * P * 16 * jobs
+        d2h = (P * 4 + P * n_words_global * 4) * jobs
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_resident / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "ms_per_step": ms_resident / a.steps, "higher_is_better": True, "scaling": "strong" if (by_targets or world == 1) else "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "targets": a.targets, "target_len": a.length, "pairs_per_step": P,
-                       "seed_threshold": thr, "detect_threshold": float(TARGET_THR), "sharding": "targets, contiguous, %d shard(s)" % world,
-                       "exchange": ("none" if world == 1 else "peer stores over NVLink from the scoring stream + flag wait (xchg.cuh), no NCCL "
+                       "seed_threshold": thr, "detect_threshold": float(TARGET_THR), "sharding": ("targets, contiguous, %d shard(s); every GPU scores the same batch" % world) if (by_targets or world == 1) else
+                       ("pairs: %d GPUs x all %d targets, each GPU scores its own batch of %d pairs per step" % (world, a.targets, P)),
+                       "exchange": ("none" if not by_targets else "peer stores over NVLink from the scoring stream + flag wait (xchg.cuh), no NCCL "
                                     "on the data path" if p2p else "NCCL all-gather + pcramp_gpu_merge_shards"),
                        "l2": "inputs larger than L2 (%.0f MB of bit-planes per GPU)" % (coll.length.sum() / 2e6),
                        "db_entries_per_step": stats_acc["n_entries"] / n_scan, "hits_per_step": stats_acc["n_hits"] / n_scan},
@@ -534,12 +607,12 @@ def run_b200(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_resident,
             "breakdown_ms_per_step": {k: stats_acc[k] / n_scan for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score")},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp}))
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp, "target_sharded": tsh}))
     # teardown order matters: torch tensors that were used on the library's stream must die before the stream does
     sys.stdout.flush()
     torch.cuda.synchronize()
     if world > 1:
-        if not p2p:
+        if by_targets and not p2p:
             del gat_any, gat_p1, packed_any, packed_p1, out_bits, out_cov
         dist.barrier()                      # p2p: nobody frees its exchange buffer while a peer could still store into it
     del ext
