@@ -70,19 +70,77 @@ def make_factory(a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  The timed region is a few
+    tens of milliseconds, so the samples come from NVML in a thread (one every ~2 ms); `nvidia-smi -lms` is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.rows = []
+        self.rows = []          # nvidia-smi rows
+        self.samples = []       # NVML: (sm MHz, power W, reasons bitmask)
         self.proc = None
         self.device = device
+        self.nvml = None
+        self.handle = None
+        self.sm_max = None
+        self.running = False
+        self.source = None
+
+    def _nvml_open(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.device])
+                except (ValueError, IndexError):
+                    pass
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self._nvml_sample()
+            return True
+        except Exception:
+            self.nvml = None
+            return False
+
+    def _nvml_sample(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        except Exception:
+            pw = None
+        try:
+            rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            try:
+                rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                rs = 0
+        return sm, pw, rs
+
+    def _nvml_loop(self):
+        while self.running:
+            try:
+                self.samples.append(self._nvml_sample())
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        if self._nvml_open():
+            self.source = "nvml"
+            self.running = True
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.source = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -93,6 +151,22 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.source == "nvml":
+            self.running = False
+            self.thread.join(timeout=2)
+            n = self.nvml
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}   # nvml.h reasons
+            sm = [x[0] for x in self.samples]
+            pw = [x[1] for x in self.samples if x[1] is not None]
+            allr = 0
+            for x in self.samples:
+                allr |= x[2]
+            try:
+                n.nvmlShutdown()
+            except Exception:
+                pass
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max, "power_w_max": max(pw) if pw else None,
+                    "samples": len(sm), "reasons": sorted(k for k, b in bits.items() if allr & b), "source": "nvml, one sample / ~2 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -115,7 +189,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # --------------------------------------------------------------------------------------------------
