@@ -238,12 +238,27 @@ __device__ __forceinline__ uint32_t index_mask(const uint4 &en, const uint4 &B, 
 	return (B.x & ~t1 & ~t0) | (B.y & ~t1 & t0) | (B.z & t1 & ~t0) | (B.w & t1 & t0);
 }
 
-// Append the candidates among N entries per lane with ONE atomic per warp: candidates are sparse (~2 % of the entries), so
-// per-candidate atomics on the single counter arrive one lane at a time and serialise in L2 -- that, not HBM, was the
-// kernel's limit.  All 32 lanes must call this together.
+// Append the candidates among N entries per lane.  Candidates are sparse (~2 % of the entries) but nearly every batch of 256
+// entries holds one, so even ONE atomic per warp per batch is 6 x 10^5 read-modify-writes of a single counter per launch, and
+// those serialise in L2 at ~1 ns each -- that, not HBM, was the kernel's limit (0.64 ms).  A warp therefore reserves
+// IDX_BLOCK slots at a time and fills them over many batches; what it leaves unused is marked invalid (gpos = ~0) for
+// index_hits_kernel to skip.  `cs.count` counts reserved slots.  All 32 lanes must call this together.
+constexpr uint32_t IDX_BLOCK = 512;
+constexpr uint32_t IDX_INVALID = 0xFFFFFFFFu;
+
+struct IdxWarpBlock { // uniform over the warp
+	uint32_t base = 0, used = IDX_BLOCK; // used == IDX_BLOCK: nothing reserved yet
+};
+
+__device__ __forceinline__ void index_block_pad(const IdxCandSink &cs, const IdxWarpBlock &wb, uint32_t lane)
+{ // mark [base + used, base + IDX_BLOCK) invalid
+	for (uint32_t k = wb.used + lane; k < IDX_BLOCK; k += 32u)
+		if (wb.base + k < cs.cap) cs.buf[wb.base + k].gpos = IDX_INVALID;
+}
+
 template <int N>
 __device__ __forceinline__ void index_append(const uint4 (&e)[N], uint32_t valid, const uint4 &B, uint32_t thr, uint32_t sh, const IdxQuery &qy,
-	const IdxCandSink &cs, uint32_t lane)
+	const IdxCandSink &cs, uint32_t lane, IdxWarpBlock &wb)
 {
 	uint32_t hits = 0u; // bit u: entry u of this lane is a candidate
 	#pragma unroll
@@ -257,22 +272,28 @@ __device__ __forceinline__ void index_append(const uint4 (&e)[N], uint32_t valid
 		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
 		if ((int)lane >= o) incl += v;
 	}
-	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-	unsigned int base = 0;
-	if (lane == 0u) base = atomicAdd(cs.count, total);
-	base = __shfl_sync(0xffffffffu, base, 0) + (incl - mine);
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31); // <= 32 N <= 256 < IDX_BLOCK
+	if (wb.used + total > IDX_BLOCK) {
+		if (wb.used < IDX_BLOCK) index_block_pad(cs, wb, lane);
+		unsigned int b = 0;
+		if (lane == 0u) b = atomicAdd(cs.count, IDX_BLOCK);
+		wb.base = __shfl_sync(0xffffffffu, b, 0);
+		wb.used = 0u;
+	}
+	uint32_t at = wb.base + wb.used + (incl - mine);
+	wb.used += total;
 	#pragma unroll
 	for (int u = 0; u < N; ++u)
 		if ((hits >> u) & 1u) {
-			if (base < cs.cap) {
+			if (at < cs.cap) {
 				IdxCand c;
 				c.gpos = e[u].x;
 				c.m = index_mask(e[u], B, sh);
 				c.pid = qy.pid;
 				c.seg = qy.seg;
-				cs.buf[base] = c;
+				cs.buf[at] = c;
 			}
-			++base;
+			++at;
 		}
 }
 
@@ -294,6 +315,7 @@ scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsi
 	const uint32_t nq = *n_queries;
 	if (warp >= nq) return;
 	IdxQuery qy = queries[warp];
+	IdxWarpBlock wb;
 	for (uint32_t q = warp; q < nq; q += n_warps) {
 		const IdxQuery cur = qy;
 		if (q + n_warps < nq) qy = queries[q + n_warps]; // next descriptor in flight while this range streams
@@ -306,7 +328,7 @@ scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsi
 			uint4 e[8];
 			#pragma unroll
 			for (int u = 0; u < 8; ++u) e[u] = ldg_stream(ix.entries + i + 32u * u + lane);
-			index_append<8>(e, 0xFFu, B, thr, sh, cur, cs, lane);
+			index_append<8>(e, 0xFFu, B, thr, sh, cur, cs, lane, wb);
 		}
 		for (; i < cur.hi; i += 128u) {
 			uint4 e[4];
@@ -320,9 +342,10 @@ scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsi
 					valid |= 1u << u;
 				}
 			}
-			index_append<4>(e, valid, B, thr, sh, cur, cs, lane);
+			index_append<4>(e, valid, B, thr, sh, cur, cs, lane, wb);
 		}
 	}
+	if (wb.used < IDX_BLOCK) index_block_pad(cs, wb, lane);
 }
 
 // place each candidate in its sequence, drop what other kernels own, report once
@@ -333,6 +356,7 @@ index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__res
 	const uint32_t total = min(*cs.count, cs.cap);
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
 		const IdxCand c = cs.buf[i];
+		if (c.gpos == IDX_INVALID) continue; // the unused tail of a warp's block
 		const uint32_t o = c.seg & 255u, si = c.seg >> 16;
 		const uint32_t seq = idx_seq_of(ix.cum, sd.n, c.gpos);
 		const int64_t x = (int64_t)(c.gpos - __ldg(ix.cum + seq)) - (int64_t)o; // text index of primer base 0
