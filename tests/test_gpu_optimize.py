@@ -17,6 +17,12 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def prepare(gpu, case):
+    # the multiplex terms of optimize() read library state (multiplex key list, assay pool): start every case from "first assay of a run"
+    from pcramp_b200 import MULTIPLEX
+    none = np.zeros((0, 2), np.uint64)
+    gpu.upload_sequences(MULTIPLEX, np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32))
+    gpu.multiplex_keys()
+    gpu.set_pool(none, none)
     gpu.upload_sequences(TARGET, case.targets.nibbles, case.targets.byte_off, case.targets.length, case.targets.weight)
     gpu.select_words(TARGET, case.f, case.r, case.target_search, optimize_5=case.optimize_5, optimize_3=case.optimize_3)
     if case.background is not None:
