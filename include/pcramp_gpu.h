@@ -124,6 +124,29 @@ int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r, uint32_t 
 	const pcramp_gpu_optimize_options *options, float *target_coverage, float *background_coverage, float *oligo_overlap,
 	uint32_t *iterations);
 
+/* ---- FASTA ingest on the device (fasta.cuh): parse_fasta (parse_fasta.cpp:9-89) + Sequence::operator=(deque<char>)
+ *      (sequence.cpp:43-71, base_to_bits base_table.h:30-76) + Sequence::defline / extract_weight (sequence.h:190-200,
+ *      sequence.cpp:332-493) for the INFLATED text of n_files FASTA files (zlib stays with the host).  The host part splits the
+ *      text into the reference's gzgets chunks and records (a chunk holding '>' is a defline) and evaluates deflines, weights
+ *      ("[w=...]") and the ignore list (lower-case substrings, ignore_record parse_fasta.cpp:171-188); the device maps the residue
+ *      characters to nibbles, drops white space and packs two bases per byte.  Records outside [min_length, max_length] or
+ *      ignored are dropped as the reference does; an unknown symbol in a kept record is the reference's "Illegal base" error.
+ *      The collection `kind` is replaced, exactly as if pcramp_gpu_upload_sequences had been called with the result. ------- */
+int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, const char *const *text, const uint64_t *bytes,
+	uint64_t min_length, uint64_t max_length, uint32_t n_ignore, const char *const *ignore, uint32_t *n_records);
+/* per sequence of that upload: source file, defline as (offset, length) into the file's text, length, weight (any may be NULL) */
+int pcramp_gpu_fasta_records(pcramp_gpu_ctx *ctx, int kind, uint32_t *file, uint64_t *defline_off, uint32_t *defline_len,
+	uint32_t *length, float *weight);
+void pcramp_gpu_fasta_free(pcramp_gpu_ctx *ctx);
+/* host-only view of the record split of ONE file (before the length window / ignore list): returns the number of records and
+ * fills at most cap entries of each non-NULL array */
+uint32_t pcramp_fasta_scan(const char *text, uint64_t bytes, uint32_t cap, uint64_t *defline_off, uint32_t *defline_len,
+	uint64_t *begin, uint64_t *end, float *weight);
+/* a collection as the reference stores it (sequence.h:85,223-228): count, size of the nibble array, per sequence byte offset and
+ * length, the packed nibbles (any output may be NULL) */
+int pcramp_gpu_sequences_copy(pcramp_gpu_ctx *ctx, int kind, uint32_t *n, uint64_t *total_bytes, uint64_t *byte_off, uint32_t *length,
+	uint8_t *nibbles);
+
 /* ---- the multiplex terms of optimize() ---------------------------------------------------------------------
  * pcramp_gpu_multiplex_keys: main.cpp:989-1003 -- every sequence of the PCRAMP_MULTIPLEX collection (the amplicons of
  * the assays chosen so far) is pack()ed whole (no select_words, no G+C filter) and keys() (pcramp.h:231-256) of the

@@ -193,6 +193,38 @@ long ref_pack_all(void *h, uint32_t pack_max_degen, uint32_t min_len)
 	return n;
 }
 
+// parse_fasta (parse_fasta.cpp:9-89) of the listed files into the context's sequences (appending, as main.cpp:255-268 does file
+// after file).  `ignore`: n_ignore NUL-terminated lower-case strings, back to back.  Returns the number of sequences or -1.
+long ref_parse_fasta(void *h, int n_files, const char *const *paths, uint64_t min_len, uint64_t max_len, int n_ignore, const char *ignore)
+{
+	RefCtx *c = (RefCtx *)h;
+	long n = -1;
+	guarded(c, [&]() {
+		deque<string> ig;
+		const char *p = ignore;
+		for (int i = 0; i < n_ignore; ++i) {
+			ig.push_back(string(p));
+			p += ig.back().size() + 1;
+		}
+		c->seq.clear();
+		for (int f = 0; f < n_files; ++f) parse_fasta(paths[f], c->seq, min_len, max_len, ig);
+		n = (long)c->seq.size();
+	});
+	return n;
+}
+
+// length, weight and nibbles (one per byte, Sequence::operator[]) of sequence i; nibbles may be NULL
+long ref_sequence_get(void *h, uint32_t i, float *weight, uint8_t *nibbles)
+{
+	RefCtx *c = (RefCtx *)h;
+	if (i >= c->seq.size()) return -1;
+	const Sequence &q = c->seq[i];
+	if (weight) *weight = q.weight();
+	if (nibbles)
+		for (size_t k = 0; k < q.length(); ++k) nibbles[k] = q[(unsigned int)k];
+	return (long)q.length();
+}
+
 long ref_db_size(void *h) { return (long)((RefCtx *)h)->db.size(); }
 long ref_num_keys(void *h) { return (long)((RefCtx *)h)->db_keys.size(); }
 

@@ -115,6 +115,12 @@ SIGNATURES = {
                                                  ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _u32p]),
     "pcramp_gpu_optimize": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32, _i32p, ctypes.c_uint32, ctypes.c_void_p, _f32p, _f32p,
                                            _f32p, _u32p]),
+    "pcramp_gpu_upload_fasta": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _u64p, ctypes.c_uint64,
+                                               ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _u32p]),
+    "pcramp_gpu_fasta_records": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u32p, _u64p, _u32p, _u32p, _f32p]),
+    "pcramp_gpu_fasta_free": (None, [ctypes.c_void_p]),
+    "pcramp_fasta_scan": (ctypes.c_uint32, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32, _u64p, _u32p, _u64p, _u64p, _f32p]),
+    "pcramp_gpu_sequences_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u32p, _u64p, _u64p, _u32p, _u8p]),
     "pcramp_gpu_multiplex_keys": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, _u64p]),
     "pcramp_gpu_multiplex_keys_copy": (ctypes.c_int, [ctypes.c_void_p, _u64p]),
     "pcramp_gpu_set_pool": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, ctypes.c_uint32]),
@@ -340,6 +346,31 @@ class PcrampGpu:
         self._ck(self.lib.pcramp_gpu_optimize(self.h, _ptr(f, _u64p), _ptr(r, _u64p), n, _ptr(mv, _i32p), len(mv), ctypes.byref(options),
                                               _ptr(tc, _f32p), _ptr(bc, _f32p), _ptr(ov, _f32p), _ptr(it, _u32p)))
         return f, r, tc, bc, ov, it
+
+    # ---- FASTA ingest on the device (fasta.cuh) ------------------------------------------------
+    def upload_fasta(self, kind, texts, min_length=0, max_length=1 << 40, ignore=()):
+        """texts: list of bytes (inflated FASTA files, in order) -> [(file, defline bytes, length, weight)] of the kept records"""
+        blobs = [bytes(t) for t in texts]
+        arr = (ctypes.c_char_p * max(1, len(blobs)))(*blobs)
+        nb = np.array([len(b) for b in blobs], np.uint64)
+        ig = [x.encode() for x in ignore]
+        iga = (ctypes.c_char_p * max(1, len(ig)))(*ig)
+        n = np.zeros(1, np.uint32)
+        self._ck(self.lib.pcramp_gpu_upload_fasta(self.h, kind, len(blobs), arr, _ptr(nb, _u64p), int(min_length), int(max_length), len(ig), iga,
+                                                  _ptr(n, _u32p)))
+        n = int(n[0])
+        self.n_seq[kind] = n
+        f, off, dl, ln, w = np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        self._ck(self.lib.pcramp_gpu_fasta_records(self.h, kind, _ptr(f, _u32p), _ptr(off, _u64p), _ptr(dl, _u32p), _ptr(ln, _u32p), _ptr(w, _f32p)))
+        return [(int(f[i]), blobs[int(f[i])][int(off[i]):int(off[i]) + int(dl[i])], int(ln[i]), float(w[i])) for i in range(n)]
+
+    def sequences_copy(self, kind):
+        """the collection as the reference stores it -> (byte_off uint64[n], length uint32[n], nibbles uint8[total])"""
+        n, tot = np.zeros(1, np.uint32), np.zeros(1, np.uint64)
+        self._ck(self.lib.pcramp_gpu_sequences_copy(self.h, kind, _ptr(n, _u32p), _ptr(tot, _u64p), None, None, None))
+        off, ln, nib = np.zeros(int(n[0]), np.uint64), np.zeros(int(n[0]), np.uint32), np.zeros(max(1, int(tot[0])), np.uint8)
+        self._ck(self.lib.pcramp_gpu_sequences_copy(self.h, kind, None, None, _ptr(off, _u64p), _ptr(ln, _u32p), _ptr(nib, _u8p)))
+        return off, ln, nib[:int(tot[0])]
 
     # ---- the multiplex terms of optimize() ---------------------------------------------------
     def multiplex_keys(self, pack_max_degen=256, min_oligo_length=18):

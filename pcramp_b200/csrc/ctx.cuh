@@ -11,6 +11,7 @@
 
 struct pcramp_gpu_ctx;
 struct pcramp_gpu_xchg; // xchg.cuh
+struct pcramp_gpu_fasta; // fasta.cuh
 namespace pcr {
 namespace nc {
 struct ThermoState; // thermo_abi.cu
@@ -125,6 +126,7 @@ struct pcramp_gpu_ctx {
 	pcramp_gpu_stats stats = {};
 	pcr::nc::ThermoState *thermo = nullptr; // K3 state, created on first use (thermo_abi.cu)
 	pcramp_gpu_xchg *xchg = nullptr;        // multi-GPU exchange state (xchg.cuh)
+	pcramp_gpu_fasta *fasta[PCRAMP_NUM_KINDS] = {}; // record table of the last FASTA upload per collection (fasta.cuh)
 	// multiplex terms of optimize() (multiplex.cuh): unique words of the multiplex background, the assay pool
 	DevBuf mpx_words, mpx_planes, mpx_items, mpx_item_off, mpx_base, mpx_var, mpx_bidx, mpx_cov, mpx_pool, mpx_ov_words, mpx_ov;
 	uint64_t mpx_n_keys = 0;

@@ -378,6 +378,7 @@ void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx)
 	nc::thermo_state_free(ctx->thermo);
 	ctx->thermo = nullptr;
 	pcramp_gpu_exchange_destroy(ctx);
+	pcramp_gpu_fasta_free(ctx);
 	cudaStream_t s = ctx->stream;
 	delete ctx;
 	cudaStreamDestroy(s);
@@ -391,6 +392,8 @@ int pcramp_gpu_synchronize(pcramp_gpu_ctx *ctx)
 	CK(cudaStreamSynchronize(ctx->stream));
 	return 0;
 }
+
+int upload_finish(pcramp_gpu_ctx *ctx, pcr::SeqSet &s, const uint8_t *nibbles, const std::vector<uint32_t> &with_eos);
 
 int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const uint8_t *nibbles, const uint64_t *byte_off,
 	const uint32_t *len, const float *weight)
@@ -449,6 +452,14 @@ int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const
 		if (len[i] & 1u) s.eos[i].push_back(len[i]); // the pad nibble pack() also pushes (seqdev.cuh)
 		s.grp_off[i + 1] = s.grp_off[i] + ((uint64_t)s.clen[i] + 31) / 32 + 1;
 	}
+	return upload_finish(ctx, s, nibbles, with_eos);
+}
+
+// device side of an upload: metadata to HBM, nibbles -> bit-planes, EOS compaction, dirty groups, tiles.  host_nibbles == NULL:
+// d_raw already holds the packed nibbles (the FASTA ingest path packs them on the device, fasta.cuh).
+int upload_finish(pcramp_gpu_ctx *ctx, SeqSet &s, const uint8_t *nibbles, const std::vector<uint32_t> &with_eos)
+{
+	const uint32_t n = s.n;
 	s.n_groups = s.grp_off[n];
 	CK(s.d_raw.ensure(std::max<uint64_t>(16, s.raw_bytes)));
 	CK(s.d_raw_off.ensure(std::max<size_t>(1, n) * 8));
@@ -459,7 +470,7 @@ int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const
 	CK(s.d_active.ensure(std::max<size_t>(1, n)));
 	CK(s.d_grp_off.ensure((size_t)(n + 1) * 8));
 	CK(s.d_planes.ensure(std::max<uint64_t>(1, s.n_groups) * 16));
-	if (s.raw_bytes) CK(cudaMemcpyAsync(s.d_raw.p, nibbles, s.raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (s.raw_bytes && nibbles) CK(cudaMemcpyAsync(s.d_raw.p, nibbles, s.raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
 	if (n) {
 		CK(cudaMemcpyAsync(s.d_raw_off.p, s.raw_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
 		CK(cudaMemcpyAsync(s.d_len.p, s.len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1571,6 +1582,7 @@ float pcramp_word_max_overlap(const uint64_t a[2], const uint64_t b[2])
 } // extern "C"
 
 #include "sw_abi.cuh" // K4: Smith-Waterman batches, find_background_match, find_multiplex_background_match
+#include "fasta.cuh" // FASTA text -> device-resident collection (parse_fasta + Sequence packing)
 #include "xchg.cuh" // multi-GPU: peer-memory exchange of the shards' bitsets fused into the tail of pair scoring
 #include "multiplex.cuh" // the multiplex terms of optimize(): multiplex background keys / coverage, pool overlap
 #include "optimize_abi.cuh" // optimize() and its moves for a batch of trials

@@ -200,7 +200,30 @@ def multiplex_optimize_kats(ref_factory):
     return rec
 
 
+def fasta_kats(ref):
+    """parse_fasta + Sequence packing of the reference on the texts of tests/fasta_cases.py"""
+    import tempfile
+    from tests import fasta_cases
+    rec = {}
+    for case in fasta_cases.cases():
+        with tempfile.TemporaryDirectory() as d:
+            paths = []
+            for k, blob in enumerate(case.files):
+                paths.append(os.path.join(d, "f%d.fa" % k))
+                open(paths[-1], "wb").write(blob)
+            seqs = ref.parse_fasta(paths, case.min_len, case.max_len, case.ignore)
+        rec["%s_len" % case.name] = np.array([s[0] for s in seqs], np.uint32)
+        rec["%s_weight" % case.name] = np.array([s[1] for s in seqs], np.float32)
+        rec["%s_nibbles" % case.name] = np.concatenate([s[2] for s in seqs]) if seqs else np.zeros(0, np.uint8)
+        print("fasta %-16s records %3d  bases %7d  weights %s" % (case.name, len(seqs), int(sum(s[0] for s in seqs)),
+                                                                 sorted(set(s[1] for s in seqs))))
+    return rec
+
+
 def main():
+    if "--fasta-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "kat_fasta.npz"), **fasta_kats(RefLib()))
+        return
     if "--multiplex-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "kat_optimize_multiplex.npz"), **multiplex_optimize_kats(RefLib))
         return
@@ -216,6 +239,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_background.npz"), **background_kats(ref))
     np.savez_compressed(os.path.join(HERE, "kat_optimize.npz"), **optimize_kats(RefLib))
     np.savez_compressed(os.path.join(HERE, "kat_optimize_multiplex.npz"), **multiplex_optimize_kats(RefLib))
+    np.savez_compressed(os.path.join(HERE, "kat_fasta.npz"), **fasta_kats(RefLib()))
     print("wrote fixtures to", HERE)
 
 

@@ -420,6 +420,24 @@ class RefLib(_Base):
         a, b = _w(a), _w(b)
         return np.array([fn(_p(a[i], _u64p), _p(b[i], _u64p)) for i in range(len(a))], np.float32)
 
+    def parse_fasta(self, paths, min_len=0, max_len=1 << 40, ignore=()):
+        """the reference's parse_fasta over the files, in order -> [(length, weight, nibbles uint8[length])]"""
+        fn = self._fn("parse_fasta", ctypes.c_long, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint64, ctypes.c_uint64,
+                                                     ctypes.c_int, ctypes.c_char_p])
+        get = self._fn("sequence_get", ctypes.c_long, [ctypes.c_void_p, ctypes.c_uint32, _f32p, _u8p])
+        arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
+        ig = b"".join(x.encode() + b"\0" for x in ignore)
+        n = fn(self.h, len(paths), arr, int(min_len), int(max_len), len(ignore), ig)
+        assert n >= 0, self.f_err(self.h)
+        out = []
+        for i in range(n):
+            w = np.zeros(1, np.float32)
+            ln = get(self.h, i, _p(w, _f32p), None)
+            nib = np.zeros(max(ln, 1), np.uint8)
+            get(self.h, i, _p(w, _f32p), _p(nib, _u8p))
+            out.append((int(ln), float(w[0]), nib[:ln].copy()))
+        return out
+
     def pack_all(self, pack_max_degen=256, min_oligo_length=18):
         """the multiplex background database of main.cpp:989-1003 (every sequence packed whole) -> its keys"""
         n = self.f_pack_all(self.h, pack_max_degen, min_oligo_length)

@@ -21,7 +21,7 @@ def lib():
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "pcramp_gpu.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(pcramp_(?:gpu|word)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(pcramp_(?:gpu|word|fasta)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_are_exported(lib):
