@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the shards' bitsets are merged -- p2p = peer stores over NVLink fused into the tail of pair scoring "
                          "(xchg.cuh, the product path); nccl = all-gather + pcramp_gpu_merge_shards (the baseline it replaces)")
+    ap.add_argument("--fasta-targets", type=int, default=8000, help="sequences in the FASTA-ingest leg (0 = skip; rank 0 only)")
     ap.add_argument("--dp-problems", type=int, default=262144, help="NucCruc problems per step of the DP GCUPS leg (0 = skip the leg)")
     ap.add_argument("--dp-cpu-problems", type=int, default=60000, help="problems in the bounded CPU sample of the DP leg")
     return ap.parse_args()
@@ -270,6 +271,85 @@ def dp_problems(seed, n):
     a[:, :32] = np.where(col < la[:, None], ra, 0)
     b[:, :32] = np.where(col < lb[:, None], rb, 0)
     return a, b, int((la * lb).sum())
+
+
+def ctypes_long():
+    import ctypes
+    return ctypes.c_long
+
+
+def ctypes_char_p():
+    import ctypes
+    return ctypes.c_char_p
+
+
+def parse_fasta_args():
+    import ctypes
+    return [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p]
+
+
+def fasta_leg(a, g, coll, hbm_peak):
+    """FASTA ingest on the device (fasta.cuh): the text of the first --fasta-targets sequences (line width 70) through
+    pcramp_gpu_upload_fasta into the BACKGROUND slot of the context.  Kernel figures from the library's CUDA events; e2e = the whole
+    call from host text (pageable) to a scan-ready collection (H2D of the text, both kernels, bit-planes, tiles)."""
+    from pcramp_b200 import BACKGROUND
+    n = min(coll.n, a.fasta_targets)
+    if n <= 0:
+        return None
+    sym = np.frombuffer(b"-ACMGRSVTWYHKDBN", np.uint8)
+    parts = []
+    for i in range(n):
+        letters = sym[coll.codes(i)]
+        L = len(letters)
+        rows = (L + 69) // 70
+        pad = np.full(rows * 70, 10, np.uint8)
+        pad[:L] = letters
+        body = np.concatenate([pad.reshape(rows, 70), np.full((rows, 1), 10, np.uint8)], axis=1).reshape(-1)
+        body = body[:L + (L // 70) + (1 if L % 70 else 0)] if L % 70 else body
+        parts.append(b">t%d\n" % i)
+        parts.append(body.tobytes())
+    blob = b"".join(parts)
+    g.upload_fasta(BACKGROUND, [blob])            # warm-up (allocations)
+    reps, ms_c, ms_p, t_e2e = 3, 0.0, 0.0, 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        recs = g.upload_fasta(BACKGROUND, [blob])
+        t_e2e += time.perf_counter() - t0
+        tm = g.fasta_timing(BACKGROUND)
+        ms_c += tm["ms_count"]
+        ms_p += tm["ms_pack"]
+    assert len(recs) == n and tm["n_bases"] == int(coll.length[:n].sum())
+    ms_c, ms_p, t_e2e = ms_c / reps, ms_p / reps, t_e2e / reps
+    chars, bases = float(tm["text_bytes"]), float(tm["n_bases"])
+    alg = chars + 0.5 * bases                                      # one read of the text + the packed nibbles (SURVEY.md 8d, K0)
+    moved = 2.0 * chars + 0.5 * bases                              # this implementation reads the text twice (count, then pack)
+    kern_s = (ms_c + ms_p) * 1e-3
+    g.upload_sequences(BACKGROUND, np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32))
+    cpu = None
+    if not a.no_cpu_baseline:
+        from tests.harness import RefLib, REF_PATH
+        if os.path.exists(REF_PATH):       # the reference's own reader (single-threaded by construction) on a slice of the same text
+            import tempfile
+            m = max(1, n // 10)
+            cut = blob.find(b">t%d\n" % m) if m < n else len(blob)
+            with tempfile.TemporaryDirectory() as d:
+                path = os.path.join(d, "slice.fa")
+                with open(path, "wb") as fh:
+                    fh.write(blob[:cut])
+                ref = RefLib()
+                ref.f_parse = ref._fn("parse_fasta", ctypes_long(), parse_fasta_args())
+                t0 = time.perf_counter()
+                k = ref.f_parse(ref.h, 1, (ctypes_char_p() * 1)(path.encode()), 0, 1 << 40, 0, b"")
+                dt = time.perf_counter() - t0
+            cpu = {"value": float(coll.length[:m].sum()) / dt / 1e9, "unit": "Gbases/s", "cores": 1, "kind": "reference", "seconds": dt,
+                   "sample": "parse_fasta of the first %d sequences (%d records read) from a file in the page cache" % (m, k)}
+    return {"metric": "fasta_ingest", "cpu_baseline": cpu, "value": bases / kern_s / 1e9, "unit": "Gbases/s (both kernels, text resident in HBM)",
+            "sequences": n, "text_bytes": int(chars), "bases": int(bases), "ms_count_kernel": ms_c, "ms_pack_kernel": ms_p,
+            "e2e": {"value": bases / t_e2e / 1e9, "unit": "Gbases/s", "ms": t_e2e * 1e3, "h2d_bytes": int(chars),
+                    "note": "host text (pageable memory) -> scan-ready collection: host record split, H2D, count + pack, bit-planes, tiles"},
+            "roofline": {"kernel": "fasta_count_kernel + fasta_pack_kernel", "bound": "hbm", "achieved": alg / kern_s / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": alg / kern_s / 1e9 / hbm_peak, "algorithmic_bytes": alg, "bytes_moved_by_design": moved,
+                         "achieved_on_moved_bytes": moved / kern_s / 1e9}}
 
 
 def dp_leg(a, g, torch, ext, rank, world, dist):
@@ -681,7 +761,8 @@ def run_b200(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_resident,
             "breakdown_ms_per_step": {k: stats_acc[k] / n_scan for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score")},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp, "target_sharded": tsh}))
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp, "target_sharded": tsh,
+            "fasta_ingest": fasta_leg(a, g, coll, hbm_peak) if a.fasta_targets > 0 else None}))
     # teardown order matters: torch tensors that were used on the library's stream must die before the stream does
     sys.stdout.flush()
     torch.cuda.synchronize()

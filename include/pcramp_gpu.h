@@ -137,6 +137,8 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 /* per sequence of that upload: source file, defline as (offset, length) into the file's text, length, weight (any may be NULL) */
 int pcramp_gpu_fasta_records(pcramp_gpu_ctx *ctx, int kind, uint32_t *file, uint64_t *defline_off, uint32_t *defline_len,
 	uint32_t *length, float *weight);
+/* CUDA-event times (ms) of the two device passes (count, pack) of the last FASTA upload, its text bytes and kept bases */
+int pcramp_gpu_fasta_timing(pcramp_gpu_ctx *ctx, int kind, float *ms_count, float *ms_pack, uint64_t *text_bytes, uint64_t *n_bases);
 void pcramp_gpu_fasta_free(pcramp_gpu_ctx *ctx);
 /* host-only view of the record split of ONE file (before the length window / ignore list): returns the number of records and
  * fills at most cap entries of each non-NULL array */

@@ -119,6 +119,7 @@ SIGNATURES = {
                                                ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _u32p]),
     "pcramp_gpu_fasta_records": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u32p, _u64p, _u32p, _u32p, _f32p]),
     "pcramp_gpu_fasta_free": (None, [ctypes.c_void_p]),
+    "pcramp_gpu_fasta_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _f32p, _f32p, _u64p, _u64p]),
     "pcramp_fasta_scan": (ctypes.c_uint32, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32, _u64p, _u32p, _u64p, _u64p, _f32p]),
     "pcramp_gpu_sequences_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u32p, _u64p, _u64p, _u32p, _u8p]),
     "pcramp_gpu_multiplex_keys": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, _u64p]),
@@ -363,6 +364,11 @@ class PcrampGpu:
         f, off, dl, ln, w = np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.float32)
         self._ck(self.lib.pcramp_gpu_fasta_records(self.h, kind, _ptr(f, _u32p), _ptr(off, _u64p), _ptr(dl, _u32p), _ptr(ln, _u32p), _ptr(w, _f32p)))
         return [(int(f[i]), blobs[int(f[i])][int(off[i]):int(off[i]) + int(dl[i])], int(ln[i]), float(w[i])) for i in range(n)]
+
+    def fasta_timing(self, kind):
+        a, b, t, n = np.zeros(1, np.float32), np.zeros(1, np.float32), np.zeros(1, np.uint64), np.zeros(1, np.uint64)
+        self._ck(self.lib.pcramp_gpu_fasta_timing(self.h, kind, _ptr(a, _f32p), _ptr(b, _f32p), _ptr(t, _u64p), _ptr(n, _u64p)))
+        return {"ms_count": float(a[0]), "ms_pack": float(b[0]), "text_bytes": int(t[0]), "n_bases": int(n[0])}
 
     def sequences_copy(self, kind):
         """the collection as the reference stores it -> (byte_off uint64[n], length uint32[n], nibbles uint8[total])"""

@@ -20,6 +20,7 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include <chrono>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -98,14 +99,22 @@ inline float extract_weight(const std::string &d)
 	return 1.0f; // DEFAULT_SCORE_WEIGHT
 }
 
-// the reader of parse_fasta over one file; `base` = the file's offset in the concatenated text
+// the reader of parse_fasta over one file; `base` = the file's offset in the concatenated text.
+// gzgets hands the reference chunks of at most READ_CHUNK bytes that end after a newline; only the chunks holding a '>' matter
+// (they are deflines and close the record before them), so the walk jumps from '>' to '>' (one memchr sweep over the text) and
+// reconstructs the chunk around each: chunks of a line start at the line's first byte and every READ_CHUNK bytes after it.
 inline void split_records(const char *text, uint64_t n, uint32_t file, uint64_t base, std::vector<Record> &out)
 {
-	bool have_def = false, any_data = false;
-	uint64_t def_off = 0, span_begin = 0, span_end = 0;
+	bool have_def = false;
+	uint64_t def_off = 0, span_begin = 0;
 	uint32_t def_len = 0;
-	auto close = [&](bool need_data) {
-		if (need_data && !any_data) return; // "if( !seq.empty() )" between records; the record after the last defline has no such test
+	auto any_data = [&](uint64_t b, uint64_t e) { // "!seq.empty()": a non-space byte in the data chunks
+		for (uint64_t k = b; k < e; ++k)
+			if (!is_space((unsigned char)text[k])) return true;
+		return false;
+	};
+	auto close = [&](uint64_t span_end, bool need_data) {
+		if (need_data && !any_data(span_begin, span_end)) return; // the record after the last defline is closed without that test
 		Record r;
 		r.file = file;
 		r.def_off = def_off;
@@ -116,32 +125,31 @@ inline void split_records(const char *text, uint64_t n, uint32_t file, uint64_t 
 		r.ignored = false;
 		out.push_back(r);
 	};
-	uint64_t pos = 0;
-	span_begin = span_end = 0;
+	uint64_t pos = 0; // always the first byte of a chunk
 	while (pos < n) {
-		// gzgets: up to READ_CHUNK bytes, stopping after a newline
-		uint64_t lim = std::min<uint64_t>(n, pos + READ_CHUNK);
-		const char *nl = (const char *)memchr(text + pos, '\n', lim - pos);
-		const uint64_t end = nl ? (uint64_t)(nl - text) + 1 : lim;
-		if (memchr(text + pos, '>', end - pos)) {
-			close(true);
-			// the defline: the chunk up to its first CR / LF
-			uint64_t e = pos;
-			while (e < end && text[e] != '\n' && text[e] != '\r') ++e;
-			have_def = true;
-			def_off = pos;
-			def_len = (uint32_t)(e - pos);
-			any_data = false;
-			span_begin = span_end = end;
-		} else {
-			if (!any_data)
-				for (uint64_t k = pos; k < end; ++k)
-					if (!is_space((unsigned char)text[k])) { any_data = true; break; }
-			span_end = end;
+		const char *gt = (const char *)memchr(text + pos, '>', n - pos);
+		if (!gt) break;
+		const uint64_t g = (uint64_t)(gt - text);
+		// the line holding g starts after the last newline in [pos, g)
+		uint64_t line = pos;
+		if (g > pos) {
+			const char *nl = (const char *)memrchr(text + pos, '\n', g - pos);
+			if (nl) line = (uint64_t)(nl - text) + 1;
 		}
+		const uint64_t chunk = line + ((g - line) / READ_CHUNK) * READ_CHUNK;
+		const uint64_t lim = std::min<uint64_t>(n, chunk + READ_CHUNK);
+		const char *nl = (const char *)memchr(text + chunk, '\n', lim - chunk);
+		const uint64_t end = nl ? (uint64_t)(nl - text) + 1 : lim;
+		close(chunk, true);
+		uint64_t e = chunk; // the defline: the chunk up to its first CR / LF
+		while (e < end && text[e] != '\n' && text[e] != '\r') ++e;
+		have_def = true;
+		def_off = chunk;
+		def_len = (uint32_t)(e - chunk);
+		span_begin = end;
 		pos = end;
 	}
-	close(false);
+	close(n, false);
 }
 
 // base_to_bits (base_table.h:30-76); 0xFF = the symbol the reference throws on, 0xFE = white space
@@ -174,6 +182,22 @@ __device__ __forceinline__ uint32_t classify(uint32_t c)
 	return 0xFFu;
 }
 
+// bytes of w that are white space (' ' or 9..13), one 0xFF per such byte
+__device__ __forceinline__ uint32_t space_mask4(uint32_t w)
+{
+	return __vcmpeq4(w, 0x20202020u) | (__vcmpgeu4(w, 0x09090909u) & __vcmpleu4(w, 0x0D0D0D0Du));
+}
+// 0xFF for the bytes of the 4-byte word at text offset `at` that lie inside [begin, end)
+__device__ __forceinline__ uint32_t inside_mask4(uint64_t at, uint64_t begin, uint64_t end)
+{
+	if (at >= begin && at + 4 <= end) return 0xFFFFFFFFu;
+	uint32_t m = 0u;
+	#pragma unroll
+	for (int k = 0; k < 4; ++k)
+		if (at + k >= begin && at + k < end) m |= 255u << (8 * k);
+	return m;
+}
+
 __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t lane, uint32_t &total)
 {
 	uint32_t incl = v;
@@ -203,11 +227,7 @@ __global__ void __launch_bounds__(256) fasta_count_kernel(const uint8_t *__restr
 		const uint4 q = *(const uint4 *)(text + at); // the text buffer is padded to a multiple of BLOCK_BYTES
 		const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
 		#pragma unroll
-		for (int k = 0; k < 16; ++k) {
-			const uint64_t p = at + k;
-			const uint32_t ch = (wd[k >> 2] >> (8 * (k & 3))) & 255u;
-			if (p >= w.begin && p < w.end && !(ch == ' ' || (ch >= 9u && ch <= 13u))) ++c;
-		}
+		for (int k = 0; k < 4; ++k) c += (uint32_t)__popc(~space_mask4(wd[k]) & inside_mask4(at + 4u * k, w.begin, w.end)) >> 3;
 	}
 	for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
 	if (lane == 0u) count[it] = c;
@@ -223,10 +243,26 @@ struct PackOut {
 	uint32_t eos_cap;
 };
 
-// item_off[it] = residues of the record before this item
+// class table entry of a text byte: nibble[3:0] | residue [4] | degenerate [5] | EOS '-' [6] | unknown symbol [7]; white space = 0
+__device__ __forceinline__ uint32_t class_entry(uint32_t c)
+{
+	const uint32_t b = classify(c);
+	if (b == 0xFEu) return 0u;
+	if (b == 0xFFu) return 0x80u;
+	return b | 0x10u | ((b & (b - 1u)) ? 0x20u : 0u) | (b == 0u ? 0x40u : 0u);
+}
+
+// item_off[it] = residues of the record before this item.  One warp per item, lane l owns bytes [128 l, 128 l + 128) of the block.
+// Pass 1 counts the lane's residues (SIMD byte compares), a warp scan gives the lane its first residue index; pass 2 walks the
+// same 128 bytes again (L1 hits) in a rolled loop of 16-byte vectors -- table look-up per character, nibbles OR-ed into a 32-bit
+// word that is stored when full (plain store when this lane produced all 8 nibbles, atomicOr for the shared words at the lane's
+// ends).  '-' and unknown symbols only raise a flag in the hot loop; their positions come from a rare third walk.
 __global__ void __launch_bounds__(256) fasta_pack_kernel(const uint8_t *__restrict__ text, const Item *__restrict__ items, uint32_t n_items,
 	const uint32_t *__restrict__ item_off, PackOut o)
 {
+	__shared__ uint8_t s_cls[256];
+	s_cls[threadIdx.x & 255u] = (uint8_t)class_entry(threadIdx.x & 255u);
+	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (it >= n_items) return;
@@ -234,64 +270,64 @@ __global__ void __launch_bounds__(256) fasta_pack_kernel(const uint8_t *__restri
 	const uint64_t roff = o.rec_raw_off[w.rec];
 	if (roff == ~0ull) return;
 	const uint64_t blk = w.begin & ~(uint64_t)(BLOCK_BYTES - 1u);
-	// pass 1 over the lane's 128 bytes (kept in registers): how many residues
-	uint4 q[8];
+	const uint64_t mine = blk + 128ull * lane;
 	uint32_t c = 0;
 	#pragma unroll
 	for (int v = 0; v < 8; ++v) {
-		const uint64_t at = blk + 128ull * lane + 16ull * v;
-		q[v] = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+		const uint64_t at = mine + 16ull * v;
 		if (at + 16 <= w.begin || at >= w.end) continue;
-		q[v] = *(const uint4 *)(text + at);
-		uint32_t *wd = (uint32_t *)&q[v];
+		const uint4 x = *(const uint4 *)(text + at);
+		const uint32_t wd[4] = {x.x, x.y, x.z, x.w};
 		#pragma unroll
-		for (int k = 0; k < 16; ++k) {
-			const uint64_t p = at + k;
-			if (p < w.begin || p >= w.end) wd[k >> 2] = (wd[k >> 2] & ~(255u << (8 * (k & 3)))) | (0x20u << (8 * (k & 3))); // outside: a blank
-			else {
-				const uint32_t ch = (wd[k >> 2] >> (8 * (k & 3))) & 255u;
-				if (!(ch == ' ' || (ch >= 9u && ch <= 13u))) ++c;
-			}
-		}
+		for (int k = 0; k < 4; ++k) c += (uint32_t)__popc(~space_mask4(wd[k]) & inside_mask4(at + 4u * k, w.begin, w.end)) >> 3;
 	}
 	uint32_t total;
-	uint64_t r = (uint64_t)item_off[it] + warp_excl_sum(c, lane, total); // residue index of this lane's first base
-	// pass 2: nibbles into 32-bit words of the output; a word is stored when this lane produced all 8 of its nibbles, else OR-ed
+	const uint64_t r0 = (uint64_t)item_off[it] + warp_excl_sum(c, lane, total); // residue index of this lane's first base
 	uint32_t *out32 = (uint32_t *)(o.raw + roff); // records start 16-byte aligned
-	uint32_t acc = 0, have = 0; // nibbles gathered for word r >> 3
-	bool degenerate = false;
-	auto flush = [&](uint64_t word) {
-		if (have == 0u) return;
-		if (have == 8u) out32[word] = acc;
-		else atomicOr(out32 + word, acc);
-		acc = 0u;
-		have = 0u;
-	};
-	#pragma unroll
+	uint64_t r = r0;
+	uint32_t acc = 0, have = 0, flags = 0;
+	#pragma unroll 1
 	for (int v = 0; v < 8; ++v) {
-		const uint32_t *wd = (const uint32_t *)&q[v];
-		#pragma unroll 4
-		for (int k = 0; k < 16; ++k) {
-			const uint32_t ch = (wd[k >> 2] >> (8 * (k & 3))) & 255u;
-			const uint32_t b = classify(ch);
-			if (b == 0xFEu) continue;
-			if (b == 0xFFu) {
-				atomicMin(o.bad, (unsigned long long)(blk + 128ull * lane + 16ull * v + k));
-				continue;
+		const uint64_t at = mine + 16ull * v;
+		if (at + 16 <= w.begin || at >= w.end) continue;
+		const uint4 x = *(const uint4 *)(text + at);
+		const uint32_t wd[4] = {x.x, x.y, x.z, x.w};
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const uint32_t y = wd[k] & inside_mask4(at + 4u * k, w.begin, w.end); // bytes outside the item become NUL ...
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const uint32_t ch = (y >> (8 * j)) & 255u;
+				const uint32_t e = ch ? s_cls[ch] : 0u;                 // ... which counts as nothing at all
+				flags |= e;
+				const uint32_t is = (e >> 4) & 1u;
+				// residue r: byte r >> 1, high nibble for even r; little-endian word r >> 3
+				acc |= (is ? (e & 15u) : 0u) << ((((uint32_t)r & 7u) << 2) ^ 4u);
+				have += is;
+				r += is;
+				if (is && ((uint32_t)r & 7u) == 0u) {
+					if (have == 8u) out32[(r - 1u) >> 3] = acc;
+					else atomicOr(out32 + ((r - 1u) >> 3), acc);
+					acc = 0u;
+					have = 0u;
+				}
 			}
-			if (b == 0u) {
-				const unsigned int e = atomicAdd(o.n_eos, 1u);
-				if (e < o.eos_cap) o.eos[e] = make_uint2(w.rec, (uint32_t)r);
-			} else if (b & (b - 1u)) degenerate = true;
-			// residue r: byte r >> 1 (high nibble for even r); little-endian word r >> 3
-			acc |= b << (8u * (uint32_t)((r >> 1) & 3u) + ((r & 1u) ? 0u : 4u));
-			++have;
-			++r;
-			if ((r & 7u) == 0u) flush((r - 1u) >> 3);
 		}
 	}
-	flush(r >> 3);
-	if (__any_sync(0xffffffffu, degenerate) && lane == 0u) atomicOr(o.flags, 1u);
+	if (have) atomicOr(out32 + (r >> 3), acc);
+	if (flags & 0xC0u) { // a '-' or an unknown symbol among this lane's bytes: find where
+		uint64_t rr = r0;
+		for (uint64_t p = (mine > w.begin ? mine : w.begin); p < mine + 128ull && p < w.end; ++p) {
+			const uint32_t e = s_cls[text[p]];
+			if (e & 0x80u) atomicMin(o.bad, (unsigned long long)p);
+			if (e & 0x40u) {
+				const unsigned int k = atomicAdd(o.n_eos, 1u);
+				if (k < o.eos_cap) o.eos[k] = make_uint2(w.rec, (uint32_t)rr);
+			}
+			rr += (e >> 4) & 1u;
+		}
+	}
+	if (__any_sync(0xffffffffu, (flags & 0x20u) != 0u) && lane == 0u) atomicOr(o.flags, 1u);
 }
 
 __global__ void fasta_lengths_kernel(const unsigned long long *__restrict__ excl, const unsigned long long *__restrict__ count,
@@ -307,6 +343,8 @@ __global__ void fasta_lengths_kernel(const unsigned long long *__restrict__ excl
 }
 
 struct Table { // the record table of the last upload_fasta, for pcramp_gpu_fasta_records
+	float ms_count = 0.0f, ms_pack = 0.0f; // CUDA-event times of the two kernels of the last upload
+	uint64_t text_bytes = 0, n_bases = 0;
 	std::vector<uint32_t> file, def_len, length;
 	std::vector<uint64_t> def_off;
 	std::vector<float> weight;
@@ -327,6 +365,9 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 	if (n_files && (!text || !bytes)) return fail(ctx, "pcramp_gpu_upload_fasta: null argument");
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
+	const bool dbg = getenv("PCRAMP_FASTA_TIMING") != nullptr;
+	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t0 = now();
 	// ---- host: records ---------------------------------------------------------------------------------------
 	std::vector<Record> recs;
 	std::vector<uint64_t> base(n_files + 1, 0);
@@ -358,6 +399,7 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 	rec_first[n_rec] = (uint32_t)items.size();
 	if (items.size() >= (1ull << 31)) return fail(ctx, "pcramp_gpu_upload_fasta: text too large for one call");
 	const uint32_t n_items = (uint32_t)items.size();
+	const double t1 = now();
 	// ---- text to HBM -----------------------------------------------------------------------------------------
 	const uint64_t text_bytes = (base[n_files] + BLOCK_BYTES) & ~(uint64_t)(BLOCK_BYTES - 1u);
 	DevBuf d_text, d_items, d_count, d_excl, d_first, d_len, d_item_off, d_rec_off, d_eos, d_misc, d_tmp;
@@ -376,8 +418,10 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 	if (n_items) {
 		CK(cudaMemcpyAsync(d_items.p, items.data(), (size_t)n_items * sizeof(Item), cudaMemcpyHostToDevice, st));
 		CK(cudaMemcpyAsync(d_first.p, rec_first.data(), (size_t)(n_rec + 1) * 4, cudaMemcpyHostToDevice, st));
+		CK(cudaEventRecord(ctx->ev[0], st));
 		fasta_count_kernel<<<grid_for(32ull * n_items, 256), 256, 0, st>>>(d_text.as<uint8_t>(), d_items.as<Item>(), n_items, d_count.as<unsigned long long>());
 		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev[1], st));
 		size_t tb = 0;
 		CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_count.as<unsigned long long>(), d_excl.as<unsigned long long>(), (int)n_items, st));
 		CK(d_tmp.ensure(tb));
@@ -388,11 +432,14 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 		CK(cudaMemcpyAsync(rec_len.data(), d_len.p, (size_t)n_rec * 8, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 	}
+	const double t2 = now();
 	// ---- which records become sequences (parse_fasta.cpp:35-47,76-86) ---------------------------------------------
 	SeqSet &s = ctx->sets[kind];
 	if (!ctx->fasta[kind]) ctx->fasta[kind] = new pcramp_gpu_fasta();
 	pcramp_gpu_fasta &tab = *ctx->fasta[kind];
 	tab = pcramp_gpu_fasta();
+	if (n_items) tab.ms_count = ev_ms(ctx->ev[0], ctx->ev[1]);
+	tab.text_bytes = base[n_files];
 	std::vector<uint64_t> rec_off(n_rec, ~0ull);
 	std::vector<uint32_t> rec_seq(n_rec, 0xFFFFFFFFu);
 	std::vector<uint64_t> raw_off;
@@ -447,8 +494,10 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 		po.n_eos = (unsigned int *)d_misc.p + 3;
 		po.eos = d_eos.as<uint2>();
 		po.eos_cap = eos_cap;
+		CK(cudaEventRecord(ctx->ev[0], st));
 		fasta_pack_kernel<<<grid_for(32ull * n_items, 256), 256, 0, st>>>(d_text.as<uint8_t>(), d_items.as<Item>(), n_items, d_item_off.as<uint32_t>(), po);
 		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev[1], st));
 		unsigned long long res[2];
 		CK(cudaMemcpyAsync(res, d_misc.p, 16, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
@@ -461,6 +510,7 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 			s.n = 0;
 			return fail(ctx, b);
 		}
+		tab.ms_pack = ev_ms(ctx->ev[0], ctx->ev[1]);
 		s.any_degenerate = ((uint32_t)res[1] & 1u) != 0u;
 		const uint32_t n_eos = (uint32_t)(res[1] >> 32);
 		if (n_eos > eos_cap) {
@@ -490,8 +540,12 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 		s.grp_off[i + 1] = s.grp_off[i] + ((uint64_t)s.clen[i] + 31) / 32 + 1;
 	}
 	if (n_records) *n_records = n;
+	for (uint32_t L : tab.length) tab.n_bases += L;
 	ctx->stats.kernel_launches = n_items ? 4 : 0;
-	return upload_finish(ctx, s, nullptr, with_eos);
+	const double t3 = now();
+	const int rc = upload_finish(ctx, s, nullptr, with_eos);
+	if (dbg) fprintf(stderr, "upload_fasta: split %.1f ms, H2D + count %.1f ms, pack %.1f ms, finish %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
+	return rc;
 }
 
 /* host-only: the record split of one file's text as pcramp_gpu_upload_fasta sees it (before the length window and the ignore
@@ -510,6 +564,19 @@ uint32_t pcramp_fasta_scan(const char *text, uint64_t bytes, uint32_t cap, uint6
 		if (weight) weight[i] = pcr::fasta::extract_weight(std::string(text + recs[i].def_off, recs[i].def_len));
 	}
 	return (uint32_t)recs.size();
+}
+
+/* CUDA-event times (ms) of the two device passes of the last pcramp_gpu_upload_fasta on `kind`, its text bytes and kept bases */
+int pcramp_gpu_fasta_timing(pcramp_gpu_ctx *ctx, int kind, float *ms_count, float *ms_pack, uint64_t *text_bytes, uint64_t *n_bases)
+{
+	if (check_kind(ctx, kind)) return 1;
+	if (!ctx->fasta[kind]) return fail(ctx, "pcramp_gpu_fasta_timing: no FASTA upload on this collection");
+	const pcramp_gpu_fasta &t = *ctx->fasta[kind];
+	if (ms_count) *ms_count = t.ms_count;
+	if (ms_pack) *ms_pack = t.ms_pack;
+	if (text_bytes) *text_bytes = t.text_bytes;
+	if (n_bases) *n_bases = t.n_bases;
+	return 0;
 }
 
 void pcramp_gpu_fasta_free(pcramp_gpu_ctx *ctx)

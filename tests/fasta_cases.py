@@ -51,6 +51,11 @@ def cases():
     long_line = _seq(rng, 7000)
     t = _wrap(_seq(rng, 100), 50) + ">a\n" + long_line + "\n>b\n" + _seq(rng, 300) + "\n" + _seq(rng, 40) + ">" + _seq(rng, 20) + "\n" + _seq(rng, 90) + "\n"
     out.append(FastaCase("chunks", [t]))
+    # '>' in the second gzgets chunk of a 5000-byte line: bytes 2047..4093 of that line are a "defline", the rest is sequence;
+    # consecutive deflines; an empty record after the last defline, kept because nothing asks for a minimum length
+    line = _seq(rng, 3000) + ">" + _seq(rng, 1999)
+    t = ">x\n" + _seq(rng, 64) + "\n" + line + "\n" + _seq(rng, 33) + "\n>y\n>z [w=4]\n" + _seq(rng, 77) + "\n>empty\n"
+    out.append(FastaCase("chunk_defline", [t]))
     # odd lengths and very short records (pad nibble, one byte)
     t = "".join(">o%d\n%s\n" % (i, _seq(rng, n)) for i, n in enumerate([1, 2, 3, 31, 32, 33, 63, 65, 4097, 8191]))
     out.append(FastaCase("odd", [t]))
