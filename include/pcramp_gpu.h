@@ -48,6 +48,9 @@ int pcramp_gpu_synchronize(pcramp_gpu_ctx *ctx);
  * weight may be NULL (1.0f each, sequence.h:22).  All sequences start active (sequence.h:143). */
 int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const uint8_t *nibbles,
 	const uint64_t *byte_off, const uint32_t *len, const float *weight);
+/* Sequence weights after the fact (Sequence::weight, e.g. opt.normalize_target_weight_per_file, main.cpp:268-278, applied to the
+ * weights pcramp_gpu_fasta_records returned): n floats for the n sequences of `kind`. */
+int pcramp_gpu_set_weights(pcramp_gpu_ctx *ctx, int kind, const float *weight);
 /* Sequence::active(bool) for the whole collection (main.cpp:493-495,1116-1121). */
 int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active);
 /* Sequence::split_sequence (sequence.h:231-243; called at main.cpp:1010-1016). */

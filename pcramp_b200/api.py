@@ -101,6 +101,7 @@ SIGNATURES = {
     "pcramp_gpu_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "pcramp_gpu_upload_sequences": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, _u8p, _u64p, _u32p, _f32p]),
     "pcramp_gpu_set_active": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u8p]),
+    "pcramp_gpu_set_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _f32p]),
     "pcramp_gpu_split_sequence": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]),
     "pcramp_gpu_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_uint32, ctypes.c_uint64, _u64p, _i32p, _u32p, _u64p]),
@@ -369,6 +370,10 @@ class PcrampGpu:
         a, b, t, n = np.zeros(1, np.float32), np.zeros(1, np.float32), np.zeros(1, np.uint64), np.zeros(1, np.uint64)
         self._ck(self.lib.pcramp_gpu_fasta_timing(self.h, kind, _ptr(a, _f32p), _ptr(b, _f32p), _ptr(t, _u64p), _ptr(n, _u64p)))
         return {"ms_count": float(a[0]), "ms_pack": float(b[0]), "text_bytes": int(t[0]), "n_bases": int(n[0])}
+
+    def set_weights(self, kind, weight):
+        w = np.ascontiguousarray(weight, dtype=np.float32)
+        self._ck(self.lib.pcramp_gpu_set_weights(self.h, kind, _ptr(w, _f32p)))
 
     def sequences_copy(self, kind):
         """the collection as the reference stores it -> (byte_off uint64[n], length uint32[n], nibbles uint8[total])"""

@@ -493,6 +493,20 @@ int upload_finish(pcramp_gpu_ctx *ctx, SeqSet &s, const uint8_t *nibbles, const 
 	return rebuild_tiles(ctx, s);
 }
 
+int pcramp_gpu_set_weights(pcramp_gpu_ctx *ctx, int kind, const float *weight)
+{ // Sequence::weight(w) (sequence.h), e.g. the per-file normalisation of main.cpp:268-278 after a FASTA upload
+	if (check_kind(ctx, kind)) return 1;
+	SeqSet &s = ctx->sets[kind];
+	if (s.n && !weight) return fail(ctx, "pcramp_gpu_set_weights: null argument");
+	CK(cudaSetDevice(ctx->device));
+	s.weight.assign(weight, weight + s.n);
+	s.unit_weights = true;
+	for (float w : s.weight) s.unit_weights = s.unit_weights && (w == 1.0f);
+	if (s.n) CK(cudaMemcpyAsync(s.d_weight.p, s.weight.data(), (size_t)s.n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
 int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active)
 {
 	if (check_kind(ctx, kind)) return 1;

@@ -71,6 +71,14 @@ def test_fasta_collection_equals_uploaded_collection(gpu):
     cov_b, bits_b = gpu.score_pairs(BACKGROUND, f, r, thr, 0.9)
     assert ne_a == ne_b and all(np.array_equal(a, b) for a, b in zip(db_a, db_b))
     assert np.array_equal(cov_a, cov_b) and np.array_equal(bits_a, bits_b) and bits_a.any()
+    # weights set after the fact (per-file normalisation) == weights given at upload
+    w = np.random.default_rng(4).uniform(0.1, 2.0, size=coll.n).astype(np.float32)
+    gpu.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length, w)
+    gpu.select_words(TARGET, f, r, thr)
+    cov_w, _ = gpu.score_pairs(TARGET, f, r, thr, 0.9)
+    gpu.set_weights(BACKGROUND, w)
+    cov_w2, _ = gpu.score_pairs(BACKGROUND, f, r, thr, 0.9)
+    assert np.array_equal(cov_w.view(np.uint32), cov_w2.view(np.uint32)) and not np.array_equal(cov_w, cov_a)
 
 
 @pytest.mark.skipif(not os.path.exists(REF_PATH), reason="compiled reference did not travel with the snapshot")
