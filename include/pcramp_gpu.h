@@ -329,7 +329,9 @@ int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
 /* Tuning / testing switches.  "force_brute_scan" = 1 sends every pattern through the brute-force scan kernel;
  * "use_index" = 0 keeps the seeded patterns on scan_seed_kernel instead of the indexed scan (default 1: the text index
  * is built on first use, ~32 bytes per base of device memory); "use_seed_table" = 0 makes pair scoring and the
- * partial-word scan compare every word with every oligo instead of going through the frame-aligned seed table (fst.cuh).
+ * partial-word scan compare every word with every oligo instead of going through the frame-aligned seed table (fst.cuh);
+ * "use_neighbours" = 0 makes pair scoring find the oligos of a database word by that table walk instead of through the
+ * neighbour list of the candidate that produced the word (score.cuh).
  * All paths are CUDA and give identical results; the tests compare them. */
 int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value);
 /* Issue-bound ceiling of the scan's own instruction mix on this GPU (alignments/s), measured live. */

@@ -69,6 +69,10 @@ struct SeqSet {
 	bool db_valid = false;
 	DevBuf e_hi, e_lo, e_planes, e_seq, e_loc, e_strand, e_perm, e_keyrank, seq_ent_off;
 	DevBuf e_key, key_planes; // key index per entry (entry-id order), letter planes per unique word
+	// neighbour filter of pair scoring (score.cuh): per entry one candidate word that produced it, and the candidate words of
+	// the select_words call that built this database (letter planes + seed threshold)
+	DevBuf e_cand, c_planes, c_thr;
+	uint32_t n_cand = 0;
 	DevBuf e_order;           // (index, loc, strand) sort key per entry: input of the canonical order, built on demand
 	bool keys_valid = false;
 	uint32_t seq_bits = 1;
@@ -121,6 +125,8 @@ struct pcramp_gpu_ctx {
 	int use_index = 1;
 	DevBuf d_idx_queries, d_idx_counters, d_idx_cand;
 	// scratch
+	DevBuf ent_cand[2], d_neigh, d_neigh_off;
+	int use_neigh = 1;
 	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
 	unsigned long long *h_counters = nullptr; // pinned
 	pcramp_gpu_stats stats = {};

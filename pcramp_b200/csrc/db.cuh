@@ -37,7 +37,7 @@ __global__ void validate_hits_kernel(SeqDev sd, PackParams pp, uint64_t *hit_key
 
 // hits sorted ascending by key; invalidated hits (key == ~0) sort last
 __global__ void tier_kernel(const uint64_t *__restrict__ hit_key, const uint32_t *__restrict__ hit_val, uint64_t n_hits,
-	uint32_t cand_bits, uint64_t *entry_id, unsigned long long *n_out)
+	uint32_t cand_bits, uint64_t *entry_id, uint32_t *entry_cand, unsigned long long *n_out)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_hits) return;
@@ -53,6 +53,8 @@ __global__ void tier_kernel(const uint64_t *__restrict__ hit_key, const uint32_t
 	const uint32_t seq = (uint32_t)(k >> (HIT_GROUP_SHIFT + cand_bits));
 	const unsigned long long o = atomicAdd(n_out, 1ull);
 	entry_id[o] = entry_id_pack(seq, (uint32_t)(k >> 1) & 3u, (uint32_t)k & 1u, hit_val[i]);
+	// one candidate word that reaches its seed threshold on this window: the anchor of the neighbour filter of pair scoring (score.cuh)
+	entry_cand[o] = (uint32_t)(k >> HIT_GROUP_SHIFT) & ((1u << cand_bits) - 1u);
 }
 
 // word, loc, strand, seq of each unique entry (entry ids sorted => grouped by sequence)

@@ -984,9 +984,11 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	stat.kernel_launches += 8;
 	CK(ctx->ent_id[0].ensure(n_hits * 8));
 	CK(ctx->ent_id[1].ensure(n_hits * 8));
+	CK(ctx->ent_cand[0].ensure(n_hits * 4));
+	CK(ctx->ent_cand[1].ensure(n_hits * 4));
 	CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
 	tier_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[1].as<uint64_t>(), ctx->hit_val[1].as<uint32_t>(), n_hits, cand_bits,
-		ctx->ent_id[0].as<uint64_t>(), d_cnt);
+		ctx->ent_id[0].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>(), d_cnt);
 	CK(cudaGetLastError());
 	stat.kernel_launches++;
 	CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1000,14 +1002,17 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	}
 
 	// ---- unique entries -------------------------------------------------------------------------
-	CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, ctx->ent_id[0].as<uint64_t>(), ctx->ent_id[1].as<uint64_t>(), (int64_t)n_flag, 0,
-		(int)(35 + seq_bits), st));
+	// (the candidate of each flagged hit rides along; any one of an entry's candidates will do, so the first is kept)
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->ent_id[0].as<uint64_t>(), ctx->ent_id[1].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>(),
+		ctx->ent_cand[1].as<uint32_t>(), (int64_t)n_flag, 0, (int)(35 + seq_bits), st));
 	CK(ctx->cub_tmp.ensure(tmp_bytes));
-	CK(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp_bytes, ctx->ent_id[0].as<uint64_t>(), ctx->ent_id[1].as<uint64_t>(), (int64_t)n_flag, 0,
-		(int)(35 + seq_bits), st));
-	CK(cub::DeviceSelect::Unique(nullptr, tmp_bytes, ctx->ent_id[1].as<uint64_t>(), ctx->ent_id[0].as<uint64_t>(), d_cnt + 1, (int64_t)n_flag, st));
+	CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->ent_id[0].as<uint64_t>(), ctx->ent_id[1].as<uint64_t>(),
+		ctx->ent_cand[0].as<uint32_t>(), ctx->ent_cand[1].as<uint32_t>(), (int64_t)n_flag, 0, (int)(35 + seq_bits), st));
+	CK(cub::DeviceSelect::UniqueByKey(nullptr, tmp_bytes, ctx->ent_id[1].as<uint64_t>(), ctx->ent_cand[1].as<uint32_t>(), ctx->ent_id[0].as<uint64_t>(),
+		ctx->ent_cand[0].as<uint32_t>(), d_cnt + 1, (int64_t)n_flag, st));
 	CK(ctx->cub_tmp.ensure(tmp_bytes));
-	CK(cub::DeviceSelect::Unique(ctx->cub_tmp.p, tmp_bytes, ctx->ent_id[1].as<uint64_t>(), ctx->ent_id[0].as<uint64_t>(), d_cnt + 1, (int64_t)n_flag, st));
+	CK(cub::DeviceSelect::UniqueByKey(ctx->cub_tmp.p, tmp_bytes, ctx->ent_id[1].as<uint64_t>(), ctx->ent_cand[1].as<uint32_t>(),
+		ctx->ent_id[0].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>(), d_cnt + 1, (int64_t)n_flag, st));
 	stat.kernel_launches += 10;
 	CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
@@ -1022,6 +1027,13 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(s.e_loc.ensure(n_ent * 4));
 	CK(s.e_strand.ensure(n_ent * 4));
 	CK(s.e_order.ensure(n_ent * 8));
+	CK(s.e_cand.ensure(n_ent * 4));
+	CK(s.c_planes.ensure(std::max<size_t>(1, n_cand) * 16));
+	CK(s.c_thr.ensure(std::max<size_t>(1, n_cand) * 4));
+	CK(cudaMemcpyAsync(s.e_cand.p, ctx->ent_cand[0].p, n_ent * 4, cudaMemcpyDeviceToDevice, st));
+	CK(cudaMemcpyAsync(s.c_planes.p, ctx->d_cand_words.p, (size_t)n_cand * 16, cudaMemcpyDeviceToDevice, st));
+	CK(cudaMemcpyAsync(s.c_thr.p, ctx->d_cand_thr.p, (size_t)n_cand * 4, cudaMemcpyDeviceToDevice, st));
+	s.n_cand = n_cand;
 	const unsigned ge = grid_for(n_ent, 256);
 	materialise_kernel<<<ge, 256, 0, st>>>(sd, pp, ctx->ent_id[0].as<uint64_t>(), n_ent, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(),
 		s.e_planes.as<uint4>(), s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), s.e_order.as<uint64_t>());
@@ -1214,7 +1226,9 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 			uint64_t item_cap = std::max<uint64_t>(ctx->d_items.cap / sizeof(ScoreItem), 1ull << 20);
 			// seed-table filter (fst.cuh) unless too many oligos cannot be seeded (low thresholds: backgrounds at 0.72^2)
 			Fst fst;
-			bool use_fst = ctx->use_fst != 0;
+			// neighbour filter (score.cuh) when the candidates x oligos comparison is small next to the table walk it replaces
+			const bool use_neigh = ctx->use_neigh != 0 && s.n_cand > 0 && (uint64_t)s.n_cand * 2ull * n_pairs <= (1ull << 28);
+			bool use_fst = ctx->use_fst != 0 && !use_neigh;
 			if (use_fst) {
 				CK(ctx->d_fst_planes.ensure((size_t)n_pairs * 2 * 16));
 				CK(ctx->d_fst_thr.ensure((size_t)n_pairs * 2 * 4));
@@ -1223,16 +1237,56 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 				CK(cudaGetLastError());
 				ctx->stats.kernel_launches++;
 			}
-			if (use_fst) chunk_pairs = std::min(chunk_pairs, chunk_for(2ull * s.n)); // seed table: two rows per sequence
+			if (use_fst || use_neigh) chunk_pairs = std::min(chunk_pairs, chunk_for(2ull * s.n)); // two bit rows per sequence
 			for (uint32_t p0 = 0; p0 < n_pairs; p0 += chunk_pairs) {
 				const uint32_t pc = std::min<uint32_t>(chunk_pairs, n_pairs - p0), nw = (2u * pc + 31u) / 32u;
 				bool chunk_fst = use_fst;
+				if (use_neigh) {
+					const uint32_t n_olig = 2u * pc;
+					const OligoDev *d_ol = d_member + 2ull * p0;
+					CK(ctx->d_neigh_off.ensure(((size_t)s.n_cand + 1) * 4));
+					unsigned int n_np = 0;
+					for (int attempt = 0;; ++attempt) { // (candidate, oligo) pairs, then sorted by candidate
+						CK(ctx->d_neigh.ensure(std::max<size_t>(ctx->d_neigh.cap, (size_t)16 * (8ull * n_olig + 4096))));
+						const uint32_t cap = (uint32_t)std::min<size_t>(ctx->d_neigh.cap / 16, 0x7FFFFFF0u); // second half: sort buffer
+						CK(cudaMemsetAsync(ctx->d_item_count.p, 0, 16, st));
+						neigh_pairs_kernel<<<dim3(grid_for(s.n_cand, 256), grid_for(n_olig, 256)), 256, 0, st>>>(s.c_planes.as<uint4>(), s.c_thr.as<uint32_t>(),
+							s.n_cand, d_ol, n_olig, ctx->d_neigh.as<unsigned long long>(), ctx->d_item_count.as<unsigned int>(), cap);
+						CK(cudaGetLastError());
+						ctx->stats.kernel_launches++;
+						CK(cudaMemcpyAsync(&n_np, ctx->d_item_count.p, 4, cudaMemcpyDeviceToHost, st));
+						CK(cudaStreamSynchronize(st));
+						if (n_np <= cap) break;
+						if (attempt >= 2) return fail(ctx, "pcramp_gpu_score_pairs: neighbour list kept overflowing");
+						CK(ctx->d_neigh.ensure((size_t)16 * ((size_t)n_np + n_np / 8 + 4096)));
+					}
+					unsigned long long *d_np = ctx->d_neigh.as<unsigned long long>();
+					if (n_np > 1) {
+						cub::DoubleBuffer<unsigned long long> dbuf(d_np, d_np + ctx->d_neigh.cap / 16);
+						size_t tb = 0;
+						const int end_bit = 32 + (int)bits_for((uint64_t)s.n_cand + 1);
+						CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dbuf, (int)n_np, 0, end_bit, st));
+						CK(ctx->cub_tmp.ensure(tb));
+						CK(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tb, dbuf, (int)n_np, 0, end_bit, st));
+						d_np = dbuf.Current();
+						ctx->stats.kernel_launches += 8;
+					}
+					neigh_offsets_kernel<<<grid_for((uint64_t)s.n_cand + 1, 256), 256, 0, st>>>(d_np, n_np, s.n_cand, ctx->d_neigh_off.as<uint32_t>());
+					const size_t row_bytes = (size_t)2 * s.n * nw * 4;
+					CK(ctx->d_seqbits.ensure(std::max<size_t>(4, row_bytes)));
+					CK(cudaMemsetAsync(ctx->d_seqbits.p, 0, row_bytes, st));
+					entry_neigh_kernel<<<grid_for(s.n_entries, 128), 128, 0, st>>>(d_np, ctx->d_neigh_off.as<uint32_t>(), d_ol, n_olig, s.e_planes.as<uint4>(),
+						s.e_seq.as<uint32_t>(), s.e_strand.as<uint32_t>(), s.e_cand.as<uint32_t>(), s.n_entries, nw, ctx->d_seqbits.as<uint32_t>());
+					CK(cudaGetLastError());
+					ctx->stats.kernel_launches += 2;
+				}
 				if (chunk_fst) {
 					uint32_t n_brute = 0;
 					if (fst_build(ctx, ctx->d_fst_planes.as<uint4>() + 2ull * p0, ctx->d_fst_thr.as<uint32_t>() + 2ull * p0, 2u * pc, fst, n_brute)) return 1;
 					if ((uint64_t)n_brute * 4u > 2ull * pc) chunk_fst = false; // mostly unseedable: the key matrix is the better brute force
 				}
-				if (chunk_fst) {
+				if (use_neigh) {
+				} else if (chunk_fst) {
 					const size_t row_bytes = (size_t)2 * s.n * nw * 4;
 					CK(ctx->d_seqbits.ensure(std::max<size_t>(4, row_bytes)));
 					CK(cudaMemsetAsync(ctx->d_seqbits.p, 0, row_bytes, st));
@@ -1252,7 +1306,7 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 				for (int attempt = 0;; ++attempt) {
 					CK(ctx->d_items.ensure(item_cap * sizeof(ScoreItem)));
 					CK(cudaMemsetAsync(ctx->d_item_count.p, 0, 16, st));
-					if (chunk_fst) {
+					if (chunk_fst || use_neigh) {
 						seq_pairs_kernel<<<grid_for((uint64_t)s.n * nw, 256), 256, 0, st>>>(s.dev(), s.seq_ent_off.as<uint32_t>(),
 							ctx->d_seqbits.as<uint32_t>(), nw, pc, ctx->d_items.as<ScoreItem>(), ctx->d_item_count.as<unsigned int>(),
 							(uint32_t)std::min<uint64_t>(item_cap, 0xFFFFFFF0ull));
@@ -1489,6 +1543,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "force_brute_scan") == 0) { ctx->force_brute = value; return 0; }
 	if (strcmp(name, "use_index") == 0) { ctx->use_index = value; return 0; }
 	if (strcmp(name, "use_seed_table") == 0) { ctx->use_fst = value; return 0; }
+	if (strcmp(name, "use_neighbours") == 0) { ctx->use_neigh = value; return 0; }
 	return fail(ctx, std::string("pcramp_gpu_set_option: unknown option ") + name);
 }
 

@@ -315,6 +315,78 @@ entry_match_kernel(Fst t, const uint4 *__restrict__ e_planes, const uint32_t *__
 	fst_match<false>(t, w, [&](uint32_t id, uint32_t) { atomicOr(row + (id >> 5), 1u << (id & 31u)); });
 }
 
+// ---- neighbour filter: match_words without a table walk ---------------------------------------------------------------
+// Every database entry W exists because some candidate word K of the select_words call reached its seed threshold on W
+// in-frame (at most e1 = size(K) - thr(K) slots of K miss).  If an oligo O also reaches ITS threshold on W (at most
+// e2 = size(O) - thr(O) misses), then on the slots K and O share, the letter of W is in both sets wherever neither misses, so
+// K and O have an empty intersection on at most e1 + e2 of their common slots.  (W must carry single letters for this: entries
+// holding a degenerate text base are compared with every oligo, as in the table walk.)  So the oligos that can match W are
+// among the "neighbours" of ONE candidate recorded for W (SeqSet::e_cand): a candidates x oligos comparison per batch
+// (2000 x 2000 set-intersection counts) leaves a short list per candidate -- the oligo itself, its shifted family, oligos cut
+// from the same place of a related target -- and every entry verifies only those.
+__global__ void __launch_bounds__(256) neigh_pairs_kernel(const uint4 *__restrict__ c_planes, const uint32_t *__restrict__ c_thr, uint32_t n_cand,
+	const OligoDev *__restrict__ olig, uint32_t n_olig, unsigned long long *pairs, unsigned int *count, uint32_t cap)
+{
+	__shared__ OligoDev s_o[256];
+	const uint32_t o0 = blockIdx.y * 256u;
+	const uint32_t no = min(256u, n_olig - o0);
+	if (threadIdx.x < no) s_o[threadIdx.x] = olig[o0 + threadIdx.x];
+	__syncthreads();
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_cand) return;
+	const uint4 kp = c_planes[k];
+	const uint32_t kocc = kp.x | kp.y | kp.z | kp.w;
+	const uint32_t kn = (uint32_t)__popc(kocc), kt = c_thr[k];
+	if (kt > kn) return; // a candidate that cannot reach its threshold produced no entry
+	const uint32_t e1 = kn - kt;
+	for (uint32_t j = 0; j < no; ++j) {
+		const OligoDev &o = s_o[j];
+		const uint32_t oocc = o.a | o.c | o.g | o.t;
+		const uint32_t on = (uint32_t)__popc(oocc), ot = o.packed & 255u;
+		if (ot > on) continue; // can never match (match_words compares against unsigned(size * thr^2))
+		const uint32_t inter = (kp.x & o.a) | (kp.y & o.c) | (kp.z & o.g) | (kp.w & o.t);
+		if ((uint32_t)__popc(kocc & oocc & ~inter) <= e1 + (on - ot)) {
+			const unsigned int at = atomicAdd(count, 1u);
+			if (at < cap) pairs[at] = ((unsigned long long)k << 32) | (o0 + j);
+		}
+	}
+}
+
+__global__ void neigh_offsets_kernel(const unsigned long long *__restrict__ pairs, uint32_t n_pairs, uint32_t n_cand, uint32_t *off)
+{
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k > n_cand) return;
+	const unsigned long long want = (unsigned long long)k << 32;
+	uint32_t lo = 0, hi = n_pairs;
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (pairs[mid] < want) lo = mid + 1; else hi = mid;
+	}
+	off[k] = lo;
+}
+
+__global__ void __launch_bounds__(128)
+entry_neigh_kernel(const unsigned long long *__restrict__ pairs, const uint32_t *__restrict__ off, const OligoDev *__restrict__ olig, uint32_t n_olig,
+	const uint4 *__restrict__ e_planes, const uint32_t *__restrict__ e_seq, const uint32_t *__restrict__ e_strand, const uint32_t *__restrict__ e_cand,
+	uint64_t n_ent, uint32_t n_words, uint32_t *seqbits)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_ent) return;
+	const uint4 w = __ldg(e_planes + e);
+	uint32_t *row = seqbits + ((size_t)__ldg(e_seq + e) * 2u + (__ldg(e_strand + e) == STRAND_MINUS ? 1u : 0u)) * n_words;
+	auto verify = [&](uint32_t id) {
+		const OligoDev o = olig[id];
+		if ((uint32_t)__popc((o.a & w.x) | (o.c & w.y) | (o.g & w.z) | (o.t & w.w)) >= (o.packed & 255u)) atomicOr(row + (id >> 5), 1u << (id & 31u));
+	};
+	const uint32_t multi = (w.x & w.y) | (w.x & w.z) | (w.x & w.w) | (w.y & w.z) | (w.y & w.w) | (w.z & w.w);
+	if (multi) { // a degenerate text base: the bound above does not hold, compare with everybody
+		for (uint32_t id = 0; id < n_olig; ++id) verify(id);
+		return;
+	}
+	const uint32_t k = __ldg(e_cand + e);
+	for (uint32_t i = __ldg(off + k), i1 = __ldg(off + k + 1u); i < i1; ++i) verify((uint32_t)pairs[i]);
+}
+
 struct ScoreItem;
 __global__ void seq_pairs_kernel(SeqDev sd, const uint32_t *__restrict__ seq_off2, const uint32_t *__restrict__ seqbits, uint32_t n_words, uint32_t n_pairs,
 	ScoreItem *items, unsigned int *n_items, uint32_t cap);

@@ -238,18 +238,25 @@ def test_seed_table_filter_equals_compare_all(gpu, name):
     for (s, p) in sc.splits:
         g.split_sequence(s, p)
     out = []
-    for use in (0, 1):
+    # (seed table, neighbour filter): compare-all; table walk (fst.cuh); neighbour lists of the generating candidate (score.cuh, the default)
+    for use, neigh in ((0, 0), (1, 0), (1, 1)):
         gpu.set_option("use_seed_table", use)
+        gpu.set_option("use_neighbours", neigh)
         try:
             g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
             db = _db_tuple(gpu)
             cov, bits = gpu.score_pairs(TARGET, sc.f, sc.r, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
-            out.append((db, cov, bits))
+            # other oligos than the ones the database was built for (what a move does): shifted / swapped pairs
+            cov2, bits2 = gpu.score_pairs(TARGET, sc.r, np.roll(sc.f, 1, axis=0), sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+            out.append((db, cov, bits, cov2, bits2))
         finally:
             gpu.set_option("use_seed_table", 1)
-    for a, b in zip(out[0][0], out[1][0]):
-        assert np.array_equal(a, b)
-    assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32)) and np.array_equal(out[0][2], out[1][2])
+            gpu.set_option("use_neighbours", 1)
+    for k in (1, 2):
+        for a, b in zip(out[0][0], out[k][0]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(out[0][1].view(np.uint32), out[k][1].view(np.uint32)) and np.array_equal(out[0][2], out[k][2])
+        assert np.array_equal(out[0][3].view(np.uint32), out[k][3].view(np.uint32)) and np.array_equal(out[0][4], out[k][4])
 
 
 def test_indexed_scan_large_vs_table_scan(gpu):
