@@ -130,6 +130,7 @@ struct pcramp_gpu_ctx {
 	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
 	unsigned long long *h_counters = nullptr; // pinned
 	pcramp_gpu_stats stats = {};
+	bool pend_ms_db = false, pend_ms_score = false; // event times of the last calls not read back yet (pcramp_gpu_get_stats)
 	pcr::nc::ThermoState *thermo = nullptr; // K3 state, created on first use (thermo_abi.cu)
 	pcramp_gpu_xchg *xchg = nullptr;        // multi-GPU exchange state (xchg.cuh)
 	pcramp_gpu_fasta *fasta[PCRAMP_NUM_KINDS] = {}; // record table of the last FASTA upload per collection (fasta.cuh)

@@ -680,6 +680,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	cudaStream_t st = ctx->stream;
 	pcramp_gpu_stats &stat = ctx->stats;
 	stat = pcramp_gpu_stats();
+	ctx->pend_ms_db = ctx->pend_ms_score = false;
 	s.db_valid = false;
 	s.n_entries = s.n_keys = 0;
 	if (n_entries_out) *n_entries_out = 0;
@@ -813,6 +814,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 			ix.cum = s.idx_cum.as<uint32_t>();
 			ix.n = s.idx_n;
 			IdxCandSink cs;
+			unsigned int h_idx[4] = {0, 0, 0, 0};
 			for (int grow = 0;; ++grow) { // candidates awaiting resolution: sized like the hit buffer, grown if they overflow
 				const uint64_t ccap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_cand.cap / sizeof(IdxCand), cap), 0xFFFFFFF0ull);
 				CK(ctx->d_idx_cand.ensure(ccap * sizeof(IdxCand)));
@@ -828,6 +830,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				stat.kernel_launches++;
 				unsigned int n_c = 0;
 				CK(cudaMemcpyAsync(&n_c, d_nq + 4, 4, cudaMemcpyDeviceToHost, st));
+				CK(cudaMemcpyAsync(h_idx, d_nq, 16, cudaMemcpyDeviceToHost, st)); // query / entry counters: same round trip
 				CK(cudaStreamSynchronize(st));
 				stat.ms_index_kernel = ev_ms(ctx->ev[8], ctx->ev[9]);
 				if (n_c <= cs.cap) break;
@@ -838,9 +841,6 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, cand_bits, hs);
 			CK(cudaGetLastError());
 			stat.kernel_launches += 2;
-			unsigned int h_idx[4] = {0, 0, 0, 0};
-			CK(cudaMemcpyAsync(h_idx, d_nq, 16, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
 			stat.n_index_queries = h_idx[0];
 			stat.n_indexed = h_idx[1];
 			stat.n_index_entries = (uint64_t)h_idx[2] | ((uint64_t)h_idx[3] << 32);
@@ -1043,8 +1043,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(cudaGetLastError());
 	stat.kernel_launches += 2;
 	CK(cudaEventRecord(ctx->ev[4], st));
-	CK(cudaStreamSynchronize(st));
-	stat.ms_db = ev_ms(ctx->ev[3], ctx->ev[4]);
+	ctx->pend_ms_db = true; // no host round trip here: pcramp_gpu_get_stats waits for the event when somebody asks
 	s.n_entries = n_ent;
 	s.n_keys = 0;
 	s.keys_valid = false;
@@ -1203,6 +1202,7 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 	CK(cudaMemsetAsync(ctx->d_bits1.p, 0, bits_bytes, st));
 	CK(cudaMemsetAsync(ctx->d_cov.p, 0, std::max<size_t>(1, n_pairs) * 4, st));
 	ctx->stats.ms_score = 0.0f;
+	ctx->pend_ms_score = false;
 	if (n_pairs && s.n) {
 		const float thr2 = search_threshold * search_threshold; // pcr_assay.cpp:31-32 (float product)
 		prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(d_f, d_r, n_pairs, thr2, ctx->d_oligos.as<OligoDev>());
@@ -1350,8 +1350,7 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 		}
 	}
 	CK(cudaEventRecord(ctx->ev[6], st));
-	CK(cudaStreamSynchronize(st));
-	ctx->stats.ms_score = ev_ms(ctx->ev[5], ctx->ev[6]);
+	ctx->pend_ms_score = true; // the results stay on the stream; fetch / exchange / get_stats synchronise when they need to
 	return 0;
 }
 
@@ -1550,6 +1549,16 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out)
 {
 	if (!ctx || !out) return 1;
+	if (ctx->pend_ms_db) {
+		CK(cudaEventSynchronize(ctx->ev[4]));
+		ctx->stats.ms_db = ev_ms(ctx->ev[3], ctx->ev[4]);
+		ctx->pend_ms_db = false;
+	}
+	if (ctx->pend_ms_score) {
+		CK(cudaEventSynchronize(ctx->ev[6]));
+		ctx->stats.ms_score = ev_ms(ctx->ev[5], ctx->ev[6]);
+		ctx->pend_ms_score = false;
+	}
 	*out = ctx->stats;
 	return 0;
 }
