@@ -125,8 +125,8 @@ struct pcramp_gpu_ctx {
 	int use_index = 1;
 	DevBuf d_idx_queries, d_idx_counters, d_idx_cand;
 	// scratch
-	DevBuf ent_cand[2], d_neigh, d_neigh_off;
-	int use_neigh = 1;
+	DevBuf ent_cand[2], d_neigh, d_neigh_off, d_tier_best;
+	int use_neigh = 1, use_tier_table = 1;
 	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
 	unsigned long long *h_counters = nullptr; // pinned
 	pcramp_gpu_stats stats = {};

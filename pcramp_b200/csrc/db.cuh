@@ -15,11 +15,12 @@
 
 namespace pcr {
 
-// entry id, low to high: pos[31:0] | type[33:32] | minus[34] | seq[35 ...]: sorted ids group a sequence's
-// plus-strand entries before its minus-strand entries (what pair scoring iterates over)
-__host__ __device__ __forceinline__ uint64_t entry_id_pack(uint32_t seq, uint32_t type, uint32_t minus, uint32_t pos)
+// entry id, low to high: pos[pb-1:0] | type[pb+1:pb] | minus[pb+2] | seq[pb+3 ...] with pb = bits of the longest sequence: sorted ids
+// group a sequence's plus-strand entries before its minus-strand entries (what pair scoring iterates over), and the radix sort of
+// the ids only has pb + 3 + seq_bits key bits to go through (33 for 20 000 x 30 kb: 5 passes, not 7)
+__host__ __device__ __forceinline__ uint64_t entry_id_pack(uint32_t seq, uint32_t type, uint32_t minus, uint32_t pos, uint32_t pb)
 {
-	return ((uint64_t)seq << 35) | ((uint64_t)minus << 34) | ((uint64_t)type << 32) | pos;
+	return ((uint64_t)seq << (pb + 3u)) | ((uint64_t)minus << (pb + 2u)) | ((uint64_t)type << pb) | pos;
 }
 
 __global__ void validate_hits_kernel(SeqDev sd, PackParams pp, uint64_t *hit_key, const uint32_t *hit_val, uint64_t n_hits,
@@ -37,7 +38,7 @@ __global__ void validate_hits_kernel(SeqDev sd, PackParams pp, uint64_t *hit_key
 
 // hits sorted ascending by key; invalidated hits (key == ~0) sort last
 __global__ void tier_kernel(const uint64_t *__restrict__ hit_key, const uint32_t *__restrict__ hit_val, uint64_t n_hits,
-	uint32_t cand_bits, uint64_t *entry_id, uint32_t *entry_cand, unsigned long long *n_out)
+	uint32_t cand_bits, uint32_t pb, uint64_t *entry_id, uint32_t *entry_cand, unsigned long long *n_out)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_hits) return;
@@ -52,23 +53,51 @@ __global__ void tier_kernel(const uint64_t *__restrict__ hit_key, const uint32_t
 	if ((hit_key[lo] >> 3) != (k >> 3)) return; // not in the best tier of its (seq, cand) group
 	const uint32_t seq = (uint32_t)(k >> (HIT_GROUP_SHIFT + cand_bits));
 	const unsigned long long o = atomicAdd(n_out, 1ull);
-	entry_id[o] = entry_id_pack(seq, (uint32_t)(k >> 1) & 3u, (uint32_t)k & 1u, hit_val[i]);
+	entry_id[o] = entry_id_pack(seq, (uint32_t)(k >> 1) & 3u, (uint32_t)k & 1u, hit_val[i], pb);
 	// one candidate word that reaches its seed threshold on this window: the anchor of the neighbour filter of pair scoring (score.cuh)
 	entry_cand[o] = (uint32_t)(k >> HIT_GROUP_SHIFT) & ((1u << cand_bits) - 1u);
 }
 
+// The same best-tier rule without sorting the hits: a (sequence, candidate) table of the best match count seen
+// (select_words.cpp:93-117 keeps, per candidate and sequence, only the words of the highest tier), filled with atomicMax and
+// read back by every hit.  Used when the table (4 bytes per cell) is small enough; the sorted variant above otherwise.
+__global__ void tier_best_kernel(const uint64_t *__restrict__ hit_key, uint64_t n_hits, uint32_t cand_bits, uint32_t n_cand, uint32_t *best)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_hits) return;
+	const uint64_t k = hit_key[i];
+	if (k == ~0ull) return;
+	const uint32_t seq = (uint32_t)(k >> (HIT_GROUP_SHIFT + cand_bits)), cand = (uint32_t)(k >> HIT_GROUP_SHIFT) & ((1u << cand_bits) - 1u);
+	atomicMax(best + (size_t)seq * n_cand + cand, 64u - ((uint32_t)(k >> 3) & 63u)); // count + 1
+}
+
+__global__ void tier_table_kernel(const uint64_t *__restrict__ hit_key, const uint32_t *__restrict__ hit_val, uint64_t n_hits, uint32_t cand_bits,
+	uint32_t n_cand, const uint32_t *__restrict__ best, uint32_t pb, uint64_t *entry_id, uint32_t *entry_cand, unsigned long long *n_out)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_hits) return;
+	const uint64_t k = hit_key[i];
+	if (k == ~0ull) return;
+	const uint32_t seq = (uint32_t)(k >> (HIT_GROUP_SHIFT + cand_bits)), cand = (uint32_t)(k >> HIT_GROUP_SHIFT) & ((1u << cand_bits) - 1u);
+	if (best[(size_t)seq * n_cand + cand] != 64u - ((uint32_t)(k >> 3) & 63u)) return; // not in the best tier of its (seq, cand) group
+	const unsigned long long o = atomicAdd(n_out, 1ull);
+	entry_id[o] = entry_id_pack(seq, (uint32_t)(k >> 1) & 3u, (uint32_t)k & 1u, hit_val[i], pb);
+	entry_cand[o] = cand;
+}
+
 // word, loc, strand, seq of each unique entry (entry ids sorted => grouped by sequence)
-__global__ void materialise_kernel(SeqDev sd, PackParams pp, const uint64_t *__restrict__ entry_id, uint64_t n, uint64_t *w_hi,
+__global__ void materialise_kernel(SeqDev sd, PackParams pp, const uint64_t *__restrict__ entry_id, uint64_t n, uint32_t pb, uint64_t *w_hi,
 	uint64_t *w_lo, uint4 *e_planes, uint32_t *e_seq, int32_t *e_loc, uint32_t *e_strand, uint64_t *order_key)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint64_t id = entry_id[i];
-	const uint32_t seq = (uint32_t)(id >> 35), type = (uint32_t)(id >> 32) & 3u, minus = (uint32_t)(id >> 34) & 1u;
+	const uint32_t seq = (uint32_t)(id >> (pb + 3u)), type = (uint32_t)(id >> pb) & 3u, minus = (uint32_t)(id >> (pb + 2u)) & 1u;
+	const uint32_t pos = (uint32_t)(id & ((1ull << pb) - 1ull));
 	W128 wp, wm;
 	int lp = 0, lm = 0;
 	wp.hi = wp.lo = wm.hi = wm.lo = 0;
-	pack_entry(sd, seq, type, (uint32_t)id, pp, wp, wm, lp, lm); // validated earlier, always true here
+	pack_entry(sd, seq, type, pos, pp, wp, wm, lp, lm); // validated earlier, always true here
 	const W128 w = minus ? wm : wp;
 	const int loc = minus ? lm : lp;
 	w_hi[i] = w.hi;

@@ -972,6 +972,25 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		CK(cudaGetLastError());
 		stat.kernel_launches++;
 	}
+	CK(ctx->ent_id[0].ensure(n_hits * 8));
+	CK(ctx->ent_id[1].ensure(n_hits * 8));
+	CK(ctx->ent_cand[0].ensure(n_hits * 4));
+	CK(ctx->ent_cand[1].ensure(n_hits * 4));
+	CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
+	uint32_t longest = 0;
+	for (uint32_t L : s.plen) longest = std::max(longest, L);
+	const uint32_t pos_bits = std::min<uint32_t>(32u, bits_for((uint64_t)longest + 64ull)); // hit positions are below plen + 32
+	const uint64_t tier_cells = (uint64_t)s.n * n_cand;
+	if (ctx->use_tier_table && tier_cells <= (1ull << 27)) {
+		// best tier per (sequence, candidate) through a table of maxima: no sort of the hit list
+		CK(ctx->d_tier_best.ensure(std::max<uint64_t>(1, tier_cells) * 4));
+		CK(cudaMemsetAsync(ctx->d_tier_best.p, 0, tier_cells * 4, st));
+		tier_best_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), n_hits, cand_bits, n_cand, ctx->d_tier_best.as<uint32_t>());
+		tier_table_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), ctx->hit_val[0].as<uint32_t>(), n_hits, cand_bits, n_cand,
+			ctx->d_tier_best.as<uint32_t>(), pos_bits, ctx->ent_id[0].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>(), d_cnt);
+		CK(cudaGetLastError());
+		stat.kernel_launches += 2;
+	} else {
 	CK(ctx->hit_key[1].ensure(n_hits * 8));
 	CK(ctx->hit_val[1].ensure(n_hits * 4));
 	// all 64 bits when hits may have been invalidated to ~0 (they must sort last), else only the used field
@@ -982,15 +1001,11 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->hit_key[0].as<uint64_t>(), ctx->hit_key[1].as<uint64_t>(),
 		ctx->hit_val[0].as<uint32_t>(), ctx->hit_val[1].as<uint32_t>(), (int64_t)n_hits, 3, sort_end, st));
 	stat.kernel_launches += 8;
-	CK(ctx->ent_id[0].ensure(n_hits * 8));
-	CK(ctx->ent_id[1].ensure(n_hits * 8));
-	CK(ctx->ent_cand[0].ensure(n_hits * 4));
-	CK(ctx->ent_cand[1].ensure(n_hits * 4));
-	CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
-	tier_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[1].as<uint64_t>(), ctx->hit_val[1].as<uint32_t>(), n_hits, cand_bits,
+	tier_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[1].as<uint64_t>(), ctx->hit_val[1].as<uint32_t>(), n_hits, cand_bits, pos_bits,
 		ctx->ent_id[0].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>(), d_cnt);
 	CK(cudaGetLastError());
 	stat.kernel_launches++;
+	}
 	CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	const uint64_t n_flag = ctx->h_counters[0];
@@ -1004,10 +1019,10 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	// ---- unique entries -------------------------------------------------------------------------
 	// (the candidate of each flagged hit rides along; any one of an entry's candidates will do, so the first is kept)
 	CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->ent_id[0].as<uint64_t>(), ctx->ent_id[1].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>(),
-		ctx->ent_cand[1].as<uint32_t>(), (int64_t)n_flag, 0, (int)(35 + seq_bits), st));
+		ctx->ent_cand[1].as<uint32_t>(), (int64_t)n_flag, 0, (int)(pos_bits + 3 + seq_bits), st));
 	CK(ctx->cub_tmp.ensure(tmp_bytes));
 	CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->ent_id[0].as<uint64_t>(), ctx->ent_id[1].as<uint64_t>(),
-		ctx->ent_cand[0].as<uint32_t>(), ctx->ent_cand[1].as<uint32_t>(), (int64_t)n_flag, 0, (int)(35 + seq_bits), st));
+		ctx->ent_cand[0].as<uint32_t>(), ctx->ent_cand[1].as<uint32_t>(), (int64_t)n_flag, 0, (int)(pos_bits + 3 + seq_bits), st));
 	CK(cub::DeviceSelect::UniqueByKey(nullptr, tmp_bytes, ctx->ent_id[1].as<uint64_t>(), ctx->ent_cand[1].as<uint32_t>(), ctx->ent_id[0].as<uint64_t>(),
 		ctx->ent_cand[0].as<uint32_t>(), d_cnt + 1, (int64_t)n_flag, st));
 	CK(ctx->cub_tmp.ensure(tmp_bytes));
@@ -1035,7 +1050,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(cudaMemcpyAsync(s.c_thr.p, ctx->d_cand_thr.p, (size_t)n_cand * 4, cudaMemcpyDeviceToDevice, st));
 	s.n_cand = n_cand;
 	const unsigned ge = grid_for(n_ent, 256);
-	materialise_kernel<<<ge, 256, 0, st>>>(sd, pp, ctx->ent_id[0].as<uint64_t>(), n_ent, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(),
+	materialise_kernel<<<ge, 256, 0, st>>>(sd, pp, ctx->ent_id[0].as<uint64_t>(), n_ent, pos_bits, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(),
 		s.e_planes.as<uint4>(), s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(), s.e_order.as<uint64_t>());
 	CK(cudaGetLastError());
 	seq_offsets_kernel<<<grid_for(2ull * s.n + 1, 256), 256, 0, st>>>(s.e_seq.as<uint32_t>(), s.e_strand.as<uint32_t>(), n_ent, s.n,
@@ -1543,6 +1558,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_index") == 0) { ctx->use_index = value; return 0; }
 	if (strcmp(name, "use_seed_table") == 0) { ctx->use_fst = value; return 0; }
 	if (strcmp(name, "use_neighbours") == 0) { ctx->use_neigh = value; return 0; }
+	if (strcmp(name, "use_tier_table") == 0) { ctx->use_tier_table = value; return 0; }
 	return fail(ctx, std::string("pcramp_gpu_set_option: unknown option ") + name);
 }
 

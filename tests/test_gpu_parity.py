@@ -259,6 +259,27 @@ def test_seed_table_filter_equals_compare_all(gpu, name):
         assert np.array_equal(out[0][3].view(np.uint32), out[k][3].view(np.uint32)) and np.array_equal(out[0][4], out[k][4])
 
 
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_tier_table_equals_sorted_tiers(gpu, name):
+    """select_words' best-tier rule through the (sequence, candidate) table of maxima == through the sorted hit list"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    out = []
+    for use in (0, 1):
+        gpu.set_option("use_tier_table", use)
+        try:
+            g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+            out.append(_db_tuple(gpu))
+        finally:
+            gpu.set_option("use_tier_table", 1)
+    assert len(out[0][0]) > 0
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
 def test_indexed_scan_large_vs_table_scan(gpu):
     """a collection of several tiles per sequence with degenerate text, EOS and degenerate primers: index path == table path
     (both also equal the oracle in the next test), and most patterns take the index"""
