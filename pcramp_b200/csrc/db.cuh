@@ -52,7 +52,7 @@ __global__ void tier_kernel(const uint64_t *__restrict__ hit_key, const uint32_t
 	}
 	if ((hit_key[lo] >> 3) != (k >> 3)) return; // not in the best tier of its (seq, cand) group
 	const uint32_t seq = (uint32_t)(k >> (HIT_GROUP_SHIFT + cand_bits));
-	const unsigned long long o = atomicAdd(n_out, 1ull);
+	const unsigned long long o = warp_slot(n_out);
 	entry_id[o] = entry_id_pack(seq, (uint32_t)(k >> 1) & 3u, (uint32_t)k & 1u, hit_val[i], pb);
 	// one candidate word that reaches its seed threshold on this window: the anchor of the neighbour filter of pair scoring (score.cuh)
 	entry_cand[o] = (uint32_t)(k >> HIT_GROUP_SHIFT) & ((1u << cand_bits) - 1u);
@@ -80,7 +80,7 @@ __global__ void tier_table_kernel(const uint64_t *__restrict__ hit_key, const ui
 	if (k == ~0ull) return;
 	const uint32_t seq = (uint32_t)(k >> (HIT_GROUP_SHIFT + cand_bits)), cand = (uint32_t)(k >> HIT_GROUP_SHIFT) & ((1u << cand_bits) - 1u);
 	if (best[(size_t)seq * n_cand + cand] != 64u - ((uint32_t)(k >> 3) & 63u)) return; // not in the best tier of its (seq, cand) group
-	const unsigned long long o = atomicAdd(n_out, 1ull);
+	const unsigned long long o = warp_slot(n_out);
 	entry_id[o] = entry_id_pack(seq, (uint32_t)(k >> 1) & 3u, (uint32_t)k & 1u, hit_val[i], pb);
 	entry_cand[o] = cand;
 }

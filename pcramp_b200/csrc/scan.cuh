@@ -70,9 +70,22 @@ struct HitSink {
 	uint64_t cap;
 };
 
+// One slot of a list behind a 64-bit counter, one atomic per group of converged lanes (the lanes of a warp that reach this
+// call together): millions of appends to ONE counter otherwise serialise in L2 (64-bit adds are not merged by the compiler).
+__device__ __forceinline__ unsigned long long warp_slot(unsigned long long *counter)
+{
+	const unsigned m = __activemask();
+	const unsigned lane = threadIdx.x & 31u;
+	const int leader = __ffs(m) - 1;
+	unsigned long long base = 0;
+	if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+	base = __shfl_sync(m, base, leader);
+	return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void hit_append(const HitSink &hs, uint64_t key, uint32_t val)
 {
-	const unsigned long long i = atomicAdd(hs.count, 1ull);
+	const unsigned long long i = warp_slot(hs.count);
 	if (i < hs.cap) {
 		hs.key[i] = key;
 		hs.val[i] = val;
