@@ -55,6 +55,9 @@ int pcramp_gpu_set_weights(pcramp_gpu_ctx *ctx, int kind, const float *weight);
 int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active);
 /* Sequence::split_sequence (sequence.h:231-243; called at main.cpp:1010-1016). */
 int pcramp_gpu_split_sequence(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pos);
+/* The same for n (sequence, position) pairs in one call: one rebuild of the device-side text for the whole list (the loop of
+ * main.cpp:1008-1017 issues three splits per amplicon). */
+int pcramp_gpu_split_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const uint32_t *seq, const uint32_t *pos);
 
 /* Sequence::pack (sequence.cpp:92-267) of ONE sequence: every (word, loc, strand) it would insert, in no
  * particular order.  The scan below never materialises this list; the call exists so that the device-side
@@ -170,6 +173,40 @@ int pcramp_gpu_multiplex_coverage(pcramp_gpu_ctx *ctx, const uint64_t *base_f, c
 /* PCR::compute_oligo_overlap (pcr_assay.cpp:736-754) of n_pairs assays against the pool: Word::max_overlap
  * (word.h:38-92) of each oligo with every pool oligo, MULTIPLEX_OLIGO_REUSE_BONUS for an exact reuse. */
 int pcramp_gpu_oligo_overlap(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, float *overlap);
+
+/* ---- multiplex bookkeeping on the device ----------------------------------------------------------
+ * pcramp_gpu_unique_amplicons: PCR::collect_unique_amplicons (pcr_assay.cpp:756-813) with extract_amplicon_seq
+ * (:443-542) for n_pairs assays against the database pcramp_gpu_select_words built on `kind`: threshold =
+ * opt.target_threshold (match_words at threshold^2), amplicon range = opt.target_amplicon_range.  The amplicons stay
+ * in HBM as regions of the collection; n_amplicons = distinct amplicon strings summed over the pairs, n_bases = their
+ * total length, n_bounds = candidate amplicons before the strings are made unique (one AmpliconBounds each, assay.h:64-90).
+ * want_bounds != 0 is the call with m_bounds_ptr (main.cpp:920): a negative begin then fails with the reference's
+ * ":AmpliconBounds(): Amplicon begin > amplicon end".  A region that leaves its sequence is undefined in the reference
+ * (unchecked deque index, sequence.h:223-228) and is dropped here like a region holding an EOS.
+ * pcramp_gpu_unique_amplicons_copy (any output may be NULL): pair_off[n_pairs + 1] = first amplicon of every pair;
+ * text_off[n_amplicons + 1] / text = the strings (bits_to_base letters, no terminators) in the order of the returned
+ * deque<Sequence> (sorted, unique) pair after pair; bounds_pair[n_bounds] / bounds[3 * n_bounds] = pair and
+ * {index, begin, end} of every AmpliconBounds in the reference's push order, pair after pair. */
+int pcramp_gpu_unique_amplicons(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r, uint32_t n_pairs, float threshold,
+	int amplicon_min, int amplicon_max, int want_bounds, uint64_t *n_amplicons, uint64_t *n_bases, uint64_t *n_bounds);
+int pcramp_gpu_unique_amplicons_copy(pcramp_gpu_ctx *ctx, uint32_t *pair_off, uint64_t *text_off, char *text, uint32_t *bounds_pair,
+	uint32_t *bounds);
+/* main.cpp:783-803 for n_pairs trial assays: collect_unique_amplicons (no bounds), then find_multiplex_background_match
+ * (background_match.cpp:168-295) of EVERY assay of the pool (pcramp_gpu_set_pool / pcramp_gpu_accept_assay) against those
+ * amplicons, accumulated in one bitset, and weighted_coverage (main.cpp:1402-1418) of it: coverage[i] = the number of
+ * distinct amplicons of assay i that some pool primer (either strand) aligns to with a normalised Smith-Waterman score >=
+ * background_threshold. */
+int pcramp_gpu_pool_amplicon_coverage(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r, uint32_t n_pairs,
+	float target_threshold, int amplicon_min, int amplicon_max, float background_threshold, int use_taq_mama, float *coverage);
+/* main.cpp:989-1017 + :1123 for assay `pair` of the last pcramp_gpu_unique_amplicons(want_bounds = 1) call, nothing
+ * leaving the device: its amplicons are appended to the PCRAMP_MULTIPLEX collection (index = its size so far, weight 1,
+ * active), keys() of the multiplex background database is rebuilt (as pcramp_gpu_multiplex_keys: n_multiplex_keys), the
+ * assay joins the pool, and the collection the amplicons were cut from is split at begin, (begin + end) / 2 and end of
+ * every AmpliconBounds.  n_added = amplicons appended.  The word database of the split collection is dropped (the next
+ * design iteration rebuilds it, main.cpp:574-631); marking the amplified targets inactive stays with the caller
+ * (pcramp_gpu_set_active). */
+int pcramp_gpu_accept_assay(pcramp_gpu_ctx *ctx, uint32_t pair, uint32_t pack_max_degen, uint32_t min_oligo_length, uint64_t *n_added,
+	uint64_t *n_multiplex_keys);
 
 /* ---- resident variants: the same two steps with the pairs already staged in HBM and the results
  *      left in HBM (what a multi-batch driver, the NCCL exchange and bench.py's `value` use). -------- */

@@ -777,4 +777,110 @@ int ref_oligo_overlap(uint32_t n, const uint64_t *f, const uint64_t *r, uint32_t
 	return 0;
 }
 
+// ---- multiplex bookkeeping ---------------------------------------------------------------------------------
+// PCR::collect_unique_amplicons (pcr_assay.cpp:756-813) of one assay against the context's database and sequences.
+// counts[0] = amplicons returned, counts[1] = their total length, counts[2] = AmpliconBounds pushed.  text_off / text / bounds
+// (may be NULL: sizing call) receive the returned Sequences spelled with bits_to_base, and {index, begin, end} per bound.
+int ref_unique_amplicons(void *h, const uint64_t *f, const uint64_t *r, float threshold, int amp_min, int amp_max, int want_bounds,
+	uint64_t *counts, uint64_t *text_off, char *text, uint32_t *bounds)
+{
+	RefCtx *c = (RefCtx *)h;
+	return guarded(c, [&]() {
+		PCR p;
+		p.oligo(FORWARD, make_word(f));
+		p.oligo(REVERSE, make_word(r));
+		deque<AmpliconBounds> b;
+		const deque<Sequence> amp = p.collect_unique_amplicons(c->db_keys, c->db, c->seq, threshold, make_pair(amp_min, amp_max),
+			want_bounds ? &b : NULL);
+		uint64_t total = 0;
+		for (size_t i = 0; i < amp.size(); ++i) {
+			if (text_off) text_off[i] = total;
+			if (text)
+				for (unsigned int k = 0; k < amp[i].length(); ++k) text[total + k] = bits_to_base(amp[i][k]);
+			total += amp[i].length();
+		}
+		if (text_off) text_off[amp.size()] = total;
+		if (bounds)
+			for (size_t i = 0; i < b.size(); ++i) {
+				bounds[3 * i] = b[i].index;
+				bounds[3 * i + 1] = b[i].begin;
+				bounds[3 * i + 2] = b[i].end;
+			}
+		counts[0] = amp.size();
+		counts[1] = total;
+		counts[2] = b.size();
+	});
+}
+
+// main.cpp:783-803 for every trial assay: its unique amplicons against every assay of the pool through
+// PCR::find_multiplex_background_match (background_match.cpp:168-295), one bitset accumulated over the pool, then the sum
+// of weighted_coverage (main.cpp:1402-1418; main.o is not linked: its five lines -- a double sum of Sequence::weight over the
+// set bits, returned as float -- are spelled out here).
+int ref_pool_amplicon_coverage(void *h, uint32_t n_pairs, const uint64_t *f, const uint64_t *r, uint32_t n_pool, const uint64_t *pool_f,
+	const uint64_t *pool_r, float target_threshold, int amp_min, int amp_max, float background_threshold, int taq_mama, float *coverage)
+{
+	RefCtx *c = (RefCtx *)h;
+	Options opt;
+	opt.background_threshold = background_threshold;
+	opt.use_taq_mama = (taq_mama != 0);
+	deque<PCR> pool;
+	for (uint32_t i = 0; i < n_pool; ++i) {
+		PCR q;
+		q.oligo(FORWARD, make_word(pool_f + 2 * i));
+		q.oligo(REVERSE, make_word(pool_r + 2 * i));
+		pool.push_back(q);
+	}
+	int fail = 0;
+	#pragma omp parallel for schedule(dynamic)
+	for (uint32_t t = 0; t < n_pairs; ++t) {
+		try {
+			PCR p;
+			p.oligo(FORWARD, make_word(f + 2 * t));
+			p.oligo(REVERSE, make_word(r + 2 * t));
+			const deque<Sequence> amplicons = p.collect_unique_amplicons(c->db_keys, c->db, c->seq, target_threshold, make_pair(amp_min, amp_max));
+			BitSet local(amplicons.size(), false);
+			ostringstream sink;
+			for (deque<PCR>::const_iterator i = pool.begin(); i != pool.end(); ++i) i->find_multiplex_background_match(local, amplicons, opt, sink);
+			double ret = 0.0;
+			for (size_t i = 0; i < amplicons.size(); ++i)
+				if (local[i]) ret += amplicons[i].weight();
+			coverage[t] = ret;
+		} catch (...) {
+			#pragma omp critical
+			fail = 1;
+		}
+	}
+	if (fail) c->err = "exception inside ref_pool_amplicon_coverage";
+	return fail;
+}
+
+// main.cpp:989-1017 with the reference's own calls: the amplicons of the assay are appended to the multiplex context `h_m`
+// (whose database / keys are rebuilt by pack() of every sequence, as ref_pack_all) and the sequences of `h` are split at begin,
+// centre and end of every bound.  Returns the number of amplicons appended or -1.
+long ref_accept_assay(void *h, void *h_m, const uint64_t *f, const uint64_t *r, float threshold, int amp_min, int amp_max, uint32_t pack_max_degen,
+	uint32_t min_len)
+{
+	RefCtx *c = (RefCtx *)h, *m = (RefCtx *)h_m;
+	long n = -1;
+	guarded(c, [&]() {
+		PCR p;
+		p.oligo(FORWARD, make_word(f));
+		p.oligo(REVERSE, make_word(r));
+		deque<AmpliconBounds> bounds;
+		const deque<Sequence> amplicons = p.collect_unique_amplicons(c->db_keys, c->db, c->seq, threshold, make_pair(amp_min, amp_max), &bounds);
+		for (deque<Sequence>::const_iterator i = amplicons.begin(); i != amplicons.end(); ++i) {
+			i->pack(m->db, m->seq.size(), pack_max_degen, 0.0, 1.0, min_len);
+			m->seq.push_back(*i);
+		}
+		m->db_keys = keys(m->db);
+		for (deque<AmpliconBounds>::const_iterator i = bounds.begin(); i != bounds.end(); ++i) {
+			c->seq[i->index].split_sequence(i->begin);
+			c->seq[i->index].split_sequence((i->begin + i->end) / 2);
+			c->seq[i->index].split_sequence(i->end);
+		}
+		n = (long)amplicons.size();
+	});
+	return n;
+}
+
 } // extern "C"

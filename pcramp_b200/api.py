@@ -103,6 +103,13 @@ SIGNATURES = {
     "pcramp_gpu_set_active": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u8p]),
     "pcramp_gpu_set_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _f32p]),
     "pcramp_gpu_split_sequence": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]),
+    "pcramp_gpu_split_sequences": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, _u32p, _u32p]),
+    "pcramp_gpu_unique_amplicons": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_int, _u64p, _u64p, _u64p]),
+    "pcramp_gpu_unique_amplicons_copy": (ctypes.c_int, [ctypes.c_void_p, _u32p, _u64p, ctypes.c_char_p, _u32p, _u32p]),
+    "pcramp_gpu_pool_amplicon_coverage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int,
+                                                         ctypes.c_int, ctypes.c_float, ctypes.c_int, _f32p]),
+    "pcramp_gpu_accept_assay": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u64p, _u64p]),
     "pcramp_gpu_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_uint32, ctypes.c_uint64, _u64p, _i32p, _u32p, _u64p]),
     "pcramp_gpu_select_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
@@ -266,6 +273,53 @@ class PcrampGpu:
 
     def split_sequence(self, kind, seq, pos):
         self._ck(self.lib.pcramp_gpu_split_sequence(self.h, kind, int(seq), int(pos)))
+
+    def split_sequences(self, kind, seq, pos):
+        seq, pos = np.ascontiguousarray(seq, dtype=np.uint32), np.ascontiguousarray(pos, dtype=np.uint32)
+        self._ck(self.lib.pcramp_gpu_split_sequences(self.h, kind, len(seq), _ptr(seq, _u32p), _ptr(pos, _u32p)))
+
+    # ---- multiplex bookkeeping (amplicon.cuh) --------------------------------------------------
+    def unique_amplicons(self, kind, f, r, threshold, amplicon_min=80, amplicon_max=200, want_bounds=True, copy=True):
+        """PCR::collect_unique_amplicons for every pair -> list per pair of (amplicon strings in the returned deque's order,
+        bounds (n, 3) uint32 {index, begin, end} in push order); copy=False leaves everything on the device and returns the counts"""
+        f, r = _words(f), _words(r)
+        cnt = np.zeros(3, np.uint64)
+        self._ck(self.lib.pcramp_gpu_unique_amplicons(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), len(f), float(threshold), int(amplicon_min),
+                                                      int(amplicon_max), int(bool(want_bounds)), _ptr(cnt[0:1], _u64p), _ptr(cnt[1:2], _u64p),
+                                                      _ptr(cnt[2:3], _u64p)))
+        n_amp, n_bases, n_bounds = (int(x) for x in cnt)
+        if not copy:
+            return n_amp, n_bases, n_bounds
+        pair_off = np.zeros(len(f) + 1, np.uint32)
+        text_off = np.zeros(n_amp + 1, np.uint64)
+        text = ctypes.create_string_buffer(max(1, n_bases))
+        b_pair = np.zeros(max(1, n_bounds), np.uint32)
+        bounds = np.zeros((max(1, n_bounds), 3), np.uint32)
+        self._ck(self.lib.pcramp_gpu_unique_amplicons_copy(self.h, _ptr(pair_off, _u32p), _ptr(text_off, _u64p), text, _ptr(b_pair, _u32p),
+                                                           _ptr(bounds, _u32p) if want_bounds else None))
+        raw = text.raw[:n_bases]
+        b_pair, bounds = b_pair[:n_bounds], bounds[:n_bounds]
+        out = []
+        for p in range(len(f)):
+            amps = [raw[int(text_off[u]):int(text_off[u + 1])].decode("ascii") for u in range(int(pair_off[p]), int(pair_off[p + 1]))]
+            out.append((amps, bounds[b_pair == p].copy() if want_bounds else None))
+        return out
+
+    def pool_amplicon_coverage(self, kind, f, r, target_threshold, amplicon_min, amplicon_max, background_threshold, use_taq_mama=False):
+        f, r = _words(f), _words(r)
+        cov = np.zeros(len(f), np.float32)
+        self._ck(self.lib.pcramp_gpu_pool_amplicon_coverage(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), len(f), float(target_threshold),
+                                                            int(amplicon_min), int(amplicon_max), float(background_threshold), int(use_taq_mama),
+                                                            _ptr(cov, _f32p)))
+        return cov
+
+    def accept_assay(self, pair=0, pack_max_degen=256, min_oligo_length=18):
+        """main.cpp:989-1017,1123 for one pair of the last unique_amplicons(want_bounds=True) call -> (amplicons appended, multiplex keys)"""
+        out = np.zeros(2, np.uint64)
+        self._ck(self.lib.pcramp_gpu_accept_assay(self.h, int(pair), int(pack_max_degen), int(min_oligo_length), _ptr(out[0:1], _u64p),
+                                                  _ptr(out[1:2], _u64p)))
+        self.n_seq[MULTIPLEX] = self.n_seq.get(MULTIPLEX, 0) + int(out[0])
+        return int(out[0]), int(out[1])
 
     def pack(self, kind, seq, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0, min_oligo_length=18):
         """Sequence::pack of one sequence -> (words, loc, strand), unordered."""

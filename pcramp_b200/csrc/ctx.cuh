@@ -139,6 +139,14 @@ struct pcramp_gpu_ctx {
 	uint64_t mpx_n_keys = 0;
 	bool mpx_valid = false;
 	std::vector<uint64_t> pool_words; // F0 R0 F1 R1 ... (2 x uint64 each)
+	// unique amplicons of the last pcramp_gpu_unique_amplicons call (amplicon.cuh): candidate records in the reference's order
+	// (region = sequence, first base, length; bounds), and the records that stand for the distinct amplicon strings of every pair
+	DevBuf amp_seq, amp_start, amp_len, amp_pair, amp_bounds, amp_uniq, amp_pair_off, amp_text_off, amp_flags;
+	uint64_t amp_n_rec = 0, amp_n_uniq = 0, amp_n_bases = 0;
+	uint32_t amp_n_pairs = 0;
+	int amp_kind = -1;
+	bool amp_bounds_ok = false;
+	std::vector<uint64_t> amp_words; // F0 R0 F1 R1 ... of that call
 };
 
 namespace pcr {

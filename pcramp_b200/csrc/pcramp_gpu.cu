@@ -90,11 +90,13 @@ __global__ void planes_compact_kernel(const uint8_t *__restrict__ raw, const uin
 	}
 }
 
-__global__ void set_raw_nibble_kernel(uint8_t *raw, uint64_t byte, uint32_t low, uint32_t value)
-{
-	uint8_t v = raw[byte];
-	v = low ? (uint8_t)((v & 0xF0u) | value) : (uint8_t)((v & 0x0Fu) | (value << 4));
-	raw[byte] = v;
+__global__ void clear_raw_nibbles_kernel(uint32_t *raw, const uint64_t *__restrict__ nib, uint32_t n)
+{ // nibble q of the collection (even = high half of byte q / 2) becomes EOS (0); several splits may share a 32-bit word
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t byte = nib[i] >> 1;
+	const uint32_t shift = 8u * (uint32_t)(byte & 3ull) + ((nib[i] & 1ull) ? 0u : 4u); // little-endian bytes inside the word
+	atomicAnd(raw + (byte >> 2), ~(15u << shift));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -517,27 +519,47 @@ int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active)
 	return 0;
 }
 
-int pcramp_gpu_split_sequence(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pos)
-{
+int pcramp_gpu_split_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const uint32_t *seq, const uint32_t *pos)
+{ // Sequence::split_sequence (sequence.h:231-243) for a list of positions, e.g. the three splits per amplicon of main.cpp:1008-1017
 	if (check_kind(ctx, kind)) return 1;
 	SeqSet &s = ctx->sets[kind];
-	if (seq >= s.n || pos >= s.len[seq]) return fail(ctx, "pcramp_gpu_split_sequence: out of range");
-	std::vector<uint32_t> &e = s.eos[seq];
-	auto it = std::lower_bound(e.begin(), e.end(), pos);
-	if (it != e.end() && *it == pos) return 0; // already EOS
-	e.insert(it, pos);
-	s.clen[seq] -= 1;
+	if (n && (!seq || !pos)) return fail(ctx, "pcramp_gpu_split_sequences: null argument");
+	for (uint32_t i = 0; i < n; ++i)
+		if (seq[i] >= s.n || pos[i] >= s.len[seq[i]]) return fail(ctx, "pcramp_gpu_split_sequence: out of range");
+	CK(cudaSetDevice(ctx->device));
+	std::vector<uint64_t> nib; // global nibble index of every position that becomes EOS now
+	std::vector<uint32_t> touched;
+	for (uint32_t i = 0; i < n; ++i) {
+		std::vector<uint32_t> &e = s.eos[seq[i]];
+		auto it = std::lower_bound(e.begin(), e.end(), pos[i]);
+		if (it != e.end() && *it == pos[i]) continue; // already EOS
+		e.insert(it, pos[i]);
+		s.clen[seq[i]] -= 1;
+		nib.push_back(2 * s.raw_off[seq[i]] + pos[i]);
+		touched.push_back(seq[i]);
+	}
+	if (nib.empty()) return 0;
+	std::sort(touched.begin(), touched.end());
+	touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
 	s.db_valid = false;
 	if (kind == PCRAMP_MULTIPLEX) ctx->mpx_valid = false;
 	s.idx_valid = s.idx_failed = false;
-	set_raw_nibble_kernel<<<1, 1, 0, ctx->stream>>>(s.d_raw.as<uint8_t>(), s.raw_off[seq] + pos / 2, pos & 1u, 0u);
+	DevBuf d_nib;
+	CK(d_nib.ensure(nib.size() * 8));
+	CK(cudaMemcpyAsync(d_nib.p, nib.data(), nib.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+	clear_raw_nibbles_kernel<<<grid_for(nib.size(), 128), 128, 0, ctx->stream>>>(s.d_raw.as<uint32_t>(), d_nib.as<uint64_t>(), (uint32_t)nib.size());
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(s.d_clen.as<uint32_t>() + seq, &s.clen[seq], 4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(s.d_clen.p, s.clen.data(), (size_t)s.n * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	if (upload_eos(ctx, s)) return 1;
-	if (compact_sequences(ctx, s, std::vector<uint32_t>(1, seq))) return 1;
-	if (rebuild_dirty(ctx, s)) return 1; // the compressed text moved by one base
+	if (compact_sequences(ctx, s, touched)) return 1;
+	if (rebuild_dirty(ctx, s)) return 1; // the compressed text moved
 	return rebuild_tiles(ctx, s);
+}
+
+int pcramp_gpu_split_sequence(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pos)
+{
+	return pcramp_gpu_split_sequences(ctx, kind, 1, &seq, &pos);
 }
 
 int pcramp_gpu_pack(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pack_max_degen, float min_gc, float max_gc, uint32_t min_len,
@@ -1680,3 +1702,4 @@ float pcramp_word_max_overlap(const uint64_t a[2], const uint64_t b[2])
 #include "xchg.cuh" // multi-GPU: peer-memory exchange of the shards' bitsets fused into the tail of pair scoring
 #include "multiplex.cuh" // the multiplex terms of optimize(): multiplex background keys / coverage, pool overlap
 #include "optimize_abi.cuh" // optimize() and its moves for a batch of trials
+#include "amplicon.cuh" // multiplex bookkeeping: unique amplicons of an assay, pool x amplicon coverage, accept (append / keys / splits)

@@ -75,6 +75,11 @@ struct AmpliconOut {
 	uint64_t cap;
 };
 
+// EXTRACT = false: find_amplicon_match's rules (pcr_assay.cpp:338-441); EXTRACT = true: extract_amplicon_seq's
+// (pcr_assay.cpp:443-542): no clipping to the sequence end, and the test for a split runs over the padded non-primer
+// region that becomes the amplicon sequence (amplicon.cuh)
+constexpr int MPX_PAD = 4; // MULTIPLEX_AMPLICON_PADDING (pcramp.h:57)
+template <bool EXTRACT>
 __device__ inline void amplicon_emit_pass(const SeqDev &sd, uint32_t seq, const ScoreEntry *s_ent, const uint4 *__restrict__ g_pl,
 	const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand, uint32_t e0, uint32_t Ep, uint32_t E, const OligoDev &P,
 	const OligoDev &M, int amp_min, int amp_max, uint32_t lane, uint32_t pair, uint32_t pass, const AmpliconOut &out)
@@ -100,7 +105,19 @@ __device__ inline void amplicon_emit_pass(const SeqDev &sd, uint32_t seq, const 
 				if (e2 < E) {
 					const ScoreEntry m2 = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e2);
 					mloc = m2.loc;
-					if (oligo_count(M, m2) >= m_thr && plus_loc3 < m2.loc - m_stop) { // pcr_assay.cpp:368-371
+					if (EXTRACT) {
+						if (oligo_count(M, m2) >= m_thr && plus_loc3 < m2.loc - m_stop) { // pcr_assay.cpp:474-477
+							const int amp_len = (m2.loc - m_start) - (ploc + p_start) + 1; // :479-490 (the `break` only prunes)
+							if (amp_len >= amp_min && amp_len <= amp_max) {
+								// :494-499: the region starts MPX_PAD bases inside the plus primer and its length adds 2 * MPX_PAD
+								// to (minus 5' end - region start), i.e. it ends MPX_PAD + 3 bases inside the minus primer
+								const int a0 = plus_loc3 + 1 - MPX_PAD, n = (m2.loc - m_stop) - a0 + 2 * MPX_PAD;
+								// :505-523 (an EOS also lies inside every longer region: `break` only prunes).  A region that
+								// leaves [0, L) is undefined in the reference (unchecked deque index); rejected here
+								ok = a0 >= 0 && a0 + n <= L && !has_split_dev(sd, seq, a0, n);
+							}
+						}
+					} else if (oligo_count(M, m2) >= m_thr && plus_loc3 < m2.loc - m_stop) { // pcr_assay.cpp:368-371
 						int amp_start = ploc + p_start;
 						const int amp_stop = min(m2.loc - m_start, L - 1);
 						int amp_len = amp_stop - amp_start + 1;
@@ -131,6 +148,7 @@ __device__ inline void amplicon_emit_pass(const SeqDev &sd, uint32_t seq, const 
 	}
 }
 
+template <bool EXTRACT>
 __global__ void __launch_bounds__(SCORE_THREADS)
 amplicon_list_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand,
 	const uint32_t *__restrict__ seq_off2, const OligoDev *__restrict__ oligos, uint32_t n_pairs, int amp_min, int amp_max, AmpliconOut out)
@@ -177,9 +195,9 @@ amplicon_list_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *_
 				const uint32_t q = chunk * 32u + src;
 				const OligoDev Fq = oligos[2 * q], Rq = oligos[2 * q + 1];
 				if ((todo1 >> src) & 1u)
-					amplicon_emit_pass(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Fq, Rq, amp_min, amp_max, lane, q, 0u, out);
+					amplicon_emit_pass<EXTRACT>(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Fq, Rq, amp_min, amp_max, lane, q, 0u, out);
 				if ((todo2 >> src) & 1u)
-					amplicon_emit_pass(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Rq, Fq, amp_min, amp_max, lane, q, 1u, out);
+					amplicon_emit_pass<EXTRACT>(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Rq, Fq, amp_min, amp_max, lane, q, 1u, out);
 			}
 		}
 	}
@@ -194,6 +212,69 @@ __global__ void gather64_kernel(const uint64_t *__restrict__ src, const uint32_t
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) dst[i] = src[perm[i]];
+}
+
+// Candidate amplicons of every pair in the reference's order -- pass {F+,R-} then {R+,F-}, each by (sequence, plus loc, minus loc):
+// the list kernel (re-run once if the first capacity guess was short; the list is deterministic) and two stable radix sorts
+// carrying a permutation.  After the call: k1[0] = sorted key1, perm[0][i] = record of sorted position i; k2[0], pid, mid are
+// indexed by record.
+struct AmpList {
+	DevBuf k1[2], k2[2], pid, mid, perm[2], tmp, cnt;
+	uint64_t n = 0;
+};
+
+template <bool EXTRACT>
+int build_amplicon_list(pcramp_gpu_ctx *ctx, SeqSet &s, const OligoDev *d_ol, uint32_t n_pairs, int amp_min, int amp_max, AmpList &L, const char *who)
+{
+	cudaStream_t st = ctx->stream;
+	CK(L.cnt.ensure(8));
+	uint64_t cap = std::max<uint64_t>(1u << 16, (uint64_t)n_pairs * 64), n = 0;
+	const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		CK(L.k1[0].ensure(cap * 8));
+		CK(L.k2[0].ensure(cap * 8));
+		CK(L.pid.ensure(cap * 4));
+		CK(L.mid.ensure(cap * 4));
+		CK(cudaMemsetAsync(L.cnt.p, 0, 8, st));
+		AmpliconOut out;
+		out.key1 = L.k1[0].as<uint64_t>();
+		out.key2 = L.k2[0].as<uint64_t>();
+		out.plus_id = L.pid.as<uint32_t>();
+		out.minus_id = L.mid.as<uint32_t>();
+		out.count = L.cnt.as<unsigned long long>();
+		out.cap = cap;
+		amplicon_list_kernel<EXTRACT><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+			s.seq_ent_off.as<uint32_t>(), d_ol, n_pairs, amp_min, amp_max, out);
+		CK(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+		unsigned long long h_n = 0;
+		CK(cudaMemcpyAsync(&h_n, L.cnt.p, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		n = h_n;
+		if (n <= cap) break;
+		if (attempt == 1) return fail(ctx, std::string(who) + ": candidate list kept growing");
+		cap = n; // the list is deterministic: the second run fits exactly
+	}
+	L.n = n;
+	if (n >= (1ull << 31)) return fail(ctx, std::string(who) + ": more than 2^31 candidate amplicons in one batch");
+	if (!n) return 0;
+	CK(L.k1[1].ensure(n * 8));
+	CK(L.k2[1].ensure(n * 8));
+	CK(L.perm[0].ensure(n * 4));
+	CK(L.perm[1].ensure(n * 4));
+	iota32_kernel<<<grid_for(n, 256), 256, 0, st>>>(L.perm[0].as<uint32_t>(), n);
+	size_t tmp_bytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, L.k2[0].as<uint64_t>(), L.k2[1].as<uint64_t>(), L.perm[0].as<uint32_t>(), L.perm[1].as<uint32_t>(),
+		(int)n, 0, 64, st);
+	CK(L.tmp.ensure(tmp_bytes));
+	CK(cub::DeviceRadixSort::SortPairs(L.tmp.p, tmp_bytes, L.k2[0].as<uint64_t>(), L.k2[1].as<uint64_t>(), L.perm[0].as<uint32_t>(),
+		L.perm[1].as<uint32_t>(), (int)n, 0, 64, st));
+	gather64_kernel<<<grid_for(n, 256), 256, 0, st>>>(L.k1[0].as<uint64_t>(), L.perm[1].as<uint32_t>(), L.k1[1].as<uint64_t>(), n);
+	CK(cub::DeviceRadixSort::SortPairs(L.tmp.p, tmp_bytes, L.k1[1].as<uint64_t>(), L.k1[0].as<uint64_t>(), L.perm[1].as<uint32_t>(),
+		L.perm[0].as<uint32_t>(), (int)n, 0, 64, st));
+	CK(cudaGetLastError());
+	ctx->stats.kernel_launches += 4;
+	return 0;
 }
 
 // find_background_match's scoring loop (background_match.cpp:66-165) for the amplicon at sorted position i.
@@ -347,12 +428,11 @@ int pcramp_gpu_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f
 	if (!n_pairs || !s.n) return 0;
 	memset(bitsets, 0, (size_t)n_pairs * n_words * 4);
 	if (!s.n_entries) return 0; // collect_background_candidates does nothing on an empty database (assay.h:411-421)
-	DevBuf d_f, d_r, d_ol, d_bits, d_cnt, k1[2], k2[2], pid, mid, perm[2], tmp;
+	DevBuf d_f, d_r, d_ol, d_bits;
 	CK(d_f.ensure((size_t)n_pairs * 16));
 	CK(d_r.ensure((size_t)n_pairs * 16));
 	CK(d_ol.ensure((size_t)n_pairs * 2 * sizeof(OligoDev)));
 	CK(d_bits.ensure(bits_bytes));
-	CK(d_cnt.ensure(8));
 	CK(cudaMemcpyAsync(d_f.p, f, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, st));
 	CK(cudaMemcpyAsync(d_r.p, r, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, st));
 	CK(cudaMemsetAsync(d_bits.p, 0, bits_bytes, st));
@@ -360,55 +440,15 @@ int pcramp_gpu_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f
 	prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(d_f.as<uint64_t>(), d_r.as<uint64_t>(), n_pairs, thr2, d_ol.as<OligoDev>());
 	CK(cudaGetLastError());
 	ctx->stats.kernel_launches++;
-	uint64_t cap = std::max<uint64_t>(1u << 16, (uint64_t)n_pairs * 64), n = 0;
-	const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
-	for (int attempt = 0; attempt < 2; ++attempt) {
-		CK(k1[0].ensure(cap * 8));
-		CK(k2[0].ensure(cap * 8));
-		CK(pid.ensure(cap * 4));
-		CK(mid.ensure(cap * 4));
-		CK(cudaMemsetAsync(d_cnt.p, 0, 8, st));
-		AmpliconOut out;
-		out.key1 = k1[0].as<uint64_t>();
-		out.key2 = k2[0].as<uint64_t>();
-		out.plus_id = pid.as<uint32_t>();
-		out.minus_id = mid.as<uint32_t>();
-		out.count = d_cnt.as<unsigned long long>();
-		out.cap = cap;
-		amplicon_list_kernel<<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
-			s.seq_ent_off.as<uint32_t>(), d_ol.as<OligoDev>(), n_pairs, amp_min, amp_max, out);
-		CK(cudaGetLastError());
-		ctx->stats.kernel_launches++;
-		unsigned long long h_n = 0;
-		CK(cudaMemcpyAsync(&h_n, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		n = h_n;
-		if (n <= cap) break;
-		if (attempt == 1) return fail(ctx, "pcramp_gpu_background_match: candidate list kept growing");
-		cap = n; // the list is deterministic: the second run fits exactly
-	}
+	AmpList L;
+	if (build_amplicon_list<false>(ctx, s, d_ol.as<OligoDev>(), n_pairs, amp_min, amp_max, L, "pcramp_gpu_background_match")) return 1;
+	const uint64_t n = L.n;
 	if (n_amplicons) *n_amplicons = n;
-	if (n >= (1ull << 32)) return fail(ctx, "pcramp_gpu_background_match: more than 2^32 candidate amplicons in one batch");
 	if (n) {
-		// order = (pair, pass, sequence, plus loc, minus loc): LSD, two stable radix sorts carrying a permutation
-		CK(k1[1].ensure(n * 8));
-		CK(k2[1].ensure(n * 8));
-		CK(perm[0].ensure(n * 4));
-		CK(perm[1].ensure(n * 4));
-		iota32_kernel<<<grid_for(n, 256), 256, 0, st>>>(perm[0].as<uint32_t>(), n);
-		size_t tmp_bytes = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k2[0].as<uint64_t>(), k2[1].as<uint64_t>(), perm[0].as<uint32_t>(), perm[1].as<uint32_t>(),
-			(int)n, 0, 64, st);
-		CK(tmp.ensure(tmp_bytes));
-		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k2[0].as<uint64_t>(), k2[1].as<uint64_t>(), perm[0].as<uint32_t>(), perm[1].as<uint32_t>(),
-			(int)n, 0, 64, st));
-		gather64_kernel<<<grid_for(n, 256), 256, 0, st>>>(k1[0].as<uint64_t>(), perm[1].as<uint32_t>(), k1[1].as<uint64_t>(), n);
-		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k1[1].as<uint64_t>(), k1[0].as<uint64_t>(), perm[1].as<uint32_t>(), perm[0].as<uint32_t>(),
-			(int)n, 0, 64, st));
-		background_sw_kernel<<<grid_for(n, 128), 128, 0, st>>>(n, k1[0].as<uint64_t>(), perm[0].as<uint32_t>(), pid.as<uint32_t>(), mid.as<uint32_t>(),
+		background_sw_kernel<<<grid_for(n, 128), 128, 0, st>>>(n, L.k1[0].as<uint64_t>(), L.perm[0].as<uint32_t>(), L.pid.as<uint32_t>(), L.mid.as<uint32_t>(),
 			s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), d_f.as<uint64_t>(), d_r.as<uint64_t>(), s.n, detect_threshold, taq, d_bits.as<uint32_t>(), n_words);
 		CK(cudaGetLastError());
-		ctx->stats.kernel_launches += 5;
+		ctx->stats.kernel_launches += 1;
 	}
 	CK(cudaMemcpyAsync(bitsets, d_bits.p, (size_t)n_pairs * n_words * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));

@@ -18,6 +18,7 @@ from tests import scenarios  # noqa: E402
 from tests import thermo_cases  # noqa: E402
 from tests import background_cases  # noqa: E402
 from tests import optimize_cases  # noqa: E402
+from tests import amplicon_cases  # noqa: E402
 from tests.harness import RefLib  # noqa: E402
 
 
@@ -220,7 +221,44 @@ def fasta_kats(ref):
     return rec
 
 
+def amplicon_kats(ref_factory):
+    """multiplex bookkeeping: collect_unique_amplicons per pair, pool x amplicon coverage, two accept steps"""
+    rec = {}
+    for case in amplicon_cases.amp_cases():
+        ref, mref = ref_factory(), ref_factory()
+        ref.set_sequences(case.coll, case.active)
+        for seq, pos in case.splits:
+            ref.split_sequence(seq, pos)
+        ref.select_words(case.f, case.r, case.search_threshold)
+        thr = float(case.threshold)
+        rec.update(amplicon_cases.flatten(case.name, [ref.unique_amplicons(case.f[p], case.r[p], thr, *case.amp) for p in range(len(case.f))]))
+        counts = rec["%s_n_amp" % case.name]
+        order = np.argsort(-counts, kind="stable")
+        pool = order[:case.pool]
+        rec["%s_pool" % case.name] = pool.astype(np.uint32)
+        rec["%s_pool_cov" % case.name] = ref.pool_amplicon_coverage(case.f, case.r, case.f[pool], case.r[pool], thr, case.amp[0], case.amp[1],
+                                                                    float(amplicon_cases.BG_THRESHOLD), case.taq)
+        # two accept steps (main.cpp:989-1017): the second one sees the split targets and appends to a non-empty multiplex background
+        for step, p in enumerate(order[:2]):
+            if step:
+                ref.select_words(case.f, case.r, case.search_threshold)
+            n = ref.accept_assay(mref, case.f[p], case.r[p], thr, *case.amp)
+            rec["%s_accept%d_n" % (case.name, step)] = np.array([n, len(mref.keys())], np.uint64)
+            rec["%s_accept%d_keys" % (case.name, step)] = mref.keys()
+            for tag, ctx in (("mpx", mref), ("tgt", ref)):
+                seqs = ctx.sequences()
+                rec["%s_accept%d_%s_len" % (case.name, step, tag)] = np.array([q[0] for q in seqs], np.uint32)
+                rec["%s_accept%d_%s_nib" % (case.name, step, tag)] = np.concatenate([q[2] for q in seqs] + [np.zeros(0, np.uint8)])
+        print("amplicons %-16s pairs %3d unique amplicons %4d bounds %5d pool coverage sum %4d accepted %s" % (
+            case.name, len(case.f), int(counts.sum()), int(rec["%s_n_bounds" % case.name].sum()), int(rec["%s_pool_cov" % case.name].sum()),
+            [int(rec["%s_accept%d_n" % (case.name, k)][0]) for k in (0, 1)]))
+    return rec
+
+
 def main():
+    if "--amplicons-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "kat_amplicons.npz"), **amplicon_kats(RefLib))
+        return
     if "--fasta-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "kat_fasta.npz"), **fasta_kats(RefLib()))
         return
@@ -240,6 +278,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_optimize.npz"), **optimize_kats(RefLib))
     np.savez_compressed(os.path.join(HERE, "kat_optimize_multiplex.npz"), **multiplex_optimize_kats(RefLib))
     np.savez_compressed(os.path.join(HERE, "kat_fasta.npz"), **fasta_kats(RefLib()))
+    np.savez_compressed(os.path.join(HERE, "kat_amplicons.npz"), **amplicon_kats(RefLib))
     print("wrote fixtures to", HERE)
 
 

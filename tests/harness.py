@@ -263,6 +263,13 @@ class RefLib(_Base):
         self.f_mpx_cov = self._fn("multiplex_coverage", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, _u64p, _u64p, ctypes.c_float, ctypes.c_int,
                                                                        _f32p])
         self.f_overlap = self._fn("oligo_overlap", ctypes.c_int, [ctypes.c_uint32, _u64p, _u64p, ctypes.c_uint32, _u64p, _u64p, _f32p])
+        self.f_uamp = self._fn("unique_amplicons", ctypes.c_int, [vp, _u64p, _u64p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64p,
+                                                                  _u64p, ctypes.c_char_p, _u32p])
+        self.f_pool_amp = self._fn("pool_amplicon_coverage", ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_uint32, _u64p, _u64p,
+                                                                            ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                                                            _f32p])
+        self.f_accept = self._fn("accept_assay", ctypes.c_long, [vp, vp, _u64p, _u64p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                                                 ctypes.c_uint32])
         self.n_seq = 0
 
     def set_threads(self, n):
@@ -495,6 +502,56 @@ class RefLib(_Base):
         rc = self.f_mbg(self.h, len(f), _p(f, _u64p), _p(r, _u64p), background_threshold, int(taq), _p(bits, _u8p))
         assert rc == 0, self.f_err(self.h)
         return bits
+
+
+    def unique_amplicons(self, f, r, threshold, amp_min=80, amp_max=200, want_bounds=True):
+        """PCR::collect_unique_amplicons of ONE assay -> (amplicon strings in the returned order, bounds (n, 3) uint32), or None when the
+        reference threw (last_error() tells what)"""
+        f, r = _w(np.asarray(f).reshape(1, 2)).reshape(-1), _w(np.asarray(r).reshape(1, 2)).reshape(-1)
+        cnt = np.zeros(3, np.uint64)
+        if self.f_uamp(self.h, _p(f, _u64p), _p(r, _u64p), threshold, amp_min, amp_max, int(want_bounds), _p(cnt, _u64p), None, None, None):
+            return None
+        off = np.zeros(int(cnt[0]) + 1, np.uint64)
+        text = ctypes.create_string_buffer(max(1, int(cnt[1])))
+        bounds = np.zeros((max(1, int(cnt[2])), 3), np.uint32)
+        assert self.f_uamp(self.h, _p(f, _u64p), _p(r, _u64p), threshold, amp_min, amp_max, int(want_bounds), _p(cnt, _u64p), _p(off, _u64p), text,
+                           _p(bounds, _u32p)) == 0
+        raw = text.raw[:int(cnt[1])]
+        return [raw[int(off[i]):int(off[i + 1])].decode("ascii") for i in range(int(cnt[0]))], bounds[:int(cnt[2])]
+
+    def last_error(self):
+        return self.f_err(self.h).decode()
+
+    def pool_amplicon_coverage(self, f, r, pool_f, pool_r, target_threshold, amp_min, amp_max, background_threshold, taq=False):
+        f, r, pf, pr = _w(f), _w(r), _w(pool_f), _w(pool_r)
+        cov = np.zeros(len(f), np.float32)
+        rc = self.f_pool_amp(self.h, len(f), _p(f, _u64p), _p(r, _u64p), len(pf), _p(pf, _u64p), _p(pr, _u64p), target_threshold, amp_min, amp_max,
+                             background_threshold, int(taq), _p(cov, _f32p))
+        assert rc == 0, self.f_err(self.h)
+        return cov
+
+    def accept_assay(self, multiplex, f, r, threshold, amp_min=80, amp_max=200, pack_max_degen=256, min_oligo_length=18):
+        """main.cpp:989-1017: amplicons appended to the RefLib `multiplex` (database + keys rebuilt), this context's sequences split"""
+        f, r = _w(np.asarray(f).reshape(1, 2)).reshape(-1), _w(np.asarray(r).reshape(1, 2)).reshape(-1)
+        n = self.f_accept(self.h, multiplex.h, _p(f, _u64p), _p(r, _u64p), threshold, amp_min, amp_max, pack_max_degen, min_oligo_length)
+        assert n >= 0, self.f_err(self.h)
+        multiplex.n_seq += n
+        return n
+
+    def sequences(self):
+        """[(length, weight, nibbles uint8[length])] of the context's sequences"""
+        get = self._fn("sequence_get", ctypes.c_long, [ctypes.c_void_p, ctypes.c_uint32, _f32p, _u8p])
+        out = []
+        i = 0
+        while True:
+            w = np.zeros(1, np.float32)
+            ln = get(self.h, i, _p(w, _f32p), None)
+            if ln < 0:
+                return out
+            nib = np.zeros(max(ln, 1), np.uint8)
+            get(self.h, i, _p(w, _f32p), _p(nib, _u8p))
+            out.append((int(ln), float(w[0]), nib[:ln].copy()))
+            i += 1
 
 
 def pack_strings(strs, stride=33):
