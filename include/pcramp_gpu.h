@@ -341,6 +341,25 @@ int pcramp_gpu_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f
 int pcramp_gpu_multiplex_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r,
 	uint32_t n_pairs, float threshold, int use_taq_mama, uint32_t *bitsets);
 
+/* ---- candidate generation ----------------------------------------------------------------------
+ * PCR::random_assay (pcr_assay.cpp:580-734) under the seeding protocol of main.cpp:527-548.  A "stream" is what one
+ * OpenMP thread of the reference runs: its own NucCruc object, its own seed (seeds[i] = the thread's
+ * `local_seed = rand_r(&global_seed)`; advanced in place, glibc rand_r), and trials_per_stream[i] consecutive trials of
+ * the static schedule.  Stream i's assays follow stream i-1's in f / r (2 uint64 per oligo, centred like
+ * PCR::center()).  One GPU thread per stream: n_streams = number of trials gives the reference's result for
+ * `--thread <num_trial>`, n_streams = 1 for `--thread 1`.  attempts (may be NULL) = candidates tried per trial.
+ * Errors carry the reference's messages (":PCR::random_assay: No active sequences found", "... Unable to generate a
+ * valid initial assay to test!", "... sequence length is too small!"). */
+typedef struct pcramp_gpu_random_assay_options {
+	int primer_min, primer_max;       /* opt.primer_range */
+	int amplicon_min, amplicon_max;   /* opt.target_amplicon_range */
+	uint32_t degen;                   /* opt.degen */
+	float salt, primer_strand;        /* opt.salt, opt.primer_strand */
+	float primer_tm_min, primer_tm_max, max_hairpin, max_dimer;
+} pcramp_gpu_random_assay_options;
+int pcramp_gpu_random_assays(pcramp_gpu_ctx *ctx, int kind, uint32_t n_streams, uint32_t *seeds, const uint32_t *trials_per_stream,
+	const pcramp_gpu_random_assay_options *options, uint64_t *f, uint64_t *r, uint32_t *attempts);
+
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* Counters of the last select_words / score_pairs call on this ctx. */
 typedef struct pcramp_gpu_stats {

@@ -883,4 +883,35 @@ long ref_accept_assay(void *h, void *h_m, const uint64_t *f, const uint64_t *r, 
 	return n;
 }
 
+// PCR::random_assay (pcr_assay.cpp:580-734) as ONE OpenMP thread of main.cpp:527-548 runs it: a fresh NucCruc object, the
+// thread's local seed (advanced in place), n_trials consecutive trials.  attempts is not available from the reference.
+int ref_random_assay_stream(void *h, uint32_t n_trials, uint32_t *seed, int primer_min, int primer_max, int amp_min, int amp_max, uint32_t degen,
+	float salt, float primer_strand, float tm_min, float tm_max, float max_hairpin, float max_dimer, uint64_t *f, uint64_t *r)
+{
+	RefCtx *c = (RefCtx *)h;
+	return guarded(c, [&]() {
+		Options opt;
+		opt.primer_range = make_pair(primer_min, primer_max);
+		opt.target_amplicon_range = make_pair(amp_min, amp_max);
+		opt.degen = degen;
+		opt.salt = salt;
+		opt.primer_strand = primer_strand;
+		opt.primer_tm_range = make_pair(tm_min, tm_max);
+		opt.max_hairpin = max_hairpin;
+		opt.max_dimer = max_dimer;
+		opt.output_filter = Options::SILENT;
+		NucCruc melt;
+		melt.salt(opt.salt);
+		unsigned int local_seed = *seed;
+		ostringstream sink;
+		for (uint32_t t = 0; t < n_trials; ++t) {
+			PCR p;
+			p.random_assay(c->seq, melt, opt, local_seed, sink);
+			put_word(f + 2 * t, p.oligo(FORWARD));
+			put_word(r + 2 * t, p.oligo(REVERSE));
+		}
+		*seed = local_seed;
+	});
+}
+
 } // extern "C"

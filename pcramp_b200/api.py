@@ -84,6 +84,18 @@ class OptimizeOptions(ctypes.Structure):
         super().__init__(**d)
 
 
+class RandomAssayOptions(ctypes.Structure):
+    """pcramp_gpu_random_assay_options (include/pcramp_gpu.h); defaults = the reference's (pcramp.h:14-31)"""
+    _fields_ = [("primer_min", ctypes.c_int), ("primer_max", ctypes.c_int), ("amplicon_min", ctypes.c_int), ("amplicon_max", ctypes.c_int),
+                ("degen", ctypes.c_uint32), ("salt", ctypes.c_float), ("primer_strand", ctypes.c_float), ("primer_tm_min", ctypes.c_float),
+                ("primer_tm_max", ctypes.c_float), ("max_hairpin", ctypes.c_float), ("max_dimer", ctypes.c_float)]
+
+    def __init__(self, primer_range=(18, 25), amplicon_range=(80, 200), degen=1, salt=0.05, primer_strand=900.0e-9, primer_tm_range=(50.0, 75.0),
+                 max_hairpin=40.0, max_dimer=40.0):
+        super().__init__(primer_range[0], primer_range[1], amplicon_range[0], amplicon_range[1], degen, salt, primer_strand, primer_tm_range[0],
+                         primer_tm_range[1], max_hairpin, max_dimer)
+
+
 MOVES = {"IncreaseDegeneracy": 0, "DecreaseDegeneracy": 1, "Trim5": 2, "Trim3": 3, "Grow5": 4, "Grow3": 5}
 
 # op codes of pcramp_gpu_thermo_batch (include/pcramp_gpu.h)
@@ -110,6 +122,8 @@ SIGNATURES = {
     "pcramp_gpu_pool_amplicon_coverage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int,
                                                          ctypes.c_int, ctypes.c_float, ctypes.c_int, _f32p]),
     "pcramp_gpu_accept_assay": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u64p, _u64p]),
+    "pcramp_gpu_random_assays": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, _u32p, _u32p, ctypes.POINTER(RandomAssayOptions),
+                                                _u64p, _u64p, _u32p]),
     "pcramp_gpu_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_uint32, ctypes.c_uint64, _u64p, _i32p, _u32p, _u64p]),
     "pcramp_gpu_select_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
@@ -630,6 +644,19 @@ class PcrampGpu:
         self._ck(self.lib.pcramp_gpu_multiplex_background_match(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), len(f), float(threshold),
                                                                 int(use_taq_mama), _ptr(bits, _u32p)))
         return bits
+
+    def random_assays(self, kind, seeds, trials_per_stream, options=None):
+        """PCR::random_assay, one GPU thread per seed stream -> (f, r (n_trials, 2) uint64, seeds after the run, attempts per trial)"""
+        seeds = np.array(seeds, dtype=np.uint32).reshape(-1)
+        per = np.ascontiguousarray(trials_per_stream, dtype=np.uint32).reshape(-1)
+        assert len(seeds) == len(per)
+        n = int(per.sum())
+        f, r = np.zeros((n, 2), np.uint64), np.zeros((n, 2), np.uint64)
+        att = np.zeros(max(1, n), np.uint32)
+        opt = options if options is not None else RandomAssayOptions()
+        self._ck(self.lib.pcramp_gpu_random_assays(self.h, kind, len(seeds), _ptr(seeds, _u32p), _ptr(per, _u32p), ctypes.byref(opt),
+                                                   _ptr(f, _u64p), _ptr(r, _u64p), _ptr(att, _u32p)))
+        return f, r, seeds, att[:n]
 
     def thermo_stats(self):
         s = ThermoStats()

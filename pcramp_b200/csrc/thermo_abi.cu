@@ -597,3 +597,5 @@ int pcramp_gpu_multiplex_compatible(pcramp_gpu_ctx *ctx, const uint64_t *f, cons
 }
 
 } // extern "C"
+
+#include "random_assay.cuh" // candidate generation: PCR::random_assay, one GPU thread per seed stream

@@ -19,6 +19,7 @@ from tests import thermo_cases  # noqa: E402
 from tests import background_cases  # noqa: E402
 from tests import optimize_cases  # noqa: E402
 from tests import amplicon_cases  # noqa: E402
+from tests import random_assay_cases  # noqa: E402
 from tests.harness import RefLib  # noqa: E402
 
 
@@ -255,7 +256,28 @@ def amplicon_kats(ref_factory):
     return rec
 
 
+def random_assay_kats(ref_factory):
+    """candidate generation (SURVEY 8f-1): PCR::random_assay per seed stream (one OpenMP thread of main.cpp:527-548 each)"""
+    rec = {}
+    for case in random_assay_cases.ra_cases():
+        ref = ref_factory()
+        ref.set_sequences(case.coll, case.active)
+        for seq, pos in case.splits:
+            ref.split_sequence(seq, pos)
+        F, R, S = [], [], []
+        for seed, n in zip(case.seeds, case.per):
+            f, r, after = ref.random_assay_stream(int(n), int(seed), case.opt)
+            F.append(f); R.append(r); S.append(after)
+        rec["%s_f" % case.name], rec["%s_r" % case.name] = np.concatenate(F), np.concatenate(R)
+        rec["%s_seed_after" % case.name] = np.array(S, np.uint32)
+        print("random_assay %-14s streams %3d trials %4d" % (case.name, len(case.seeds), int(case.per.sum())))
+    return rec
+
+
 def main():
+    if "--random-assay-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "kat_random_assay.npz"), **random_assay_kats(RefLib))
+        return
     if "--amplicons-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "kat_amplicons.npz"), **amplicon_kats(RefLib))
         return
@@ -279,6 +301,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_optimize_multiplex.npz"), **multiplex_optimize_kats(RefLib))
     np.savez_compressed(os.path.join(HERE, "kat_fasta.npz"), **fasta_kats(RefLib()))
     np.savez_compressed(os.path.join(HERE, "kat_amplicons.npz"), **amplicon_kats(RefLib))
+    np.savez_compressed(os.path.join(HERE, "kat_random_assay.npz"), **random_assay_kats(RefLib))
     print("wrote fixtures to", HERE)
 
 

@@ -357,6 +357,18 @@ class RefLib(_Base):
         assert rc == 0, self.f_err(self.h)
         return f, r
 
+    def random_assay_stream(self, n_trials, seed, opt):
+        """one OpenMP thread of main.cpp:527-548: fresh NucCruc object, local seed -> (f, r, seed after); opt = RandomAssayOptions"""
+        fn = self._fn("random_assay_stream", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, _u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                            ctypes.c_int, ctypes.c_uint32] + [ctypes.c_float] * 6 + [_u64p, _u64p])
+        f, r = np.zeros((n_trials, 2), np.uint64), np.zeros((n_trials, 2), np.uint64)
+        sd = np.array([seed], np.uint32)
+        rc = fn(self.h, n_trials, _p(sd, _u32p), opt.primer_min, opt.primer_max, opt.amplicon_min, opt.amplicon_max, opt.degen, opt.salt,
+                opt.primer_strand, opt.primer_tm_min, opt.primer_tm_max, opt.max_hairpin, opt.max_dimer, _p(f, _u64p), _p(r, _u64p))
+        if rc:
+            return None
+        return f, r, int(sd[0])
+
     def has_split(self, seq, loc, length):
         return self.f_has_split(self.h, seq, loc, length)
 
