@@ -145,10 +145,11 @@ __device__ inline bool cut_oligo(const SeqDev &sd, uint32_t seq, int start, int 
 }
 
 __device__ inline W128 oligo_word_centred(const Oligo5 &o)
-{ // Word built by push_back, then center() (pcr_assay.cpp:720, assay.h)
+{ // subword() fills an empty Word from position 0 (Word::push_back, word.cpp:31-48) and complement() writes left-justified
+	// (word.h:140-183); then PCR::center() (pcr_assay.cpp:720, assay.h:395-399)
 	W128 w;
 	w.hi = w.lo = 0;
-	for (int k = 0; k < o.len; ++k) w_set(w, WORD_LEN - o.len + k, o.nib[k]);
+	for (int k = 0; k < o.len; ++k) w_set(w, k, o.nib[k]);
 	return w_center(w);
 }
 

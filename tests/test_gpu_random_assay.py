@@ -35,7 +35,7 @@ def test_random_assays_match_reference_golden(gpu, case):
     assert gpu.thermo_stats()["kernel_launches"] == 1
     # a stream is self-contained: any subset of the streams gives the same assays
     pick = np.arange(len(case.seeds))[::3]
-    off = np.concatenate([[0], np.cumsum(case.per)])
+    off = np.concatenate([[0], np.cumsum(case.per.astype(np.int64))]).astype(np.int64)
     f2, r2, after2, _ = gpu.random_assays(TARGET, case.seeds[pick], case.per[pick], case.opt)
     want = np.concatenate([np.arange(off[i], off[i + 1]) for i in pick])
     assert np.array_equal(f2, f[want]) and np.array_equal(r2, r[want]) and np.array_equal(after2, after[pick])
@@ -83,7 +83,7 @@ def test_against_live_reference(gpu):
         seeds = rng.integers(0, 2**32, size=64, dtype=np.uint64).astype(np.uint32)
         per = rng.integers(1, 10, size=64).astype(np.uint32)
         f, r, after, _ = gpu.random_assays(TARGET, seeds, per, case.opt)
-        off = np.concatenate([[0], np.cumsum(per)])
+        off = np.concatenate([[0], np.cumsum(per.astype(np.int64))]).astype(np.int64)
         for i, (seed, n) in enumerate(zip(seeds, per)):
             wf, wr, wa = ref.random_assay_stream(int(n), int(seed), case.opt)
             assert wa == int(after[i]), (case.name, i)
