@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the shards' bitsets are merged -- p2p = peer stores over NVLink fused into the tail of pair scoring "
                          "(xchg.cuh, the product path); nccl = all-gather + pcramp_gpu_merge_shards (the baseline it replaces)")
+    ap.add_argument("--workers", type=int, default=2,
+                    help="batches in flight per GPU (pairs sharding / one GPU): worker contexts (pcramp_gpu_create_worker) that share the resident "
+                         "targets + text index, one host thread each; 1 = one batch at a time")
     ap.add_argument("--fasta-targets", type=int, default=8000, help="sequences in the FASTA-ingest leg (0 = skip; rank 0 only)")
     ap.add_argument("--dp-problems", type=int, default=262144, help="NucCruc problems per step of the DP GCUPS leg (0 = skip the leg)")
     ap.add_argument("--dp-cpu-problems", type=int, default=60000, help="problems in the bounded CPU sample of the DP leg")
@@ -545,6 +548,12 @@ def run_b200(a):
     g.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
     ext = torch.cuda.ExternalStream(g.stream, device=local)
     thr = float(TARGET_THR * SEARCH_MULT)
+    W = 1 if by_targets else max(1, a.workers)
+    g.stage_pairs(f_all[:a.pairs], r_all[:a.pairs])
+    g.select_words_staged(TARGET, thr, want_keys=False)   # builds the text index the workers share
+    ctxs = [g] + [g.worker() for _ in range(W - 1)]
+    import threading
+    lock = threading.Lock()
     n_words_local = (int(shard_nseq[rank]) + 31) // 32
     n_words_global = (a.targets + 31) // 32
     P = a.pairs
@@ -562,8 +571,8 @@ def run_b200(a):
         packed_p1 = torch.zeros_like(packed_any)
         out_bits = torch.zeros((P, n_words_global), dtype=torch.int32, device="cuda")
         out_cov = torch.zeros(P, dtype=torch.float32, device="cuda")
-    host_cov = torch.zeros(P, dtype=torch.float32).pin_memory()
-    host_bits = torch.zeros((P, n_words_global), dtype=torch.int32).pin_memory()
+    host_cov = [torch.zeros(P, dtype=torch.float32).pin_memory() for _ in ctxs]
+    host_bits = [torch.zeros((P, n_words_global), dtype=torch.int32).pin_memory() for _ in ctxs]
     launches = [0]
     stats_acc = {"ms_seed": 0.0, "ms_scan": 0.0, "ms_edge": 0.0, "ms_db": 0.0, "ms_score": 0.0, "ms_index_kernel": 0.0, "n_entries": 0, "n_hits": 0,
                  "scan_launches": 0,
@@ -589,50 +598,60 @@ def run_b200(a):
         g.merge_shards(packed_any.data_ptr(), packed_p1.data_ptr(), shard_nseq, P, out_bits.data_ptr(), out_cov.data_ptr())
         launches[0] += 1
 
-    def account(timed):
-        st = g.stats()
-        last.update(st)
-        if timed:
-            launches[0] += st["kernel_launches"]
-            for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score", "ms_index_kernel"):
-                stats_acc[k] += st[k]
-            for k in ("n_entries", "n_hits", "n_index_entries", "n_index_queries", "n_indexed", "n_seeded"):
-                stats_acc[k] += st[k]
-            stats_acc["scan_launches"] += 1
+    def account(c, timed):
+        """timed: True = count launches; "stats" = also accumulate the library's stage / kernel event times (sequential pass only:
+        under several batches in flight a kernel's own time is not its time alone)"""
+        st = c.stats()
+        with lock:
+            last.update(st)
+            if timed:
+                launches[0] += st["kernel_launches"]
+            if timed == "stats":
+                for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score", "ms_index_kernel"):
+                    stats_acc[k] += st[k]
+                for k in ("n_entries", "n_hits", "n_index_entries", "n_index_queries", "n_indexed", "n_seeded"):
+                    stats_acc[k] += st[k]
+                stats_acc["scan_launches"] += 1
 
-    def step_resident(b, timed):
-        g.set_batch(b * P, P)
-        g.select_words_staged(TARGET, thr, want_keys=False)   # keys() is only for hosts that walk the database themselves
-        g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
-        account(timed)
+    def step_resident(b, timed, k=0):
+        c = ctxs[k]
+        c.set_batch(b * P, P)
+        c.select_words_staged(TARGET, thr, want_keys=False)   # keys() is only for hosts that walk the database themselves
+        c.score_pairs_staged(TARGET, thr, float(TARGET_THR))
+        account(c, timed)
         if p2p:
             g.exchange_step(TARGET)
             launches[0] += 3 if timed else 0
         elif by_targets:
             exchange()
 
-    def step_e2e(b, timed):
+    def step_e2e(b, timed, k=0):
         fb, rb = f_host[b * P:(b + 1) * P], r_host[b * P:(b + 1) * P]
+        host_cov_k, host_bits_k = host_cov[k], host_bits[k]
         if not by_targets:
-            g.select_words(TARGET, fb, rb, thr, want_keys=False)
-            cov, bits = g.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR))
-            host_cov.numpy()[:] = cov
-            host_bits.numpy().view(np.uint32)[:] = bits
+            c = ctxs[k]
+            c.select_words(TARGET, fb, rb, thr, want_keys=False)
+            cov, bits = c.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR))
+            host_cov_k.numpy()[:] = cov
+            host_bits_k.numpy().view(np.uint32)[:] = bits
+            if timed:
+                with lock:
+                    launches[0] += c.stats()["kernel_launches"]
         elif p2p:
             g.stage_pairs(fb, rb)
             g.select_words_staged(TARGET, thr, want_keys=False)
             g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
             g.exchange_step(TARGET)
             cov, bits = g.exchange_fetch(P)
-            host_cov.numpy()[:] = cov
-            host_bits.numpy().view(np.uint32)[:] = bits
+            host_cov_k.numpy()[:] = cov
+            host_bits_k.numpy().view(np.uint32)[:] = bits
         else:
             g.stage_pairs(fb, rb)
             g.select_words_staged(TARGET, thr, want_keys=False)
             g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
             exchange()
-            host_cov.copy_(out_cov, non_blocking=True)
-            host_bits.copy_(out_bits, non_blocking=True)
+            host_cov_k.copy_(out_cov, non_blocking=True)
+            host_bits_k.copy_(out_bits, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -640,12 +659,35 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(fn, first_batch, n_steps):
+    def run_steps(fn, first_batch, n_steps, timed, workers):
+        """steps first_batch .. first_batch + n_steps - 1; with several workers step s runs on context s % workers, one host thread each"""
+        if workers == 1:
+            for s in range(n_steps):
+                fn(first_batch + s, timed)
+            return
+        errors = []
+
+        def work(k):
+            try:
+                for s in range(k, n_steps, workers):
+                    fn(first_batch + s, timed, k)
+            except Exception as e:                                 # noqa: BLE001
+                errors.append(e)
+        th = [threading.Thread(target=work, args=(k,)) for k in range(workers)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errors:
+            raise errors[0]
+
+    def timed_region(fn, first_batch, n_steps, timed=True, workers=1):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ext)
-        for s in range(n_steps):
-            fn(first_batch + s, True)
+        e0.record(ext)                      # the device is idle here (barrier): the event marks the start for every stream
+        run_steps(fn, first_batch, n_steps, timed, workers)
+        if workers > 1:
+            torch.cuda.synchronize()        # every context's stream has drained before the closing event
         e1.record(ext)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -656,18 +698,24 @@ def run_b200(a):
         return ms
 
     with torch.cuda.stream(ext):
-        g.stage_pairs(f_all, r_all)                      # every batch resident in HBM before the timed region
-        for s in range(a.warmup):
-            step_resident(s, False)
+        for k, c in enumerate(ctxs):
+            c.stage_pairs(f_all, r_all)                  # every batch resident in HBM before the timed region
+            for s in range(a.warmup):                    # every context warms up (its scratch buffers grow to their working size)
+                step_resident(s, False, k)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        ms_resident = timed_region(step_resident, a.warmup, a.steps)
+        ms_resident = timed_region(step_resident, a.warmup, a.steps, True, W)
         launches_resident = launches[0]
-        step_e2e(total, False)
+        for k in range(W):
+            step_e2e(total, False, k)
         launches[0] = 0
-        ms_e2e = timed_region(step_e2e, total + 1, a.steps)
+        ms_e2e = timed_region(step_e2e, total + 1, a.steps, True, W)
         clocks = sampler.stop() if rank == 0 else None
+        # one batch at a time on one context: the library's per-kernel event times (roofline, stage breakdown) are taken here,
+        # where a kernel's duration is its own
+        g.stage_pairs(f_all, r_all)                      # (the e2e steps staged their own batches)
+        ms_sequential = timed_region(step_resident, a.warmup, a.steps, "stats", 1)
         int_peak = g.measure_int_peak() if rank == 0 else 0.0
         dp = dp_leg(a, g, torch, ext, rank, world, dist if world > 1 else None) if a.dp_problems > 0 else None
 
@@ -711,7 +759,7 @@ def run_b200(a):
             "kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": traffic,
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms, "share_of_step": kernel_ms * n_scan / ms_resident,
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms, "share_of_step": kernel_ms * n_scan / ms_sequential,
             "note": "algorithmic bytes = SURVEY.md 8d (nibbles of the active targets + 16 B/candidate + 28 B/entry): what ONE pass over the text "
                     "would move.  The seeded scan does not stream the text: %d patterns are resolved through a text index (index.cuh) whose "
                     "16-byte entries are the kernel's real HBM stream -- `traffic` (ncu dram bytes, profiles/) is ~6.5x the algorithmic bytes "
@@ -761,6 +809,9 @@ def run_b200(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_resident,
             "breakdown_ms_per_step": {k: stats_acc[k] / n_scan for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score")},
+            "pipeline": {"workers": W, "ms_per_step_one_batch_at_a_time": ms_sequential / a.steps,
+                         "note": "value / e2e: %d batch(es) in flight per GPU (worker contexts sharing the resident targets and text index, one "
+                                 "host thread each); roofline / breakdown: from a pass with one batch at a time" % W},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp, "target_sharded": tsh,
             "fasta_ingest": fasta_leg(a, g, coll, hbm_peak) if a.fasta_targets > 0 else None}))
     # teardown order matters: torch tensors that were used on the library's stream must die before the stream does

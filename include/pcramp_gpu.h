@@ -38,6 +38,13 @@ enum { PCRAMP_TARGET = 0, PCRAMP_BACKGROUND = 1, PCRAMP_MULTIPLEX = 2, PCRAMP_NU
 /* ---- lifetime ------------------------------------------------------------------------------ */
 int pcramp_gpu_create(pcramp_gpu_ctx **ctx, int device);
 void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx);
+/* A worker: a second context on the parent's device that reads the parent's collections and text index in place (no copy:
+ * 300 MB of planes + 9.6 GB of index for 20 000 x 30 kb stay single) and owns its stream, scratch, word database and results.
+ * Independent batches -- the trial batches of a sweep, main.cpp:697-887 run for several batches at once -- are then driven from
+ * one host thread per context and overlap on the GPU.  Calls that change a collection (upload, split, set_active, set_weights,
+ * accept_assay) are refused on a worker; after such a call on the parent its workers fail every call ("sequences changed")
+ * and must be re-created.  Destroy the workers before the parent. */
+int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **worker);
 const char *pcramp_gpu_last_error(const pcramp_gpu_ctx *ctx);
 /* cudaStream_t every kernel of this ctx is launched on (for CUDA-event timing by the caller). */
 void *pcramp_gpu_stream(pcramp_gpu_ctx *ctx);

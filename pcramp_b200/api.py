@@ -108,6 +108,7 @@ _lib = None
 SIGNATURES = {
     "pcramp_gpu_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     "pcramp_gpu_destroy": (None, [ctypes.c_void_p]),
+    "pcramp_gpu_create_worker": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "pcramp_gpu_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "pcramp_gpu_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "pcramp_gpu_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
@@ -247,7 +248,21 @@ class PcrampGpu:
         self.n_pairs = 0
         self._db = {}
 
+    def worker(self):
+        """pcramp_gpu_create_worker: a context with its own stream / scratch / database that reads this context's collections and text
+        index in place.  Drive it from its own host thread (ctypes releases the GIL during a call); close it before this context."""
+        h = ctypes.c_void_p()
+        self._ck(self.lib.pcramp_gpu_create_worker(self.h, ctypes.byref(h)))
+        w = PcrampGpu.__new__(PcrampGpu)
+        w.lib, w.h, w.n_seq, w.n_pairs, w._db = self.lib, h, dict(self.n_seq), 0, {}
+        self._workers = getattr(self, "_workers", [])
+        self._workers.append(w)
+        return w
+
     def close(self):
+        for w in getattr(self, "_workers", []):
+            w.close()
+        self._workers = []
         if getattr(self, "h", None):
             self.lib.pcramp_gpu_destroy(self.h)
             self.h = None

@@ -384,6 +384,8 @@ int pcramp_gpu_accept_assay(pcramp_gpu_ctx *ctx, uint32_t pair, uint32_t pack_ma
 		return fail(ctx, "pcramp_gpu_accept_assay: no amplicon list with bounds (call pcramp_gpu_unique_amplicons with want_bounds first)");
 	if (ctx->amp_kind == PCRAMP_MULTIPLEX) return fail(ctx, "pcramp_gpu_accept_assay: the amplicons were cut from the multiplex collection itself");
 	if (pair >= ctx->amp_n_pairs) return fail(ctx, "pcramp_gpu_accept_assay: pair out of range");
+	if (ctx->parent) return fail(ctx, "pcramp_gpu_accept_assay: a worker context shares its parent's sequences and cannot change them");
+	ctx->text_gen++;
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
 	SeqSet &src = ctx->sets[ctx->amp_kind];

@@ -26,12 +26,24 @@ namespace pcr {
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
+	bool owned = true; // false: a view of another context's buffer (worker contexts, pcramp_gpu_create_worker)
+	DevBuf() = default;
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
 	~DevBuf() { release(); }
 	void release()
 	{
-		if (p) cudaFree(p);
+		if (p && owned) cudaFree(p);
 		p = nullptr;
 		cap = 0;
+		owned = true;
+	}
+	void alias(const DevBuf &o)
+	{
+		release();
+		p = o.p;
+		cap = o.cap;
+		owned = false;
 	}
 	cudaError_t ensure(size_t bytes)
 	{
@@ -101,6 +113,10 @@ struct SeqSet {
 struct pcramp_gpu_ctx {
 	using DevBuf = pcr::DevBuf;
 	using SeqSet = pcr::SeqSet;
+	// worker contexts (pcramp_gpu_create_worker): own stream / scratch / database, the parent's sequences and text index by reference.
+	// text_gen counts changes of the parent's collections; a worker refuses to run once it is behind.
+	pcramp_gpu_ctx *parent = nullptr;
+	uint64_t text_gen = 0, seen_gen = 0;
 	int device = 0;
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;

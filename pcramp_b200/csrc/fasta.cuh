@@ -361,7 +361,7 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 	uint64_t max_length, uint32_t n_ignore, const char *const *ignore, uint32_t *n_records)
 {
 	using namespace pcr::fasta;
-	if (check_kind(ctx, kind)) return 1;
+	if (check_kind(ctx, kind) || text_change(ctx, "pcramp_gpu_upload_fasta")) return 1;
 	if (n_files && (!text || !bytes)) return fail(ctx, "pcramp_gpu_upload_fasta: null argument");
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;

@@ -332,6 +332,16 @@ int check_kind(pcramp_gpu_ctx *ctx, int kind)
 {
 	if (!ctx) return 1;
 	if (kind < 0 || kind >= PCRAMP_NUM_KINDS) return fail(ctx, "pcramp_gpu: bad sequence kind");
+	if (ctx->parent && ctx->parent->text_gen != ctx->seen_gen)
+		return fail(ctx, "pcramp_gpu: the parent's sequences changed after this worker was created (destroy it and create a new one)");
+	return 0;
+}
+
+// calls that change a collection: not on a worker (its text is the parent's); every change is counted for the workers' guard
+int text_change(pcramp_gpu_ctx *ctx, const char *who)
+{
+	if (ctx->parent) return fail(ctx, std::string(who) + ": a worker context shares its parent's sequences and cannot change them");
+	ctx->text_gen++;
 	return 0;
 }
 
@@ -370,6 +380,48 @@ int pcramp_gpu_create(pcramp_gpu_ctx **out, int device)
 	return 0;
 }
 
+// A second context on the same device that reads the parent's collections and text index in place and owns everything a batch
+// writes (stream, candidates, hit lists, word database, results): independent batches of a sweep then run concurrently on the
+// GPU, one host thread per context, and the short latency-bound stages of one batch (sorts, list builds, host round trips that
+// size the next stage) fill behind the bandwidth-bound scan of another.
+int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
+{
+	if (!parent || !out) return 1;
+	*out = nullptr;
+	if (parent->parent) return fail(parent, "pcramp_gpu_create_worker: the parent is itself a worker");
+	pcramp_gpu_ctx *ctx = parent;
+	CK(cudaSetDevice(parent->device));
+	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) { // the index is shared: build it once, here
+		SeqSet &s = parent->sets[kind];
+		if (kind != PCRAMP_MULTIPLEX && parent->use_index && s.n_tiles && !s.idx_valid && !s.idx_failed && build_index(parent, s)) return 1;
+	}
+	CK(cudaStreamSynchronize(parent->stream));
+	pcramp_gpu_ctx *w = nullptr;
+	const int rc = pcramp_gpu_create(&w, parent->device);
+	if (rc) return fail(parent, "pcramp_gpu_create_worker: pcramp_gpu_create failed");
+	w->parent = parent;
+	w->seen_gen = parent->text_gen;
+	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index;
+	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table;
+	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
+		const SeqSet &p = parent->sets[kind];
+		SeqSet &s = w->sets[kind];
+		s.n = p.n; s.any_degenerate = p.any_degenerate; s.unit_weights = p.unit_weights; s.total_positions = p.total_positions;
+		s.len = p.len; s.plen = p.plen; s.clen = p.clen; s.weight = p.weight; s.active = p.active; s.raw_off = p.raw_off; s.grp_off = p.grp_off;
+		s.eos = p.eos;
+		s.raw_bytes = p.raw_bytes; s.n_groups = p.n_groups; s.n_tiles = p.n_tiles; s.n_dirty = p.n_dirty;
+		s.d_raw.alias(p.d_raw); s.d_raw_off.alias(p.d_raw_off); s.d_len.alias(p.d_len); s.d_plen.alias(p.d_plen); s.d_clen.alias(p.d_clen);
+		s.d_planes.alias(p.d_planes); s.d_grp_off.alias(p.d_grp_off); s.d_eos_pos.alias(p.d_eos_pos); s.d_eos_off.alias(p.d_eos_off);
+		s.d_weight.alias(p.d_weight); s.d_active.alias(p.d_active); s.d_tile_seq.alias(p.d_tile_seq); s.d_tile_x0.alias(p.d_tile_x0);
+		s.d_dirty_bits.alias(p.d_dirty_bits); s.d_dirty_seq.alias(p.d_dirty_seq); s.d_dirty_grp.alias(p.d_dirty_grp);
+		s.idx_entries.alias(p.idx_entries); s.idx_off.alias(p.idx_off); s.idx_cum.alias(p.idx_cum);
+		s.idx_valid = p.idx_valid; s.idx_failed = p.idx_failed || !p.idx_valid; // never build a private copy of the index
+		s.idx_n = p.idx_n;
+	}
+	*out = w;
+	return 0;
+}
+
 void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx)
 {
 	if (!ctx) return;
@@ -400,7 +452,7 @@ int upload_finish(pcramp_gpu_ctx *ctx, pcr::SeqSet &s, const uint8_t *nibbles, c
 int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const uint8_t *nibbles, const uint64_t *byte_off,
 	const uint32_t *len, const float *weight)
 {
-	if (check_kind(ctx, kind)) return 1;
+	if (check_kind(ctx, kind) || text_change(ctx, "pcramp_gpu_upload_sequences")) return 1;
 	if (n >= (1u << 24)) return fail(ctx, "pcramp_gpu_upload_sequences: at most 2^24 - 1 sequences per collection");
 	CK(cudaSetDevice(ctx->device));
 	SeqSet &s = ctx->sets[kind];
@@ -497,7 +549,7 @@ int upload_finish(pcramp_gpu_ctx *ctx, SeqSet &s, const uint8_t *nibbles, const 
 
 int pcramp_gpu_set_weights(pcramp_gpu_ctx *ctx, int kind, const float *weight)
 { // Sequence::weight(w) (sequence.h), e.g. the per-file normalisation of main.cpp:268-278 after a FASTA upload
-	if (check_kind(ctx, kind)) return 1;
+	if (check_kind(ctx, kind) || text_change(ctx, "pcramp_gpu_set_weights")) return 1;
 	SeqSet &s = ctx->sets[kind];
 	if (s.n && !weight) return fail(ctx, "pcramp_gpu_set_weights: null argument");
 	CK(cudaSetDevice(ctx->device));
@@ -511,7 +563,7 @@ int pcramp_gpu_set_weights(pcramp_gpu_ctx *ctx, int kind, const float *weight)
 
 int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active)
 {
-	if (check_kind(ctx, kind)) return 1;
+	if (check_kind(ctx, kind) || text_change(ctx, "pcramp_gpu_set_active")) return 1;
 	SeqSet &s = ctx->sets[kind];
 	for (uint32_t i = 0; i < s.n; ++i) s.active[i] = active[i] ? 1 : 0;
 	if (s.n) CK(cudaMemcpyAsync(s.d_active.p, s.active.data(), s.n, cudaMemcpyHostToDevice, ctx->stream));
@@ -521,7 +573,7 @@ int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active)
 
 int pcramp_gpu_split_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const uint32_t *seq, const uint32_t *pos)
 { // Sequence::split_sequence (sequence.h:231-243) for a list of positions, e.g. the three splits per amplicon of main.cpp:1008-1017
-	if (check_kind(ctx, kind)) return 1;
+	if (check_kind(ctx, kind) || text_change(ctx, "pcramp_gpu_split_sequence")) return 1;
 	SeqSet &s = ctx->sets[kind];
 	if (n && (!seq || !pos)) return fail(ctx, "pcramp_gpu_split_sequences: null argument");
 	for (uint32_t i = 0; i < n; ++i)
