@@ -73,7 +73,7 @@ struct SeqSet {
 	DevBuf d_dirty_bits, d_dirty_seq, d_dirty_grp; // groups whose alignments read a degenerate base (scan.cuh)
 	uint32_t n_dirty = 0;
 	// text index for the indexed seed scan (index.cuh): built lazily, dropped when the text changes
-	DevBuf idx_entries, idx_off, idx_cum;
+	DevBuf idx_entries, idx_off, idx_cum, idx_blk;
 	bool idx_valid = false, idx_failed = false;
 	uint32_t idx_n = 0;
 	// database (seq-grouped order = entry-id order) + canonical permutation

@@ -35,8 +35,10 @@ struct TextIndex {
 	const uint4 *entries;   // sorted by 12-mer code: {global position, plane0[31:0], plane1[31:0], plane0[47:32] | plane1[47:32] << 16}
 	const uint32_t *off;    // IDX_CODES + 1: first entry whose code is >= c
 	const uint32_t *cum;    // n_seq + 1: global position of each sequence's first base
+	const uint32_t *blk;    // (n >> IDX_BLK_SHIFT) + 2: sequence that holds global position b << IDX_BLK_SHIFT
 	uint32_t n;             // entries
 };
+constexpr uint32_t IDX_BLK_SHIFT = 10u;
 
 // segments of a pattern of n bases with e allowed mismatches
 __host__ __device__ __forceinline__ uint32_t idx_segments(uint32_t e) { return e / 2u + 1u; }
@@ -109,6 +111,19 @@ __device__ __forceinline__ uint32_t idx_seq_of(const uint32_t *__restrict__ cum,
 	return lo;
 }
 
+// the same through the block table: the answer lies between the sequences that hold the ends of the candidate's 1024-position
+// block -- one or two probes instead of log2(n_seq) dependent loads per candidate (index_hits_kernel was 0.14 ms of the step)
+__device__ __forceinline__ uint32_t idx_seq_of_fast(const TextIndex &ix, uint32_t n_seq, uint32_t gpos)
+{
+	const uint32_t b = gpos >> IDX_BLK_SHIFT;
+	uint32_t lo = __ldg(ix.blk + b), hi = min(__ldg(ix.blk + b + 1u) + 1u, n_seq);
+	while (hi - lo > 1u) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (__ldg(ix.cum + mid) <= gpos) lo = mid; else hi = mid;
+	}
+	return lo;
+}
+
 // ---- build ---------------------------------------------------------------------------------------------------
 __global__ void index_key_kernel(SeqDev sd, const uint32_t *__restrict__ cum, uint32_t n_pos, uint32_t *key, uint32_t *val)
 {
@@ -148,19 +163,42 @@ __global__ void index_entry_kernel(SeqDev sd, const uint32_t *__restrict__ cum, 
 struct IdxQuery {
 	uint32_t lo, hi;   // entry range
 	uint32_t pid;      // pattern (index into the seeded part of the partitioned pattern arrays)
-	uint32_t seg;      // segment offset o[7:0] | prefix length k[15:8] | segment number[23:16]
+	uint32_t seg;      // segment offset o[7:0] | prefix length k[15:8] | segment number[23:16] | window offset wo[31:24]
 };
 
+// Extended seeds.  A segment prefix shorter than the 12-base index key (k = 9..11: 18..23-mers) used to be looked up as a
+// PREFIX RANGE -- 4^(12-k) buckets per neighbour, 73 % of all entries streamed came from the k = 9 queries of 18/19-mers.
+// But the x = 12 - k bases next to the segment are pattern bases too, and the whole alignment has at most e mismatches:
+// a neighbour that already spends m (0 or 1) of them inside the segment leaves e - m for those x bases.  When that is
+// fewer than x, only the 12-mers whose extension is within e - m mismatches of the pattern can belong to a hit, and they
+// are queried one bucket each (e = 2, k = 9: 37 + 27 * 10 = 307 buckets instead of 28 * 64).  The window is the segment
+// plus the next x pattern bases (window offset wo = o), or, for a segment that ends with the pattern, the x bases before
+// it (wo = o - x; the bucket of text position X then belongs to the alignment whose primer base 0 is at X - wo).  The
+// pigeonhole argument and the leftmost-segment rule are untouched: a true hit is still found through every segment
+// whose k-prefix is within one mismatch, exactly once per segment (the text 12-mer at the window is one code).
+constexpr uint32_t IDX_EXT_MAX = 64u;  // most single-bucket queries one neighbour may expand into
+
+__device__ __forceinline__ uint32_t idx_ext_count(uint32_t x, uint32_t b)
+{ // 12-mers with at most b substitutions in x positions
+	uint32_t total = 0, c = 1; // c = C(x, j) 3^j
+	for (uint32_t j = 0; j <= b && j <= x; ++j) {
+		total += c;
+		c = c * (x - j) * 3u / (j + 1u);
+	}
+	return total;
+}
+
 __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta2, uint32_t n_pat, const uint32_t *__restrict__ off,
-	IdxQuery *queries, unsigned int *n_queries, unsigned int *n_indexed, unsigned long long *n_entries)
+	IdxQuery *queries, uint32_t q_cap, unsigned int *n_queries, unsigned int *n_indexed, unsigned long long *n_entries)
 {
 	// every lane stays to the end: the three counters are bumped once per WARP (a quarter of a million same-address atomics
 	// serialise in L2 -- they, not the work, were this kernel's 0.23 ms)
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
 	const uint32_t p = t / IDX_SLOTS, slot = t % IDX_SLOTS;
-	bool have = false, counts = false;
-	IdxQuery qy;
-	qy.lo = qy.hi = qy.pid = qy.seg = 0u;
+	bool counts = false;
+	uint32_t n_emit = 0;        // queries this lane writes
+	uint32_t seg_code = 0, k = 0, o = 0, si = 0, wo = 0, x = 0, budget = 0, ext_pat = 0;
+	bool ext_left = false, ext = false;
 	if (p < n_pat) {
 		const uint4 m = mask[p];
 		const uint32_t m2 = meta2[p];
@@ -168,9 +206,9 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 			counts = (slot == 0u);
 			const uint32_t n = (m2 >> 10) & 63u, e = (m2 >> 16) & 63u, segs = idx_segments(e);
 			const uint32_t per = 1u + 3u * IDX_K;
-			const uint32_t si = slot / per, j = slot % per;
+			const uint32_t j = slot % per;
+			si = slot / per;
 			if (si < segs) {
-				uint32_t o, k;
 				idx_segment(n, segs, si, o, k);
 				uint32_t sub_pos = 0xFFFFFFFFu, sub_alt = 0u;
 				bool ok = true;
@@ -180,38 +218,80 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 					ok = sub_pos < k;
 				}
 				if (ok) {
-					uint32_t code = 0;
 					for (uint32_t q = 0; q < k; ++q) {
 						uint32_t l = idx_letter(m, o + q);
 						if (q == sub_pos) l = (l + 1u + sub_alt) & 3u;
-						code = (code << 2) | l;
+						seg_code = (seg_code << 2) | l;
 					}
-					const uint32_t sh = 2u * (IDX_K - k);
-					const uint32_t lo = __ldg(off + (code << sh)), hi = __ldg(off + ((code + 1u) << sh));
-					if (lo < hi) {
-						have = true;
-						qy.lo = lo;
-						qy.hi = hi;
-						qy.pid = p;
-						qy.seg = o | (k << 8) | (si << 16);
+					n_emit = 1u;
+					wo = o;
+					x = IDX_K - k;
+					budget = e - (j > 0u ? 1u : 0u); // e >= 1 whenever a substituted neighbour can be a hit; e == 0 -> j > 0 finds nothing
+					if (j > 0u && e == 0u) n_emit = 0u;
+					if (n_emit && x > 0u && budget < x && idx_ext_count(x, budget) <= IDX_EXT_MAX) {
+						// the x pattern bases after the segment, or before it when the pattern ends with the segment
+						uint32_t first = 0;
+						bool can = false;
+						if (o + IDX_K <= n) { first = o + k; can = true; ext_left = false; }
+						else if (o >= x && o - x <= IDX_CTX_BEFORE) { first = o - x; can = true; ext_left = true; }
+						for (uint32_t q = 0; can && q < x; ++q) {
+							const uint32_t l = idx_letter(m, first + q);
+							if (l > 3u) can = false;
+							ext_pat = (ext_pat << 2) | l;
+						}
+						if (can) {
+							ext = true;
+							if (ext_left) wo = o - x;
+							n_emit = idx_ext_count(x, budget);
+						}
 					}
 				}
 			}
 		}
 	}
-	const uint32_t bal = __ballot_sync(0xffffffffu, have), cnt = __ballot_sync(0xffffffffu, counts);
-	uint32_t span = have ? qy.hi - qy.lo : 0u;
-	for (int s = 16; s > 0; s >>= 1) span += __shfl_xor_sync(0xffffffffu, span, s);
+	// reserve: one atomic per warp
+	uint32_t incl = n_emit;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+		if ((int)lane >= d) incl += v;
+	}
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	const uint32_t cnt = __ballot_sync(0xffffffffu, counts);
 	uint32_t base = 0u;
 	if (lane == 0u) {
-		if (bal) {
-			base = atomicAdd(n_queries, (unsigned int)__popc(bal));
-			atomicAdd(n_entries, (unsigned long long)span);
-		}
+		if (total) base = atomicAdd(n_queries, total);
 		if (cnt) atomicAdd(n_indexed, (unsigned int)__popc(cnt));
 	}
 	base = __shfl_sync(0xffffffffu, base, 0);
-	if (have) queries[base + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = qy;
+	uint32_t at = base + incl - n_emit;
+	unsigned long long span = 0;
+	if (n_emit) {
+		IdxQuery qy;
+		qy.pid = p;
+		qy.seg = o | (k << 8) | (si << 16) | (wo << 24);
+		if (!ext) { // the k-prefix as a range of 4^x buckets
+			const uint32_t sh = 2u * x;
+			qy.lo = __ldg(off + (seg_code << sh));
+			qy.hi = __ldg(off + ((seg_code + 1u) << sh));
+			span += qy.hi - qy.lo;
+			if (at < q_cap) queries[at] = qy;
+		} else {
+			for (uint32_t c = 0; c < (1u << (2u * x)); ++c) {
+				const uint32_t d = c ^ ext_pat, bad = (d | (d >> 1)) & 0x55u;
+				if ((uint32_t)__popc(bad) > budget) continue;
+				const uint32_t code = ext_left ? ((c << (2u * k)) | seg_code) : ((seg_code << (2u * x)) | c);
+				qy.lo = __ldg(off + code);
+				qy.hi = __ldg(off + code + 1u);
+				span += qy.hi - qy.lo;
+				if (at < q_cap) queries[at] = qy;
+				++at;
+			}
+		}
+	}
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) span += __shfl_xor_sync(0xffffffffu, span, d);
+	if (lane == 0u && span) atomicAdd(n_entries, span);
 }
 
 // A verified candidate.  Resolving it (which sequence, is that one active, is the alignment somebody else's, which family
@@ -229,7 +309,10 @@ struct IdxCandSink {
 };
 
 constexpr int IDX_THREADS = 256;
-constexpr int IDX_BLOCKS_PER_SM = 4; // one resident wave of persistent warps, eight 16-byte loads in flight per lane
+#ifndef IDX_BLOCKS
+#define IDX_BLOCKS 4
+#endif
+constexpr int IDX_BLOCKS_PER_SM = IDX_BLOCKS; // one resident wave of persistent warps, eight 16-byte loads in flight per lane
 
 __device__ __forceinline__ uint32_t index_mask(const uint4 &en, const uint4 &B, uint32_t sh)
 {
@@ -304,15 +387,19 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 	return v;
 }
 
-// one warp per query; lanes stride over the entry range (coalesced 16-byte loads, four in flight per lane), the pattern
-// sits in registers
+// one warp per query; lanes stride over the entry range (coalesced 16-byte loads, IDX_ROWS in flight per lane), the pattern
+// sits in registers.  (A version that issued the next query's loads before verifying the current chunk was measured slower:
+// 0.42 against 0.31 ms -- more registers per warp and a longer dependent chain per range than the extra overlap paid for.)
+#ifndef IDX_ROWS
+#define IDX_ROWS 8
+#endif
 __global__ void __launch_bounds__(IDX_THREADS, IDX_BLOCKS_PER_SM)
-scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsigned int *__restrict__ n_queries, const uint4 *__restrict__ mask,
-	const uint32_t *__restrict__ meta, IdxCandSink cs)
+scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsigned int *__restrict__ n_queries, uint32_t q_cap,
+	const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta, IdxCandSink cs)
 {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-	const uint32_t nq = *n_queries;
+	const uint32_t nq = min(*n_queries, q_cap); // more queries than slots: the host grows the buffer and re-runs
 	if (warp >= nq) return;
 	IdxQuery qy = queries[warp];
 	IdxWarpBlock wb;
@@ -321,15 +408,17 @@ scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsi
 		if (q + n_warps < nq) qy = queries[q + n_warps]; // next descriptor in flight while this range streams
 		const uint4 B = __ldg(mask + cur.pid);
 		const uint32_t thr = __ldg(meta + cur.pid) & 63u;
-		const uint32_t sh = IDX_CTX_BEFORE - (cur.seg & 255u); // context bit of primer base 0 (idx_indexable: offset <= 16)
-		// whole rows of 32 entries, eight rows (then one row) at a time; lanes past the end of the range carry no entry
+		const uint32_t sh = IDX_CTX_BEFORE - (cur.seg >> 24); // context bit of primer base 0 (window offset <= 16)
+		// whole rows of 32 entries, IDX_ROWS rows (then up to four) at a time; lanes past the end of the range carry no entry
 		uint32_t i = cur.lo;
-		for (; i + 256u <= cur.hi; i += 256u) {
-			uint4 e[8];
+#if IDX_ROWS > 4
+		for (; i + 32u * IDX_ROWS <= cur.hi; i += 32u * IDX_ROWS) {
+			uint4 e[IDX_ROWS];
 			#pragma unroll
-			for (int u = 0; u < 8; ++u) e[u] = ldg_stream(ix.entries + i + 32u * u + lane);
-			index_append<8>(e, 0xFFu, B, thr, sh, cur, cs, lane, wb);
+			for (int u = 0; u < IDX_ROWS; ++u) e[u] = ldg_stream(ix.entries + i + 32u * u + lane);
+			index_append<IDX_ROWS>(e, (1u << IDX_ROWS) - 1u, B, thr, sh, cur, cs, lane, wb);
 		}
+#endif
 		for (; i < cur.hi; i += 128u) {
 			uint4 e[4];
 			uint32_t valid = 0u;
@@ -357,9 +446,9 @@ index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__res
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
 		const IdxCand c = cs.buf[i];
 		if (c.gpos == IDX_INVALID) continue; // the unused tail of a warp's block
-		const uint32_t o = c.seg & 255u, si = c.seg >> 16;
-		const uint32_t seq = idx_seq_of(ix.cum, sd.n, c.gpos);
-		const int64_t x = (int64_t)(c.gpos - __ldg(ix.cum + seq)) - (int64_t)o; // text index of primer base 0
+		const uint32_t wo = c.seg >> 24, si = (c.seg >> 16) & 255u;
+		const uint32_t seq = idx_seq_of_fast(ix, sd.n, c.gpos);
+		const int64_t x = (int64_t)(c.gpos - __ldg(ix.cum + seq)) - (int64_t)wo; // text index of primer base 0
 		if (x < 0 || !sd.active[seq]) continue;
 		if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
 			const uint64_t G = sd.grp_off[seq] + (uint64_t)(x >> 5);

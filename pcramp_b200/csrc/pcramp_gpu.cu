@@ -313,6 +313,18 @@ int build_index(pcramp_gpu_ctx *ctx, SeqSet &s)
 		return 0;
 	}
 	CK(cudaMemcpyAsync(s.idx_cum.p, cum.data(), (size_t)(s.n + 1) * 4, cudaMemcpyHostToDevice, st));
+	{ // block table: last sequence whose first position is <= b << IDX_BLK_SHIFT (idx_seq_of_fast)
+		std::vector<uint32_t> blk((N >> IDX_BLK_SHIFT) + 2, 0);
+		uint32_t q = 0;
+		for (size_t b = 0; b < blk.size(); ++b) {
+			const uint64_t g = (uint64_t)b << IDX_BLK_SHIFT;
+			while (q + 1 < s.n && cum[q + 1] <= g) ++q;
+			blk[b] = q;
+		}
+		CK(s.idx_blk.ensure(blk.size() * 4));
+		CK(cudaMemcpyAsync(s.idx_blk.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, st));
+		CK(cudaStreamSynchronize(st));
+	}
 	const SeqDev sd = s.dev();
 	index_key_kernel<<<grid_for(N, 256), 256, 0, st>>>(sd, s.idx_cum.as<uint32_t>(), (uint32_t)N, key[0].as<uint32_t>(), val[0].as<uint32_t>());
 	CK(cudaGetLastError());
@@ -414,7 +426,7 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 		s.d_planes.alias(p.d_planes); s.d_grp_off.alias(p.d_grp_off); s.d_eos_pos.alias(p.d_eos_pos); s.d_eos_off.alias(p.d_eos_off);
 		s.d_weight.alias(p.d_weight); s.d_active.alias(p.d_active); s.d_tile_seq.alias(p.d_tile_seq); s.d_tile_x0.alias(p.d_tile_x0);
 		s.d_dirty_bits.alias(p.d_dirty_bits); s.d_dirty_seq.alias(p.d_dirty_seq); s.d_dirty_grp.alias(p.d_dirty_grp);
-		s.idx_entries.alias(p.idx_entries); s.idx_off.alias(p.idx_off); s.idx_cum.alias(p.idx_cum);
+		s.idx_entries.alias(p.idx_entries); s.idx_off.alias(p.idx_off); s.idx_cum.alias(p.idx_cum); s.idx_blk.alias(p.idx_blk);
 		s.idx_valid = p.idx_valid; s.idx_failed = p.idx_failed || !p.idx_valid; // never build a private copy of the index
 		s.idx_n = p.idx_n;
 	}
@@ -874,30 +886,32 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		}
 		use_idx = use_idx && s.idx_valid;
 		if (use_idx) {
-			CK(ctx->d_idx_queries.ensure((size_t)n_seeded * IDX_SLOTS * sizeof(IdxQuery)));
 			CK(ctx->d_idx_counters.ensure(32));
-			CK(cudaMemsetAsync(ctx->d_idx_counters.p, 0, 32, st));
 			unsigned int *d_nq = ctx->d_idx_counters.as<unsigned int>();
-			index_query_kernel<<<grid_for((uint64_t)n_seeded * IDX_SLOTS, 256), 256, 0, st>>>(ctx->d_part_mask.as<uint4>(),
-				ctx->d_part_meta2.as<uint32_t>(), n_seeded, s.idx_off.as<uint32_t>(), ctx->d_idx_queries.as<IdxQuery>(), d_nq, d_nq + 1,
-				(unsigned long long *)(d_nq + 2));
-			CK(cudaGetLastError());
 			TextIndex ix;
 			ix.entries = s.idx_entries.as<uint4>();
 			ix.off = s.idx_off.as<uint32_t>();
 			ix.cum = s.idx_cum.as<uint32_t>();
+			ix.blk = s.idx_blk.as<uint32_t>();
 			ix.n = s.idx_n;
 			IdxCandSink cs;
 			unsigned int h_idx[4] = {0, 0, 0, 0};
-			for (int grow = 0;; ++grow) { // candidates awaiting resolution: sized like the hit buffer, grown if they overflow
+			for (int grow = 0;; ++grow) { // queries and candidates awaiting resolution: grown if they overflow (sizes repeat from batch to batch)
+				// extended seeds expand a neighbour into up to IDX_EXT_MAX single-bucket queries: ~600 per 18-mer, fewer for longer primers
+				const uint64_t qcap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_queries.cap / sizeof(IdxQuery), (uint64_t)n_seeded * 640u), 0xFFFFFFF0ull);
+				CK(ctx->d_idx_queries.ensure(qcap * sizeof(IdxQuery)));
+				CK(cudaMemsetAsync(ctx->d_idx_counters.p, 0, 32, st));
+				index_query_kernel<<<grid_for((uint64_t)n_seeded * IDX_SLOTS, 256), 256, 0, st>>>(ctx->d_part_mask.as<uint4>(),
+					ctx->d_part_meta2.as<uint32_t>(), n_seeded, s.idx_off.as<uint32_t>(), ctx->d_idx_queries.as<IdxQuery>(), (uint32_t)qcap, d_nq, d_nq + 1,
+					(unsigned long long *)(d_nq + 2));
+				CK(cudaGetLastError());
 				const uint64_t ccap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_cand.cap / sizeof(IdxCand), cap), 0xFFFFFFF0ull);
 				CK(ctx->d_idx_cand.ensure(ccap * sizeof(IdxCand)));
 				cs.buf = ctx->d_idx_cand.as<IdxCand>();
 				cs.count = d_nq + 4;
 				cs.cap = (uint32_t)ccap;
-				CK(cudaMemsetAsync(d_nq + 4, 0, 4, st));
 				CK(cudaEventRecord(ctx->ev[8], st));
-				scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq,
+				scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq, (uint32_t)qcap,
 					ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
 				CK(cudaGetLastError());
 				CK(cudaEventRecord(ctx->ev[9], st));
@@ -907,9 +921,10 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				CK(cudaMemcpyAsync(h_idx, d_nq, 16, cudaMemcpyDeviceToHost, st)); // query / entry counters: same round trip
 				CK(cudaStreamSynchronize(st));
 				stat.ms_index_kernel = ev_ms(ctx->ev[8], ctx->ev[9]);
-				if (n_c <= cs.cap) break;
-				if (grow >= 2) return fail(ctx, "pcramp_gpu_select_words: index candidate buffer kept overflowing");
-				CK(ctx->d_idx_cand.ensure(((size_t)n_c + n_c / 8 + 1024) * sizeof(IdxCand)));
+				if (n_c <= cs.cap && h_idx[0] <= qcap) break;
+				if (grow >= 3) return fail(ctx, "pcramp_gpu_select_words: index query / candidate buffers kept overflowing");
+				if (h_idx[0] > qcap) CK(ctx->d_idx_queries.ensure(((size_t)h_idx[0] + h_idx[0] / 8 + 1024) * sizeof(IdxQuery)));
+				if (n_c > cs.cap) CK(ctx->d_idx_cand.ensure(((size_t)n_c + n_c / 8 + 1024) * sizeof(IdxCand)));
 			}
 			index_hits_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, st>>>(sd, ix, cs, ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(),
 				s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, cand_bits, hs);

@@ -109,12 +109,35 @@ __device__ __forceinline__ bool has_split_dev(const SeqDev &sd, uint32_t seq, in
 	return eos_upto_raw(sd, seq, (int64_t)loc + len - 1) != eos_upto_raw(sd, seq, (int64_t)loc - 1);
 }
 
-// n bases b_{first..first+n-1} of the compressed text, left-justified in a word
+// 16 plane bits -> 16 nibble slots of a 64-bit limb: bit j -> bit 4 j
+__device__ __forceinline__ uint64_t spread_to_nibbles(uint32_t v)
+{
+	uint64_t x = v & 0xFFFFu;
+	x = (x ^ (x << 24)) & 0x000000FF000000FFull;
+	x = (x ^ (x << 12)) & 0x000F000F000F000Full;
+	x = (x ^ (x << 6)) & 0x0303030303030303ull;
+	x = (x ^ (x << 3)) & 0x1111111111111111ull;
+	return x;
+}
+
+// n <= 32 bases b_{first..first+n-1} of the compressed text, left-justified in a word.  Two 16-byte plane loads and four funnel
+// shifts give the window as four 32-bit letter planes (bit k = base first + k); word position k is nibble 15 - k of its limb
+// (word128.cuh), so each 16-bit half is bit-reversed and spread to every fourth bit.  (One plane load per base -- 32 dependent
+// extractions per entry -- made materialise_kernel 0.22 ms of the step.)
 __device__ inline W128 gather_bases(const SeqDev &sd, uint32_t seq, uint32_t first, uint32_t n)
 {
+	const uint64_t gb = sd.grp_off[seq];
+	const uint32_t ngrp = (uint32_t)(sd.grp_off[seq + 1] - gb), g = first >> 5, sh = first & 31u;
+	const uint4 z = make_uint4(0, 0, 0, 0);
+	const uint4 p0 = g < ngrp ? __ldg(sd.planes + gb + g) : z;
+	const uint4 p1 = g + 1u < ngrp ? __ldg(sd.planes + gb + g + 1u) : z;
+	const uint32_t keep = n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
+	const uint32_t a = __brev(__funnelshift_r(p0.x, p1.x, sh) & keep), c = __brev(__funnelshift_r(p0.y, p1.y, sh) & keep);
+	const uint32_t gg = __brev(__funnelshift_r(p0.z, p1.z, sh) & keep), t = __brev(__funnelshift_r(p0.w, p1.w, sh) & keep);
+	// after the reversal base k sits at bit 31 - k: bases 0..15 are the high half-word, in limb order already
 	W128 w;
-	w.hi = w.lo = 0;
-	for (uint32_t k = 0; k < n; ++k) w_set(w, (int)k, comp_nibble_at(sd, seq, first + k));
+	w.hi = spread_to_nibbles(a >> 16) | (spread_to_nibbles(c >> 16) << 1) | (spread_to_nibbles(gg >> 16) << 2) | (spread_to_nibbles(t >> 16) << 3);
+	w.lo = spread_to_nibbles(a) | (spread_to_nibbles(c) << 1) | (spread_to_nibbles(gg) << 2) | (spread_to_nibbles(t) << 3);
 	return w;
 }
 
