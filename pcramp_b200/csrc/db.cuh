@@ -85,6 +85,41 @@ __global__ void tier_table_kernel(const uint64_t *__restrict__ hit_key, const ui
 	entry_cand[o] = cand;
 }
 
+// The same table with ONE BYTE per cell: bit t of a cell = "a hit with count = threshold + t was seen" (every hit of a candidate
+// has count >= its threshold, so t <= size - threshold; the host uses this form when that is at most 7 for every oligo size).
+// 20 000 sequences x 2 000 candidates are then 40 MB instead of 160 MB -- resident in L2, where the 160 MB table turned every
+// atomic into a DRAM round trip (tier_best + tier_table were 0.20 ms of the step) -- and the best tier is the highest bit set.
+__global__ void tier_mask_kernel(const uint64_t *__restrict__ hit_key, uint64_t n_hits, uint32_t cand_bits, uint32_t n_cand,
+	const uint32_t *__restrict__ cand_thr, uint32_t *mask)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_hits) return;
+	const uint64_t k = hit_key[i];
+	if (k == ~0ull) return;
+	const uint32_t seq = (uint32_t)(k >> (HIT_GROUP_SHIFT + cand_bits)), cand = (uint32_t)(k >> HIT_GROUP_SHIFT) & ((1u << cand_bits) - 1u);
+	const uint32_t count = 63u - ((uint32_t)(k >> 3) & 63u), t = min(count - __ldg(cand_thr + cand), 7u);
+	const uint64_t cell = (uint64_t)seq * n_cand + cand;
+	atomicOr(mask + (cell >> 2), 1u << (8u * (uint32_t)(cell & 3ull) + t));
+}
+
+__global__ void tier_mask_select_kernel(const uint64_t *__restrict__ hit_key, const uint32_t *__restrict__ hit_val, uint64_t n_hits, uint32_t cand_bits,
+	uint32_t n_cand, const uint32_t *__restrict__ cand_thr, const uint32_t *__restrict__ mask, uint32_t pb, uint64_t *entry_id, uint32_t *entry_cand,
+	unsigned long long *n_out)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_hits) return;
+	const uint64_t k = hit_key[i];
+	if (k == ~0ull) return;
+	const uint32_t seq = (uint32_t)(k >> (HIT_GROUP_SHIFT + cand_bits)), cand = (uint32_t)(k >> HIT_GROUP_SHIFT) & ((1u << cand_bits) - 1u);
+	const uint32_t count = 63u - ((uint32_t)(k >> 3) & 63u), t = min(count - __ldg(cand_thr + cand), 7u);
+	const uint64_t cell = (uint64_t)seq * n_cand + cand;
+	const uint32_t byte = (mask[cell >> 2] >> (8u * (uint32_t)(cell & 3ull))) & 255u;
+	if ((byte >> (t + 1u)) != 0u) return; // a higher tier exists for this (sequence, candidate)
+	const unsigned long long o = warp_slot(n_out);
+	entry_id[o] = entry_id_pack(seq, (uint32_t)(k >> 1) & 3u, (uint32_t)k & 1u, hit_val[i], pb);
+	entry_cand[o] = cand;
+}
+
 // word, loc, strand, seq of each unique entry (entry ids sorted => grouped by sequence)
 __global__ void materialise_kernel(SeqDev sd, PackParams pp, const uint64_t *__restrict__ entry_id, uint64_t n, uint32_t pb, uint64_t *w_hi,
 	uint64_t *w_lo, uint4 *e_planes, uint32_t *e_seq, int32_t *e_loc, uint32_t *e_strand, uint64_t *order_key)

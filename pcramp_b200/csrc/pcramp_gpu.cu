@@ -1070,7 +1070,21 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	for (uint32_t L : s.plen) longest = std::max(longest, L);
 	const uint32_t pos_bits = std::min<uint32_t>(32u, bits_for((uint64_t)longest + 64ull)); // hit positions are below plen + 32
 	const uint64_t tier_cells = (uint64_t)s.n * n_cand;
-	if (ctx->use_tier_table && tier_cells <= (1ull << 27)) {
+	uint32_t tier_span = 0; // largest (size - threshold count) over the oligo sizes: the tiers a candidate can have
+	for (uint32_t sz = 1; sz <= 32u; ++sz) tier_span = std::max(tier_span, sz - std::min(sz, (uint32_t)((float)sz * threshold)));
+	if (ctx->use_tier_table && tier_span <= 7u && tier_cells <= (1ull << 31)) {
+		// best tier per (sequence, candidate) through a byte-per-cell table of tier bits (db.cuh): no sort of the hit list
+		const uint64_t words = tier_cells / 4 + 1;
+		CK(ctx->d_tier_best.ensure(words * 4));
+		CK(cudaMemsetAsync(ctx->d_tier_best.p, 0, words * 4, st));
+		tier_mask_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), n_hits, cand_bits, n_cand, ctx->d_cand_thr.as<uint32_t>(),
+			ctx->d_tier_best.as<uint32_t>());
+		tier_mask_select_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), ctx->hit_val[0].as<uint32_t>(), n_hits, cand_bits,
+			n_cand, ctx->d_cand_thr.as<uint32_t>(), ctx->d_tier_best.as<uint32_t>(), pos_bits, ctx->ent_id[0].as<uint64_t>(),
+			ctx->ent_cand[0].as<uint32_t>(), d_cnt);
+		CK(cudaGetLastError());
+		stat.kernel_launches += 2;
+	} else if (ctx->use_tier_table && tier_cells <= (1ull << 27)) {
 		// best tier per (sequence, candidate) through a table of maxima: no sort of the hit list
 		CK(ctx->d_tier_best.ensure(std::max<uint64_t>(1, tier_cells) * 4));
 		CK(cudaMemsetAsync(ctx->d_tier_best.p, 0, tier_cells * 4, st));
