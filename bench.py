@@ -38,7 +38,7 @@ TARGET_THR = np.float32(1.0)    # DEFAULT_TARGET_THRESHOLD (pcramp.h:36)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--targets", type=int, default=20000)
@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the shards' bitsets are merged -- p2p = peer stores over NVLink fused into the tail of pair scoring "
                          "(xchg.cuh, the product path); nccl = all-gather + pcramp_gpu_merge_shards (the baseline it replaces)")
-    ap.add_argument("--workers", type=int, default=2,
+    ap.add_argument("--workers", type=int, default=4,
                     help="batches in flight per GPU (pairs sharding / one GPU): worker contexts (pcramp_gpu_create_worker) that share the resident "
                          "targets + text index, one host thread each; 1 = one batch at a time")
     ap.add_argument("--fasta-targets", type=int, default=8000, help="sequences in the FASTA-ingest leg (0 = skip; rank 0 only)")
@@ -631,9 +631,7 @@ def run_b200(a):
         if not by_targets:
             c = ctxs[k]
             c.select_words(TARGET, fb, rb, thr, want_keys=False)
-            cov, bits = c.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR))
-            host_cov_k.numpy()[:] = cov
-            host_bits_k.numpy().view(np.uint32)[:] = bits
+            c.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR), out=(host_cov_k.numpy(), host_bits_k.numpy().view(np.uint32)))
             if timed:
                 with lock:
                     launches[0] += c.stats()["kernel_launches"]

@@ -397,12 +397,19 @@ class PcrampGpu:
         return keys
 
     # ---- pair scoring -------------------------------------------------------------------------
-    def score_pairs(self, kind, f, r, search_threshold, detect_threshold, amplicon_min=80, amplicon_max=200, use_taq_mama=False):
+    def score_pairs(self, kind, f, r, search_threshold, detect_threshold, amplicon_min=80, amplicon_max=200, use_taq_mama=False, out=None):
+        """-> (coverage float32[n], bitsets uint32[n, words]); out = (coverage, bitsets) arrays to fill instead (e.g. views of pinned
+        host memory: the device-to-host copy then runs at full PCIe rate instead of through the driver's staging buffer)"""
         f, r = _words(f), _words(r)
         n = len(f)
         nw = (self.n_seq[kind] + 31) // 32
-        cov = np.zeros(n, np.float32)
-        bits = np.zeros((n, nw), np.uint32)
+        if out is not None:
+            cov, bits = out
+            assert cov.dtype == np.float32 and bits.dtype == np.uint32 and cov.shape == (n,) and bits.shape == (n, nw)
+            assert cov.flags.c_contiguous and bits.flags.c_contiguous
+        else:
+            cov = np.zeros(n, np.float32)
+            bits = np.zeros((n, nw), np.uint32)
         self._ck(self.lib.pcramp_gpu_score_pairs(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), n, float(search_threshold),
                                                  float(detect_threshold), int(amplicon_min), int(amplicon_max), int(use_taq_mama),
                                                  _ptr(cov, _f32p), _ptr(bits, _u32p)))

@@ -388,8 +388,11 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 }
 
 // one warp per query; lanes stride over the entry range (coalesced 16-byte loads, IDX_ROWS in flight per lane), the pattern
-// sits in registers.  (A version that issued the next query's loads before verifying the current chunk was measured slower:
-// 0.42 against 0.31 ms -- more registers per warp and a longer dependent chain per range than the extra overlap paid for.)
+// sits in registers.  Measured alternatives, all slower than this loop's 0.31 ms on the bench batch (6 x 10^7 entries in 9.5 x 10^5
+// ranges): issuing the next range's loads before verifying the current chunk 0.42 ms; 8 or 16 lanes per range with 4 / 2 ranges
+// side by side in a warp 0.71 / 0.65 ms (per-lane pattern registers push the kernel into spills at 64 registers); 5, 6 or 8
+// resident CTAs per SM 0.40 / 0.54 / 0.83 ms (spills again).  What is left is latency: ~60 entries per range, one range at a time
+// per warp, 32 warps per SM -- 3.1 TB/s of index stream, 0.47 of the HBM peak.
 #ifndef IDX_ROWS
 #define IDX_ROWS 8
 #endif
