@@ -446,27 +446,61 @@ index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__res
 	const uint32_t *__restrict__ dirty_bits, uint32_t cand_bits, HitSink hs)
 {
 	const uint32_t total = min(*cs.count, cs.cap);
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-		const IdxCand c = cs.buf[i];
-		if (c.gpos == IDX_INVALID) continue; // the unused tail of a warp's block
-		const uint32_t wo = c.seg >> 24, si = (c.seg >> 16) & 255u;
-		const uint32_t seq = idx_seq_of_fast(ix, sd.n, c.gpos);
-		const int64_t x = (int64_t)(c.gpos - __ldg(ix.cum + seq)) - (int64_t)wo; // text index of primer base 0
-		if (x < 0 || !sd.active[seq]) continue;
-		if (dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
-			const uint64_t G = sd.grp_off[seq] + (uint64_t)(x >> 5);
-			if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) continue;
+	const uint32_t lane = threadIdx.x & 31u;
+	// warp-uniform trip count: the lanes of a warp meet again before the hit list is touched, so a row of 32 candidates costs one
+	// atomic on the list counter instead of one per group of lanes that happened to survive the same branches
+	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += gridDim.x * blockDim.x) {
+		const uint32_t i = i0 + lane;
+		bool ok = false;
+		uint32_t seq = 0, meta = 0, meta2 = 0, cnt = 0;
+		int64_t x = 0;
+		if (i < total) {
+			const IdxCand c = cs.buf[i];
+			if (c.gpos != IDX_INVALID) { // (else: the unused tail of a warp's block)
+				const uint32_t wo = c.seg >> 24, si = (c.seg >> 16) & 255u;
+				seq = idx_seq_of_fast(ix, sd.n, c.gpos);
+				x = (int64_t)(c.gpos - __ldg(ix.cum + seq)) - (int64_t)wo; // text index of primer base 0
+				ok = x >= 0 && sd.active[seq];
+				if (ok && dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
+					const uint64_t G = sd.grp_off[seq] + (uint64_t)(x >> 5);
+					if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) ok = false;
+				}
+				if (ok) {
+					meta = __ldg(g_meta + c.pid);
+					meta2 = __ldg(g_meta2 + c.pid);
+					const uint32_t n = (meta2 >> 10) & 63u, segs = idx_segments((meta2 >> 16) & 63u);
+					for (uint32_t k = 0; k < si; ++k) { // an earlier segment whose prefix is within one mismatch reports this alignment
+						uint32_t oo, kk;
+						idx_segment(n, segs, k, oo, kk);
+						if ((uint32_t)__popc((c.m >> oo) & ((1u << kk) - 1u)) + 1u >= kk) ok = false;
+					}
+					cnt = (uint32_t)__popc(c.m);
+				}
+			}
 		}
-		const uint32_t meta = __ldg(g_meta + c.pid), meta2 = __ldg(g_meta2 + c.pid);
-		const uint32_t n = (meta2 >> 10) & 63u, segs = idx_segments((meta2 >> 16) & 63u);
-		bool earlier = false;
-		for (uint32_t k = 0; k < si; ++k) { // an earlier segment whose prefix is within one mismatch reports this alignment
-			uint32_t oo, kk;
-			idx_segment(n, segs, k, oo, kk);
-			if ((uint32_t)__popc((c.m >> oo) & ((1u << kk) - 1u)) + 1u >= kk) earlier = true;
+		const bool family = ok && (meta2 & 1023u) != 0u; // 5'/3' shift families fan out to several candidates: the general path
+		if (family) emit_family(hs, seq, sd.clen[seq], cand_bits, meta, meta2, x, cnt);
+		// the plain case (no shift family): at most one hit per candidate, appended with one atomic per warp
+		bool one = ok && !family;
+		uint32_t wstart = 0;
+		if (one) {
+			const int64_t ws = x - (int64_t)((meta >> 6) & 31u);
+			one = ws >= 0 && ws + 32 <= (int64_t)sd.clen[seq];
+			wstart = (uint32_t)ws;
 		}
-		if (earlier) continue;
-		emit_family(hs, seq, sd.clen[seq], cand_bits, meta, meta2, x, (uint32_t)__popc(c.m));
+		const uint32_t bal = __ballot_sync(0xffffffffu, one);
+		if (bal) {
+			unsigned long long base = 0;
+			if (lane == 0u) base = atomicAdd(hs.count, (unsigned long long)__popc(bal));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (one) {
+				const unsigned long long at = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+				if (at < hs.cap) {
+					hs.key[at] = hit_key_pack(seq, meta >> 12, cand_bits, cnt, ENT_FULL, (meta >> 11) & 1u);
+					hs.val[at] = wstart + 31u;
+				}
+			}
+		}
 	}
 }
 

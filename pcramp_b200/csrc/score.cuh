@@ -445,7 +445,12 @@ __global__ void seq_pairs_kernel(SeqDev sd, const uint32_t *__restrict__ seq_off
 		any &= any - 1u;
 		const uint32_t pair = (w * 32u + b) >> 1;
 		if (pair < n_pairs) {
-			const unsigned int i = atomicAdd(n_items, 1u);
+			// one atomic per group of lanes that are here together (~10^6 items per batch on ONE counter otherwise)
+			const unsigned am = __activemask(), ln = threadIdx.x & 31u;
+			const int leader = __ffs(am) - 1;
+			unsigned int i = 0;
+			if ((int)ln == leader) i = atomicAdd(n_items, (unsigned int)__popc(am));
+			i = __shfl_sync(am, i, leader) + (unsigned int)__popc(am & ((1u << ln) - 1u));
 			if (i < cap) {
 				ScoreItem it;
 				it.seq = seq;
