@@ -142,7 +142,7 @@ struct pcramp_gpu_ctx {
 	DevBuf d_idx_queries, d_idx_counters, d_idx_cand;
 	// scratch
 	DevBuf ent_cand[2], d_neigh, d_neigh_off, d_tier_best;
-	int use_neigh = 1, use_tier_table = 1;
+	int use_neigh = 1, use_tier_table = 1, use_fused_score = 0; // score_seqbits_kernel: measured slower than the item list (0.65 vs 0.60 ms), kept as an option
 	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
 	unsigned long long *h_counters = nullptr; // pinned
 	pcramp_gpu_stats stats = {};

@@ -414,7 +414,7 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	w->parent = parent;
 	w->seen_gen = parent->text_gen;
 	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index;
-	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table;
+	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
 	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
 		const SeqSet &p = parent->sets[kind];
 		SeqSet &s = w->sets[kind];
@@ -1421,6 +1421,23 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 					CK(cudaGetLastError());
 					ctx->stats.kernel_launches++;
 				}
+				if ((chunk_fst || use_neigh) && ctx->use_fused_score) {
+					// bit rows -> exact amplicon test, one CTA per sequence with its entries in shared memory (no item list, no round trip)
+					const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8u);
+					if (variant)
+						score_seqbits_kernel<true><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+							s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>() + 2ull * p0, ctx->d_oligos_base.as<OligoDev>() + 2ull * p0,
+							ctx->d_seqbits.as<uint32_t>(), nw, pc, detect_threshold, amp_min, amp_max, taq,
+							ctx->d_bits.as<uint32_t>() + (size_t)p0 * n_words, ctx->d_bits1.as<uint32_t>() + (size_t)p0 * n_words, n_words);
+					else
+						score_seqbits_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+							s.seq_ent_off.as<uint32_t>(), ctx->d_oligos.as<OligoDev>() + 2ull * p0, nullptr, ctx->d_seqbits.as<uint32_t>(), nw, pc,
+							detect_threshold, amp_min, amp_max, taq,
+							ctx->d_bits.as<uint32_t>() + (size_t)p0 * n_words, ctx->d_bits1.as<uint32_t>() + (size_t)p0 * n_words, n_words);
+					CK(cudaGetLastError());
+					ctx->stats.kernel_launches++;
+					continue;
+				}
 				for (int attempt = 0;; ++attempt) {
 					CK(ctx->d_items.ensure(item_cap * sizeof(ScoreItem)));
 					CK(cudaMemsetAsync(ctx->d_item_count.p, 0, 16, st));
@@ -1662,6 +1679,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_seed_table") == 0) { ctx->use_fst = value; return 0; }
 	if (strcmp(name, "use_neighbours") == 0) { ctx->use_neigh = value; return 0; }
 	if (strcmp(name, "use_tier_table") == 0) { ctx->use_tier_table = value; return 0; }
+	if (strcmp(name, "use_fused_score") == 0) { ctx->use_fused_score = value; return 0; }
 	return fail(ctx, std::string("pcramp_gpu_set_option: unknown option ") + name);
 }
 

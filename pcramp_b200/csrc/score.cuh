@@ -491,6 +491,61 @@ score_items_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__r
 	}
 }
 
+// seq_pairs_kernel + score_items_kernel in one: a CTA takes a sequence, stages its database entries in shared memory once
+// (~130 entries, 24 bytes each), and its warps walk the sequence's two (strand, oligo) bit rows; every pair with F(+) & R(-) or
+// R(+) & F(-) gets the exact amplicon test straight away, against the staged entries.  The item list, the host round trip that
+// sized it, and the per-item re-reads of the entries through L2 (score_items_kernel: 0.34 ms, long-scoreboard bound) go away.
+// MEASURED SLOWER on the bench batch (pair scoring 0.65 ms against 0.60 ms with the item list): ~50 items per sequence over 8
+// warps and two barriers per sequence leave the SMs emptier than one warp per item over 10^6 items does.  Option
+// "use_fused_score" (default off); tests/test_gpu_parity.py::test_fused_sequence_scoring_equals_item_list keeps it honest.
+template <bool VARIANT>
+__global__ void __launch_bounds__(SCORE_THREADS)
+score_seqbits_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand,
+	const uint32_t *__restrict__ seq_off2, const OligoDev *__restrict__ oligos, const OligoDev *__restrict__ base, const uint32_t *__restrict__ seqbits,
+	uint32_t n_words, uint32_t n_pairs, float detect, int amp_min, int amp_max, int taq, uint32_t *bits_any, uint32_t *bits_pass1, uint32_t n_words_seq)
+{
+	__shared__ ScoreEntry s_ent[SCORE_SMEM_ENTRIES];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = SCORE_THREADS / 32;
+	for (uint32_t seq = blockIdx.x; seq < sd.n; seq += gridDim.x) {
+		const uint32_t e0 = seq_off2[2 * seq], Ep = seq_off2[2 * seq + 1] - e0, E = seq_off2[2 * seq + 2] - e0;
+		if (Ep == 0u || Ep == E || !sd.active[seq]) continue; // needs both strands; inactive: optimize.cpp:280-283
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < min(E, (uint32_t)SCORE_SMEM_ENTRIES); i += SCORE_THREADS) {
+			ScoreEntry en;
+			const uint4 v = g_pl[e0 + i];
+			en.a = v.x; en.c = v.y; en.g = v.z; en.t = v.w;
+			en.loc = g_loc[e0 + i]; en.strand = g_strand[e0 + i];
+			s_ent[i] = en;
+		}
+		__syncthreads();
+		for (uint32_t w = warp; w < n_words; w += n_warps) {
+			const uint32_t plus = __ldg(seqbits + (size_t)(2u * seq) * n_words + w), minus = __ldg(seqbits + (size_t)(2u * seq + 1u) * n_words + w);
+			const uint32_t pass1 = (plus & 0x55555555u) & ((minus >> 1) & 0x55555555u); // F(+) & R(-): even bits F, odd bits R
+			const uint32_t pass2 = ((plus >> 1) & 0x55555555u) & (minus & 0x55555555u); // R(+) & F(-)
+			uint32_t any = pass1 | pass2; // uniform over the warp
+			while (any) {
+				const uint32_t b = (uint32_t)__ffs(any) - 1u;
+				any &= any - 1u;
+				const uint32_t q = (w * 32u + b) >> 1;
+				if (q >= n_pairs) continue;
+				const OligoDev Fq = oligos[2 * q], Rq = oligos[2 * q + 1];
+				const OligoDev Fb = VARIANT ? base[2 * q] : Fq, Rb = VARIANT ? base[2 * q + 1] : Rq;
+				const bool d1 = ((pass1 >> b) & 1u)
+				                    ? amplicon_pass<VARIANT>(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Fq, Rq, Fb, Rb, detect, amp_min, amp_max, taq, lane)
+				                    : false;
+				const bool d2 = (d1 || !((pass2 >> b) & 1u))
+				                    ? false
+				                    : amplicon_pass<VARIANT>(sd, seq, s_ent, g_pl, g_loc, g_strand, e0, Ep, E, Rq, Fq, Rb, Fb, detect, amp_min, amp_max, taq, lane);
+				if (lane == 0u && (d1 || d2)) {
+					const uint32_t bit = 1u << (seq & 31u);
+					atomicOr(bits_any + (size_t)q * n_words_seq + (seq >> 5), bit);
+					if (d1) atomicOr(bits_pass1 + (size_t)q * n_words_seq + (seq >> 5), bit);
+				}
+			}
+		}
+	}
+}
+
 // compute_coverage (pcr_assay.cpp:271-302): weights of the detected sequences summed in double in the
 // order the reference meets them -- pass-1 amplicons by ascending sequence, then the sequences only
 // pass 2 finds, ascending -- and narrowed to float on return.

@@ -391,3 +391,26 @@ def test_merge_shards_equals_unsharded(gpu):
     assert np.array_equal(out_bits.cpu().numpy().view(np.uint32), bits_all)
     assert np.array_equal(out_cov.cpu().numpy(), cov_all)
     assert bits_all.any()
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_fused_sequence_scoring_equals_item_list(gpu, name):
+    """the per-sequence scoring kernel (entries staged in shared memory, pairs read off the bit rows) == the item list +
+    one warp per item it replaces: coverages and bitsets identical, for the oligos of the database and for others"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+    out = []
+    for fused in (0, 1):
+        gpu.set_option("use_fused_score", fused)
+        try:
+            cov, bits = gpu.score_pairs(TARGET, sc.f, sc.r, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+            cov2, bits2 = gpu.score_pairs(TARGET, sc.r, np.roll(sc.f, 1, axis=0), sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+            out.append((cov, bits, cov2, bits2))
+        finally:
+            gpu.set_option("use_fused_score", 0)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
