@@ -54,9 +54,10 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the shards' bitsets are merged -- p2p = peer stores over NVLink fused into the tail of pair scoring "
                          "(xchg.cuh, the product path); nccl = all-gather + pcramp_gpu_merge_shards (the baseline it replaces)")
-    ap.add_argument("--workers", type=int, default=4,
+    ap.add_argument("--workers", type=int, default=0,
                     help="batches in flight per GPU (pairs sharding / one GPU): worker contexts (pcramp_gpu_create_worker) that share the resident "
-                         "targets + text index, one host thread each; 1 = one batch at a time")
+                         "targets + text index, one host thread each; 1 = one batch at a time; 0 = 4, 5 or 6, whichever divides --steps with "
+                         "the fewest idle slots in the last round")
     ap.add_argument("--fasta-targets", type=int, default=8000, help="sequences in the FASTA-ingest leg (0 = skip; rank 0 only)")
     ap.add_argument("--dp-problems", type=int, default=262144, help="NucCruc problems per step of the DP GCUPS leg (0 = skip the leg)")
     ap.add_argument("--dp-cpu-problems", type=int, default=60000, help="problems in the bounded CPU sample of the DP leg")
@@ -548,7 +549,14 @@ def run_b200(a):
     g.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
     ext = torch.cuda.ExternalStream(g.stream, device=local)
     thr = float(TARGET_THR * SEARCH_MULT)
-    W = 1 if by_targets else max(1, a.workers)
+    if a.workers > 0:
+        W = a.workers
+    elif a.steps < 4:
+        W = max(1, a.steps)
+    else:                                                             # rounds x W >= steps: the fewest idle slots, then the fewest contexts
+        W = min((4, 5, 6), key=lambda w: (-(-a.steps // w) * w - a.steps, w))
+    if by_targets:
+        W = 1
     g.stage_pairs(f_all[:a.pairs], r_all[:a.pairs])
     g.select_words_staged(TARGET, thr, want_keys=False)   # builds the text index the workers share
     ctxs = [g] + [g.worker() for _ in range(W - 1)]
