@@ -174,6 +174,7 @@ struct IdxQuery {
 // are queried one bucket each (e = 2, k = 9: 37 + 27 * 10 = 307 buckets instead of 28 * 64).  The window is the segment
 // plus the next x pattern bases (window offset wo = o), or, for a segment that ends with the pattern, the x bases before
 // it (wo = o - x; the bucket of text position X then belongs to the alignment whose primer base 0 is at X - wo).  The
+// Allowed codes that are consecutive (the extension sits in the low digits when it follows the segment) are queried as one range.  The
 // pigeonhole argument and the leftmost-segment rule are untouched: a true hit is still found through every segment
 // whose k-prefix is within one mismatch, exactly once per segment (the text 12-mer at the window is one code).
 constexpr uint32_t IDX_EXT_MAX = 64u;  // most single-bucket queries one neighbour may expand into
@@ -243,6 +244,16 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 							ext = true;
 							if (ext_left) wo = o - x;
 							n_emit = idx_ext_count(x, budget);
+							if (!ext_left) { // extension in the low digits of the code: runs of consecutive allowed codes are ONE range
+								n_emit = 0u;
+								bool prev = false;
+								for (uint32_t c = 0; c < (1u << (2u * x)); ++c) {
+									const uint32_t d = c ^ ext_pat;
+									const bool okc = (uint32_t)__popc((d | (d >> 1)) & 0x55u) <= budget;
+									n_emit += (okc && !prev) ? 1u : 0u;
+									prev = okc;
+								}
+							}
 						}
 					}
 				}
@@ -276,16 +287,33 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 			qy.hi = __ldg(off + ((seg_code + 1u) << sh));
 			span += qy.hi - qy.lo;
 			if (at < q_cap) queries[at] = qy;
-		} else {
+		} else if (ext_left) {
 			for (uint32_t c = 0; c < (1u << (2u * x)); ++c) {
 				const uint32_t d = c ^ ext_pat, bad = (d | (d >> 1)) & 0x55u;
 				if ((uint32_t)__popc(bad) > budget) continue;
-				const uint32_t code = ext_left ? ((c << (2u * k)) | seg_code) : ((seg_code << (2u * x)) | c);
+				const uint32_t code = (c << (2u * k)) | seg_code;
 				qy.lo = __ldg(off + code);
 				qy.hi = __ldg(off + code + 1u);
 				span += qy.hi - qy.lo;
 				if (at < q_cap) queries[at] = qy;
 				++at;
+			}
+		} else {
+			const uint32_t n_codes = 1u << (2u * x), code0 = seg_code << (2u * x);
+			uint32_t run_start = 0;
+			bool prev = false;
+			for (uint32_t c = 0; c <= n_codes; ++c) { // one step past the end closes the last run
+				const uint32_t d = c ^ ext_pat;
+				const bool okc = c < n_codes && (uint32_t)__popc((d | (d >> 1)) & 0x55u) <= budget;
+				if (okc && !prev) run_start = c;
+				if (!okc && prev) {
+					qy.lo = __ldg(off + code0 + run_start);
+					qy.hi = __ldg(off + code0 + c);
+					span += qy.hi - qy.lo;
+					if (at < q_cap) queries[at] = qy;
+					++at;
+				}
+				prev = okc;
 			}
 		}
 	}
