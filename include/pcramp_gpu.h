@@ -147,6 +147,15 @@ int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r, uint32_t 
  *      The collection `kind` is replaced, exactly as if pcramp_gpu_upload_sequences had been called with the result. ------- */
 int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, const char *const *text, const uint64_t *bytes,
 	uint64_t min_length, uint64_t max_length, uint32_t n_ignore, const char *const *ignore, uint32_t *n_records);
+/* The same for GROUPS of files -- append_fasta_group (parse_fasta.cpp:91-169) driven as main.cpp:296-341 / :386-431 drive it: the
+ * files with the same file_group[f] (consecutive) form ONE sequence, the kept records in order with num_pad EOS between them
+ * (target_group_padding = 1, main.cpp:212); the length window (the caller passes max(amplicon_min, length_min) as main.cpp:328 does)
+ * and the ignore list apply per record; a group that keeps nothing gives no sequence.  Weights are 1 (a "[w=...]" in a group's name
+ * is the caller's: pcramp_gpu_set_weights); pcramp_gpu_fasta_records reports, per sequence, the file and defline of its first
+ * kept record, from which the caller recovers the group. */
+int pcramp_gpu_upload_fasta_groups(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, const char *const *text, const uint64_t *bytes,
+	const uint32_t *file_group, uint64_t min_length, uint64_t max_length, uint32_t num_pad, uint32_t n_ignore, const char *const *ignore,
+	uint32_t *n_sequences);
 /* per sequence of that upload: source file, defline as (offset, length) into the file's text, length, weight (any may be NULL) */
 int pcramp_gpu_fasta_records(pcramp_gpu_ctx *ctx, int kind, uint32_t *file, uint64_t *defline_off, uint32_t *defline_len,
 	uint32_t *length, float *weight);

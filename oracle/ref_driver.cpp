@@ -914,4 +914,34 @@ int ref_random_assay_stream(void *h, uint32_t n_trials, uint32_t *seed, int prim
 	});
 }
 
+// append_fasta_group (parse_fasta.cpp:91-169) driven as main.cpp:296-341 drives it: one (initially empty) Sequence per group, every
+// file of the group appended to it, the Sequence dropped again when nothing was kept.  Replaces the context's sequences; returns
+// their number or -1.
+long ref_append_fasta_groups(void *h, int n_files, const char *const *paths, const uint32_t *file_group, uint64_t min_len, uint64_t max_len,
+	uint64_t num_pad, int n_ignore, const char *ignore)
+{
+	RefCtx *c = (RefCtx *)h;
+	long n = -1;
+	guarded(c, [&]() {
+		deque<string> ig;
+		const char *p = ignore;
+		for (int i = 0; i < n_ignore; ++i) {
+			ig.push_back(string(p));
+			p += ig.back().size() + 1;
+		}
+		c->seq.clear();
+		int f = 0;
+		while (f < n_files) {
+			c->seq.push_back(Sequence());
+			Sequence &ref = c->seq.back();
+			ref.active(true);
+			const uint32_t g = file_group[f];
+			for (; f < n_files && file_group[f] == g; ++f) append_fasta_group(paths[f], ref, min_len, max_len, num_pad, ig);
+			if (ref.empty()) c->seq.pop_back();
+		}
+		n = (long)c->seq.size();
+	});
+	return n;
+}
+
 } // extern "C"

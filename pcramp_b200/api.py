@@ -125,6 +125,9 @@ SIGNATURES = {
     "pcramp_gpu_accept_assay": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u64p, _u64p]),
     "pcramp_gpu_random_assays": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, _u32p, _u32p, ctypes.POINTER(RandomAssayOptions),
                                                 _u64p, _u64p, _u32p]),
+    "pcramp_gpu_upload_fasta_groups": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _u64p, _u32p,
+                                                      ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p),
+                                                      _u32p]),
     "pcramp_gpu_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_uint32, ctypes.c_uint64, _u64p, _i32p, _u32p, _u64p]),
     "pcramp_gpu_select_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
@@ -450,6 +453,24 @@ class PcrampGpu:
         n = np.zeros(1, np.uint32)
         self._ck(self.lib.pcramp_gpu_upload_fasta(self.h, kind, len(blobs), arr, _ptr(nb, _u64p), int(min_length), int(max_length), len(ig), iga,
                                                   _ptr(n, _u32p)))
+        n = int(n[0])
+        self.n_seq[kind] = n
+        f, off, dl, ln, w = np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        self._ck(self.lib.pcramp_gpu_fasta_records(self.h, kind, _ptr(f, _u32p), _ptr(off, _u64p), _ptr(dl, _u32p), _ptr(ln, _u32p), _ptr(w, _f32p)))
+        return [(int(f[i]), blobs[int(f[i])][int(off[i]):int(off[i]) + int(dl[i])], int(ln[i]), float(w[i])) for i in range(n)]
+
+    def upload_fasta_groups(self, kind, texts, file_group, min_length=0, max_length=1 << 40, num_pad=1, ignore=()):
+        """append_fasta_group: the files of a group form one sequence -> [(first file, first kept defline, length, weight)] per sequence"""
+        blobs = [bytes(t) for t in texts]
+        arr = (ctypes.c_char_p * max(1, len(blobs)))(*blobs)
+        nb = np.array([len(b) for b in blobs], np.uint64)
+        fg = np.ascontiguousarray(file_group, dtype=np.uint32)
+        assert len(fg) == len(blobs)
+        ig = [x.encode() for x in ignore]
+        iga = (ctypes.c_char_p * max(1, len(ig)))(*ig)
+        n = np.zeros(1, np.uint32)
+        self._ck(self.lib.pcramp_gpu_upload_fasta_groups(self.h, kind, len(blobs), arr, _ptr(nb, _u64p), _ptr(fg, _u32p), int(min_length),
+                                                         int(max_length), int(num_pad), len(ig), iga, _ptr(n, _u32p)))
         n = int(n[0])
         self.n_seq[kind] = n
         f, off, dl, ln, w = np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.float32)

@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(256) fasta_count_kernel(const uint8_t *__restr
 
 struct PackOut {
 	uint8_t *raw;                 // the collection's nibble array (zeroed)
-	const uint64_t *rec_raw_off;  // per record: byte offset of its first nibble, ~0 = record not kept
+	const uint64_t *rec_raw_off;  // per record: byte offset of its sequence's first nibble, ~0 = record not kept
+	const uint32_t *rec_nib_base; // per record: residue index of its first base inside that sequence (0 unless records are grouped)
 	unsigned long long *bad;      // smallest text offset of an illegal symbol (~0 = none)
 	unsigned int *flags;          // bit 0: some base is degenerate
 	uint2 *eos;                   // (record, residue index) of every '-'
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(256) fasta_pack_kernel(const uint8_t *__restri
 		for (int k = 0; k < 4; ++k) c += (uint32_t)__popc(~space_mask4(wd[k]) & inside_mask4(at + 4u * k, w.begin, w.end)) >> 3;
 	}
 	uint32_t total;
-	const uint64_t r0 = (uint64_t)item_off[it] + warp_excl_sum(c, lane, total); // residue index of this lane's first base
+	const uint64_t r0 = (uint64_t)o.rec_nib_base[w.rec] + item_off[it] + warp_excl_sum(c, lane, total); // residue index of this lane's first base
 	uint32_t *out32 = (uint32_t *)(o.raw + roff); // records start 16-byte aligned
 	uint64_t r = r0;
 	uint32_t acc = 0, have = 0, flags = 0;
@@ -357,11 +358,16 @@ struct pcramp_gpu_fasta : pcr::fasta::Table {};
 
 extern "C" {
 
-int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, const char *const *text, const uint64_t *bytes, uint64_t min_length,
-	uint64_t max_length, uint32_t n_ignore, const char *const *ignore, uint32_t *n_records)
+// file_group == NULL: parse_fasta, one sequence per kept record.  Otherwise append_fasta_group (parse_fasta.cpp:91-169) driven as
+// main.cpp:296-341 does: the files of a group (file_group[f], non-decreasing) form ONE sequence -- the kept records in order, num_pad
+// EOS between them (Sequence::pad, sequence.h:258-270) -- and a group that keeps nothing gives no sequence.
+static int upload_fasta_impl(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, const char *const *text, const uint64_t *bytes, uint64_t min_length,
+	uint64_t max_length, uint32_t n_ignore, const char *const *ignore, uint32_t *n_records, const uint32_t *file_group, uint32_t num_pad)
 {
 	using namespace pcr::fasta;
 	if (check_kind(ctx, kind) || text_change(ctx, "pcramp_gpu_upload_fasta")) return 1;
+	for (uint32_t f = 1; file_group && f < n_files; ++f)
+		if (file_group[f] < file_group[f - 1]) return fail(ctx, "pcramp_gpu_upload_fasta_groups: the files of a group must be consecutive");
 	if (n_files && (!text || !bytes)) return fail(ctx, "pcramp_gpu_upload_fasta: null argument");
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
@@ -402,7 +408,7 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 	const double t1 = now();
 	// ---- text to HBM -----------------------------------------------------------------------------------------
 	const uint64_t text_bytes = (base[n_files] + BLOCK_BYTES) & ~(uint64_t)(BLOCK_BYTES - 1u);
-	DevBuf d_text, d_items, d_count, d_excl, d_first, d_len, d_item_off, d_rec_off, d_eos, d_misc, d_tmp;
+	DevBuf d_text, d_items, d_count, d_excl, d_first, d_len, d_item_off, d_rec_off, d_nib_base, d_eos, d_misc, d_tmp;
 	CK(d_text.ensure(text_bytes));
 	for (uint32_t f = 0; f < n_files; ++f)
 		if (bytes[f]) CK(cudaMemcpyAsync((char *)d_text.p + base[f], text[f], bytes[f], cudaMemcpyHostToDevice, st));
@@ -441,23 +447,64 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 	if (n_items) tab.ms_count = ev_ms(ctx->ev[0], ctx->ev[1]);
 	tab.text_bytes = base[n_files];
 	std::vector<uint64_t> rec_off(n_rec, ~0ull);
-	std::vector<uint32_t> rec_seq(n_rec, 0xFFFFFFFFu);
+	std::vector<uint32_t> rec_seq(n_rec, 0xFFFFFFFFu), rec_nib_base(n_rec, 0u);
+	std::vector<std::pair<uint32_t, uint32_t>> pads; // (sequence, position) of the EOS between the records of a group
 	std::vector<uint64_t> raw_off;
 	uint64_t off = 0;
-	for (uint32_t r = 0; r < n_rec; ++r) {
-		const uint64_t L = rec_len[r];
-		if (L < min_length || L > max_length || recs[r].ignored) continue;
-		if (L >= (1ull << 32)) return fail(ctx, "pcramp_gpu_upload_fasta: a record of 2^32 bases or more");
-		if (recs[r].weight < 0.0f) return fail(ctx, ":Sequence::defline: Negative weights are not allowed!"); // sequence.h:197-199
-		rec_seq[r] = (uint32_t)tab.length.size();
-		rec_off[r] = off;
-		raw_off.push_back(off);
-		off += (((L + 1) / 2) + 15u) & ~15ull;
-		tab.file.push_back(recs[r].file);
-		tab.def_off.push_back(recs[r].def_off);
-		tab.def_len.push_back(recs[r].def_len);
-		tab.length.push_back((uint32_t)L);
-		tab.weight.push_back(recs[r].weight);
+	if (!file_group) {
+		for (uint32_t r = 0; r < n_rec; ++r) {
+			const uint64_t L = rec_len[r];
+			if (L < min_length || L > max_length || recs[r].ignored) continue;
+			if (L >= (1ull << 32)) return fail(ctx, "pcramp_gpu_upload_fasta: a record of 2^32 bases or more");
+			if (recs[r].weight < 0.0f) return fail(ctx, ":Sequence::defline: Negative weights are not allowed!"); // sequence.h:197-199
+			rec_seq[r] = (uint32_t)tab.length.size();
+			rec_off[r] = off;
+			raw_off.push_back(off);
+			off += (((L + 1) / 2) + 15u) & ~15ull;
+			tab.file.push_back(recs[r].file);
+			tab.def_off.push_back(recs[r].def_off);
+			tab.def_len.push_back(recs[r].def_len);
+			tab.length.push_back((uint32_t)L);
+			tab.weight.push_back(recs[r].weight);
+		}
+	} else {
+		std::vector<uint64_t> seq_len;
+		uint32_t cur_group = 0;
+		bool open = false;
+		for (uint32_t r = 0; r < n_rec; ++r) {
+			const uint64_t L = rec_len[r];
+			if (L < min_length || L > max_length || recs[r].ignored) continue; // parse_fasta.cpp:116-118,155-156
+			const uint32_t g = file_group[recs[r].file];
+			if (!open || g != cur_group) { // the next group's (so far empty) Sequence, main.cpp:300
+				open = false;
+				cur_group = g;
+			}
+			if (!open && L == 0) continue; // m_seq is empty: no pad, and nothing is appended
+			if (!open) {
+				open = true;
+				seq_len.push_back(0);
+				tab.file.push_back(recs[r].file);
+				tab.def_off.push_back(recs[r].def_off);
+				tab.def_len.push_back(recs[r].def_len);
+				tab.weight.push_back(1.0f); // DEFAULT_SCORE_WEIGHT; a weight in the group's name is the caller's (pcramp_gpu_set_weights)
+			}
+			const uint32_t q = (uint32_t)seq_len.size() - 1u;
+			if (seq_len[q] > 0) { // :120-125: m_num_pad EOS between records
+				for (uint32_t k = 0; k < num_pad; ++k) pads.push_back(std::make_pair(q, (uint32_t)(seq_len[q] + k)));
+				seq_len[q] += num_pad;
+			}
+			rec_seq[r] = q;
+			rec_nib_base[r] = (uint32_t)seq_len[q];
+			seq_len[q] += L;
+			if (seq_len[q] >= (1ull << 32)) return fail(ctx, "pcramp_gpu_upload_fasta_groups: a group of 2^32 bases or more");
+		}
+		for (uint64_t L : seq_len) {
+			raw_off.push_back(off);
+			off += (((L + 1) / 2) + 15u) & ~15ull;
+			tab.length.push_back((uint32_t)L);
+		}
+		for (uint32_t r = 0; r < n_rec; ++r)
+			if (rec_seq[r] != 0xFFFFFFFFu) rec_off[r] = raw_off[rec_seq[r]];
 	}
 	const uint32_t n = (uint32_t)tab.length.size();
 	if (n >= (1u << 24)) return fail(ctx, "pcramp_gpu_upload_fasta: at most 2^24 - 1 sequences per collection");
@@ -485,10 +532,13 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 		unsigned long long init[2] = {~0ull, 0ull}; // bad offset | flags (lo), n_eos (hi)
 		CK(cudaMemcpyAsync(d_misc.p, init, 16, cudaMemcpyHostToDevice, st));
 		CK(cudaMemcpyAsync(d_rec_off.p, rec_off.data(), (size_t)n_rec * 8, cudaMemcpyHostToDevice, st));
+		CK(d_nib_base.ensure(std::max<size_t>(1, n_rec) * 4));
+		CK(cudaMemcpyAsync(d_nib_base.p, rec_nib_base.data(), (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
 		if (attempt) CK(cudaMemsetAsync(s.d_raw.p, 0, std::max<uint64_t>(16, s.raw_bytes), st));
 		PackOut po;
 		po.raw = s.d_raw.as<uint8_t>();
 		po.rec_raw_off = d_rec_off.as<uint64_t>();
+		po.rec_nib_base = d_nib_base.as<uint32_t>();
 		po.bad = (unsigned long long *)d_misc.p;
 		po.flags = (unsigned int *)d_misc.p + 2;
 		po.n_eos = (unsigned int *)d_misc.p + 3;
@@ -526,6 +576,7 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 		break;
 	}
 	for (const uint2 &e : eos_list) s.eos[rec_seq[e.x]].push_back(e.y);
+	for (const std::pair<uint32_t, uint32_t> &pd : pads) s.eos[pd.first].push_back(pd.second);
 	std::vector<uint32_t> with_eos;
 	s.plen.assign(n, 0);
 	s.clen.assign(n, 0);
@@ -546,6 +597,21 @@ int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, con
 	const int rc = upload_finish(ctx, s, nullptr, with_eos);
 	if (dbg) fprintf(stderr, "upload_fasta: split %.1f ms, H2D + count %.1f ms, pack %.1f ms, finish %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
 	return rc;
+}
+
+int pcramp_gpu_upload_fasta(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, const char *const *text, const uint64_t *bytes, uint64_t min_length,
+	uint64_t max_length, uint32_t n_ignore, const char *const *ignore, uint32_t *n_records)
+{
+	return upload_fasta_impl(ctx, kind, n_files, text, bytes, min_length, max_length, n_ignore, ignore, n_records, nullptr, 0);
+}
+
+int pcramp_gpu_upload_fasta_groups(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, const char *const *text, const uint64_t *bytes,
+	const uint32_t *file_group, uint64_t min_length, uint64_t max_length, uint32_t num_pad, uint32_t n_ignore, const char *const *ignore,
+	uint32_t *n_sequences)
+{
+	if (n_files && !file_group) return ctx ? fail(ctx, "pcramp_gpu_upload_fasta_groups: null argument") : 1;
+	static const uint32_t none = 0;
+	return upload_fasta_impl(ctx, kind, n_files, text, bytes, min_length, max_length, n_ignore, ignore, n_sequences, n_files ? file_group : &none, num_pad);
 }
 
 /* host-only: the record split of one file's text as pcramp_gpu_upload_fasta sees it (before the length window and the ignore

@@ -60,3 +60,38 @@ def cases():
     t = "".join(">o%d\n%s\n" % (i, _seq(rng, n)) for i, n in enumerate([1, 2, 3, 31, 32, 33, 63, 65, 4097, 8191]))
     out.append(FastaCase("odd", [t]))
     return out
+
+
+class GroupCase:
+    """append_fasta_group (parse_fasta.cpp:91-169): files, the group of each file, the record window, the pad between records"""
+    def __init__(self, name, files, file_group, min_len=0, max_len=1 << 40, num_pad=1, ignore=()):
+        self.name, self.files, self.file_group = name, [f.encode() for f in files], list(file_group)
+        self.min_len, self.max_len, self.num_pad, self.ignore = min_len, max_len, num_pad, list(ignore)
+
+
+def group_cases():
+    rng = np.random.default_rng(177)
+    out = []
+
+    def fa(names_lens, alphabet="ACGT", width=70):
+        return "".join(">%s\n%s" % (nm, _wrap(_seq(rng, n, alphabet), width) if n else "") for nm, n in names_lens)
+
+    # three groups: contigs of a draft genome in one file, a genome split over two files, a single-record group; odd and even
+    # record lengths (a pad lands on either nibble of a byte), records across file boundaries
+    f0 = fa([("c1", 301), ("c2", 120), ("c3", 77)])
+    f1 = fa([("a1", 250)])
+    f2 = fa([("a2", 33), ("a3", 500)])
+    f3 = fa([("solo", 999)])
+    out.append(GroupCase("three_groups", [f0, f1, f2, f3], [0, 1, 1, 2]))
+    # length window, ignore list, a group that keeps nothing (dropped), IUPAC / lower case / '-' inside records, two pads, CR LF
+    g0 = fa([("k1 plasmid", 400), ("k2", 30), ("k3", 200)], "ACGTacgtNRY-")
+    g1 = fa([("short1", 10), ("short2", 20)])
+    g2 = fa([("m1", 150), ("m2 PLASMID x", 300), ("m3", 151)], width=61).replace("\n", "\r\n")
+    g3 = fa([("z", 90)])
+    out.append(GroupCase("window_ignore_pad2", [g0, g1, g2, g3], [0, 1, 2, 2], min_len=50, max_len=380, num_pad=2, ignore=["plasmid"]))
+    # gzgets chunking inside a group: a 5000-base line, a '>' in the middle of a sequence line, no final newline, a file that does
+    # not start with a defline, an empty last record
+    t = _seq(rng, 64) + "\n>p\n" + _seq(rng, 5000) + "\n>q\n" + _seq(rng, 40) + ">" + _seq(rng, 20) + "\n" + _seq(rng, 95)
+    u = ">r\n" + _wrap(_seq(rng, 333), 50) + ">empty\n"
+    out.append(GroupCase("chunks", [t, u], [0, 0]))
+    return out

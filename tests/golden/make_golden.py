@@ -219,6 +219,17 @@ def fasta_kats(ref):
         rec["%s_nibbles" % case.name] = np.concatenate([s[2] for s in seqs]) if seqs else np.zeros(0, np.uint8)
         print("fasta %-16s records %3d  bases %7d  weights %s" % (case.name, len(seqs), int(sum(s[0] for s in seqs)),
                                                                  sorted(set(s[1] for s in seqs))))
+    for case in fasta_cases.group_cases():                       # append_fasta_group (parse_fasta.cpp:91-169)
+        with tempfile.TemporaryDirectory() as d:
+            paths = []
+            for k, blob in enumerate(case.files):
+                paths.append(os.path.join(d, "g%d.fa" % k))
+                open(paths[-1], "wb").write(blob)
+            seqs = ref.append_fasta_groups(paths, case.file_group, case.min_len, case.max_len, case.num_pad, case.ignore)
+        rec["group_%s_len" % case.name] = np.array([s[0] for s in seqs], np.uint32)
+        rec["group_%s_nibbles" % case.name] = np.concatenate([s[2] for s in seqs]) if seqs else np.zeros(0, np.uint8)
+        print("fasta groups %-20s sequences %2d  lengths %s  EOS %d" % (case.name, len(seqs), [s[0] for s in seqs],
+                                                                        int(sum((s[2] == 0).sum() for s in seqs))))
     return rec
 
 

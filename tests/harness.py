@@ -457,6 +457,17 @@ class RefLib(_Base):
             out.append((int(ln), float(w[0]), nib[:ln].copy()))
         return out
 
+    def append_fasta_groups(self, paths, file_group, min_len=0, max_len=1 << 40, num_pad=1, ignore=()):
+        """append_fasta_group per group as main.cpp:296-341 -> [(length, weight, nibbles)] of the groups that kept something"""
+        fn = self._fn("append_fasta_groups", ctypes.c_long, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), _u32p, ctypes.c_uint64,
+                                                             ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p])
+        arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
+        fg = np.ascontiguousarray(file_group, dtype=np.uint32)
+        ig = b"".join(x.encode() + b"\0" for x in ignore)
+        n = fn(self.h, len(paths), arr, _p(fg, _u32p), int(min_len), int(max_len), int(num_pad), len(ignore), ig)
+        assert n >= 0, self.f_err(self.h)
+        return self.sequences()
+
     def pack_all(self, pack_max_degen=256, min_oligo_length=18):
         """the multiplex background database of main.cpp:989-1003 (every sequence packed whole) -> its keys"""
         n = self.f_pack_all(self.h, pack_max_degen, min_oligo_length)

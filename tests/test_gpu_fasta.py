@@ -100,3 +100,60 @@ def test_large_random_fasta_vs_live_reference(gpu):
     assert [w[0] for w in want] == list(ln)
     assert [np.float32(w[1]) for w in want] == [np.float32(x[3]) for x in recs]
     assert all(np.array_equal(a[2], b) for a, b in zip(want, nibs))
+
+
+@pytest.mark.parametrize("case", fasta_cases.group_cases(), ids=lambda c: c.name)
+def test_upload_fasta_groups_matches_reference_golden(gpu, case):
+    """append_fasta_group (parse_fasta.cpp:91-169): the files of a group as ONE sequence, pads between the kept records"""
+    g = np.load(GOLD)
+    recs = gpu.upload_fasta_groups(TARGET, case.files, case.file_group, case.min_len, case.max_len, case.num_pad, case.ignore)
+    ln, nibs = device_nibbles(gpu, TARGET)
+    assert list(ln) == list(g["group_%s_len" % case.name]) == [r[2] for r in recs]
+    got = np.concatenate(nibs) if nibs else np.zeros(0, np.uint8)
+    assert np.array_equal(got, g["group_%s_nibbles" % case.name])
+    # the grouped collection scans like the same sequences uploaded directly (pads and '-' are EOS the device text knows about)
+    off, _, raw = gpu.sequences_copy(TARGET)
+    rng = np.random.default_rng(3)
+    words = []
+    for _ in range(16):                                         # 20-mers cut from the grouped sequences
+        i = int(rng.integers(0, len(nibs)))
+        a = int(rng.integers(0, max(1, len(nibs[i]) - 20)))
+        w = nibs[i][a:a + 20]
+        if len(w) == 20 and (w != 0).all():
+            words.append(synth.word_from_codes(w))
+    if len(words) >= 2:
+        f = np.array(words[:len(words) // 2], dtype=np.uint64)
+        r = np.array(words[len(words) // 2:2 * (len(words) // 2)], dtype=np.uint64)
+        ne_a = gpu.select_words(TARGET, f, r, 0.9)
+        db_a = gpu.db_copy(TARGET)
+        gpu.upload_sequences(BACKGROUND, raw, off, ln)
+        ne_b = gpu.select_words(BACKGROUND, f, r, 0.9)
+        db_b = gpu.db_copy(BACKGROUND)
+        assert ne_a == ne_b and ne_a[0] > 0 and all(np.array_equal(x, y) for x, y in zip(db_a, db_b))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PATH), reason="compiled reference did not travel with the snapshot")
+def test_fasta_groups_vs_live_reference(gpu):
+    rng = np.random.default_rng(15)
+    files, groups = [], []
+    for gidx in range(12):
+        for _ in range(int(rng.integers(1, 4))):
+            parts = []
+            for i in range(int(rng.integers(1, 6))):
+                n = int(rng.integers(0, 3000))
+                body = "".join(rng.choice(list("ACGTacgtN-"), size=n, p=[.23, .23, .23, .23, .02, .02, .01, .01, .01, .01]))
+                w = int(rng.integers(30, 120))
+                parts.append(">g%d_%d%s\n%s" % (gidx, i, " phage" if rng.random() < 0.15 else "", "".join(body[k:k + w] + "\n" for k in range(0, n, w))))
+            files.append("".join(parts).encode())
+            groups.append(gidx)
+    for num_pad in (1, 3):
+        with tempfile.TemporaryDirectory() as d:
+            paths = []
+            for k, blob in enumerate(files):
+                paths.append(os.path.join(d, "x%d.fa" % k))
+                open(paths[-1], "wb").write(blob)
+            want = RefLib().append_fasta_groups(paths, groups, 80, 2500, num_pad, ["phage"])
+        gpu.upload_fasta_groups(TARGET, files, groups, 80, 2500, num_pad, ["phage"])
+        ln, nibs = device_nibbles(gpu, TARGET)
+        assert [w[0] for w in want] == list(ln) and len(ln) > 3
+        assert all(np.array_equal(a[2], b) for a, b in zip(want, nibs))
