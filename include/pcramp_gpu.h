@@ -224,6 +224,16 @@ int pcramp_gpu_pool_amplicon_coverage(pcramp_gpu_ctx *ctx, int kind, const uint6
 int pcramp_gpu_accept_assay(pcramp_gpu_ctx *ctx, uint32_t pair, uint32_t pack_max_degen, uint32_t min_oligo_length, uint64_t *n_added,
 	uint64_t *n_multiplex_keys);
 
+/* The best assay of a batch of scored trials: the update rule of main.cpp:829-858 (Score::operator< / ==, pcramp.h:180-201: accuracy =
+ * target - background coverage, then oligo_overlap; on an equal Score the smaller PCR::total_degeneracy(), assay.h:536-539; only
+ * trials with background coverage <= max_background_cover compete) folded over the trials in order = the first maximum, found by a
+ * device reduction.  best_index = -1 when nothing competes.  oligo_overlap may be NULL (no multiplex: 0).  Across ranks
+ * (reduce_best_assay, main.cpp:1421-1601) the same rule is applied to the gathered per-rank winners (pcramp_b200/sharding.py
+ * reduce_best in the Python mirror: all-gather of {accuracy, overlap, degeneracy, global trial index}, lowest index on ties). */
+int pcramp_gpu_best_assay(pcramp_gpu_ctx *ctx, uint32_t n, const float *target_coverage, const float *background_coverage,
+	const float *oligo_overlap, const uint64_t *f, const uint64_t *r, float max_background_cover, int64_t *best_index, float *best_accuracy,
+	float *best_overlap, double *best_degeneracy);
+
 /* ---- resident variants: the same two steps with the pairs already staged in HBM and the results
  *      left in HBM (what a multi-batch driver, the NCCL exchange and bench.py's `value` use). -------- */
 int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs);

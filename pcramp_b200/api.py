@@ -128,6 +128,8 @@ SIGNATURES = {
     "pcramp_gpu_upload_fasta_groups": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _u64p, _u32p,
                                                       ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p),
                                                       _u32p]),
+    "pcramp_gpu_best_assay": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, _f32p, _f32p, _f32p, _u64p, _u64p, ctypes.c_float,
+                                             ctypes.POINTER(ctypes.c_int64), _f32p, _f32p, ctypes.POINTER(ctypes.c_double)]),
     "pcramp_gpu_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_uint32, ctypes.c_uint64, _u64p, _i32p, _u32p, _u64p]),
     "pcramp_gpu_select_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
@@ -352,6 +354,17 @@ class PcrampGpu:
                                                   _ptr(out[1:2], _u64p)))
         self.n_seq[MULTIPLEX] = self.n_seq.get(MULTIPLEX, 0) + int(out[0])
         return int(out[0]), int(out[1])
+
+    def best_assay(self, target_cov, background_cov, overlap, f, r, max_background_cover=0.0):
+        """main.cpp:829-858 over the trials in order -> (index or -1, accuracy, overlap, total degeneracy)"""
+        t = np.ascontiguousarray(target_cov, dtype=np.float32)
+        b = np.ascontiguousarray(background_cov, dtype=np.float32)
+        o = None if overlap is None else np.ascontiguousarray(overlap, dtype=np.float32)
+        f, r = _words(f), _words(r)
+        idx, acc, ov, dg = ctypes.c_int64(-1), np.zeros(1, np.float32), np.zeros(1, np.float32), ctypes.c_double(0.0)
+        self._ck(self.lib.pcramp_gpu_best_assay(self.h, len(t), _ptr(t, _f32p), _ptr(b, _f32p), _ptr(o, _f32p), _ptr(f, _u64p), _ptr(r, _u64p),
+                                                float(max_background_cover), ctypes.byref(idx), _ptr(acc, _f32p), _ptr(ov, _f32p), ctypes.byref(dg)))
+        return int(idx.value), float(acc[0]), float(ov[0]), float(dg.value)
 
     def pack(self, kind, seq, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0, min_oligo_length=18):
         """Sequence::pack of one sequence -> (words, loc, strand), unordered."""

@@ -487,3 +487,105 @@ int pcramp_gpu_accept_assay(pcramp_gpu_ctx *ctx, uint32_t pair, uint32_t pack_ma
 }
 
 } // extern "C"
+
+// ---- the best assay of a batch ----------------------------------------------------------------------------
+// main.cpp:829-858 keeps, over the trials in order, the assay whose Score is larger (Score::operator<, pcramp.h:180-187:
+// accuracy = target - background coverage, then oligo_overlap) and, on an equal Score, the one with the smaller
+// PCR::total_degeneracy() (assay.h:536-539); only trials with background coverage <= max_background_cover compete.  A fold with
+// strict comparisons = the FIRST maximum of the total order (accuracy, overlap, -degeneracy), which a parallel reduction finds
+// exactly.  reduce_best_assay (main.cpp:1421-1601) applies the same two comparisons to the per-rank winners.
+namespace pcr {
+namespace amp {
+
+struct BestKey {
+	float accuracy, overlap;
+	double degeneracy;
+	uint32_t index; // 0xFFFFFFFF = nothing competes
+};
+
+__host__ __device__ inline bool best_beats(const BestKey &a, const BestKey &b)
+{ // would the fold replace b by a, a coming later?  (equal keys: the earlier index stays)
+	if (a.index == 0xFFFFFFFFu) return false;
+	if (b.index == 0xFFFFFFFFu) return true;
+	if (a.accuracy != b.accuracy) return a.accuracy > b.accuracy;
+	if (a.overlap != b.overlap) return a.overlap > b.overlap;
+	if (a.degeneracy != b.degeneracy) return a.degeneracy < b.degeneracy;
+	return a.index < b.index;
+}
+
+__global__ void __launch_bounds__(256) best_assay_kernel(uint32_t n, const float *__restrict__ target, const float *__restrict__ background,
+	const float *__restrict__ overlap, const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, float max_background, BestKey *out)
+{
+	__shared__ BestKey s_best[256];
+	BestKey best;
+	best.accuracy = best.overlap = 0.0f;
+	best.degeneracy = 0.0;
+	best.index = 0xFFFFFFFFu;
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		if (!(background[i] <= max_background)) continue; // main.cpp:829,846
+		W128 wf, wr;
+		wf.hi = f[2 * i]; wf.lo = f[2 * i + 1];
+		wr.hi = r[2 * i]; wr.lo = r[2 * i + 1];
+		double df = 1.0, dr = 1.0; // Word::degeneracy (word.h:97-138)
+		for (int k = 0; k < WORD_LEN; ++k) {
+			const int a = __popc(w_get(wf, k)), b = __popc(w_get(wr, k));
+			if (a) df *= (double)a;
+			if (b) dr *= (double)b;
+		}
+		BestKey c;
+		c.accuracy = __fsub_rn(target[i], background[i]); // Score::accuracy (pcramp.h:204-207)
+		c.overlap = overlap[i];
+		c.degeneracy = df + dr;
+		c.index = i;
+		if (best_beats(c, best)) best = c;
+	}
+	s_best[threadIdx.x] = best;
+	__syncthreads();
+	for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+		if (threadIdx.x < s && best_beats(s_best[threadIdx.x + s], s_best[threadIdx.x])) s_best[threadIdx.x] = s_best[threadIdx.x + s];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *out = s_best[0];
+}
+
+} // namespace amp
+} // namespace pcr
+
+extern "C" {
+
+int pcramp_gpu_best_assay(pcramp_gpu_ctx *ctx, uint32_t n, const float *target_coverage, const float *background_coverage, const float *oligo_overlap,
+	const uint64_t *f, const uint64_t *r, float max_background_cover, int64_t *best_index, float *best_accuracy, float *best_overlap,
+	double *best_degeneracy)
+{
+	using namespace pcr::amp;
+	if (!ctx) return 1;
+	if (n && (!target_coverage || !background_coverage || !f || !r)) return fail(ctx, "pcramp_gpu_best_assay: null argument");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	if (best_index) *best_index = -1;
+	if (!n) return 0;
+	DevBuf d_t, d_b, d_o, d_f, d_r, d_out;
+	CK(d_t.ensure((size_t)n * 4)); CK(d_b.ensure((size_t)n * 4)); CK(d_o.ensure((size_t)n * 4));
+	CK(d_f.ensure((size_t)n * 16)); CK(d_r.ensure((size_t)n * 16)); CK(d_out.ensure(sizeof(BestKey)));
+	CK(cudaMemcpyAsync(d_t.p, target_coverage, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_b.p, background_coverage, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+	if (oligo_overlap) CK(cudaMemcpyAsync(d_o.p, oligo_overlap, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+	else CK(cudaMemsetAsync(d_o.p, 0, (size_t)n * 4, st));
+	CK(cudaMemcpyAsync(d_f.p, f, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_r.p, r, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+	best_assay_kernel<<<1, 256, 0, st>>>(n, d_t.as<float>(), d_b.as<float>(), d_o.as<float>(), d_f.as<uint64_t>(), d_r.as<uint64_t>(), max_background_cover,
+		d_out.as<BestKey>());
+	CK(cudaGetLastError());
+	BestKey k;
+	CK(cudaMemcpyAsync(&k, d_out.p, sizeof(BestKey), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.kernel_launches = 1;
+	if (k.index == 0xFFFFFFFFu) return 0;
+	if (best_index) *best_index = (int64_t)k.index;
+	if (best_accuracy) *best_accuracy = k.accuracy;
+	if (best_overlap) *best_overlap = k.overlap;
+	if (best_degeneracy) *best_degeneracy = k.degeneracy;
+	return 0;
+}
+
+} // extern "C"

@@ -110,3 +110,50 @@ def test_two_rank_exchange_equals_unsharded(tmp_path, oracle):
     # pass-1 := any the merged sum visits detected sequences in ascending order, as the oracle does here
     want = np.array([np.float32(sum(float(coll.weight[i]) for i in np.nonzero(bits[p])[0])) for p in range(len(f))], np.float32)
     assert np.array_equal(got["cov"], want)
+
+
+# ---- the best assay over ranks (reduce_best_assay, main.cpp:1421-1601) ----------------------------------------------------------
+def fold_best(records):
+    """the reference's update rule (main.cpp:829-858) folded over (accuracy, overlap, degeneracy, index) records in order"""
+    from pcramp_b200.sharding import better
+    best = None
+    for rec in records:
+        if better(rec, best):
+            best = rec
+    return best
+
+
+def best_scenario():
+    rng = np.random.default_rng(11)
+    n = 64
+    acc = rng.integers(0, 4, size=n).astype(np.float32)          # many ties
+    ov = (rng.integers(0, 3, size=n) * 0.5).astype(np.float32)
+    deg = rng.integers(2, 5, size=n).astype(np.float64)
+    return [(acc[i], ov[i], deg[i], i) for i in range(n)]
+
+
+def best_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pcramp_b200.sharding import reduce_best
+    recs = best_scenario()
+    mine = recs[rank::world]                                     # the pair-sharded sweep: every rank scores its own trials
+    local = fold_best(mine) if rank != 1 or world == 1 else fold_best(mine)
+    best, owner = reduce_best(dist, local)
+    none_best, none_owner = reduce_best(dist, None if rank == 0 else local)   # a rank without a candidate
+    if rank == 0:
+        np.savez(out, best=np.array(best, np.float64), owner=owner, none_best=np.array(none_best, np.float64), none_owner=none_owner)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_best_assay_equals_single_fold(tmp_path):
+    out = str(tmp_path / "best.npz")
+    mp.spawn(best_worker, args=(2, free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    recs = best_scenario()
+    want = fold_best(recs)                                       # one process, trials in order
+    assert tuple(got["best"]) == tuple(float(x) for x in want)
+    assert int(got["owner"]) == want[3] % 2
+    want1 = fold_best(recs[1::2])
+    assert tuple(got["none_best"]) == tuple(float(x) for x in want1) and int(got["none_owner"]) == 1
