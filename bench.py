@@ -292,6 +292,43 @@ def parse_fasta_args():
     return [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p]
 
 
+def candidate_leg(a, g, factory):
+    """candidate generation on the device (random_assay.cuh): opt.num_trial = 1000 trial assays drawn by
+    PCR::random_assay, one seed stream per trial (the reference at --thread 1000), against 256 of the targets in the BACKGROUND slot;
+    kernel time from the library's CUDA events, e2e = the whole call (seeds in, oligos out).  CPU: the same 1000 streams through the
+    unmodified reference, one after the other on one host thread (each stream owns its NucCruc object, as an OpenMP thread would)."""
+    from pcramp_b200 import BACKGROUND
+    from tests.harness import RefLib, REF_PATH
+    n_t, n_streams = min(a.targets, 256), 1000
+    sample = factory.collection(range(n_t))
+    g.upload_sequences(BACKGROUND, sample.nibbles, sample.byte_off, sample.length)
+    rng = np.random.default_rng(17)
+    seeds = rng.integers(0, 2**32, size=n_streams, dtype=np.uint64).astype(np.uint32)
+    per = np.ones(n_streams, np.uint32)
+    g.random_assays(BACKGROUND, seeds, per)                       # warm-up (tables, buffers)
+    t0 = time.perf_counter()
+    f, r, _, attempts = g.random_assays(BACKGROUND, seeds, per)
+    dt = time.perf_counter() - t0
+    ms_kernel = g.thermo_stats()["ms_kernel"]
+    out = {"metric": "random_assay_trials_per_s", "value": n_streams / (ms_kernel * 1e-3), "unit": "trial assays/s (kernel, one GPU thread per seed stream)",
+           "streams": n_streams, "ms_kernel": ms_kernel, "candidates_tried_per_trial": float(attempts.mean()),
+           "e2e": {"value": n_streams / dt, "unit": "trial assays/s", "ms": dt * 1e3}, "gpu_launches": 1, "cpu_baseline": None}
+    if os.path.exists(REF_PATH) and not a.no_cpu_baseline:
+        from pcramp_b200.api import RandomAssayOptions
+        ref = RefLib()
+        ref.set_sequences(sample)
+        opt = RandomAssayOptions()
+        t0 = time.perf_counter()
+        same = True
+        for k in range(n_streams):
+            wf, wr, _ = ref.random_assay_stream(1, int(seeds[k]), opt)
+            same = same and np.array_equal(wf[0], f[k]) and np.array_equal(wr[0], r[k])
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_streams / dt, "unit": "trial assays/s", "cores": 1, "kind": "reference", "seconds": dt,
+                               "sample": "the same 1000 seed streams, one host thread", "identical_to_gpu": bool(same)}
+    return out
+
+
 def fasta_leg(a, g, coll, hbm_peak):
     """FASTA ingest on the device (fasta.cuh): the text of the first --fasta-targets sequences (line width 70) through
     pcramp_gpu_upload_fasta into the BACKGROUND slot of the context.  Kernel figures from the library's CUDA events; e2e = the whole
@@ -819,6 +856,7 @@ def run_b200(a):
                          "note": "value / e2e: %d batch(es) in flight per GPU (worker contexts sharing the resident targets and text index, one "
                                  "host thread each); roofline / breakdown: from a pass with one batch at a time" % W},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp, "target_sharded": tsh,
+            "candidate_generation": candidate_leg(a, g, factory) if a.fasta_targets > 0 else None,
             "fasta_ingest": fasta_leg(a, g, coll, hbm_peak) if a.fasta_targets > 0 else None}))
     # teardown order matters: torch tensors that were used on the library's stream must die before the stream does
     sys.stdout.flush()
