@@ -292,6 +292,46 @@ def parse_fasta_args():
     return [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p]
 
 
+def sw_leg(a, g, ext, torch):
+    """the Smith-Waterman half of the DP metric (SURVEY.md 8d: cells = q x t per slot): SO::SeqOverlap alignments of primer-like queries
+    (18-25 nt) against 32-base database words, what find_background_match runs four times per candidate amplicon.  Timed through
+    pcramp_gpu_sw_batch with host pointers (H2D of the words, kernel, D2H of score + coordinates inside the region); CPU: the
+    reference's SSE SeqOverlap, 8 problems per align(), one host thread."""
+    from pcramp_b200 import synth
+    from tests.harness import RefLib, REF_PATH
+    rng = np.random.default_rng(29)
+    sym = synth.CODE
+    qs = np.array([synth.word_from_codes(sym[rng.integers(0, 4, size=int(rng.integers(18, 26)))]) for _ in range(4096)], dtype=np.uint64)
+    ts = np.array([synth.word_from_codes(sym[rng.integers(0, 4, size=32)]) for _ in range(4096)], dtype=np.uint64)
+    n = 1 << 18
+    qi, ti = rng.integers(0, 4096, size=n), rng.integers(0, 4096, size=n)
+    q, t = np.ascontiguousarray(qs[qi]), np.ascontiguousarray(ts[ti])
+    qlen = np.array([bin(int(w[0])).count("1") + bin(int(w[1])).count("1") for w in qs])[qi]   # single letters: one bit per base
+    cells = float((qlen * 32).sum())
+    g.sw_batch(q, t)                                              # warm-up at full size
+    torch.cuda.synchronize()
+    ms = 1e30
+    for _ in range(3):                                            # wall clock around the whole call: copies, kernel, read-back
+        t0 = time.perf_counter()
+        out = g.sw_batch(q, t)
+        ms = min(ms, (time.perf_counter() - t0) * 1e3)
+    ms_kernel = g.sw_timing()
+    res = {"metric": "sw_gcups", "value": cells / (ms_kernel * 1e-3) / 1e9, "unit": "GCUPS (sw_words_kernel, cells = q x t, with start coordinates)",
+           "problems": n, "ms_kernel": ms_kernel,
+           "e2e": {"value": cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms": ms, "h2d_bytes": 32 * n, "d2h_bytes": 24 * n,
+                   "note": "wall clock of pcramp_gpu_sw_batch with pageable host arrays: copies, kernel, read-back, host unpacking"},
+           "gpu_launches": 1, "cpu_baseline": None}
+    if os.path.exists(REF_PATH) and not a.no_cpu_baseline:
+        ref = RefLib()
+        m = 1 << 16
+        t0 = time.perf_counter()
+        want = ref.sw_batch(q[:m], t[:m])
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": float((qlen[:m] * 32).sum()) / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "reference", "seconds": dt,
+                               "sample": "the first %d problems, SSE int16 x 8 slots" % m, "scores_identical_to_gpu": bool(np.array_equal(want[:, 0], out[:m, 0]))}
+    return res
+
+
 def candidate_leg(a, g, factory):
     """candidate generation on the device (random_assay.cuh): opt.num_trial = 1000 trial assays drawn by
     PCR::random_assay, one seed stream per trial (the reference at --thread 1000), against 256 of the targets in the BACKGROUND slot;
@@ -856,6 +896,7 @@ def run_b200(a):
                          "note": "value / e2e: %d batch(es) in flight per GPU (worker contexts sharing the resident targets and text index, one "
                                  "host thread each); roofline / breakdown: from a pass with one batch at a time" % W},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp, "target_sharded": tsh,
+            "sw_gcups": sw_leg(a, g, ext, torch) if (a.dp_problems > 0 and rank == 0) else None,
             "candidate_generation": candidate_leg(a, g, factory) if a.fasta_targets > 0 else None,
             "fasta_ingest": fasta_leg(a, g, coll, hbm_peak) if a.fasta_targets > 0 else None}))
     # teardown order matters: torch tensors that were used on the library's stream must die before the stream does

@@ -351,6 +351,8 @@ int pcramp_gpu_get_thermo_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_thermo_stats *ou
  * 15 = N).  Any output may be NULL. */
 int pcramp_gpu_sw_batch(pcramp_gpu_ctx *ctx, uint32_t n, const uint64_t *query, const uint64_t *target, int32_t *score,
 	int32_t *q_start, int32_t *q_stop, int32_t *t_start, int32_t *t_stop, uint8_t *last_two);
+/* CUDA-event time (ms) of the alignment kernel of the last pcramp_gpu_sw_batch (instrumentation, bench.py's sw_gcups leg). */
+int pcramp_gpu_sw_timing(pcramp_gpu_ctx *ctx, float *ms_kernel);
 /* PCR::find_background_match (background_match.cpp:7-166) for n_pairs assays against the database built by
  * pcramp_gpu_select_words on `kind` (normally PCRAMP_BACKGROUND): collect_background_candidates with
  * search_threshold = opt.background_threshold * opt.background_search_multiplier and the background amplicon range

@@ -130,6 +130,7 @@ SIGNATURES = {
                                                       _u32p]),
     "pcramp_gpu_best_assay": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, _f32p, _f32p, _f32p, _u64p, _u64p, ctypes.c_float,
                                              ctypes.POINTER(ctypes.c_int64), _f32p, _f32p, ctypes.POINTER(ctypes.c_double)]),
+    "pcramp_gpu_sw_timing": (ctypes.c_int, [ctypes.c_void_p, _f32p]),
     "pcramp_gpu_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_uint32, ctypes.c_uint64, _u64p, _i32p, _u32p, _u64p]),
     "pcramp_gpu_select_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
@@ -681,6 +682,11 @@ class PcrampGpu:
         l2 = np.zeros((n, 2), np.uint8)
         self._ck(self.lib.pcramp_gpu_sw_batch(self.h, n, _ptr(q, _u64p), _ptr(t, _u64p), *[_ptr(c, _i32p) for c in cols], _ptr(l2, _u8p)))
         return np.stack(cols + [(l2[:, 0].astype(np.int32) << 4) | l2[:, 1]], 1)
+
+    def sw_timing(self):
+        ms = np.zeros(1, np.float32)
+        self._ck(self.lib.pcramp_gpu_sw_timing(self.h, _ptr(ms, _f32p)))
+        return float(ms[0])
 
     def background_match(self, kind, f, r, search_threshold, detect_threshold, amplicon_min=0, amplicon_max=2000, use_taq_mama=False):
         """-> (bitsets (n_pairs, words) uint32, number of candidate amplicons)"""

@@ -163,6 +163,8 @@ struct pcramp_gpu_ctx {
 	int amp_kind = -1;
 	bool amp_bounds_ok = false;
 	std::vector<uint64_t> amp_words; // F0 R0 F1 R1 ... of that call
+	DevBuf sw_q, sw_t, sw_out;       // pcramp_gpu_sw_batch staging (kept between calls)
+	float sw_ms_kernel = 0.0f;
 };
 
 namespace pcr {

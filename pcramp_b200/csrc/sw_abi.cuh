@@ -387,17 +387,20 @@ int pcramp_gpu_sw_batch(pcramp_gpu_ctx *ctx, uint32_t n, const uint64_t *query, 
 	for (uint32_t p = 0; p < n; ++p) { // pack_query_slots throws on an empty query (seq_overlap.h:832-834)
 		if ((query[2 * p] | query[2 * p + 1]) == 0) return fail(ctx, ":SeqOverlap::pack_query_slots: len == 0");
 	}
-	DevBuf dq, dt, dout;
+	DevBuf &dq = ctx->sw_q, &dt = ctx->sw_t, &dout = ctx->sw_out;
 	CK(dq.ensure((size_t)n * 16));
 	CK(dt.ensure((size_t)n * 16));
 	CK(dout.ensure((size_t)n * 24));
 	CK(cudaMemcpyAsync(dq.p, query, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(dt.p, target, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 	sw_words_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, dq.as<uint64_t>(), dt.as<uint64_t>(), dout.as<int>());
 	CK(cudaGetLastError());
+	CK(cudaEventRecord(ctx->ev[1], ctx->stream));
 	std::vector<int> h((size_t)n * 6);
 	CK(cudaMemcpyAsync(h.data(), dout.p, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	cudaEventElapsedTime(&ctx->sw_ms_kernel, ctx->ev[0], ctx->ev[1]);
 	for (uint32_t p = 0; p < n; ++p) {
 		const int *o = h.data() + 6 * (size_t)p;
 		if (score) score[p] = o[0];
@@ -408,6 +411,13 @@ int pcramp_gpu_sw_batch(pcramp_gpu_ctx *ctx, uint32_t n, const uint64_t *query, 
 		if (last_two) { last_two[2 * p] = (uint8_t)((o[5] >> 4) & 15); last_two[2 * p + 1] = (uint8_t)(o[5] & 15); }
 	}
 	ctx->stats.kernel_launches = 1;
+	return 0;
+}
+
+int pcramp_gpu_sw_timing(pcramp_gpu_ctx *ctx, float *ms_kernel)
+{ // CUDA-event time of sw_words_kernel in the last pcramp_gpu_sw_batch
+	if (!ctx) return 1;
+	if (ms_kernel) *ms_kernel = ctx->sw_ms_kernel;
 	return 0;
 }
 
