@@ -1383,11 +1383,13 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 						cub::DoubleBuffer<unsigned long long> dbuf(d_np, d_np + ctx->d_neigh.cap / 16);
 						size_t tb = 0;
 						const int end_bit = 32 + (int)bits_for((uint64_t)s.n_cand + 1);
-						CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dbuf, (int)n_np, 0, end_bit, st));
+						// grouping by candidate is all neigh_offsets_kernel / entry_neigh_kernel need (the oligos of a candidate in any order):
+						// only the candidate bits are sorted -- two radix passes instead of six
+						CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dbuf, (int)n_np, 32, end_bit, st));
 						CK(ctx->cub_tmp.ensure(tb));
-						CK(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tb, dbuf, (int)n_np, 0, end_bit, st));
+						CK(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tb, dbuf, (int)n_np, 32, end_bit, st));
 						d_np = dbuf.Current();
-						ctx->stats.kernel_launches += 8;
+						ctx->stats.kernel_launches += 4;
 					}
 					neigh_offsets_kernel<<<grid_for((uint64_t)s.n_cand + 1, 256), 256, 0, st>>>(d_np, n_np, s.n_cand, ctx->d_neigh_off.as<uint32_t>());
 					const size_t row_bytes = (size_t)2 * s.n * nw * 4;
