@@ -45,8 +45,11 @@ def parse_args():
     ap.add_argument("--length", type=int, default=30000)
     ap.add_argument("--clades", type=int, default=20)
     ap.add_argument("--pairs", type=int, default=1000)
-    ap.add_argument("--cpu-targets", type=int, default=96, help="targets in the bounded CPU sample")
+    ap.add_argument("--cpu-targets", type=int, default=200, help="targets in the bounded CPU sample of the b200 arm (also the parity pin)")
+    ap.add_argument("--ref-targets", type=int, default=200, help="targets per step of --impl reference (every k-th target of the collection)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="the timed region of --steps steps is repeated (same steps, same brackets) until this much device time was measured")
     ap.add_argument("--shard", default="pairs", choices=["pairs", "targets"],
                     help="N>1: pairs = every GPU holds all targets and scores its own batches of the sweep (no data-path exchange, the "
                          "headline); targets = the sequences are split across the GPUs, every GPU scores the same batch and the shards' "
@@ -67,6 +70,13 @@ def parse_args():
 def workload_name(a):
     return ("C5 sweep: batches of %d fixed primer pairs (18-25 nt, amplicon 80-200 nt) vs %d x %d nt synthetic viral targets "
             "(%d clades, 15%%/5%% divergence); step = seed scan + pair scoring of one batch" % (a.pairs, a.targets, a.length, a.clades))
+
+
+def bench_config(a):
+    """the workload, identical in both arms (the driver compares the two lines' `config`)"""
+    return {"workload": workload_name(a), "targets": a.targets, "target_len": a.length, "pairs_per_step": a.pairs,
+            "seed_threshold": float(TARGET_THR * SEARCH_MULT), "detect_threshold": float(TARGET_THR),
+            "l2": "inputs larger than L2 (%.0f MB of packed bases)" % (a.targets * a.length / 2e6)}
 
 
 def make_factory(a):
@@ -209,13 +219,16 @@ def cpu_checker():
     return OracleLib(), "port", 1
 
 
-def cpu_step(chk, kind, sample, f, r):
+def cpu_step(chk, kind, sample, f, r, want_bits=False):
+    """one step on the CPU; -> (coverage at search 0.9 / detect 1.0, find_target_match bits or None)"""
     thr = float(TARGET_THR * SEARCH_MULT)
     chk.select_words(f, r, thr)
     if kind == "reference":
-        chk.score_pairs(f, r, float(TARGET_THR), float(SEARCH_MULT), 80, 200, False, want_cov=True, want_bits=False)
-    else:
-        chk.score_pairs(f, r, thr, float(TARGET_THR), 80, 200, False)
+        cov, bits = chk.score_pairs(f, r, float(TARGET_THR), float(SEARCH_MULT), 80, 200, False, want_cov=True, want_bits=want_bits)
+        return cov, (bits if want_bits else None)
+    cov, _ = chk.score_pairs(f, r, thr, float(TARGET_THR), 80, 200, False)
+    bits = chk.score_pairs(f, r, float(TARGET_THR), float(TARGET_THR), 80, 200, False)[1] if want_bits else None
+    return cov, bits
 
 
 def cpu_sample(a, factory, n_targets):
@@ -231,7 +244,7 @@ def run_reference(a):
         return
     factory = make_factory(a)
     chk, kind, cores = cpu_checker()
-    n_t = max(8, a.cpu_targets // 2)
+    n_t = min(a.targets, a.ref_targets)       # a stated subsample of >= 200 targets, scaled linearly
     sample, _ = cpu_sample(a, factory, n_t)
     chk.set_sequences(sample)
     total = a.steps + a.warmup
@@ -248,7 +261,7 @@ def run_reference(a):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
-        "data": "synthetic", "config": {"workload": workload_name(a), "targets": a.targets, "target_len": a.length, "pairs_per_step": a.pairs},
+        "data": "synthetic", "config": bench_config(a),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -585,6 +598,59 @@ def target_sharded_leg(a, factory, rank, world, local, dist, torch, thr):
             "detected_bits_last_step": int(chk[1].item())}
 
 
+def parity_at_bench(a, g, factory, coll, fb, rb, thr, device):
+    """The bounded CPU sample of the bench's own workload doubles as the parity pin at bench scale: the reference scores batch 0
+    (the bench's own 1000 pairs) against every k-th target of the bench's own collection, and its coverage (optimize()'s first
+    score: search 0.9, detect 1.0) and find_target_match bitsets (search = detect = 1.0) must equal, bit for bit,
+      (i)  the same sub-collection through a second context of the CUDA library, and
+      (ii) those targets' columns of the FULL collection's result for the same pairs (per-sequence independence of the path,
+           select_words.cpp:131-138, pcr_assay.cpp:348-360) -- which is the resident index / tier table / id sort at full size.
+    -> (cpu_baseline dict, parity dict)"""
+    from pcramp_b200 import PcrampGpu, TARGET
+    from pcramp_b200.api import unpack_bits
+    chk, kind, cores = cpu_checker()
+    sample, idx = cpu_sample(a, factory, a.cpu_targets)
+    chk.set_sequences(sample)
+    t0 = time.perf_counter()
+    cov_ref, bits_ref = cpu_step(chk, kind, sample, fb, rb, want_bits=True)
+    dt = time.perf_counter() - t0
+    P = len(fb)
+    cpu_baseline = {"value": P * len(idx) / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
+                    "sample": "one step of %d pairs x %d of the %d targets (every %d-th target), coverage + find_target_match bitsets" % (
+                        P, len(idx), a.targets, max(1, a.targets // len(idx)))}
+    one = float(TARGET_THR)
+    # (ii) the full collection, through the resident context the timed region used
+    g.select_words(TARGET, fb, rb, thr, want_keys=False)
+    cov_full, bits_full = g.score_pairs(TARGET, fb, rb, thr, one)
+    _, bits_full_tm = g.score_pairs(TARGET, fb, rb, one, one)
+    col = np.asarray(idx, dtype=np.int64)
+    full_cols = unpack_bits(bits_full, coll.n)[:, col]
+    full_cols_tm = unpack_bits(bits_full_tm, coll.n)[:, col]
+    # (i) the sub-collection on its own context
+    g2 = PcrampGpu(device)
+    try:
+        g2.upload_sequences(TARGET, sample.nibbles, sample.byte_off, sample.length)
+        g2.select_words(TARGET, fb, rb, thr, want_keys=False)
+        cov_sub, bits_sub = g2.score_pairs(TARGET, fb, rb, thr, one)
+        _, bits_sub_tm = g2.score_pairs(TARGET, fb, rb, one, one)
+    finally:
+        g2.close()
+    sub = unpack_bits(bits_sub, sample.n)
+    sub_tm = unpack_bits(bits_sub_tm, sample.n)
+    checks = {
+        "coverage_subsample_vs_reference": bool(np.array_equal(cov_sub, cov_ref)),
+        "bitsets_subsample_vs_reference": bool(np.array_equal(sub_tm, bits_ref)),
+        "coverage_full_columns_vs_reference": bool(np.array_equal(full_cols.sum(axis=1).astype(np.float32), cov_ref)),
+        "bitsets_full_columns_vs_reference": bool(np.array_equal(full_cols_tm, bits_ref)),
+        "full_columns_vs_subsample_search": bool(np.array_equal(full_cols, sub)),
+        "full_coverage_is_popcount": bool(np.array_equal(cov_full, unpack_bits(bits_full, coll.n).sum(axis=1).astype(np.float32))),
+    }
+    parity = {"ok": all(checks.values()), "checks": checks, "pairs": P, "targets_compared": len(idx), "of_targets": coll.n,
+              "detected_bits_reference": int(bits_ref.sum()), "detected_bits_full_collection": int(unpack_bits(bits_full_tm, coll.n).sum()),
+              "checker": kind}
+    return cpu_baseline, parity
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -788,12 +854,21 @@ def run_b200(a):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        ms_resident = timed_region(step_resident, a.warmup, a.steps, True, W)
+        def repeated(fn, first_batch):
+            """the K-step region, repeated until --min-seconds of device time have been measured (K steps at ~1.4 ms are tens of
+            milliseconds): every repeat is the same K steps bracketed by barrier + synchronize; -> (mean ms per K steps, repeats)"""
+            ms, reps = timed_region(fn, first_batch, a.steps, True, W), 1
+            while ms < a.min_seconds * 1e3 and reps < 4096:
+                ms += timed_region(fn, first_batch, a.steps, False, W)
+                reps += 1
+            return ms / reps, reps
+
+        ms_resident, reps_resident = repeated(step_resident, a.warmup)
         launches_resident = launches[0]
         for k in range(W):
             step_e2e(total, False, k)
         launches[0] = 0
-        ms_e2e = timed_region(step_e2e, total + 1, a.steps, True, W)
+        ms_e2e, reps_e2e = repeated(step_e2e, total + 1)
         clocks = sampler.stop() if rank == 0 else None
         # one batch at a time on one context: the library's per-kernel event times (roofline, stage breakdown) are taken here,
         # where a kernel's duration is its own
@@ -806,7 +881,7 @@ def run_b200(a):
     tsh = None
     if world > 1 and not by_targets:
         tsh = target_sharded_leg(a, factory, rank, world, local, dist, torch, thr)
-    value = evals_per_step * a.steps / (ms_resident * 1e-3)
+    value = evals_per_step * a.steps / (ms_resident * 1e-3)      # ms_*: mean over the repeats of the --steps-step region
     e2e_value = evals_per_step * a.steps / (ms_e2e * 1e-3)
 
     if rank == 0:
@@ -845,8 +920,7 @@ def run_b200(a):
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms, "share_of_step": kernel_ms * n_scan / ms_sequential,
             "note": "algorithmic bytes = SURVEY.md 8d (nibbles of the active targets + 16 B/candidate + 28 B/entry): what ONE pass over the text "
                     "would move.  The seeded scan does not stream the text: %d patterns are resolved through a text index (index.cuh) whose "
-                    "16-byte entries are the kernel's real HBM stream -- `traffic` (ncu dram bytes, profiles/) is ~6.5x the algorithmic bytes "
-                    "by design (1.5e8 candidate entries instead of 3e9 verifications), see `index_stream`" % last["n_patterns"],
+                    "16-byte entries are the kernel's real HBM stream, see `index_stream` and `traffic` (ncu dram bytes, profiles/)" % last["n_patterns"],
             "index_stream": {
                 "unit": "GB/s", "bytes_per_launch": stream_bytes, "achieved": stream_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0,
                 "frac_of_hbm_peak": (stream_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if kernel_ms > 0 else 0.0,
@@ -862,43 +936,52 @@ def run_b200(a):
                         "pcramp_gpu_measure_int_peak).  The brute-force kernel sits at ~1.0 of it; the exact filters exceed 1.0 because they "
                         "skip alignments."},
         }
-        cpu_baseline = None
+        cpu_baseline, parity = None, None
         if world == 1 and not a.no_cpu_baseline:
-            chk, kind, cores = cpu_checker()
-            sample, _ = cpu_sample(a, factory, a.cpu_targets)
-            chk.set_sequences(sample)
-            fb, rb = f_all[:P], r_all[:P]
-            t0 = time.perf_counter()
-            cpu_step(chk, kind, sample, fb, rb)
-            dt = time.perf_counter() - t0
-            cpu_baseline = {"value": P * a.cpu_targets / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
-                            "sample": "one step of %d pairs x %d of the %d targets (every %d-th target)" % (
-                                P, a.cpu_targets, a.targets, max(1, a.targets // a.cpu_targets))}
+            cpu_baseline, parity = parity_at_bench(a, g, factory, coll, f_all[:P], r_all[:P], thr, local)
         jobs = 1 if by_targets else world                  # pair-sharded: every rank moves its own batch
         h2d = 2 * P * 16 * jobs
         d2h = (P * 4 + P * n_words_global * 4) * jobs
-        print(json.dumps({
+        legs = {
+            "dp_gcups": dp, "target_sharded": tsh,
+            "sw_gcups": sw_leg(a, g, ext, torch) if a.dp_problems > 0 else None,
+            "candidate_generation": candidate_leg(a, g, factory) if a.fasta_targets > 0 else None,
+            "fasta_ingest": fasta_leg(a, g, coll, hbm_peak) if a.fasta_targets > 0 else None}
+        line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_resident / a.steps, "higher_is_better": True, "scaling": "strong" if (by_targets or world == 1) else "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic",
-            "config": {"workload": workload_name(a), "targets": a.targets, "target_len": a.length, "pairs_per_step": P,
-                       "seed_threshold": thr, "detect_threshold": float(TARGET_THR), "sharding": ("targets, contiguous, %d shard(s); every GPU scores the same batch" % world) if (by_targets or world == 1) else
+            "ms_per_step": ms_resident / a.steps, "higher_is_better": True, "scaling": "strong" if (by_targets or world == 1) else "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": bench_config(a),
+            "layout": {"sharding": ("targets, contiguous, %d shard(s); every GPU scores the same batch" % world) if (by_targets or world == 1) else
                        ("pairs: %d GPUs x all %d targets, each GPU scores its own batch of %d pairs per step" % (world, a.targets, P)),
                        "exchange": ("none" if not by_targets else "peer stores over NVLink from the scoring stream + flag wait (xchg.cuh), no NCCL "
                                     "on the data path" if p2p else "NCCL all-gather + pcramp_gpu_merge_shards"),
-                       "l2": "inputs larger than L2 (%.0f MB of bit-planes per GPU)" % (coll.length.sum() / 2e6),
                        "db_entries_per_step": stats_acc["n_entries"] / n_scan, "hits_per_step": stats_acc["n_hits"] / n_scan},
+            "timed_region": {"repeats_resident": reps_resident, "repeats_e2e": reps_e2e, "seconds_resident": ms_resident * reps_resident * 1e-3,
+                             "seconds_e2e": ms_e2e * reps_e2e * 1e-3,
+                             "note": "the region of --steps steps (barrier + synchronize on both sides, CUDA events) is repeated until "
+                                     "--min-seconds of device time; ms_per_step is the mean over all repeats"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_resident,
             "breakdown_ms_per_step": {k: stats_acc[k] / n_scan for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score")},
             "pipeline": {"workers": W, "ms_per_step_one_batch_at_a_time": ms_sequential / a.steps,
+                         "launches_per_step": launches_resident / max(1, a.steps),
                          "note": "value / e2e: %d batch(es) in flight per GPU (worker contexts sharing the resident targets and text index, one "
                                  "host thread each); roofline / breakdown: from a pass with one batch at a time" % W},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "dp_gcups": dp, "target_sharded": tsh,
-            "sw_gcups": sw_leg(a, g, ext, torch) if (a.dp_problems > 0 and rank == 0) else None,
-            "candidate_generation": candidate_leg(a, g, factory) if a.fasta_targets > 0 else None,
-            "fasta_ingest": fasta_leg(a, g, coll, hbm_peak) if a.fasta_targets > 0 else None}))
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_at_bench": parity}
+        line.update(legs)
+        # the driver keeps the last ~1500 characters of the line: the facts a reader needs first go last
+        line["summary"] = {
+            "value": value, "e2e": e2e_value, "ms_per_step": ms_resident / a.steps, "ms_one_batch_at_a_time": ms_sequential / a.steps,
+            "launches_per_step": launches_resident / max(1, a.steps), "roofline_frac": roofline["frac"], "roofline_kernel": roofline["kernel"],
+            "parity_at_bench": None if parity is None else parity["ok"],
+            "cpu_reference_evals_per_s": None if cpu_baseline is None else cpu_baseline["value"],
+            "dp_gcups": None if dp is None else dp["value"], "dp_gcups_e2e": None if dp is None else dp["e2e"]["value"],
+            "sw_gcups": None if legs["sw_gcups"] is None else legs["sw_gcups"]["value"],
+            "target_sharded_evals_per_s": None if tsh is None else tsh["value"],
+            "target_sharded_ms_per_step": None if tsh is None else tsh["ms_per_step"],
+            "timed_seconds": ms_resident * reps_resident * 1e-3}
+        print(json.dumps(line))
     # teardown order matters: torch tensors that were used on the library's stream must die before the stream does
     sys.stdout.flush()
     torch.cuda.synchronize()
@@ -906,13 +989,15 @@ def run_b200(a):
         if by_targets and not p2p:
             del gat_any, gat_p1, packed_any, packed_p1, out_bits, out_cov
         dist.barrier()                      # p2p: nobody frees its exchange buffer while a peer could still store into it
-    del ext
+    for c in ctxs[1:]:
+        c.close()                           # workers before their parent (include/pcramp_gpu.h)
+    del ext, host_cov, host_bits, f_pin, r_pin
     torch.cuda.empty_cache()
     g.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    os._exit(0)
+    # a normal interpreter exit from here on (exit hooks run): nothing of torch's still refers to the library's stream
 
 
 def main():

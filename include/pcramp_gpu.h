@@ -272,7 +272,7 @@ int pcramp_gpu_merge_shards(pcramp_gpu_ctx *ctx, const void *d_any_gathered, con
  *   connect  peers = world pointers (from_ipc = 0) or world x 64 bytes of handles gathered from all ranks (from_ipc = 1)
  *   step     after pcramp_gpu_score_pairs_staged on this rank's shard; asynchronous
  *   coverage / bitsets / words   device pointers + row pitch of the merged result;  fetch = host copies (synchronises, and
- *            reports a rank that did not arrive within ~2 s instead of hanging) */
+ *            reports a rank that did not arrive within the timeout instead of hanging) */
 int pcramp_gpu_exchange_create(pcramp_gpu_ctx *ctx, uint32_t rank, uint32_t world, const uint32_t *shard_nseq, uint32_t max_pairs,
 	const float *weight_all);
 void *pcramp_gpu_exchange_buffer(pcramp_gpu_ctx *ctx);
@@ -283,7 +283,26 @@ void *pcramp_gpu_exchange_coverage(pcramp_gpu_ctx *ctx);
 void *pcramp_gpu_exchange_bitsets(pcramp_gpu_ctx *ctx);
 uint32_t pcramp_gpu_exchange_words(pcramp_gpu_ctx *ctx);
 int pcramp_gpu_exchange_fetch(pcramp_gpu_ctx *ctx, float *coverage, uint32_t *bitsets);
+/* rows (pairs) of the last step: what pcramp_gpu_exchange_fetch copies (size the host arrays from this, not from memory) */
+uint32_t pcramp_gpu_exchange_pairs(pcramp_gpu_ctx *ctx);
+/* Failure model: a rank that never arrives is detected after a bound (default 120 s of GPU time; ranks legitimately skew by
+ * seconds -- first-step index build, allocation growth, rank-0 I/O).  The step's coverage is then poisoned (NaN) for consumers of
+ * the device pointers, _status / _fetch report the missing ranks, and every later _step / _reduce_best fails until the exchange
+ * has been destroyed on ALL ranks and created again (_create refuses while one exists; _connect refuses a second call and
+ * undoes a partial one).  Ranks must not share a device. */
+int pcramp_gpu_exchange_set_timeout_ms(pcramp_gpu_ctx *ctx, uint32_t ms);
+int pcramp_gpu_exchange_status(pcramp_gpu_ctx *ctx, uint32_t *timed_out_mask);
 int pcramp_gpu_exchange_destroy(pcramp_gpu_ctx *ctx);
+/* reduce_best_assay (main.cpp:1421-1601) over the ranks of the exchange, without MPI / NCCL / host staging: every rank passes the
+ * winner of ITS trials (pcramp_gpu_best_assay: Score members, PCR::total_degeneracy, GLOBAL trial index; index < 0 = no assay, the
+ * rank then competes with the default Score, pcramp.h:176-179) and receives the overall winner and the rank that owns it (which
+ * then broadcasts oligos / amplicons, as the root does at main.cpp:1503-1601).  Rule of main.cpp:1455-1480 folded in rank order:
+ * a later record wins unless its Score is lower (Score::operator<, pcramp.h:180-187), or equal (operator==) with a total degeneracy
+ * that is not smaller.  One single-CTA kernel pushes the 32-byte record into every peer's buffer, waits for all ranks' flags and
+ * folds.  Synchronises the stream. */
+int pcramp_gpu_reduce_best(pcramp_gpu_ctx *ctx, float target_coverage, float background_coverage, float oligo_overlap, double degeneracy,
+	int64_t global_trial, uint32_t *owner_rank, float *best_target, float *best_background, float *best_overlap, double *best_degeneracy,
+	int64_t *best_trial);
 
 /* ---- K3: SantaLucia nearest-neighbour thermodynamics: replaces the NucCruc call surface pcramp uses
  *      (nuc_cruc.h:696-763 tm_pm_duplex / approximate_tm_hairpin, :775-838 salt / strand, :875-994 set_query /

@@ -944,4 +944,65 @@ long ref_append_fasta_groups(void *h, int n_files, const char *const *paths, con
 	return n;
 }
 
+// The best-assay update rule of main.cpp:829-858 (the branch without background sequences; the one with them, :812-827, applies the
+// same test) folded over n scored trials in order, with the reference's own Score::operator< / == (pcramp.h:180-201) and
+// PCR::total_degeneracy (assay.h:536-539) on the reference's own objects.  best = -1 when no trial was taken.
+int ref_best_assay(uint32_t n, const float *target_cov, const float *background_cov, const float *overlap, const uint64_t *f, const uint64_t *r,
+	float max_background_cover, int64_t *best, float *best_accuracy, float *best_overlap, double *best_degeneracy)
+{
+	return guarded(NULL, [&]() {
+		PCR best_assay;
+		Score best_score;
+		int64_t bi = -1;
+		for (uint32_t t = 0; t < n; ++t) {
+			Score s;
+			s.target_coverage = target_cov[t];
+			s.background_coverage = background_cov[t];
+			s.oligo_overlap = overlap ? overlap[t] : 0.0f;
+			PCR trial;
+			trial.oligo(FORWARD, make_word(f + 2 * t));
+			trial.oligo(REVERSE, make_word(r + 2 * t));
+			const bool update_best = (s.background_coverage <= max_background_cover) &&
+				((best_score < s) || ((best_score == s) && (best_assay.total_degeneracy() > trial.total_degeneracy())));
+			if (update_best) {
+				best_score = s;
+				best_assay.copy_oligos(trial);
+				bi = t;
+			}
+		}
+		*best = bi;
+		if (bi >= 0) {
+			*best_accuracy = best_score.accuracy();
+			*best_overlap = best_score.oligo_overlap;
+			*best_degeneracy = best_assay.total_degeneracy();
+		}
+	});
+}
+
+// The root's receive loop of reduce_best_assay (main.cpp:1455-1480) over the records of n_ranks ranks taken in rank order (rank 0 =
+// the root's own best; MPI_ANY_SOURCE makes the real arrival order unspecified, rank order is one of them): a record replaces the
+// running best unless `trial_score < m_score`, or `trial_score == m_score && m_assay.total_degeneracy() <= trial_degeneracy`.
+// score: n_ranks x {target, background, overlap}.  -> index of the rank whose record is kept.
+int ref_reduce_best(uint32_t n_ranks, const float *score, const double *degeneracy)
+{
+	Score m_score;
+	m_score.target_coverage = score[0];
+	m_score.background_coverage = score[1];
+	m_score.oligo_overlap = score[2];
+	double m_degeneracy = degeneracy[0];
+	int owner = 0;
+	for (uint32_t k = 1; k < n_ranks; ++k) {
+		Score trial_score;
+		trial_score.target_coverage = score[3 * k];
+		trial_score.background_coverage = score[3 * k + 1];
+		trial_score.oligo_overlap = score[3 * k + 2];
+		if (trial_score < m_score) continue;
+		if ((trial_score == m_score) && (m_degeneracy <= degeneracy[k])) continue;
+		m_score = trial_score;
+		m_degeneracy = degeneracy[k];
+		owner = (int)k;
+	}
+	return owner;
+}
+
 } // extern "C"

@@ -178,6 +178,11 @@ SIGNATURES = {
     "pcramp_gpu_exchange_words": (ctypes.c_uint32, [ctypes.c_void_p]),
     "pcramp_gpu_exchange_fetch": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
     "pcramp_gpu_exchange_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pcramp_gpu_exchange_pairs": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "pcramp_gpu_exchange_set_timeout_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32]),
+    "pcramp_gpu_exchange_status": (ctypes.c_int, [ctypes.c_void_p, _u32p]),
+    "pcramp_gpu_reduce_best": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_double, ctypes.c_int64,
+                                               _u32p, _f32p, _f32p, _f32p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "pcramp_gpu_measure_int_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "pcramp_gpu_bitset_words": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_int]),
     "pcramp_gpu_fetch_results": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
@@ -607,14 +612,38 @@ class PcrampGpu:
         return (self.lib.pcramp_gpu_exchange_coverage(self.h), self.lib.pcramp_gpu_exchange_bitsets(self.h),
                 int(self.lib.pcramp_gpu_exchange_words(self.h)))
 
-    def exchange_fetch(self, n_pairs):
+    def exchange_fetch(self, n_pairs=None):
+        """host copies of the merged result of the last step; the row count is the library's (n_pairs, when given, must agree)"""
         words = int(self.lib.pcramp_gpu_exchange_words(self.h))
-        cov = np.zeros(n_pairs, np.float32)
-        bits = np.zeros((n_pairs, words), np.uint32)
+        rows = int(self.lib.pcramp_gpu_exchange_pairs(self.h))
+        if n_pairs is not None and int(n_pairs) != rows:
+            raise GpuError("exchange_fetch: the last step held %d pairs, not %d" % (rows, int(n_pairs)))
+        cov = np.zeros(rows, np.float32)
+        bits = np.zeros((rows, max(1, words)), np.uint32)
         self._ck(self.lib.pcramp_gpu_exchange_fetch(self.h, _ptr(cov, _f32p), _ptr(bits, _u32p)))
         return cov, bits
 
-    # ---- K3: nearest-neighbour thermodynamics -------------------------------------------------------
+    def exchange_set_timeout_ms(self, ms):
+        self._ck(self.lib.pcramp_gpu_exchange_set_timeout_ms(self.h, int(ms)))
+
+    def exchange_status(self):
+        """-> bit mask of the ranks that never arrived (0 = healthy); synchronises"""
+        m = ctypes.c_uint32()
+        self._ck(self.lib.pcramp_gpu_exchange_status(self.h, ctypes.byref(m)))
+        return int(m.value)
+
+    def exchange_destroy(self):
+        self._ck(self.lib.pcramp_gpu_exchange_destroy(self.h))
+
+    def reduce_best(self, target_coverage, background_coverage, oligo_overlap, degeneracy, global_trial):
+        """pcramp_gpu_reduce_best -> (owner rank, target, background, overlap, degeneracy, global trial or -1)"""
+        o, t, b, v = ctypes.c_uint32(), ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        d, k = ctypes.c_double(), ctypes.c_int64()
+        self._ck(self.lib.pcramp_gpu_reduce_best(self.h, float(target_coverage), float(background_coverage), float(oligo_overlap), float(degeneracy),
+                                                 int(global_trial), ctypes.byref(o), ctypes.byref(t), ctypes.byref(b), ctypes.byref(v),
+                                                 ctypes.byref(d), ctypes.byref(k)))
+        return int(o.value), np.float32(t.value), np.float32(b.value), np.float32(v.value), float(d.value), int(k.value)
+
     def _thermo_args(self, op, seq_a, seq_b, strand_a, strand_b):
         a = seq_a if isinstance(seq_a, np.ndarray) else pack_strings(seq_a)
         n = len(a)

@@ -285,7 +285,22 @@ def random_assay_kats(ref_factory):
     return rec
 
 
+def best_assay_kats(ref):
+    """a15: the best-assay update rule and the cross-rank fold, by the reference's own Score / PCR objects (ref_driver.cpp)"""
+    from tests import best_assay_cases
+    rec = {}
+    for name, tgt, bg, ov, f, r, max_bg in best_assay_cases.trial_cases():
+        rec["trial_" + name] = np.array(ref.best_assay(tgt, bg, ov, f, r, max_bg), np.float64)
+    for name, score, deg, valid in best_assay_cases.rank_cases():
+        rec["rank_" + name] = np.array([ref.reduce_best(score, deg)], np.int64)
+    print("best_assay: %d fixtures" % len(rec))
+    return rec
+
+
 def main():
+    if "--best-assay-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "kat_best_assay.npz"), **best_assay_kats(RefLib()))
+        return
     if "--random-assay-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "kat_random_assay.npz"), **random_assay_kats(RefLib))
         return
@@ -313,6 +328,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_fasta.npz"), **fasta_kats(RefLib()))
     np.savez_compressed(os.path.join(HERE, "kat_amplicons.npz"), **amplicon_kats(RefLib))
     np.savez_compressed(os.path.join(HERE, "kat_random_assay.npz"), **random_assay_kats(RefLib))
+    np.savez_compressed(os.path.join(HERE, "kat_best_assay.npz"), **best_assay_kats(RefLib()))
     print("wrote fixtures to", HERE)
 
 

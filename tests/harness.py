@@ -561,6 +561,25 @@ class RefLib(_Base):
         multiplex.n_seq += n
         return n
 
+    def best_assay(self, target, background, overlap, f, r, max_background_cover):
+        """main.cpp:829-858 folded over the trials with the reference's Score / PCR -> (index or -1, accuracy, overlap, degeneracy)"""
+        fn = self._fn("best_assay", ctypes.c_int, [ctypes.c_uint32, _f32p, _f32p, _f32p, _u64p, _u64p, ctypes.c_float, ctypes.POINTER(ctypes.c_int64),
+                                                   _f32p, _f32p, ctypes.POINTER(ctypes.c_double)])
+        f, r = _w(f), _w(r)
+        t, b = np.ascontiguousarray(target, np.float32), np.ascontiguousarray(background, np.float32)
+        o = None if overlap is None else np.ascontiguousarray(overlap, np.float32)
+        bi, acc, ov, dg = ctypes.c_int64(-1), np.zeros(1, np.float32), np.zeros(1, np.float32), ctypes.c_double(0.0)
+        assert fn(len(f), _p(t, _f32p), _p(b, _f32p), _p(o, _f32p), _p(f, _u64p), _p(r, _u64p), float(max_background_cover), ctypes.byref(bi),
+                  _p(acc, _f32p), _p(ov, _f32p), ctypes.byref(dg)) == 0
+        return int(bi.value), float(acc[0]), float(ov[0]), float(dg.value)
+
+    def reduce_best(self, score, degeneracy):
+        """the root's receive loop of reduce_best_assay (main.cpp:1455-1480) in rank order -> owning rank"""
+        fn = self._fn("reduce_best", ctypes.c_int, [ctypes.c_uint32, _f32p, ctypes.POINTER(ctypes.c_double)])
+        sc = np.ascontiguousarray(score, np.float32)
+        dg = np.ascontiguousarray(degeneracy, np.float64)
+        return int(fn(len(dg), _p(sc, _f32p), dg.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+
     def sequences(self):
         """[(length, weight, nibbles uint8[length])] of the context's sequences"""
         get = self._fn("sequence_get", ctypes.c_long, [ctypes.c_void_p, ctypes.c_uint32, _f32p, _u8p])

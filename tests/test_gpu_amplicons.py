@@ -183,35 +183,19 @@ def test_bounds_before_the_sequence_start_fail_like_the_reference(gpu):
         assert ref.unique_amplicons(f[0], r[0], float(thr), 80, 200, want_bounds=True) is None and "AmpliconBounds" in ref.last_error()
 
 
-def test_best_assay_equals_the_serial_update_rule(gpu):
-    """pcramp_gpu_best_assay == main.cpp:829-858 folded over the trials in order (ties on Score -> lower total degeneracy -> first)"""
-    from pcramp_b200 import synth
-    from pcramp_b200.sharding import better
-    rng = np.random.default_rng(21)
-    coll = synth.make_targets(22, 4, 800, n_clades=1, within=0.02)
-    for n, degfrac in ((1, 0.0), (300, 0.0), (5000, 0.3)):
-        f, r = synth.make_pairs(23 + n, coll, n, degenerate_fraction=degfrac)
-        tgt = rng.integers(0, 6, size=n).astype(np.float32)
-        bg = (rng.integers(0, 3, size=n) * 0.5).astype(np.float32)
-        ov = (rng.integers(0, 3, size=n) * 0.25).astype(np.float32)
-
-        def degen(w):
-            d = 1.0
-            for limb in (int(w[0]), int(w[1])):
-                for k in range(16):
-                    c = bin((limb >> (4 * k)) & 15).count("1")
-                    d *= c if c else 1
-            return d
-        for max_bg in (0.0, 0.5, 10.0):
-            best = None
-            for i in range(n):
-                if not bg[i] <= max_bg:
-                    continue
-                rec = (np.float32(tgt[i] - bg[i]), ov[i], degen(f[i]) + degen(r[i]), i)
-                if better(rec, best):
-                    best = rec
-            idx, acc, o, dg = gpu.best_assay(tgt, bg, ov, f, r, max_bg)
-            assert idx == (best[3] if best else -1)
-            if best:
-                assert (np.float32(acc), np.float32(o), dg) == (best[0], best[1], best[2])
-    assert gpu.best_assay(np.ones(3, np.float32), np.full(3, 5.0, np.float32), None, f[:3], r[:3], 0.0)[0] == -1
+def test_best_assay_equals_the_reference_update_rule(gpu):
+    """pcramp_gpu_best_assay == main.cpp:829-858 folded over the trials in order with the reference's own Score::operator< / == and
+    PCR::total_degeneracy (pcramp.h:180-201, assay.h:536-539): goldens written by oracle/ref_driver.cpp::ref_best_assay, and the live
+    reference when it travelled"""
+    from tests import best_assay_cases
+    gold = np.load(os.path.join(GOLDEN, "kat_best_assay.npz"))
+    ref = RefLib() if os.path.exists(REF_PATH) else None
+    for name, tgt, bg, ov, f, r, max_bg in best_assay_cases.trial_cases():
+        idx, acc, o, dg = gpu.best_assay(tgt, bg, ov, f, r, max_bg)
+        want = gold["trial_" + name]
+        assert idx == int(want[0]), name
+        if idx >= 0:
+            assert (np.float32(acc), np.float32(o), float(dg)) == (np.float32(want[1]), np.float32(want[2]), float(want[3])), name
+        if ref is not None:
+            live = ref.best_assay(tgt, bg, ov, f, r, max_bg)
+            assert live[0] == idx and (idx < 0 or (np.float32(live[1]), np.float32(live[2]), live[3]) == (np.float32(acc), np.float32(o), float(dg))), name

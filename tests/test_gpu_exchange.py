@@ -117,3 +117,59 @@ def test_exchange_between_processes_over_ipc(gpu, tmp_path):
             got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
             assert np.array_equal(got["bits%d" % i], bits_all)
             assert np.array_equal(got["cov%d" % i].view(np.uint32), cov_all.view(np.uint32))
+
+
+def test_reduce_best_over_peer_memory_equals_reference_fold(gpu):
+    """pcramp_gpu_reduce_best (one kernel: push the 32-byte record to every rank, wait, fold) against the reference's receive loop
+    (main.cpp:1455-1480 via ref_reduce_best goldens): every rank must report the same owner and the owner's record"""
+    import threading
+    import torch
+    from pcramp_b200 import PcrampGpu
+    from tests import best_assay_cases
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_best_assay.npz"))
+    n_dev = torch.cuda.device_count()
+    for world in (1, 2, 3, 4, 8):
+        cases = [c for c in best_assay_cases.rank_cases() if len(c[2]) == world]
+        ranks = [PcrampGpu(k % n_dev) for k in range(world)]
+        try:
+            sizes = np.full(world, 32, np.uint32)
+            for k, g in enumerate(ranks):
+                g.exchange_create(k, world, sizes, 4)
+            ptrs = [g.exchange_buffer() for g in ranks]
+            for g in ranks:
+                g.exchange_connect_pointers(ptrs)
+            for name, score, deg, valid in cases:                      # several rounds on one exchange: both record buffers re-used
+                out = [None] * world
+
+                def call(k):
+                    out[k] = ranks[k].reduce_best(score[k, 0], score[k, 1], score[k, 2], deg[k], 1000 + k if valid[k] else -1)
+                th = [threading.Thread(target=call, args=(k,)) for k in range(world)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                owner = int(gold["rank_" + name][0])
+                for k in range(world):
+                    assert out[k] is not None and out[k][0] == owner, (name, k, out[k])
+                    assert (out[k][1], out[k][2], out[k][3], out[k][4]) == (score[owner, 0], score[owner, 1], score[owner, 2], deg[owner]), name
+                    assert out[k][5] == (1000 + owner if valid[owner] else -1)
+        finally:
+            for g in ranks:
+                g.close()
+
+
+def test_exchange_guards(gpu):
+    """advisor findings: create refuses while an exchange exists, connect refuses a second call, fetch sizes from the library"""
+    sizes = np.array([32], np.uint32)
+    gpu.exchange_create(0, 1, sizes, 8)
+    try:
+        with pytest.raises(RuntimeError, match="exists"):
+            gpu.exchange_create(0, 1, sizes, 8)
+        gpu.exchange_connect_pointers([gpu.exchange_buffer()])
+        with pytest.raises(RuntimeError, match="already connected"):
+            gpu.exchange_connect_pointers([gpu.exchange_buffer()])
+        assert gpu.exchange_status() == 0
+        cov, bits = gpu.exchange_fetch()
+        assert len(cov) == 0
+    finally:
+        gpu.exchange_destroy()

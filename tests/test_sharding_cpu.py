@@ -157,3 +157,32 @@ def test_two_rank_best_assay_equals_single_fold(tmp_path):
     assert int(got["owner"]) == want[3] % 2
     want1 = fold_best(recs[1::2])
     assert tuple(got["none_best"]) == tuple(float(x) for x in want1) and int(got["none_owner"]) == 1
+
+
+def test_rank_fold_equals_reference_golden():
+    """sharding.better (the rule sharding.reduce_best applies to the gathered records) against the reference's own fold
+    (main.cpp:1455-1480 through oracle/ref_driver.cpp::ref_reduce_best, golden kat_best_assay.npz): records in rank order,
+    trial index := rank, so a full tie keeps the lower rank as the root's receive loop does"""
+    from tests import best_assay_cases
+    from pcramp_b200.sharding import better
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_best_assay.npz"))
+    n = 0
+    for name, score, deg, valid in best_assay_cases.rank_cases():
+        best, owner = None, 0
+        for k in range(len(deg)):
+            rec = (np.float32(score[k, 0] - score[k, 1]), score[k, 2], deg[k], k) if valid[k] else None
+            if better(rec, best):
+                best, owner = rec, k
+        if valid.any():
+            assert owner == int(gold["rank_" + name][0]), name
+            n += 1
+    assert n > 20
+
+
+def test_rank_fold_golden_matches_live_reference(ref):
+    from tests import best_assay_cases
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_best_assay.npz"))
+    for name, score, deg, valid in best_assay_cases.rank_cases():
+        assert ref.reduce_best(score, deg) == int(gold["rank_" + name][0])
+    for name, tgt, bg, ov, f, r, max_bg in best_assay_cases.trial_cases():
+        assert np.array_equal(np.array(ref.best_assay(tgt, bg, ov, f, r, max_bg), np.float64), gold["trial_" + name])
