@@ -435,7 +435,9 @@ int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
  * partial-word scan compare every word with every oligo instead of going through the frame-aligned seed table (fst.cuh);
  * "use_neighbours" = 0 makes pair scoring find the oligos of a database word by that table walk instead of through the
  * neighbour list of the candidate that produced the word (score.cuh); "use_tier_table" = 0 applies select_words' best-tier rule
- * by sorting the hit list instead of through a (sequence, candidate) table of maxima (db.cuh).
+ * by sorting the hit list instead of through a (sequence, candidate) table of maxima (db.cuh); "tiny_buffers" = 1 makes every
+ * growable device buffer (hits, index queries / candidates, neighbour list, work list) start far too small on a fresh context,
+ * so that the overflow -> grow -> re-run paths are exercised.
  * All paths are CUDA and give identical results; the tests compare them. */
 int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value);
 /* Issue-bound ceiling of the scan's own instruction mix on this GPU (alignments/s), measured live. */

@@ -139,6 +139,7 @@ struct pcramp_gpu_ctx {
 	int max_smem_optin = 0;
 	int force_brute = 0;
 	int use_index = 1;
+	int tiny_buffers = 0; // testing hook (pcramp_gpu_set_option): growable buffers start far too small
 	DevBuf d_idx_queries, d_idx_counters, d_idx_cand;
 	// scratch
 	DevBuf ent_cand[2], d_neigh, d_neigh_off, d_tier_best;

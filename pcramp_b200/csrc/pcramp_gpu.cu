@@ -866,7 +866,8 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(ctx->d_seed_bucket.ensure(SEED_BUCKETS * 4));
 	CK(ctx->d_tile_counter.ensure(16));
 	uint64_t n_hits = 0;
-	uint64_t cap = std::max<uint64_t>(ctx->hit_key[0].cap / 8, 1ull << 20);
+	const bool tiny = ctx->tiny_buffers != 0; // testing hook: every growable buffer starts far too small, so the overflow re-runs engage
+	uint64_t cap = std::max<uint64_t>(ctx->hit_key[0].cap / 8, tiny ? 2048ull : 1ull << 20);
 	for (int attempt = 0;; ++attempt) {
 		CK(ctx->hit_key[0].ensure(cap * 8));
 		CK(ctx->hit_val[0].ensure(cap * 4));
@@ -898,14 +899,14 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 			unsigned int h_idx[4] = {0, 0, 0, 0};
 			for (int grow = 0;; ++grow) { // queries and candidates awaiting resolution: grown if they overflow (sizes repeat from batch to batch)
 				// extended seeds expand a neighbour into up to IDX_EXT_MAX single-bucket queries: ~600 per 18-mer, fewer for longer primers
-				const uint64_t qcap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_queries.cap / sizeof(IdxQuery), (uint64_t)n_seeded * 640u), 0xFFFFFFF0ull);
+				const uint64_t qcap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_queries.cap / sizeof(IdxQuery), tiny ? 1024ull : (uint64_t)n_seeded * 640u), 0xFFFFFFF0ull);
 				CK(ctx->d_idx_queries.ensure(qcap * sizeof(IdxQuery)));
 				CK(cudaMemsetAsync(ctx->d_idx_counters.p, 0, 32, st));
 				index_query_kernel<<<grid_for((uint64_t)n_seeded * IDX_SLOTS, 256), 256, 0, st>>>(ctx->d_part_mask.as<uint4>(),
 					ctx->d_part_meta2.as<uint32_t>(), n_seeded, s.idx_off.as<uint32_t>(), ctx->d_idx_queries.as<IdxQuery>(), (uint32_t)qcap, d_nq, d_nq + 1,
 					(unsigned long long *)(d_nq + 2));
 				CK(cudaGetLastError());
-				const uint64_t ccap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_cand.cap / sizeof(IdxCand), cap), 0xFFFFFFF0ull);
+				const uint64_t ccap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_cand.cap / sizeof(IdxCand), tiny ? 1024ull : cap), 0xFFFFFFF0ull);
 				CK(ctx->d_idx_cand.ensure(ccap * sizeof(IdxCand)));
 				cs.buf = ctx->d_idx_cand.as<IdxCand>();
 				cs.count = d_nq + 4;
@@ -1341,7 +1342,7 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 			};
 			uint32_t chunk_pairs = chunk_for(s.n_entries); // key matrix: at most one key per entry
 			CK(ctx->d_item_count.ensure(16));
-			uint64_t item_cap = std::max<uint64_t>(ctx->d_items.cap / sizeof(ScoreItem), 1ull << 20);
+			uint64_t item_cap = std::max<uint64_t>(ctx->d_items.cap / sizeof(ScoreItem), ctx->tiny_buffers ? 256ull : 1ull << 20);
 			// seed-table filter (fst.cuh) unless too many oligos cannot be seeded (low thresholds: backgrounds at 0.72^2)
 			Fst fst;
 			// neighbour filter (score.cuh) when the candidates x oligos comparison is small next to the table walk it replaces
@@ -1365,7 +1366,7 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 					CK(ctx->d_neigh_off.ensure(((size_t)s.n_cand + 1) * 4));
 					unsigned int n_np = 0;
 					for (int attempt = 0;; ++attempt) { // (candidate, oligo) pairs, then sorted by candidate
-						CK(ctx->d_neigh.ensure(std::max<size_t>(ctx->d_neigh.cap, (size_t)16 * (8ull * n_olig + 4096))));
+						CK(ctx->d_neigh.ensure(std::max<size_t>(ctx->d_neigh.cap, ctx->tiny_buffers ? (size_t)16 * 64 : (size_t)16 * (8ull * n_olig + 4096))));
 						const uint32_t cap = (uint32_t)std::min<size_t>(ctx->d_neigh.cap / 16, 0x7FFFFFF0u); // second half: sort buffer
 						CK(cudaMemsetAsync(ctx->d_item_count.p, 0, 16, st));
 						neigh_pairs_kernel<<<dim3(grid_for(s.n_cand, 256), grid_for(n_olig, 256)), 256, 0, st>>>(s.c_planes.as<uint4>(), s.c_thr.as<uint32_t>(),
@@ -1682,6 +1683,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_neighbours") == 0) { ctx->use_neigh = value; return 0; }
 	if (strcmp(name, "use_tier_table") == 0) { ctx->use_tier_table = value; return 0; }
 	if (strcmp(name, "use_fused_score") == 0) { ctx->use_fused_score = value; return 0; }
+	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }
 	return fail(ctx, std::string("pcramp_gpu_set_option: unknown option ") + name);
 }
 

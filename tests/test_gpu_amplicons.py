@@ -188,7 +188,7 @@ def test_best_assay_equals_the_reference_update_rule(gpu):
     PCR::total_degeneracy (pcramp.h:180-201, assay.h:536-539): goldens written by oracle/ref_driver.cpp::ref_best_assay, and the live
     reference when it travelled"""
     from tests import best_assay_cases
-    gold = np.load(os.path.join(GOLDEN, "kat_best_assay.npz"))
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "kat_best_assay.npz"))
     ref = RefLib() if os.path.exists(REF_PATH) else None
     for name, tgt, bg, ov, f, r, max_bg in best_assay_cases.trial_cases():
         idx, acc, o, dg = gpu.best_assay(tgt, bg, ov, f, r, max_bg)
