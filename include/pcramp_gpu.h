@@ -407,6 +407,56 @@ typedef struct pcramp_gpu_random_assay_options {
 int pcramp_gpu_random_assays(pcramp_gpu_ctx *ctx, int kind, uint32_t n_streams, uint32_t *seeds, const uint32_t *trials_per_stream,
 	const pcramp_gpu_random_assay_options *options, uint64_t *f, uint64_t *r, uint32_t *attempts);
 
+/* ---- one design iteration: the body of the `while(true)` loop of main.cpp:471-1130 ---------------------------------------------
+ * With the targets (PCRAMP_TARGET) and backgrounds (PCRAMP_BACKGROUND) resident on `ctx`, one call does what one pass of that loop
+ * does: draws opt.num_trial trial assays (PCR::random_assay under the seeding of :527-548), indexes the backgrounds and the active
+ * targets against them (:560-691), runs optimize() on every trial (:697-729), screens the survivors -- multiplex_compatible with
+ * the pool, find_multiplex_background_match, the pool x amplicon test, find_background_match (:731-840) -- keeps the best under the
+ * update rule of :829-858, records its target matches (find_target_match, :898) and, for multiplex designs, appends its amplicons
+ * to the multiplex background and splits the targets at their bounds (:989-1017), and retires the detected targets (:1116-1121).
+ * Every step is a batch call of this header over all trials; the decisions the reference takes trial by trial (the running best
+ * score gates which trials are screened) are replayed in trial order from the batched results = the reference at `--thread 1`.
+ *   n_streams   seed streams of candidate generation: 1 = `--thread 1` (one stream draws all trials, bit-exact with the stock
+ *               program); k > 1 = the static schedule of `--thread k` with the threads' seeds drawn in thread order (the reference
+ *               draws them in whatever order its threads reach the critical section).
+ *   seed        opt.seed (main.cpp:112: the global seed every iteration's local seeds are drawn from with rand_r).
+ * --optimize.top-down (make_degenerate) is not offered. */
+typedef struct pcramp_gpu_design_options {
+	uint32_t num_trial, n_streams;                             /* opt.num_trial; OpenMP threads of the trial loop */
+	uint32_t degen;                                            /* opt.degen (-d) */
+	int optimize_5, optimize_3;                                /* opt.optimize_5 / optimize_3 */
+	int primer_min, primer_max;                                /* opt.primer_range */
+	float primer_tm_min, primer_tm_max, primer_strand, salt, max_hairpin, max_dimer;
+	int target_amplicon_min, target_amplicon_max, background_amplicon_min, background_amplicon_max;
+	float target_threshold, target_search_multiplier, background_threshold, background_search_multiplier;
+	float min_target_cover, max_background_cover;              /* opt.min_target_cover, opt.max_background_cover */
+	uint32_t pack_max_degen;
+	float pack_min_gc, pack_max_gc;
+	int use_taq_mama, use_multiplex;
+} pcramp_gpu_design_options;
+typedef struct pcramp_gpu_design_result {
+	int found;                                /* best_score.target_coverage > 0 (main.cpp:928): 0 ends the run */
+	uint32_t iteration, major_id, minor_id;   /* assay_iteration, major_assay_id, minor_assay_id (:458-502) */
+	uint32_t targets_remaining, num_active_target, num_active_background, trial;
+	float active_target_norm, active_background_norm;
+	uint64_t f[2], r[2];                      /* best_assay */
+	double degeneracy_f, degeneracy_r;
+	int reused_f, reused_r;                   /* PCR::write(out, pool) writes a re-used oligo in lower case (assay.h:305-343) */
+	float target_coverage, background_coverage, oligo_overlap; /* best_score */
+	uint64_t n_target_entries, n_background_entries, n_amplicons_added, n_splits, n_multiplex_keys;
+	float ms_total, ms_candidates, ms_select_background, ms_select_target, ms_optimize, ms_screen, ms_accept; /* host wall clock */
+} pcramp_gpu_design_result;
+typedef struct pcramp_gpu_design pcramp_gpu_design;
+void pcramp_gpu_design_default_options(pcramp_gpu_design_options *options); /* Options::Options(), options.cpp:40-92 */
+int pcramp_gpu_design_create(pcramp_gpu_ctx *ctx, const pcramp_gpu_design_options *options, uint32_t seed, pcramp_gpu_design **out);
+void pcramp_gpu_design_destroy(pcramp_gpu_design *d);
+const char *pcramp_gpu_design_last_error(const pcramp_gpu_design *d);
+int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *result);
+/* LSB-first bitsets of the last iteration's best assay: best_target_match, best_background_match (either may be NULL) */
+int pcramp_gpu_design_matches(pcramp_gpu_design *d, uint32_t *target_bits, uint32_t *background_bits);
+/* Sequence::active() of every target, and the union of the accepted assays' background matches (main.cpp:1131-1153) */
+int pcramp_gpu_design_active(pcramp_gpu_design *d, uint8_t *target_active, uint32_t *background_union);
+
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* Counters of the last select_words / score_pairs call on this ctx. */
 typedef struct pcramp_gpu_stats {

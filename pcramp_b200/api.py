@@ -96,6 +96,43 @@ class RandomAssayOptions(ctypes.Structure):
                          primer_tm_range[1], max_hairpin, max_dimer)
 
 
+
+class DesignOptions(ctypes.Structure):
+    """pcramp_gpu_design_options (include/pcramp_gpu.h); filled by pcramp_gpu_design_default_options"""
+    _fields_ = [("num_trial", ctypes.c_uint32), ("n_streams", ctypes.c_uint32), ("degen", ctypes.c_uint32),
+                ("optimize_5", ctypes.c_int), ("optimize_3", ctypes.c_int), ("primer_min", ctypes.c_int), ("primer_max", ctypes.c_int),
+                ("primer_tm_min", ctypes.c_float), ("primer_tm_max", ctypes.c_float), ("primer_strand", ctypes.c_float), ("salt", ctypes.c_float),
+                ("max_hairpin", ctypes.c_float), ("max_dimer", ctypes.c_float),
+                ("target_amplicon_min", ctypes.c_int), ("target_amplicon_max", ctypes.c_int),
+                ("background_amplicon_min", ctypes.c_int), ("background_amplicon_max", ctypes.c_int),
+                ("target_threshold", ctypes.c_float), ("target_search_multiplier", ctypes.c_float),
+                ("background_threshold", ctypes.c_float), ("background_search_multiplier", ctypes.c_float),
+                ("min_target_cover", ctypes.c_float), ("max_background_cover", ctypes.c_float),
+                ("pack_max_degen", ctypes.c_uint32), ("pack_min_gc", ctypes.c_float), ("pack_max_gc", ctypes.c_float),
+                ("use_taq_mama", ctypes.c_int), ("use_multiplex", ctypes.c_int)]
+
+
+class DesignResult(ctypes.Structure):
+    """pcramp_gpu_design_result (include/pcramp_gpu.h)"""
+    _fields_ = [("found", ctypes.c_int), ("iteration", ctypes.c_uint32), ("major_id", ctypes.c_uint32), ("minor_id", ctypes.c_uint32),
+                ("targets_remaining", ctypes.c_uint32), ("num_active_target", ctypes.c_uint32), ("num_active_background", ctypes.c_uint32),
+                ("trial", ctypes.c_uint32), ("active_target_norm", ctypes.c_float), ("active_background_norm", ctypes.c_float),
+                ("f", ctypes.c_uint64 * 2), ("r", ctypes.c_uint64 * 2), ("degeneracy_f", ctypes.c_double), ("degeneracy_r", ctypes.c_double),
+                ("reused_f", ctypes.c_int), ("reused_r", ctypes.c_int),
+                ("target_coverage", ctypes.c_float), ("background_coverage", ctypes.c_float), ("oligo_overlap", ctypes.c_float),
+                ("n_target_entries", ctypes.c_uint64), ("n_background_entries", ctypes.c_uint64), ("n_amplicons_added", ctypes.c_uint64),
+                ("n_splits", ctypes.c_uint64), ("n_multiplex_keys", ctypes.c_uint64),
+                ("ms_total", ctypes.c_float), ("ms_candidates", ctypes.c_float), ("ms_select_background", ctypes.c_float),
+                ("ms_select_target", ctypes.c_float), ("ms_optimize", ctypes.c_float), ("ms_screen", ctypes.c_float), ("ms_accept", ctypes.c_float)]
+
+    def as_dict(self):
+        out = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            out[k] = [int(v[0]), int(v[1])] if k in ("f", "r") else v
+        return out
+
+
 MOVES = {"IncreaseDegeneracy": 0, "DecreaseDegeneracy": 1, "Trim5": 2, "Trim3": 3, "Grow5": 4, "Grow3": 5}
 
 # op codes of pcramp_gpu_thermo_batch (include/pcramp_gpu.h)
@@ -178,6 +215,13 @@ SIGNATURES = {
     "pcramp_gpu_exchange_words": (ctypes.c_uint32, [ctypes.c_void_p]),
     "pcramp_gpu_exchange_fetch": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
     "pcramp_gpu_exchange_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pcramp_gpu_design_default_options": (None, [ctypes.POINTER(DesignOptions)]),
+    "pcramp_gpu_design_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(DesignOptions), ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p)]),
+    "pcramp_gpu_design_destroy": (None, [ctypes.c_void_p]),
+    "pcramp_gpu_design_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "pcramp_gpu_design_iteration": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(DesignResult)]),
+    "pcramp_gpu_design_matches": (ctypes.c_int, [ctypes.c_void_p, _u32p, _u32p]),
+    "pcramp_gpu_design_active": (ctypes.c_int, [ctypes.c_void_p, _u8p, _u32p]),
     "pcramp_gpu_exchange_pairs": (ctypes.c_uint32, [ctypes.c_void_p]),
     "pcramp_gpu_exchange_set_timeout_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32]),
     "pcramp_gpu_exchange_status": (ctypes.c_int, [ctypes.c_void_p, _u32p]),
@@ -766,6 +810,38 @@ class PcrampGpu:
         s = Stats()
         self._ck(self.lib.pcramp_gpu_get_stats(self.h, ctypes.byref(s)))
         return s.as_dict()
+
+
+class DesignLoop:
+    """pcramp_gpu_design_*: the body of pcramp's `while(true)` design loop (main.cpp:471-1130), one iteration per call"""
+
+    def __init__(self, gpu, seed, **options):
+        self.g = gpu
+        self.opt = DesignOptions()
+        gpu.lib.pcramp_gpu_design_default_options(ctypes.byref(self.opt))
+        for k, v in options.items():
+            if not hasattr(self.opt, k):
+                raise KeyError(k)
+            setattr(self.opt, k, v)
+        self.h = ctypes.c_void_p()
+        gpu._ck(gpu.lib.pcramp_gpu_design_create(gpu.h, ctypes.byref(self.opt), int(seed), ctypes.byref(self.h)))
+
+    def iteration(self):
+        res = DesignResult()
+        if self.g.lib.pcramp_gpu_design_iteration(self.h, ctypes.byref(res)):
+            raise GpuError(self.g.lib.pcramp_gpu_design_last_error(self.h).decode())
+        return res
+
+    def matches(self, n_target, n_background=0):
+        t = np.zeros(max(1, (n_target + 31) // 32), np.uint32)
+        b = np.zeros(max(1, (n_background + 31) // 32), np.uint32)
+        self.g.lib.pcramp_gpu_design_matches(self.h, _ptr(t, _u32p), _ptr(b, _u32p))
+        return unpack_bits(t[None, :], n_target)[0], unpack_bits(b[None, :], n_background)[0]
+
+    def close(self):
+        if self.h:
+            self.g.lib.pcramp_gpu_design_destroy(self.h)
+            self.h = None
 
 
 def pack_strings(strs, stride=THERMO_STRIDE):

@@ -11,6 +11,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "pcramp_b200", "csrc")
 LIB = os.path.join(CSRC, "libpcramp_gpu.so")
+HOST_DIR = os.path.join(ROOT, "pcramp_b200", "host")
+HOST_BIN = os.path.join(HOST_DIR, "pcramp_b200")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,6 +53,17 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
+def build_host(force=False):
+    """the command-line host (pcramp_b200/host/pcramp_b200): plain g++, linked against the C-ABI library next to it"""
+    src = os.path.join(HOST_DIR, "pcramp_b200_main.cpp")
+    if not force and not _stale(HOST_BIN, [src, os.path.join(ROOT, "include", "pcramp_gpu.h"), LIB]):
+        return HOST_BIN
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", HOST_BIN, src, "-L" + CSRC, "-lpcramp_gpu", "-lz",
+                    "-Wl,-rpath,$ORIGIN/../csrc"], check=True)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print("built", LIB)
+    print("built", build_host(force="--force" in sys.argv))
