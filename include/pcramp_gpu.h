@@ -476,7 +476,11 @@ typedef struct pcramp_gpu_stats {
 	float ms_edge;            /* ... of the partial-window kernel */
 	float ms_db;              /* ... of hit filtering, sorting, materialisation */
 	float ms_score;           /* ... of the pair-scoring kernels */
-	float ms_index_kernel;    /* ... of scan_index_kernel alone (last launch) */
+	float ms_index_kernel;    /* ... of scan_index_kernel alone (summed over the parts of the index) */
+	float ms_index_build;     /* host wall clock of the last build of the collection's text index (one-time per upload; splits do not rebuild) */
+	uint64_t index_bytes;     /* device memory the text index holds */
+	uint64_t n_index_builds;  /* builds of this collection's index so far */
+	uint64_t n_index_stale;   /* sequences split since the build and active again: covered by the table scan in this call */
 } pcramp_gpu_stats;
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
 /* Tuning / testing switches.  "force_brute_scan" = 1 sends every pattern through the brute-force scan kernel;
@@ -487,7 +491,8 @@ int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
  * neighbour list of the candidate that produced the word (score.cuh); "use_tier_table" = 0 applies select_words' best-tier rule
  * by sorting the hit list instead of through a (sequence, candidate) table of maxima (db.cuh); "tiny_buffers" = 1 makes every
  * growable device buffer (hits, index queries / candidates, neighbour list, work list) start far too small on a fresh context,
- * so that the overflow -> grow -> re-run paths are exercised.
+ * so that the overflow -> grow -> re-run paths are exercised; "index_part_positions" = the most positions one part of the text index
+ * may hold (default 2^31; a small value cuts a test collection into several parts, as a collection above 2^31 bases is).
  * All paths are CUDA and give identical results; the tests compare them. */
 int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value);
 /* Issue-bound ceiling of the scan's own instruction mix on this GPU (alignments/s), measured live. */

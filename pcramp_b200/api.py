@@ -44,6 +44,10 @@ class Stats(ctypes.Structure):
         ("ms_db", ctypes.c_float),
         ("ms_score", ctypes.c_float),
         ("ms_index_kernel", ctypes.c_float),
+        ("ms_index_build", ctypes.c_float),
+        ("index_bytes", ctypes.c_uint64),
+        ("n_index_builds", ctypes.c_uint64),
+        ("n_index_stale", ctypes.c_uint64),
     ]
 
     def as_dict(self):

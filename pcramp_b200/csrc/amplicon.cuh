@@ -460,7 +460,7 @@ int pcramp_gpu_accept_assay(pcramp_gpu_ctx *ctx, uint32_t pair, uint32_t pack_ma
 		m.raw_bytes = old_bytes + add_bytes;
 		m.any_degenerate = m.any_degenerate || (h_flags[1] != 0);
 		m.db_valid = false;
-		m.idx_valid = m.idx_failed = false;
+		m.idx_drop();
 		m.n_entries = m.n_keys = 0;
 		ctx->mpx_valid = false;
 		std::vector<uint32_t> with_eos;

@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -72,10 +75,31 @@ struct SeqSet {
 	DevBuf d_raw, d_raw_off, d_len, d_plen, d_clen, d_planes, d_grp_off, d_eos_pos, d_eos_off, d_weight, d_active, d_tile_seq, d_tile_x0;
 	DevBuf d_dirty_bits, d_dirty_seq, d_dirty_grp; // groups whose alignments read a degenerate base (scan.cuh)
 	uint32_t n_dirty = 0;
-	// text index for the indexed seed scan (index.cuh): built lazily, dropped when the text changes
-	DevBuf idx_entries, idx_off, idx_cum, idx_blk;
+	// text index for the indexed seed scan (index.cuh): built lazily on the first seeded scan, in PARTS of consecutive sequences that
+	// hold fewer than idx_part_cap positions each (32-bit positions inside a part; a 5 x 10^9-base collection is three parts).
+	// A split does not rebuild it: the split sequences are flagged stale -- their entries are ignored, and while they are active
+	// (normally they are retired by the assay that split them, main.cpp:1116-1121) the table scan covers them; the index is rebuilt
+	// only when the stale sequences that are active again hold a sizeable share of the text.
+	struct IndexPart {
+		uint32_t seq_lo = 0, seq_hi = 0; // sequences [seq_lo, seq_hi)
+		uint32_t n = 0;                  // positions = entries
+		DevBuf entries, off, cum, blk;
+	};
+	std::vector<std::unique_ptr<IndexPart>> idx_parts;
 	bool idx_valid = false, idx_failed = false;
-	uint32_t idx_n = 0;
+	std::vector<uint8_t> idx_stale;      // per sequence: split since the index was built
+	uint32_t n_idx_stale = 0;
+	DevBuf d_idx_stale;
+	uint64_t idx_bytes = 0, idx_builds = 0;
+	float idx_build_ms = 0.0f;
+	void idx_drop()
+	{
+		idx_parts.clear();
+		idx_valid = idx_failed = false;
+		idx_stale.clear();
+		n_idx_stale = 0;
+		idx_bytes = 0;
+	}
 	// database (seq-grouped order = entry-id order) + canonical permutation
 	uint64_t n_entries = 0, n_keys = 0;
 	bool db_valid = false;
@@ -140,6 +164,8 @@ struct pcramp_gpu_ctx {
 	int force_brute = 0;
 	int use_index = 1;
 	int tiny_buffers = 0; // testing hook (pcramp_gpu_set_option): growable buffers start far too small
+	uint64_t idx_part_cap = 1ull << 31; // positions per part of the text index (option "index_part_positions": small values for the tests)
+	DevBuf idx_key[2], idx_val[2], idx_tmp, d_stale_tile_seq, d_stale_tile_x0; // build scratch (kept while small), tiles of stale sequences
 	DevBuf d_idx_queries, d_idx_counters, d_idx_cand;
 	// scratch
 	DevBuf ent_cand[2], d_neigh, d_neigh_off, d_tier_best;
@@ -195,5 +221,32 @@ inline uint32_t bits_for(uint64_t n)
 }
 
 inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+// host-side stage trace (environment PCRAMP_TRACE=1): wall-clock between marks, printed to stderr; synchronises the stream at
+// every mark, so it is a debugging aid and never on in measurements
+struct Trace {
+	bool on;
+	cudaStream_t st;
+	const char *who;
+	double t0, last;
+	static double now()
+	{
+		struct timespec ts;
+		clock_gettime(CLOCK_MONOTONIC, &ts);
+		return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+	}
+	Trace(const char *w, cudaStream_t s) : on(getenv("PCRAMP_TRACE") != nullptr), st(s), who(w), t0(0), last(0)
+	{
+		if (on) t0 = last = now();
+	}
+	void mark(const char *what)
+	{
+		if (!on) return;
+		cudaStreamSynchronize(st);
+		const double t = now();
+		fprintf(stderr, "[trace] %s: %-28s %9.3f ms (at %9.3f)\n", who, what, t - last, t - t0);
+		last = t;
+	}
+};
 
 } // namespace pcr

@@ -512,7 +512,7 @@ static int upload_fasta_impl(pcramp_gpu_ctx *ctx, int kind, uint32_t n_files, co
 	s.n = n;
 	s.db_valid = false;
 	if (kind == PCRAMP_MULTIPLEX) ctx->mpx_valid = false;
-	s.idx_valid = s.idx_failed = false;
+	s.idx_drop();
 	s.n_entries = s.n_keys = 0;
 	s.len = tab.length;
 	s.weight = tab.weight;

@@ -31,12 +31,13 @@ constexpr uint32_t IDX_MAX_SEG = 4u;                // e <= 7
 constexpr uint32_t IDX_SLOTS = IDX_MAX_SEG * (1u + 3u * IDX_K);
 constexpr uint32_t IDX_CTX_BEFORE = 16u;
 
-struct TextIndex {
-	const uint4 *entries;   // sorted by 12-mer code: {global position, plane0[31:0], plane1[31:0], plane0[47:32] | plane1[47:32] << 16}
+struct TextIndex { // one part of the index: the sequences [seq_lo, seq_lo + n_seq) of the collection, positions counted from the part's start
+	const uint4 *entries;   // sorted by 12-mer code: {position in the part, plane0[31:0], plane1[31:0], plane0[47:32] | plane1[47:32] << 16}
 	const uint32_t *off;    // IDX_CODES + 1: first entry whose code is >= c
-	const uint32_t *cum;    // n_seq + 1: global position of each sequence's first base
-	const uint32_t *blk;    // (n >> IDX_BLK_SHIFT) + 2: sequence that holds global position b << IDX_BLK_SHIFT
+	const uint32_t *cum;    // n_seq + 1: position of each sequence's first base (as of the build: splits do not move it)
+	const uint32_t *blk;    // (n >> IDX_BLK_SHIFT) + 2: sequence (part-relative) that holds position b << IDX_BLK_SHIFT
 	uint32_t n;             // entries
+	uint32_t seq_lo, n_seq;
 };
 constexpr uint32_t IDX_BLK_SHIFT = 10u;
 
@@ -125,13 +126,14 @@ __device__ __forceinline__ uint32_t idx_seq_of_fast(const TextIndex &ix, uint32_
 }
 
 // ---- build ---------------------------------------------------------------------------------------------------
-__global__ void index_key_kernel(SeqDev sd, const uint32_t *__restrict__ cum, uint32_t n_pos, uint32_t *key, uint32_t *val)
+__global__ void index_key_kernel(SeqDev sd, const uint32_t *__restrict__ cum, uint32_t seq_lo, uint32_t n_seq, uint32_t n_pos, uint32_t *key,
+	uint32_t *val)
 {
 	const uint32_t gpos = blockIdx.x * blockDim.x + threadIdx.x;
 	if (gpos >= n_pos) return;
-	const uint32_t seq = idx_seq_of(cum, sd.n, gpos);
+	const uint32_t rel = idx_seq_of(cum, n_seq, gpos), seq = seq_lo + rel;
 	uint64_t c0, c1;
-	idx_context(sd, seq, gpos - __ldg(cum + seq), c0, c1);
+	idx_context(sd, seq, gpos - __ldg(cum + rel), c0, c1);
 	const uint32_t b0 = (uint32_t)(c0 >> IDX_CTX_BEFORE) & 0xFFFu, b1 = (uint32_t)(c1 >> IDX_CTX_BEFORE) & 0xFFFu;
 	// first base most significant: reverse the 12 bits, then interleave (b1 above b0)
 	const uint32_t r0 = __brev(b0) >> 20, r1 = __brev(b1) >> 20;
@@ -148,14 +150,15 @@ __global__ void index_offsets_kernel(const uint32_t *__restrict__ key_sorted, ui
 	for (int64_t c = prev + 1; c <= cur; ++c) off[c] = i;
 }
 
-__global__ void index_entry_kernel(SeqDev sd, const uint32_t *__restrict__ cum, const uint32_t *__restrict__ pos_sorted, uint32_t n, uint4 *entries)
+__global__ void index_entry_kernel(SeqDev sd, const uint32_t *__restrict__ cum, uint32_t seq_lo, uint32_t n_seq,
+	const uint32_t *__restrict__ pos_sorted, uint32_t n, uint4 *entries)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint32_t gpos = pos_sorted[i];
-	const uint32_t seq = idx_seq_of(cum, sd.n, gpos);
+	const uint32_t rel = idx_seq_of(cum, n_seq, gpos), seq = seq_lo + rel;
 	uint64_t c0, c1;
-	idx_context(sd, seq, gpos - __ldg(cum + seq), c0, c1);
+	idx_context(sd, seq, gpos - __ldg(cum + rel), c0, c1);
 	entries[i] = make_uint4(gpos, (uint32_t)c0, (uint32_t)c1, (uint32_t)(c0 >> 32) | ((uint32_t)(c1 >> 32) << 16));
 }
 
@@ -471,7 +474,7 @@ scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsi
 // place each candidate in its sequence, drop what other kernels own, report once
 __global__ void __launch_bounds__(256)
 index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__restrict__ g_meta, const uint32_t *__restrict__ g_meta2,
-	const uint32_t *__restrict__ dirty_bits, uint32_t cand_bits, HitSink hs)
+	const uint32_t *__restrict__ dirty_bits, const uint8_t *__restrict__ stale, uint32_t cand_bits, HitSink hs)
 {
 	const uint32_t total = min(*cs.count, cs.cap);
 	const uint32_t lane = threadIdx.x & 31u;
@@ -486,9 +489,11 @@ index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__res
 			const IdxCand c = cs.buf[i];
 			if (c.gpos != IDX_INVALID) { // (else: the unused tail of a warp's block)
 				const uint32_t wo = c.seg >> 24, si = (c.seg >> 16) & 255u;
-				seq = idx_seq_of_fast(ix, sd.n, c.gpos);
-				x = (int64_t)(c.gpos - __ldg(ix.cum + seq)) - (int64_t)wo; // text index of primer base 0
-				ok = x >= 0 && sd.active[seq];
+				const uint32_t rel = idx_seq_of_fast(ix, ix.n_seq, c.gpos);
+				seq = ix.seq_lo + rel;
+				x = (int64_t)(c.gpos - __ldg(ix.cum + rel)) - (int64_t)wo; // text index of primer base 0
+				// a sequence split since the build has moved under its entries: the table scan covers it (pcramp_gpu.cu)
+				ok = x >= 0 && sd.active[seq] && !(stale && stale[seq]);
 				if (ok && dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
 					const uint64_t G = sd.grp_off[seq] + (uint64_t)(x >> 5);
 					if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) ok = false;

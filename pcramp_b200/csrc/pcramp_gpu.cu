@@ -283,60 +283,95 @@ inline float ev_ms(cudaEvent_t a, cudaEvent_t b)
 }
 
 // The text index of the indexed seed scan (index.cuh): every position of the collection sorted by its 12-mer code, with the
-// 48-base context planes.  One-time cost per upload / split (a radix sort of the positions); ~32 bytes per base while it is
-// built, 16 afterwards.  Collections of 2^31 positions or more, or a failed allocation, stay on scan_seed_kernel.
+// 48-base context planes, in parts of consecutive sequences that hold fewer than ctx->idx_part_cap (2^31) positions each -- a
+// collection of 5 x 10^9 bases is three parts, each queried on its own.  Cost per part: one radix sort of its positions; ~32 bytes
+// per base while it is built (the scratch is kept between builds while it is small), 16 afterwards.  A failed allocation leaves the
+// collection on scan_seed_kernel.  Splits do not come here (see SeqSet::idx_stale).
 int build_index(pcramp_gpu_ctx *ctx, SeqSet &s)
 {
-	s.idx_valid = false;
-	s.idx_n = 0;
+	s.idx_drop();
 	const uint64_t N = s.total_positions;
-	if (N == 0 || N >= (1ull << 31)) {
+	if (N == 0) {
 		s.idx_failed = true;
 		return 0;
 	}
 	cudaStream_t st = ctx->stream;
-	std::vector<uint32_t> cum(s.n + 1, 0);
-	for (uint32_t i = 0; i < s.n; ++i) cum[i + 1] = cum[i] + s.clen[i];
-	DevBuf key[2], val[2], tmp;
-	size_t tmp_bytes = 0;
-	cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-		(int64_t)N, 0, (int)(2 * IDX_K), st);
-	const bool ok = s.idx_cum.ensure((size_t)(s.n + 1) * 4) == cudaSuccess && key[0].ensure(N * 4) == cudaSuccess &&
-	                key[1].ensure(N * 4) == cudaSuccess && val[0].ensure(N * 4) == cudaSuccess && val[1].ensure(N * 4) == cudaSuccess &&
-	                tmp.ensure(tmp_bytes) == cudaSuccess && s.idx_off.ensure((size_t)(IDX_CODES + 1) * 4) == cudaSuccess &&
-	                s.idx_entries.ensure(N * 16) == cudaSuccess;
+	const uint64_t cap = std::max<uint64_t>(1024, std::min<uint64_t>(ctx->idx_part_cap, 1ull << 31));
+	for (uint32_t i = 0; i < s.n; ++i)
+		if (s.clen[i] >= cap) { // one sequence longer than a part: not indexable
+			s.idx_failed = true;
+			return 0;
+		}
+	const double t0 = Trace::now();
+	const SeqDev sd = s.dev();
+	bool ok = true;
+	uint32_t lo = 0;
+	while (lo < s.n && ok) {
+		uint32_t hi = lo;
+		uint64_t n = 0;
+		while (hi < s.n && n + s.clen[hi] < cap) n += s.clen[hi++];
+		std::unique_ptr<SeqSet::IndexPart> part(new SeqSet::IndexPart());
+		part->seq_lo = lo;
+		part->seq_hi = hi;
+		part->n = (uint32_t)n;
+		const uint32_t ns = hi - lo;
+		lo = hi;
+		if (n == 0) continue;
+		std::vector<uint32_t> cum(ns + 1, 0);
+		for (uint32_t i = 0; i < ns; ++i) cum[i + 1] = cum[i] + s.clen[part->seq_lo + i];
+		size_t tmp_bytes = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+			(int64_t)n, 0, (int)(2 * IDX_K), st);
+		ok = part->cum.ensure((size_t)(ns + 1) * 4) == cudaSuccess && ctx->idx_key[0].ensure(n * 4) == cudaSuccess &&
+		     ctx->idx_key[1].ensure(n * 4) == cudaSuccess && ctx->idx_val[0].ensure(n * 4) == cudaSuccess && ctx->idx_val[1].ensure(n * 4) == cudaSuccess &&
+		     ctx->idx_tmp.ensure(tmp_bytes) == cudaSuccess && part->off.ensure((size_t)(IDX_CODES + 1) * 4) == cudaSuccess &&
+		     part->entries.ensure(n * 16) == cudaSuccess;
+		if (!ok) break;
+		CK(cudaMemcpyAsync(part->cum.p, cum.data(), (size_t)(ns + 1) * 4, cudaMemcpyHostToDevice, st));
+		{ // block table: last sequence (part-relative) whose first position is <= b << IDX_BLK_SHIFT (idx_seq_of_fast)
+			std::vector<uint32_t> blk((n >> IDX_BLK_SHIFT) + 2, 0);
+			uint32_t q = 0;
+			for (size_t b = 0; b < blk.size(); ++b) {
+				const uint64_t g = (uint64_t)b << IDX_BLK_SHIFT;
+				while (q + 1 < ns && cum[q + 1] <= g) ++q;
+				blk[b] = q;
+			}
+			CK(part->blk.ensure(blk.size() * 4));
+			CK(cudaMemcpyAsync(part->blk.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, st));
+			CK(cudaStreamSynchronize(st));
+		}
+		uint32_t *k0 = ctx->idx_key[0].as<uint32_t>(), *k1 = ctx->idx_key[1].as<uint32_t>(), *v0 = ctx->idx_val[0].as<uint32_t>(),
+		         *v1 = ctx->idx_val[1].as<uint32_t>();
+		index_key_kernel<<<grid_for(n, 256), 256, 0, st>>>(sd, part->cum.as<uint32_t>(), part->seq_lo, ns, (uint32_t)n, k0, v0);
+		CK(cudaGetLastError());
+		CK(cub::DeviceRadixSort::SortPairs(ctx->idx_tmp.p, tmp_bytes, k0, k1, v0, v1, (int64_t)n, 0, (int)(2 * IDX_K), st));
+		index_offsets_kernel<<<grid_for(n + 1, 256), 256, 0, st>>>(k1, (uint32_t)n, part->off.as<uint32_t>());
+		CK(cudaGetLastError());
+		index_entry_kernel<<<grid_for(n, 256), 256, 0, st>>>(sd, part->cum.as<uint32_t>(), part->seq_lo, ns, v1, (uint32_t)n, part->entries.as<uint4>());
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(st));
+		s.idx_bytes += part->entries.cap + part->off.cap + part->cum.cap + part->blk.cap;
+		s.idx_parts.push_back(std::move(part));
+	}
+	// the sort scratch of a large collection (4 x 4 bytes per position) is given back; a small one stays for the next build
+	if (ctx->idx_key[0].cap > (256ull << 20)) {
+		for (int k = 0; k < 2; ++k) { ctx->idx_key[k].release(); ctx->idx_val[k].release(); }
+		ctx->idx_tmp.release();
+	}
 	if (!ok) { // not enough device memory: keep the table-based scan
 		cudaGetLastError();
-		s.idx_entries.release();
-		s.idx_off.release();
+		s.idx_drop();
 		s.idx_failed = true;
 		return 0;
 	}
-	CK(cudaMemcpyAsync(s.idx_cum.p, cum.data(), (size_t)(s.n + 1) * 4, cudaMemcpyHostToDevice, st));
-	{ // block table: last sequence whose first position is <= b << IDX_BLK_SHIFT (idx_seq_of_fast)
-		std::vector<uint32_t> blk((N >> IDX_BLK_SHIFT) + 2, 0);
-		uint32_t q = 0;
-		for (size_t b = 0; b < blk.size(); ++b) {
-			const uint64_t g = (uint64_t)b << IDX_BLK_SHIFT;
-			while (q + 1 < s.n && cum[q + 1] <= g) ++q;
-			blk[b] = q;
-		}
-		CK(s.idx_blk.ensure(blk.size() * 4));
-		CK(cudaMemcpyAsync(s.idx_blk.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, st));
-		CK(cudaStreamSynchronize(st));
-	}
-	const SeqDev sd = s.dev();
-	index_key_kernel<<<grid_for(N, 256), 256, 0, st>>>(sd, s.idx_cum.as<uint32_t>(), (uint32_t)N, key[0].as<uint32_t>(), val[0].as<uint32_t>());
-	CK(cudaGetLastError());
-	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key[0].as<uint32_t>(), key[1].as<uint32_t>(), val[0].as<uint32_t>(), val[1].as<uint32_t>(),
-		(int64_t)N, 0, (int)(2 * IDX_K), st));
-	index_offsets_kernel<<<grid_for(N + 1, 256), 256, 0, st>>>(key[1].as<uint32_t>(), (uint32_t)N, s.idx_off.as<uint32_t>());
-	CK(cudaGetLastError());
-	index_entry_kernel<<<grid_for(N, 256), 256, 0, st>>>(sd, s.idx_cum.as<uint32_t>(), val[1].as<uint32_t>(), (uint32_t)N, s.idx_entries.as<uint4>());
-	CK(cudaGetLastError());
+	s.idx_stale.assign(s.n, 0);
+	s.n_idx_stale = 0;
+	CK(s.d_idx_stale.ensure(std::max<size_t>(1, s.n)));
+	CK(cudaMemsetAsync(s.d_idx_stale.p, 0, std::max<size_t>(1, s.n), st));
 	CK(cudaStreamSynchronize(st));
 	s.idx_valid = true;
-	s.idx_n = (uint32_t)N;
+	s.idx_builds += 1;
+	s.idx_build_ms = (float)(Trace::now() - t0);
 	return 0;
 }
 
@@ -413,7 +448,7 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	if (rc) return fail(parent, "pcramp_gpu_create_worker: pcramp_gpu_create failed");
 	w->parent = parent;
 	w->seen_gen = parent->text_gen;
-	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index;
+	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index; w->idx_part_cap = parent->idx_part_cap;
 	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
 	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
 		const SeqSet &p = parent->sets[kind];
@@ -426,9 +461,16 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 		s.d_planes.alias(p.d_planes); s.d_grp_off.alias(p.d_grp_off); s.d_eos_pos.alias(p.d_eos_pos); s.d_eos_off.alias(p.d_eos_off);
 		s.d_weight.alias(p.d_weight); s.d_active.alias(p.d_active); s.d_tile_seq.alias(p.d_tile_seq); s.d_tile_x0.alias(p.d_tile_x0);
 		s.d_dirty_bits.alias(p.d_dirty_bits); s.d_dirty_seq.alias(p.d_dirty_seq); s.d_dirty_grp.alias(p.d_dirty_grp);
-		s.idx_entries.alias(p.idx_entries); s.idx_off.alias(p.idx_off); s.idx_cum.alias(p.idx_cum); s.idx_blk.alias(p.idx_blk);
+		s.idx_parts.clear();
+		for (const auto &pp : p.idx_parts) {
+			std::unique_ptr<SeqSet::IndexPart> q(new SeqSet::IndexPart());
+			q->seq_lo = pp->seq_lo; q->seq_hi = pp->seq_hi; q->n = pp->n;
+			q->entries.alias(pp->entries); q->off.alias(pp->off); q->cum.alias(pp->cum); q->blk.alias(pp->blk);
+			s.idx_parts.push_back(std::move(q));
+		}
+		s.idx_stale = p.idx_stale; s.n_idx_stale = p.n_idx_stale; s.d_idx_stale.alias(p.d_idx_stale);
+		s.idx_bytes = p.idx_bytes; s.idx_builds = p.idx_builds; s.idx_build_ms = p.idx_build_ms;
 		s.idx_valid = p.idx_valid; s.idx_failed = p.idx_failed || !p.idx_valid; // never build a private copy of the index
-		s.idx_n = p.idx_n;
 	}
 	*out = w;
 	return 0;
@@ -471,7 +513,7 @@ int pcramp_gpu_upload_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const
 	s.n = n;
 	s.db_valid = false;
 	if (kind == PCRAMP_MULTIPLEX) ctx->mpx_valid = false;
-	s.idx_valid = s.idx_failed = false; // the text index (index.cuh) is rebuilt on the next seeded scan
+	s.idx_drop(); // the text index (index.cuh) is rebuilt on the next seeded scan
 	s.n_entries = s.n_keys = 0;
 	s.len.assign(len, len + n);
 	s.plen.assign(n, 0);
@@ -607,7 +649,16 @@ int pcramp_gpu_split_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const 
 	touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
 	s.db_valid = false;
 	if (kind == PCRAMP_MULTIPLEX) ctx->mpx_valid = false;
-	s.idx_valid = s.idx_failed = false;
+	if (s.idx_valid) { // the index stays: the split sequences' entries are ignored from now on (SeqSet::idx_stale)
+		for (uint32_t q : touched)
+			if (!s.idx_stale[q]) {
+				s.idx_stale[q] = 1;
+				s.n_idx_stale++;
+			}
+		CK(cudaMemcpyAsync(s.d_idx_stale.p, s.idx_stale.data(), s.n, cudaMemcpyHostToDevice, ctx->stream));
+	} else {
+		s.idx_failed = false;
+	}
 	DevBuf d_nib;
 	CK(d_nib.ensure(nib.size() * 8));
 	CK(cudaMemcpyAsync(d_nib.p, nib.data(), nib.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -787,6 +838,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		return 0;
 	}
 	const SeqDev sd = s.dev();
+	Trace tr("select_words", st);
 	unsigned long long *d_cnt = nullptr;
 	CK(ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
 	d_cnt = ctx->d_counters.as<unsigned long long>();
@@ -881,65 +933,91 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		CK(cudaEventRecord(ctx->ev[0], st));
 		// (a0) seeded patterns whose segment prefixes are plain k-mers: the indexed scan (index.cuh)
 		bool use_idx = ctx->use_index && !ctx->force_brute && s.n_tiles && n_seeded;
+		// sequences split since the index was built and active again: below a few per cent of the text the table scan covers
+		// them (their index entries are ignored); above, the index is rebuilt
+		std::vector<uint32_t> stale_seq;
+		if (use_idx && s.idx_valid && s.n_idx_stale) {
+			uint64_t stale_pos = 0;
+			for (uint32_t i = 0; i < s.n; ++i)
+				if (s.idx_stale[i] && s.active[i]) {
+					stale_seq.push_back(i);
+					stale_pos += s.clen[i];
+				}
+			if (stale_pos * 16ull > stat.n_positions && !ctx->parent) { // > 1/16 of the active text (workers never rebuild: they keep the table scan)
+				s.idx_valid = false;
+				stale_seq.clear();
+			}
+		}
 		if (use_idx && !s.idx_valid && !s.idx_failed) {
+			tr.mark("patterns");
 			if (build_index(ctx, s)) return 1;
+			tr.mark("build_index");
 			CK(cudaEventRecord(ctx->ev[0], st)); // the one-time build is not part of the scan's time
 		}
 		use_idx = use_idx && s.idx_valid;
+		stat.ms_index_build = s.idx_build_ms;
+		stat.index_bytes = s.idx_bytes;
+		stat.n_index_builds = s.idx_builds;
+		stat.n_index_stale = (uint64_t)stale_seq.size();
 		if (use_idx) {
 			CK(ctx->d_idx_counters.ensure(32));
 			unsigned int *d_nq = ctx->d_idx_counters.as<unsigned int>();
-			TextIndex ix;
-			ix.entries = s.idx_entries.as<uint4>();
-			ix.off = s.idx_off.as<uint32_t>();
-			ix.cum = s.idx_cum.as<uint32_t>();
-			ix.blk = s.idx_blk.as<uint32_t>();
-			ix.n = s.idx_n;
-			IdxCandSink cs;
-			unsigned int h_idx[4] = {0, 0, 0, 0};
-			for (int grow = 0;; ++grow) { // queries and candidates awaiting resolution: grown if they overflow (sizes repeat from batch to batch)
-				// extended seeds expand a neighbour into up to IDX_EXT_MAX single-bucket queries: ~600 per 18-mer, fewer for longer primers
-				const uint64_t qcap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_queries.cap / sizeof(IdxQuery), tiny ? 1024ull : (uint64_t)n_seeded * 640u), 0xFFFFFFF0ull);
-				CK(ctx->d_idx_queries.ensure(qcap * sizeof(IdxQuery)));
-				CK(cudaMemsetAsync(ctx->d_idx_counters.p, 0, 32, st));
-				index_query_kernel<<<grid_for((uint64_t)n_seeded * IDX_SLOTS, 256), 256, 0, st>>>(ctx->d_part_mask.as<uint4>(),
-					ctx->d_part_meta2.as<uint32_t>(), n_seeded, s.idx_off.as<uint32_t>(), ctx->d_idx_queries.as<IdxQuery>(), (uint32_t)qcap, d_nq, d_nq + 1,
-					(unsigned long long *)(d_nq + 2));
+			stat.ms_index_kernel = 0.0f;
+			for (const auto &part : s.idx_parts) {
+				TextIndex ix;
+				ix.entries = part->entries.as<uint4>();
+				ix.off = part->off.as<uint32_t>();
+				ix.cum = part->cum.as<uint32_t>();
+				ix.blk = part->blk.as<uint32_t>();
+				ix.n = part->n;
+				ix.seq_lo = part->seq_lo;
+				ix.n_seq = part->seq_hi - part->seq_lo;
+				IdxCandSink cs;
+				unsigned int h_idx[4] = {0, 0, 0, 0};
+				for (int grow = 0;; ++grow) { // queries and candidates awaiting resolution: grown if they overflow (sizes repeat from batch to batch)
+					// extended seeds expand a neighbour into up to IDX_EXT_MAX single-bucket queries: ~600 per 18-mer, fewer for longer primers
+					const uint64_t qcap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_queries.cap / sizeof(IdxQuery), tiny ? 1024ull : (uint64_t)n_seeded * 640u), 0xFFFFFFF0ull);
+					CK(ctx->d_idx_queries.ensure(qcap * sizeof(IdxQuery)));
+					CK(cudaMemsetAsync(ctx->d_idx_counters.p, 0, 32, st));
+					index_query_kernel<<<grid_for((uint64_t)n_seeded * IDX_SLOTS, 256), 256, 0, st>>>(ctx->d_part_mask.as<uint4>(),
+						ctx->d_part_meta2.as<uint32_t>(), n_seeded, ix.off, ctx->d_idx_queries.as<IdxQuery>(), (uint32_t)qcap, d_nq, d_nq + 1,
+						(unsigned long long *)(d_nq + 2));
+					CK(cudaGetLastError());
+					const uint64_t ccap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_cand.cap / sizeof(IdxCand), tiny ? 1024ull : cap), 0xFFFFFFF0ull);
+					CK(ctx->d_idx_cand.ensure(ccap * sizeof(IdxCand)));
+					cs.buf = ctx->d_idx_cand.as<IdxCand>();
+					cs.count = d_nq + 4;
+					cs.cap = (uint32_t)ccap;
+					CK(cudaEventRecord(ctx->ev[8], st));
+					scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq, (uint32_t)qcap,
+						ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
+					CK(cudaGetLastError());
+					CK(cudaEventRecord(ctx->ev[9], st));
+					stat.kernel_launches++;
+					unsigned int n_c = 0;
+					CK(cudaMemcpyAsync(&n_c, d_nq + 4, 4, cudaMemcpyDeviceToHost, st));
+					CK(cudaMemcpyAsync(h_idx, d_nq, 16, cudaMemcpyDeviceToHost, st)); // query / entry counters: same round trip
+					CK(cudaStreamSynchronize(st));
+					if (n_c <= cs.cap && h_idx[0] <= qcap) break;
+					if (grow >= 3) return fail(ctx, "pcramp_gpu_select_words: index query / candidate buffers kept overflowing");
+					if (h_idx[0] > qcap) CK(ctx->d_idx_queries.ensure(((size_t)h_idx[0] + h_idx[0] / 8 + 1024) * sizeof(IdxQuery)));
+					if (n_c > cs.cap) CK(ctx->d_idx_cand.ensure(((size_t)n_c + n_c / 8 + 1024) * sizeof(IdxCand)));
+				}
+				stat.ms_index_kernel += ev_ms(ctx->ev[8], ctx->ev[9]);
+				index_hits_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, st>>>(sd, ix, cs, ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(),
+					s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, s.n_idx_stale ? s.d_idx_stale.as<uint8_t>() : nullptr, cand_bits, hs);
 				CK(cudaGetLastError());
-				const uint64_t ccap = std::min<uint64_t>(std::max<uint64_t>(ctx->d_idx_cand.cap / sizeof(IdxCand), tiny ? 1024ull : cap), 0xFFFFFFF0ull);
-				CK(ctx->d_idx_cand.ensure(ccap * sizeof(IdxCand)));
-				cs.buf = ctx->d_idx_cand.as<IdxCand>();
-				cs.count = d_nq + 4;
-				cs.cap = (uint32_t)ccap;
-				CK(cudaEventRecord(ctx->ev[8], st));
-				scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq, (uint32_t)qcap,
-					ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
-				CK(cudaGetLastError());
-				CK(cudaEventRecord(ctx->ev[9], st));
-				stat.kernel_launches++;
-				unsigned int n_c = 0;
-				CK(cudaMemcpyAsync(&n_c, d_nq + 4, 4, cudaMemcpyDeviceToHost, st));
-				CK(cudaMemcpyAsync(h_idx, d_nq, 16, cudaMemcpyDeviceToHost, st)); // query / entry counters: same round trip
-				CK(cudaStreamSynchronize(st));
-				stat.ms_index_kernel = ev_ms(ctx->ev[8], ctx->ev[9]);
-				if (n_c <= cs.cap && h_idx[0] <= qcap) break;
-				if (grow >= 3) return fail(ctx, "pcramp_gpu_select_words: index query / candidate buffers kept overflowing");
-				if (h_idx[0] > qcap) CK(ctx->d_idx_queries.ensure(((size_t)h_idx[0] + h_idx[0] / 8 + 1024) * sizeof(IdxQuery)));
-				if (n_c > cs.cap) CK(ctx->d_idx_cand.ensure(((size_t)n_c + n_c / 8 + 1024) * sizeof(IdxCand)));
+				stat.kernel_launches += 2;
+				stat.n_index_queries += h_idx[0];
+				stat.n_indexed = h_idx[1];
+				stat.n_index_entries += (uint64_t)h_idx[2] | ((uint64_t)h_idx[3] << 32);
 			}
-			index_hits_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, st>>>(sd, ix, cs, ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(),
-				s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, cand_bits, hs);
-			CK(cudaGetLastError());
-			stat.kernel_launches += 2;
-			stat.n_index_queries = h_idx[0];
-			stat.n_indexed = h_idx[1];
-			stat.n_index_entries = (uint64_t)h_idx[2] | ((uint64_t)h_idx[3] << 32);
 		}
-		const int skip_idx = use_idx ? 1 : 0;
-		// (a) the remaining seeded patterns, in chunks that fit shared memory
-		if (s.n_tiles && n_seeded) {
+		tr.mark("indexed scan");
+		// (a) the table-based seeded scan, in chunks of patterns that fit shared memory: the patterns the index did not take over
+		// every sequence, and -- when split sequences are active again -- EVERY seeded pattern over the tiles of those sequences
+		auto table_scan = [&](const uint32_t *d_tseq, const uint32_t *d_tx0, uint32_t n_tiles, int skip_idx, uint32_t done) -> int {
 			uint32_t chunk = std::min<uint32_t>(n_seeded, 4096u);
-			uint32_t done = (use_idx && stat.n_indexed == n_seeded) ? n_seeded : 0u; // nothing left for the table-based scan
 			while (done < n_seeded) {
 				const uint32_t cn = std::min<uint32_t>(chunk, n_seeded - done);
 				const uint4 *c_mask = ctx->d_part_mask.as<uint4>() + done;
@@ -990,15 +1068,38 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				ch.n_pat = cn;
 				ch.ecap = ecap;
 				ch.pcap = pcap;
-				const unsigned grid = (unsigned)std::min<uint64_t>(s.n_tiles, (uint64_t)ctx->sm_count);
-				scan_seed_kernel<<<grid, SEED_THREADS, smem, st>>>(sd, s.d_tile_seq.as<uint32_t>(), s.d_tile_x0.as<uint32_t>(), (uint32_t)s.n_tiles,
-					ctx->d_tile_counter.as<unsigned int>(), ch, s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, cand_bits, hs);
+				const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count);
+				scan_seed_kernel<<<grid, SEED_THREADS, smem, st>>>(sd, d_tseq, d_tx0, n_tiles, ctx->d_tile_counter.as<unsigned int>(), ch,
+					s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, cand_bits, hs);
 				CK(cudaGetLastError());
 				stat.kernel_launches += 3;
 				stat.n_seed_entries += n_ent;
 				done += cn;
 			}
-			// (b) the seeded patterns, brute force, on the groups whose text holds a degenerate base
+			return 0;
+		};
+		if (s.n_tiles && n_seeded) {
+			// nothing left for the table-based scan when the index took every seeded pattern
+			if (table_scan(s.d_tile_seq.as<uint32_t>(), s.d_tile_x0.as<uint32_t>(), (uint32_t)s.n_tiles, use_idx ? 1 : 0,
+					(use_idx && stat.n_indexed == n_seeded) ? n_seeded : 0u)) return 1;
+			if (use_idx && !stale_seq.empty()) {
+				std::vector<uint32_t> tseq, tx0;
+				for (uint32_t q : stale_seq)
+					for (uint64_t x = 0; x < s.clen[q]; x += SCAN_TILE) {
+						tseq.push_back(q);
+						tx0.push_back((uint32_t)x);
+					}
+				if (!tseq.empty()) {
+					CK(ctx->d_stale_tile_seq.ensure(tseq.size() * 4));
+					CK(ctx->d_stale_tile_x0.ensure(tx0.size() * 4));
+					CK(cudaMemcpyAsync(ctx->d_stale_tile_seq.p, tseq.data(), tseq.size() * 4, cudaMemcpyHostToDevice, st));
+					CK(cudaMemcpyAsync(ctx->d_stale_tile_x0.p, tx0.data(), tx0.size() * 4, cudaMemcpyHostToDevice, st));
+					CK(cudaStreamSynchronize(st)); // (the host vectors go out of scope)
+					// only the patterns the index took: the others were just scanned over every tile, these sequences included
+					if (table_scan(ctx->d_stale_tile_seq.as<uint32_t>(), ctx->d_stale_tile_x0.as<uint32_t>(), (uint32_t)tseq.size(), 2, 0u)) return 1;
+				}
+			}
+		// (b) the seeded patterns, brute force, on the groups whose text holds a degenerate base
 			if (s.n_dirty) {
 				scan_groups_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n_dirty + 7) / 8, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(sd,
 					s.d_dirty_seq.as<uint32_t>(), s.d_dirty_grp.as<uint32_t>(), s.n_dirty, ctx->d_part_mask.as<uint4>(),
@@ -1007,6 +1108,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				stat.kernel_launches++;
 			}
 		}
+		tr.mark("table scan + dirty groups");
 		CK(cudaEventRecord(ctx->ev[7], st));
 		// (c) patterns that cannot be seeded: brute force over every alignment
 		if (s.n_tiles && n_brute) {
@@ -1018,6 +1120,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 			stat.kernel_launches++;
 		}
 		CK(cudaEventRecord(ctx->ev[1], st));
+		tr.mark("brute-force scan");
 		{
 			bool edge_fst = ctx->use_fst != 0;
 			Fst fst;
@@ -1047,6 +1150,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		cap = n_hits + n_hits / 8 + 1024;
 	}
 	stat.n_hits = n_hits;
+	tr.mark("partial words");
 	CK(cudaEventRecord(ctx->ev[3], st));
 	if (n_hits == 0) {
 		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(2 * s.n + 1) * 4, st));
@@ -1113,6 +1217,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	const uint64_t n_flag = ctx->h_counters[0];
+	tr.mark("tiers");
 	if (n_flag == 0) {
 		CK(cudaMemsetAsync(s.seq_ent_off.p, 0, (size_t)(2 * s.n + 1) * 4, st));
 		CK(cudaStreamSynchronize(st));
@@ -1161,6 +1266,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		s.seq_ent_off.as<uint32_t>());
 	CK(cudaGetLastError());
 	stat.kernel_launches += 2;
+	tr.mark("unique + materialise");
 	CK(cudaEventRecord(ctx->ev[4], st));
 	ctx->pend_ms_db = true; // no host round trip here: pcramp_gpu_get_stats waits for the event when somebody asks
 	s.n_entries = n_ent;
@@ -1684,6 +1790,11 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_tier_table") == 0) { ctx->use_tier_table = value; return 0; }
 	if (strcmp(name, "use_fused_score") == 0) { ctx->use_fused_score = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }
+	if (strcmp(name, "index_part_positions") == 0) {
+		ctx->idx_part_cap = value > 0 ? (uint64_t)value : (1ull << 31);
+		for (auto &s : ctx->sets) s.idx_drop(); // rebuilt with the new part size on the next seeded scan
+		return 0;
+	}
 	return fail(ctx, std::string("pcramp_gpu_set_option: unknown option ") + name);
 }
 

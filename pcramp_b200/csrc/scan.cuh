@@ -620,14 +620,15 @@ __device__ __forceinline__ uint32_t seed_entries_needed(const uint4 &mask, uint3
 
 __device__ __forceinline__ bool idx_indexable(const uint4 &m, uint32_t meta2); // index.cuh
 
-// skip_indexable: patterns the indexed scan (index.cuh) takes are left out of the table
+// skip_indexable = 1: patterns the indexed scan (index.cuh) takes are left out of the table; 2: ONLY those go in (the pass over
+// sequences whose index entries are stale); 0: every pattern
 __global__ void seed_count_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta2, uint32_t n_pat, uint32_t *bucket_cnt,
 	int skip_indexable)
 {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n_pat) return;
 	const uint4 m = mask[p];
-	if (skip_indexable && idx_indexable(m, meta2[p])) return;
+	if (skip_indexable && (idx_indexable(m, meta2[p]) == (skip_indexable == 1))) return;
 	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u;
 	for (uint32_t i = 0; i < pieces; ++i) for_each_seed(m, n, pieces, i, [&](uint32_t code, uint32_t) { atomicAdd(bucket_cnt + code, 1u); });
 }
@@ -639,7 +640,7 @@ __global__ void seed_fill_kernel(const uint4 *__restrict__ mask, const uint32_t 
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n_pat) return;
 	const uint4 m = mask[p];
-	if (skip_indexable && idx_indexable(m, meta2[p])) return;
+	if (skip_indexable && (idx_indexable(m, meta2[p]) == (skip_indexable == 1))) return;
 	const uint32_t thr = meta[p] & 63u;
 	const uint32_t m2 = meta2[p], n = (m2 >> 10) & 63u, pieces = ((m2 >> 16) & 63u) + 1u;
 	for (uint32_t i = 0; i < pieces; ++i)

@@ -205,3 +205,65 @@ def test_bench_scale_four_workers_vs_reference(full, ref):
     finally:
         for c in ctxs[1:]:
             c.close()
+
+
+# ---- index lifecycle ----------------------------------------------------------------------------------------------------------------
+def test_index_in_several_parts(ref):
+    """a collection cut into several index parts (what a collection above 2^31 bases is): every part queried, same database"""
+    from pcramp_b200 import PcrampGpu
+    coll = synth.make_targets(61, 50, 12000, n_clades=4, between=0.12, within=0.05)
+    f, r = synth.make_pairs(62, coll, 300)
+    g = PcrampGpu(0)
+    try:
+        g.set_option("index_part_positions", 100000)              # 8 sequences per part -> 7 parts
+        st, ne = compare_all(g, ref, coll, f, r)
+        assert st["n_indexed"] > 0 and st["index_bytes"] > 7 * (1 << 26) and st["n_index_builds"] == 1
+    finally:
+        g.close()
+
+
+def test_splits_do_not_rebuild_the_index(ref):
+    """main.cpp:1008-1017 splits the targets an assay amplifies; the index is kept: the split sequences' entries are ignored and,
+    while such a sequence is still active, the table scan covers it.  Databases / coverage / bitsets == the reference with the same
+    splits, before and after the stale share grows past the rebuild threshold."""
+    from pcramp_b200 import PcrampGpu
+    coll = synth.make_targets(71, 80, 9000, n_clades=4, between=0.12, within=0.05)
+    f, r = synth.make_pairs(72, coll, 250)
+    rng = np.random.default_rng(73)
+    g = PcrampGpu(0)
+    try:
+        g.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
+        ref.set_sequences(coll)
+        g.select_words(TARGET, f, r, THR)                         # builds the index
+        assert g.stats()["n_index_builds"] == 1
+
+        def check(expect_builds, expect_stale):
+            ne, nk = g.select_words(TARGET, f, r, THR)
+            st = g.stats()
+            assert (ne, nk) == ref.select_words(f, r, THR)
+            for a, b in zip(canonical(*g.db_copy(TARGET)[:4]), ref.db()):
+                assert np.array_equal(a, b)
+            cov_r, bits_r = ref.score_pairs(f, r, 1.0, 0.9)
+            cov_g, _ = g.score_pairs(TARGET, f, r, THR, 1.0)
+            _, bits_g = g.score_pairs(TARGET, f, r, 1.0, 1.0)
+            assert np.array_equal(cov_g, cov_r) and np.array_equal(unpack_bits(bits_g, coll.n), bits_r)
+            assert st["n_index_builds"] == expect_builds and st["n_index_stale"] == expect_stale, st
+        # three sequences split (inside primer sites of some pairs, so that results change), all still active
+        for seq in (3, 17, 40):
+            for pos in rng.integers(100, 8900, size=6):
+                g.split_sequence(TARGET, seq, int(pos))
+                ref.split_sequence(seq, int(pos))
+        check(1, 3)
+        # one of them retired: its stale entries are simply never looked at
+        active = np.ones(coll.n, np.uint8)
+        active[17] = 0
+        g.set_active(TARGET, active)
+        ref.set_active(active)
+        check(1, 2)
+        # many more split and active: past 1/16 of the active text the index is rebuilt
+        for seq in range(50, 62):
+            g.split_sequence(TARGET, seq, 4000)
+            ref.split_sequence(seq, 4000)
+        check(2, 0)
+    finally:
+        g.close()
