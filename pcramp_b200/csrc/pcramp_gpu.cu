@@ -450,6 +450,7 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	w->seen_gen = parent->text_gen;
 	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index; w->idx_part_cap = parent->idx_part_cap;
 	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
+	w->use_entry_score = parent->use_entry_score;
 	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
 		const SeqSet &p = parent->sets[kind];
 		SeqSet &s = w->sets[kind];
@@ -1265,7 +1266,10 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	seq_offsets_kernel<<<grid_for(2ull * s.n + 1, 256), 256, 0, st>>>(s.e_seq.as<uint32_t>(), s.e_strand.as<uint32_t>(), n_ent, s.n,
 		s.seq_ent_off.as<uint32_t>());
 	CK(cudaGetLastError());
-	stat.kernel_launches += 2;
+	CK(s.seq_full_end.ensure((size_t)(2 * s.n + 1) * 4));
+	seq_full_end_kernel<<<grid_for(2ull * s.n, 256), 256, 0, st>>>(ctx->ent_id[0].as<uint64_t>(), n_ent, s.n, pos_bits, s.seq_full_end.as<uint32_t>());
+	CK(cudaGetLastError());
+	stat.kernel_launches += 3;
 	tr.mark("unique + materialise");
 	CK(cudaEventRecord(ctx->ev[4], st));
 	ctx->pend_ms_db = true; // no host round trip here: pcramp_gpu_get_stats waits for the event when somebody asks
@@ -1462,8 +1466,32 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 				CK(cudaGetLastError());
 				ctx->stats.kernel_launches++;
 			}
+			if (use_neigh && ctx->use_entry_score) {
+				// entry-driven scoring (score.cuh): neighbour slots per candidate, then one thread per plus-strand entry -- three launches,
+				// no list whose size the host would have to learn
+				const uint32_t n_olig = 2u * n_pairs;
+				CK(ctx->d_neigh_off.ensure(((size_t)s.n_cand + 1) * 4));
+				CK(ctx->d_neigh.ensure((size_t)s.n_cand * NEIGH_SLOTS * 4));
+				CK(cudaMemsetAsync(ctx->d_neigh_off.p, 0, ((size_t)s.n_cand + 1) * 4, st));
+				neigh_slots_kernel<<<dim3(grid_for(s.n_cand, 256), grid_for(n_olig, 256)), 256, 0, st>>>(s.c_planes.as<uint4>(), s.c_thr.as<uint32_t>(),
+					s.n_cand, d_member, n_olig, ctx->d_neigh.as<uint32_t>(), ctx->d_neigh_off.as<uint32_t>());
+				CK(cudaGetLastError());
+				if (variant)
+					score_entries_kernel<true><<<grid_for(s.n_entries, 128), 128, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(),
+						s.e_strand.as<uint32_t>(), s.e_seq.as<uint32_t>(), s.e_cand.as<uint32_t>(), s.n_entries, s.seq_ent_off.as<uint32_t>(),
+						s.seq_full_end.as<uint32_t>(), ctx->d_neigh.as<uint32_t>(), ctx->d_neigh_off.as<uint32_t>(), d_member, ctx->d_oligos.as<OligoDev>(),
+						n_olig, detect_threshold, amp_min, amp_max, taq, ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
+				else
+					score_entries_kernel<false><<<grid_for(s.n_entries, 128), 128, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(),
+						s.e_strand.as<uint32_t>(), s.e_seq.as<uint32_t>(), s.e_cand.as<uint32_t>(), s.n_entries, s.seq_ent_off.as<uint32_t>(),
+						s.seq_full_end.as<uint32_t>(), ctx->d_neigh.as<uint32_t>(), ctx->d_neigh_off.as<uint32_t>(), d_member, ctx->d_oligos.as<OligoDev>(),
+						n_olig, detect_threshold, amp_min, amp_max, taq, ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
+				CK(cudaGetLastError());
+				ctx->stats.kernel_launches += 2;
+				chunk_pairs = n_pairs;
+			}
 			if (use_fst || use_neigh) chunk_pairs = std::min(chunk_pairs, chunk_for(2ull * s.n)); // two bit rows per sequence
-			for (uint32_t p0 = 0; p0 < n_pairs; p0 += chunk_pairs) {
+			for (uint32_t p0 = (use_neigh && ctx->use_entry_score) ? n_pairs : 0u; p0 < n_pairs; p0 += chunk_pairs) {
 				const uint32_t pc = std::min<uint32_t>(chunk_pairs, n_pairs - p0), nw = (2u * pc + 31u) / 32u;
 				bool chunk_fst = use_fst;
 				if (use_neigh) {
@@ -1789,6 +1817,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_neighbours") == 0) { ctx->use_neigh = value; return 0; }
 	if (strcmp(name, "use_tier_table") == 0) { ctx->use_tier_table = value; return 0; }
 	if (strcmp(name, "use_fused_score") == 0) { ctx->use_fused_score = value; return 0; }
+	if (strcmp(name, "use_entry_score") == 0) { ctx->use_entry_score = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }
 	if (strcmp(name, "index_part_positions") == 0) {
 		ctx->idx_part_cap = value > 0 ? (uint64_t)value : (1ull << 31);

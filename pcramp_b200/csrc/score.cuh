@@ -387,6 +387,146 @@ entry_neigh_kernel(const unsigned long long *__restrict__ pairs, const uint32_t 
 	for (uint32_t i = __ldg(off + k), i1 = __ldg(off + k + 1u); i < i1; ++i) verify((uint32_t)pairs[i]);
 }
 
+// ---- entry-driven scoring (the default): no bit rows, no item list, no host round trip --------------------------------------------
+// A (pair, sequence) is amplified iff some plus-strand entry p and some minus-strand entry m of that sequence pass the test of
+// find_amplicon_match (pcr_assay.cpp:338-441) with {F on p, R on m} (pass 1) or {R on p, F on m} (pass 2) -- a predicate over
+// PAIRS OF ENTRIES, whatever order the reference meets them in.  So one thread takes one plus-strand entry, finds the oligos that
+// reach their match_words threshold on it among the neighbours of the entry's candidate (the filter above; a fixed number of
+// slots per candidate, filled with one atomic each -- a candidate with more neighbours, or an entry holding a degenerate text
+// base, is compared with every oligo), and for each such oligo looks for its partner among the minus-strand entries of the SAME
+// sequence that can close an amplicon: the full-window entries of a (sequence, strand) run are sorted by loc (entry ids sort by
+// position, db.cuh), and amplicon_max bounds m.loc - p.loc, so that is a binary search plus a handful of entries; the few
+// partial-word entries at the end of the run are all tried.  The exact test itself is amplicon_pass's, line by line.
+constexpr uint32_t NEIGH_SLOTS = 24u;
+
+__global__ void __launch_bounds__(256) neigh_slots_kernel(const uint4 *__restrict__ c_planes, const uint32_t *__restrict__ c_thr, uint32_t n_cand,
+	const OligoDev *__restrict__ olig, uint32_t n_olig, uint32_t *slots, uint32_t *cnt)
+{
+	__shared__ OligoDev s_o[256];
+	const uint32_t o0 = blockIdx.y * 256u;
+	const uint32_t no = min(256u, n_olig - o0);
+	if (threadIdx.x < no) s_o[threadIdx.x] = olig[o0 + threadIdx.x];
+	__syncthreads();
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_cand) return;
+	const uint4 kp = c_planes[k];
+	const uint32_t kocc = kp.x | kp.y | kp.z | kp.w;
+	const uint32_t kn = (uint32_t)__popc(kocc), kt = c_thr[k];
+	if (kt > kn) return; // a candidate that cannot reach its threshold produced no entry
+	const uint32_t e1 = kn - kt;
+	for (uint32_t j = 0; j < no; ++j) {
+		const OligoDev &o = s_o[j];
+		const uint32_t oocc = o.a | o.c | o.g | o.t;
+		const uint32_t on = (uint32_t)__popc(oocc), ot = o.packed & 255u;
+		if (ot > on) continue; // can never match (match_words compares against unsigned(size * thr^2))
+		const uint32_t inter = (kp.x & o.a) | (kp.y & o.c) | (kp.z & o.g) | (kp.w & o.t);
+		if ((uint32_t)__popc(kocc & oocc & ~inter) <= e1 + (on - ot)) {
+			const uint32_t at = atomicAdd(cnt + k, 1u);
+			if (at < NEIGH_SLOTS) slots[(size_t)k * NEIGH_SLOTS + at] = o0 + j;
+		}
+	}
+}
+
+// first entry of each (sequence, strand) run that is not a full-window entry (entry ids: seq | minus | type | pos, db.cuh)
+__global__ void seq_full_end_kernel(const uint64_t *__restrict__ entry_id, uint64_t n, uint32_t n_seq, uint32_t pb, uint32_t *full_end)
+{
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= 2u * n_seq) return;
+	const uint64_t want = ((uint64_t)k << 2) | 1ull; // (seq, minus) then type >= 1
+	uint64_t lo = 0, hi = n;
+	while (lo < hi) {
+		const uint64_t mid = (lo + hi) >> 1;
+		if ((entry_id[mid] >> pb) < want) lo = mid + 1; else hi = mid;
+	}
+	full_end[k] = (uint32_t)lo;
+}
+
+template <bool VARIANT>
+__global__ void __launch_bounds__(128)
+score_entries_kernel(SeqDev sd, const uint4 *__restrict__ e_planes, const int32_t *__restrict__ e_loc, const uint32_t *__restrict__ e_strand,
+	const uint32_t *__restrict__ e_seq, const uint32_t *__restrict__ e_cand, uint64_t n_ent, const uint32_t *__restrict__ seq_off2,
+	const uint32_t *__restrict__ full_end, const uint32_t *__restrict__ slots, const uint32_t *__restrict__ slot_cnt,
+	const OligoDev *__restrict__ member, const OligoDev *__restrict__ oligos, uint32_t n_olig, float detect, int amp_min, int amp_max, int taq,
+	uint32_t *bits_any, uint32_t *bits_pass1, uint32_t n_words_seq)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_ent) return;
+	if (__ldg(e_strand + e) != STRAND_PLUS) return;
+	const uint32_t seq = __ldg(e_seq + e);
+	if (!sd.active[seq]) return; // optimize.cpp:280-283
+	const uint32_t m0 = __ldg(seq_off2 + 2u * seq + 1u), m1 = __ldg(seq_off2 + 2u * seq + 2u);
+	if (m0 == m1) return; // no minus-strand entry: nothing can pair
+	const uint32_t mf = __ldg(full_end + 2u * seq + 1u);
+	const uint4 w = __ldg(e_planes + e);
+	ScoreEntry pe;
+	pe.a = w.x; pe.c = w.y; pe.g = w.z; pe.t = w.w;
+	pe.loc = __ldg(e_loc + e);
+	pe.strand = STRAND_PLUS;
+	const int L = (int)sd.len[seq];
+	auto try_oligo = [&](uint32_t id) {
+		const OligoDev Pb = member[id];
+		const int cpb = oligo_count(Pb, pe);
+		if (cpb < (int)(Pb.packed & 255u)) return;
+		const uint32_t partner = id ^ 1u;
+		const OligoDev Mb = member[partner];
+		const OligoDev P = VARIANT ? oligos[id] : Pb, M = VARIANT ? oligos[partner] : Mb;
+		const int cnt_p = VARIANT ? oligo_count(P, pe) : cpb;
+		const int p_start = (int)((Pb.packed >> 8) & 255u), p_stop = (int)((Pb.packed >> 16) & 255u);
+		const int m_thr = (int)(Mb.packed & 255u), m_start = (int)((Mb.packed >> 8) & 255u), m_stop = (int)((Mb.packed >> 16) & 255u);
+		const int plus_loc3 = pe.loc + p_stop; // sequence.h:67-75, plus strand
+		const float ident_p = oligo_identity(P, cnt_p, pe, taq);
+		bool found = false;
+		auto test = [&](uint32_t j) {
+			ScoreEntry m2;
+			const uint4 v = __ldg(e_planes + j);
+			m2.a = v.x; m2.c = v.y; m2.g = v.z; m2.t = v.w;
+			m2.loc = __ldg(e_loc + j);
+			m2.strand = STRAND_MINUS;
+			const int cm = oligo_count(M, m2);
+			if ((VARIANT ? oligo_count(Mb, m2) : cm) < m_thr) return;
+			const int minus_loc5 = m2.loc - m_stop; // sequence.h:57-65, minus strand
+			if (!(plus_loc3 < minus_loc5)) return;   // pcr_assay.cpp:368-371
+			int amp_start = pe.loc + p_start;
+			const int amp_stop = min(m2.loc - m_start, L - 1);
+			int amp_len = amp_stop - amp_start + 1;
+			if (amp_len < amp_min || amp_len > amp_max) return; // :383-392
+			if (amp_start < 0) { amp_len += amp_start; amp_start = 0; } // :412-416
+			if (amp_len >= 0 && !has_split_dev(sd, seq, amp_start, amp_len)) { // :418
+				const float ident_m = oligo_identity(M, cm, m2, taq);
+				if (__fsqrt_rn(__fmul_rn(ident_p, ident_m)) >= detect) found = true; // :292-294
+			}
+		};
+		// full-window entries: m.loc > plus_loc3 + m_stop, and amp_len <= amp_max bounds m.loc - p.loc by amp_max + 62 (both frame offsets
+		// are below 32; a clipped amplicon ends at L - 1 >= m.loc - 31)
+		{
+			const int lo_loc = plus_loc3 + m_stop, hi_loc = pe.loc + max(amp_max, 0) + 96;
+			uint32_t lo = m0, hi = mf;
+			while (lo < hi) {
+				const uint32_t mid = (lo + hi) >> 1;
+				if (__ldg(e_loc + mid) <= lo_loc) lo = mid + 1; else hi = mid;
+			}
+			for (uint32_t j = lo; j < mf && !found; ++j) {
+				if (__ldg(e_loc + j) > hi_loc) break;
+				test(j);
+			}
+		}
+		for (uint32_t j = mf; j < m1 && !found; ++j) test(j); // the partial words of the run
+		if (found) {
+			const uint32_t q = id >> 1, bit = 1u << (seq & 31u);
+			atomicOr(bits_any + (size_t)q * n_words_seq + (seq >> 5), bit);
+			if (!(id & 1u)) atomicOr(bits_pass1 + (size_t)q * n_words_seq + (seq >> 5), bit); // {F(+), R(-)}: pass 1 (pcr_assay.cpp:37-47)
+		}
+	};
+	const uint32_t multi = (w.x & w.y) | (w.x & w.z) | (w.x & w.w) | (w.y & w.z) | (w.y & w.w) | (w.z & w.w);
+	const uint32_t k = __ldg(e_cand + e);
+	const uint32_t nk = __ldg(slot_cnt + k);
+	if (multi || nk > NEIGH_SLOTS) { // a degenerate text base (the neighbour bound does not hold) or more neighbours than slots: everybody
+		for (uint32_t id = 0; id < n_olig; ++id) try_oligo(id);
+		return;
+	}
+	for (uint32_t i = 0; i < nk; ++i) try_oligo(__ldg(slots + (size_t)k * NEIGH_SLOTS + i));
+}
+
 struct ScoreItem;
 __global__ void seq_pairs_kernel(SeqDev sd, const uint32_t *__restrict__ seq_off2, const uint32_t *__restrict__ seqbits, uint32_t n_words, uint32_t n_pairs,
 	ScoreItem *items, unsigned int *n_items, uint32_t cap);

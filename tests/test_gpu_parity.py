@@ -406,11 +406,41 @@ def test_fused_sequence_scoring_equals_item_list(gpu, name):
     out = []
     for fused in (0, 1):
         gpu.set_option("use_fused_score", fused)
+        gpu.set_option("use_entry_score", 0)
         try:
             cov, bits = gpu.score_pairs(TARGET, sc.f, sc.r, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
             cov2, bits2 = gpu.score_pairs(TARGET, sc.r, np.roll(sc.f, 1, axis=0), sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
             out.append((cov, bits, cov2, bits2))
         finally:
             gpu.set_option("use_fused_score", 0)
+            gpu.set_option("use_entry_score", 1)
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_entry_driven_scoring_equals_item_list(gpu, name):
+    """pair scoring driven by the plus-strand entries (binary search for the partner among the minus-strand entries in amplicon
+    range; score.cuh, the default) == bit rows + item list + one warp per item: coverages and bitsets identical, for the oligos of
+    the database, for others, and in variant mode (the scoring of an optimisation move)"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+    out = []
+    rolled = np.roll(sc.f, 1, axis=0)
+    for entry in (0, 1):
+        gpu.set_option("use_entry_score", entry)
+        try:
+            a = gpu.score_pairs(TARGET, sc.f, sc.r, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+            b = gpu.score_pairs(TARGET, sc.r, rolled, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+            c = gpu.score_variants(TARGET, sc.f, sc.r, sc.f, np.roll(sc.r, 1, axis=0), sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1],
+                                   sc.taq)
+            d = gpu.score_pairs(TARGET, sc.f, sc.r, sc.search_threshold, sc.target_threshold, 0, 2000, sc.taq)
+            out.append(a + b + c + d)
+        finally:
+            gpu.set_option("use_entry_score", 1)
+    for x, y in zip(out[0], out[1]):
+        assert np.array_equal(np.asarray(x).view(np.uint32), np.asarray(y).view(np.uint32))
