@@ -104,6 +104,10 @@ struct SeqSet {
 	uint64_t n_entries = 0, n_keys = 0;
 	bool db_valid = false;
 	DevBuf e_hi, e_lo, e_planes, e_seq, e_loc, e_strand, e_perm, e_keyrank, seq_ent_off;
+	DevBuf e_id;         // (type | position) of every entry: what the words are re-derived from on demand (db.cuh words_kernel)
+	bool words_valid = false;
+	PackParams db_pp = {};
+	uint32_t db_pb = 0;
 	DevBuf seq_full_end; // per (sequence, strand) run: first entry that is not a full-window entry (score.cuh, entry-driven scoring)
 	DevBuf e_key, key_planes; // key index per entry (entry-id order), letter planes per unique word
 	// neighbour filter of pair scoring (score.cuh): per entry one candidate word that produced it, and the candidate words of
@@ -170,6 +174,8 @@ struct pcramp_gpu_ctx {
 	DevBuf d_idx_queries, d_idx_counters, d_idx_cand;
 	// scratch
 	DevBuf ent_cand[2], d_neigh, d_neigh_off, d_tier_best;
+	int use_seg_db = 1;      // segmented database build (db.cuh); 0 = radix sort + unique-by-key of the entry ids
+	DevBuf seg_cnt, seg_off, seg_cursor, seg_uniq, seg_full, seg_big;
 	int use_entry_score = 1; // pair scoring driven by the plus-strand entries (score.cuh); 0 = bit rows + item list
 	int use_neigh = 1, use_tier_table = 1, use_fused_score = 0; // score_seqbits_kernel: measured slower than the item list (0.65 vs 0.60 ms), kept as an option
 	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;

@@ -82,8 +82,9 @@ __device__ __forceinline__ bool fst_piece_seeds(const uint4 &p, uint32_t p0, uin
 }
 
 // pass 0 (ids == nullptr): bucket counts, combo flags, brute list; pass 1: fill ids (cursor = bucket starts, advanced)
+// ids_cap / overflow: the fill pass of a table whose size the host has not read (capacity from the previous batch)
 __global__ void fst_build_kernel(const uint4 *__restrict__ planes, const uint32_t *__restrict__ thr, uint32_t n, uint32_t *bucket, uint32_t *combo,
-	uint32_t *brute, uint32_t *n_brute, uint32_t *ids)
+	uint32_t *brute, uint32_t *n_brute, uint32_t *ids, uint32_t ids_cap, unsigned int *overflow)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -108,8 +109,10 @@ __global__ void fst_build_kernel(const uint4 *__restrict__ planes, const uint32_
 		fst_piece(len, pieces, k, o, q);
 		fst_piece_seeds(p, first + o, q, [&](uint32_t b) {
 			const uint32_t slot = atomicAdd(bucket + b, 1u);
-			if (ids) ids[slot] = i;
-			else combo[b >> 12] = 1u;
+			if (ids) {
+				if (slot < ids_cap) ids[slot] = i;
+				else if (overflow) atomicOr(overflow, 4u);
+			} else combo[b >> 12] = 1u;
 		});
 	}
 }

@@ -450,7 +450,7 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	w->seen_gen = parent->text_gen;
 	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index; w->idx_part_cap = parent->idx_part_cap;
 	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
-	w->use_entry_score = parent->use_entry_score;
+	w->use_entry_score = parent->use_entry_score; w->use_seg_db = parent->use_seg_db;
 	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
 		const SeqSet &p = parent->sets[kind];
 		SeqSet &s = w->sets[kind];
@@ -746,9 +746,29 @@ static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t 
 // The canonical (word, index, loc, strand) order of the database and its keys() numbering (read_only_multimap::sort,
 // pcramp.h:231-256).  Pair scoring on the GPU does not need it, so it is built on demand: by db_copy / keys_copy, by
 // select_words when the caller asks for the key count, and by the key-matrix fallback of pair scoring.
+// The words of the entries (and the (index, loc, strand) sort key): the segmented build does not write them -- pair scoring reads
+// letter planes -- so whoever needs them (canonical order, keys(), db_copy, the Smith-Waterman background test) asks here first.
+static int db_words(pcramp_gpu_ctx *ctx, SeqSet &s)
+{
+	if (s.words_valid || !s.db_valid) return 0;
+	const uint64_t n = s.n_entries;
+	CK(s.e_hi.ensure(std::max<uint64_t>(1, n) * 8));
+	CK(s.e_lo.ensure(std::max<uint64_t>(1, n) * 8));
+	CK(s.e_order.ensure(std::max<uint64_t>(1, n) * 8));
+	if (n) {
+		words_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s.dev(), s.db_pp, s.e_id.as<uint32_t>(), s.e_seq.as<uint32_t>(), s.e_strand.as<uint32_t>(), n,
+			s.db_pb, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), s.e_order.as<uint64_t>());
+		CK(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+	}
+	s.words_valid = true;
+	return 0;
+}
+
 static int db_finalize_keys(pcramp_gpu_ctx *ctx, SeqSet &s)
 {
 	if (s.keys_valid || !s.db_valid) return 0;
+	if (db_words(ctx, s)) return 1;
 	cudaStream_t st = ctx->stream;
 	const uint64_t n_ent = s.n_entries;
 	if (n_ent == 0) {
@@ -778,7 +798,7 @@ static int db_finalize_keys(pcramp_gpu_ctx *ctx, SeqSet &s)
 		CK(ctx->cub_tmp.ensure(tb));
 		CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, key_in, ctx->order_key[1].as<uint64_t>(), ctx->perm[src].as<uint32_t>(),
 			ctx->perm[dst].as<uint32_t>(), (int64_t)n_ent, 0, end_bit, st));
-		stat.kernel_launches += 8;
+		stat.kernel_launches += 10;
 		return 0;
 	};
 	if (sort_pass(s.e_order.as<uint64_t>(), (int)(34 + seq_bits), 0, 1)) return 1;
@@ -1163,28 +1183,106 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	// ---- validate, sort, tier ------------------------------------------------------------------
 	if (pp.gc_filter || s.any_degenerate) {
 		validate_hits_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(sd, pp, ctx->hit_key[0].as<uint64_t>(), ctx->hit_val[0].as<uint32_t>(), n_hits,
-			cand_bits);
+			cand_bits, nullptr);
 		CK(cudaGetLastError());
 		stat.kernel_launches++;
 	}
-	CK(ctx->ent_id[0].ensure(n_hits * 8));
-	CK(ctx->ent_id[1].ensure(n_hits * 8));
-	CK(ctx->ent_cand[0].ensure(n_hits * 4));
-	CK(ctx->ent_cand[1].ensure(n_hits * 4));
-	CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
 	uint32_t longest = 0;
 	for (uint32_t L : s.plen) longest = std::max(longest, L);
 	const uint32_t pos_bits = std::min<uint32_t>(32u, bits_for((uint64_t)longest + 64ull)); // hit positions are below plen + 32
 	const uint64_t tier_cells = (uint64_t)s.n * n_cand;
 	uint32_t tier_span = 0; // largest (size - threshold count) over the oligo sizes: the tiers a candidate can have
 	for (uint32_t sz = 1; sz <= 32u; ++sz) tier_span = std::max(tier_span, sz - std::min(sz, (uint32_t)((float)sz * threshold)));
+	s.db_pp = pp;
+	s.db_pb = pos_bits;
+	if (ctx->use_seg_db && ctx->use_tier_table && tier_span <= 7u && tier_cells <= (1ull << 31) && pos_bits + 2u <= 32u && n_hits < (1ull << 32)) {
+		// ---- segmented build (db.cuh): tiers, unique entries grouped by (sequence, strand) and sorted by position, planes -- no library
+		//      sort, every size on the device
+		const uint32_t n_seg = 2u * s.n;
+		const uint64_t words = tier_cells / 4 + 1;
+		CK(ctx->d_tier_best.ensure(words * 4));
+		CK(ctx->seg_cnt.ensure((size_t)(n_seg + 1) * 4));
+		CK(ctx->seg_off.ensure((size_t)(n_seg + 1) * 4));
+		CK(ctx->seg_cursor.ensure((size_t)(n_seg + 1) * 4));
+		CK(ctx->seg_uniq.ensure((size_t)(n_seg + 1) * 4));
+		CK(ctx->seg_full.ensure((size_t)(n_seg + 1) * 4));
+		CK(ctx->ent_id[0].ensure(n_hits * 8));
+		CK(ctx->ent_cand[0].ensure(n_hits * 4));
+		CK(s.e_planes.ensure(n_hits * 16)); // sized by the hits: the number of unique entries stays on the device until somebody asks
+		CK(s.e_seq.ensure(n_hits * 4));
+		CK(s.e_loc.ensure(n_hits * 4));
+		CK(s.e_strand.ensure(n_hits * 4));
+		CK(s.e_cand.ensure(n_hits * 4));
+		CK(s.e_id.ensure(n_hits * 4));
+		CK(s.seq_full_end.ensure((size_t)(n_seg + 1) * 4));
+		CK(s.c_planes.ensure(std::max<size_t>(1, n_cand) * 16));
+		CK(s.c_thr.ensure(std::max<size_t>(1, n_cand) * 4));
+		CK(cudaMemsetAsync(ctx->d_tier_best.p, 0, words * 4, st));
+		CK(cudaMemsetAsync(ctx->seg_cnt.p, 0, (size_t)(n_seg + 1) * 4, st));
+		CK(cudaMemsetAsync(ctx->seg_cursor.p, 0, (size_t)(n_seg + 1) * 4, st));
+		const unsigned gh = (unsigned)std::min<uint64_t>(grid_for(n_hits, 256), (uint64_t)ctx->sm_count * 32u);
+		const unsigned gs = (unsigned)std::min<uint64_t>(n_seg, (uint64_t)ctx->sm_count * 32u);
+		tier_mask_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), n_hits, cand_bits, n_cand, ctx->d_cand_thr.as<uint32_t>(),
+			ctx->d_tier_best.as<uint32_t>(), nullptr);
+		seg_count_kernel<<<gh, 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), d_cnt, n_hits, cand_bits, n_cand, ctx->d_cand_thr.as<uint32_t>(),
+			ctx->d_tier_best.as<uint32_t>(), ctx->seg_cnt.as<uint32_t>());
+		CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->seg_cnt.as<uint32_t>(), ctx->seg_off.as<uint32_t>(), (int)(n_seg + 1), st));
+		CK(ctx->cub_tmp.ensure(tmp_bytes));
+		CK(ctx->seg_big.ensure((size_t)(n_seg + 2) * 4));
+		CK(cudaMemsetAsync(ctx->seg_big.p, 0, 4, st)); // word 0: number of long segments; the list follows
+		CK(cudaMemsetAsync(ctx->seg_uniq.as<uint32_t>() + n_seg, 0, 4, st));
+		// (seg_cnt[n_seg] = 0: the scan's last output is the total)
+		CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->seg_cnt.as<uint32_t>(), ctx->seg_off.as<uint32_t>(), (int)(n_seg + 1), st));
+		seg_scatter_kernel<<<gh, 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), ctx->hit_val[0].as<uint32_t>(), d_cnt, n_hits, cand_bits, n_cand,
+			ctx->d_cand_thr.as<uint32_t>(), ctx->d_tier_best.as<uint32_t>(), pos_bits, ctx->seg_off.as<uint32_t>(), ctx->seg_cursor.as<uint32_t>(),
+			ctx->ent_id[0].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>());
+		seg_sort_small_kernel<<<(unsigned)std::min<uint64_t>(grid_for(n_seg, SEG_WARPS), (uint64_t)ctx->sm_count * 16u), SEG_WARPS * 32u, 0, st>>>(
+			ctx->seg_off.as<uint32_t>(), n_seg, ctx->ent_id[0].as<uint64_t>(), pos_bits, ctx->seg_uniq.as<uint32_t>(), ctx->seg_full.as<uint32_t>(),
+			ctx->seg_big.as<uint32_t>() + 1, ctx->seg_big.as<unsigned int>());
+		seg_sort_big_kernel<<<(unsigned)ctx->sm_count * 2u, SEG_BIG_THREADS, 0, st>>>(ctx->seg_off.as<uint32_t>(), ctx->seg_big.as<uint32_t>() + 1,
+			ctx->seg_big.as<unsigned int>(), ctx->ent_id[0].as<uint64_t>(), pos_bits, ctx->seg_uniq.as<uint32_t>(), ctx->seg_full.as<uint32_t>());
+		CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->seg_uniq.as<uint32_t>(), s.seq_ent_off.as<uint32_t>(), (int)(n_seg + 1), st));
+		seg_materialise_kernel<<<gh, 256, 0, st>>>(sd, pp, ctx->seg_off.as<uint32_t>(), s.seq_ent_off.as<uint32_t>(), ctx->seg_full.as<uint32_t>(), n_seg,
+			ctx->ent_id[0].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>(), pos_bits, s.e_planes.as<uint4>(), s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(),
+			s.e_strand.as<uint32_t>(), s.e_cand.as<uint32_t>(), s.e_id.as<uint32_t>(), s.seq_full_end.as<uint32_t>());
+		CK(cudaGetLastError());
+		stat.kernel_launches += 10;
+		CK(cudaMemcpyAsync(s.c_planes.p, ctx->d_cand_words.p, (size_t)n_cand * 16, cudaMemcpyDeviceToDevice, st));
+		CK(cudaMemcpyAsync(s.c_thr.p, ctx->d_cand_thr.p, (size_t)n_cand * 4, cudaMemcpyDeviceToDevice, st));
+		s.n_cand = n_cand;
+		uint32_t n_ent32 = 0;
+		CK(cudaMemcpyAsync(&n_ent32, s.seq_ent_off.as<uint32_t>() + n_seg, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		tr.mark("segmented database");
+		CK(cudaEventRecord(ctx->ev[4], st));
+		ctx->pend_ms_db = true;
+		s.n_entries = n_ent32;
+		s.n_keys = 0;
+		s.keys_valid = false;
+		s.words_valid = false; // e_hi / e_lo / e_order on demand (db_words)
+		s.seq_bits = seq_bits;
+		s.db_valid = true;
+		stat.n_entries = n_ent32;
+		if (n_entries_out) *n_entries_out = n_ent32;
+		if (n_keys_out) {
+			if (db_finalize_keys(ctx, s)) return 1;
+			stat.n_keys = s.n_keys;
+			*n_keys_out = s.n_keys;
+		}
+		return 0;
+	}
+	CK(ctx->ent_id[0].ensure(n_hits * 8));
+	CK(ctx->ent_id[1].ensure(n_hits * 8));
+	CK(ctx->ent_cand[0].ensure(n_hits * 4));
+	CK(ctx->ent_cand[1].ensure(n_hits * 4));
+	CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
 	if (ctx->use_tier_table && tier_span <= 7u && tier_cells <= (1ull << 31)) {
 		// best tier per (sequence, candidate) through a byte-per-cell table of tier bits (db.cuh): no sort of the hit list
 		const uint64_t words = tier_cells / 4 + 1;
 		CK(ctx->d_tier_best.ensure(words * 4));
 		CK(cudaMemsetAsync(ctx->d_tier_best.p, 0, words * 4, st));
 		tier_mask_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), n_hits, cand_bits, n_cand, ctx->d_cand_thr.as<uint32_t>(),
-			ctx->d_tier_best.as<uint32_t>());
+			ctx->d_tier_best.as<uint32_t>(), nullptr);
 		tier_mask_select_kernel<<<grid_for(n_hits, 256), 256, 0, st>>>(ctx->hit_key[0].as<uint64_t>(), ctx->hit_val[0].as<uint32_t>(), n_hits, cand_bits,
 			n_cand, ctx->d_cand_thr.as<uint32_t>(), ctx->d_tier_best.as<uint32_t>(), pos_bits, ctx->ent_id[0].as<uint64_t>(),
 			ctx->ent_cand[0].as<uint32_t>(), d_cnt);
@@ -1276,6 +1374,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	s.n_entries = n_ent;
 	s.n_keys = 0;
 	s.keys_valid = false;
+	s.words_valid = true;
 	s.seq_bits = seq_bits;
 	s.db_valid = true;
 	stat.n_entries = n_ent;
@@ -1379,7 +1478,7 @@ static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t 
 	CK(cudaMemsetAsync(ctx->d_fst_combo.p, 0, FST_COMBOS * 4, st));
 	CK(cudaMemsetAsync(ctx->d_fst_nbrute.p, 0, 16, st));
 	fst_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(d_planes, d_thr, n, ctx->d_fst_cnt.as<uint32_t>(), ctx->d_fst_combo.as<uint32_t>(),
-		ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), nullptr);
+		ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), nullptr, 0u, nullptr);
 	CK(cudaGetLastError());
 	fst_combo_list_kernel<<<1, 32, 0, st>>>(ctx->d_fst_combo.as<uint32_t>());
 	CK(cudaGetLastError());
@@ -1394,7 +1493,7 @@ static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t 
 	CK(cudaStreamSynchronize(st));
 	CK(ctx->d_fst_ids.ensure(std::max<size_t>(1, total) * 4));
 	fst_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(d_planes, d_thr, n, ctx->d_fst_cursor.as<uint32_t>(), ctx->d_fst_combo.as<uint32_t>(),
-		ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), ctx->d_fst_ids.as<uint32_t>());
+		ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), ctx->d_fst_ids.as<uint32_t>(), 0xFFFFFFFFu, nullptr);
 	CK(cudaGetLastError());
 	ctx->stats.kernel_launches += 5;
 	t.planes = d_planes;
@@ -1818,6 +1917,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_tier_table") == 0) { ctx->use_tier_table = value; return 0; }
 	if (strcmp(name, "use_fused_score") == 0) { ctx->use_fused_score = value; return 0; }
 	if (strcmp(name, "use_entry_score") == 0) { ctx->use_entry_score = value; return 0; }
+	if (strcmp(name, "use_segmented_db") == 0) { ctx->use_seg_db = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }
 	if (strcmp(name, "index_part_positions") == 0) {
 		ctx->idx_part_cap = value > 0 ? (uint64_t)value : (1ull << 31);

@@ -154,15 +154,13 @@ __device__ __forceinline__ bool gc_pass(uint32_t num_gc, const PackParams &pp)
 	return !(fraction < pp.min_gc || fraction > pp.max_gc);
 }
 
-// One pack() entry pair, identified by (type, pos).  Returns false when the event emits nothing
-// (too short, filtered).  plus/minus are the two database words, loc_p/loc_m their WordMatch.loc.
-__device__ inline bool pack_entry(const SeqDev &sd, uint32_t seq, uint32_t type, uint32_t pos, const PackParams &pp,
-	W128 &plus, W128 &minus, int &loc_p, int &loc_m)
+// Geometry of one pack() event, identified by (type, pos): the n bases starting at compressed position `first`, the frame shift
+// st of the word, the two WordMatch.loc values and where the G+C window ends.  false: the event emits nothing (too short).
+__device__ inline bool pack_geom(const SeqDev &sd, uint32_t seq, uint32_t type, uint32_t pos, const PackParams &pp, uint32_t &n, uint32_t &first,
+	int &st, int &loc_p, int &loc_m, int64_t &gc_end)
 {
 	const uint32_t L = sd.plen[seq], Lc = sd.clen[seq];
-	uint32_t n, first;
-	int st;
-	int64_t gc_end = -1; // raw index the GC window ends at; -2 = tail rule
+	gc_end = -1; // raw index the GC window ends at; -2 = tail rule
 	if (type == ENT_FULL) {
 		if (pos < 31u || pos >= Lc) return false;
 		n = 32; first = pos - 31u; st = 0;
@@ -200,6 +198,19 @@ __device__ inline bool pack_entry(const SeqDev &sd, uint32_t seq, uint32_t type,
 		loc_m = (int)L - 1 + st;
 		gc_end = -2;
 	}
+	return true;
+}
+
+// One pack() entry pair, identified by (type, pos).  Returns false when the event emits nothing
+// (too short, filtered).  plus/minus are the two database words, loc_p/loc_m their WordMatch.loc.
+__device__ inline bool pack_entry(const SeqDev &sd, uint32_t seq, uint32_t type, uint32_t pos, const PackParams &pp,
+	W128 &plus, W128 &minus, int &loc_p, int &loc_m)
+{
+	const uint32_t L = sd.plen[seq];
+	uint32_t n, first;
+	int st;
+	int64_t gc_end;
+	if (!pack_geom(sd, seq, type, pos, pp, n, first, st, loc_p, loc_m, gc_end)) return false;
 	if (pp.gc_filter) {
 		uint32_t num_gc;
 		if (gc_end == -2) { // tail: one pop when 32 nibbles were buffered, then frozen (sequence.cpp:204-222)
@@ -215,6 +226,36 @@ __device__ inline bool pack_entry(const SeqDev &sd, uint32_t seq, uint32_t type,
 	plus = w_shr(left, st);
 	minus = w_shr(w_complement(left), st); // complement() left-justifies; centring gives the same st
 	return true;
+}
+
+// The letter planes (word128.cuh w_planes: bit k = word position k) and loc of ONE strand's word of an entry that is known to
+// pass the filters -- what the database build needs.  The window's planes come straight off the collection's bit-planes (two
+// 16-byte loads, four funnel shifts); the reverse complement is a bit reversal with A <-> T, C <-> G; no nibble form in between.
+__device__ inline void pack_entry_planes(const SeqDev &sd, uint32_t seq, uint32_t type, uint32_t pos, const PackParams &pp, bool minus, Planes4 &out,
+	int &loc)
+{
+	uint32_t n = 0, first = 0;
+	int st = 0, lp = 0, lm = 0;
+	int64_t gc_end;
+	out.a = out.c = out.g = out.t = 0u;
+	loc = 0;
+	if (!pack_geom(sd, seq, type, pos, pp, n, first, st, lp, lm, gc_end)) return;
+	const uint64_t gb = sd.grp_off[seq];
+	const uint32_t ngrp = (uint32_t)(sd.grp_off[seq + 1] - gb), g = first >> 5, sh = first & 31u;
+	const uint4 z = make_uint4(0, 0, 0, 0);
+	const uint4 p0 = g < ngrp ? __ldg(sd.planes + gb + g) : z;
+	const uint4 p1 = g + 1u < ngrp ? __ldg(sd.planes + gb + g + 1u) : z;
+	const uint32_t keep = n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
+	const uint32_t a = __funnelshift_r(p0.x, p1.x, sh) & keep, c = __funnelshift_r(p0.y, p1.y, sh) & keep;
+	const uint32_t gg = __funnelshift_r(p0.z, p1.z, sh) & keep, t = __funnelshift_r(p0.w, p1.w, sh) & keep;
+	if (!minus) {
+		out.a = a << st; out.c = c << st; out.g = gg << st; out.t = t << st;
+		loc = lp;
+	} else { // word position k of the complement = complement of base n - 1 - k
+		const uint32_t r = 32u - n;
+		out.a = (__brev(t) >> r) << st; out.c = (__brev(gg) >> r) << st; out.g = (__brev(c) >> r) << st; out.t = (__brev(a) >> r) << st;
+		loc = lm;
+	}
 }
 
 #endif // __CUDACC__

@@ -438,6 +438,7 @@ int pcramp_gpu_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f
 	if (!n_pairs || !s.n) return 0;
 	memset(bitsets, 0, (size_t)n_pairs * n_words * 4);
 	if (!s.n_entries) return 0; // collect_background_candidates does nothing on an empty database (assay.h:411-421)
+	if (db_words(ctx, s)) return 1; // the alignments read the words themselves
 	DevBuf d_f, d_r, d_ol, d_bits;
 	CK(d_f.ensure((size_t)n_pairs * 16));
 	CK(d_r.ensure((size_t)n_pairs * 16));

@@ -14,6 +14,7 @@ from tests.harness import canonical
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+THR_09 = float(np.float32(1.0) * np.float32(0.9))
 SCENARIOS = {fn.__name__[2:]: fn for fn in scenarios.ALL}
 
 
@@ -444,3 +445,56 @@ def test_entry_driven_scoring_equals_item_list(gpu, name):
             gpu.set_option("use_entry_score", 1)
     for x, y in zip(out[0], out[1]):
         assert np.array_equal(np.asarray(x).view(np.uint32), np.asarray(y).view(np.uint32))
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_segmented_database_equals_sorted_ids(gpu, name):
+    """the database built from per-(sequence, strand) segments sorted in shared memory (db.cuh, the default) == the radix sort +
+    unique-by-key of the entry ids: same entries, keys, coverages and bitsets (the words are materialised on demand in the first)"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    out = []
+    for seg in (0, 1):
+        gpu.set_option("use_segmented_db", seg)
+        try:
+            g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+            cov, bits = gpu.score_pairs(TARGET, sc.f, sc.r, sc.search_threshold, sc.target_threshold, sc.amp[0], sc.amp[1], sc.taq)
+            out.append(_db_tuple(gpu) + (cov, bits))
+        finally:
+            gpu.set_option("use_segmented_db", 1)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
+def test_segments_longer_than_shared_memory(gpu, oracle):
+    """a tandem repeat: thousands of hits in ONE (sequence, strand) segment -- the in-place global-memory sort of db.cuh -- next to
+    ordinary sequences; against the oracle and the sorted-id build"""
+    rng = np.random.default_rng(91)
+    unit = synth.CODE[rng.integers(0, 4, size=120)]
+    rep = np.tile(unit, 450)                                    # 54 kb of one 120-base unit
+    base = synth.make_targets(92, 6, 4000, n_clades=2, between=0.1, within=0.03)
+    coll = synth.Collection([rep] + [base.codes(i) for i in range(base.n)])
+    f, r = synth.make_pairs(93, synth.Collection([np.tile(unit, 4)]), 12)
+    f2, r2 = synth.make_pairs(94, base, 20)
+    f, r = np.concatenate([f, f2]), np.concatenate([r, r2])
+    g = GpuChecker(gpu)
+    g.set_sequences(coll)
+    oracle.set_sequences(coll)
+    ne, nk = g.select_words(f, r, THR_09)
+    assert (ne, nk) == oracle.select_words(f, r, THR_09) and ne > 5000
+    for a, c in zip(g.db(), oracle.db()):
+        assert np.array_equal(a, c)
+    cov_o, bits_o = oracle.score_pairs(f, r, THR_09, 1.0, 80, 200, False)
+    cov_g, bits_g = g.score_pairs(f, r, THR_09, 1.0, 80, 200, False)
+    assert np.array_equal(bits_g, bits_o) and np.array_equal(cov_g, cov_o)
+    seg = _db_tuple(gpu)
+    gpu.set_option("use_segmented_db", 0)
+    try:
+        g.select_words(f, r, THR_09)
+        for a, b in zip(seg, _db_tuple(gpu)):
+            assert np.array_equal(a, b)
+    finally:
+        gpu.set_option("use_segmented_db", 1)
