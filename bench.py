@@ -564,7 +564,7 @@ def target_sharded_leg(a, factory, rank, world, local, dist, torch, thr):
 
         def step(b):
             g.set_batch(b * P, P)
-            g.select_words_staged(TARGET, thr, want_keys=False)
+            g.select_words_staged(TARGET, thr, want_keys=False, want_entries=False)
             g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
             g.exchange_step(TARGET)
 
@@ -767,7 +767,7 @@ def run_b200(a):
     def step_resident(b, timed, k=0):
         c = ctxs[k]
         c.set_batch(b * P, P)
-        c.select_words_staged(TARGET, thr, want_keys=False)   # keys() is only for hosts that walk the database themselves
+        c.select_words_staged(TARGET, thr, want_keys=False, want_entries=False)   # sizes / keys() only for hosts that walk the database
         c.score_pairs_staged(TARGET, thr, float(TARGET_THR))
         account(c, timed)
         if p2p:
@@ -781,14 +781,14 @@ def run_b200(a):
         host_cov_k, host_bits_k = host_cov[k], host_bits[k]
         if not by_targets:
             c = ctxs[k]
-            c.select_words(TARGET, fb, rb, thr, want_keys=False)
+            c.select_words(TARGET, fb, rb, thr, want_keys=False, want_entries=False)
             c.score_pairs(TARGET, fb, rb, thr, float(TARGET_THR), out=(host_cov_k.numpy(), host_bits_k.numpy().view(np.uint32)))
             if timed:
                 with lock:
                     launches[0] += c.stats()["kernel_launches"]
         elif p2p:
             g.stage_pairs(fb, rb)
-            g.select_words_staged(TARGET, thr, want_keys=False)
+            g.select_words_staged(TARGET, thr, want_keys=False, want_entries=False)
             g.score_pairs_staged(TARGET, thr, float(TARGET_THR))
             g.exchange_step(TARGET)
             cov, bits = g.exchange_fetch(P)

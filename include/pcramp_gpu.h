@@ -81,7 +81,14 @@ int pcramp_gpu_pack(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pack_m
 int pcramp_gpu_select_words(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f, const uint64_t *r,
 	uint32_t n_pairs, int optimize_5, int optimize_3, float threshold, uint32_t pack_max_degen,
 	float pack_min_gc, float pack_max_gc, uint32_t min_oligo_length, uint64_t *n_entries, uint64_t *n_keys);
-/* n_keys may be NULL in the two calls above: the canonical order of the database and its keys() numbering are only
+/* The fast form.  Batch after batch of one shape (same number of pairs, thresholds and pack parameters, no --optimize.5 / .3
+ * families) is the normal load: a sweep, a design run, a sharded job.  After one batch of a shape has gone through the general
+ * form with every pattern resolved by the one-part text index, the following ones are launched without the host reading anything
+ * back -- sizes from the previous batch, counts in device memory, the partial-word scan on a second stream beside the indexed scan
+ * -- and verified from ONE small read-back when the database is next needed (pair scoring, a copy, the statistics, n_entries /
+ * n_keys != NULL here).  A batch whose assumptions did not hold (a buffer too small, a pattern the index cannot take) is run again
+ * in the general form, so results are the same either way; option "use_fast_path" = 0 switches the fast form off.
+ * n_keys may be NULL in the two calls above: the canonical order of the database and its keys() numbering are only
  * needed by a host that still walks the database itself; pair scoring on the GPU does not use them, and they are then
  * built on demand (by the calls below). */
 int pcramp_gpu_db_size(pcramp_gpu_ctx *ctx, int kind, uint64_t *n_entries, uint64_t *n_keys);
@@ -481,6 +488,8 @@ typedef struct pcramp_gpu_stats {
 	uint64_t index_bytes;     /* device memory the text index holds */
 	uint64_t n_index_builds;  /* builds of this collection's index so far */
 	uint64_t n_index_stale;   /* sequences split since the build and active again: covered by the table scan in this call */
+	uint64_t n_fast;          /* select_words batches of this ctx that ran in the fast form (no host round trip inside) so far */
+	uint64_t n_fast_redo;     /* ... of those, batches whose verification failed and that were run again in the general form */
 } pcramp_gpu_stats;
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
 /* Tuning / testing switches.  "force_brute_scan" = 1 sends every pattern through the brute-force scan kernel;

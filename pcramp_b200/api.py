@@ -48,6 +48,8 @@ class Stats(ctypes.Structure):
         ("index_bytes", ctypes.c_uint64),
         ("n_index_builds", ctypes.c_uint64),
         ("n_index_stale", ctypes.c_uint64),
+        ("n_fast", ctypes.c_uint64),
+        ("n_fast_redo", ctypes.c_uint64),
     ]
 
     def as_dict(self):
@@ -434,15 +436,17 @@ class PcrampGpu:
 
     # ---- seed scan ----------------------------------------------------------------------------
     def select_words(self, kind, f, r, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0,
-                     pack_max_gc=1.0, min_oligo_length=18, want_keys=True):
-        """-> (entries, keys); want_keys=False skips the canonical order / keys() numbering (keys = None)"""
+                     pack_max_gc=1.0, min_oligo_length=18, want_keys=True, want_entries=True):
+        """-> (entries, keys); want_keys=False skips the canonical order / keys() numbering (keys = None); want_entries=False does not
+        ask for the entry count either (entries = None), which lets a batch in the fast form return without a host round trip"""
         f, r = _words(f), _words(r)
         ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
         self._ck(self.lib.pcramp_gpu_select_words(self.h, kind, _ptr(f, _u64p), _ptr(r, _u64p), len(f), int(optimize_5), int(optimize_3),
                                                   float(threshold), int(pack_max_degen), float(pack_min_gc), float(pack_max_gc),
-                                                  int(min_oligo_length), ctypes.byref(ne), ctypes.byref(nk) if want_keys else None))
+                                                  int(min_oligo_length), ctypes.byref(ne) if want_entries else None,
+                                                  ctypes.byref(nk) if want_keys else None))
         self.n_pairs = len(f)
-        return ne.value, (nk.value if want_keys else None)
+        return (ne.value if want_entries else None), (nk.value if want_keys else None)
 
     def db_size(self, kind):
         ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
@@ -598,12 +602,12 @@ class PcrampGpu:
         self.n_pairs = int(count)
 
     def select_words_staged(self, kind, threshold, optimize_5=False, optimize_3=False, pack_max_degen=256, pack_min_gc=0.0, pack_max_gc=1.0,
-                            min_oligo_length=18, want_keys=True):
+                            min_oligo_length=18, want_keys=True, want_entries=True):
         ne, nk = ctypes.c_uint64(), ctypes.c_uint64()
         self._ck(self.lib.pcramp_gpu_select_words_staged(self.h, kind, int(optimize_5), int(optimize_3), float(threshold), int(pack_max_degen),
-                                                         float(pack_min_gc), float(pack_max_gc), int(min_oligo_length), ctypes.byref(ne),
-                                                         ctypes.byref(nk) if want_keys else None))
-        return ne.value, (nk.value if want_keys else None)
+                                                         float(pack_min_gc), float(pack_max_gc), int(min_oligo_length),
+                                                         ctypes.byref(ne) if want_entries else None, ctypes.byref(nk) if want_keys else None))
+        return (ne.value if want_entries else None), (nk.value if want_keys else None)
 
     def score_pairs_staged(self, kind, search_threshold, detect_threshold, amplicon_min=80, amplicon_max=200, use_taq_mama=False):
         self._ck(self.lib.pcramp_gpu_score_pairs_staged(self.h, kind, float(search_threshold), float(detect_threshold), int(amplicon_min),

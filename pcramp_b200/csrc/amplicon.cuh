@@ -223,6 +223,7 @@ int pcramp_gpu_unique_amplicons(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f
 	CK(cudaSetDevice(ctx->device));
 	SeqSet &s = ctx->sets[kind];
 	cudaStream_t st = ctx->stream;
+	if (fast_resolve(ctx)) return 1;
 	if (!s.db_valid) return fail(ctx, "pcramp_gpu_unique_amplicons: no database (call pcramp_gpu_select_words first)");
 	ctx->amp_kind = -1;
 	ctx->amp_n_rec = ctx->amp_n_uniq = ctx->amp_n_bases = 0;

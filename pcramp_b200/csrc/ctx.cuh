@@ -168,6 +168,29 @@ struct pcramp_gpu_ctx {
 	int max_smem_optin = 0;
 	int force_brute = 0;
 	int use_index = 1;
+	// the speculative, host-round-trip-free form of select_words (pcramp_gpu.cu select_words_fast): sizes come from the previous
+	// batch of the same shape, everything is verified from ONE read-back when somebody needs the result
+	struct FastHint {
+		bool ok = false;
+		uint32_t n_pairs = 0;
+		float threshold = 0.0f;
+		pcr::PackParams pp = {};
+		uint64_t hit_cap = 0, q_cap = 0, c_cap = 0, fst_cap = 0;
+	} fast_hint[PCRAMP_NUM_KINDS];
+	struct FastPending {
+		bool active = false;
+		int kind = 0;
+		float threshold = 0.0f;
+		pcr::PackParams pp = {};
+		uint32_t n_pat = 0, n_seg = 0;
+		uint64_t hit_cap = 0, q_cap = 0, c_cap = 0;
+	} fast_pending;
+	int use_fast = 1;
+	uint64_t n_fast = 0, n_fast_redo = 0; // batches that took the fast form; of those, batches whose verification failed (re-run in the general form)
+	cudaStream_t stream2 = nullptr;       // the partial-word scan runs beside the indexed scan
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
+	unsigned long long *h_fast = nullptr; // pinned: {flags, n_hits, n_queries, n_indexed, n_index_entries, n_candidates, n_entries}
+	DevBuf d_fast;
 	int tiny_buffers = 0; // testing hook (pcramp_gpu_set_option): growable buffers start far too small
 	uint64_t idx_part_cap = 1ull << 31; // positions per part of the text index (option "index_part_positions": small values for the tests)
 	DevBuf idx_key[2], idx_val[2], idx_tmp, d_stale_tile_seq, d_stale_tile_x0; // build scratch (kept while small), tiles of stale sequences
@@ -178,7 +201,7 @@ struct pcramp_gpu_ctx {
 	DevBuf seg_cnt, seg_off, seg_cursor, seg_uniq, seg_full, seg_big;
 	int use_entry_score = 1; // pair scoring driven by the plus-strand entries (score.cuh); 0 = bit rows + item list
 	int use_neigh = 1, use_tier_table = 1, use_fused_score = 0; // score_seqbits_kernel: measured slower than the item list (0.65 vs 0.60 ms), kept as an option
-	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, order_key[2], perm[2], head;
+	DevBuf hit_key[2], hit_val[2], ent_id[2], d_counters, cub_tmp, cub_tmp2, order_key[2], perm[2], head;
 	unsigned long long *h_counters = nullptr; // pinned
 	pcramp_gpu_stats stats = {};
 	bool pend_ms_db = false, pend_ms_score = false; // event times of the last calls not read back yet (pcramp_gpu_get_stats)

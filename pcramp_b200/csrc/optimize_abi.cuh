@@ -174,6 +174,7 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 	using namespace pcr::opt;
 	if (!ctx) return 1;
 	if (!o || (n_trials && (!f || !r)) || (n_moves && !moves)) return fail(ctx, "pcramp_gpu_optimize: null argument");
+	if (fast_resolve(ctx)) return 1;
 	CK(cudaSetDevice(ctx->device));
 	SeqSet &T = ctx->sets[PCRAMP_TARGET], &B = ctx->sets[PCRAMP_BACKGROUND], &M = ctx->sets[PCRAMP_MULTIPLEX];
 	if (!T.db_valid) return fail(ctx, "pcramp_gpu_optimize: no target database (call pcramp_gpu_select_words first)");

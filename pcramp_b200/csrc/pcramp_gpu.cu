@@ -176,6 +176,66 @@ __global__ void cand_build_kernel(const uint64_t *__restrict__ f, const uint64_t
 	pat_seeded[2 * i + 1] = cls ? 1u : 0u;
 }
 
+// The same for a batch without shift families (the default: no --optimize.5 / .3): candidate i = oligo i, so nothing has to be
+// counted or scanned first, and when every pattern is seedable (what the fast form of select_words assumes and then verifies) the
+// seeded-first partition is the identity.  flags: bit 0 = a candidate has threshold 0, bit 1 = a pattern is not seedable.
+__global__ void cand_build_direct_kernel(const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs, float threshold,
+	uint4 *cand_planes, uint32_t *cand_thr, uint4 *pat_mask, uint32_t *pat_meta, uint32_t *pat_meta2, unsigned long long *flags)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 2u * n_pairs) return;
+	const uint64_t *src = (i & 1u) ? r : f;
+	W128 w;
+	w.hi = src[2 * (i >> 1)];
+	w.lo = src[2 * (i >> 1) + 1];
+	const int start = w_start(w), stop = w_stop(w), size = w_size(w);
+	const uint32_t thr = (uint32_t)__fmul_rn((float)size, threshold); // select_words.cpp:83
+	const Planes4 fp = w_planes(w);
+	cand_planes[i] = make_uint4(fp.a, fp.c, fp.g, fp.t);
+	cand_thr[i] = thr;
+	uint4 mp = make_uint4(0, 0, 0, 0), mm = make_uint4(0, 0, 0, 0);
+	for (int k = 0; start + k <= stop; ++k) {
+		const uint32_t a = w_get(w, start + k); // plus strand: primer[k]
+		mp.x |= (a & 1u) << k;
+		mp.y |= ((a >> 1) & 1u) << k;
+		mp.z |= ((a >> 2) & 1u) << k;
+		mp.w |= ((a >> 3) & 1u) << k;
+		const uint32_t b = w_get(w, stop - k);  // minus strand: complement of the primer read backwards
+		mm.x |= ((b >> 3) & 1u) << k;
+		mm.y |= ((b >> 2) & 1u) << k;
+		mm.z |= ((b >> 1) & 1u) << k;
+		mm.w |= (b & 1u) << k;
+	}
+	const uint32_t n = stop >= start ? (uint32_t)(stop - start + 1) : 0u;
+	uint32_t e = 0, cls = 0;
+	if (thr >= 1u && thr <= (uint32_t)size && (uint32_t)size == n) {
+		e = (uint32_t)size - thr;
+		cls = (n / (e + 1u) >= SEED_QMIN) ? 1u : 0u;
+		if (cls && (seed_entries_needed(mp, n, e + 1u) == 0u || seed_entries_needed(mm, n, e + 1u) == 0u)) cls = 0u;
+	}
+	if (thr == 0u) atomicOr(flags, 1ull);
+	if (!cls) atomicOr(flags, 2ull);
+	pat_mask[2 * i] = mp;
+	pat_meta[2 * i] = pat_meta_pack(thr, (uint32_t)start, 0u, i);
+	pat_meta2[2 * i] = pat_meta2_pack(0u, 0u, n, e, cls);
+	pat_mask[2 * i + 1] = mm;
+	pat_meta[2 * i + 1] = pat_meta_pack(thr, (uint32_t)(31 - stop), 1u, i);
+	pat_meta2[2 * i + 1] = pat_meta2_pack(0u, 0u, n, e, cls);
+}
+
+// everything the host has to see of a fast batch, in one place: {flags, n_hits, n_queries, n_indexed, n_index_entries, n_candidates, n_entries}
+__global__ void fast_gather_kernel(unsigned long long *out, const unsigned long long *hit_count, const unsigned int *idx_counters,
+	const unsigned int *fst_flags, const uint32_t *seq_ent_off, uint32_t n_seg)
+{
+	out[0] |= (unsigned long long)fst_flags[1];
+	out[1] = hit_count[0];
+	out[2] = idx_counters[0];
+	out[3] = idx_counters[1];
+	out[4] = (unsigned long long)idx_counters[2] | ((unsigned long long)idx_counters[3] << 32);
+	out[5] = idx_counters[4];
+	out[6] = seq_ent_off[n_seg];
+}
+
 // seeded patterns first (in order), brute-force patterns after them
 __global__ void pat_partition_kernel(const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ meta2,
 	const uint32_t *__restrict__ seeded, const uint32_t *__restrict__ seeded_before, uint32_t n_pat, uint32_t n_seeded, uint4 *o_mask,
@@ -375,13 +435,15 @@ int build_index(pcramp_gpu_ctx *ctx, SeqSet &s)
 	return 0;
 }
 
+int fast_resolve(pcramp_gpu_ctx *ctx); // below: verify (and if need be re-run) a batch that select_words_fast left unverified
+
 int check_kind(pcramp_gpu_ctx *ctx, int kind)
 {
 	if (!ctx) return 1;
 	if (kind < 0 || kind >= PCRAMP_NUM_KINDS) return fail(ctx, "pcramp_gpu: bad sequence kind");
 	if (ctx->parent && ctx->parent->text_gen != ctx->seen_gen)
 		return fail(ctx, "pcramp_gpu: the parent's sequences changed after this worker was created (destroy it and create a new one)");
-	return 0;
+	return fast_resolve(ctx);
 }
 
 // calls that change a collection: not on a worker (its text is the parent's); every change is counted for the workers' guard
@@ -423,6 +485,11 @@ int pcramp_gpu_create(pcramp_gpu_ctx **out, int device)
 	}
 	for (auto &e : ctx->ev) cudaEventCreate(&e);
 	cudaMallocHost((void **)&ctx->h_counters, 8 * sizeof(unsigned long long));
+	cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
+	cudaMallocHost((void **)&ctx->h_fast, 8 * sizeof(unsigned long long));
 	*out = ctx;
 	return 0;
 }
@@ -450,7 +517,7 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	w->seen_gen = parent->text_gen;
 	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index; w->idx_part_cap = parent->idx_part_cap;
 	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
-	w->use_entry_score = parent->use_entry_score; w->use_seg_db = parent->use_seg_db;
+	w->use_entry_score = parent->use_entry_score; w->use_seg_db = parent->use_seg_db; w->use_fast = parent->use_fast;
 	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
 		const SeqSet &p = parent->sets[kind];
 		SeqSet &s = w->sets[kind];
@@ -484,6 +551,11 @@ void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	for (auto &e : ctx->ev) cudaEventDestroy(e);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+	if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+	if (ctx->h_fast) cudaFreeHost(ctx->h_fast);
 	nc::thermo_state_free(ctx->thermo);
 	ctx->thermo = nullptr;
 	pcramp_gpu_exchange_destroy(ctx);
@@ -719,6 +791,7 @@ int pcramp_gpu_pack(pcramp_gpu_ctx *ctx, int kind, uint32_t seq, uint32_t pack_m
 int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_t *r, uint32_t n_pairs)
 {
 	if (!ctx) return 1;
+	if (fast_resolve(ctx)) return 1; // a re-run of the previous batch would need the pairs that are about to be replaced
 	CK(cudaSetDevice(ctx->device));
 	ctx->n_pairs = ctx->n_staged = n_pairs;
 	ctx->batch_first = 0;
@@ -735,6 +808,7 @@ int pcramp_gpu_stage_pairs(pcramp_gpu_ctx *ctx, const uint64_t *f, const uint64_
 int pcramp_gpu_set_batch(pcramp_gpu_ctx *ctx, uint32_t first, uint32_t count)
 {
 	if (!ctx) return 1;
+	if (fast_resolve(ctx)) return 1;
 	if ((uint64_t)first + count > ctx->n_staged) return fail(ctx, "pcramp_gpu_set_batch: window exceeds the staged pairs");
 	ctx->batch_first = first;
 	ctx->n_pairs = count;
@@ -829,7 +903,7 @@ static int db_finalize_keys(pcramp_gpu_ctx *ctx, SeqSet &s)
 	return 0;
 }
 
-int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int opt3, float threshold, uint32_t pack_max_degen,
+static int select_words_general(pcramp_gpu_ctx *ctx, int kind, int opt5, int opt3, float threshold, uint32_t pack_max_degen,
 	float min_gc, float max_gc, uint32_t min_len, uint64_t *n_entries_out, uint64_t *n_keys_out)
 {
 	if (check_kind(ctx, kind)) return 1;
@@ -838,6 +912,8 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 	cudaStream_t st = ctx->stream;
 	pcramp_gpu_stats &stat = ctx->stats;
 	stat = pcramp_gpu_stats();
+	bool used_edge_fst = false;
+	ctx->fast_hint[kind].ok = false;
 	ctx->pend_ms_db = ctx->pend_ms_score = false;
 	s.db_valid = false;
 	s.n_entries = s.n_keys = 0;
@@ -1150,6 +1226,7 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 				if (fst_build(ctx, ctx->d_cand_words.as<uint4>(), ctx->d_cand_thr.as<uint32_t>(), n_cand, fst, n_brute)) return 1;
 				if ((uint64_t)n_brute * 4u > n_cand) edge_fst = false;
 			}
+			used_edge_fst = edge_fst;
 			if (edge_fst)
 				scan_edge_fst_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n + 3) / 4, (uint64_t)ctx->sm_count * 16), 128, 0, st>>>(sd, pp, fst,
 					cand_bits, hs);
@@ -1263,6 +1340,20 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		s.seq_bits = seq_bits;
 		s.db_valid = true;
 		stat.n_entries = n_ent32;
+		// the next batch of this shape may run without the host in the loop: every pattern went through a one-part index, the
+		// partial words through the seed table, nothing was brute-forced -- and its buffers are known to be large enough
+		if (!opt5 && !opt3 && used_edge_fst && n_brute == 0u && stat.n_indexed == n_seeded && n_seeded == n_pat && s.idx_parts.size() == 1 &&
+		    stat.n_index_stale == 0u) {
+			pcramp_gpu_ctx::FastHint &h = ctx->fast_hint[kind];
+			h.ok = true;
+			h.n_pairs = n_pairs;
+			h.threshold = threshold;
+			h.pp = pp;
+			h.hit_cap = std::min<uint64_t>(ctx->hit_key[0].cap / 8, ctx->hit_val[0].cap / 4);
+			h.q_cap = ctx->d_idx_queries.cap / sizeof(IdxQuery);
+			h.c_cap = ctx->d_idx_cand.cap / sizeof(IdxCand);
+			h.fst_cap = ctx->d_fst_ids.cap / 4;
+		}
 		if (n_entries_out) *n_entries_out = n_ent32;
 		if (n_keys_out) {
 			if (db_finalize_keys(ctx, s)) return 1;
@@ -1383,6 +1474,292 @@ int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int 
 		if (db_finalize_keys(ctx, s)) return 1;
 		stat.n_keys = s.n_keys;
 		*n_keys_out = s.n_keys;
+	}
+	return 0;
+}
+
+// ---- the fast form of select_words ------------------------------------------------------------------------------------------------
+// A design run, a sweep, a target-sharded job all send batch after batch of the same shape.  Once a batch of a shape has gone
+// through the general form above -- every pattern through the (one-part) text index, nothing brute-forced, the partial words through
+// the seed table -- the next one is launched WITHOUT the host reading anything back: candidate i = oligo i (no shift families), the
+// buffers keep the sizes that were enough last time, every kernel takes its counts from device memory, the partial-word scan runs
+// on a second stream beside the indexed scan, and one small kernel gathers the counters and flags that say whether the
+// assumptions held.  Whoever needs the database next (pair scoring, a copy, the statistics) waits for that one read-back
+// (fast_resolve); if an assumption failed -- a buffer overflowed, a pattern was not indexable -- the batch is run again in the
+// general form, so the result is the same either way.
+static int select_words_fast(pcramp_gpu_ctx *ctx, int kind, float threshold, const PackParams &pp)
+{
+	SeqSet &s = ctx->sets[kind];
+	cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+	pcramp_gpu_stats &stat = ctx->stats;
+	const pcramp_gpu_ctx::FastHint &h = ctx->fast_hint[kind];
+	stat = pcramp_gpu_stats();
+	ctx->pend_ms_db = ctx->pend_ms_score = false;
+	const uint32_t n_pairs = ctx->n_pairs, n_oligo = 2u * n_pairs, n_cand = n_oligo, n_pat = 2u * n_oligo, n_seg = 2u * s.n;
+	const uint32_t cand_bits = bits_for(n_cand), seq_bits = bits_for(s.n);
+	const SeqDev sd = s.dev();
+	uint32_t longest = 0;
+	for (uint32_t L : s.plen) longest = std::max(longest, L);
+	const uint32_t pos_bits = std::min<uint32_t>(32u, bits_for((uint64_t)longest + 64ull));
+	const uint64_t tier_cells = (uint64_t)s.n * n_cand, tier_words = tier_cells / 4 + 1;
+	const uint64_t cap = h.hit_cap;
+	// buffers: everything sized by capacities the host already knows
+	CK(ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
+	CK(ctx->d_fast.ensure(8 * sizeof(unsigned long long)));
+	CK(ctx->d_idx_counters.ensure(32));
+	CK(ctx->d_part_mask.ensure((size_t)n_pat * 16));
+	CK(ctx->d_part_meta.ensure((size_t)n_pat * 4));
+	CK(ctx->d_part_meta2.ensure((size_t)n_pat * 4));
+	CK(s.c_planes.ensure((size_t)n_cand * 16));
+	CK(s.c_thr.ensure((size_t)n_cand * 4));
+	CK(ctx->hit_key[0].ensure(cap * 8));
+	CK(ctx->hit_val[0].ensure(cap * 4));
+	CK(ctx->d_idx_queries.ensure(h.q_cap * sizeof(IdxQuery)));
+	CK(ctx->d_idx_cand.ensure(h.c_cap * sizeof(IdxCand)));
+	CK(ctx->d_fst_cnt.ensure((size_t)(FST_BUCKETS + 1) * 4));
+	CK(ctx->d_fst_start.ensure((size_t)(FST_BUCKETS + 1) * 4));
+	CK(ctx->d_fst_cursor.ensure((size_t)(FST_BUCKETS + 1) * 4));
+	CK(ctx->d_fst_combo.ensure((2 * FST_COMBOS + 1) * 4));
+	CK(ctx->d_fst_brute.ensure(std::max<size_t>(1, n_cand) * 4));
+	CK(ctx->d_fst_nbrute.ensure(16));
+	CK(ctx->d_fst_ids.ensure(std::max<uint64_t>(1, h.fst_cap) * 4));
+	CK(ctx->d_tier_best.ensure(tier_words * 4));
+	CK(ctx->seg_cnt.ensure((size_t)(n_seg + 1) * 4));
+	CK(ctx->seg_off.ensure((size_t)(n_seg + 1) * 4));
+	CK(ctx->seg_cursor.ensure((size_t)(n_seg + 1) * 4));
+	CK(ctx->seg_uniq.ensure((size_t)(n_seg + 1) * 4));
+	CK(ctx->seg_full.ensure((size_t)(n_seg + 1) * 4));
+	CK(ctx->seg_big.ensure((size_t)(n_seg + 2) * 4));
+	CK(ctx->ent_id[0].ensure(cap * 8));
+	CK(ctx->ent_cand[0].ensure(cap * 4));
+	CK(s.e_planes.ensure(cap * 16));
+	CK(s.e_seq.ensure(cap * 4));
+	CK(s.e_loc.ensure(cap * 4));
+	CK(s.e_strand.ensure(cap * 4));
+	CK(s.e_cand.ensure(cap * 4));
+	CK(s.e_id.ensure(cap * 4));
+	CK(s.seq_ent_off.ensure((size_t)(n_seg + 1) * 4));
+	CK(s.seq_full_end.ensure((size_t)(n_seg + 1) * 4));
+	size_t tmp_bytes = 0;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)std::max<uint32_t>(n_seg + 1, FST_BUCKETS + 1), st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	unsigned long long *d_cnt = ctx->d_counters.as<unsigned long long>();
+	unsigned long long *d_flags = ctx->d_fast.as<unsigned long long>();
+	unsigned int *d_nq = ctx->d_idx_counters.as<unsigned int>();
+	HitSink hs;
+	hs.key = ctx->hit_key[0].as<uint64_t>();
+	hs.val = ctx->hit_val[0].as<uint32_t>();
+	hs.count = d_cnt;
+	hs.cap = cap;
+	// ---- candidates + patterns ------------------------------------------------------------------------------------------
+	CK(cudaEventRecord(ctx->ev[0], st));
+	CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
+	CK(cudaMemsetAsync(d_flags, 0, 8 * sizeof(unsigned long long), st));
+	CK(cudaMemsetAsync(d_nq, 0, 32, st));
+	CK(cudaMemsetAsync(ctx->d_fst_nbrute.p, 0, 16, st));
+	cand_build_direct_kernel<<<grid_for(n_oligo, 256), 256, 0, st>>>(ctx->pf(), ctx->pr(), n_pairs, threshold, s.c_planes.as<uint4>(), s.c_thr.as<uint32_t>(),
+		ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(), d_flags);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(ctx->ev_fork, st));
+	// ---- second stream: the partial words through the seed table over the candidates ---------------------------------------
+	CK(cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
+	{
+		Fst fst;
+		CK(cudaMemsetAsync(ctx->d_fst_cnt.p, 0, (size_t)(FST_BUCKETS + 1) * 4, st2));
+		CK(cudaMemsetAsync(ctx->d_fst_combo.p, 0, FST_COMBOS * 4, st2));
+		fst_build_kernel<<<grid_for(n_cand, 128), 128, 0, st2>>>(s.c_planes.as<uint4>(), s.c_thr.as<uint32_t>(), n_cand, ctx->d_fst_cnt.as<uint32_t>(),
+			ctx->d_fst_combo.as<uint32_t>(), ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), nullptr, 0u, nullptr);
+		fst_combo_list_kernel<<<1, 32, 0, st2>>>(ctx->d_fst_combo.as<uint32_t>());
+		// (a second scratch for the scan: the main stream scans too)
+		CK(ctx->cub_tmp2.ensure(tmp_bytes));
+		size_t tb = tmp_bytes;
+		CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp2.p, tb, ctx->d_fst_cnt.as<uint32_t>(), ctx->d_fst_start.as<uint32_t>(), (int)(FST_BUCKETS + 1), st2));
+		CK(cudaMemcpyAsync(ctx->d_fst_cursor.p, ctx->d_fst_start.p, (size_t)(FST_BUCKETS + 1) * 4, cudaMemcpyDeviceToDevice, st2));
+		fst_build_kernel<<<grid_for(n_cand, 128), 128, 0, st2>>>(s.c_planes.as<uint4>(), s.c_thr.as<uint32_t>(), n_cand, ctx->d_fst_cursor.as<uint32_t>(),
+			ctx->d_fst_combo.as<uint32_t>(), ctx->d_fst_brute.as<uint32_t>(), ctx->d_fst_nbrute.as<uint32_t>(), ctx->d_fst_ids.as<uint32_t>(),
+			(uint32_t)std::min<uint64_t>(h.fst_cap, 0xFFFFFFFFull), ctx->d_fst_nbrute.as<unsigned int>() + 1);
+		fst.planes = s.c_planes.as<uint4>();
+		fst.thr = s.c_thr.as<uint32_t>();
+		fst.start = ctx->d_fst_start.as<uint32_t>();
+		fst.ids = ctx->d_fst_ids.as<uint32_t>();
+		fst.combo = ctx->d_fst_combo.as<uint32_t>();
+		fst.brute = ctx->d_fst_brute.as<uint32_t>();
+		fst.n_brute = ctx->d_fst_nbrute.as<uint32_t>();
+		fst.n = n_cand;
+		scan_edge_fst_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n + 3) / 4, (uint64_t)ctx->sm_count * 16), 128, 0, st2>>>(sd, pp, fst, cand_bits, hs);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev_join, st2));
+	}
+	// ---- main stream: the indexed scan --------------------------------------------------------------------------------------
+	{
+		const SeqSet::IndexPart &part = *s.idx_parts[0];
+		TextIndex ix;
+		ix.entries = part.entries.as<uint4>();
+		ix.off = part.off.as<uint32_t>();
+		ix.cum = part.cum.as<uint32_t>();
+		ix.blk = part.blk.as<uint32_t>();
+		ix.n = part.n;
+		ix.seq_lo = part.seq_lo;
+		ix.n_seq = part.seq_hi - part.seq_lo;
+		IdxCandSink cs;
+		cs.buf = ctx->d_idx_cand.as<IdxCand>();
+		cs.count = d_nq + 4;
+		cs.cap = (uint32_t)std::min<uint64_t>(h.c_cap, 0xFFFFFFF0ull);
+		const uint32_t qcap = (uint32_t)std::min<uint64_t>(h.q_cap, 0xFFFFFFF0ull);
+		index_query_kernel<<<grid_for((uint64_t)n_pat * IDX_SLOTS, 256), 256, 0, st>>>(ctx->d_part_mask.as<uint4>(), ctx->d_part_meta2.as<uint32_t>(), n_pat,
+			ix.off, ctx->d_idx_queries.as<IdxQuery>(), qcap, d_nq, d_nq + 1, (unsigned long long *)(d_nq + 2));
+		CK(cudaEventRecord(ctx->ev[8], st));
+		scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq, qcap,
+			ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
+		CK(cudaEventRecord(ctx->ev[9], st));
+		index_hits_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, st>>>(sd, ix, cs, ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(),
+			s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, nullptr, cand_bits, hs);
+		CK(cudaGetLastError());
+		stat.kernel_launches += 4;
+		if (s.n_dirty) { // the seeded patterns, brute force, on the groups whose text holds a degenerate base
+			scan_groups_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)s.n_dirty + 7) / 8, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(sd,
+				s.d_dirty_seq.as<uint32_t>(), s.d_dirty_grp.as<uint32_t>(), s.n_dirty, ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(),
+				ctx->d_part_meta2.as<uint32_t>(), n_pat, cand_bits, hs);
+			CK(cudaGetLastError());
+			stat.kernel_launches++;
+		}
+	}
+	CK(cudaEventRecord(ctx->ev[7], st));
+	CK(cudaEventRecord(ctx->ev[1], st));
+	CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); // every hit is in the list from here on
+	CK(cudaEventRecord(ctx->ev[2], st));
+	CK(cudaEventRecord(ctx->ev[3], st));
+	stat.kernel_launches += 6;
+	// ---- database (db.cuh, segmented form; the hit count stays on the device) -----------------------------------------------
+	if (pp.gc_filter || s.any_degenerate) {
+		validate_hits_kernel<<<grid_for(cap, 256), 256, 0, st>>>(sd, pp, hs.key, hs.val, cap, cand_bits, d_cnt);
+		stat.kernel_launches++;
+	}
+	CK(cudaMemsetAsync(ctx->d_tier_best.p, 0, tier_words * 4, st));
+	CK(cudaMemsetAsync(ctx->seg_cnt.p, 0, (size_t)(n_seg + 1) * 4, st));
+	CK(cudaMemsetAsync(ctx->seg_cursor.p, 0, (size_t)(n_seg + 1) * 4, st));
+	CK(cudaMemsetAsync(ctx->seg_big.p, 0, 4, st));
+	CK(cudaMemsetAsync(ctx->seg_uniq.as<uint32_t>() + n_seg, 0, 4, st));
+	const unsigned gh = (unsigned)std::min<uint64_t>(grid_for(cap, 256), (uint64_t)ctx->sm_count * 32u);
+	tier_mask_kernel<<<grid_for(cap, 256), 256, 0, st>>>(hs.key, cap, cand_bits, n_cand, s.c_thr.as<uint32_t>(), ctx->d_tier_best.as<uint32_t>(), d_cnt);
+	seg_count_kernel<<<gh, 256, 0, st>>>(hs.key, d_cnt, cap, cand_bits, n_cand, s.c_thr.as<uint32_t>(), ctx->d_tier_best.as<uint32_t>(), ctx->seg_cnt.as<uint32_t>());
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->seg_cnt.as<uint32_t>(), ctx->seg_off.as<uint32_t>(), (int)(n_seg + 1), st));
+	seg_scatter_kernel<<<gh, 256, 0, st>>>(hs.key, hs.val, d_cnt, cap, cand_bits, n_cand, s.c_thr.as<uint32_t>(), ctx->d_tier_best.as<uint32_t>(), pos_bits,
+		ctx->seg_off.as<uint32_t>(), ctx->seg_cursor.as<uint32_t>(), ctx->ent_id[0].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>());
+	seg_sort_small_kernel<<<(unsigned)std::min<uint64_t>(grid_for(n_seg, SEG_WARPS), (uint64_t)ctx->sm_count * 16u), SEG_WARPS * 32u, 0, st>>>(
+		ctx->seg_off.as<uint32_t>(), n_seg, ctx->ent_id[0].as<uint64_t>(), pos_bits, ctx->seg_uniq.as<uint32_t>(), ctx->seg_full.as<uint32_t>(),
+		ctx->seg_big.as<uint32_t>() + 1, ctx->seg_big.as<unsigned int>());
+	seg_sort_big_kernel<<<(unsigned)ctx->sm_count * 2u, SEG_BIG_THREADS, 0, st>>>(ctx->seg_off.as<uint32_t>(), ctx->seg_big.as<uint32_t>() + 1,
+		ctx->seg_big.as<unsigned int>(), ctx->ent_id[0].as<uint64_t>(), pos_bits, ctx->seg_uniq.as<uint32_t>(), ctx->seg_full.as<uint32_t>());
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->seg_uniq.as<uint32_t>(), s.seq_ent_off.as<uint32_t>(), (int)(n_seg + 1), st));
+	seg_materialise_kernel<<<gh, 256, 0, st>>>(sd, pp, ctx->seg_off.as<uint32_t>(), s.seq_ent_off.as<uint32_t>(), ctx->seg_full.as<uint32_t>(), n_seg,
+		ctx->ent_id[0].as<uint64_t>(), ctx->ent_cand[0].as<uint32_t>(), pos_bits, s.e_planes.as<uint4>(), s.e_seq.as<uint32_t>(), s.e_loc.as<int32_t>(),
+		s.e_strand.as<uint32_t>(), s.e_cand.as<uint32_t>(), s.e_id.as<uint32_t>(), s.seq_full_end.as<uint32_t>());
+	fast_gather_kernel<<<1, 1, 0, st>>>(d_flags, d_cnt, d_nq, ctx->d_fst_nbrute.as<unsigned int>(), s.seq_ent_off.as<uint32_t>(), n_seg);
+	CK(cudaGetLastError());
+	stat.kernel_launches += 11;
+	CK(cudaEventRecord(ctx->ev[4], st));
+	CK(cudaMemcpyAsync(ctx->h_fast, d_flags, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CK(cudaEventRecord(ctx->ev_done, st));
+	// host-side state of the database: valid, its size pending
+	s.n_cand = n_cand;
+	s.db_pp = pp;
+	s.db_pb = pos_bits;
+	s.n_entries = 0;
+	s.n_keys = 0;
+	s.keys_valid = false;
+	s.words_valid = false;
+	s.seq_bits = seq_bits;
+	s.db_valid = true;
+	stat.n_patterns = 2ull * n_cand;
+	stat.n_seeded = n_pat;
+	stat.n_positions = 0;
+	for (uint32_t i = 0; i < s.n; ++i)
+		if (s.active[i]) stat.n_positions += s.clen[i];
+	stat.ms_index_build = s.idx_build_ms;
+	stat.index_bytes = s.idx_bytes;
+	stat.n_index_builds = s.idx_builds;
+	pcramp_gpu_ctx::FastPending &p = ctx->fast_pending;
+	p.active = true;
+	p.kind = kind;
+	p.threshold = threshold;
+	p.pp = pp;
+	p.n_pat = n_pat;
+	p.n_seg = n_seg;
+	p.hit_cap = cap;
+	p.q_cap = std::min<uint64_t>(h.q_cap, 0xFFFFFFF0ull);
+	p.c_cap = std::min<uint64_t>(h.c_cap, 0xFFFFFFF0ull);
+	ctx->n_fast++;
+	return 0;
+}
+
+extern "C++" {
+namespace {
+int fast_resolve(pcramp_gpu_ctx *ctx)
+{
+	if (!ctx->fast_pending.active) return 0;
+	const pcramp_gpu_ctx::FastPending p = ctx->fast_pending;
+	ctx->fast_pending.active = false;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaEventSynchronize(ctx->ev_done));
+	const unsigned long long *h = ctx->h_fast;
+	SeqSet &s = ctx->sets[p.kind];
+	pcramp_gpu_stats &stat = ctx->stats;
+	const bool ok = h[0] == 0ull && h[1] <= p.hit_cap && h[2] <= p.q_cap && h[5] <= p.c_cap && h[3] == p.n_pat && h[6] < (1ull << 32);
+	if (ok) {
+		s.n_entries = h[6];
+		stat.n_hits = h[1];
+		stat.n_entries = h[6];
+		stat.n_index_queries = h[2];
+		stat.n_indexed = h[3];
+		stat.n_index_entries = h[4];
+		stat.ms_seed = ev_ms(ctx->ev[0], ctx->ev[7]);
+		stat.ms_scan = 0.0f;
+		stat.ms_edge = ev_ms(ctx->ev[1], ctx->ev[2]); // what is left of the partial-word scan after the indexed scan it runs beside
+		stat.ms_index_kernel = ev_ms(ctx->ev[8], ctx->ev[9]);
+		ctx->pend_ms_db = true;
+		return 0;
+	}
+	// an assumption did not hold (a buffer was too small, a pattern not indexable, a zero threshold): the general form decides
+	ctx->fast_hint[p.kind].ok = false;
+	ctx->n_fast_redo++;
+	return select_words_general(ctx, p.kind, 0, 0, p.threshold, p.pp.max_degen, p.pp.min_gc, p.pp.max_gc, p.pp.min_len, nullptr, nullptr);
+}
+} // namespace
+} // extern "C++"
+
+int pcramp_gpu_select_words_staged(pcramp_gpu_ctx *ctx, int kind, int opt5, int opt3, float threshold, uint32_t pack_max_degen,
+	float min_gc, float max_gc, uint32_t min_len, uint64_t *n_entries_out, uint64_t *n_keys_out)
+{
+	if (check_kind(ctx, kind)) return 1; // (also settles a batch the fast form left unverified)
+	CK(cudaSetDevice(ctx->device));
+	SeqSet &s = ctx->sets[kind];
+	const pcramp_gpu_ctx::FastHint &h = ctx->fast_hint[kind];
+	PackParams pp;
+	pp.max_degen = pack_max_degen;
+	pp.min_gc = min_gc;
+	pp.max_gc = max_gc;
+	pp.min_len = min_len;
+	pp.gc_filter = (min_gc > 0.0f) || (max_gc < 1.0f);
+	bool fast = ctx->use_fast && h.ok && !opt5 && !opt3 && h.n_pairs == ctx->n_pairs && h.threshold == threshold && h.pp.max_degen == pp.max_degen &&
+	            h.pp.min_gc == pp.min_gc && h.pp.max_gc == pp.max_gc && h.pp.min_len == pp.min_len && ctx->use_index && !ctx->force_brute &&
+	            ctx->use_fst && ctx->use_seg_db && ctx->use_tier_table && s.idx_valid && s.idx_parts.size() == 1 && s.n > 0 &&
+	            ctx->n_pairs > 0;
+	if (fast && s.n_idx_stale) // split sequences that are active again need the table scan: the general form
+		for (uint32_t i = 0; i < s.n && fast; ++i)
+			if (s.idx_stale[i] && s.active[i]) fast = false;
+	if (!fast) return select_words_general(ctx, kind, opt5, opt3, threshold, pack_max_degen, min_gc, max_gc, min_len, n_entries_out, n_keys_out);
+	if (n_entries_out) *n_entries_out = 0;
+	if (n_keys_out) *n_keys_out = 0;
+	if (select_words_fast(ctx, kind, threshold, pp)) return 1;
+	if (n_entries_out || n_keys_out) { // the caller wants sizes now: settle the batch
+		if (fast_resolve(ctx)) return 1;
+		if (n_entries_out) *n_entries_out = s.n_entries;
+		if (n_keys_out) {
+			if (db_finalize_keys(ctx, s)) return 1;
+			ctx->stats.n_keys = s.n_keys;
+			*n_keys_out = s.n_keys;
+		}
 	}
 	return 0;
 }
@@ -1918,6 +2295,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_fused_score") == 0) { ctx->use_fused_score = value; return 0; }
 	if (strcmp(name, "use_entry_score") == 0) { ctx->use_entry_score = value; return 0; }
 	if (strcmp(name, "use_segmented_db") == 0) { ctx->use_seg_db = value; return 0; }
+	if (strcmp(name, "use_fast_path") == 0) { ctx->use_fast = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }
 	if (strcmp(name, "index_part_positions") == 0) {
 		ctx->idx_part_cap = value > 0 ? (uint64_t)value : (1ull << 31);
@@ -1930,6 +2308,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out)
 {
 	if (!ctx || !out) return 1;
+	if (fast_resolve(ctx)) return 1;
 	if (ctx->pend_ms_db) {
 		CK(cudaEventSynchronize(ctx->ev[4]));
 		ctx->stats.ms_db = ev_ms(ctx->ev[3], ctx->ev[4]);
@@ -1940,6 +2319,8 @@ int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out)
 		ctx->stats.ms_score = ev_ms(ctx->ev[5], ctx->ev[6]);
 		ctx->pend_ms_score = false;
 	}
+	ctx->stats.n_fast = ctx->n_fast;
+	ctx->stats.n_fast_redo = ctx->n_fast_redo;
 	*out = ctx->stats;
 	return 0;
 }

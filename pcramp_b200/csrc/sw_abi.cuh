@@ -26,7 +26,7 @@ int check_kind2(pcramp_gpu_ctx *ctx, int kind)
 {
 	if (!ctx) return 1;
 	if (kind < 0 || kind >= PCRAMP_NUM_KINDS) return fail(ctx, "pcramp_gpu: bad sequence kind");
-	return 0;
+	return fast_resolve(ctx);
 }
 
 __device__ __forceinline__ float taq_correction(unsigned p0, unsigned p1, unsigned t0, unsigned t1)

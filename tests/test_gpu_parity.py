@@ -498,3 +498,58 @@ def test_segments_longer_than_shared_memory(gpu, oracle):
             assert np.array_equal(a, b)
     finally:
         gpu.set_option("use_segmented_db", 1)
+
+
+def test_fast_form_equals_general_form(oracle):
+    """batches of one shape after the first run without the host in the loop (select_words_fast): databases, coverages and bitsets
+    equal the oracle's; a batch that breaks an assumption -- more hits than the buffers were sized for (tiny_buffers keeps them
+    tight), a degenerate primer the index cannot take -- is detected from the read-back and re-run in the general form"""
+    from pcramp_b200 import PcrampGpu
+    base = synth.make_targets(131, 60, 7000, n_clades=3, between=0.12, within=0.04)
+    loner = synth.make_targets(135, 1, 7000)                       # related to nothing: its primers hit one sequence
+    coll = synth.Collection([base.codes(i) for i in range(base.n)] + [loner.codes(0)])
+    f, r = synth.make_pairs(132, base, 180)
+    fd, rd = synth.make_pairs(133, base, 60, degenerate_fraction=1.0)
+    oracle.set_sequences(coll)
+    g = PcrampGpu(0)
+    try:
+        g.set_option("tiny_buffers", 1)
+        g.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
+        chk = GpuChecker(g)
+        chk.n_seq = coll.n
+
+        def batch(fb, rb, staged):
+            if staged:
+                g.stage_pairs(fb, rb)
+                g.select_words_staged(TARGET, THR_09, want_keys=False, want_entries=False)
+                g.score_pairs_staged(TARGET, THR_09, 1.0)
+                cov, bits = g.fetch_results(TARGET)
+            else:
+                g.select_words(TARGET, fb, rb, THR_09, want_keys=False, want_entries=False)
+                cov, bits = g.score_pairs(TARGET, fb, rb, THR_09, 1.0)
+            no, nko = oracle.select_words(fb, rb, THR_09)
+            cov_o, bits_o = oracle.score_pairs(fb, rb, THR_09, 1.0, 80, 200, False)
+            assert np.array_equal(cov, cov_o) and np.array_equal(unpack_bits(bits, coll.n), bits_o)
+            assert g.db_size(TARGET) == (no, nko)
+            for a, c in zip(chk.db(), oracle.db()):
+                assert np.array_equal(a, c)
+            return g.stats()
+        # 60 pairs cut from the loner first: a few hundred hits, tight buffers
+        f1, r1 = synth.make_pairs(134, loner, 60)
+        st = batch(f1, r1, False)
+        assert st["n_fast"] == 0                                   # the first batch of a shape: general form
+        st = batch(f1[::-1].copy(), r1[::-1].copy(), True)
+        assert st["n_fast"] == 1 and st["n_fast_redo"] == 0        # the second: fast, verified
+        st = batch(f[:60], r[:60], True)                           # pairs from everywhere: several times the hits -> overflow -> re-run
+        assert st["n_fast"] == 2 and st["n_fast_redo"] == 1
+        st = batch(f[60:120], r[60:120], False)                    # fast again (the buffers stay tight: it may overflow once more)
+        assert st["n_fast"] == 3 and st["n_fast_redo"] in (1, 2)
+        if st["n_fast_redo"] == 2:                                 # the re-run is a general-form batch: the next one is fast again
+            st = batch(f[60:120], r[60:120], True)
+        redo, fast = st["n_fast_redo"], st["n_fast"]
+        st = batch(fd, rd, True)                                   # degenerate primers: the index cannot take them all
+        assert st["n_fast"] == fast + 1 and st["n_fast_redo"] == redo + 1
+        st = batch(f[120:180], r[120:180], True)                   # and the general form of that batch withdrew the hint
+        assert st["n_fast"] == fast + 1
+    finally:
+        g.close()
