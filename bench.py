@@ -316,23 +316,37 @@ def sw_leg(a, g, ext, torch):
     sym = synth.CODE
     qs = np.array([synth.word_from_codes(sym[rng.integers(0, 4, size=int(rng.integers(18, 26)))]) for _ in range(4096)], dtype=np.uint64)
     ts = np.array([synth.word_from_codes(sym[rng.integers(0, 4, size=32)]) for _ in range(4096)], dtype=np.uint64)
-    n = 1 << 18
+    n = 1 << 20
     qi, ti = rng.integers(0, 4096, size=n), rng.integers(0, 4096, size=n)
-    q, t = np.ascontiguousarray(qs[qi]), np.ascontiguousarray(ts[ti])
     qlen = np.array([bin(int(w[0])).count("1") + bin(int(w[1])).count("1") for w in qs])[qi]   # single letters: one bit per base
     cells = float((qlen * 32).sum())
-    g.sw_batch(q, t)                                              # warm-up at full size
+    # the caller's host buffers, page-locked (what a host that calls this per design iteration keeps): words in, one array per field out
+    q_pin, t_pin = torch.from_numpy(qs[qi].view(np.int64)).pin_memory(), torch.from_numpy(ts[ti].view(np.int64)).pin_memory()
+    q, t = q_pin.numpy().view(np.uint64), t_pin.numpy().view(np.uint64)
+    out_pin = [torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(5)], torch.zeros((n, 2), dtype=torch.uint8).pin_memory()
+    out = [c.numpy() for c in out_pin[0]], out_pin[1].numpy()
+    g.sw_batch(q, t, out=out)                                     # warm-up at full size
     torch.cuda.synchronize()
-    ms = 1e30
-    for _ in range(3):                                            # wall clock around the whole call: copies, kernel, read-back
+    ms, ms_kernel = 1e30, 1e30
+    for _ in range(5):                                            # wall clock around the whole call: copies in, kernel, copies out
         t0 = time.perf_counter()
-        out = g.sw_batch(q, t)
+        g.sw_batch(q, t, out=out)
         ms = min(ms, (time.perf_counter() - t0) * 1e3)
-    ms_kernel = g.sw_timing()
+        ms_kernel = min(ms_kernel, g.sw_timing())
+    scores = out[0][0].copy()
+    int32_peak = g.measure_int32_peak()
+    ops_per_cell = 12.0                                           # 12 INT32 operations per SW cell
+    achieved = cells * ops_per_cell / (ms_kernel * 1e-3)
     res = {"metric": "sw_gcups", "value": cells / (ms_kernel * 1e-3) / 1e9, "unit": "GCUPS (sw_words_kernel, cells = q x t, with start coordinates)",
            "problems": n, "ms_kernel": ms_kernel,
-           "e2e": {"value": cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms": ms, "h2d_bytes": 32 * n, "d2h_bytes": 24 * n,
-                   "note": "wall clock of pcramp_gpu_sw_batch with pageable host arrays: copies, kernel, read-back, host unpacking"},
+           "e2e": {"value": cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms": ms, "h2d_bytes": 32 * n, "d2h_bytes": 22 * n,
+                   "note": "wall clock of pcramp_gpu_sw_batch with page-locked host arrays: two copies in, kernel, six copies out (one per field)"},
+           "roofline": {"kernel": "sw_words_kernel", "bound": "int32 issue", "achieved": achieved / 1e12, "peak": int32_peak / 1e12, "unit": "Tops/s",
+                        "frac": achieved / int32_peak, "traffic": None,
+                        "peak_source": "measured live (pcramp_gpu_measure_int32_peak: VIMNMX3 / VIADDMNMX / LOP3 / IADD chains)",
+                        "note": "algorithmic cost 12 INT32 operations per cell (SURVEY.md 8d) x cells / kernel time; the kernel spends ~19 "
+                                "instructions per cell of the rows it computes (packed score + start words) and computes 20 / 24 / 28 / 32 rows "
+                                "for the longest query of a warp"},
            "gpu_launches": 1, "cpu_baseline": None}
     if os.path.exists(REF_PATH) and not a.no_cpu_baseline:
         ref = RefLib()
@@ -341,7 +355,7 @@ def sw_leg(a, g, ext, torch):
         want = ref.sw_batch(q[:m], t[:m])
         dt = time.perf_counter() - t0
         res["cpu_baseline"] = {"value": float((qlen[:m] * 32).sum()) / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "reference", "seconds": dt,
-                               "sample": "the first %d problems, SSE int16 x 8 slots" % m, "scores_identical_to_gpu": bool(np.array_equal(want[:, 0], out[:m, 0]))}
+                               "sample": "the first %d problems, SSE int16 x 8 slots" % m, "scores_identical_to_gpu": bool(np.array_equal(want[:, 0], scores[:m]))}
     return res
 
 
@@ -451,7 +465,11 @@ def dp_leg(a, g, torch, ext, rank, world, dist):
     import ctypes
     n = a.dp_problems
     sa, sb, cells = dp_problems(1000 + rank, n)
-    strand = np.float32(9e-7)
+    # the caller's host buffers, page-locked: sequence text in, one float array per field out
+    pins = [torch.from_numpy(sa).pin_memory(), torch.from_numpy(sb).pin_memory(), torch.full((n,), 9e-7, dtype=torch.float32).pin_memory()]
+    sa, sb, strand = pins[0].numpy(), pins[1].numpy(), pins[2].numpy()
+    out_pin = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(4)]
+    out_np = [o.numpy() for o in out_pin]
 
     def barrier():
         if world > 1:
@@ -485,28 +503,30 @@ def dp_leg(a, g, torch, ext, rank, world, dist):
     g.synchronize()
     st = g.thermo_stats()
     assert st["dp_cells"] == cells and st["n_problems"] == n
-    g.thermo_batch(3, sa, sb, 0.05, strand, strand)
-    ms_e2e = timed(lambda: g.thermo_batch(3, sa, sb, 0.05, strand, strand), a.steps)
+    g.thermo_batch(3, sa, sb, 0.05, strand, strand, out=out_np)
+    ms_e2e = timed(lambda: g.thermo_batch(3, sa, sb, 0.05, strand, strand, out=out_np), a.steps)
     kernel_ms = g.thermo_stats()["ms_kernel"]
     if rank != 0:
         return None
     total_cells = float(cells) * world   # every rank runs its own batch of the same shape (replicas)
     gcups = total_cells * a.steps / (ms_res * 1e-3) / 1e9
     gcups_e2e = total_cells * a.steps / (ms_e2e * 1e-3) / 1e9
-    sm_clock = 1.965e9
-    int_peak = 148 * 128 * sm_clock   # one INT32 op per lane per clock on the unified FP32/INT32 pipe
+    int_peak = g.measure_int32_peak()   # issue-bound INT32 operations/s of the DP instruction mix, measured live on this GPU
     out = {
         "metric": "dp_gcups", "value": gcups, "unit": "GCUPS (1e9 DP cells/s, cells = q x t)", "ms_per_step": ms_res / a.steps,
         "problems_per_step_per_gpu": n, "cells_per_step_per_gpu": cells, "scaling": "weak (replicas: every rank runs its own batch)",
         "op": "approximate_tm_heterodimer, gapped (align_dimer + enumeration + evaluation), 18-25-mer pairs",
-        "e2e": {"value": gcups_e2e, "unit": "GCUPS", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": n * (32 + 32 + 1 + 1 + 4),
-                "d2h_bytes_per_step": n * 16},
+        "e2e": {"value": gcups_e2e, "unit": "GCUPS", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": n * (33 + 33 + 4),
+                "d2h_bytes_per_step": n * 16,
+                "note": "pcramp_gpu_thermo_batch with page-locked host arrays: sequence text in (encoded on the device while the host takes "
+                        "logf of the strand concentrations), size-ordered launch, one copy per result field out"},
         "gpu_launches": a.steps,
         "roofline": {"kernel": "thermo_kernel", "bound": "int32 issue", "achieved": total_cells / world * DP_INT_OPS_PER_CELL / (kernel_ms * 1e-3) / 1e12,
                      "peak": int_peak / 1e12, "unit": "Tops/s (INT32)", "frac": (total_cells / world * DP_INT_OPS_PER_CELL / (kernel_ms * 1e-3)) / int_peak,
                      "avg_launch_ms": kernel_ms,
-                     "note": "algorithmic cost 45 INT32 ops per gapped cell (SURVEY.md 8d) against 148 SM x 128 lanes x 1.965 GHz; the "
-                             "kernel also runs the traceback / enumeration / float evaluation epilogue, which this model does not credit"},
+                     "peak_source": "measured live (pcramp_gpu_measure_int32_peak: VIMNMX3 / VIADDMNMX / LOP3 / IADD chains)", "traffic": None,
+                     "note": "algorithmic cost 45 INT32 ops per gapped cell (SURVEY.md 8d) against the measured issue peak of the DP instruction "
+                             "mix; the kernel also runs the traceback / enumeration / float evaluation epilogue, which this model does not credit"},
     }
     if world == 1 and not a.no_cpu_baseline:
         from tests.harness import RefLib, REF_PATH
@@ -516,12 +536,12 @@ def dp_leg(a, g, torch, ext, rank, world, dist):
             m = min(n, a.dp_cpu_problems)
             A = [bytes(r[:int(np.argmax(r == 0))]).decode() for r in sa[:m]]
             B = [bytes(r[:int(np.argmax(r == 0))]).decode() for r in sb[:m]]
-            ref.thermo_batch(3, A[:2000], B[:2000], 0.05, strand, strand)
+            ref.thermo_batch(3, A[:2000], B[:2000], 0.05, np.float32(9e-7), np.float32(9e-7))
             c1 = float(sum(len(x) * len(y) for x, y in zip(A, B)))
             reps, c = 0, 0.0
             t0 = time.perf_counter()
             while reps < 64 and (reps == 0 or time.perf_counter() - t0 < 8.0):
-                ref.thermo_batch(3, A, B, 0.05, strand, strand)
+                ref.thermo_batch(3, A, B, 0.05, np.float32(9e-7), np.float32(9e-7))
                 reps += 1
                 c += c1
             dt = time.perf_counter() - t0

@@ -509,6 +509,9 @@ int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
 int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value);
 /* Issue-bound ceiling of the scan's own instruction mix on this GPU (alignments/s), measured live. */
 int pcramp_gpu_measure_int_peak(pcramp_gpu_ctx *ctx, double *alignments_per_s);
+/* Issue-bound ceiling of the dynamic-programming kernels' instruction mix (three-input maximum, add-maximum, logic op, add) in
+ * INT32 operations/s, measured live: the denominator of the K3 / K4 rooflines (SURVEY.md 8d costs a DP cell in INT32 operations). */
+int pcramp_gpu_measure_int32_peak(pcramp_gpu_ctx *ctx, double *ops_per_s);
 
 /* ---- host-side word helpers (word.h / word.cpp), for building candidate lists ------------------- */
 void pcramp_word_from_string(const char *iupac, int centre, uint64_t out[2]);

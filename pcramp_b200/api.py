@@ -234,6 +234,7 @@ SIGNATURES = {
     "pcramp_gpu_reduce_best": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_double, ctypes.c_int64,
                                                _u32p, _f32p, _f32p, _f32p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "pcramp_gpu_measure_int_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "pcramp_gpu_measure_int32_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "pcramp_gpu_bitset_words": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_int]),
     "pcramp_gpu_fetch_results": (ctypes.c_int, [ctypes.c_void_p, _f32p, _u32p]),
     "pcramp_gpu_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
@@ -706,10 +707,14 @@ class PcrampGpu:
         sb = None if strand_b is None else np.ascontiguousarray(np.broadcast_to(np.asarray(strand_b, dtype=np.float32), (n,)))
         return n, a, b, sa, sb
 
-    def thermo_batch(self, op, seq_a, seq_b=None, salt=0.05, strand_a=9e-7, strand_b=None):
-        """-> (tm, dH, dS, dG_dp) float32 arrays; seq_* are lists of str or (n, stride) uint8 arrays"""
+    def thermo_batch(self, op, seq_a, seq_b=None, salt=0.05, strand_a=9e-7, strand_b=None, out=None):
+        """-> (tm, dH, dS, dG_dp) float32 arrays; seq_* are lists of str or (n, stride) uint8 arrays; out = four float32 arrays of n
+        to fill (page-locked arrays, like page-locked seq_* arrays, move at link speed)"""
         n, a, b, sa, sb = self._thermo_args(op, seq_a, seq_b, strand_a, strand_b)
-        out = [np.zeros(n, np.float32) for _ in range(4)]
+        if out is None:
+            out = [np.zeros(n, np.float32) for _ in range(4)]
+        else:
+            assert len(out) == 4 and all(o.dtype == np.float32 and o.size == n and o.flags.c_contiguous for o in out)
         self._ck(self.lib.pcramp_gpu_thermo_batch(self.h, int(op), n, a.ctypes.data_as(ctypes.c_char_p),
                                                   None if b is None else b.ctypes.data_as(ctypes.c_char_p), a.shape[1], float(salt),
                                                   _ptr(sa, _f32p), _ptr(sb, _f32p), *[_ptr(o, _f32p) for o in out]))
@@ -755,13 +760,21 @@ class PcrampGpu:
         return ok
 
     # ---- K4: Smith-Waterman and the background tests ------------------------------------------------
-    def sw_batch(self, query, target):
-        """-> (n, 6) int32 {score, q_start, q_stop, t_start, t_stop, (last_two.first << 4) | last_two.second}"""
+    def sw_batch(self, query, target, out=None):
+        """-> (n, 6) int32 {score, q_start, q_stop, t_start, t_stop, (last_two.first << 4) | last_two.second};
+        out = (five int32 arrays of n, one uint8 array of (n, 2)): the library copies straight into them (page-locked arrays
+        move at link speed) and they are returned as they are"""
         q, t = _words(query), _words(target)
         n = len(q)
-        cols = [np.zeros(n, np.int32) for _ in range(5)]
-        l2 = np.zeros((n, 2), np.uint8)
+        if out is not None:
+            cols, l2 = list(out[0]), out[1]
+            assert all(c.dtype == np.int32 and c.size == n and c.flags.c_contiguous for c in cols) and l2.dtype == np.uint8 and l2.size == 2 * n
+        else:
+            cols = [np.zeros(n, np.int32) for _ in range(5)]
+            l2 = np.zeros((n, 2), np.uint8)
         self._ck(self.lib.pcramp_gpu_sw_batch(self.h, n, _ptr(q, _u64p), _ptr(t, _u64p), *[_ptr(c, _i32p) for c in cols], _ptr(l2, _u8p)))
+        if out is not None:
+            return out
         return np.stack(cols + [(l2[:, 0].astype(np.int32) << 4) | l2[:, 1]], 1)
 
     def sw_timing(self):
@@ -809,6 +822,12 @@ class PcrampGpu:
     def measure_int_peak(self):
         v = ctypes.c_double()
         self._ck(self.lib.pcramp_gpu_measure_int_peak(self.h, ctypes.byref(v)))
+        return v.value
+
+    def measure_int32_peak(self):
+        """INT32 operations/s of the DP kernels' instruction mix, issue-bound (the K3 / K4 roofline denominator)"""
+        v = ctypes.c_double()
+        self._ck(self.lib.pcramp_gpu_measure_int32_peak(self.h, ctypes.byref(v)))
         return v.value
 
     def set_option(self, name, value):

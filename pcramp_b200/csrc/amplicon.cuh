@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128) pool_sw_kernel(Regions R, const uint32_t 
 	sw::query_from_word(w, q);
 	const uint32_t rec = uniq[u];
 	const RegionTarget t(R.raw + R.raw_off[R.seq[rec]], R.start[rec], (int)R.len[rec]);
-	const sw::Result s = sw::align<false>(q, t);
+	const sw::Result s = sw::align_warp<false>(q, t);
 	float norm = __fmul_rn(2.0f, (float)size);
 	if (norm > 0.0f) norm = __fdiv_rn(1.0f, norm);
 	float score = __fmul_rn((float)s.score, norm);

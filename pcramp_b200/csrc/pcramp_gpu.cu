@@ -2246,6 +2246,34 @@ __global__ void __launch_bounds__(256, 2) int_peak_kernel(uint32_t iters, uint32
 	if (hits == 0xffffffffu) sink[t] = hits;
 }
 
+// The dynamic-programming kernels' instruction mix (K3 fill, K4 cells): three-input maximum, add-maximum, logic op, add on
+// eight independent register chains per thread: "INT32 operations/s if nothing but issue limits them" -- the denominator of the
+// DP rooflines (SURVEY.md 8d costs a cell in INT32 operations).
+__global__ void __launch_bounds__(256, 2) int32_peak_kernel(uint32_t iters, int seed, int *sink)
+{
+	int x[8], y[8];
+	const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	#pragma unroll
+	for (int r = 0; r < 8; ++r) {
+		x[r] = t * 7919 + seed + r;
+		y[r] = (t ^ (r * 0x9e37)) - seed;
+	}
+	for (uint32_t i = 0; i < iters; ++i) {
+		#pragma unroll
+		for (int r = 0; r < 8; ++r) {
+			const int a = __vimax3_s32(x[r], y[r], seed);
+			const int b = __viaddmax_s32(a, -5, y[r]);
+			const int c = (b & 0x7fff0fff) ^ x[r];
+			x[r] = c + y[r];
+			y[r] = a;
+		}
+	}
+	int acc = 0;
+	#pragma unroll
+	for (int r = 0; r < 8; ++r) acc ^= x[r] ^ y[r];
+	if (acc == 0x7fffffff) *sink = acc;
+}
+
 int pcramp_gpu_measure_int_peak(pcramp_gpu_ctx *ctx, double *alignments_per_s)
 {
 	if (!ctx || !alignments_per_s) return 1;
@@ -2262,6 +2290,25 @@ int pcramp_gpu_measure_int_peak(pcramp_gpu_ctx *ctx, double *alignments_per_s)
 	CK(cudaStreamSynchronize(ctx->stream));
 	const double s = ev_ms(ctx->ev[0], ctx->ev[1]) * 1e-3;
 	*alignments_per_s = (double)grid * 256.0 * 8.0 * (double)iters / s;
+	return 0;
+}
+
+int pcramp_gpu_measure_int32_peak(pcramp_gpu_ctx *ctx, double *ops_per_s)
+{
+	if (!ctx || !ops_per_s) return 1;
+	CK(cudaSetDevice(ctx->device));
+	DevBuf sink;
+	CK(sink.ensure(4));
+	const uint32_t iters = 100000;
+	const unsigned grid = (unsigned)ctx->sm_count * 4;
+	int32_peak_kernel<<<grid, 256, 0, ctx->stream>>>(1000, 1, sink.as<int>()); // warm-up
+	CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+	int32_peak_kernel<<<grid, 256, 0, ctx->stream>>>(iters, 2, sink.as<int>());
+	CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(ctx->stream));
+	const double s = ev_ms(ctx->ev[0], ctx->ev[1]) * 1e-3;
+	*ops_per_s = (double)grid * 256.0 * 8.0 * 4.0 * (double)iters / s;
 	return 0;
 }
 

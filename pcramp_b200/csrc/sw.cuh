@@ -14,8 +14,8 @@
 // Scores stay within [-69, 64] for 32-base operands, so the reference's int16 never wraps; int here.
 //
 // The DP is walked column by column (target outer, query inner) so that the per-problem state is indexed by
-// the query (<= 32 bases, Word length) whatever the target length; the reference's row-major tie rule is kept
-// by comparing coordinates explicitly.
+// the query (<= 32 bases, Word length) whatever the target length, and kept in registers (see align_score / align_start);
+// the reference's row-major tie rule is kept by comparing (score, i) keys.
 #pragma once
 #include "word128.cuh"
 
@@ -32,8 +32,8 @@ struct Result {
 	bool any;                      // false: no cell reached the initial maximum (0); the reference then reports stale coordinates
 };
 
-struct Query {
-	unsigned char b[SW_MAX_QUERY]; // 4-bit codes
+struct Query { // the query as four bit-planes over its positions: bit i of plane[k] = bit k of the 4-bit code of base i
+	uint32_t plane[4];
 	int len;
 };
 
@@ -42,7 +42,20 @@ PCR_HD void query_from_word(const W128 &w, Query &q)
 {
 	q.len = w_size(w);
 	const int s = w_start(w);
-	for (int i = 0; i < SW_MAX_QUERY; ++i) q.b[i] = (i < q.len && s >= 0 && s + i < WORD_LEN) ? (unsigned char)w_get(w, s + i) : 0;
+	q.plane[0] = q.plane[1] = q.plane[2] = q.plane[3] = 0u;
+	for (int i = 0; i < SW_MAX_QUERY; ++i) {
+		const uint32_t b = (i < q.len && s >= 0 && s + i < WORD_LEN) ? w_get(w, s + i) : 0u;
+		q.plane[0] |= (b & 1u) << i;
+		q.plane[1] |= ((b >> 1) & 1u) << i;
+		q.plane[2] |= ((b >> 2) & 1u) << i;
+		q.plane[3] |= ((b >> 3) & 1u) << i;
+	}
+}
+
+// bit i = "query base i and the target code tb share a letter" (the +2 / -3 choice of :419-424 for a whole column)
+PCR_HD uint32_t match_mask(const Query &q, unsigned tb)
+{
+	return ((tb & 1u) ? q.plane[0] : 0u) | ((tb & 2u) ? q.plane[1] : 0u) | ((tb & 4u) ? q.plane[2] : 0u) | ((tb & 8u) ? q.plane[3] : 0u);
 }
 
 struct WordTarget { // pack_target_slots(Word) (seq_overlap.h:1102-1136)
@@ -65,92 +78,175 @@ struct NibbleTarget { // pack_target_slots(Sequence) (seq_overlap.h:1071-1100): 
 	}
 };
 
-template <bool WITH_START, class Target>
-PCR_HD Result align(const Query &q, const Target &t)
+// three-input integer maximum / fused add-maximum: one instruction each on sm_100a (VIMNMX3 / VIADDMNMX)
+PCR_HD int max3i(int a, int b, int c)
+{
+#ifdef __CUDA_ARCH__
+	return __vimax3_s32(a, b, c);
+#else
+	return max(max(a, b), c);
+#endif
+}
+PCR_HD int max3i_relu(int a, int b, int c)
+{
+#ifdef __CUDA_ARCH__
+	return __vimax3_s32_relu(a, b, c);
+#else
+	return max(max(max(a, b), c), 0);
+#endif
+}
+PCR_HD int addmaxi(int a, int b, int c) // max(a + b, c)
+{
+#ifdef __CUDA_ARCH__
+	return __viaddmax_s32(a, b, c);
+#else
+	return max(a + b, c);
+#endif
+}
+
+// The state of column j-1 lives in registers: the loop over the query is fully unrolled (32 statically indexed slots,
+// left early at the query's end) and only the loop over the target is a run-time loop.
+//
+// Score only (any target length):
+//   M  = max(aM, aIq, aIt, 0) + s                 one VIMNMX3.RELU + the +2 / -3 choice
+//   Iq = max(cM - 5, cIq - 2, -2)                 (max(x, 0) - 5 = max(x - 5, -5) and -5 < -2): two VIADDMNMX
+//   It = max(bM - 5, bIt - 2, -2)
+// The winner -- the largest (i, j) among the cells equal to the maximum -- is kept as one key (score, i): columns are
+// visited in increasing j, so among equal scores a later cell replaces the kept one exactly when its i is not smaller.
+//
+// ROWS = the number of query slots computed (a compile-time count >= the query's length; kernels pick the smallest
+// instantiation that covers the longest query of the warp).  Slots past the end of the query need no mask: their plane
+// bits are 0, so they always score a mismatch, and a cell there stays at least 3 below the best real cell seen so far.
+template <int ROWS, class Target>
+PCR_HD Result align_score(const Query &q, const Target &t)
 {
 	Result r;
 	r.score = 0;
 	r.q_start = r.q_stop = r.t_start = r.t_stop = 0;
 	r.any = false;
-	const int qlen = q.len, tlen = t.length();
-	// state of column j-1, indexed by query position
-	int M[SW_MAX_QUERY], Iq[SW_MAX_QUERY], It[SW_MAX_QUERY];
-	int Msi[WITH_START ? SW_MAX_QUERY : 1], Msj[WITH_START ? SW_MAX_QUERY : 1];   // start of the path into M
-	int Qsi[WITH_START ? SW_MAX_QUERY : 1], Qsj[WITH_START ? SW_MAX_QUERY : 1];   // ... into Iq
-	int Tsi[WITH_START ? SW_MAX_QUERY : 1], Tsj[WITH_START ? SW_MAX_QUERY : 1];   // ... into It
-	for (int i = 0; i < qlen; ++i) { // column -1: the border (curr_row[0], :400-408)
+	const int tlen = t.length();
+	int M[ROWS], Iq[ROWS], It[ROWS];
+#pragma unroll
+	for (int i = 0; i < ROWS; ++i) { // column -1: the border (curr_row[0], :400-408)
 		M[i] = 0;
 		Iq[i] = It[i] = SW_GAP_OPEN;
-		if (WITH_START) {
-			Msi[i] = i + 1;
-			Msj[i] = 0;
-			Qsi[i] = Qsj[i] = Tsi[i] = Tsj[i] = 0; // never observable: only ever carried by negative scores
-		}
 	}
-	int best = 0, best_i = -1, best_j = -1, best_si = 0, best_sj = 0;
+	int best_key = 0, best_j = -1; // key = score * 64 + i
 	for (int j = 0; j < tlen; ++j) {
-		const unsigned tb = t.at(j);
-		// cell (i-1, j-1) and (i-1, j) for i = 0: the top border (last_row, :381-389): M = 0, gaps = -5, start = (0, j)
-		int aM = 0, aIq = SW_GAP_OPEN, aIt = SW_GAP_OPEN, aMsi = 0, aMsj = j, aQsi = 0, aQsj = 0, aTsi = 0, aTsj = 0;
-		int bM = 0, bIt = SW_GAP_OPEN, bMsi = 0, bMsj = j + 1, bTsi = 0, bTsj = 0;
-		for (int i = 0; i < qlen; ++i) {
-			// C = (i, j-1) is the stored state; it becomes A for the next i
-			const int cM = M[i], cIq = Iq[i], cIt = It[i];
-			int cMsi = 0, cMsj = 0, cQsi = 0, cQsj = 0, cTsi = 0, cTsj = 0;
-			if (WITH_START) {
-				cMsi = Msi[i]; cMsj = Msj[i]; cQsi = Qsi[i]; cQsj = Qsj[i]; cTsi = Tsi[i]; cTsj = Tsj[i];
-			}
-			const int amax = max(max(aM, aIq), aIt);
-			const int xM = max(amax, 0) + ((q.b[i] & tb) ? SW_MATCH : SW_MISMATCH);
-			int xMsi = 0, xMsj = 0;
-			if (WITH_START) { // :457-512, in the reference's order of overrides
-				const bool gap_beats_m = (aM < aIq) || (aM < aIt);
-				xMsi = gap_beats_m ? 0 : aMsi;
-				xMsj = gap_beats_m ? 0 : aMsj;
-				if (!(aIq < aIt) && (aIq > aM)) { xMsi = aQsi; xMsj = aQsj; }
-				if ((aIt > aM) && (aIt > aIq)) { xMsi = aTsi; xMsj = aTsj; }
-				if (0 > amax) { xMsi = i; xMsj = j; }
-			}
-			const int q_open = max(cM, 0) + SW_GAP_OPEN, q_ext = max(cIq, 0) + SW_GAP_EXTEND;
-			const int xIq = max(q_open, q_ext);
-			const int t_open = max(bM, 0) + SW_GAP_OPEN, t_ext = max(bIt, 0) + SW_GAP_EXTEND;
-			const int xIt = max(t_open, t_ext);
-			int xQsi = 0, xQsj = 0, xTsi = 0, xTsj = 0;
-			if (WITH_START) {
-				const bool qe = q_open < q_ext;
-				xQsi = qe ? cQsi : cMsi;
-				xQsj = qe ? cQsj : cMsj;
-				const bool te = t_open < t_ext;
-				xTsi = te ? bTsi : bMsi;
-				xTsj = te ? bTsj : bMsj;
-			}
-			// the reference replaces the maximum whenever M is not less than it, scanning i outer / j inner:
-			// the winner is the cell with the largest (i, j) among those equal to the final maximum
-			if (xM > best || (xM == best && (i > best_i || (i == best_i && j > best_j)))) {
-				best = xM;
-				best_i = i;
-				best_j = j;
-				if (WITH_START) { best_si = xMsi; best_sj = xMsj; }
-			}
-			// slide: this column's (i) becomes B for i+1; the stored previous column's (i) becomes A for i+1
+		const uint32_t m = match_mask(q, t.at(j));
+		int aM = 0, aIq = SW_GAP_OPEN, aIt = SW_GAP_OPEN; // (i-1, j-1) for i = 0: the top border (last_row, :381-389)
+		int bM = 0, bIt = SW_GAP_OPEN;                    // (i-1, j)
+#pragma unroll
+		for (int i = 0; i < ROWS; ++i) {
+			const int cM = M[i], cIq = Iq[i], cIt = It[i]; // (i, j-1)
+			const int xM = max3i_relu(aM, aIq, aIt) + (((m >> i) & 1u) ? SW_MATCH : SW_MISMATCH);
+			const int xIq = addmaxi(cM, SW_GAP_OPEN, addmaxi(cIq, SW_GAP_EXTEND, SW_GAP_EXTEND));
+			const int xIt = addmaxi(bM, SW_GAP_OPEN, addmaxi(bIt, SW_GAP_EXTEND, SW_GAP_EXTEND));
+			const int key = xM * 64 + i;
+			if (key >= best_key) { best_key = key; best_j = j; }
 			aM = cM; aIq = cIq; aIt = cIt;
-			if (WITH_START) { aMsi = cMsi; aMsj = cMsj; aQsi = cQsi; aQsj = cQsj; aTsi = cTsi; aTsj = cTsj; }
 			bM = xM; bIt = xIt;
-			if (WITH_START) { bMsi = xMsi; bMsj = xMsj; bTsi = xTsi; bTsj = xTsj; }
 			M[i] = xM; Iq[i] = xIq; It[i] = xIt;
-			if (WITH_START) { Msi[i] = xMsi; Msj[i] = xMsj; Qsi[i] = xQsi; Qsj[i] = xQsj; Tsi[i] = xTsi; Tsj[i] = xTsj; }
 		}
 	}
-	if (best_i >= 0) {
+	if (best_j >= 0) {
 		r.any = true;
-		r.score = best;
-		r.q_stop = best_i;
+		r.score = best_key >> 6;
+		r.q_stop = best_key & 63;
 		r.t_stop = best_j;
-		r.q_start = best_si;
-		r.t_start = best_sj;
 	}
 	return r;
 }
+
+// With start coordinates (operands of at most 32 bases: Word against Word).  Every state is ONE 32-bit word
+//   [31:16] score   [13:12] state (M = 3, Iq = 1, It = 0: re-labelling a maximum is one OR / AND)   [11:6] 63 - start_i   [5:0] 63 - start_j
+// and the reference's propagation rules (:457-512) are what a plain signed maximum of such words does:
+//   * M takes the start of M when M is not beaten, else of Iq when Iq >= It, else of It: ties on the score fall to the
+//     larger state code;
+//   * a gap state takes the start of its opening M unless the extension scores strictly more: M (3) wins ties against
+//     Iq (1) and It (0) (the label left on a negative word is irrelevant: it only orders words nobody reports);
+//   * max(x, 0) ahead of a gap: a gap state that only exists through the clamp has a negative score, and a negative
+//     state can never hand its start to a cell that is reported (it loses to the clamp or to the fresh start below),
+//     so the clamp is the constant word "-2" in the maximum;
+//   * the fresh start (i, j) is taken when the incoming maximum is negative (`0 > amax` strictly, :502-512): a path
+//     that comes in with score 0 started at some i' < i, so its inverted start field is larger than the fresh one and a
+//     maximum against the word (0, M, i, j) keeps it.  The borders carry score 0 with the start the fresh rule would give.
+constexpr int SWP_ONE = 1 << 16, SWP_STATE_M = 3 << 12, SWP_STATE_IQ = 1 << 12;
+PCR_HD int swp_pack(int score, int state, int si, int sj) { return score * SWP_ONE + state + ((63 - si) << 6) + (63 - sj); }
+
+template <int ROWS, class Target>
+PCR_HD Result align_start(const Query &q, const Target &t)
+{
+	Result r;
+	r.score = 0;
+	r.q_start = r.q_stop = r.t_start = r.t_stop = 0;
+	r.any = false;
+	const int tlen = t.length();
+	int M[ROWS], Iq[ROWS], It[ROWS];
+	const int border_gap = swp_pack(SW_GAP_OPEN, 0, 63, 63), floor_gap = swp_pack(SW_GAP_EXTEND, 0, 63, 63);
+#pragma unroll
+	for (int i = 0; i < ROWS; ++i) { // column -1 (:400-408): M = 0 with start (i + 1, 0)
+		M[i] = swp_pack(0, SWP_STATE_M, i + 1, 0);
+		Iq[i] = It[i] = border_gap;
+	}
+	int best_key = 0, best_j = -1, best_w = 0;
+	for (int j = 0; j < tlen; ++j) {
+		const uint32_t m = match_mask(q, t.at(j));
+		// the top border (:381-389): M = 0 with start (0, j) on the diagonal side and (0, j + 1) above the column
+		int aM = swp_pack(0, SWP_STATE_M, 0, j), aIq = border_gap, aIt = border_gap;
+		int bM = swp_pack(0, SWP_STATE_M, 0, j + 1), bIt = border_gap;
+		const int fresh0 = swp_pack(0, SWP_STATE_M, 0, j);
+#pragma unroll
+		for (int i = 0; i < ROWS; ++i) {
+			const int cM = M[i], cIq = Iq[i], cIt = It[i];
+			const int in = max3i(aM, aIq, aIt) | SWP_STATE_M;
+			const int xM = max(in, fresh0 - (i << 6)) + (((m >> i) & 1u) ? SW_MATCH * SWP_ONE : SW_MISMATCH * SWP_ONE);
+			const int xIq = (addmaxi(cM, SW_GAP_OPEN * SWP_ONE, addmaxi(cIq, SW_GAP_EXTEND * SWP_ONE, floor_gap)) & ~(SWP_STATE_M ^ SWP_STATE_IQ));
+			const int xIt = addmaxi(bM, SW_GAP_OPEN * SWP_ONE, addmaxi(bIt, SW_GAP_EXTEND * SWP_ONE, floor_gap)) & ~SWP_STATE_M;
+			const int key = (xM >> 16) * 64 + i;
+			if (key >= best_key) { best_key = key; best_j = j; best_w = xM; }
+			aM = cM; aIq = cIq; aIt = cIt;
+			bM = xM; bIt = xIt;
+			M[i] = xM; Iq[i] = xIq; It[i] = xIt;
+		}
+	}
+	if (best_j >= 0) {
+		r.any = true;
+		r.score = best_key >> 6;
+		r.q_stop = best_key & 63;
+		r.t_stop = best_j;
+		r.q_start = 63 - ((best_w >> 6) & 63);
+		r.t_start = 63 - (best_w & 63);
+	}
+	return r;
+}
+
+template <bool WITH_START, class Target, int ROWS = SW_MAX_QUERY>
+PCR_HD Result align(const Query &q, const Target &t)
+{
+	if constexpr (WITH_START) return align_start<ROWS>(q, t);
+	else return align_score<ROWS>(q, t);
+}
+
+// the same with ROWS chosen at run time (a warp-uniform value keeps the warp on one instantiation)
+template <bool WITH_START, class Target>
+PCR_HD Result align_rows(const Query &q, const Target &t, int rows)
+{
+	if (rows <= 20) return align<WITH_START, Target, 20>(q, t);
+	if (rows <= 24) return align<WITH_START, Target, 24>(q, t);
+	if (rows <= 28) return align<WITH_START, Target, 28>(q, t);
+	return align<WITH_START, Target, 32>(q, t);
+}
+
+#ifdef __CUDACC__
+// align_rows with the row count of the longest query among the lanes that are here together
+template <bool WITH_START, class Target>
+__device__ __forceinline__ Result align_warp(const Query &q, const Target &t)
+{
+	const int rows = __reduce_max_sync(__activemask(), q.len);
+	return align_rows<WITH_START>(q, t, rows);
+}
+#endif
 
 // target_last_two_aligned (seq_overlap.h:1265-1283): {N, N} unless 1 <= stop_j < target length
 template <class Target>

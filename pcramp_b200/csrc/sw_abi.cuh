@@ -47,23 +47,28 @@ __device__ __forceinline__ void word_last_two(const W128 &w, unsigned &p0, unsig
 __global__ void __launch_bounds__(128) sw_words_kernel(uint32_t n, const uint64_t *__restrict__ query, const uint64_t *__restrict__ target, int *out)
 {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= n) return;
+	const bool live = p < n;
 	W128 qw, tw;
-	qw.hi = query[2 * p]; qw.lo = query[2 * p + 1];
-	tw.hi = target[2 * p]; tw.lo = target[2 * p + 1];
+	qw.hi = qw.lo = tw.hi = tw.lo = 0ull;
+	if (live) {
+		qw.hi = query[2 * p]; qw.lo = query[2 * p + 1];
+		tw.hi = target[2 * p]; tw.lo = target[2 * p + 1];
+	}
 	sw::Query q;
 	sw::query_from_word(qw, q);
 	const sw::WordTarget t(tw);
-	const sw::Result r = sw::align<true>(q, t);
+	const int rows = __reduce_max_sync(0xffffffffu, q.len); // the warp runs the instantiation that covers its longest query
+	const sw::Result r = sw::align_rows<true>(q, t, rows);
+	if (!live) return;
 	unsigned a, b;
 	sw::last_two(r, t, a, b);
-	int *o = out + 6 * (size_t)p;
-	o[0] = r.score;
-	o[1] = r.any ? r.q_start : -1;
-	o[2] = r.any ? r.q_stop : -1;
-	o[3] = r.any ? r.t_start : -1;
-	o[4] = r.any ? r.t_stop : -1;
-	o[5] = (int)((a << 4) | b);
+	// one array per field (what the caller's arrays are): each leaves the device with one copy, nothing is re-packed on the host
+	out[p] = r.score;
+	out[(size_t)n + p] = r.any ? r.q_start : -1;
+	out[2 * (size_t)n + p] = r.any ? r.q_stop : -1;
+	out[3 * (size_t)n + p] = r.any ? r.t_start : -1;
+	out[4 * (size_t)n + p] = r.any ? r.t_stop : -1;
+	reinterpret_cast<uchar2 *>(out + 5 * (size_t)n)[p] = make_uchar2((unsigned char)a, (unsigned char)b);
 }
 
 // ---- candidate amplicons --------------------------------------------------------------------------------
@@ -311,13 +316,13 @@ __global__ void __launch_bounds__(128) background_sw_kernel(uint64_t n, const ui
 	const sw::WordTarget tf(fk), tr(rk);
 	sw::Query q;
 	sw::query_from_word(fw, q);
-	const sw::Result s0 = sw::align<false>(q, tf); // slot 0: F   + f
+	const sw::Result s0 = sw::align_warp<false>(q, tf); // slot 0: F   + f
 	sw::query_from_word(fc, q);
-	const sw::Result s1 = sw::align<false>(q, tf); // slot 1: (F) + f
+	const sw::Result s1 = sw::align_warp<false>(q, tf); // slot 1: (F) + f
 	sw::query_from_word(rw, q);
-	const sw::Result s2 = sw::align<false>(q, tr); // slot 2: R   + r
+	const sw::Result s2 = sw::align_warp<false>(q, tr); // slot 2: R   + r
 	sw::query_from_word(rc, q);
-	const sw::Result s3 = sw::align<false>(q, tr); // slot 3: (R) + r
+	const sw::Result s3 = sw::align_warp<false>(q, tr); // slot 3: (R) + r
 	float f_norm = __fmul_rn(2.0f, (float)w_size(fw)), r_norm = __fmul_rn(2.0f, (float)w_size(rw));
 	if (f_norm > 0.0f) f_norm = __fdiv_rn(1.0f, f_norm);
 	if (r_norm > 0.0f) r_norm = __fdiv_rn(1.0f, r_norm);
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(128) multiplex_sw_kernel(SeqDev sd, const uint
 	sw::Query q;
 	sw::query_from_word(w, q);
 	const sw::NibbleTarget t(sd.raw + sd.raw_off[seq], (int)sd.len[seq]);
-	const sw::Result s = sw::align<false>(q, t);
+	const sw::Result s = sw::align_warp<false>(q, t);
 	float norm = __fmul_rn(2.0f, (float)size);
 	if (norm > 0.0f) norm = __fdiv_rn(1.0f, norm);
 	float score = __fmul_rn((float)s.score, norm);
@@ -390,26 +395,20 @@ int pcramp_gpu_sw_batch(pcramp_gpu_ctx *ctx, uint32_t n, const uint64_t *query, 
 	DevBuf &dq = ctx->sw_q, &dt = ctx->sw_t, &dout = ctx->sw_out;
 	CK(dq.ensure((size_t)n * 16));
 	CK(dt.ensure((size_t)n * 16));
-	CK(dout.ensure((size_t)n * 24));
+	CK(dout.ensure((size_t)n * 22));
+	// the caller's arrays are the staging: page-locked arrays move at link speed, pageable ones through the driver's bounce buffers
 	CK(cudaMemcpyAsync(dq.p, query, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(dt.p, target, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 	sw_words_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, dq.as<uint64_t>(), dt.as<uint64_t>(), dout.as<int>());
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-	std::vector<int> h((size_t)n * 6);
-	CK(cudaMemcpyAsync(h.data(), dout.p, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+	int32_t *dst[5] = {score, q_start, q_stop, t_start, t_stop};
+	for (int k = 0; k < 5; ++k)
+		if (dst[k]) CK(cudaMemcpyAsync(dst[k], dout.as<int>() + (size_t)k * n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (last_two) CK(cudaMemcpyAsync(last_two, dout.as<int>() + 5 * (size_t)n, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	cudaEventElapsedTime(&ctx->sw_ms_kernel, ctx->ev[0], ctx->ev[1]);
-	for (uint32_t p = 0; p < n; ++p) {
-		const int *o = h.data() + 6 * (size_t)p;
-		if (score) score[p] = o[0];
-		if (q_start) q_start[p] = o[1];
-		if (q_stop) q_stop[p] = o[2];
-		if (t_start) t_start[p] = o[3];
-		if (t_stop) t_stop[p] = o[4];
-		if (last_two) { last_two[2 * p] = (uint8_t)((o[5] >> 4) & 15); last_two[2 * p + 1] = (uint8_t)(o[5] & 15); }
-	}
 	ctx->stats.kernel_launches = 1;
 	return 0;
 }

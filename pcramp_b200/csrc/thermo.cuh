@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(THERMO_BLOCK, THERMO_MIN_BLOCKS) thermo_kernel
 }
 
 // DP cells of one problem, as SURVEY.md section 8d counts them
-inline long long problem_cells(int op, int qlen, int tlen)
+__host__ __device__ inline long long problem_cells(int op, int qlen, int tlen)
 {
 	switch (op) {
 	case OP_HAIRPIN: {

@@ -7,6 +7,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -46,6 +48,10 @@ struct ThermoState {
 	DpTable h_dp;
 	float dp_salt = -1.0f;
 	DevBuf d_tables, d_dp, d_a, d_b, d_la, d_lb, d_ls, d_out;
+	DevBuf d_text_a, d_text_b, d_note, d_fields; // string batches: the caller's text as it is, {first error, cell count}, one array per result field
+	PinnedBuf h_note;
+	DevBuf d_sort_tmp2;                           // the second stream's sort scratch (pipelined batches)
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	DevBuf d_key[2], d_ord[2], d_sort_tmp; // size-binned launch order (thermo_order)
 	const uint32_t *order = nullptr;
 	PinnedBuf h_a, h_b, h_la, h_lb, h_ls, h_out;
@@ -61,6 +67,8 @@ void thermo_state_free(ThermoState *t)
 	if (!t) return;
 	if (t->ev0) cudaEventDestroy(t->ev0);
 	if (t->ev1) cudaEventDestroy(t->ev1);
+	if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+	if (t->ev_join) cudaEventDestroy(t->ev_join);
 	delete t;
 }
 
@@ -77,6 +85,8 @@ int thermo_get(pcramp_gpu_ctx *ctx, ThermoState **out)
 		ctx->thermo = t;
 		CK(cudaEventCreate(&t->ev0));
 		CK(cudaEventCreate(&t->ev1));
+		CK(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
 	}
 	ThermoState *t = ctx->thermo;
 	if (!t->tables_ready) {
@@ -273,6 +283,325 @@ const char *stage_range(ThermoState *t, int op, uint32_t lo, uint32_t hi, const 
 	return nullptr;
 }
 
+// ---- string batches: the text is encoded on the device ---------------------------------------------------------
+// Error of problem p, ordered as stage_range meets them: key = p << 8 | stage << 4 | detail (stage 0: first sequence, 1: empty
+// hairpin query, 2: second sequence, 3: strand concentration -- the host's); the smallest key is the error the caller sees.
+constexpr unsigned long long NOTE_NONE = ~0ull;
+
+__device__ inline unsigned long long encode_text(const char *__restrict__ s, uint32_t stride, bool allow_inosine, uint8_t *dst, uint8_t *len_out,
+	unsigned long long p, unsigned stage)
+{ // encode_seq on the device
+	uint4 *d = (uint4 *)dst;
+	d[0] = d[1] = make_uint4(0u, 0u, 0u, 0u);
+	uint32_t len = 0;
+	unsigned long long err = NOTE_NONE;
+	while (len < stride) {
+		const char ch = s[len];
+		if (!ch) break;
+		if (len >= (uint32_t)NC_MAX_LEN) { err = (p << 8) | (stage << 4) | 0u; break; }
+		int c;
+		switch (ch) {
+		case 'A': case 'a': c = bA; break;
+		case 'C': case 'c': c = bC; break;
+		case 'G': case 'g': c = bG; break;
+		case 'T': case 't': c = bT; break;
+		case 'I': case 'i': c = bI; break;
+		default: c = -1;
+		}
+		if (c < 0 || (c == bI && !allow_inosine)) { err = (p << 8) | (stage << 4) | 1u; break; }
+		dst[len] = (uint8_t)c;
+		++len;
+	}
+	*len_out = (uint8_t)len;
+	return err;
+}
+
+// problems [p0, p0 + n) of a batch; every pointer is the range's own
+__global__ void __launch_bounds__(256) thermo_encode_kernel(int op, uint32_t n, uint32_t p0, const char *__restrict__ text_a, const char *__restrict__ text_b,
+	uint32_t stride, uint8_t *seq_a, uint8_t *seq_b, uint8_t *len_a, uint8_t *len_b, unsigned long long *note)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long gp = (unsigned long long)p0 + p;
+	unsigned long long err = NOTE_NONE, cells = 0;
+	if (p < n) {
+		const bool two = (op == OP_HETERODIMER || op == OP_HETERODIMER_DIAG);
+		uint8_t la = 0, lb = 0;
+		err = encode_text(text_a + (size_t)p * stride, stride, op != OP_PM_DUPLEX, seq_a + (size_t)p * THERMO_SEQ_STRIDE, &la, gp, 0u);
+		if (err == NOTE_NONE && op == OP_HAIRPIN && la == 0) err = (gp << 8) | (1u << 4);
+		if (err == NOTE_NONE && two) err = encode_text(text_b + (size_t)p * stride, stride, true, seq_b + (size_t)p * THERMO_SEQ_STRIDE, &lb, gp, 2u);
+		len_a[p] = la;
+		len_b[p] = lb;
+		cells = (unsigned long long)problem_cells(op, la, two ? lb : la);
+	}
+	for (int d = 16; d; d >>= 1) {
+		cells += __shfl_xor_sync(0xffffffffu, cells, d);
+		const unsigned long long o = __shfl_xor_sync(0xffffffffu, err, d);
+		err = o < err ? o : err;
+	}
+	if ((threadIdx.x & 31u) == 0u) {
+		if (cells) atomicAdd(note + 1, cells);
+		if (err != NOTE_NONE) atomicMin(note, err);
+	}
+}
+
+__global__ void thermo_fields_kernel(uint32_t n, const float4 *__restrict__ out, float *fields)
+{ // {Tm, dH, dS, dG_dp} records -> one array per field: each leaves with one copy into the caller's array
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	const float4 v = out[p];
+	fields[p] = v.x;
+	fields[(size_t)n + p] = v.y;
+	fields[2 * (size_t)n + p] = v.z;
+	fields[3 * (size_t)n + p] = v.w;
+}
+
+// the strand half of stage_range: logf of the strand concentration of problems [lo, hi) -> *err_p = the first problem with a bad concentration
+const char *stage_strands(ThermoState *t, int op, uint32_t lo, uint32_t hi, const float *strand_a, const float *strand_b, uint32_t *err_p)
+{
+	float *ls = t->h_ls.as<float>();
+	float last_strand = -1.0f, last_log = 0.0f;
+	for (uint32_t p = lo; p < hi; ++p) {
+		float strand = 1.0f;
+		*err_p = p;
+		if (two_sequences(op)) {
+			if (strand_a[p] < 0.0f) return ":strand: m_c_a < 0.0f";
+			if (strand_b[p] < 0.0f) return ":strand: m_c_b < 0.0f";
+			strand = hetero_strand(strand_a[p], strand_b[p]);
+		} else if (needs_strand(op)) {
+			if (strand_a[p] < 0.0f) return ":strand: strand_concentration < 0.0f";
+			strand = strand_a[p];
+		}
+		if (op != OP_PM_DUPLEX && op != OP_HAIRPIN && !(strand > 0.0f)) return ":NucCruc::tm_dimer: Invalid strand_concentration";
+		if (strand != last_strand) { // the float overload the reference's log() resolves to (nuc_cruc.cpp:2129)
+			last_strand = strand;
+			last_log = logf(strand);
+		}
+		ls[p] = last_log;
+	}
+	*err_p = 0xffffffffu;
+	return nullptr;
+}
+
+// Large string batches: the caller's text goes to the device as it is (page-locked arrays move at link speed) and is encoded
+// there, while the host takes the logarithms of the strand concentrations (the reference's libm).  Same errors, in the same
+// order, as the host loop (stage_range) that small batches use.
+constexpr uint32_t THERMO_DEVICE_ENCODE_MIN = 4096;
+const char *stage_strands_all(ThermoState *t, int op, uint32_t n, const float *strand_a, const float *strand_b, uint32_t *err_p);
+int thermo_note_error(pcramp_gpu_ctx *ctx, int op, unsigned long long note, const char *host_msg, uint32_t host_p);
+
+int thermo_stage_strings_device(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
+	const float *strand_a, const float *strand_b)
+{
+	cudaStream_t st = ctx->stream;
+	const bool two = two_sequences(op);
+	if (thermo_reserve(ctx, t, n)) return 1;
+	CK(t->d_text_a.ensure((size_t)n * stride));
+	if (two) CK(t->d_text_b.ensure((size_t)n * stride));
+	CK(t->d_note.ensure(16));
+	CK(t->h_note.ensure(16));
+	CK(cudaStreamSynchronize(st)); // the page-locked staging below may still be the source of an earlier batch's copies
+	unsigned long long *h_note = t->h_note.as<unsigned long long>();
+	h_note[0] = NOTE_NONE;
+	h_note[1] = 0;
+	CK(cudaMemcpyAsync(t->d_note.p, h_note, 16, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(t->d_text_a.p, seq_a, (size_t)n * stride, cudaMemcpyHostToDevice, st));
+	if (two) CK(cudaMemcpyAsync(t->d_text_b.p, seq_b, (size_t)n * stride, cudaMemcpyHostToDevice, st));
+	thermo_encode_kernel<<<grid_for(n, 256), 256, 0, st>>>(op, n, 0u, t->d_text_a.as<char>(), t->d_text_b.as<char>(), stride, t->d_a.as<uint8_t>(),
+		t->d_b.as<uint8_t>(), t->d_la.as<uint8_t>(), t->d_lb.as<uint8_t>(), t->d_note.as<unsigned long long>());
+	CK(cudaGetLastError());
+	// the host's half, while the copies and the encoder run
+	uint32_t host_p = 0xffffffffu;
+	const char *host_msg = stage_strands_all(t, op, n, strand_a, strand_b, &host_p);
+	CK(cudaMemcpyAsync(t->d_ls.p, t->h_ls.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(h_note, t->d_note.p, 16, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	t->op = -1;
+	if (thermo_note_error(ctx, op, h_note[0], host_msg, host_p)) return 1;
+	t->op = op;
+	t->n = n;
+	t->cells = h_note[1];
+	return thermo_order(ctx, t);
+}
+
+// every problem with the same concentrations (the usual batch): one validation, one logf, one fill
+bool strands_uniform(int op, uint32_t n, const float *strand_a, const float *strand_b)
+{
+	if (!n) return false;
+	const bool two = two_sequences(op);
+	if (!two && !needs_strand(op)) return true;
+	const float a0 = strand_a[0], b0 = two ? strand_b[0] : 0.0f;
+	uint32_t diff = 0;
+	for (uint32_t p = 0; p < n; ++p) diff |= (uint32_t)(strand_a[p] != a0);
+	if (two)
+		for (uint32_t p = 0; p < n; ++p) diff |= (uint32_t)(strand_b[p] != b0);
+	return diff == 0;
+}
+
+const char *stage_strands_all(ThermoState *t, int op, uint32_t n, const float *strand_a, const float *strand_b, uint32_t *err_p)
+{
+	if (strands_uniform(op, n, strand_a, strand_b)) {
+		const char *e = stage_strands(t, op, 0, 1, strand_a, strand_b, err_p);
+		if (e) return e; // problem 0 is the first to fail
+		float *ls = t->h_ls.as<float>();
+		std::fill(ls + 1, ls + n, ls[0]);
+		return nullptr;
+	}
+	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+	const uint32_t n_thr = n < 65536u ? 1u : std::min<uint32_t>(8u, hw);
+	std::vector<const char *> err(n_thr, nullptr);
+	std::vector<uint32_t> where(n_thr, 0xffffffffu);
+	if (n_thr == 1) {
+		err[0] = stage_strands(t, op, 0, n, strand_a, strand_b, &where[0]);
+	} else {
+		std::vector<std::thread> pool;
+		for (uint32_t k = 0; k < n_thr; ++k) {
+			const uint32_t lo = (uint32_t)((uint64_t)n * k / n_thr), hi = (uint32_t)((uint64_t)n * (k + 1) / n_thr);
+			pool.emplace_back([&, k, lo, hi]() { err[k] = stage_strands(t, op, lo, hi, strand_a, strand_b, &where[k]); });
+		}
+		for (std::thread &th : pool) th.join();
+	}
+	for (uint32_t k = 0; k < n_thr; ++k)
+		if (err[k]) { *err_p = where[k]; return err[k]; } // ranges ascend: the first is the smallest
+	*err_p = 0xffffffffu;
+	return nullptr;
+}
+
+int thermo_note_error(pcramp_gpu_ctx *ctx, int op, unsigned long long note, const char *host_msg, uint32_t host_p)
+{ // the smallest of the device's and the host's first errors (NOTE_NONE / null: none); 0 = no error
+	const unsigned long long host_key = host_msg ? (((unsigned long long)host_p << 8) | (3u << 4)) : NOTE_NONE;
+	if (note < host_key) {
+		const unsigned stage = (unsigned)(note >> 4) & 15u, detail = (unsigned)note & 15u;
+		if (stage == 1u) return fail(ctx, ":NucCruc::align_hairpin: Empty query sequence");
+		if (detail == 0u) return fail(ctx, "pcramp_gpu_thermo: sequence longer than 32 bases (Word length)");
+		return fail(ctx, (stage == 2u || op != OP_PM_DUPLEX) ? ":set_query: Illegal base" : "Unknown base in tm_pm_duplex");
+	}
+	if (host_msg) return fail(ctx, host_msg);
+	return 0;
+}
+
+int thermo_order_range(pcramp_gpu_ctx *ctx, ThermoState *t, cudaStream_t st, DevBuf &tmp, size_t tmp_bytes, uint32_t lo, uint32_t m)
+{ // thermo_order for problems [lo, lo + m): a launch order local to the range
+	thermo_key_kernel<<<grid_for(m, 256), 256, 0, st>>>(t->op, m, t->d_la.as<uint8_t>() + lo, t->d_lb.as<uint8_t>() + lo, t->d_key[0].as<uint16_t>() + lo,
+		t->d_ord[0].as<uint32_t>() + lo);
+	CK(cudaGetLastError());
+	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, t->d_key[0].as<uint16_t>() + lo, t->d_key[1].as<uint16_t>() + lo, t->d_ord[0].as<uint32_t>() + lo,
+		t->d_ord[1].as<uint32_t>() + lo, (int)m, 0, 12, st));
+	return 0;
+}
+
+// One call = one batch, host arrays in and out: the batch is cut into chunks that alternate between the context's two streams, so
+// the copies of one chunk (text in, fields out) run beside the kernel of another.  Each chunk: text -> device, encode, launch order,
+// thermo_kernel, fields, one copy per result array the caller wants.  The host takes the logarithms while the first chunk's text moves.
+constexpr uint32_t THERMO_PIPELINE_MIN = 65536;
+constexpr int THERMO_PIPELINE_CHUNKS = 4;
+
+int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
+	const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp)
+{
+	if (op < 0 || op >= OP_COUNT) return fail(ctx, "pcramp_gpu_thermo: unknown op");
+	if (!seq_a || stride == 0) return fail(ctx, "pcramp_gpu_thermo: null sequences");
+	const bool two = two_sequences(op);
+	if (two && (!seq_b || !strand_b)) return fail(ctx, "pcramp_gpu_thermo: heterodimer ops need seq_b and strand_b");
+	if (needs_strand(op) && !strand_a) return fail(ctx, "pcramp_gpu_thermo: null strand concentration");
+	cudaStream_t streams[2] = {ctx->stream, ctx->stream2 ? ctx->stream2 : ctx->stream};
+	if (thermo_reserve(ctx, t, n)) return 1;
+	CK(t->d_text_a.ensure((size_t)n * stride));
+	if (two) CK(t->d_text_b.ensure((size_t)n * stride));
+	CK(t->d_note.ensure(16));
+	CK(t->h_note.ensure(16));
+	CK(t->d_fields.ensure((size_t)n * 16));
+	const uint32_t chunk = (n + THERMO_PIPELINE_CHUNKS - 1) / THERMO_PIPELINE_CHUNKS;
+	const bool ordered = op != OP_PM_DUPLEX;
+	size_t tmp_bytes = 0;
+	if (ordered) {
+		for (int k = 0; k < 2; ++k) {
+			CK(t->d_key[k].ensure((size_t)n * 2));
+			CK(t->d_ord[k].ensure((size_t)n * 4));
+		}
+		CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, t->d_key[0].as<uint16_t>(), t->d_key[1].as<uint16_t>(), t->d_ord[0].as<uint32_t>(),
+			t->d_ord[1].as<uint32_t>(), (int)chunk, 0, 12, streams[0]));
+		CK(t->d_sort_tmp.ensure(tmp_bytes));
+		CK(t->d_sort_tmp2.ensure(tmp_bytes));
+	}
+	CK(cudaStreamSynchronize(streams[0])); // the page-locked staging below may still be the source of an earlier batch's copies
+	unsigned long long *h_note = t->h_note.as<unsigned long long>();
+	h_note[0] = NOTE_NONE;
+	h_note[1] = 0;
+	CK(cudaMemcpyAsync(t->d_note.p, h_note, 16, cudaMemcpyHostToDevice, streams[0]));
+	CK(cudaEventRecord(t->ev_fork, streams[0]));
+	if (streams[1] != streams[0]) CK(cudaStreamWaitEvent(streams[1], t->ev_fork, 0));
+	t->op = op;
+	t->n = n;
+	t->order = nullptr;
+	const char *host_msg = nullptr;
+	uint32_t host_p = 0xffffffffu;
+	float *dst[4] = {tm, dH, dS, dG_dp};
+	const bool trace = getenv("PCRAMP_TRACE") != nullptr;
+	cudaEvent_t tev[THERMO_PIPELINE_CHUNKS][4] = {};
+	if (trace)
+		for (auto &row : tev)
+			for (cudaEvent_t &e : row) cudaEventCreate(&e);
+	CK(cudaEventRecord(t->ev0, streams[0]));
+	for (int c = 0; c < THERMO_PIPELINE_CHUNKS; ++c) {
+		const uint32_t lo = (uint32_t)c * chunk;
+		if (lo >= n) break;
+		const uint32_t m = std::min(chunk, n - lo);
+		cudaStream_t st = streams[c & 1];
+		if (trace) cudaEventRecord(tev[c][0], st);
+		CK(cudaMemcpyAsync(t->d_text_a.as<char>() + (size_t)lo * stride, seq_a + (size_t)lo * stride, (size_t)m * stride, cudaMemcpyHostToDevice, st));
+		if (two) CK(cudaMemcpyAsync(t->d_text_b.as<char>() + (size_t)lo * stride, seq_b + (size_t)lo * stride, (size_t)m * stride, cudaMemcpyHostToDevice, st));
+		thermo_encode_kernel<<<grid_for(m, 256), 256, 0, st>>>(op, m, lo, t->d_text_a.as<char>() + (size_t)lo * stride, t->d_text_b.as<char>() + (size_t)lo * stride,
+			stride, t->d_a.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_b.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_la.as<uint8_t>() + lo,
+			t->d_lb.as<uint8_t>() + lo, t->d_note.as<unsigned long long>());
+		CK(cudaGetLastError());
+		if (c == 0) host_msg = stage_strands_all(t, op, n, strand_a, strand_b, &host_p); // the host's half, while the first chunk's text moves
+		CK(cudaMemcpyAsync(t->d_ls.as<float>() + lo, t->h_ls.as<float>() + lo, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, st));
+		const uint32_t *order = nullptr;
+		if (ordered) {
+			if (thermo_order_range(ctx, t, st, (c & 1) ? t->d_sort_tmp2 : t->d_sort_tmp, tmp_bytes, lo, m)) return 1;
+			order = t->d_ord[1].as<uint32_t>() + lo;
+		}
+		if (trace) cudaEventRecord(tev[c][1], st);
+		thermo_kernel<<<grid_for(m, THERMO_BLOCK), THERMO_BLOCK, 0, st>>>(op, m, order, t->d_a.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE,
+			t->d_b.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_la.as<uint8_t>() + lo, t->d_lb.as<uint8_t>() + lo, t->d_ls.as<float>() + lo,
+			t->d_tables.as<Tables>(), t->d_dp.as<DpTable>(), t->d_out.as<float4>() + lo);
+		CK(cudaGetLastError());
+		float *fields = t->d_fields.as<float>() + 4 * (size_t)lo;
+		if (trace) cudaEventRecord(tev[c][2], st);
+		thermo_fields_kernel<<<grid_for(m, 256), 256, 0, st>>>(m, t->d_out.as<float4>() + lo, fields);
+		CK(cudaGetLastError());
+		for (int k = 0; k < 4; ++k)
+			if (dst[k]) CK(cudaMemcpyAsync(dst[k] + lo, fields + (size_t)k * m, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+		if (trace) cudaEventRecord(tev[c][3], st);
+	}
+	if (streams[1] != streams[0]) {
+		CK(cudaEventRecord(t->ev_join, streams[1]));
+		CK(cudaStreamWaitEvent(streams[0], t->ev_join, 0));
+	}
+	CK(cudaEventRecord(t->ev1, streams[0]));
+	CK(cudaMemcpyAsync(h_note, t->d_note.p, 16, cudaMemcpyDeviceToHost, streams[0]));
+	CK(cudaStreamSynchronize(streams[0]));
+	t->cells = h_note[1];
+	t->stats.n_problems = n;
+	t->stats.dp_cells = t->cells;
+	t->stats.kernel_launches = (n + chunk - 1) / chunk;
+	float ms = 0.0f;
+	cudaEventElapsedTime(&ms, t->ev0, t->ev1);
+	t->stats.ms_kernel = ms; // the whole pipeline here (copies included): the kernel's own time is a staged run's
+	t->op = -1;              // nothing stays staged: the chunks were ordered one by one
+	if (trace) {
+		for (int c = 0; c < THERMO_PIPELINE_CHUNKS; ++c) {
+			float v[4] = {0, 0, 0, 0};
+			for (int k = 0; k < 4; ++k) {
+				if ((uint64_t)c * chunk < n) cudaEventElapsedTime(&v[k], t->ev0, tev[c][k]);
+				cudaEventDestroy(tev[c][k]);
+			}
+			fprintf(stderr, "[pcramp thermo] chunk %d: copy in from %.3f ms, kernel %.3f .. %.3f ms, results out by %.3f ms (of %.3f)\n", c, v[0], v[1], v[2], v[3], ms);
+		}
+	}
+	return thermo_note_error(ctx, op, h_note[0], host_msg, host_p);
+}
+
 int thermo_stage_strings(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
 	const float *strand_a, const float *strand_b)
 {
@@ -280,6 +609,7 @@ int thermo_stage_strings(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n
 	if (n && (!seq_a || stride == 0)) return fail(ctx, "pcramp_gpu_thermo: null sequences");
 	if (n && two_sequences(op) && (!seq_b || !strand_b)) return fail(ctx, "pcramp_gpu_thermo: heterodimer ops need seq_b and strand_b");
 	if (n && needs_strand(op) && !strand_a) return fail(ctx, "pcramp_gpu_thermo: null strand concentration");
+	if (n >= THERMO_DEVICE_ENCODE_MIN) return thermo_stage_strings_device(ctx, t, op, n, seq_a, seq_b, stride, strand_a, strand_b);
 	if (thermo_reserve(ctx, t, n)) return 1;
 	// host staging is a plain byte loop: split it over a few threads for large batches
 	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -407,6 +737,22 @@ int pcramp_gpu_thermo_fetch(pcramp_gpu_ctx *ctx, float *tm, float *dH, float *dS
 	CK(cudaSetDevice(ctx->device));
 	ThermoState *t = ctx->thermo;
 	if (!t || t->op < 0) return fail(ctx, "pcramp_gpu_thermo_fetch: nothing staged");
+	if (t->n >= THERMO_DEVICE_ENCODE_MIN) { // one array per field on the device, one copy per array the caller wants
+		const uint32_t n = t->n;
+		CK(t->d_fields.ensure((size_t)n * 16));
+		thermo_fields_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, t->d_out.as<float4>(), t->d_fields.as<float>());
+		CK(cudaGetLastError());
+		float *dst[4] = {tm, dH, dS, dG_dp};
+		for (int k = 0; k < 4; ++k)
+			if (dst[k]) CK(cudaMemcpyAsync(dst[k], t->d_fields.as<float>() + (size_t)k * n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (t->stats.kernel_launches) {
+			float ms = 0.0f;
+			cudaEventElapsedTime(&ms, t->ev0, t->ev1);
+			t->stats.ms_kernel = ms;
+		}
+		return 0;
+	}
 	if (thermo_download(ctx, t)) return 1;
 	const float4 *o = t->h_out.as<float4>();
 	for (uint32_t p = 0; p < t->n; ++p) {
@@ -421,6 +767,13 @@ int pcramp_gpu_thermo_fetch(pcramp_gpu_ctx *ctx, float *tm, float *dH, float *dS
 int pcramp_gpu_thermo_batch(pcramp_gpu_ctx *ctx, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride, float salt,
 	const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp)
 {
+	if (ctx && n >= THERMO_PIPELINE_MIN) {
+		CK(cudaSetDevice(ctx->device));
+		ThermoState *t = nullptr;
+		if (thermo_get(ctx, &t)) return 1;
+		if (thermo_set_salt(ctx, t, salt)) return 1;
+		return thermo_batch_pipelined(ctx, t, op, n, seq_a, seq_b, stride, strand_a, strand_b, tm, dH, dS, dG_dp);
+	}
 	if (pcramp_gpu_thermo_stage(ctx, op, n, seq_a, seq_b, stride, salt, strand_a, strand_b)) return 1;
 	if (pcramp_gpu_thermo_run_staged(ctx)) return 1;
 	return pcramp_gpu_thermo_fetch(ctx, tm, dH, dS, dG_dp);

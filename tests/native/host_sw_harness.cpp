@@ -19,7 +19,9 @@ int host_sw_batch(unsigned n, const uint64_t *query, const uint64_t *target, int
 		sw::Query q;
 		sw::query_from_word(qw, q);
 		const sw::WordTarget t(tw);
-		const sw::Result r = with_start ? sw::align<true>(q, t) : sw::align<false>(q, t);
+		// every second problem through the instantiation a warp would pick for it, the others through the full-height one
+		const int rows = (p & 1u) ? q.len : sw::SW_MAX_QUERY;
+		const sw::Result r = with_start ? sw::align_rows<true>(q, t, rows) : sw::align_rows<false>(q, t, rows);
 		unsigned a, b;
 		sw::last_two(r, t, a, b);
 		int *o = out + 6 * (size_t)p;

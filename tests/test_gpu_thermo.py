@@ -116,3 +116,65 @@ def test_thermo_errors_mirror_reference(gpu):
         gpu.thermo_batch(1, ["ACGTACGTAC"], salt=2.0)
     with pytest.raises(api.GpuError, match="strand"):
         gpu.thermo_batch(2, ["ACGTACGTAC"], strand_a=0.0)
+
+
+def _cells(op, a, b):
+    la, lb = len(a), len(b)
+    if op == 1:
+        return max(0, la - 4) * (max(0, la - 4) + 1) // 2
+    return {0: 0, 2: la * la, 3: la * lb, 4: min(la, lb), 5: la}[op]
+
+
+@pytest.mark.parametrize("op", tc.OPS)
+def test_large_batches_equal_small_ones(gpu, op):
+    """the three ways a string batch reaches the kernel -- host encoding (small), device encoding (>= 4096), chunks alternating
+    between two streams (>= 65536 through thermo_batch) -- give the same bits"""
+    n = 70001
+    A, B, sa, sb = tc.problems(33, 5000, op)
+    two = op in tc.TWO_SEQ
+    idx = np.random.default_rng(3).integers(0, 5000, size=n)
+    A2 = [A[i] for i in idx]
+    B2 = [B[i] for i in idx] if two else None
+    sa2, sb2 = sa[idx], (sb[idx] if two else None)
+    small = gpu.thermo_batch(op, A[:4000], B[:4000] if two else None, 0.05, sa[:4000], sb[:4000] if two else None)
+    piped = gpu.thermo_batch(op, A2, B2, 0.05, sa2, sb2)
+    st = gpu.thermo_stats()
+    assert st["kernel_launches"] == 4 and st["n_problems"] == n
+    want_cells = sum(_cells(op, a, b) for a, b in zip(A2, B2 if two else A2))
+    assert st["dp_cells"] == want_cells
+    gpu.thermo_stage(op, A2, B2, 0.05, sa2, sb2)
+    gpu.thermo_run_staged()
+    staged = gpu.thermo_fetch()
+    assert gpu.thermo_stats()["dp_cells"] == want_cells
+    keep = idx < 4000
+    for a, b, c in zip(piped, staged, small):
+        assert np.array_equal(bits(a), bits(b))
+        assert np.array_equal(bits(a[keep]), bits(c[idx[keep]]))
+
+
+def test_large_batch_errors_keep_their_order(gpu):
+    """the first failing problem decides the message, whether the device (text) or the host (strand concentrations) finds it"""
+    n = 70000
+    A = ["ACGTACGTACGTACGTAC"] * n
+    for m in (5000, n):                      # device encoding; chunks on two streams
+        a = list(A[:m])
+        a[m - 7] = "ACGTNACGT"
+        with pytest.raises(api.GpuError, match="Illegal base"):
+            gpu.thermo_batch(2, a)
+        with pytest.raises(api.GpuError, match="Unknown base"):
+            gpu.thermo_batch(0, a)
+        strands = np.full(m, 9e-7, np.float32)
+        strands[m - 9] = -1.0
+        with pytest.raises(api.GpuError, match="strand"):      # the bad concentration comes first
+            gpu.thermo_batch(2, a, strand_a=strands)
+        strands[m - 9], strands[m - 5] = 9e-7, -1.0
+        with pytest.raises(api.GpuError, match="Illegal base"):  # the bad base comes first
+            gpu.thermo_batch(2, a, strand_a=strands)
+        a[m - 7] = "ACGT" * 9
+        with pytest.raises(api.GpuError, match="longer than 32"):
+            gpu.thermo_batch(2, api.pack_strings(a, 40))
+        a[m - 7] = ""
+        with pytest.raises(api.GpuError, match="Empty query"):
+            gpu.thermo_batch(1, a)
+        good = gpu.thermo_batch(2, A[:m])    # and the context still works afterwards
+        assert np.all(bits(good[0]) == bits(good[0][:1]))
