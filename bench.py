@@ -64,6 +64,11 @@ def parse_args():
     ap.add_argument("--fasta-targets", type=int, default=8000, help="sequences in the FASTA-ingest leg (0 = skip; rank 0 only)")
     ap.add_argument("--dp-problems", type=int, default=262144, help="NucCruc problems per step of the DP GCUPS leg (0 = skip the leg)")
     ap.add_argument("--dp-cpu-problems", type=int, default=60000, help="problems in the bounded CPU sample of the DP leg")
+    ap.add_argument("--config-legs", default="background,degenerate,optimize,design,large",
+                    help="legs for the other BASELINE configurations (bench_legs.py; rank 0, N = 1): any of background (C2), degenerate (C3), "
+                         "optimize (C1 moves), design (C1 iterations), large (C4 shape); 'none' skips them")
+    ap.add_argument("--c4-targets", type=int, default=64, help="genomes in the large-genome leg")
+    ap.add_argument("--c4-length", type=int, default=5000000, help="bases per genome in the large-genome leg")
     return ap.parse_args()
 
 
@@ -962,8 +967,22 @@ def run_b200(a):
         jobs = 1 if by_targets else world                  # pair-sharded: every rank moves its own batch
         h2d = 2 * P * 16 * jobs
         d2h = (P * 4 + P * n_words_global * 4) * jobs
+        import bench_legs
+        want = set() if (a.config_legs == "none" or world > 1) else set(a.config_legs.split(","))
+        a.hbm_peak = hbm_peak
+        cfg = {}
+        if "degenerate" in want:
+            cfg["degenerate_primers"] = bench_legs.degenerate_leg(a, g, factory, coll, local, parity_at_bench)
+        if "background" in want:
+            cfg["background_scan"] = bench_legs.background_leg(a, local)
+        if "optimize" in want:
+            cfg["optimize_moves"] = bench_legs.optimize_leg(a, local)
+        if "design" in want:
+            cfg["design_iteration"] = bench_legs.design_leg(a, local)
+        if "large" in want:
+            cfg["large_genomes"] = bench_legs.large_genome_leg(a, local)
         legs = {
-            "dp_gcups": dp, "target_sharded": tsh,
+            "dp_gcups": dp, "target_sharded": tsh, "configs": cfg,
             "sw_gcups": sw_leg(a, g, ext, torch) if a.dp_problems > 0 else None,
             "candidate_generation": candidate_leg(a, g, factory) if a.fasta_targets > 0 else None,
             "fasta_ingest": fasta_leg(a, g, coll, hbm_peak) if a.fasta_targets > 0 else None}
@@ -998,6 +1017,10 @@ def run_b200(a):
             "cpu_reference_evals_per_s": None if cpu_baseline is None else cpu_baseline["value"],
             "dp_gcups": None if dp is None else dp["value"], "dp_gcups_e2e": None if dp is None else dp["e2e"]["value"],
             "sw_gcups": None if legs["sw_gcups"] is None else legs["sw_gcups"]["value"],
+            "sw_gcups_e2e": None if legs["sw_gcups"] is None else legs["sw_gcups"]["e2e"]["value"],
+            "configs": {k: {"value": v["value"], "unit": v["unit"], "ms": v.get("ms_per_step", v.get("ms_per_iteration")),
+                            "cpu": None if not v.get("cpu_baseline") else v["cpu_baseline"]["value"],
+                            "parity": None if not v.get("parity") else v["parity"]["ok"]} for k, v in cfg.items()},
             "target_sharded_evals_per_s": None if tsh is None else tsh["value"],
             "target_sharded_ms_per_step": None if tsh is None else tsh["ms_per_step"],
             "timed_seconds": ms_resident * reps_resident * 1e-3}

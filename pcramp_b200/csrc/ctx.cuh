@@ -222,6 +222,10 @@ struct pcramp_gpu_ctx {
 	bool amp_bounds_ok = false;
 	std::vector<uint64_t> amp_words; // F0 R0 F1 R1 ... of that call
 	DevBuf sw_q, sw_t, sw_out;       // pcramp_gpu_sw_batch staging (kept between calls)
+	DevBuf d_variant_groups;         // score_variants: base assays of the groups + group offsets
+	std::vector<uint64_t> h_group_words;
+	std::vector<uint32_t> h_group_off;
+	int use_variant_groups = 1;      // option "use_variant_groups"
 	float sw_ms_kernel = 0.0f;
 };
 

@@ -18,7 +18,9 @@
 #include "ctx.cuh"
 #include "nuccruc.cuh"
 
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -71,6 +73,33 @@ struct Variant {
 	float cov_m = 0.0f, ov = 0.0f; // multiplex background coverage; max over the pool of max_overlap(trial oligo, .)
 	uint32_t first_exp = 0, n_exp = 0; // its expansions in the thermo batch
 };
+
+// host loops over independent trials / variants, split over a few threads: fn(part, lo, hi) on [lo, hi) of n items
+template <class F>
+inline void parallel_ranges(size_t n, size_t min_per_part, const std::vector<size_t> *cuts, F fn)
+{
+	const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+	size_t parts = std::min<size_t>(std::min<size_t>(8, hw), n / std::max<size_t>(1, min_per_part));
+	if (parts <= 1) {
+		fn(0, 0, n);
+		return;
+	}
+	std::vector<size_t> edge(parts + 1, n);
+	edge[0] = 0;
+	for (size_t k = 1; k < parts; ++k) {
+		size_t e = n * k / parts;
+		if (cuts) { // move the edge up to the next allowed cut (a sorted list of item indices)
+			const auto it = std::lower_bound(cuts->begin(), cuts->end(), e);
+			e = it == cuts->end() ? n : *it;
+		}
+		edge[k] = std::max(e, edge[k - 1]);
+	}
+	std::vector<std::thread> pool;
+	for (size_t k = 0; k < parts; ++k)
+		if (edge[k] < edge[k + 1]) pool.emplace_back([&, k]() { fn(k, edge[k], edge[k + 1]); });
+	for (std::thread &t : pool) t.join();
+}
+constexpr size_t PARALLEL_PARTS = 8;
 
 // the trial oligos a move evaluates, in the reference's order (optimize_pcr.cpp)
 inline void move_variants(int move, const W128 &o, uint32_t degen_max, int primer_min, int primer_max, std::vector<W128> &out)
@@ -213,11 +242,23 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 	std::vector<uint8_t> codes, lens;
 	std::vector<float> strand, tm;
 	uint64_t launches = 0;
+	// PCRAMP_TRACE=1: host wall clock per stage, summed over the rounds
+	const bool trace_on = getenv("PCRAMP_TRACE") != nullptr;
+	double tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tr_last = trace_on ? Trace::now() : 0.0;
+	auto lap = [&](int k) {
+		if (!trace_on) return;
+		const double t = Trace::now();
+		tr_acc[k] += t - tr_last;
+		tr_last = t;
+	};
+	uint32_t rounds = 0;
+	uint64_t tr_vars = 0, tr_exp = 0, tr_hp = 0, tr_scored = 0;
 	for (;;) {
 		idx.clear();
 		for (uint32_t t = 0; t < n; ++t)
 			if (live[t]) idx.push_back(t);
 		if (idx.empty()) break;
+		++rounds;
 		const uint32_t na = (uint32_t)idx.size();
 		// ---- score the current assays (optimize.cpp:62-75) -------------------------------------------------
 		pf.resize(2ull * na);
@@ -252,7 +293,9 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 				best_r[idx[k]] = ovl[2 * k + 1];
 			}
 		}
+		lap(0);
 		vars.clear();
+		std::vector<uint32_t> gen; // the trials that go on to try their moves
 		for (uint32_t k = 0; k < na; ++k) {
 			const uint32_t t = idx[k];
 			++iters[t];
@@ -270,72 +313,117 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 			best[t] = approx[t];
 			bf[t] = af[t];
 			br[t] = ar[t];
-			// ---- the trial oligos of every move, FORWARD then REVERSE, in move-list order (optimize.cpp:117-139) -----
-			for (int og = 0; og < 2; ++og)
-				for (uint32_t m = 0; m < n_moves; ++m) {
-					move_variants(moves[m], og ? ar[t] : af[t], o->degen, o->primer_min, o->primer_max, tmp);
-					for (const W128 &w : tmp) {
-						Variant v;
-						v.trial = t;
-						v.oligo = og;
-						v.move = (int)m;
-						v.w = w;
-						vars.push_back(v);
-					}
+			gen.push_back(t);
+		}
+		// ---- the trial oligos of every move, FORWARD then REVERSE, in move-list order (optimize.cpp:117-139) -----
+		{
+			std::vector<Variant> part[PARALLEL_PARTS];
+			bool bad[PARALLEL_PARTS] = {};
+			parallel_ranges(gen.size(), 16, nullptr, [&](size_t which, size_t lo, size_t hi) {
+				std::vector<W128> local;
+				std::vector<Variant> &out = part[which];
+				for (size_t g = lo; g < hi; ++g) {
+					const uint32_t t = gen[g];
+					for (int og = 0; og < 2; ++og)
+						for (uint32_t m = 0; m < n_moves; ++m) {
+							move_variants(moves[m], og ? ar[t] : af[t], o->degen, o->primer_min, o->primer_max, local);
+							for (const W128 &w : local) {
+								Variant v;
+								v.trial = t;
+								v.oligo = og;
+								v.move = (int)m;
+								v.w = w;
+								const uint64_t c = expansion_count(w);
+								if (c == 0 || c > (1ull << 20)) bad[which] = true;
+								v.n_exp = (uint32_t)c;
+								out.push_back(v);
+							}
+						}
 				}
+			});
+			for (size_t k = 0; k < PARALLEL_PARTS; ++k) {
+				if (bad[k]) return fail(ctx, "pcramp_gpu_optimize: empty or too degenerate trial oligo");
+				vars.insert(vars.end(), part[k].begin(), part[k].end());
+			}
 		}
 		// ---- PCR::is_valid without the dimer check (valid_pcr.cpp:5-45): duplex Tm of every expansion ... ---------------
 		uint64_t n_exp = 0;
 		for (Variant &v : vars) {
 			v.first_exp = (uint32_t)n_exp;
-			const uint64_t c = expansion_count(v.w);
-			if (c == 0 || c > (1ull << 20)) return fail(ctx, "pcramp_gpu_optimize: empty or too degenerate trial oligo");
-			v.n_exp = (uint32_t)c;
-			n_exp += c;
+			n_exp += v.n_exp;
 		}
 		if (n_exp > 0xffffffffull) return fail(ctx, "pcramp_gpu_optimize: too many trial oligos in one iteration");
 		codes.assign((size_t)n_exp * 32, 0);
 		lens.assign(n_exp, 0);
 		strand.assign(n_exp, 0.0f);
 		tm.assign(n_exp, 0.0f);
-		for (const Variant &v : vars) {
-			const double dg = degeneracy(v.w);
-			const float st = (float)((double)o->primer_strand / dg); // valid_pcr.cpp:13
-			for (uint32_t e = 0; e < v.n_exp; ++e) {
-				int len = 0;
-				expansion_codes(v.w, e, codes.data() + (size_t)(v.first_exp + e) * 32, len);
-				lens[v.first_exp + e] = (uint8_t)len;
-				strand[v.first_exp + e] = st;
+		parallel_ranges(vars.size(), 2048, nullptr, [&](size_t, size_t lo, size_t hi) {
+			for (size_t i = lo; i < hi; ++i) {
+				const Variant &v = vars[i];
+				const double dg = degeneracy(v.w);
+				const float st = (float)((double)o->primer_strand / dg); // valid_pcr.cpp:13
+				for (uint32_t e = 0; e < v.n_exp; ++e) {
+					int len = 0;
+					expansion_codes(v.w, e, codes.data() + (size_t)(v.first_exp + e) * 32, len);
+					lens[v.first_exp + e] = (uint8_t)len;
+					strand[v.first_exp + e] = st;
+				}
 			}
-		}
+		});
+		lap(1);
+		tr_vars += vars.size();
+		tr_exp += n_exp;
 		if (nc::thermo_run_codes(ctx, nc::OP_PM_DUPLEX, (uint32_t)n_exp, codes.data(), lens.data(), strand.data(), o->salt, tm.data())) return 1;
 		launches += 1;
+		lap(2);
 		// ... then the hairpin of the expansions whose duplex passed, with the stale slots of the trial's NucCruc object.
 		// Replay per trial, in call order: an expansion is loaded (set_query) when its duplex Tm is in range.
 		std::vector<uint32_t> hp_src; // expansion index of each hairpin problem
 		std::vector<uint8_t> hp_codes, hp_lens;
 		std::vector<float> hp_strand;
-		for (Variant &v : vars) {
-			std::vector<uint8_t> &rg = ring[v.trial];
-			v.valid = true;
-			for (uint32_t e = 0; e < v.n_exp; ++e) {
-				const uint32_t x = v.first_exp + e;
-				const float t_pm = tm[x];
-				if ((t_pm < o->primer_tm_min) || (t_pm > o->primer_tm_max)) { // valid_pcr.cpp:20-22: return false
-					v.valid = false;
-					break;
+		{
+			std::vector<size_t> cuts; // first variant of every trial: a trial's variants share its ring buffer and stay on one thread
+			for (size_t i = 0; i < vars.size(); ++i)
+				if (i == 0 || vars[i].trial != vars[i - 1].trial) cuts.push_back(i);
+			struct Part {
+				std::vector<uint32_t> src;
+				std::vector<uint8_t> codes, lens;
+				std::vector<float> strand;
+			} part[PARALLEL_PARTS];
+			parallel_ranges(vars.size(), 4096, &cuts, [&](size_t which, size_t lo, size_t hi) {
+				Part &P = part[which];
+				for (size_t i = lo; i < hi; ++i) {
+					Variant &v = vars[i];
+					std::vector<uint8_t> &rg = ring[v.trial];
+					v.valid = true;
+					for (uint32_t e = 0; e < v.n_exp; ++e) {
+						const uint32_t x = v.first_exp + e;
+						const float t_pm = tm[x];
+						if ((t_pm < o->primer_tm_min) || (t_pm > o->primer_tm_max)) { // valid_pcr.cpp:20-22: return false
+							v.valid = false;
+							break;
+						}
+						const int len = lens[x];
+						uint8_t slot[32];
+						memcpy(slot, codes.data() + (size_t)x * 32, 32);
+						for (int k = len; k < 32 && k < len + 2; ++k) slot[k] = rg[k]; // what set_query leaves behind past the new end
+						for (int k = 0; k < len; ++k) rg[k] = slot[k];                  // set_query (nuc_cruc.h:875-913)
+						P.src.push_back(x);
+						P.codes.insert(P.codes.end(), slot, slot + 32);
+						P.lens.push_back((uint8_t)len);
+						P.strand.push_back(strand[x]);
+					}
 				}
-				const int len = lens[x];
-				uint8_t slot[32];
-				memcpy(slot, codes.data() + (size_t)x * 32, 32);
-				for (int k = len; k < 32 && k < len + 2; ++k) slot[k] = rg[k]; // what set_query leaves behind past the new end
-				for (int k = 0; k < len; ++k) rg[k] = slot[k];                  // set_query (nuc_cruc.h:875-913)
-				hp_src.push_back(x);
-				hp_codes.insert(hp_codes.end(), slot, slot + 32);
-				hp_lens.push_back((uint8_t)len);
-				hp_strand.push_back(strand[x]);
+			});
+			for (const Part &P : part) {
+				hp_src.insert(hp_src.end(), P.src.begin(), P.src.end());
+				hp_codes.insert(hp_codes.end(), P.codes.begin(), P.codes.end());
+				hp_lens.insert(hp_lens.end(), P.lens.begin(), P.lens.end());
+				hp_strand.insert(hp_strand.end(), P.strand.begin(), P.strand.end());
 			}
 		}
+		lap(3);
+		tr_hp += hp_src.size();
 		std::vector<float> hp_tm(hp_src.size(), 0.0f);
 		if (!hp_src.empty()) {
 			if (nc::thermo_run_codes(ctx, nc::OP_HAIRPIN, (uint32_t)hp_src.size(), hp_codes.data(), hp_lens.data(), hp_strand.data(), o->salt,
@@ -351,6 +439,7 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 					if (hp_of[v.first_exp + e] > o->max_hairpin) { v.valid = false; break; } // valid_pcr.cpp:28-30
 			}
 		}
+		lap(4);
 		// ---- coverage of the valid trial oligos against the unmoved assay's candidates ---------------------------------
 		std::vector<uint32_t> vi;
 		for (uint32_t k = 0; k < vars.size(); ++k)
@@ -397,6 +486,8 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 			vars[vi[k]].cov_m = cov_m[k];
 			vars[vi[k]].ov = ovl[k];
 		}
+		lap(5);
+		tr_scored += nv;
 		// ---- selection, per trial, in the reference's order ------------------------------------------------------------
 		size_t pos = 0;
 		for (uint32_t k = 0; k < na; ++k) {
@@ -455,7 +546,13 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 			}
 			previous[t].insert(key);
 		}
+		lap(6);
 	}
+	if (trace_on)
+		fprintf(stderr, "[trace] optimize: %u rounds, %llu variants, %llu duplex + %llu hairpin problems, %llu variants scored; ms: score current %.1f, "
+			"variants + expansions %.1f, duplex Tm %.1f, hairpin replay %.1f, hairpin Tm %.1f, score variants %.1f, selection %.1f\n", rounds,
+			(unsigned long long)tr_vars, (unsigned long long)tr_exp, (unsigned long long)tr_hp, (unsigned long long)tr_scored, tr_acc[0], tr_acc[1],
+			tr_acc[2], tr_acc[3], tr_acc[4], tr_acc[5], tr_acc[6]);
 	for (uint32_t t = 0; t < n; ++t) {
 		f[2 * t] = bf[t].hi; f[2 * t + 1] = bf[t].lo;
 		r[2 * t] = br[t].hi; r[2 * t + 1] = br[t].lo;

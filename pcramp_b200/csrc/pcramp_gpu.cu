@@ -2113,6 +2113,52 @@ int pcramp_gpu_score_pairs_staged(pcramp_gpu_ctx *ctx, int kind, float search_th
 // The scoring step of an optimisation move for a batch of trial oligos (optimize_pcr.cpp:8-989: every move is
 // "mutate one oligo -> is_valid -> update_identity -> compute_coverage" against the candidate amplicons that
 // collect_candidates built for the UNMOVED assay): variant i is scored against the candidate list of base assay i.
+// score_variants by groups of variants that share their base assay (score_entries_groups_kernel): d_words = {variant F, variant R,
+// group base F, group base R}; -> 0 done, 1 error, 2 not applicable (the caller takes the general path)
+static int score_variants_grouped(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_vf, const uint64_t *d_vr, const uint64_t *d_gf, const uint64_t *d_gr,
+	const uint32_t *d_goff, uint32_t n, uint32_t G, float search_threshold, float detect_threshold, int amp_min, int amp_max, int taq)
+{
+	SeqSet &s = ctx->sets[kind];
+	cudaStream_t st = ctx->stream;
+	if (!s.db_valid) return fail(ctx, "pcramp_gpu_score_pairs: no database (call pcramp_gpu_select_words first)");
+	if (!(ctx->use_neigh && ctx->use_entry_score && s.n_cand > 0 && s.n_entries > 0 && s.n && n && (uint64_t)s.n_cand * 2ull * G <= (1ull << 28))) return 2;
+	const uint32_t n_words = (s.n + 31u) / 32u;
+	ctx->res_words = n_words;
+	const size_t bits_bytes = (size_t)n * n_words * 4;
+	CK(ctx->d_cov.ensure((size_t)n * 4));
+	CK(ctx->d_bits.ensure(bits_bytes));
+	CK(ctx->d_bits1.ensure(bits_bytes));
+	CK(ctx->d_oligos.ensure((size_t)n * 2 * sizeof(OligoDev)));
+	CK(ctx->d_oligos_base.ensure((size_t)G * 2 * sizeof(OligoDev)));
+	CK(ctx->d_neigh_off.ensure(((size_t)s.n_cand + 1) * 4));
+	CK(ctx->d_neigh.ensure((size_t)s.n_cand * NEIGH_SLOTS * 4));
+	CK(cudaEventRecord(ctx->ev[5], st));
+	CK(cudaMemsetAsync(ctx->d_bits.p, 0, bits_bytes, st));
+	CK(cudaMemsetAsync(ctx->d_bits1.p, 0, bits_bytes, st));
+	CK(cudaMemsetAsync(ctx->d_neigh_off.p, 0, ((size_t)s.n_cand + 1) * 4, st));
+	ctx->stats.ms_score = 0.0f;
+	ctx->pend_ms_score = false;
+	const float thr2 = search_threshold * search_threshold; // pcr_assay.cpp:31-32 (float product)
+	prep_oligos_kernel<<<grid_for(2ull * n, 256), 256, 0, st>>>(d_vf, d_vr, n, thr2, ctx->d_oligos.as<OligoDev>());
+	prep_oligos_kernel<<<grid_for(2ull * G, 256), 256, 0, st>>>(d_gf, d_gr, G, thr2, ctx->d_oligos_base.as<OligoDev>());
+	neigh_slots_kernel<<<dim3(grid_for(s.n_cand, 256), grid_for(2u * G, 256)), 256, 0, st>>>(s.c_planes.as<uint4>(), s.c_thr.as<uint32_t>(), s.n_cand,
+		ctx->d_oligos_base.as<OligoDev>(), 2u * G, ctx->d_neigh.as<uint32_t>(), ctx->d_neigh_off.as<uint32_t>());
+	score_entries_groups_kernel<<<grid_for(s.n_entries, 128), 128, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+		s.e_seq.as<uint32_t>(), s.e_cand.as<uint32_t>(), s.n_entries, s.seq_ent_off.as<uint32_t>(), s.seq_full_end.as<uint32_t>(),
+		ctx->d_neigh.as<uint32_t>(), ctx->d_neigh_off.as<uint32_t>(), ctx->d_oligos_base.as<OligoDev>(), 2u * G, d_goff, ctx->d_oligos.as<OligoDev>(),
+		detect_threshold, amp_min, amp_max, taq, ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
+	if (s.unit_weights)
+		coverage_count_kernel<<<grid_for(32ull * n, 256), 256, 0, st>>>(ctx->d_bits.as<uint32_t>(), n, n_words, ctx->d_cov.as<float>());
+	else
+		coverage_kernel<<<grid_for(n, 128), 128, 0, st>>>(ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), s.d_weight.as<float>(), n, n_words, s.n,
+			ctx->d_cov.as<float>());
+	CK(cudaGetLastError());
+	ctx->stats.kernel_launches += 5;
+	CK(cudaEventRecord(ctx->ev[6], st));
+	ctx->pend_ms_score = true;
+	return 0;
+}
+
 int pcramp_gpu_score_variants(pcramp_gpu_ctx *ctx, int kind, const uint64_t *base_f, const uint64_t *base_r, const uint64_t *var_f,
 	const uint64_t *var_r, uint32_t n, float search_threshold, float detect_threshold, int amp_min, int amp_max, int taq, float *coverage,
 	uint32_t *bitsets)
@@ -2130,7 +2176,36 @@ int pcramp_gpu_score_variants(pcramp_gpu_ctx *ctx, int kind, const uint64_t *bas
 		CK(cudaMemcpyAsync(p + 6ull * n, var_r, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	ctx->stats.kernel_launches = 0;
-	if (score_launch(ctx, kind, p + 4ull * n, p + 6ull * n, p, p + 2ull * n, n, search_threshold, detect_threshold, amp_min, amp_max, taq)) return 1;
+	// variants that follow each other with the same base assay (the moves of one trial, optimize_abi.cuh) form a group
+	int grouped = 2;
+	if (n && ctx->use_variant_groups) {
+		std::vector<uint64_t> &gw = ctx->h_group_words;
+		std::vector<uint32_t> &go = ctx->h_group_off;
+		gw.clear();
+		go.clear();
+		std::vector<uint64_t> gr;
+		for (uint32_t i = 0; i < n; ++i) {
+			if (i == 0 || base_f[2 * i] != base_f[2 * i - 2] || base_f[2 * i + 1] != base_f[2 * i - 1] || base_r[2 * i] != base_r[2 * i - 2] ||
+			    base_r[2 * i + 1] != base_r[2 * i - 1]) {
+				go.push_back(i);
+				gw.push_back(base_f[2 * i]); gw.push_back(base_f[2 * i + 1]);
+				gr.push_back(base_r[2 * i]); gr.push_back(base_r[2 * i + 1]);
+			}
+		}
+		const uint32_t G = (uint32_t)go.size();
+		go.push_back(n);
+		gw.insert(gw.end(), gr.begin(), gr.end());
+		DevBuf &dg = ctx->d_variant_groups;
+		CK(dg.ensure((size_t)G * 32 + ((size_t)G + 1) * 4));
+		CK(cudaMemcpyAsync(dg.p, gw.data(), (size_t)G * 32, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync((char *)dg.p + (size_t)G * 32, go.data(), ((size_t)G + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+		grouped = score_variants_grouped(ctx, kind, p + 4ull * n, p + 6ull * n, dg.as<uint64_t>(), dg.as<uint64_t>() + 2ull * G,
+			(const uint32_t *)((char *)dg.p + (size_t)G * 32), n, G, search_threshold, detect_threshold, amp_min, amp_max, taq);
+		if (grouped == 1) return 1;
+		if (grouped == 0) CK(cudaStreamSynchronize(ctx->stream)); // the group arrays are host vectors of the context: done with them
+	}
+	if (grouped == 2 &&
+	    score_launch(ctx, kind, p + 4ull * n, p + 6ull * n, p, p + 2ull * n, n, search_threshold, detect_threshold, amp_min, amp_max, taq)) return 1;
 	const uint32_t save = ctx->n_pairs;
 	ctx->n_pairs = n;
 	const int rc = pcramp_gpu_fetch_results(ctx, coverage, bitsets);
@@ -2341,6 +2416,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_tier_table") == 0) { ctx->use_tier_table = value; return 0; }
 	if (strcmp(name, "use_fused_score") == 0) { ctx->use_fused_score = value; return 0; }
 	if (strcmp(name, "use_entry_score") == 0) { ctx->use_entry_score = value; return 0; }
+	if (strcmp(name, "use_variant_groups") == 0) { ctx->use_variant_groups = value; return 0; }
 	if (strcmp(name, "use_segmented_db") == 0) { ctx->use_seg_db = value; return 0; }
 	if (strcmp(name, "use_fast_path") == 0) { ctx->use_fast = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }

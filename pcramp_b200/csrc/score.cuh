@@ -527,6 +527,96 @@ score_entries_kernel(SeqDev sd, const uint4 *__restrict__ e_planes, const int32_
 	for (uint32_t i = 0; i < nk; ++i) try_oligo(__ldg(slots + (size_t)k * NEIGH_SLOTS + i));
 }
 
+// Move scoring by groups (optimize_pcr.cpp: every trial oligo of a move is scored against the candidates of the UNMOVED assay): the
+// variants [goff[g], goff[g + 1]) share base assay g = (member[2g], member[2g + 1]).  Membership (which entries an oligo of the base
+// assay matches), the partner entries and the amplicon geometry belong to the base assay and are found once per (entry, base oligo);
+// only the two identities and the detection test are the variant's.  The neighbour slots are built over the 2G base oligos, so their
+// number does not grow with the variants.
+__global__ void __launch_bounds__(128)
+score_entries_groups_kernel(SeqDev sd, const uint4 *__restrict__ e_planes, const int32_t *__restrict__ e_loc, const uint32_t *__restrict__ e_strand,
+	const uint32_t *__restrict__ e_seq, const uint32_t *__restrict__ e_cand, uint64_t n_ent, const uint32_t *__restrict__ seq_off2,
+	const uint32_t *__restrict__ full_end, const uint32_t *__restrict__ slots, const uint32_t *__restrict__ slot_cnt,
+	const OligoDev *__restrict__ member, uint32_t n_member, const uint32_t *__restrict__ goff, const OligoDev *__restrict__ oligos, float detect,
+	int amp_min, int amp_max, int taq, uint32_t *bits_any, uint32_t *bits_pass1, uint32_t n_words_seq)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_ent) return;
+	if (__ldg(e_strand + e) != STRAND_PLUS) return;
+	const uint32_t seq = __ldg(e_seq + e);
+	if (!sd.active[seq]) return; // optimize.cpp:280-283
+	const uint32_t m0 = __ldg(seq_off2 + 2u * seq + 1u), m1 = __ldg(seq_off2 + 2u * seq + 2u);
+	if (m0 == m1) return;
+	const uint32_t mf = __ldg(full_end + 2u * seq + 1u);
+	const uint4 w = __ldg(e_planes + e);
+	ScoreEntry pe;
+	pe.a = w.x; pe.c = w.y; pe.g = w.z; pe.t = w.w;
+	pe.loc = __ldg(e_loc + e);
+	pe.strand = STRAND_PLUS;
+	const int L = (int)sd.len[seq];
+	const uint32_t bit = 1u << (seq & 31u), word = seq >> 5;
+	auto try_base = [&](uint32_t id) {
+		const OligoDev Pb = member[id];
+		if (oligo_count(Pb, pe) < (int)(Pb.packed & 255u)) return;
+		const uint32_t side = id & 1u, g = id >> 1;
+		const OligoDev Mb = member[id ^ 1u];
+		const uint32_t v0 = __ldg(goff + g), v1 = __ldg(goff + g + 1u);
+		if (v0 == v1) return;
+		const int p_start = (int)((Pb.packed >> 8) & 255u), p_stop = (int)((Pb.packed >> 16) & 255u);
+		const int m_thr = (int)(Mb.packed & 255u), m_start = (int)((Mb.packed >> 8) & 255u), m_stop = (int)((Mb.packed >> 16) & 255u);
+		const int plus_loc3 = pe.loc + p_stop;
+		auto test = [&](uint32_t j) {
+			ScoreEntry m2;
+			const uint4 v = __ldg(e_planes + j);
+			m2.a = v.x; m2.c = v.y; m2.g = v.z; m2.t = v.w;
+			m2.loc = __ldg(e_loc + j);
+			m2.strand = STRAND_MINUS;
+			if (oligo_count(Mb, m2) < m_thr) return;
+			const int minus_loc5 = m2.loc - m_stop;
+			if (!(plus_loc3 < minus_loc5)) return;   // pcr_assay.cpp:368-371
+			int amp_start = pe.loc + p_start;
+			const int amp_stop = min(m2.loc - m_start, L - 1);
+			int amp_len = amp_stop - amp_start + 1;
+			if (amp_len < amp_min || amp_len > amp_max) return; // :383-392
+			if (amp_start < 0) { amp_len += amp_start; amp_start = 0; } // :412-416
+			if (amp_len < 0 || has_split_dev(sd, seq, amp_start, amp_len)) return; // :418
+			for (uint32_t q = v0; q < v1; ++q) { // the variants of this base assay
+				const OligoDev P = oligos[2u * q + side], M = oligos[2u * q + (side ^ 1u)];
+				const float ident_p = oligo_identity(P, oligo_count(P, pe), pe, taq);
+				const float ident_m = oligo_identity(M, oligo_count(M, m2), m2, taq);
+				if (__fsqrt_rn(__fmul_rn(ident_p, ident_m)) >= detect) { // :292-294
+					uint32_t *a = bits_any + (size_t)q * n_words_seq + word;
+					if (!(*a & bit)) atomicOr(a, bit);
+					if (!side) { // {F(+), R(-)}: pass 1 (pcr_assay.cpp:37-47)
+						uint32_t *b = bits_pass1 + (size_t)q * n_words_seq + word;
+						if (!(*b & bit)) atomicOr(b, bit);
+					}
+				}
+			}
+		};
+		{
+			const int lo_loc = plus_loc3 + m_stop, hi_loc = pe.loc + max(amp_max, 0) + 96;
+			uint32_t lo = m0, hi = mf;
+			while (lo < hi) {
+				const uint32_t mid = (lo + hi) >> 1;
+				if (__ldg(e_loc + mid) <= lo_loc) lo = mid + 1; else hi = mid;
+			}
+			for (uint32_t j = lo; j < mf; ++j) {
+				if (__ldg(e_loc + j) > hi_loc) break;
+				test(j);
+			}
+		}
+		for (uint32_t j = mf; j < m1; ++j) test(j); // the partial words of the run
+	};
+	const uint32_t multi = (w.x & w.y) | (w.x & w.z) | (w.x & w.w) | (w.y & w.z) | (w.y & w.w) | (w.z & w.w);
+	const uint32_t k = __ldg(e_cand + e);
+	const uint32_t nk = __ldg(slot_cnt + k);
+	if (multi || nk > NEIGH_SLOTS) {
+		for (uint32_t id = 0; id < n_member; ++id) try_base(id);
+		return;
+	}
+	for (uint32_t i = 0; i < nk; ++i) try_base(__ldg(slots + (size_t)k * NEIGH_SLOTS + i));
+}
+
 struct ScoreItem;
 __global__ void seq_pairs_kernel(SeqDev sd, const uint32_t *__restrict__ seq_off2, const uint32_t *__restrict__ seqbits, uint32_t n_words, uint32_t n_pairs,
 	ScoreItem *items, unsigned int *n_items, uint32_t cap);

@@ -50,8 +50,11 @@ struct ThermoState {
 	DevBuf d_tables, d_dp, d_a, d_b, d_la, d_lb, d_ls, d_out;
 	DevBuf d_text_a, d_text_b, d_note, d_fields; // string batches: the caller's text as it is, {first error, cell count}, one array per result field
 	PinnedBuf h_note;
-	DevBuf d_sort_tmp2;                           // the second stream's sort scratch (pipelined batches)
-	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	// pipelined batches (thermo_batch_pipelined): one stream, one sort scratch and one join event per chunk
+	static constexpr int PIPE = 4;
+	cudaStream_t pipe[PIPE] = {};
+	DevBuf d_pipe_tmp[PIPE];
+	cudaEvent_t ev_fork = nullptr, ev_join[PIPE] = {}, ev_in[PIPE] = {};
 	DevBuf d_key[2], d_ord[2], d_sort_tmp; // size-binned launch order (thermo_order)
 	const uint32_t *order = nullptr;
 	PinnedBuf h_a, h_b, h_la, h_lb, h_ls, h_out;
@@ -68,7 +71,11 @@ void thermo_state_free(ThermoState *t)
 	if (t->ev0) cudaEventDestroy(t->ev0);
 	if (t->ev1) cudaEventDestroy(t->ev1);
 	if (t->ev_fork) cudaEventDestroy(t->ev_fork);
-	if (t->ev_join) cudaEventDestroy(t->ev_join);
+	for (int k = 0; k < ThermoState::PIPE; ++k) {
+		if (t->ev_join[k]) cudaEventDestroy(t->ev_join[k]);
+		if (t->ev_in[k]) cudaEventDestroy(t->ev_in[k]);
+		if (t->pipe[k]) { cudaStreamSynchronize(t->pipe[k]); cudaStreamDestroy(t->pipe[k]); }
+	}
 	delete t;
 }
 
@@ -86,7 +93,6 @@ int thermo_get(pcramp_gpu_ctx *ctx, ThermoState **out)
 		CK(cudaEventCreate(&t->ev0));
 		CK(cudaEventCreate(&t->ev1));
 		CK(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
 	}
 	ThermoState *t = ctx->thermo;
 	if (!t->tables_ready) {
@@ -489,11 +495,13 @@ int thermo_order_range(pcramp_gpu_ctx *ctx, ThermoState *t, cudaStream_t st, Dev
 	return 0;
 }
 
-// One call = one batch, host arrays in and out: the batch is cut into chunks that alternate between the context's two streams, so
-// the copies of one chunk (text in, fields out) run beside the kernel of another.  Each chunk: text -> device, encode, launch order,
-// thermo_kernel, fields, one copy per result array the caller wants.  The host takes the logarithms while the first chunk's text moves.
+// One call = one batch, host arrays in and out: the batch is cut into chunks, each on its own stream, so the copies of one
+// chunk (text in, fields out) run beside the kernels of the others: the copy engine streams the text in back to back and the last
+// kernel ends soon after the last byte arrived.  Each chunk: text -> device, encode, launch order, thermo_kernel, fields, one copy
+// per result array the caller wants.  The host takes the logarithms while the first chunk's text moves.  The chunks shrink
+// towards the end (a chunk's kernel cannot take less than one problem's latency, whatever its size).
 constexpr uint32_t THERMO_PIPELINE_MIN = 65536;
-constexpr int THERMO_PIPELINE_CHUNKS = 4;
+constexpr int THERMO_PIPELINE_CHUNKS = ThermoState::PIPE;
 
 int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
 	const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp)
@@ -503,14 +511,26 @@ int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t
 	const bool two = two_sequences(op);
 	if (two && (!seq_b || !strand_b)) return fail(ctx, "pcramp_gpu_thermo: heterodimer ops need seq_b and strand_b");
 	if (needs_strand(op) && !strand_a) return fail(ctx, "pcramp_gpu_thermo: null strand concentration");
-	cudaStream_t streams[2] = {ctx->stream, ctx->stream2 ? ctx->stream2 : ctx->stream};
+	for (int k = 0; k < THERMO_PIPELINE_CHUNKS; ++k) {
+		if (!t->pipe[k]) CK(cudaStreamCreateWithFlags(&t->pipe[k], cudaStreamNonBlocking));
+		if (!t->ev_join[k]) CK(cudaEventCreateWithFlags(&t->ev_join[k], cudaEventDisableTiming));
+		if (!t->ev_in[k]) CK(cudaEventCreateWithFlags(&t->ev_in[k], cudaEventDisableTiming));
+	}
+	cudaStream_t main_st = ctx->stream;
 	if (thermo_reserve(ctx, t, n)) return 1;
 	CK(t->d_text_a.ensure((size_t)n * stride));
 	if (two) CK(t->d_text_b.ensure((size_t)n * stride));
 	CK(t->d_note.ensure(16));
 	CK(t->h_note.ensure(16));
 	CK(t->d_fields.ensure((size_t)n * 16));
-	const uint32_t chunk = (n + THERMO_PIPELINE_CHUNKS - 1) / THERMO_PIPELINE_CHUNKS;
+	uint32_t bound[THERMO_PIPELINE_CHUNKS + 1];
+	{
+		static const double upto[THERMO_PIPELINE_CHUNKS] = {0.35, 0.65, 0.85, 1.0};
+		bound[0] = 0;
+		for (int c = 0; c < THERMO_PIPELINE_CHUNKS; ++c)
+			bound[c + 1] = c + 1 == THERMO_PIPELINE_CHUNKS ? n : std::min<uint32_t>(n, (uint32_t)((double)n * upto[c]) / THERMO_BLOCK * THERMO_BLOCK);
+	}
+	const uint32_t chunk = bound[1]; // the largest
 	const bool ordered = op != OP_PM_DUPLEX;
 	size_t tmp_bytes = 0;
 	if (ordered) {
@@ -519,17 +539,17 @@ int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t
 			CK(t->d_ord[k].ensure((size_t)n * 4));
 		}
 		CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, t->d_key[0].as<uint16_t>(), t->d_key[1].as<uint16_t>(), t->d_ord[0].as<uint32_t>(),
-			t->d_ord[1].as<uint32_t>(), (int)chunk, 0, 12, streams[0]));
-		CK(t->d_sort_tmp.ensure(tmp_bytes));
-		CK(t->d_sort_tmp2.ensure(tmp_bytes));
+			t->d_ord[1].as<uint32_t>(), (int)chunk, 0, 12, main_st));
+		for (int k = 0; k < THERMO_PIPELINE_CHUNKS; ++k) CK(t->d_pipe_tmp[k].ensure(tmp_bytes));
 	}
-	CK(cudaStreamSynchronize(streams[0])); // the page-locked staging below may still be the source of an earlier batch's copies
+	CK(cudaStreamSynchronize(main_st)); // the page-locked staging below may still be the source of an earlier batch's copies
 	unsigned long long *h_note = t->h_note.as<unsigned long long>();
 	h_note[0] = NOTE_NONE;
 	h_note[1] = 0;
-	CK(cudaMemcpyAsync(t->d_note.p, h_note, 16, cudaMemcpyHostToDevice, streams[0]));
-	CK(cudaEventRecord(t->ev_fork, streams[0]));
-	if (streams[1] != streams[0]) CK(cudaStreamWaitEvent(streams[1], t->ev_fork, 0));
+	CK(cudaMemcpyAsync(t->d_note.p, h_note, 16, cudaMemcpyHostToDevice, main_st));
+	CK(cudaEventRecord(t->ev0, main_st));
+	CK(cudaEventRecord(t->ev_fork, main_st));
+	for (int k = 0; k < THERMO_PIPELINE_CHUNKS; ++k) CK(cudaStreamWaitEvent(t->pipe[k], t->ev_fork, 0));
 	t->op = op;
 	t->n = n;
 	t->order = nullptr;
@@ -541,24 +561,30 @@ int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t
 	if (trace)
 		for (auto &row : tev)
 			for (cudaEvent_t &e : row) cudaEventCreate(&e);
-	CK(cudaEventRecord(t->ev0, streams[0]));
+	int n_chunks = 0;
 	for (int c = 0; c < THERMO_PIPELINE_CHUNKS; ++c) {
-		const uint32_t lo = (uint32_t)c * chunk;
-		if (lo >= n) break;
-		const uint32_t m = std::min(chunk, n - lo);
-		cudaStream_t st = streams[c & 1];
-		if (trace) cudaEventRecord(tev[c][0], st);
-		CK(cudaMemcpyAsync(t->d_text_a.as<char>() + (size_t)lo * stride, seq_a + (size_t)lo * stride, (size_t)m * stride, cudaMemcpyHostToDevice, st));
-		if (two) CK(cudaMemcpyAsync(t->d_text_b.as<char>() + (size_t)lo * stride, seq_b + (size_t)lo * stride, (size_t)m * stride, cudaMemcpyHostToDevice, st));
+		const uint32_t lo = bound[c], m = bound[c + 1] - bound[c];
+		if (!m) continue;
+		++n_chunks;
+		cudaStream_t st = t->pipe[c];
+		// the text moves on the context's stream, chunk after chunk in order (one queue: the first chunk is complete as early as the
+		// link allows); the chunk's own stream takes over from there
+		if (trace) cudaEventRecord(tev[c][0], main_st);
+		CK(cudaMemcpyAsync(t->d_text_a.as<char>() + (size_t)lo * stride, seq_a + (size_t)lo * stride, (size_t)m * stride, cudaMemcpyHostToDevice, main_st));
+		if (two) CK(cudaMemcpyAsync(t->d_text_b.as<char>() + (size_t)lo * stride, seq_b + (size_t)lo * stride, (size_t)m * stride, cudaMemcpyHostToDevice, main_st));
+		if (c == 0) { // the host's half, while the first chunk's text moves
+			host_msg = stage_strands_all(t, op, n, strand_a, strand_b, &host_p);
+			CK(cudaMemcpyAsync(t->d_ls.p, t->h_ls.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, main_st));
+		}
+		CK(cudaEventRecord(t->ev_in[c], main_st));
+		CK(cudaStreamWaitEvent(st, t->ev_in[c], 0));
 		thermo_encode_kernel<<<grid_for(m, 256), 256, 0, st>>>(op, m, lo, t->d_text_a.as<char>() + (size_t)lo * stride, t->d_text_b.as<char>() + (size_t)lo * stride,
 			stride, t->d_a.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_b.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_la.as<uint8_t>() + lo,
 			t->d_lb.as<uint8_t>() + lo, t->d_note.as<unsigned long long>());
 		CK(cudaGetLastError());
-		if (c == 0) host_msg = stage_strands_all(t, op, n, strand_a, strand_b, &host_p); // the host's half, while the first chunk's text moves
-		CK(cudaMemcpyAsync(t->d_ls.as<float>() + lo, t->h_ls.as<float>() + lo, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, st));
 		const uint32_t *order = nullptr;
 		if (ordered) {
-			if (thermo_order_range(ctx, t, st, (c & 1) ? t->d_sort_tmp2 : t->d_sort_tmp, tmp_bytes, lo, m)) return 1;
+			if (thermo_order_range(ctx, t, st, t->d_pipe_tmp[c], tmp_bytes, lo, m)) return 1;
 			order = t->d_ord[1].as<uint32_t>() + lo;
 		}
 		if (trace) cudaEventRecord(tev[c][1], st);
@@ -574,17 +600,17 @@ int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t
 			if (dst[k]) CK(cudaMemcpyAsync(dst[k] + lo, fields + (size_t)k * m, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
 		if (trace) cudaEventRecord(tev[c][3], st);
 	}
-	if (streams[1] != streams[0]) {
-		CK(cudaEventRecord(t->ev_join, streams[1]));
-		CK(cudaStreamWaitEvent(streams[0], t->ev_join, 0));
+	for (int k = 0; k < THERMO_PIPELINE_CHUNKS; ++k) {
+		CK(cudaEventRecord(t->ev_join[k], t->pipe[k]));
+		CK(cudaStreamWaitEvent(main_st, t->ev_join[k], 0));
 	}
-	CK(cudaEventRecord(t->ev1, streams[0]));
-	CK(cudaMemcpyAsync(h_note, t->d_note.p, 16, cudaMemcpyDeviceToHost, streams[0]));
-	CK(cudaStreamSynchronize(streams[0]));
+	CK(cudaEventRecord(t->ev1, main_st));
+	CK(cudaMemcpyAsync(h_note, t->d_note.p, 16, cudaMemcpyDeviceToHost, main_st));
+	CK(cudaStreamSynchronize(main_st));
 	t->cells = h_note[1];
 	t->stats.n_problems = n;
 	t->stats.dp_cells = t->cells;
-	t->stats.kernel_launches = (n + chunk - 1) / chunk;
+	t->stats.kernel_launches = n_chunks;
 	float ms = 0.0f;
 	cudaEventElapsedTime(&ms, t->ev0, t->ev1);
 	t->stats.ms_kernel = ms; // the whole pipeline here (copies included): the kernel's own time is a staged run's
@@ -593,7 +619,7 @@ int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t
 		for (int c = 0; c < THERMO_PIPELINE_CHUNKS; ++c) {
 			float v[4] = {0, 0, 0, 0};
 			for (int k = 0; k < 4; ++k) {
-				if ((uint64_t)c * chunk < n) cudaEventElapsedTime(&v[k], t->ev0, tev[c][k]);
+				if (bound[c + 1] > bound[c]) cudaEventElapsedTime(&v[k], t->ev0, tev[c][k]);
 				cudaEventDestroy(tev[c][k]);
 			}
 			fprintf(stderr, "[pcramp thermo] chunk %d: copy in from %.3f ms, kernel %.3f .. %.3f ms, results out by %.3f ms (of %.3f)\n", c, v[0], v[1], v[2], v[3], ms);
@@ -700,7 +726,14 @@ int thermo_run_codes(pcramp_gpu_ctx *ctx, int op, uint32_t n, const uint8_t *cod
 		memcpy(t->h_la.p, len, n);
 		memset(t->h_lb.p, 0, n);
 		float *ls = t->h_ls.as<float>();
-		for (uint32_t p = 0; p < n; ++p) ls[p] = logf(strand[p]);
+		float last_strand = -1.0f, last_log = 0.0f;
+		for (uint32_t p = 0; p < n; ++p) { // runs of equal concentrations (the expansions of one oligo) share one logf
+			if (strand[p] != last_strand) {
+				last_strand = strand[p];
+				last_log = logf(last_strand);
+			}
+			ls[p] = last_log;
+		}
 	}
 	if (run_and_fetch(ctx, t, op, n)) return 1;
 	const float4 *o = t->h_out.as<float4>();

@@ -159,3 +159,32 @@ def synth_pairs(case, n):
     from pcramp_b200 import synth
     coll = synth.Collection([case.multiplex.codes(i)[case.multiplex.codes(i) != 0] for i in (0, 1, 2, 4)])
     return synth.make_pairs(9, coll, n, primer_range=(18, 25), degenerate_fraction=0.3)
+
+
+def test_grouped_variants_equal_one_by_one(gpu):
+    """score_variants by groups that share their base assay (score_entries_groups_kernel) == variant by variant"""
+    case = oc.cases()[1]
+    prepare(gpu, case)
+    o = case.options
+    rng = np.random.default_rng(8)
+    reps = rng.integers(1, 9, size=len(case.f))
+    base_f, base_r = np.repeat(case.f, reps, axis=0), np.repeat(case.r, reps, axis=0)
+    g = np.load(os.path.join(GOLD, "kat_optimize.npz"))
+    pool_f = np.concatenate([case.f, g["opt_%s_f" % case.name]])
+    pool_r = np.concatenate([case.r, g["opt_%s_r" % case.name]])
+    var_f, var_r = base_f.copy(), base_r.copy()
+    pick = rng.integers(0, len(pool_f), size=len(base_f))
+    side = rng.integers(0, 2, size=len(base_f)).astype(bool)
+    var_f[side] = pool_f[pick[side]]
+    var_r[~side] = pool_r[pick[~side]]
+    out = {}
+    for groups in (1, 0):
+        gpu.set_option("use_variant_groups", groups)
+        for taq in (False, True):
+            out[groups, taq] = gpu.score_variants(TARGET, base_f, base_r, var_f, var_r, case.target_search, float(o.target_threshold),
+                                                  o.target_amplicon_min, o.target_amplicon_max, taq)
+    gpu.set_option("use_variant_groups", 1)
+    for taq in (False, True):
+        assert np.array_equal(out[1, taq][0].view(np.uint32), out[0, taq][0].view(np.uint32))
+        assert np.array_equal(out[1, taq][1], out[0, taq][1])
+    assert out[1, False][0].max() > 0
