@@ -226,6 +226,8 @@ struct pcramp_gpu_ctx {
 	std::vector<uint64_t> h_group_words;
 	std::vector<uint32_t> h_group_off;
 	int use_variant_groups = 1;      // option "use_variant_groups"
+	DevBuf bg_cnt4, bg_off4, bg_entry, bg_res, bg_cnt2, bg_off2; // find_background_match by units (sw_abi.cuh)
+	int use_background_units = 1;    // option "use_background_units"
 	float sw_ms_kernel = 0.0f;
 };
 

@@ -2417,6 +2417,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_fused_score") == 0) { ctx->use_fused_score = value; return 0; }
 	if (strcmp(name, "use_entry_score") == 0) { ctx->use_entry_score = value; return 0; }
 	if (strcmp(name, "use_variant_groups") == 0) { ctx->use_variant_groups = value; return 0; }
+	if (strcmp(name, "use_background_units") == 0) { ctx->use_background_units = value; return 0; }
 	if (strcmp(name, "use_segmented_db") == 0) { ctx->use_seg_db = value; return 0; }
 	if (strcmp(name, "use_fast_path") == 0) { ctx->use_fast = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }

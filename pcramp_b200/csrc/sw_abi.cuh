@@ -378,6 +378,264 @@ __global__ void __launch_bounds__(128) multiplex_sw_kernel(SeqDev sd, const uint
 	if (score >= threshold) atomicOr(bits + (size_t)pair * n_words + (seq >> 5), 1u << (seq & 31u));
 }
 
+
+// ---- find_background_match by units ----------------------------------------------------------------------------------
+// The record list above holds one entry per candidate amplicon and background_sw_kernel aligns four times per record.  At the
+// background thresholds a pair has ~10^5 candidate amplicons on 10^3 sequences, but an amplicon is a (plus entry, minus entry)
+// combination and its four alignments are two per entry: F and rc(F) against the word the forward primer matched, R and rc(R)
+// against the word the reverse primer matched (background_match.cpp:66-118).  So the alignments are done once per
+// (pair, matching entry) and the amplicons are never written down:
+//   unit = (sequence, pair); its four lists = the plus / minus entries its F / R match (PF, PR, MF, MR), by loc
+//   bg_match_kernel<false / true>   sizes of the lists, then the entry ids (CTA per sequence, lane = pair, as amplicon_list_kernel)
+//   bg_sw_kernel                    one thread per list element: the two alignments of its oligo against the entry's word
+//   bg_amp_kernel<false>            valid (plus, minus) combinations per (pair, pass, sequence): find_amplicon_match's geometry
+//   prefix sum per pair             = the index each unit's first amplicon has in the reference's list of the pair
+//                                   (pass {F+,R-} then {R+,F-}, each by (sequence, plus loc, minus loc))
+//   bg_amp_kernel<true>             walks the combinations in that order, applies the odd-index guard of :122 and the score
+struct BgLists {
+	const uint32_t *off4;    // exclusive prefix of the list sizes: list (unit, l) = [off4[4 unit + l], off4[4 unit + l + 1])
+	const uint32_t *entry;   // database entry ids, each list by (loc, id)
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(SCORE_THREADS)
+bg_match_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__restrict__ g_loc, const uint32_t *__restrict__ g_strand,
+	const uint32_t *__restrict__ seq_off2, const OligoDev *__restrict__ oligos, uint32_t n_pairs, uint32_t *cnt4, const uint32_t *__restrict__ off4,
+	uint32_t *m_entry)
+{
+	__shared__ ScoreEntry s_ent[SCORE_SMEM_ENTRIES];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = SCORE_THREADS / 32;
+	const uint32_t n_chunks = (n_pairs + 31u) / 32u;
+	for (uint32_t seq = blockIdx.x; seq < sd.n; seq += gridDim.x) {
+		const uint32_t e0 = seq_off2[2 * seq], Ep = seq_off2[2 * seq + 1] - e0, E = seq_off2[2 * seq + 2] - e0;
+		if (Ep == 0u || Ep == E || !sd.active[seq]) continue;
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < min(E, (uint32_t)SCORE_SMEM_ENTRIES); i += SCORE_THREADS) {
+			ScoreEntry en;
+			const uint4 v = g_pl[e0 + i];
+			en.a = v.x; en.c = v.y; en.g = v.z; en.t = v.w;
+			en.loc = g_loc[e0 + i]; en.strand = g_strand[e0 + i];
+			s_ent[i] = en;
+		}
+		__syncthreads();
+		for (uint32_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+			const uint32_t p = chunk * 32u + lane;
+			if (p >= n_pairs) continue;
+			const OligoDev F = oligos[2 * p], R = oligos[2 * p + 1];
+			const int f_thr = (int)(F.packed & 255u), r_thr = (int)(R.packed & 255u);
+			const size_t u4 = ((size_t)seq * n_pairs + p) * 4u;
+			uint32_t at[4] = {0u, 0u, 0u, 0u}, want[4] = {0u, 0u, 0u, 0u};
+			if (FILL) {
+#pragma unroll
+				for (int l = 0; l < 4; ++l) {
+					at[l] = off4[u4 + l];
+					want[l] = off4[u4 + l + 1] - at[l];
+				}
+				if (!(want[0] | want[1] | want[2] | want[3])) continue;
+			}
+			uint32_t n[4] = {0u, 0u, 0u, 0u};
+			for (uint32_t e = 0; e < E; ++e) {
+				const ScoreEntry en = load_entry(s_ent, g_pl, g_loc, g_strand, e0, e);
+				const int base = e < Ep ? 0 : 2;
+				if (oligo_count(F, en) >= f_thr) {
+					if (FILL && want[base]) m_entry[at[base] + n[base]] = e0 + e;
+					++n[base];
+				}
+				if (oligo_count(R, en) >= r_thr) {
+					if (FILL && want[base + 1]) m_entry[at[base + 1] + n[base + 1]] = e0 + e;
+					++n[base + 1];
+				}
+			}
+			if (!FILL) { // pass {F+, R-} needs PF and MR, pass {R+, F-} needs PR and MF: a list without its partner is dropped
+				const bool p0 = n[0] && n[3], p1 = n[1] && n[2];
+				cnt4[u4 + 0] = p0 ? n[0] : 0u;
+				cnt4[u4 + 3] = p0 ? n[3] : 0u;
+				cnt4[u4 + 1] = p1 ? n[1] : 0u;
+				cnt4[u4 + 2] = p1 ? n[2] : 0u;
+			} else { // by (loc, id): the full-window entries of a run already are, the few partial words at its end are moved into place
+#pragma unroll
+				for (int l = 0; l < 4; ++l) {
+					uint32_t *L = m_entry + at[l];
+					for (uint32_t i = 1; i < want[l]; ++i) {
+						const uint32_t x = L[i];
+						const int xl = g_loc[x];
+						uint32_t j = i;
+						while (j > 0 && g_loc[L[j - 1]] > xl) {
+							L[j] = L[j - 1];
+							--j;
+						}
+						L[j] = x;
+					}
+				}
+			}
+		}
+	}
+}
+
+// one thread per list element: {score(oligo, word), score(rc(oligo), word)} and the two aligned target bases of each (TaqMAMA)
+__global__ void __launch_bounds__(128) bg_sw_kernel(uint32_t n_match, uint32_t n_lists, BgLists B, const uint64_t *__restrict__ e_hi,
+	const uint64_t *__restrict__ e_lo, const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs, uint2 *res)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = i < n_match;
+	W128 ow, tw;
+	ow.hi = ow.lo = tw.hi = tw.lo = 0ull;
+	if (live) {
+		uint32_t lo = 0, hi = n_lists; // the list that holds element i: the last one that starts at or before it
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (__ldg(B.off4 + mid + 1) <= i) lo = mid + 1; else hi = mid;
+		}
+		const uint32_t pair = (lo >> 2) % n_pairs, l = lo & 3u;
+		const uint64_t *src = (l == 0u || l == 2u) ? f : r; // PF, MF: the forward primer's words
+		ow.hi = src[2 * pair]; ow.lo = src[2 * pair + 1];
+		const uint32_t e = B.entry[i];
+		tw.hi = e_hi[e]; tw.lo = e_lo[e];
+	}
+	const sw::WordTarget t(tw);
+	sw::Query q;
+	sw::query_from_word(ow, q);
+	const sw::Result a = sw::align_warp<false>(q, t);
+	sw::query_from_word(w_complement(ow), q);
+	const sw::Result b = sw::align_warp<false>(q, t);
+	if (!live) return;
+	unsigned a0, a1, b0, b1;
+	sw::last_two(a, t, a0, a1);
+	sw::last_two(b, t, b0, b1);
+	res[i] = make_uint2((uint32_t)(uint16_t)(int16_t)a.score | ((uint32_t)(uint16_t)(int16_t)b.score << 16), (a0 << 4) | a1 | (b0 << 12) | (b1 << 8));
+}
+
+template <bool SCORE>
+__global__ void __launch_bounds__(128) bg_amp_kernel(SeqDev sd, BgLists B, const int32_t *__restrict__ g_loc, const OligoDev *__restrict__ oligos,
+	uint32_t n_pairs, int amp_min, int amp_max, unsigned long long *cnt2, const unsigned long long *__restrict__ off2, const uint2 *__restrict__ res,
+	const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, float threshold, int taq, uint32_t *bits, uint32_t n_words)
+{
+	const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= (uint64_t)sd.n * n_pairs) return;
+	const uint32_t seq = (uint32_t)(u / n_pairs), pair = (uint32_t)(u % n_pairs);
+	uint32_t o[5];
+#pragma unroll
+	for (int l = 0; l < 5; ++l) o[l] = B.off4[4 * u + l];
+	if (o[4] == o[0]) return;
+	const int L = (int)sd.len[seq];
+	const OligoDev F = oligos[2 * pair], R = oligos[2 * pair + 1];
+	float f_norm = 0.0f, r_norm = 0.0f;
+	W128 fw, rw, fc, rc;
+	fw.hi = fw.lo = rw.hi = rw.lo = 0ull;
+	fc = fw; rc = fw;
+	if (SCORE) {
+		fw.hi = f[2 * pair]; fw.lo = f[2 * pair + 1];
+		rw.hi = r[2 * pair]; rw.lo = r[2 * pair + 1];
+		fc = w_complement(fw); rc = w_complement(rw);
+		f_norm = __fmul_rn(2.0f, (float)w_size(fw)); r_norm = __fmul_rn(2.0f, (float)w_size(rw));
+		if (f_norm > 0.0f) f_norm = __fdiv_rn(1.0f, f_norm);
+		if (r_norm > 0.0f) r_norm = __fdiv_rn(1.0f, r_norm);
+	}
+	bool found = false;
+	for (uint32_t pass = 0; pass < 2u && !found; ++pass) {
+		// pass 0: F on the plus entry (PF), R on the minus entry (MR); pass 1: R on plus (PR), F on minus (MF) (pcr_assay.cpp:421-435)
+		const uint32_t p0 = pass ? o[1] : o[0], p1 = pass ? o[2] : o[1], m0 = pass ? o[2] : o[3], m1 = pass ? o[3] : o[4];
+		if (p0 == p1 || m0 == m1) continue;
+		const OligoDev &P = pass ? R : F, &M = pass ? F : R;
+		const int p_start = (int)((P.packed >> 8) & 255u), p_stop = (int)((P.packed >> 16) & 255u);
+		const int m_start = (int)((M.packed >> 8) & 255u), m_stop = (int)((M.packed >> 16) & 255u);
+		const size_t slot = ((size_t)pair * 2u + pass) * sd.n + seq;
+		unsigned long long rank = 0;
+		if (SCORE) rank = off2[slot] - off2[(size_t)pair * 2u * sd.n]; // position of this unit's first amplicon in the pair's list
+		unsigned long long count = 0;
+		for (uint32_t a = p0; a < p1 && !found; ++a) {
+			const int ploc = g_loc[B.entry[a]];
+			const int plus_loc3 = ploc + p_stop;
+			for (uint32_t b = m0; b < m1; ++b) {
+				const int mloc = g_loc[B.entry[b]];
+				if (!(plus_loc3 < mloc - m_stop)) continue; // pcr_assay.cpp:368-371
+				int amp_start = ploc + p_start;
+				const int amp_stop = min(mloc - m_start, L - 1);
+				int amp_len = amp_stop - amp_start + 1;
+				if (amp_len < amp_min || amp_len > amp_max) continue; // :383-392
+				if (amp_start < 0) { amp_len += amp_start; amp_start = 0; }
+				if (amp_len < 0 || has_split_dev(sd, seq, amp_start, amp_len)) continue; // :418
+				if (!SCORE) { ++count; continue; }
+				const unsigned long long idx = rank++;
+				if ((idx & 1ull) && idx >= (unsigned long long)sd.n) continue; // background_match.cpp:122, as written
+				const uint2 vf = res[pass ? b : a], vr = res[pass ? a : b]; // the entry the forward / the reverse primer matched
+				const int s0 = (int)(int16_t)(vf.x & 0xffffu), s1 = (int)(int16_t)(vf.x >> 16); // F, rc(F) against the f-key
+				const int s2 = (int)(int16_t)(vr.x & 0xffffu), s3 = (int)(int16_t)(vr.x >> 16); // R, rc(R) against the r-key
+				float FpRm = __fmul_rn(__fmul_rn((float)(s0 * s3), f_norm), r_norm);
+				float RpFm = __fmul_rn(__fmul_rn((float)(s1 * s2), f_norm), r_norm);
+				if (taq) {
+					unsigned q0, q1, u0, u1;
+					word_last_two(fw, q0, q1); // Fp against slot 0's target bases
+					word_last_two(rc, u0, u1); // Rm against slot 3's
+					FpRm = __fmul_rn(FpRm, __fmul_rn(taq_correction(q0, q1, (vf.y >> 4) & 15u, vf.y & 15u), taq_correction(u0, u1, (vr.y >> 12) & 15u, (vr.y >> 8) & 15u)));
+					word_last_two(rw, q0, q1); // Rp against slot 2's
+					word_last_two(fc, u0, u1); // Fm against slot 1's
+					RpFm = __fmul_rn(RpFm, __fmul_rn(taq_correction(q0, q1, (vr.y >> 4) & 15u, vr.y & 15u), taq_correction(u0, u1, (vf.y >> 12) & 15u, (vf.y >> 8) & 15u)));
+				}
+				const float score = (FpRm > RpFm) ? __fsqrt_rn(FpRm) : __fsqrt_rn(RpFm);
+				if (score >= threshold) { found = true; break; }
+			}
+		}
+		if (!SCORE) cnt2[slot] = count;
+	}
+	if (SCORE && found) atomicOr(bits + (size_t)pair * n_words + (seq >> 5), 1u << (seq & 31u));
+}
+
+int background_match_units(pcramp_gpu_ctx *ctx, SeqSet &s, const uint64_t *d_f, const uint64_t *d_r, const OligoDev *d_ol, uint32_t n_pairs,
+	float detect_threshold, int amp_min, int amp_max, int taq, uint32_t *d_bits, uint32_t n_words, uint64_t *n_amplicons)
+{
+	cudaStream_t st = ctx->stream;
+	const uint64_t U = (uint64_t)s.n * n_pairs;
+	if (U * 4 + 1 >= (1ull << 32)) return fail(ctx, "pcramp_gpu_background_match: too many (sequence, pair) units in one batch");
+	const uint32_t n_lists = (uint32_t)(U * 4);
+	DevBuf &d_cnt4 = ctx->bg_cnt4, &d_off4 = ctx->bg_off4, &d_entry = ctx->bg_entry, &d_res = ctx->bg_res, &d_cnt2 = ctx->bg_cnt2, &d_off2 = ctx->bg_off2;
+	CK(d_cnt4.ensure(((size_t)n_lists + 1) * 4));
+	CK(d_off4.ensure(((size_t)n_lists + 1) * 4));
+	CK(cudaMemsetAsync(d_cnt4.p, 0, ((size_t)n_lists + 1) * 4, st));
+	const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
+	bg_match_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+		s.seq_ent_off.as<uint32_t>(), d_ol, n_pairs, d_cnt4.as<uint32_t>(), nullptr, nullptr);
+	CK(cudaGetLastError());
+	size_t tb = 0, tb2 = 0;
+	const size_t n2 = (size_t)n_pairs * 2 * s.n + 1;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt4.as<uint32_t>(), d_off4.as<uint32_t>(), (int)(n_lists + 1), st));
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_cnt2.as<unsigned long long>(), d_off2.as<unsigned long long>(), (int)n2, st));
+	CK(ctx->cub_tmp.ensure(std::max(tb, tb2)));
+	tb = tb2 = ctx->cub_tmp.cap;
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, d_cnt4.as<uint32_t>(), d_off4.as<uint32_t>(), (int)(n_lists + 1), st));
+	uint32_t n_match = 0;
+	CK(cudaMemcpyAsync(&n_match, d_off4.as<uint32_t>() + n_lists, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.kernel_launches += 3;
+	if (n_amplicons) *n_amplicons = 0;
+	if (!n_match) return 0;
+	CK(d_entry.ensure((size_t)n_match * 4));
+	CK(d_res.ensure((size_t)n_match * 8));
+	CK(d_cnt2.ensure(n2 * 8));
+	CK(d_off2.ensure(n2 * 8));
+	BgLists B;
+	B.off4 = d_off4.as<uint32_t>();
+	B.entry = d_entry.as<uint32_t>();
+	bg_match_kernel<true><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+		s.seq_ent_off.as<uint32_t>(), d_ol, n_pairs, nullptr, d_off4.as<uint32_t>(), d_entry.as<uint32_t>());
+	bg_sw_kernel<<<grid_for(n_match, 128), 128, 0, st>>>(n_match, n_lists, B, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), d_f, d_r, n_pairs, d_res.as<uint2>());
+	CK(cudaMemsetAsync(d_cnt2.p, 0, n2 * 8, st));
+	bg_amp_kernel<false><<<grid_for(U, 128), 128, 0, st>>>(s.dev(), B, s.e_loc.as<int32_t>(), d_ol, n_pairs, amp_min, amp_max, d_cnt2.as<unsigned long long>(),
+		nullptr, nullptr, nullptr, nullptr, 0.0f, 0, nullptr, 0u);
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb2, d_cnt2.as<unsigned long long>(), d_off2.as<unsigned long long>(), (int)n2, st));
+	bg_amp_kernel<true><<<grid_for(U, 128), 128, 0, st>>>(s.dev(), B, s.e_loc.as<int32_t>(), d_ol, n_pairs, amp_min, amp_max, nullptr,
+		d_off2.as<unsigned long long>(), d_res.as<uint2>(), d_f, d_r, detect_threshold, taq, d_bits, n_words);
+	CK(cudaGetLastError());
+	ctx->stats.kernel_launches += 6;
+	if (n_amplicons) {
+		unsigned long long total = 0;
+		CK(cudaMemcpyAsync(&total, d_off2.as<unsigned long long>() + (n2 - 1), 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		*n_amplicons = total;
+	}
+	return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -450,6 +708,13 @@ int pcramp_gpu_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f
 	prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(d_f.as<uint64_t>(), d_r.as<uint64_t>(), n_pairs, thr2, d_ol.as<OligoDev>());
 	CK(cudaGetLastError());
 	ctx->stats.kernel_launches++;
+	if (ctx->use_background_units) {
+		if (background_match_units(ctx, s, d_f.as<uint64_t>(), d_r.as<uint64_t>(), d_ol.as<OligoDev>(), n_pairs, detect_threshold, amp_min, amp_max, taq,
+				d_bits.as<uint32_t>(), n_words, n_amplicons)) return 1;
+		CK(cudaMemcpyAsync(bitsets, d_bits.p, (size_t)n_pairs * n_words * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		return 0;
+	}
 	AmpList L;
 	if (build_amplicon_list<false>(ctx, s, d_ol.as<OligoDev>(), n_pairs, amp_min, amp_max, L, "pcramp_gpu_background_match")) return 1;
 	const uint64_t n = L.n;

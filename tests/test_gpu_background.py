@@ -81,3 +81,16 @@ def test_against_live_reference(gpu):
         got, n_amp = run_case(gpu, case)
         defined = ~(want == 255).any(1)
         assert n_amp == int(cnt.sum()) and np.array_equal(got[defined], want[defined]), case.name
+
+
+@pytest.mark.parametrize("case", bc.bg_cases(), ids=lambda c: c.name)
+def test_background_units_equal_amplicon_records(gpu, case):
+    """aligning once per (pair, matching entry) and walking the combinations in the reference's order == one record and four
+    alignments per candidate amplicon"""
+    out = {}
+    for units in (1, 0):
+        gpu.set_option("use_background_units", units)
+        out[units] = run_case(gpu, case)
+    gpu.set_option("use_background_units", 1)
+    assert out[1][1] == out[0][1] and out[1][1] > 0
+    assert np.array_equal(out[1][0], out[0][0])
