@@ -37,6 +37,8 @@ enum { PCRAMP_TARGET = 0, PCRAMP_BACKGROUND = 1, PCRAMP_MULTIPLEX = 2, PCRAMP_NU
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
 int pcramp_gpu_create(pcramp_gpu_ctx **ctx, int device);
+/* A context that still has live workers (below) is NOT destroyed (they read its device buffers in place): the call prints a message,
+ * records it as the context's last error and returns; destroy the workers first. */
 void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx);
 /* A worker: a second context on the parent's device that reads the parent's collections and text index in place (no copy:
  * 300 MB of planes + 9.6 GB of index for 20 000 x 30 kb stay single) and owns its stream, scratch, word database and results.

@@ -10,6 +10,7 @@
 #include <ctime>
 #include <memory>
 #include <string>
+#include <atomic>
 #include <vector>
 
 struct pcramp_gpu_ctx;
@@ -145,7 +146,9 @@ struct pcramp_gpu_ctx {
 	// worker contexts (pcramp_gpu_create_worker): own stream / scratch / database, the parent's sequences and text index by reference.
 	// text_gen counts changes of the parent's collections; a worker refuses to run once it is behind.
 	pcramp_gpu_ctx *parent = nullptr;
-	uint64_t text_gen = 0, seen_gen = 0;
+	std::atomic<uint64_t> text_gen{0};   // read by the workers' host threads
+	uint64_t seen_gen = 0;
+	std::atomic<int> n_workers{0};       // live workers: the parent is not destroyed under them
 	int device = 0;
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;

@@ -17,7 +17,8 @@
 // neighbours, exactly one, so an alignment is found once per qualifying segment and reported through the leftmost
 // qualifying segment only; (iii) alignments that start in a "dirty" 32-base group (text with a degenerate base nearby)
 // are left to scan_groups_kernel, exactly as in scan_seed_kernel; (iv) patterns whose segment prefixes contain a
-// degenerate base or are shorter than 8 stay on scan_seed_kernel / scan_full_kernel.  Hits leave through the same
+// degenerate base with more than 16 letter combinations (or an empty position) or are shorter than 8 stay on scan_seed_kernel /
+// scan_full_kernel; the degenerate positions of a prefix are enumerated letter by letter.  Hits leave through the same
 // emit_family / HitSink as the other scan kernels.
 #pragma once
 #include "scan.cuh"
@@ -58,7 +59,24 @@ __device__ __forceinline__ uint32_t idx_letter(const uint4 &m, uint32_t j)
 	return c | (g << 1) | (t * 3u);
 }
 
-// can this (seedable) pattern go through the index?  every segment prefix >= IDX_KMIN single-letter bases
+// the letters pattern position j admits: bit 0 = A, 1 = C, 2 = G, 3 = T (the letter codes of the index key)
+__device__ __forceinline__ uint32_t idx_set(const uint4 &m, uint32_t j)
+{
+	return ((m.x >> j) & 1u) | (((m.y >> j) & 1u) << 1) | (((m.z >> j) & 1u) << 2) | (((m.w >> j) & 1u) << 3);
+}
+__device__ __forceinline__ uint32_t idx_nth_letter(uint32_t set, uint32_t n)
+{ // the n-th letter (ascending) of a non-empty set
+	for (uint32_t l = 0; l < 4u; ++l)
+		if ((set >> l) & 1u) {
+			if (n == 0u) return l;
+			--n;
+		}
+	return 0u;
+}
+constexpr uint32_t IDX_MAX_COMBOS = 16u; // letter combinations of the degenerate positions of one segment prefix (primers of degeneracy <= 16)
+
+// can this (seedable) pattern go through the index?  every segment prefix >= IDX_KMIN bases, no empty position, and at most
+// IDX_MAX_COMBOS letter combinations over its degenerate positions (each combination is queried on its own, see index_query_kernel)
 __device__ __forceinline__ bool idx_indexable(const uint4 &m, uint32_t meta2)
 {
 	const uint32_t n = (meta2 >> 10) & 63u, e = (meta2 >> 16) & 63u, cls = (meta2 >> 22) & 7u;
@@ -69,8 +87,13 @@ __device__ __forceinline__ bool idx_indexable(const uint4 &m, uint32_t meta2)
 		uint32_t o, k;
 		idx_segment(n, segs, i, o, k);
 		if (k < IDX_KMIN || o > IDX_CTX_BEFORE) return false; // the entry's context reaches 16 bases back
-		for (uint32_t j = 0; j < k; ++j)
-			if (idx_letter(m, o + j) > 3u) return false;
+		uint32_t combos = 1u;
+		for (uint32_t j = 0; j < k; ++j) {
+			const uint32_t c = (uint32_t)__popc(idx_set(m, o + j));
+			if (c == 0u) return false;
+			combos *= c;
+			if (combos > IDX_MAX_COMBOS) return false;
+		}
 	}
 	return true;
 }
@@ -201,7 +224,8 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 	const uint32_t p = t / IDX_SLOTS, slot = t % IDX_SLOTS;
 	bool counts = false;
 	uint32_t n_emit = 0;        // queries this lane writes
-	uint32_t seg_code = 0, k = 0, o = 0, si = 0, wo = 0, x = 0, budget = 0, ext_pat = 0;
+	uint32_t k = 0, o = 0, si = 0, wo = 0, x = 0, budget = 0, ext_pat = 0, n_combo = 1u, sub_letter = 0u, sub_at = 0xFFFFFFFFu;
+	uint4 seg_m = make_uint4(0u, 0u, 0u, 0u);
 	bool ext_left = false, ext = false;
 	if (p < n_pat) {
 		const uint4 m = mask[p];
@@ -222,11 +246,24 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 					ok = sub_pos < k;
 				}
 				if (ok) {
+					// Degenerate prefix positions: the text k-mers within one SET mismatch of the prefix are enumerated without
+					// repeats as (which position misses, with which letter outside its set) x (one letter of its set at every other
+					// position): n_combo codes per neighbour, each queried like the single code of a plain prefix.
+					n_combo = 1u;
 					for (uint32_t q = 0; q < k; ++q) {
-						uint32_t l = idx_letter(m, o + q);
-						if (q == sub_pos) l = (l + 1u + sub_alt) & 3u;
-						seg_code = (seg_code << 2) | l;
+						const uint32_t set = idx_set(m, o + q);
+						if (q == sub_pos) {
+							const uint32_t out = ~set & 15u; // the substituted letter is one the pattern does NOT admit here
+							if (sub_alt >= (uint32_t)__popc(out)) ok = false;
+							else sub_letter = idx_nth_letter(out, sub_alt);
+						} else {
+							n_combo *= (uint32_t)__popc(set);
+						}
 					}
+				}
+				if (ok) {
+					seg_m = m;
+					sub_at = sub_pos;
 					n_emit = 1u;
 					wo = o;
 					x = IDX_K - k;
@@ -263,6 +300,7 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 			}
 		}
 	}
+	n_emit *= n_combo;
 	// reserve: one atomic per warp
 	uint32_t incl = n_emit;
 	#pragma unroll
@@ -284,39 +322,54 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 		IdxQuery qy;
 		qy.pid = p;
 		qy.seg = o | (k << 8) | (si << 16) | (wo << 24);
-		if (!ext) { // the k-prefix as a range of 4^x buckets
-			const uint32_t sh = 2u * x;
-			qy.lo = __ldg(off + (seg_code << sh));
-			qy.hi = __ldg(off + ((seg_code + 1u) << sh));
-			span += qy.hi - qy.lo;
-			if (at < q_cap) queries[at] = qy;
-		} else if (ext_left) {
-			for (uint32_t c = 0; c < (1u << (2u * x)); ++c) {
-				const uint32_t d = c ^ ext_pat, bad = (d | (d >> 1)) & 0x55u;
-				if ((uint32_t)__popc(bad) > budget) continue;
-				const uint32_t code = (c << (2u * k)) | seg_code;
-				qy.lo = __ldg(off + code);
-				qy.hi = __ldg(off + code + 1u);
+		for (uint32_t combo = 0; combo < n_combo; ++combo) {
+			uint32_t seg_code = 0u, rest = combo;
+			for (uint32_t q = 0; q < k; ++q) {
+				uint32_t l;
+				if (q == sub_at) {
+					l = sub_letter;
+				} else {
+					const uint32_t set = idx_set(seg_m, o + q), c = (uint32_t)__popc(set);
+					l = idx_nth_letter(set, rest % c);
+					rest /= c;
+				}
+				seg_code = (seg_code << 2) | l;
+			}
+			if (!ext) { // the k-prefix as a range of 4^x buckets
+				const uint32_t sh = 2u * x;
+				qy.lo = __ldg(off + (seg_code << sh));
+				qy.hi = __ldg(off + ((seg_code + 1u) << sh));
 				span += qy.hi - qy.lo;
 				if (at < q_cap) queries[at] = qy;
 				++at;
-			}
-		} else {
-			const uint32_t n_codes = 1u << (2u * x), code0 = seg_code << (2u * x);
-			uint32_t run_start = 0;
-			bool prev = false;
-			for (uint32_t c = 0; c <= n_codes; ++c) { // one step past the end closes the last run
-				const uint32_t d = c ^ ext_pat;
-				const bool okc = c < n_codes && (uint32_t)__popc((d | (d >> 1)) & 0x55u) <= budget;
-				if (okc && !prev) run_start = c;
-				if (!okc && prev) {
-					qy.lo = __ldg(off + code0 + run_start);
-					qy.hi = __ldg(off + code0 + c);
+			} else if (ext_left) {
+				for (uint32_t c = 0; c < (1u << (2u * x)); ++c) {
+					const uint32_t d = c ^ ext_pat, bad = (d | (d >> 1)) & 0x55u;
+					if ((uint32_t)__popc(bad) > budget) continue;
+					const uint32_t code = (c << (2u * k)) | seg_code;
+					qy.lo = __ldg(off + code);
+					qy.hi = __ldg(off + code + 1u);
 					span += qy.hi - qy.lo;
 					if (at < q_cap) queries[at] = qy;
 					++at;
 				}
-				prev = okc;
+			} else {
+				const uint32_t n_codes = 1u << (2u * x), code0 = seg_code << (2u * x);
+				uint32_t run_start = 0;
+				bool prev = false;
+				for (uint32_t c = 0; c <= n_codes; ++c) { // one step past the end closes the last run
+					const uint32_t d = c ^ ext_pat;
+					const bool okc = c < n_codes && (uint32_t)__popc((d | (d >> 1)) & 0x55u) <= budget;
+					if (okc && !prev) run_start = c;
+					if (!okc && prev) {
+						qy.lo = __ldg(off + code0 + run_start);
+						qy.hi = __ldg(off + code0 + c);
+						span += qy.hi - qy.lo;
+						if (at < q_cap) queries[at] = qy;
+						++at;
+					}
+					prev = okc;
+				}
 			}
 		}
 	}

@@ -514,7 +514,8 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	const int rc = pcramp_gpu_create(&w, parent->device);
 	if (rc) return fail(parent, "pcramp_gpu_create_worker: pcramp_gpu_create failed");
 	w->parent = parent;
-	w->seen_gen = parent->text_gen;
+	w->seen_gen = parent->text_gen.load();
+	parent->n_workers.fetch_add(1);
 	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index; w->idx_part_cap = parent->idx_part_cap;
 	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
 	w->use_entry_score = parent->use_entry_score; w->use_seg_db = parent->use_seg_db; w->use_fast = parent->use_fast;
@@ -547,6 +548,12 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx)
 {
 	if (!ctx) return;
+	if (ctx->n_workers.load() > 0) { // its workers read its sequences and text index in place: freeing them would leave dangling pointers
+		fprintf(stderr, "pcramp_gpu_destroy: %d worker context(s) still alive; destroy the workers first (context kept)\n", ctx->n_workers.load());
+		ctx->err = "pcramp_gpu_destroy: worker contexts still alive";
+		return;
+	}
+	if (ctx->parent) ctx->parent->n_workers.fetch_sub(1);
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	for (auto &e : ctx->ev) cudaEventDestroy(e);
@@ -566,10 +573,11 @@ void pcramp_gpu_destroy(pcramp_gpu_ctx *ctx)
 }
 
 const char *pcramp_gpu_last_error(const pcramp_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "pcramp_gpu: null context"; }
-void *pcramp_gpu_stream(pcramp_gpu_ctx *ctx) { return (void *)ctx->stream; }
+void *pcramp_gpu_stream(pcramp_gpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int pcramp_gpu_synchronize(pcramp_gpu_ctx *ctx)
 {
+	if (!ctx) return 1;
 	CK(cudaStreamSynchronize(ctx->stream));
 	return 0;
 }
@@ -691,6 +699,7 @@ int pcramp_gpu_set_weights(pcramp_gpu_ctx *ctx, int kind, const float *weight)
 int pcramp_gpu_set_active(pcramp_gpu_ctx *ctx, int kind, const uint8_t *active)
 {
 	if (check_kind(ctx, kind) || text_change(ctx, "pcramp_gpu_set_active")) return 1;
+	if (!active && ctx->sets[kind].n) return fail(ctx, "pcramp_gpu_set_active: null argument");
 	SeqSet &s = ctx->sets[kind];
 	for (uint32_t i = 0; i < s.n; ++i) s.active[i] = active[i] ? 1 : 0;
 	if (s.n) CK(cudaMemcpyAsync(s.d_active.p, s.active.data(), s.n, cudaMemcpyHostToDevice, ctx->stream));

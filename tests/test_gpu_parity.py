@@ -503,13 +503,20 @@ def test_segments_longer_than_shared_memory(gpu, oracle):
 def test_fast_form_equals_general_form(oracle):
     """batches of one shape after the first run without the host in the loop (select_words_fast): databases, coverages and bitsets
     equal the oracle's; a batch that breaks an assumption -- more hits than the buffers were sized for (tiny_buffers keeps them
-    tight), a degenerate primer the index cannot take -- is detected from the read-back and re-run in the general form"""
+    tight), a primer too degenerate for the index (more than 16 letter combinations in a segment prefix) -- is detected from the read-back and re-run in the general form"""
     from pcramp_b200 import PcrampGpu
     base = synth.make_targets(131, 60, 7000, n_clades=3, between=0.12, within=0.04)
     loner = synth.make_targets(135, 1, 7000)                       # related to nothing: its primers hit one sequence
     coll = synth.Collection([base.codes(i) for i in range(base.n)] + [loner.codes(0)])
     f, r = synth.make_pairs(132, base, 180)
     fd, rd = synth.make_pairs(133, base, 60, degenerate_fraction=1.0)
+    for w in fd:                                                   # five two-letter positions at the 5' end: 32 letter combinations in
+        nib = [(int(w[i // 16]) >> ((15 - i % 16) * 4)) & 15 for i in range(32)]   # one segment prefix, more than the index enumerates
+        pos = [i for i in range(32) if nib[i]][:5]
+        for i in pos:
+            nib[i] |= int(synth.CODE[(int(np.log2(nib[i] & -nib[i])) + 1) % 4]) if bin(nib[i]).count("1") == 1 else 0
+        w[0] = sum(nib[i] << ((15 - i) * 4) for i in range(16))
+        w[1] = sum(nib[i] << ((31 - i) * 4) for i in range(16, 32))
     oracle.set_sequences(coll)
     g = PcrampGpu(0)
     try:
@@ -547,9 +554,44 @@ def test_fast_form_equals_general_form(oracle):
         if st["n_fast_redo"] == 2:                                 # the re-run is a general-form batch: the next one is fast again
             st = batch(f[60:120], r[60:120], True)
         redo, fast = st["n_fast_redo"], st["n_fast"]
-        st = batch(fd, rd, True)                                   # degenerate primers: the index cannot take them all
+        st = batch(fd, rd, True)                                   # very degenerate primers: the index cannot take them all
         assert st["n_fast"] == fast + 1 and st["n_fast_redo"] == redo + 1
         st = batch(f[120:180], r[120:180], True)                   # and the general form of that batch withdrew the hint
         assert st["n_fast"] == fast + 1
     finally:
         g.close()
+
+
+def test_degenerate_primers_through_the_index(gpu, oracle):
+    """primers as `-d 16` leaves them (up to four two-letter positions): the degenerate positions of a segment prefix are enumerated
+    letter by letter in the index queries -- same database, keys, coverage and bits as the oracle and as the table scan, the same
+    number of hits (no alignment reported twice), and the patterns really take the index"""
+    from bench_legs import widen
+    coll = synth.make_targets(801, 30, 6000, n_clades=3, between=0.10, within=0.04)
+    f, r = synth.make_pairs(802, coll, 300)
+    rng = np.random.default_rng(5)
+    f, r = widen(f, rng), widen(r, rng)
+    thr = float(np.float32(1.0) * np.float32(0.9))
+    g = GpuChecker(gpu)
+    g.set_sequences(coll)
+    oracle.set_sequences(coll)
+    out = []
+    for use in (0, 1):
+        gpu.set_option("use_index", use)
+        try:
+            ne, nk = g.select_words(f, r, thr)
+            out.append((g.db(), g.keys(), gpu.stats(), (ne, nk)))
+        finally:
+            gpu.set_option("use_index", 1)
+    no, nko = oracle.select_words(f, r, thr)
+    assert out[1][3] == (no, nko) == out[0][3] and no > 1000
+    for a, b, c in zip(out[1][0], out[0][0], oracle.db()):
+        assert np.array_equal(a, c) and np.array_equal(b, c)
+    assert np.array_equal(out[1][1], oracle.keys())
+    st = out[1][2]
+    assert st["n_indexed"] > 0.8 * st["n_seeded"] and st["n_hits"] == out[0][2]["n_hits"]
+    for search, detect in ((thr, 1.0), (1.0, 1.0)):
+        cov_o, bits_o = oracle.score_pairs(f, r, search, detect, 80, 200, False)
+        cov_g, bits_g = g.score_pairs(f, r, search, detect, 80, 200, False)
+        assert np.array_equal(bits_g, bits_o) and np.array_equal(cov_g, cov_o)
+    assert int(bits_o.sum()) > 0
