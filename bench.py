@@ -510,12 +510,31 @@ def dp_leg(a, g, torch, ext, rank, world, dist):
     assert st["dp_cells"] == cells and st["n_problems"] == n
     g.thermo_batch(3, sa, sb, 0.05, strand, strand, out=out_np)
     ms_e2e = timed(lambda: g.thermo_batch(3, sa, sb, 0.05, strand, strand, out=out_np), a.steps)
+    # the same batch handed over as words (what the reference's own callers hold): 36 instead of 70 bytes per problem across the host link
+    lut = np.zeros(256, np.uint8)
+    lut[[65, 67, 71, 84]] = [1, 2, 4, 8]
+
+    def to_words(text):
+        nib = lut[text[:, :32]].astype(np.uint64)                        # codes, left-justified (Word::str() reads start()..stop())
+        sh = (np.uint64(60) - np.uint64(4) * np.arange(16, dtype=np.uint64))
+        return np.stack([(nib[:, :16] << sh).sum(axis=1, dtype=np.uint64), (nib[:, 16:] << sh).sum(axis=1, dtype=np.uint64)], 1)
+
+    wpins = [torch.from_numpy(to_words(sa).view(np.int64)).pin_memory(), torch.from_numpy(to_words(sb).view(np.int64)).pin_memory()]
+    wa, wb = wpins[0].numpy().view(np.uint64), wpins[1].numpy().view(np.uint64)
+    ref_out = [o.copy() for o in out_np]
+    g.thermo_words(3, wa, wb, 0.05, strand, strand, out=out_np)
+    words_identical = all(np.array_equal(x.view(np.uint32), y.view(np.uint32)) for x, y in zip(out_np, ref_out))
+    ms_words = timed(lambda: g.thermo_words(3, wa, wb, 0.05, strand, strand, out=out_np), a.steps)
+    g.thermo_stage(3, sa, sb, 0.05, strand, strand)
+    g.thermo_run_staged()
+    g.thermo_fetch()                                              # reads the kernel's own event time of the staged run
     kernel_ms = g.thermo_stats()["ms_kernel"]
     if rank != 0:
         return None
     total_cells = float(cells) * world   # every rank runs its own batch of the same shape (replicas)
     gcups = total_cells * a.steps / (ms_res * 1e-3) / 1e9
     gcups_e2e = total_cells * a.steps / (ms_e2e * 1e-3) / 1e9
+    gcups_words = total_cells * a.steps / (ms_words * 1e-3) / 1e9
     int_peak = g.measure_int32_peak()   # issue-bound INT32 operations/s of the DP instruction mix, measured live on this GPU
     out = {
         "metric": "dp_gcups", "value": gcups, "unit": "GCUPS (1e9 DP cells/s, cells = q x t)", "ms_per_step": ms_res / a.steps,
@@ -525,6 +544,9 @@ def dp_leg(a, g, torch, ext, rank, world, dist):
                 "d2h_bytes_per_step": n * 16,
                 "note": "pcramp_gpu_thermo_batch with page-locked host arrays: sequence text in (encoded on the device while the host takes "
                         "logf of the strand concentrations), size-ordered launch, one copy per result field out"},
+        "e2e_words": {"value": gcups_words, "unit": "GCUPS", "ms_per_step": ms_words / a.steps, "h2d_bytes_per_step": n * (16 + 16 + 4),
+                      "d2h_bytes_per_step": n * 16, "identical_to_text": bool(words_identical),
+                      "note": "pcramp_gpu_thermo_words: the same problems as 16-byte words instead of text"},
         "gpu_launches": a.steps,
         "roofline": {"kernel": "thermo_kernel", "bound": "int32 issue", "achieved": total_cells / world * DP_INT_OPS_PER_CELL / (kernel_ms * 1e-3) / 1e12,
                      "peak": int_peak / 1e12, "unit": "Tops/s (INT32)", "frac": (total_cells / world * DP_INT_OPS_PER_CELL / (kernel_ms * 1e-3)) / int_peak,
@@ -1016,6 +1038,7 @@ def run_b200(a):
             "parity_at_bench": None if parity is None else parity["ok"],
             "cpu_reference_evals_per_s": None if cpu_baseline is None else cpu_baseline["value"],
             "dp_gcups": None if dp is None else dp["value"], "dp_gcups_e2e": None if dp is None else dp["e2e"]["value"],
+            "dp_gcups_e2e_words": None if dp is None else dp["e2e_words"]["value"],
             "sw_gcups": None if legs["sw_gcups"] is None else legs["sw_gcups"]["value"],
             "sw_gcups_e2e": None if legs["sw_gcups"] is None else legs["sw_gcups"]["e2e"]["value"],
             "configs": {k: {"value": v["value"], "unit": v["unit"], "ms": v.get("ms_per_step", v.get("ms_per_iteration")),

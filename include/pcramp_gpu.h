@@ -362,6 +362,11 @@ int pcramp_gpu_multiplex_compatible(pcramp_gpu_ctx *ctx, const uint64_t *f, cons
 	int fast_alignment, uint8_t *ok);
 /* Counters of the last K3 call: problems, DP cells (q*t gapped dimer, (n-4)(n-3)/2 hairpin, min(q,t) diagonal;
  * SURVEY.md section 8d), kernel launches, CUDA-event time of the kernels. */
+/* The same batch with the oligos as WORDS (two uint64 each: what PCR::is_valid / max_dimer_tm hold and Word::str() turns into the text
+ * the calls above take, word.h:649-666): 16 bytes per oligo across the host link instead of its text.  Every base must be a single
+ * letter (a degenerate base or an EOS inside an oligo fails like its text would: "Unknown base" / "Illegal base"). */
+int pcramp_gpu_thermo_words(pcramp_gpu_ctx *ctx, int op, uint32_t n, const uint64_t *words_a, const uint64_t *words_b, float salt,
+	const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp);
 typedef struct pcramp_gpu_thermo_stats {
 	uint64_t n_problems;
 	uint64_t dp_cells;

@@ -241,6 +241,8 @@ SIGNATURES = {
     "pcramp_gpu_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
     "pcramp_gpu_thermo_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32,
                                                ctypes.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]),
+    "pcramp_gpu_thermo_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, _u64p, _u64p, ctypes.c_float, _f32p, _f32p, _f32p, _f32p,
+                                               _f32p, _f32p]),
     "pcramp_gpu_thermo_stage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32,
                                                ctypes.c_float, _f32p, _f32p]),
     "pcramp_gpu_thermo_run_staged": (ctypes.c_int, [ctypes.c_void_p]),
@@ -718,6 +720,19 @@ class PcrampGpu:
         self._ck(self.lib.pcramp_gpu_thermo_batch(self.h, int(op), n, a.ctypes.data_as(ctypes.c_char_p),
                                                   None if b is None else b.ctypes.data_as(ctypes.c_char_p), a.shape[1], float(salt),
                                                   _ptr(sa, _f32p), _ptr(sb, _f32p), *[_ptr(o, _f32p) for o in out]))
+        return tuple(out)
+
+    def thermo_words(self, op, words_a, words_b=None, salt=0.05, strand_a=9e-7, strand_b=None, out=None):
+        """pcramp_gpu_thermo_words: the batch of thermo_batch with the oligos as (n, 2) uint64 words"""
+        a = _words(words_a)
+        n = len(a)
+        b = None if words_b is None else _words(words_b)
+        sa = None if strand_a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(strand_a, dtype=np.float32), (n,)))
+        sb = None if strand_b is None else np.ascontiguousarray(np.broadcast_to(np.asarray(strand_b, dtype=np.float32), (n,)))
+        if out is None:
+            out = [np.zeros(n, np.float32) for _ in range(4)]
+        self._ck(self.lib.pcramp_gpu_thermo_words(self.h, int(op), n, _ptr(a, _u64p), _ptr(b, _u64p), float(salt), _ptr(sa, _f32p), _ptr(sb, _f32p),
+                                                  *[_ptr(o, _f32p) for o in out]))
         return tuple(out)
 
     def thermo_stage(self, op, seq_a, seq_b=None, salt=0.05, strand_a=9e-7, strand_b=None):

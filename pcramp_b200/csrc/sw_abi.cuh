@@ -585,6 +585,7 @@ int background_match_units(pcramp_gpu_ctx *ctx, SeqSet &s, const uint64_t *d_f, 
 	float detect_threshold, int amp_min, int amp_max, int taq, uint32_t *d_bits, uint32_t n_words, uint64_t *n_amplicons)
 {
 	cudaStream_t st = ctx->stream;
+	Trace tr("background_match", st);
 	const uint64_t U = (uint64_t)s.n * n_pairs;
 	if (U * 4 + 1 >= (1ull << 32)) return fail(ctx, "pcramp_gpu_background_match: too many (sequence, pair) units in one batch");
 	const uint32_t n_lists = (uint32_t)(U * 4);
@@ -607,6 +608,7 @@ int background_match_units(pcramp_gpu_ctx *ctx, SeqSet &s, const uint64_t *d_f, 
 	CK(cudaMemcpyAsync(&n_match, d_off4.as<uint32_t>() + n_lists, 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	ctx->stats.kernel_launches += 3;
+	tr.mark("list sizes");
 	if (n_amplicons) *n_amplicons = 0;
 	if (!n_match) return 0;
 	CK(d_entry.ensure((size_t)n_match * 4));
@@ -618,15 +620,20 @@ int background_match_units(pcramp_gpu_ctx *ctx, SeqSet &s, const uint64_t *d_f, 
 	B.entry = d_entry.as<uint32_t>();
 	bg_match_kernel<true><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
 		s.seq_ent_off.as<uint32_t>(), d_ol, n_pairs, nullptr, d_off4.as<uint32_t>(), d_entry.as<uint32_t>());
+	tr.mark("lists");
 	bg_sw_kernel<<<grid_for(n_match, 128), 128, 0, st>>>(n_match, n_lists, B, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), d_f, d_r, n_pairs, d_res.as<uint2>());
+	tr.mark("alignments");
 	CK(cudaMemsetAsync(d_cnt2.p, 0, n2 * 8, st));
 	bg_amp_kernel<false><<<grid_for(U, 128), 128, 0, st>>>(s.dev(), B, s.e_loc.as<int32_t>(), d_ol, n_pairs, amp_min, amp_max, d_cnt2.as<unsigned long long>(),
 		nullptr, nullptr, nullptr, nullptr, 0.0f, 0, nullptr, 0u);
 	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb2, d_cnt2.as<unsigned long long>(), d_off2.as<unsigned long long>(), (int)n2, st));
+	tr.mark("amplicon counts");
 	bg_amp_kernel<true><<<grid_for(U, 128), 128, 0, st>>>(s.dev(), B, s.e_loc.as<int32_t>(), d_ol, n_pairs, amp_min, amp_max, nullptr,
 		d_off2.as<unsigned long long>(), d_res.as<uint2>(), d_f, d_r, detect_threshold, taq, d_bits, n_words);
 	CK(cudaGetLastError());
 	ctx->stats.kernel_launches += 6;
+	tr.mark("amplicon scores");
+	if (tr.on) fprintf(stderr, "[trace] background_match: %u list elements (2 alignments each), %llu units\n", n_match, (unsigned long long)U);
 	if (n_amplicons) {
 		unsigned long long total = 0;
 		CK(cudaMemcpyAsync(&total, d_off2.as<unsigned long long>() + (n2 - 1), 8, cudaMemcpyDeviceToHost, st));

@@ -4,7 +4,8 @@
 //   seq_a / seq_b   n x 32 bytes of base codes (A=0 C=1 G=2 T=3 I=4), 5'->3', zero (= A) padded: the padding is
 //                   what the reference's ring buffer holds past the end of a sequence (see nuccruc.cuh header)
 //   len_a / len_b   n bytes
-//   log_strand      n floats: logf(total strand concentration), taken on the host with the reference's libm
+//   log_strand      n floats: logf(total strand concentration), taken on the host with the reference's libm (NULL: every problem has
+//                   the concentration whose logarithm is log_strand_all)
 //   out             n x float4 {Tm, dH, dS, dG_dp}
 //   order           optional permutation: thread `slot` works on problem order[slot] (problems binned by size, so that the lanes
 //                   of a warp run DP fills of the same shape)
@@ -32,7 +33,7 @@ struct DpShared {
 
 __global__ void __launch_bounds__(THERMO_BLOCK, THERMO_MIN_BLOCKS) thermo_kernel(int op, uint32_t n, const uint32_t *__restrict__ order, const uint8_t *__restrict__ seq_a, const uint8_t *__restrict__ seq_b,
 	const uint8_t *__restrict__ len_a, const uint8_t *__restrict__ len_b, const float *__restrict__ log_strand, const Tables *__restrict__ tables,
-	const DpTable *__restrict__ dp, float4 *__restrict__ out)
+	const DpTable *__restrict__ dp, float4 *__restrict__ out, float log_strand_all = 0.0f)
 {
 	__shared__ DpTable s_dp;
 	{
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(THERMO_BLOCK, THERMO_MIN_BLOCKS) thermo_kernel
 	c.t = two ? t : q;
 	c.qlen = len_a[p];
 	c.tlen = two ? len_b[p] : c.qlen;
-	c.log_strand = log_strand[p];
+	c.log_strand = log_strand ? log_strand[p] : log_strand_all;
 	c.info = info + NC_INFO_PAD;
 	const Result r = run_problem(c, op);
 	out[p] = make_float4(r.tm, r.dH, r.dS, r.dp_dg);

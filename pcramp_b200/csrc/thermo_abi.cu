@@ -350,6 +350,62 @@ __global__ void __launch_bounds__(256) thermo_encode_kernel(int op, uint32_t n, 
 	}
 }
 
+// the same from words (word.h: 4-bit codes, what PCR::is_valid / max_dimer_tm hold): Word::str()'s bases from start() to stop(),
+// every one a single letter (a degenerate base or an EOS inside the oligo is an error, as its text would be)
+__device__ inline unsigned long long encode_word(const uint64_t *__restrict__ w, uint8_t *dst, uint8_t *len_out, unsigned long long p, unsigned stage)
+{
+	uint4 *d = (uint4 *)dst;
+	d[0] = d[1] = make_uint4(0u, 0u, 0u, 0u);
+	W128 x;
+	x.hi = w[0];
+	x.lo = w[1];
+	const int first = w_start(x), last = w_stop(x);
+	uint32_t len = 0;
+	unsigned long long err = NOTE_NONE;
+	for (int i = first; i >= 0 && i <= last; ++i) {
+		const uint32_t nib = w_get(x, i);
+		int c;
+		switch (nib) {
+		case 1u: c = bA; break;
+		case 2u: c = bC; break;
+		case 4u: c = bG; break;
+		case 8u: c = bT; break;
+		default: c = -1;
+		}
+		if (c < 0) { err = (p << 8) | (stage << 4) | 1u; break; }
+		dst[len++] = (uint8_t)c;
+	}
+	*len_out = (uint8_t)len;
+	return err;
+}
+
+__global__ void __launch_bounds__(256) thermo_encode_words_kernel(int op, uint32_t n, uint32_t p0, const uint64_t *__restrict__ words_a,
+	const uint64_t *__restrict__ words_b, uint8_t *seq_a, uint8_t *seq_b, uint8_t *len_a, uint8_t *len_b, unsigned long long *note)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long gp = (unsigned long long)p0 + p;
+	unsigned long long err = NOTE_NONE, cells = 0;
+	if (p < n) {
+		const bool two = (op == OP_HETERODIMER || op == OP_HETERODIMER_DIAG);
+		uint8_t la = 0, lb = 0;
+		err = encode_word(words_a + 2ull * p, seq_a + (size_t)p * THERMO_SEQ_STRIDE, &la, gp, 0u);
+		if (err == NOTE_NONE && op == OP_HAIRPIN && la == 0) err = (gp << 8) | (1u << 4);
+		if (err == NOTE_NONE && two) err = encode_word(words_b + 2ull * p, seq_b + (size_t)p * THERMO_SEQ_STRIDE, &lb, gp, 2u);
+		len_a[p] = la;
+		len_b[p] = lb;
+		cells = (unsigned long long)problem_cells(op, la, two ? lb : la);
+	}
+	for (int d = 16; d; d >>= 1) {
+		cells += __shfl_xor_sync(0xffffffffu, cells, d);
+		const unsigned long long o = __shfl_xor_sync(0xffffffffu, err, d);
+		err = o < err ? o : err;
+	}
+	if ((threadIdx.x & 31u) == 0u) {
+		if (cells) atomicAdd(note + 1, cells);
+		if (err != NOTE_NONE) atomicMin(note, err);
+	}
+}
+
 __global__ void thermo_fields_kernel(uint32_t n, const float4 *__restrict__ out, float *fields)
 { // {Tm, dH, dS, dG_dp} records -> one array per field: each leaves with one copy into the caller's array
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,8 +560,8 @@ constexpr uint32_t THERMO_PIPELINE_MIN = 65536;
 constexpr int THERMO_PIPELINE_CHUNKS = ThermoState::PIPE;
 
 int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n, const char *seq_a, const char *seq_b, uint32_t stride,
-	const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp)
-{
+	const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp, bool words = false)
+{ // words: seq_a / seq_b are arrays of 16-byte words (stride 16) instead of text
 	if (op < 0 || op >= OP_COUNT) return fail(ctx, "pcramp_gpu_thermo: unknown op");
 	if (!seq_a || stride == 0) return fail(ctx, "pcramp_gpu_thermo: null sequences");
 	const bool two = two_sequences(op);
@@ -562,6 +618,8 @@ int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t
 		for (auto &row : tev)
 			for (cudaEvent_t &e : row) cudaEventCreate(&e);
 	int n_chunks = 0;
+	bool ls_uniform = false;
+	float ls_all = 0.0f;
 	for (int c = 0; c < THERMO_PIPELINE_CHUNKS; ++c) {
 		const uint32_t lo = bound[c], m = bound[c + 1] - bound[c];
 		if (!m) continue;
@@ -573,14 +631,26 @@ int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t
 		CK(cudaMemcpyAsync(t->d_text_a.as<char>() + (size_t)lo * stride, seq_a + (size_t)lo * stride, (size_t)m * stride, cudaMemcpyHostToDevice, main_st));
 		if (two) CK(cudaMemcpyAsync(t->d_text_b.as<char>() + (size_t)lo * stride, seq_b + (size_t)lo * stride, (size_t)m * stride, cudaMemcpyHostToDevice, main_st));
 		if (c == 0) { // the host's half, while the first chunk's text moves
-			host_msg = stage_strands_all(t, op, n, strand_a, strand_b, &host_p);
-			CK(cudaMemcpyAsync(t->d_ls.p, t->h_ls.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, main_st));
+			if (strands_uniform(op, n, strand_a, strand_b)) { // one concentration for the whole batch: its logarithm rides in the launch
+				host_msg = stage_strands(t, op, 0, 1, strand_a, strand_b, &host_p);
+				ls_all = t->h_ls.as<float>()[0];
+				ls_uniform = true;
+			} else {
+				host_msg = stage_strands_all(t, op, n, strand_a, strand_b, &host_p);
+				CK(cudaMemcpyAsync(t->d_ls.p, t->h_ls.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, main_st));
+			}
 		}
 		CK(cudaEventRecord(t->ev_in[c], main_st));
 		CK(cudaStreamWaitEvent(st, t->ev_in[c], 0));
-		thermo_encode_kernel<<<grid_for(m, 256), 256, 0, st>>>(op, m, lo, t->d_text_a.as<char>() + (size_t)lo * stride, t->d_text_b.as<char>() + (size_t)lo * stride,
-			stride, t->d_a.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_b.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_la.as<uint8_t>() + lo,
-			t->d_lb.as<uint8_t>() + lo, t->d_note.as<unsigned long long>());
+		if (words)
+			thermo_encode_words_kernel<<<grid_for(m, 256), 256, 0, st>>>(op, m, lo, (const uint64_t *)(t->d_text_a.as<char>() + (size_t)lo * stride),
+				(const uint64_t *)(t->d_text_b.as<char>() + (size_t)lo * stride), t->d_a.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE,
+				t->d_b.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_la.as<uint8_t>() + lo, t->d_lb.as<uint8_t>() + lo,
+				t->d_note.as<unsigned long long>());
+		else
+			thermo_encode_kernel<<<grid_for(m, 256), 256, 0, st>>>(op, m, lo, t->d_text_a.as<char>() + (size_t)lo * stride, t->d_text_b.as<char>() + (size_t)lo * stride,
+				stride, t->d_a.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_b.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_la.as<uint8_t>() + lo,
+				t->d_lb.as<uint8_t>() + lo, t->d_note.as<unsigned long long>());
 		CK(cudaGetLastError());
 		const uint32_t *order = nullptr;
 		if (ordered) {
@@ -589,8 +659,8 @@ int thermo_batch_pipelined(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t
 		}
 		if (trace) cudaEventRecord(tev[c][1], st);
 		thermo_kernel<<<grid_for(m, THERMO_BLOCK), THERMO_BLOCK, 0, st>>>(op, m, order, t->d_a.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE,
-			t->d_b.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_la.as<uint8_t>() + lo, t->d_lb.as<uint8_t>() + lo, t->d_ls.as<float>() + lo,
-			t->d_tables.as<Tables>(), t->d_dp.as<DpTable>(), t->d_out.as<float4>() + lo);
+			t->d_b.as<uint8_t>() + (size_t)lo * THERMO_SEQ_STRIDE, t->d_la.as<uint8_t>() + lo, t->d_lb.as<uint8_t>() + lo,
+			ls_uniform ? nullptr : t->d_ls.as<float>() + lo, t->d_tables.as<Tables>(), t->d_dp.as<DpTable>(), t->d_out.as<float4>() + lo, ls_all);
 		CK(cudaGetLastError());
 		float *fields = t->d_fields.as<float>() + 4 * (size_t)lo;
 		if (trace) cudaEventRecord(tev[c][2], st);
@@ -810,6 +880,38 @@ int pcramp_gpu_thermo_batch(pcramp_gpu_ctx *ctx, int op, uint32_t n, const char 
 	if (pcramp_gpu_thermo_stage(ctx, op, n, seq_a, seq_b, stride, salt, strand_a, strand_b)) return 1;
 	if (pcramp_gpu_thermo_run_staged(ctx)) return 1;
 	return pcramp_gpu_thermo_fetch(ctx, tm, dH, dS, dG_dp);
+}
+
+int pcramp_gpu_thermo_words(pcramp_gpu_ctx *ctx, int op, uint32_t n, const uint64_t *words_a, const uint64_t *words_b, float salt,
+	const float *strand_a, const float *strand_b, float *tm, float *dH, float *dS, float *dG_dp)
+{
+	if (!ctx) return 1;
+	if (n && !words_a) return fail(ctx, "pcramp_gpu_thermo_words: null argument");
+	if (n && two_sequences(op) && !words_b) return fail(ctx, "pcramp_gpu_thermo: heterodimer ops need seq_b and strand_b");
+	if (n >= THERMO_PIPELINE_MIN) {
+		CK(cudaSetDevice(ctx->device));
+		ThermoState *t = nullptr;
+		if (thermo_get(ctx, &t)) return 1;
+		if (thermo_set_salt(ctx, t, salt)) return 1;
+		return thermo_batch_pipelined(ctx, t, op, n, (const char *)words_a, (const char *)words_b, 16u, strand_a, strand_b, tm, dH, dS, dG_dp, true);
+	}
+	// small batches: Word::str() on the host, then the text path
+	static const char letter[16] = {'-', 'A', 'C', 'M', 'G', 'R', 'S', 'V', 'T', 'W', 'Y', 'H', 'K', 'D', 'B', 'N'}; // bits_to_base (base_table.h)
+	const uint32_t stride = 33;
+	std::vector<char> ta((size_t)n * stride, 0), tb(two_sequences(op) ? (size_t)n * stride : 0, 0);
+	auto text = [&](const uint64_t *w, char *dst) {
+		W128 x;
+		x.hi = w[0];
+		x.lo = w[1];
+		const int first = w_start(x), last = w_stop(x);
+		int k = 0;
+		for (int i = first; i >= 0 && i <= last; ++i) dst[k++] = letter[w_get(x, i)];
+	};
+	for (uint32_t p = 0; p < n; ++p) {
+		text(words_a + 2ull * p, ta.data() + (size_t)p * stride);
+		if (!tb.empty()) text(words_b + 2ull * p, tb.data() + (size_t)p * stride);
+	}
+	return pcramp_gpu_thermo_batch(ctx, op, n, ta.data(), tb.empty() ? nullptr : tb.data(), stride, salt, strand_a, strand_b, tm, dH, dS, dG_dp);
 }
 
 int pcramp_gpu_get_thermo_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_thermo_stats *out)

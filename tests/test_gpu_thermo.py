@@ -178,3 +178,30 @@ def test_large_batch_errors_keep_their_order(gpu):
             gpu.thermo_batch(1, a)
         good = gpu.thermo_batch(2, A[:m])    # and the context still works afterwards
         assert np.all(bits(good[0]) == bits(good[0][:1]))
+
+
+@pytest.mark.parametrize("op", (0, 1, 2, 3))
+def test_words_in_equal_text_in(gpu, op):
+    """pcramp_gpu_thermo_words: the oligos as words (what PCR::is_valid / max_dimer_tm hold) == their text through thermo_batch, for a
+    small batch (converted on the host) and a chunked one (encoded on the device); a degenerate base fails like its text"""
+    from pcramp_b200 import synth
+    A, B, sa, sb = tc.problems(77, 3000, op)
+    keep = [i for i in range(len(A)) if "I" not in A[i] and (B is None or "I" not in B[i])]
+    A = [A[i] for i in keep]
+    B = None if B is None else [B[i] for i in keep]
+    sa, sb = sa[keep], sb[keep]
+    two = op in tc.TWO_SEQ
+    for n in (len(A), 70000):
+        idx = np.arange(n) % len(A)
+        a = [A[i] for i in idx]
+        b = [B[i] for i in idx] if two else None
+        wa = np.array([synth.word_from_string(x, bool(i & 1)) for i, x in enumerate(a)], dtype=np.uint64)
+        wb = np.array([synth.word_from_string(x) for x in b], dtype=np.uint64) if two else None
+        want = gpu.thermo_batch(op, a, b, 0.05, sa[idx], sb[idx] if two else None)
+        got = gpu.thermo_words(op, wa, wb, 0.05, sa[idx], sb[idx] if two else None)
+        for x, y in zip(got, want):
+            assert np.array_equal(bits(x), bits(y))
+        bad = wa.copy()
+        bad[n - 3] = synth.word_from_string("ACGTRACGTACGTACGT")
+        with pytest.raises(api.GpuError, match="Unknown base" if op == 0 else "Illegal base"):
+            gpu.thermo_words(op, bad, wb, 0.05, sa[idx], sb[idx] if two else None)
