@@ -310,6 +310,17 @@ def parse_fasta_args():
     return [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p]
 
 
+def _ncu_traffic(kernel, **match):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/r02_traffic.json) when it was taken on this workload"""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(kernel)
+        if tr and all(tr.get(k) == v for k, v in match.items()):
+            return tr["dram_bytes_per_launch"]
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def sw_leg(a, g, ext, torch):
     """the Smith-Waterman half of the DP metric (SURVEY.md 8d: cells = q x t per slot): SO::SeqOverlap alignments of primer-like queries
     (18-25 nt) against 32-base database words, what find_background_match runs four times per candidate amplicon.  Timed through
@@ -347,7 +358,7 @@ def sw_leg(a, g, ext, torch):
            "e2e": {"value": cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms": ms, "h2d_bytes": 32 * n, "d2h_bytes": 22 * n,
                    "note": "wall clock of pcramp_gpu_sw_batch with page-locked host arrays: two copies in, kernel, six copies out (one per field)"},
            "roofline": {"kernel": "sw_words_kernel", "bound": "int32 issue", "achieved": achieved / 1e12, "peak": int32_peak / 1e12, "unit": "Tops/s",
-                        "frac": achieved / int32_peak, "traffic": None,
+                        "frac": achieved / int32_peak, "traffic": _ncu_traffic("sw_words_kernel", problems=n),
                         "peak_source": "measured live (pcramp_gpu_measure_int32_peak: VIMNMX3 / VIADDMNMX / LOP3 / IADD chains)",
                         "note": "algorithmic cost 12 INT32 operations per cell (SURVEY.md 8d) x cells / kernel time; the kernel spends ~19 "
                                 "instructions per cell of the rows it computes (packed score + start words) and computes 20 / 24 / 28 / 32 rows "
@@ -551,7 +562,8 @@ def dp_leg(a, g, torch, ext, rank, world, dist):
         "roofline": {"kernel": "thermo_kernel", "bound": "int32 issue", "achieved": total_cells / world * DP_INT_OPS_PER_CELL / (kernel_ms * 1e-3) / 1e12,
                      "peak": int_peak / 1e12, "unit": "Tops/s (INT32)", "frac": (total_cells / world * DP_INT_OPS_PER_CELL / (kernel_ms * 1e-3)) / int_peak,
                      "avg_launch_ms": kernel_ms,
-                     "peak_source": "measured live (pcramp_gpu_measure_int32_peak: VIMNMX3 / VIADDMNMX / LOP3 / IADD chains)", "traffic": None,
+                     "peak_source": "measured live (pcramp_gpu_measure_int32_peak: VIMNMX3 / VIADDMNMX / LOP3 / IADD chains)",
+                     "traffic": _ncu_traffic("thermo_kernel", problems=n),
                      "note": "algorithmic cost 45 INT32 ops per gapped cell (SURVEY.md 8d) against the measured issue peak of the DP instruction "
                              "mix; the kernel also runs the traceback / enumeration / float evaluation epilogue, which this model does not credit"},
     }
@@ -955,7 +967,7 @@ def run_b200(a):
         stream_bytes = 16.0 * stats_acc["n_index_entries"] / n_scan   # 16-byte index entries in the queried ranges
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kernel)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(kernel)
             if tr and tr.get("targets") == a.targets and tr.get("target_len") == a.length and tr.get("pairs_per_step") == a.pairs and world == 1:
                 traffic = tr["dram_bytes_per_launch"]
         except (OSError, ValueError):

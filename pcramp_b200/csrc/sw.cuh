@@ -248,6 +248,55 @@ __device__ __forceinline__ Result align_warp(const Query &q, const Target &t)
 }
 #endif
 
+#ifdef __CUDACC__
+// Two score-only alignments against the SAME target in one pass: the two problems ride in the 16-bit halves of one word
+// (a primer and its reverse complement against a database word -- find_background_match's slot pairs, background_match.cpp:66-118).
+// The recurrences are align_score's, every operation the two-lane form of the same instruction (VIMNMX3.S16X2.RELU, VIADDMNMX.S16X2;
+// an add is "add-maximum against -32768"): 11 instructions per PAIR of cells.  Scores only: no coordinates, so no TaqMAMA bases.
+template <int ROWS, class Target>
+__device__ __forceinline__ void align_score_pair_rows(const Query &qa, const Query &qb, const Target &t, int &score_a, int &score_b)
+{
+	constexpr unsigned GO2 = 0xFFFBFFFBu, GE2 = 0xFFFEFFFEu, LOW2 = 0x80008000u; // (-5, -5), (-2, -2), (-32768, -32768)
+	const int tlen = t.length();
+	unsigned M[ROWS], Iq[ROWS], It[ROWS];
+#pragma unroll
+	for (int i = 0; i < ROWS; ++i) {
+		M[i] = 0u;
+		Iq[i] = It[i] = GO2;
+	}
+	unsigned best = 0u;
+	for (int j = 0; j < tlen; ++j) {
+		const unsigned tb = t.at(j);
+		const uint32_t ma = match_mask(qa, tb), mb = match_mask(qb, tb);
+		unsigned aM = 0u, aIq = GO2, aIt = GO2, bM = 0u, bIt = GO2;
+#pragma unroll
+		for (int i = 0; i < ROWS; ++i) {
+			const unsigned cM = M[i], cIq = Iq[i], cIt = It[i];
+			const unsigned s2 = (((ma >> i) & 1u) ? 0x00000002u : 0x0000FFFDu) | (((mb >> i) & 1u) ? 0x00020000u : 0xFFFD0000u);
+			const unsigned xM = __viaddmax_s16x2(__vimax3_s16x2_relu(aM, aIq, aIt), s2, LOW2);
+			const unsigned xIq = __viaddmax_s16x2(cM, GO2, __viaddmax_s16x2(cIq, GE2, GE2));
+			const unsigned xIt = __viaddmax_s16x2(bM, GO2, __viaddmax_s16x2(bIt, GE2, GE2));
+			best = __vimax_s16x2_relu(best, xM);
+			aM = cM; aIq = cIq; aIt = cIt;
+			bM = xM; bIt = xIt;
+			M[i] = xM; Iq[i] = xIq; It[i] = xIt;
+		}
+	}
+	score_a = (int)(short)(best & 0xFFFFu);
+	score_b = (int)(short)(best >> 16);
+}
+
+template <class Target>
+__device__ __forceinline__ void align_score_pair_warp(const Query &qa, const Query &qb, const Target &t, int &score_a, int &score_b)
+{
+	const int rows = __reduce_max_sync(__activemask(), max(qa.len, qb.len));
+	if (rows <= 20) align_score_pair_rows<20>(qa, qb, t, score_a, score_b);
+	else if (rows <= 24) align_score_pair_rows<24>(qa, qb, t, score_a, score_b);
+	else if (rows <= 28) align_score_pair_rows<28>(qa, qb, t, score_a, score_b);
+	else align_score_pair_rows<32>(qa, qb, t, score_a, score_b);
+}
+#endif
+
 // target_last_two_aligned (seq_overlap.h:1265-1283): {N, N} unless 1 <= stop_j < target length
 template <class Target>
 PCR_HD void last_two(const Result &r, const Target &t, unsigned &first, unsigned &second)

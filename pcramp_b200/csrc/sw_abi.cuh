@@ -472,7 +472,9 @@ bg_match_kernel(SeqDev sd, const uint4 *__restrict__ g_pl, const int32_t *__rest
 	}
 }
 
-// one thread per list element: {score(oligo, word), score(rc(oligo), word)} and the two aligned target bases of each (TaqMAMA)
+// one thread per list element: {score(oligo, word), score(rc(oligo), word)} and, for TaqMAMA, the two aligned target bases of each.
+// Without TaqMAMA only the scores are needed: the two alignments run as the 16-bit halves of one pass (sw.cuh).
+template <bool TAQ>
 __global__ void __launch_bounds__(128) bg_sw_kernel(uint32_t n_match, uint32_t n_lists, BgLists B, const uint64_t *__restrict__ e_hi,
 	const uint64_t *__restrict__ e_lo, const uint64_t *__restrict__ f, const uint64_t *__restrict__ r, uint32_t n_pairs, uint2 *res)
 {
@@ -493,11 +495,17 @@ __global__ void __launch_bounds__(128) bg_sw_kernel(uint32_t n_match, uint32_t n
 		tw.hi = e_hi[e]; tw.lo = e_lo[e];
 	}
 	const sw::WordTarget t(tw);
-	sw::Query q;
+	sw::Query q, qc;
 	sw::query_from_word(ow, q);
+	sw::query_from_word(w_complement(ow), qc);
+	if (!TAQ) {
+		int sa, sb;
+		sw::align_score_pair_warp(q, qc, t, sa, sb);
+		if (live) res[i] = make_uint2((uint32_t)(uint16_t)(int16_t)sa | ((uint32_t)(uint16_t)(int16_t)sb << 16), 0u);
+		return;
+	}
 	const sw::Result a = sw::align_warp<false>(q, t);
-	sw::query_from_word(w_complement(ow), q);
-	const sw::Result b = sw::align_warp<false>(q, t);
+	const sw::Result b = sw::align_warp<false>(qc, t);
 	if (!live) return;
 	unsigned a0, a1, b0, b1;
 	sw::last_two(a, t, a0, a1);
@@ -581,6 +589,15 @@ __global__ void __launch_bounds__(128) bg_amp_kernel(SeqDev sd, BgLists B, const
 	if (SCORE && found) atomicOr(bits + (size_t)pair * n_words + (seq >> 5), 1u << (seq & 31u));
 }
 
+// 64-bit total of the list sizes: the prefix sum runs in 32 bits and must not wrap unnoticed
+__global__ void bg_total_kernel(const uint32_t *__restrict__ cnt, uint32_t n, unsigned long long *total)
+{
+	unsigned long long v = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v += cnt[i];
+	for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+	if ((threadIdx.x & 31u) == 0u && v) atomicAdd(total, v);
+}
+
 int background_match_units(pcramp_gpu_ctx *ctx, SeqSet &s, const uint64_t *d_f, const uint64_t *d_r, const OligoDev *d_ol, uint32_t n_pairs,
 	float detect_threshold, int amp_min, int amp_max, int taq, uint32_t *d_bits, uint32_t n_words, uint64_t *n_amplicons)
 {
@@ -604,10 +621,16 @@ int background_match_units(pcramp_gpu_ctx *ctx, SeqSet &s, const uint64_t *d_f, 
 	CK(ctx->cub_tmp.ensure(std::max(tb, tb2)));
 	tb = tb2 = ctx->cub_tmp.cap;
 	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, d_cnt4.as<uint32_t>(), d_off4.as<uint32_t>(), (int)(n_lists + 1), st));
+	CK(ctx->d_item_count.ensure(16));
+	CK(cudaMemsetAsync(ctx->d_item_count.p, 0, 8, st));
+	bg_total_kernel<<<(unsigned)ctx->sm_count * 4u, 256, 0, st>>>(d_cnt4.as<uint32_t>(), n_lists, ctx->d_item_count.as<unsigned long long>());
 	uint32_t n_match = 0;
+	unsigned long long n_match64 = 0;
 	CK(cudaMemcpyAsync(&n_match, d_off4.as<uint32_t>() + n_lists, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&n_match64, ctx->d_item_count.p, 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
-	ctx->stats.kernel_launches += 3;
+	ctx->stats.kernel_launches += 4;
+	if (n_match64 >= (1ull << 32)) return fail(ctx, "pcramp_gpu_background_match: more than 2^32 (pair, matching entry) combinations in one batch (use fewer pairs per call)");
 	tr.mark("list sizes");
 	if (n_amplicons) *n_amplicons = 0;
 	if (!n_match) return 0;
@@ -621,7 +644,10 @@ int background_match_units(pcramp_gpu_ctx *ctx, SeqSet &s, const uint64_t *d_f, 
 	bg_match_kernel<true><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
 		s.seq_ent_off.as<uint32_t>(), d_ol, n_pairs, nullptr, d_off4.as<uint32_t>(), d_entry.as<uint32_t>());
 	tr.mark("lists");
-	bg_sw_kernel<<<grid_for(n_match, 128), 128, 0, st>>>(n_match, n_lists, B, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), d_f, d_r, n_pairs, d_res.as<uint2>());
+	if (taq)
+		bg_sw_kernel<true><<<grid_for(n_match, 128), 128, 0, st>>>(n_match, n_lists, B, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), d_f, d_r, n_pairs, d_res.as<uint2>());
+	else
+		bg_sw_kernel<false><<<grid_for(n_match, 128), 128, 0, st>>>(n_match, n_lists, B, s.e_hi.as<uint64_t>(), s.e_lo.as<uint64_t>(), d_f, d_r, n_pairs, d_res.as<uint2>());
 	tr.mark("alignments");
 	CK(cudaMemsetAsync(d_cnt2.p, 0, n2 * 8, st));
 	bg_amp_kernel<false><<<grid_for(U, 128), 128, 0, st>>>(s.dev(), B, s.e_loc.as<int32_t>(), d_ol, n_pairs, amp_min, amp_max, d_cnt2.as<unsigned long long>(),
