@@ -290,7 +290,7 @@ def design_leg(a, device):
     tg = _c1_targets()
     streams = max(1, min(64, os.cpu_count() or 1))
     runs = {}
-    for label, n_streams in (("thread_1", 1), ("threads_%d" % streams, streams)):
+    for label, n_streams in (("thread_1", 1), ("threads_%d" % streams, streams), ("threads_1000", 1000)):
         g = PcrampGpu(device)
         try:
             _empty_other_collections(g)
@@ -315,14 +315,16 @@ def design_leg(a, device):
                            "index_builds": int(st.get("n_index_builds", 0)), "ms_index_build": float(st.get("ms_index_build", 0.0))}
         finally:
             g.close()
-    key = "threads_%d" % streams
+    key = "threads_1000"
     out = {
         "config": "C1 design run: 100 x 10 kb targets at 3 %, --seed 42 --count 3 --trial 1000; step = one pcramp_gpu_design_iteration "
                   "(candidates, word database incl. index maintenance after the previous assay's splits, optimize, screens, accept + splits)",
         "metric": "design_iterations_per_s", "value": 1e3 / runs[key]["ms_per_iteration"], "unit": "iterations/s",
         "ms_per_iteration": runs[key]["ms_per_iteration"], "runs": runs,
-        "note": "thread_1 = the stock program at --thread 1 (one seed stream draws all trials: its reports are what tests/test_gpu_design_loop.py "
-                "compares line by line); %s = the static schedule of --thread %d (one GPU thread per seed stream)" % (key, streams),
+        "note": "value: one seed stream per trial (the static schedule of --thread 1000: candidate generation is a serial rand_r chain per seed "
+                "stream, so the device wants as many streams as trials); thread_1 = the stock program at --thread 1 (one stream draws all trials: "
+                "its reports are what tests/test_gpu_design_loop.py compares line by line); threads_%d = the schedule of the stock program's best "
+                "run on this host (cpu_baseline)" % streams,
         "roofline": {"kernel": "random_assay_kernel (candidates) + the headline's kernels", "bound": "latency", "achieved": None, "peak": None, "unit": None,
                      "frac": None, "traffic": None, "note": "C1 is 10^6 bases: every stage is launch- / latency-bound at this size"},
         "cpu_baseline": None}
