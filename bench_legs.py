@@ -6,8 +6,8 @@ sample with a bit-for-bit comparison of that sample:
 
   background_scan      C2: the background screen -- select_words at the background thresholds (0.8 x 0.9: cannot be seeded, the
                        brute-force scan) + find_background_match (Smith-Waterman on every candidate amplicon)
-  degenerate_primers   C3: the sweep's own collection scored with primers as `-d 16` leaves them (degenerate segment prefixes go to
-                       the table-based seed scan)
+  degenerate_primers   C3: the sweep's own collection scored with primers as `-d 16` leaves them (the degenerate positions of a segment
+                       prefix are enumerated letter by letter in the index queries)
   optimize_moves       C1: optimize() with all six moves on the trials of one design iteration
   design_iteration     C1: whole iterations of pcramp's main loop (candidates, index maintenance, optimize, screens, accept,
                        splits) through pcramp_gpu_design_iteration, next to the stock program
@@ -188,12 +188,12 @@ def degenerate_leg(a, g, factory, coll, device, parity_at_bench):
         "ms_per_step_best": best_s * 1e3, "gpu_launches": acc["launches"],
         "patterns_indexed": int(last.get("n_indexed", 0)), "patterns_seeded": int(last.get("n_seeded", 0)), "patterns": int(last["n_patterns"]),
         "breakdown_ms": {k: acc[k] / n for k in ("ms_seed", "ms_scan", "ms_edge", "ms_db", "ms_score")},
-        "roofline": {"kernel": "scan_index_kernel + scan_seed_kernel (seeded scan stage)", "bound": "integer issue",
+        "roofline": {"kernel": "index_query_kernel + scan_index_kernel + index_hits_kernel (+ scan_seed_kernel for patterns the index cannot take)", "bound": "integer issue",
                      "achieved": alignments / (scan_ms * 1e-3) if scan_ms > 0 else None, "peak": int_peak, "unit": "alignments/s (brute-force equivalent)",
                      "frac": (alignments / (scan_ms * 1e-3) / int_peak) if scan_ms > 0 and int_peak else None, "traffic": None, "avg_stage_ms": scan_ms,
                      "peak_source": "measured live (pcramp_gpu_measure_int_peak)",
-                     "note": "patterns whose segment prefixes hold a degenerate base leave the text index for the table-based seed filter, "
-                             "which verifies ~5 candidates per text position; above 1.0 = alignments the exact filters skip"},
+                     "note": "a degenerate base inside a segment prefix multiplies the index queries (one per letter combination, at most 16); "
+                             "patterns beyond that take the table-based seed filter.  Above 1.0 = alignments the exact filters skip"},
         "cpu_baseline": None, "parity": None}
     if not a.no_cpu_baseline:
         cpu, parity = parity_at_bench(a, g, factory, coll, f[:P], r[:P], thr, device)
