@@ -125,6 +125,8 @@ inline bool needs_strand(int op) { return op != OP_HAIRPIN; }
 // reserve pinned staging for n problems
 int thermo_reserve(pcramp_gpu_ctx *ctx, ThermoState *t, uint32_t n)
 {
+	// single staging buffers: a batch staged earlier may still be copying out of them (stage -> stage without a fetch in between)
+	CK(cudaStreamSynchronize(ctx->stream));
 	const size_t m = n ? n : 1;
 	CK(t->h_a.ensure(m * THERMO_SEQ_STRIDE));
 	CK(t->h_b.ensure(m * THERMO_SEQ_STRIDE));
@@ -707,6 +709,7 @@ int thermo_stage_strings(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n
 	if (n && needs_strand(op) && !strand_a) return fail(ctx, "pcramp_gpu_thermo: null strand concentration");
 	if (n >= THERMO_DEVICE_ENCODE_MIN) return thermo_stage_strings_device(ctx, t, op, n, seq_a, seq_b, stride, strand_a, strand_b);
 	if (thermo_reserve(ctx, t, n)) return 1;
+
 	// host staging is a plain byte loop: split it over a few threads for large batches
 	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
 	const uint32_t n_thr = n < 65536u ? 1u : std::min<uint32_t>(8u, hw);
