@@ -408,6 +408,7 @@ int pcramp_gpu_accept_assay(pcramp_gpu_ctx *ctx, uint32_t pair, uint32_t pack_ma
 		CK(cudaMemcpyAsync(b.data(), ctx->amp_bounds.p, ctx->amp_n_rec * 12, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 	}
+	Trace tr("accept_assay", st);
 	std::vector<uint32_t> sp_seq, sp_pos;
 	for (uint64_t i = 0; i < ctx->amp_n_rec; ++i) {
 		if (b_pair[i] != pair) continue;
@@ -471,8 +472,10 @@ int pcramp_gpu_accept_assay(pcramp_gpu_ctx *ctx, uint32_t pair, uint32_t pack_ma
 		ctx->stats.kernel_launches += 2;
 	}
 	if (n_added) *n_added = n_new;
+	tr.mark("append amplicons");
 	// ---- keys() of the multiplex background database (main.cpp:1002) ---------------------------------------------------
 	if (pcramp_gpu_multiplex_keys(ctx, pack_max_degen, min_oligo_length, n_multiplex_keys)) return 1;
+	tr.mark("multiplex keys");
 	// ---- the assay joins the pool (main.cpp:1123) -----------------------------------------------------------------------
 	for (int k = 0; k < 4; ++k) ctx->pool_words.push_back(ctx->amp_words[4ull * pair + k]);
 	CK(ctx->mpx_pool.ensure(ctx->pool_words.size() * 8));
@@ -483,6 +486,7 @@ int pcramp_gpu_accept_assay(pcramp_gpu_ctx *ctx, uint32_t pair, uint32_t pack_ma
 	ctx->amp_kind = -1; // the records point into text that is about to change
 	ctx->amp_bounds_ok = false;
 	if (!sp_seq.empty() && pcramp_gpu_split_sequences(ctx, kind, (uint32_t)sp_seq.size(), sp_seq.data(), sp_pos.data())) return 1;
+	tr.mark("splits");
 	(void)src;
 	return 0;
 }

@@ -266,6 +266,7 @@ int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *
 	std::vector<uint8_t> compat(nc, 1);
 	std::vector<float> mbg_cov(nc, 0.0f), pool_amp_cov(nc, 0.0f), bg_cov(nc, 0.0f);
 	std::vector<uint32_t> bg_bits;
+	pcr::Trace trs("design screen", ctx->stream);
 	if (nc && o.use_multiplex) {
 		if (n_pool) { // :746-752
 			std::vector<uint64_t> pf(2ull * n_pool), pr(2ull * n_pool);
@@ -275,6 +276,7 @@ int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *
 			}
 			DCALL(pcramp_gpu_multiplex_compatible(ctx, cf.data(), cr.data(), nc, pf.data(), pr.data(), n_pool, o.salt, o.primer_strand, o.max_dimer,
 				0, compat.data()));
+			trs.mark("multiplex_compatible");
 		}
 		if (M.n) { // :760-771: weighted_coverage over the multiplex background (weights 1: a count)
 			const uint32_t mw = (M.n + 31u) / 32u;
@@ -287,10 +289,13 @@ int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *
 					if ((mb[(size_t)k * mw + (i >> 5)] >> (i & 31u)) & 1u) sum += M.weight[i];
 				mbg_cov[k] = (float)sum;
 			}
+			trs.mark("multiplex background");
 		}
-		if (n_pool) // :783-803
+		if (n_pool) { // :783-803
 			DCALL(pcramp_gpu_pool_amplicon_coverage(ctx, PCRAMP_TARGET, cf.data(), cr.data(), nc, o.target_threshold, o.target_amplicon_min,
 				o.target_amplicon_max, o.background_threshold, o.use_taq_mama, pool_amp_cov.data()));
+			trs.mark("pool x amplicons");
+		}
 	}
 	if (nc && num_active_background > 0) { // :814-834
 		bg_bits.assign((size_t)nc * b_words, 0);
@@ -302,6 +307,7 @@ int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *
 				if ((bg_bits[(size_t)k * b_words + (i >> 5)] >> (i & 31u)) & 1u) sum += B.weight[i];
 			bg_cov[k] = (float)sum;
 		}
+		trs.mark("find_background_match");
 	}
 	ScoreH best;
 	int64_t best_trial = -1;
@@ -360,8 +366,10 @@ int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *
 		for (uint32_t k = 0; k < nc; ++k)
 			if (cand[k] == (uint32_t)best_trial) memcpy(d->background_match.data(), &bg_bits[(size_t)k * b_words], (size_t)b_words * 4);
 	// find_target_match (pcr_assay.cpp:544-578): search = detect = opt.target_threshold
+	pcr::Trace tr("design accept", ctx->stream);
 	DCALL(pcramp_gpu_score_pairs(ctx, PCRAMP_TARGET, bf, br, 1, o.target_threshold, o.target_threshold, o.target_amplicon_min,
 		o.target_amplicon_max, o.use_taq_mama, nullptr, d->target_match.data()));
+	tr.mark("find_target_match");
 	// PCR::write(fout, assay_pool) (assay.h:305-343): an oligo that is re-used from the pool is written in lower case
 	for (uint32_t i = 0; i < 2 * n_pool; ++i) {
 		if (pcramp_word_max_overlap(bf, &d->pool[2ull * i]) == 1.0f) res->reused_f = 1;
@@ -371,7 +379,9 @@ int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *
 		uint64_t n_amp = 0, n_bases = 0, n_bounds = 0, n_added = 0, n_keys = 0;
 		DCALL(pcramp_gpu_unique_amplicons(ctx, PCRAMP_TARGET, bf, br, 1, o.target_threshold, o.target_amplicon_min, o.target_amplicon_max, 1, &n_amp,
 			&n_bases, &n_bounds));
+		tr.mark("unique amplicons");
 		DCALL(pcramp_gpu_accept_assay(ctx, 0, o.pack_max_degen, min_oligo, &n_added, &n_keys)); // also: the assay joins the library's pool
+		tr.mark("accept_assay");
 		res->n_amplicons_added = n_added;
 		res->n_splits = 3 * n_bounds;
 		res->n_multiplex_keys = n_keys;
@@ -380,6 +390,7 @@ int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *
 	for (uint32_t i = 0; i < n_target; ++i)
 		if ((d->target_match[i >> 5] >> (i & 31u)) & 1u) active[i] = 0;
 	if (n_target) DCALL(pcramp_gpu_set_active(ctx, PCRAMP_TARGET, active.data()));
+	tr.mark("set_active");
 	d->pool.insert(d->pool.end(), bf, bf + 2); // :1123-1124
 	d->pool.insert(d->pool.end(), br, br + 2);
 	d->pool_background.push_back(d->background_match);

@@ -1941,7 +1941,12 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 			// seed-table filter (fst.cuh) unless too many oligos cannot be seeded (low thresholds: backgrounds at 0.72^2)
 			Fst fst;
 			// neighbour filter (score.cuh) when the candidates x oligos comparison is small next to the table walk it replaces
-			const bool use_neigh = ctx->use_neigh != 0 && s.n_cand > 0 && (uint64_t)s.n_cand * 2ull * n_pairs <= (1ull << 28);
+			// ... and when the neighbour bound can exclude anybody: candidate K (found at the seed threshold t, e1 = (1 - t) n misses) and oligo O
+			// (matched at t^2, e2 = (1 - t^2) n misses) are neighbours when they differ in at most e1 + e2 of their ~n common slots, and two
+			// unrelated words differ in 0.75 n -+ a few: below t^2 + t = 1.5 (t < 0.823: the background thresholds, 0.72) nearly every oligo
+			// is every candidate's neighbour, the slots overflow and every entry would be compared with every oligo
+			const bool neigh_selective = search_threshold * search_threshold + search_threshold >= 1.5f;
+			const bool use_neigh = ctx->use_neigh != 0 && neigh_selective && s.n_cand > 0 && (uint64_t)s.n_cand * 2ull * n_pairs <= (1ull << 28);
 			bool use_fst = ctx->use_fst != 0 && !use_neigh;
 			if (use_fst) {
 				CK(ctx->d_fst_planes.ensure((size_t)n_pairs * 2 * 16));
@@ -2131,6 +2136,7 @@ static int score_variants_grouped(pcramp_gpu_ctx *ctx, int kind, const uint64_t 
 	cudaStream_t st = ctx->stream;
 	if (!s.db_valid) return fail(ctx, "pcramp_gpu_score_pairs: no database (call pcramp_gpu_select_words first)");
 	if (!(ctx->use_neigh && ctx->use_entry_score && s.n_cand > 0 && s.n_entries > 0 && s.n && n && (uint64_t)s.n_cand * 2ull * G <= (1ull << 28))) return 2;
+	if (search_threshold * search_threshold + search_threshold < 1.5f) return 2; // the neighbour bound excludes nobody (score_launch)
 	const uint32_t n_words = (s.n + 31u) / 32u;
 	ctx->res_words = n_words;
 	const size_t bits_bytes = (size_t)n * n_words * 4;

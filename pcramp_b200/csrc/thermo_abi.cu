@@ -169,6 +169,7 @@ int thermo_upload(pcramp_gpu_ctx *ctx, ThermoState *t, int op, uint32_t n)
 // Launch order: a warp pays for its longest problem (rows x column strips of the DP fill), so problems of equal size are
 // put next to each other: slot s of the launch works on problem order[s] (results still land in out[problem]).
 constexpr uint32_t THERMO_ORDER_MIN = 2048; // below this the launch is a handful of warps anyway
+constexpr uint32_t THERMO_CHUNK = 1u << 20;  // problems per launch of the library's own large batches (thermo_run_codes, multiplex_compatible)
 
 __global__ void thermo_key_kernel(int op, uint32_t n, const uint8_t *__restrict__ len_a, const uint8_t *__restrict__ len_b, uint16_t *key, uint32_t *ord)
 {
@@ -793,24 +794,38 @@ int thermo_run_codes(pcramp_gpu_ctx *ctx, int op, uint32_t n, const uint8_t *cod
 	if (thermo_get(ctx, &t)) return 1;
 	if (thermo_set_salt(ctx, t, salt)) return 1;
 	if (two_sequences(op)) return fail(ctx, "thermo_run_codes: single-sequence ops only");
-	if (thermo_reserve(ctx, t, n)) return 1;
-	if (n) {
-		memcpy(t->h_a.p, codes, (size_t)n * THERMO_SEQ_STRIDE);
-		memcpy(t->h_la.p, len, n);
-		memset(t->h_lb.p, 0, n);
-		float *ls = t->h_ls.as<float>();
-		float last_strand = -1.0f, last_log = 0.0f;
-		for (uint32_t p = 0; p < n; ++p) { // runs of equal concentrations (the expansions of one oligo) share one logf
-			if (strand[p] != last_strand) {
-				last_strand = strand[p];
-				last_log = logf(last_strand);
+	// in chunks: the page-locked staging stays at one chunk whatever the batch (growing it is slow: hundreds of ms for 10^7 problems)
+	uint64_t launches = 0, cells = 0;
+	float ms = 0.0f;
+	for (uint32_t lo = 0; lo < n || lo == 0; lo += THERMO_CHUNK) {
+		const uint32_t m = std::min<uint32_t>(THERMO_CHUNK, n - lo);
+		if (thermo_reserve(ctx, t, m)) return 1;
+		if (m) {
+			memcpy(t->h_a.p, codes + (size_t)lo * THERMO_SEQ_STRIDE, (size_t)m * THERMO_SEQ_STRIDE);
+			memcpy(t->h_la.p, len + lo, m);
+			memset(t->h_lb.p, 0, m);
+			float *ls = t->h_ls.as<float>();
+			float last_strand = -1.0f, last_log = 0.0f;
+			for (uint32_t p = 0; p < m; ++p) { // runs of equal concentrations (the expansions of one oligo) share one logf
+				if (strand[lo + p] != last_strand) {
+					last_strand = strand[lo + p];
+					last_log = logf(last_strand);
+				}
+				ls[p] = last_log;
 			}
-			ls[p] = last_log;
 		}
+		if (run_and_fetch(ctx, t, op, m)) return 1;
+		const float4 *o = t->h_out.as<float4>();
+		for (uint32_t p = 0; p < m; ++p) tm_out[lo + p] = o[p].x;
+		launches += t->stats.kernel_launches;
+		cells += t->stats.dp_cells;
+		ms += t->stats.ms_kernel;
+		if (!n) break;
 	}
-	if (run_and_fetch(ctx, t, op, n)) return 1;
-	const float4 *o = t->h_out.as<float4>();
-	for (uint32_t p = 0; p < n; ++p) tm_out[p] = o[p].x;
+	t->stats.kernel_launches = launches;
+	t->stats.dp_cells = cells;
+	t->stats.n_problems = n;
+	t->stats.ms_kernel = ms;
 	return 0;
 }
 } // namespace nc
@@ -1073,17 +1088,56 @@ int pcramp_gpu_multiplex_compatible(pcramp_gpu_ctx *ctx, const uint64_t *f, cons
 	uint64_t pool_count = 0, total = 0;
 	for (const Expansion &e : pool) pool_count += e.count;
 	for (const Expansion &e : trial) total += e.count * pool_count;
-	if (total > 0xffffffffull) return fail(ctx, "pcramp_gpu_multiplex_compatible: too many expansions in one batch");
-	if (thermo_reserve(ctx, t, (uint32_t)total)) return 1;
-	std::vector<uint32_t> owner(total);
-	uint32_t p = 0;
-	for (uint32_t i = 0; i < n_pairs; ++i)
-		for (const Expansion &q : pool) // main.cpp:748-752: pool_assay.multiplex_compatible(melt, opt, trial) -> the pool oligo is the query
-			for (int so = 0; so < 2; ++so) stage_pair_products(t, q, trial[2 * i + so], log_strand, i, owner, p);
-	if (run_and_fetch(ctx, t, fast_alignment ? OP_HETERODIMER_DIAG : OP_HETERODIMER, (uint32_t)total)) return 1;
-	const float4 *o = t->h_out.as<float4>();
-	for (uint32_t q = 0; q < (uint32_t)total; ++q)
-		if (o[q].x >= max_dimer) ok[owner[q]] = 0; // pcr_assay.cpp:842
+	// groups of trials of about THERMO_CHUNK problems: the page-locked staging stays at one group whatever the pool has grown to
+	std::vector<uint64_t> first((size_t)n_pairs + 1, 0);
+	for (uint32_t i = 0; i < n_pairs; ++i) first[i + 1] = first[i] + (trial[2 * i].count + trial[2 * i + 1].count) * pool_count;
+	(void)total;
+	std::vector<uint32_t> owner;
+	uint64_t launches = 0, cells = 0;
+	float ms = 0.0f;
+	for (uint32_t g0 = 0; g0 < n_pairs;) {
+		uint32_t g1 = g0 + 1;
+		while (g1 < n_pairs && first[g1 + 1] - first[g0] <= THERMO_CHUNK) ++g1;
+		const uint64_t m = first[g1] - first[g0];
+		if (m > 0xffffffffull) return fail(ctx, "pcramp_gpu_multiplex_compatible: too many expansions of one trial against the pool");
+		if (thermo_reserve(ctx, t, (uint32_t)m)) return 1;
+		owner.resize(m);
+		auto stage = [&](uint32_t lo, uint32_t hi) { // every trial's problems start at a known slot
+			for (uint32_t i = lo; i < hi; ++i) {
+				uint32_t p = (uint32_t)(first[i] - first[g0]);
+				for (const Expansion &q : pool) // main.cpp:748-752: pool_assay.multiplex_compatible(melt, opt, trial) -> the pool oligo is the query
+					for (int so = 0; so < 2; ++so) stage_pair_products(t, q, trial[2 * i + so], log_strand, i, owner, p);
+			}
+		};
+		const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+		const uint32_t n_thr = m < 65536ull ? 1u : std::min<uint32_t>(std::min<uint32_t>(8u, hw), g1 - g0);
+		if (n_thr <= 1) {
+			stage(g0, g1);
+		} else { // equal shares of the problems, cut at trial boundaries
+			std::vector<std::thread> workers;
+			uint32_t lo = g0;
+			for (uint32_t k = 0; k < n_thr; ++k) {
+				uint32_t hi = lo;
+				const uint64_t want = first[g0] + m * (k + 1) / n_thr;
+				while (hi < g1 && (first[hi + 1] <= want || k + 1 == n_thr)) ++hi;
+				if (hi > lo) workers.emplace_back(stage, lo, hi);
+				lo = hi;
+			}
+			for (std::thread &th : workers) th.join();
+		}
+		if (run_and_fetch(ctx, t, fast_alignment ? OP_HETERODIMER_DIAG : OP_HETERODIMER, (uint32_t)m)) return 1;
+		const float4 *o = t->h_out.as<float4>();
+		for (uint32_t q = 0; q < (uint32_t)m; ++q)
+			if (o[q].x >= max_dimer) ok[owner[q]] = 0; // pcr_assay.cpp:842
+		launches += t->stats.kernel_launches;
+		cells += t->stats.dp_cells;
+		ms += t->stats.ms_kernel;
+		g0 = g1;
+	}
+	t->stats.kernel_launches = launches;
+	t->stats.dp_cells = cells;
+	t->stats.n_problems = first[n_pairs];
+	t->stats.ms_kernel = ms;
 	return 0;
 }
 
