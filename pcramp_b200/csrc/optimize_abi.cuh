@@ -194,6 +194,43 @@ inline void expansion_codes(const W128 &w, uint64_t idx, uint8_t *dst, int &len)
 	}
 }
 
+// all n_exp expansions of an oligo, in expansion_codes' order, 32 bytes each: the single-letter positions are written once and the few
+// degenerate ones (at most four for degeneracy <= 16) are stepped like an odometer, position 0 fastest
+inline void expansion_codes_all(const W128 &w, uint32_t n_exp, uint8_t *dst, uint8_t *lens)
+{
+	static const uint8_t code_of_bit[4] = {nc::bA, nc::bC, nc::bG, nc::bT};
+	const int a = w_start(w), b = w_stop(w);
+	uint8_t base[32] = {0};
+	uint8_t deg_pos[32], deg_k[32], deg_letters[32][4], digit[32];
+	int len = 0, nd = 0;
+	for (int i = a; i >= 0 && i <= b; ++i) {
+		const uint32_t nb = w_get(w, i);
+		uint8_t letters[4];
+		int k = 0;
+		for (int bit = 0; bit < 4; ++bit)
+			if (nb & (1u << bit)) letters[k++] = code_of_bit[bit];
+		base[len] = k ? letters[0] : 0;
+		if (k > 1) {
+			deg_pos[nd] = (uint8_t)len;
+			deg_k[nd] = (uint8_t)k;
+			memcpy(deg_letters[nd], letters, 4);
+			digit[nd] = 0;
+			++nd;
+		}
+		++len;
+	}
+	for (uint32_t e = 0; e < n_exp; ++e) {
+		uint8_t *out = dst + (size_t)e * 32;
+		memcpy(out, base, 32);
+		for (int d = 0; d < nd; ++d) out[deg_pos[d]] = deg_letters[d][digit[d]];
+		lens[e] = (uint8_t)len;
+		for (int d = 0; d < nd; ++d) { // next combination
+			if (++digit[d] < deg_k[d]) break;
+			digit[d] = 0;
+		}
+	}
+}
+
 } // namespace opt
 } // namespace pcr
 
@@ -353,21 +390,17 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 			n_exp += v.n_exp;
 		}
 		if (n_exp > 0xffffffffull) return fail(ctx, "pcramp_gpu_optimize: too many trial oligos in one iteration");
-		codes.assign((size_t)n_exp * 32, 0);
-		lens.assign(n_exp, 0);
-		strand.assign(n_exp, 0.0f);
-		tm.assign(n_exp, 0.0f);
+		codes.resize((size_t)n_exp * 32); // every byte is written below
+		lens.resize(n_exp);
+		strand.resize(n_exp);
+		tm.resize(n_exp);
 		parallel_ranges(vars.size(), 2048, nullptr, [&](size_t, size_t lo, size_t hi) {
 			for (size_t i = lo; i < hi; ++i) {
 				const Variant &v = vars[i];
 				const double dg = degeneracy(v.w);
 				const float st = (float)((double)o->primer_strand / dg); // valid_pcr.cpp:13
-				for (uint32_t e = 0; e < v.n_exp; ++e) {
-					int len = 0;
-					expansion_codes(v.w, e, codes.data() + (size_t)(v.first_exp + e) * 32, len);
-					lens[v.first_exp + e] = (uint8_t)len;
-					strand[v.first_exp + e] = st;
-				}
+				expansion_codes_all(v.w, v.n_exp, codes.data() + (size_t)v.first_exp * 32, lens.data() + v.first_exp);
+				for (uint32_t e = 0; e < v.n_exp; ++e) strand[v.first_exp + e] = st;
 			}
 		});
 		lap(1);
@@ -382,45 +415,51 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 		std::vector<uint8_t> hp_codes, hp_lens;
 		std::vector<float> hp_strand;
 		{
-			std::vector<size_t> cuts; // first variant of every trial: a trial's variants share its ring buffer and stay on one thread
-			for (size_t i = 0; i < vars.size(); ++i)
-				if (i == 0 || vars[i].trial != vars[i - 1].trial) cuts.push_back(i);
-			struct Part {
-				std::vector<uint32_t> src;
-				std::vector<uint8_t> codes, lens;
-				std::vector<float> strand;
-			} part[PARALLEL_PARTS];
-			parallel_ranges(vars.size(), 4096, &cuts, [&](size_t which, size_t lo, size_t hi) {
-				Part &P = part[which];
+			// how many hairpin problems a variant contributes: its expansions up to the first whose duplex Tm is out of range
+			std::vector<uint32_t> hp_at(vars.size() + 1, 0);
+			parallel_ranges(vars.size(), 4096, nullptr, [&](size_t, size_t lo, size_t hi) {
 				for (size_t i = lo; i < hi; ++i) {
 					Variant &v = vars[i];
-					std::vector<uint8_t> &rg = ring[v.trial];
 					v.valid = true;
-					for (uint32_t e = 0; e < v.n_exp; ++e) {
-						const uint32_t x = v.first_exp + e;
-						const float t_pm = tm[x];
+					uint32_t k = 0;
+					for (; k < v.n_exp; ++k) {
+						const float t_pm = tm[v.first_exp + k];
 						if ((t_pm < o->primer_tm_min) || (t_pm > o->primer_tm_max)) { // valid_pcr.cpp:20-22: return false
 							v.valid = false;
 							break;
 						}
+					}
+					hp_at[i + 1] = k;
+				}
+			});
+			for (size_t i = 0; i < vars.size(); ++i) hp_at[i + 1] += hp_at[i];
+			const size_t n_hp = hp_at[vars.size()];
+			hp_src.resize(n_hp);
+			hp_codes.resize(n_hp * 32);
+			hp_lens.resize(n_hp);
+			hp_strand.resize(n_hp);
+			std::vector<size_t> cuts; // first variant of every trial: a trial's variants share its ring buffer and stay on one thread
+			for (size_t i = 0; i < vars.size(); ++i)
+				if (i == 0 || vars[i].trial != vars[i - 1].trial) cuts.push_back(i);
+			parallel_ranges(vars.size(), 4096, &cuts, [&](size_t, size_t lo, size_t hi) {
+				for (size_t i = lo; i < hi; ++i) {
+					const Variant &v = vars[i];
+					std::vector<uint8_t> &rg = ring[v.trial];
+					const uint32_t n_load = hp_at[i + 1] - hp_at[i];
+					for (uint32_t e = 0; e < n_load; ++e) {
+						const uint32_t x = v.first_exp + e;
+						const size_t at = (size_t)hp_at[i] + e;
 						const int len = lens[x];
-						uint8_t slot[32];
+						uint8_t *slot = hp_codes.data() + at * 32;
 						memcpy(slot, codes.data() + (size_t)x * 32, 32);
 						for (int k = len; k < 32 && k < len + 2; ++k) slot[k] = rg[k]; // what set_query leaves behind past the new end
 						for (int k = 0; k < len; ++k) rg[k] = slot[k];                  // set_query (nuc_cruc.h:875-913)
-						P.src.push_back(x);
-						P.codes.insert(P.codes.end(), slot, slot + 32);
-						P.lens.push_back((uint8_t)len);
-						P.strand.push_back(strand[x]);
+						hp_src[at] = x;
+						hp_lens[at] = (uint8_t)len;
+						hp_strand[at] = strand[x];
 					}
 				}
 			});
-			for (const Part &P : part) {
-				hp_src.insert(hp_src.end(), P.src.begin(), P.src.end());
-				hp_codes.insert(hp_codes.end(), P.codes.begin(), P.codes.end());
-				hp_lens.insert(hp_lens.end(), P.lens.begin(), P.lens.end());
-				hp_strand.insert(hp_strand.end(), P.strand.begin(), P.strand.end());
-			}
 		}
 		lap(3);
 		tr_hp += hp_src.size();
