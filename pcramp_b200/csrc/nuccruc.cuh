@@ -274,7 +274,6 @@ struct alignas(16) InfoRow8 {
 PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 {
 	constexpr int W = NC_STRIP;
-	constexpr int NS = (NC_MAX_LEN + W - 1) / W;
 	constexpr int NEG = -0x7fffffff;
 	dp_border(c);
 	c.n_max_cell = 0;
@@ -286,10 +285,10 @@ PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 	const int *__restrict__ dg = c.D->dg;
 	int eM[NC_MAX_LEN + 2], eIq[NC_MAX_LEN + 2], eIt[NC_MAX_LEN + 2]; // clamped state of column j0 - 1, per row (column 0: the border)
 	for (int i = 0; i < NC_MAX_LEN + 2; ++i) eM[i] = eIq[i] = eIt[i] = 0;
-	// per (strip, row): the largest M among the row's cells of the strip and which of them reach it; the maximal cells of the
-	// matrix are read back from these in row-major order after the fill (no per-cell bookkeeping inside it)
-	int rmax[NS][NC_MAX_LEN + 1];
-	unsigned char rmask[NS][NC_MAX_LEN + 1];
+	// max_ptr bookkeeping (nuc_cruc.cpp:517-537) per (strip, row), not per cell: the row's largest M within the strip and which cells
+	// reach it are compared with the running maximum -- a larger one restarts the list, an equal one appends to it.  (Round 1 stored
+	// both per (strip, row) and read them back after the fill: a chain of dependent local-memory loads that was 20 % of the kernel's
+	// stall samples, ncu source page.)  Cells arrive strip-major; the list is put into row-major order at the end.
 	int max_score = -1;
 	long long cells = 0;
 	int n_strips = 0;
@@ -369,29 +368,34 @@ PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 			unsigned int eq = 0u;
 #pragma unroll
 			for (int k = 0; k < W; ++k) eq |= (xm[k] == row_max ? 1u : 0u) << k;
-			rmax[n_strips][i] = row_max;
-			rmask[n_strips][i] = (unsigned char)eq;
-			max_score = imax(max_score, row_max);
+			if (row_max >= max_score) {
+				if (row_max > max_score) {
+					max_score = row_max;
+					c.n_max_cell = 0;
+				}
+				while (eq) {
+					int k = 0;
+					while (!((eq >> k) & 1u)) ++k;
+					eq &= eq - 1u;
+					if (c.n_max_cell < NC_MAX_CELLS) c.max_cell[c.n_max_cell] = i * NC_STRIDE + j0 + k;
+					++c.n_max_cell;
+				}
+			}
 			cells += nv < W ? nv : W;
 			pqb = qb;
 		}
 	}
-	// max_ptr bookkeeping (nuc_cruc.cpp:517-537) after the fact: the cells that equal the maximum, in row-major order
-	for (int i = 1; i <= rows; ++i) {
-		const int cols = hairpin ? (max_stem - (i - 1)) : tlen;
-		for (int s = 0; s < n_strips; ++s) {
-			if (s * W + 1 > cols) break;
-			if (rmax[s][i] != max_score) continue;
-			unsigned int eq = rmask[s][i];
-			while (eq) {
-				int k = 0;
-				while (!((eq >> k) & 1u)) ++k;
-				eq &= eq - 1u;
-				if (c.n_max_cell < NC_MAX_CELLS) c.max_cell[c.n_max_cell] = i * NC_STRIDE + s * W + 1 + k;
-				++c.n_max_cell;
+	// row-major order (cell ids ascend with (row, column)); a list that overflowed is not used (the replay pass takes over)
+	if (c.n_max_cell <= NC_MAX_CELLS)
+		for (int a = 1; a < c.n_max_cell; ++a) {
+			const int x = c.max_cell[a];
+			int b = a;
+			while (b > 0 && c.max_cell[b - 1] > x) {
+				c.max_cell[b] = c.max_cell[b - 1];
+				--b;
 			}
+			c.max_cell[b] = x;
 		}
-	}
 	if (cells_out) *cells_out = cells;
 	return max_score;
 }
