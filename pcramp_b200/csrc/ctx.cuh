@@ -231,6 +231,8 @@ struct pcramp_gpu_ctx {
 	int use_variant_groups = 1;      // option "use_variant_groups"
 	DevBuf bg_cnt4, bg_off4, bg_entry, bg_res, bg_cnt2, bg_off2; // find_background_match by units (sw_abi.cuh)
 	int use_background_units = 1;    // option "use_background_units"
+	int use_async_scan = 0;          // option "use_async_scan" = 1: scan_index_async_kernel instead of scan_index_kernel (measured slower)
+	bool async_scan_ready = false;   // its dynamic shared memory size has been set on this context's device
 	float sw_ms_kernel = 0.0f;
 };
 

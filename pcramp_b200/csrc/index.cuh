@@ -524,6 +524,125 @@ scan_index_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsi
 	if (wb.used < IDX_BLOCK) index_block_pad(cs, wb, lane);
 }
 
+// The same scan with the entry loads taken out of the registers (round 2; option "use_async_scan" = 1, NOT the default: measured
+// slower).  ncu's source page of the kernel above puts 49 % of its stall samples on the first use of the loaded entries: a warp has
+// one range (~75 entries, three 16-byte loads per lane) in flight, waits a DRAM round trip for it, verifies, and only then asks for
+// the next; keeping a second range in flight in registers costs 16 more of them and spills (measured, above).  Here every warp owns
+// a ring of IDXA_STAGES chunks of 128 entries in SHARED memory and fills it with cp.async (16 bytes per lane, no destination
+// register): while chunk k is verified, chunks k+1 .. k+STAGES-1 -- the next ranges, or the next 128 entries of a long one -- are
+// already on their way, together with their pattern mask and threshold.  Result on the bench batch (64 registers, no spills, 4
+// resident CTAs per SM): 0.371 / 0.367 / 0.439 ms with 2 / 3 / 4 stages against 0.293 ms for the register version -- two or three
+// times the bytes in flight per warp buy nothing, so the limit is not the latency a warp sees but what the memory system delivers
+// for this access pattern: 7.9 x 10^5 independent ~1.2 KB reads scattered over 9.6 GB (every range opens its own DRAM page), 3.3 TB/s
+// = 0.5 of the streaming peak.  Kept for the record and as a cross-check of the scan (tests/test_gpu_parity.py).
+#ifndef IDXA_STAGES
+#define IDXA_STAGES 3
+#endif
+constexpr int IDXA_CHUNK = 128;                                   // entries per chunk: four rows of 32
+constexpr int IDXA_WARPS = IDX_THREADS / 32;
+struct IdxaMeta {                                                 // per (warp, stage), written by lane 0 / cp.async at issue time
+	uint4 mask;                                                   // the pattern's letter planes (cp.async)
+	uint32_t thr_word;                                            // meta[pid] (cp.async)
+	uint32_t pid, seg, n;                                         // n = entries in the chunk, 0 = the warp has run out of work
+};
+constexpr size_t IDXA_SMEM = (size_t)IDXA_WARPS * IDXA_STAGES * (IDXA_CHUNK * sizeof(uint4) + sizeof(IdxaMeta));
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+	const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+	const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(gmem) : "memory");
+}
+
+__global__ void __launch_bounds__(IDX_THREADS, IDX_BLOCKS_PER_SM)
+scan_index_async_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, const unsigned int *__restrict__ n_queries, uint32_t q_cap,
+	const uint4 *__restrict__ mask, const uint32_t *__restrict__ meta, IdxCandSink cs)
+{
+	extern __shared__ uint4 s_idxa[];
+	const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	uint4 *ring = s_idxa + (size_t)wib * IDXA_STAGES * IDXA_CHUNK;
+	IdxaMeta *smeta = reinterpret_cast<IdxaMeta *>(s_idxa + (size_t)IDXA_WARPS * IDXA_STAGES * IDXA_CHUNK) + wib * IDXA_STAGES;
+	const uint32_t nq = min(*n_queries, q_cap); // more queries than slots: the host grows the buffer and re-runs
+	// producer: the range being cut into chunks, and the next descriptor already loaded
+	uint32_t q = warp;
+	IdxQuery cur, nxt;
+	cur.lo = cur.hi = cur.pid = cur.seg = 0u;
+	nxt = cur;
+	bool have_cur = q < nq, have_nxt = false;
+	if (have_cur) cur = queries[q];
+	if (q + n_warps < nq) { nxt = queries[q + n_warps]; have_nxt = true; }
+	uint32_t off = 0u;
+	auto issue = [&](uint32_t stage) {
+		while (have_cur && cur.lo + off >= cur.hi) { // this range is finished (or empty): on to the next one
+			cur = nxt;
+			have_cur = have_nxt;
+			off = 0u;
+			q += n_warps;
+			have_nxt = q + n_warps < nq;
+			if (have_nxt) nxt = queries[q + n_warps];
+		}
+		uint32_t n = 0u;
+		if (have_cur) {
+			const uint32_t base = cur.lo + off;
+			n = min((uint32_t)IDXA_CHUNK, cur.hi - base);
+			uint4 *dst = ring + (size_t)stage * IDXA_CHUNK;
+			#pragma unroll
+			for (int u = 0; u < IDXA_CHUNK / 32; ++u) {
+				const uint32_t j = 32u * u + lane;
+				if (j < n) cp_async16(dst + j, ix.entries + base + j);
+			}
+			if (lane == 0u) {
+				cp_async16(&smeta[stage].mask, mask + cur.pid);
+				cp_async4(&smeta[stage].thr_word, meta + cur.pid);
+				smeta[stage].pid = cur.pid;
+				smeta[stage].seg = cur.seg;
+			}
+			off += n;
+		}
+		if (lane == 0u) smeta[stage].n = n;
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	#pragma unroll
+	for (int s = 0; s < IDXA_STAGES; ++s) issue((uint32_t)s);
+	IdxWarpBlock wb;
+	uint32_t head = 0u;
+	for (;;) {
+		asm volatile("cp.async.wait_group %0;" ::"n"(IDXA_STAGES - 1) : "memory");
+		__syncwarp();
+		const IdxaMeta m = smeta[head];
+		if (m.n == 0u) break; // chunks are issued in order: an empty one means nothing follows
+		const uint32_t thr = m.thr_word & 63u;
+		const uint32_t sh = IDX_CTX_BEFORE - (m.seg >> 24); // context bit of primer base 0 (window offset <= 16)
+		IdxQuery qy;
+		qy.lo = qy.hi = 0u;
+		qy.pid = m.pid;
+		qy.seg = m.seg;
+		const uint4 *src = ring + (size_t)head * IDXA_CHUNK;
+		uint4 e[IDXA_CHUNK / 32];
+		uint32_t valid = 0u;
+		#pragma unroll
+		for (int u = 0; u < IDXA_CHUNK / 32; ++u) {
+			const uint32_t j = 32u * u + lane;
+			e[u] = make_uint4(0, 0, 0, 0);
+			if (j < m.n) {
+				e[u] = src[j];
+				valid |= 1u << u;
+			}
+		}
+		index_append<IDXA_CHUNK / 32>(e, valid, m.mask, thr, sh, qy, cs, lane, wb);
+		__syncwarp(); // every lane has read this stage before it is refilled
+		issue(head);
+		head = head + 1u == (uint32_t)IDXA_STAGES ? 0u : head + 1u;
+	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	if (wb.used < IDX_BLOCK) index_block_pad(cs, wb, lane);
+}
+
 // place each candidate in its sequence, drop what other kernels own, report once
 __global__ void __launch_bounds__(256)
 index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__restrict__ g_meta, const uint32_t *__restrict__ g_meta2,

@@ -347,6 +347,31 @@ inline float ev_ms(cudaEvent_t a, cudaEvent_t b)
 // collection of 5 x 10^9 bases is three parts, each queried on its own.  Cost per part: one radix sort of its positions; ~32 bytes
 // per base while it is built (the scratch is kept between builds while it is small), 16 afterwards.  A failed allocation leaves the
 // collection on scan_seed_kernel.  Splits do not come here (see SeqSet::idx_stale).
+// scan_index_async_kernel (a ring of chunks in shared memory filled by cp.async, index.cuh) or, with option "use_async_scan" = 0,
+// scan_index_kernel (the entries of one range in registers)
+static int launch_scan_index(pcramp_gpu_ctx *ctx, cudaStream_t st, const TextIndex &ix, const IdxQuery *queries, const unsigned int *n_queries,
+	uint32_t q_cap, const uint4 *mask, const uint32_t *meta, const IdxCandSink &cs)
+{
+	const unsigned grid = (unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM;
+	if (ctx->use_async_scan) {
+		if (!ctx->async_scan_ready) {
+			CK(cudaFuncSetAttribute(scan_index_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDXA_SMEM));
+			CK(cudaFuncSetAttribute(scan_index_async_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+			if (getenv("PCRAMP_TRACE")) {
+				int nb = 0;
+				cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_index_async_kernel, IDX_THREADS, IDXA_SMEM);
+				fprintf(stderr, "[trace] scan_index_async_kernel: %d resident CTAs per SM, %zu bytes of shared memory each\n", nb, (size_t)IDXA_SMEM);
+			}
+			ctx->async_scan_ready = true;
+		}
+		scan_index_async_kernel<<<grid, IDX_THREADS, IDXA_SMEM, st>>>(ix, queries, n_queries, q_cap, mask, meta, cs);
+	} else {
+		scan_index_kernel<<<grid, IDX_THREADS, 0, st>>>(ix, queries, n_queries, q_cap, mask, meta, cs);
+	}
+	CK(cudaGetLastError());
+	return 0;
+}
+
 int build_index(pcramp_gpu_ctx *ctx, SeqSet &s)
 {
 	s.idx_drop();
@@ -519,6 +544,7 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index; w->idx_part_cap = parent->idx_part_cap;
 	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
 	w->use_entry_score = parent->use_entry_score; w->use_seg_db = parent->use_seg_db; w->use_fast = parent->use_fast;
+	w->use_async_scan = parent->use_async_scan;
 	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
 		const SeqSet &p = parent->sets[kind];
 		SeqSet &s = w->sets[kind];
@@ -1095,8 +1121,8 @@ static int select_words_general(pcramp_gpu_ctx *ctx, int kind, int opt5, int opt
 					cs.count = d_nq + 4;
 					cs.cap = (uint32_t)ccap;
 					CK(cudaEventRecord(ctx->ev[8], st));
-					scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq, (uint32_t)qcap,
-						ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
+					if (launch_scan_index(ctx, st, ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq, (uint32_t)qcap, ctx->d_part_mask.as<uint4>(),
+							ctx->d_part_meta.as<uint32_t>(), cs)) return 1;
 					CK(cudaGetLastError());
 					CK(cudaEventRecord(ctx->ev[9], st));
 					stat.kernel_launches++;
@@ -1618,8 +1644,8 @@ static int select_words_fast(pcramp_gpu_ctx *ctx, int kind, float threshold, con
 		index_query_kernel<<<grid_for((uint64_t)n_pat * IDX_SLOTS, 256), 256, 0, st>>>(ctx->d_part_mask.as<uint4>(), ctx->d_part_meta2.as<uint32_t>(), n_pat,
 			ix.off, ctx->d_idx_queries.as<IdxQuery>(), qcap, d_nq, d_nq + 1, (unsigned long long *)(d_nq + 2));
 		CK(cudaEventRecord(ctx->ev[8], st));
-		scan_index_kernel<<<(unsigned)ctx->sm_count * IDX_BLOCKS_PER_SM, IDX_THREADS, 0, st>>>(ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq, qcap,
-			ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs);
+		if (launch_scan_index(ctx, st, ix, ctx->d_idx_queries.as<IdxQuery>(), d_nq, qcap, ctx->d_part_mask.as<uint4>(), ctx->d_part_meta.as<uint32_t>(), cs))
+			return 1;
 		CK(cudaEventRecord(ctx->ev[9], st));
 		index_hits_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, st>>>(sd, ix, cs, ctx->d_part_meta.as<uint32_t>(), ctx->d_part_meta2.as<uint32_t>(),
 			s.n_dirty ? s.d_dirty_bits.as<uint32_t>() : nullptr, nullptr, cand_bits, hs);
@@ -2433,6 +2459,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_entry_score") == 0) { ctx->use_entry_score = value; return 0; }
 	if (strcmp(name, "use_variant_groups") == 0) { ctx->use_variant_groups = value; return 0; }
 	if (strcmp(name, "use_background_units") == 0) { ctx->use_background_units = value; return 0; }
+	if (strcmp(name, "use_async_scan") == 0) { ctx->use_async_scan = value; return 0; }
 	if (strcmp(name, "use_segmented_db") == 0) { ctx->use_seg_db = value; return 0; }
 	if (strcmp(name, "use_fast_path") == 0) { ctx->use_fast = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }

@@ -595,3 +595,24 @@ def test_degenerate_primers_through_the_index(gpu, oracle):
         cov_g, bits_g = g.score_pairs(f, r, search, detect, 80, 200, False)
         assert np.array_equal(bits_g, bits_o) and np.array_equal(cov_g, cov_o)
     assert int(bits_o.sum()) > 0
+
+
+@pytest.mark.parametrize("name", ["basic", "degenerate", "splits", "shift"])
+def test_async_index_scan_equals_register_scan(gpu, name):
+    """scan_index_async_kernel (a cp.async ring of chunks in shared memory; option use_async_scan) == scan_index_kernel"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    out = []
+    for use in (0, 1):
+        gpu.set_option("use_async_scan", use)
+        try:
+            g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+            out.append((_db_tuple(gpu), gpu.stats()["n_hits"]))
+        finally:
+            gpu.set_option("use_async_scan", 0)
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.array_equal(a, b)
+    assert out[0][1] == out[1][1]
