@@ -649,13 +649,10 @@ index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__res
 	const uint32_t *__restrict__ dirty_bits, const uint8_t *__restrict__ stale, uint32_t cand_bits, HitSink hs)
 {
 	const uint32_t total = min(*cs.count, cs.cap);
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	__shared__ uint32_t s_cnt[8];               // hits per warp of this row of 256 candidates
-	__shared__ unsigned long long s_base;
-	// block-uniform trip count: the warps of a CTA meet before the hit list is touched, so a row of 256 candidates costs ONE atomic on
-	// the list counter (2.7 x 10^6 hits per batch: one atomic per warp was 8 x 10^4 read-modify-writes of one address, ~1 ns each)
-	for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < total; b0 += gridDim.x * blockDim.x) {
-		const uint32_t i0 = b0 + (threadIdx.x - lane);
+	const uint32_t lane = threadIdx.x & 31u;
+	// warp-uniform trip count: the lanes of a warp meet again before the hit list is touched, so a row of 32 candidates costs one
+	// atomic on the list counter instead of one per group of lanes that happened to survive the same branches
+	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += gridDim.x * blockDim.x) {
 		const uint32_t i = i0 + lane;
 		bool ok = false;
 		uint32_t seq = 0, meta = 0, meta2 = 0, cnt = 0;
@@ -697,23 +694,18 @@ index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__res
 			wstart = (uint32_t)ws;
 		}
 		const uint32_t bal = __ballot_sync(0xffffffffu, one);
-		if (lane == 0u) s_cnt[warp] = (uint32_t)__popc(bal);
-		__syncthreads();
-		if (threadIdx.x == 0u) {
-			uint32_t sum = 0;
-			for (uint32_t w = 0; w < blockDim.x / 32u; ++w) sum += s_cnt[w];
-			s_base = sum ? atomicAdd(hs.count, (unsigned long long)sum) : 0ull;
-		}
-		__syncthreads();
-		if (one) {
-			unsigned long long at = s_base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
-			for (uint32_t w = 0; w < warp; ++w) at += s_cnt[w];
-			if (at < hs.cap) {
-				hs.key[at] = hit_key_pack(seq, meta >> 12, cand_bits, cnt, ENT_FULL, (meta >> 11) & 1u);
-				hs.val[at] = wstart + 31u;
+		if (bal) {
+			unsigned long long base = 0;
+			if (lane == 0u) base = atomicAdd(hs.count, (unsigned long long)__popc(bal));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (one) {
+				const unsigned long long at = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+				if (at < hs.cap) {
+					hs.key[at] = hit_key_pack(seq, meta >> 12, cand_bits, cnt, ENT_FULL, (meta >> 11) & 1u);
+					hs.val[at] = wstart + 31u;
+				}
 			}
 		}
-		__syncthreads(); // s_cnt / s_base are rewritten by the next row
 	}
 }
 

@@ -374,8 +374,7 @@ PCR_HD int dp_fill_strips(Ctx &c, bool hairpin, long long *cells_out)
 					c.n_max_cell = 0;
 				}
 				while (eq) {
-					int k = 0;
-					while (!((eq >> k) & 1u)) ++k;
+					const int k = ctz64((uint64_t)eq);
 					eq &= eq - 1u;
 					if (c.n_max_cell < NC_MAX_CELLS) c.max_cell[c.n_max_cell] = i * NC_STRIDE + j0 + k;
 					++c.n_max_cell;
