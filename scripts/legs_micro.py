@@ -14,7 +14,7 @@ from pcramp_b200 import PcrampGpu  # noqa: E402
 import bench_legs  # noqa: E402
 
 a = argparse.Namespace(no_cpu_baseline="--no-cpu" in sys.argv, dp_problems=262144, dp_cpu_problems=60000, steps=10, warmup=3, pairs=1000,
-                       c4_targets=64, c4_length=5000000, hbm_peak=6553.0)
+                       c4_targets=int(os.environ.get("C4_TARGETS", "64")), c4_length=5000000, hbm_peak=6553.0)
 for name, fn in (("background", bench_legs.background_leg), ("optimize", bench_legs.optimize_leg), ("design", bench_legs.design_leg),
                  ("large", bench_legs.large_genome_leg)):
     if name in sys.argv:
