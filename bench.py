@@ -67,7 +67,7 @@ def parse_args():
     ap.add_argument("--config-legs", default="background,degenerate,optimize,design,large",
                     help="legs for the other BASELINE configurations (bench_legs.py; rank 0, N = 1): any of background (C2), degenerate (C3), "
                          "optimize (C1 moves), design (C1 iterations), large (C4 shape); 'none' skips them")
-    ap.add_argument("--c4-targets", type=int, default=64, help="genomes in the large-genome leg")
+    ap.add_argument("--c4-targets", type=int, default=1000, help="genomes in the large-genome leg (1000 x 5 Mb = BASELINE config 4's targets)")
     ap.add_argument("--c4-length", type=int, default=5000000, help="bases per genome in the large-genome leg")
     return ap.parse_args()
 

@@ -11,7 +11,8 @@ sample with a bit-for-bit comparison of that sample:
   optimize_moves       C1: optimize() with all six moves on the trials of one design iteration
   design_iteration     C1: whole iterations of pcramp's main loop (candidates, index maintenance, optimize, screens, accept,
                        splits) through pcramp_gpu_design_iteration, next to the stock program
-  large_genomes        C4 shape: 5 Mb genomes -- index build time / bytes, one batch per step on the indexed scan
+  large_genomes        C4: 1000 x 5 Mb genomes (5 x 10^9 positions: the text index in parts of < 2^31 positions) -- index build time /
+                       bytes, one batch per step on the indexed scan
 
 Only bench.py imports this module; the reference is loaded as the checker / CPU arm only (tests.harness.RefLib)."""
 import os
@@ -348,7 +349,7 @@ def design_leg(a, device):
 
 # ---------------------------------------------------------------------------------------------------------------------
 def large_genome_leg(a, device):
-    """C4 shape: a.c4_targets x 5 Mb genomes at 1 %"""
+    """C4: a.c4_targets x 5 Mb genomes at 1 % (the default 1000 is BASELINE config 4's target set)"""
     from pcramp_b200 import TARGET, PcrampGpu, synth
     from pcramp_b200.api import unpack_bits
     n, L, P = a.c4_targets, a.c4_length, a.pairs
@@ -395,7 +396,7 @@ def large_genome_leg(a, device):
         stream_bytes = 16.0 * last["n_index_entries"]
         kern_ms = acc["ms_index_kernel"] / k
         out = {
-            "config": "C4 shape: %d x %d nt genomes at 1 %%, %d pairs per step, thresholds 1.0 x 0.9; step = seed scan + pair scoring, pairs and "
+            "config": "C4 targets: %d x %d nt genomes at 1 %%, %d pairs per step, thresholds 1.0 x 0.9; step = seed scan + pair scoring, pairs and "
                       "results resident" % (n, L, P),
             "metric": "primer_pair_x_target_evaluations_per_s", "value": P * n / mean_s, "unit": EVAL_UNIT, "ms_per_step": mean_s * 1e3,
             "ms_per_step_best": best_s * 1e3, "positions": int(last["n_positions"]), "positions_x_patterns_per_s": float(last["n_positions"]) * last["n_patterns"] / mean_s,
