@@ -1081,7 +1081,8 @@ def run_b200(a):
             "sw_gcups_e2e": None if legs["sw_gcups"] is None else legs["sw_gcups"]["e2e"]["value"],
             "configs": {k: {"value": v["value"], "unit": v["unit"], "ms": v.get("ms_per_step", v.get("ms_per_iteration")),
                             "cpu": None if not v.get("cpu_baseline") else v["cpu_baseline"]["value"],
-                            "parity": None if not v.get("parity") else v["parity"]["ok"]} for k, v in cfg.items()},
+                            "parity": None if not v.get("parity") else v["parity"]["ok"],
+                            "roofline_frac": (v.get("roofline") or {}).get("frac")} for k, v in cfg.items()},
             "target_sharded_evals_per_s": None if tsh is None else tsh["value"],
             "target_sharded_ms_per_step": None if tsh is None else tsh["ms_per_step"],
             "timed_seconds": ms_resident * reps_resident * 1e-3}
