@@ -286,9 +286,10 @@ def _write_fasta(path, coll, prefix):
 
 def design_leg(a, device):
     """C1: whole design iterations (--seed 42 --count 3 --trial 1000), index maintenance included"""
-    from pcramp_b200 import TARGET, PcrampGpu
+    from pcramp_b200 import TARGET, PcrampGpu, synth
     from pcramp_b200.api import DesignLoop
     tg = _c1_targets()
+    assays = []
     streams = max(1, min(64, os.cpu_count() or 1))
     runs = {}
     for label, n_streams in (("thread_1", 1), ("threads_%d" % streams, streams), ("threads_1000", 1000)):
@@ -302,6 +303,9 @@ def design_leg(a, device):
                 t0 = time.perf_counter()
                 for _ in range(3):
                     res = loop.iteration()
+                    if label == "thread_1":
+                        assays.append((synth.words_to_strings(np.array([[res.f[0], res.f[1]]], np.uint64))[0],
+                                       synth.words_to_strings(np.array([[res.r[0], res.r[1]]], np.uint64))[0], float(res.target_coverage)))
                     its.append({"ms_total": res.ms_total, "ms_candidates": res.ms_candidates, "ms_index_and_database": res.ms_select_target + res.ms_select_background,
                                 "ms_optimize": res.ms_optimize, "ms_screen": res.ms_screen, "ms_accept_and_splits": res.ms_accept,
                                 "found": int(res.found), "target_coverage": float(res.target_coverage), "targets_remaining": int(res.targets_remaining),
@@ -328,7 +332,22 @@ def design_leg(a, device):
                 "run on this host (cpu_baseline)" % streams,
         "roofline": {"kernel": "random_assay_kernel (candidates) + the headline's kernels", "bound": "latency", "achieved": None, "peak": None, "unit": None,
                      "frac": None, "traffic": None, "note": "C1 is 10^6 bases: every stage is launch- / latency-bound at this size"},
-        "cpu_baseline": None}
+        "cpu_baseline": None, "parity": None}
+    # the --thread 1 run is BASELINE config 1 as the stock program ran it for tests/golden/design_c1_seed42_count3.txt: same assays?
+    gold = os.path.join(ROOT, "tests", "golden", "design_c1_seed42_count3.txt")
+    if os.path.exists(gold):
+        want = []
+        cover = []
+        with open(gold) as fh:
+            for line in fh:
+                if line.startswith("ASSAY"):
+                    want.append(tuple(line.split("\t")[1:3]))
+                elif line.startswith("# Assay") and "target coverage score = " in line:
+                    cover.append(float(line.split("target coverage score = ")[1].split()[0]))
+        got = [(a.upper(), b.upper()) for a, b, _ in assays]      # a re-used oligo is written in lower case in the report
+        out["parity"] = {"ok": bool(got == [(a.upper(), b.upper()) for a, b in want] and [c for _, _, c in assays] == cover[:len(assays)]),
+                         "assays_compared": len(want), "checker": "golden report of the stock program (tests/golden/make_design_golden.py)",
+                         "assays": ["%s / %s" % (a, b) for a, b in got]}
     stock = os.path.join(ROOT, "oracle", "_ref", "pcramp")
     if os.path.exists(stock) and not a.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as d:
