@@ -430,6 +430,12 @@ def large_genome_leg(a, device):
                                  "nibbles = %.0f MB) over the same time is %.3f of peak" % (
                                      sum((int(x) + 1) // 2 for x in coll.length) / 1e6,
                                      (sum((int(x) + 1) // 2 for x in coll.length) / (kern_ms * 1e-3) / 1e9 / hbm_peak) if kern_ms > 0 else 0.0)},
+            "whole_step_on_8d_bytes": {
+                "algorithmic_bytes": float(sum((int(x) + 1) // 2 for x in coll.length)) + 16.0 * 2 * P + 28.0 * float(last["n_entries"]),
+                "GB_per_s": (float(sum((int(x) + 1) // 2 for x in coll.length)) + 16.0 * 2 * P + 28.0 * float(last["n_entries"])) / mean_s / 1e9,
+                "frac_of_hbm_peak": (float(sum((int(x) + 1) // 2 for x in coll.length)) + 16.0 * 2 * P + 28.0 * float(last["n_entries"])) / mean_s / 1e9 / hbm_peak,
+                "note": "SURVEY.md 8d: nibbles of the active targets + 16 B per candidate + 28 B per database entry, over the WHOLE step (seed scan, "
+                        "database, pair scoring)"},
             "host_generation_s": gen_s, "cpu_baseline": None, "parity": None}
         ref = _ref()
         if ref is not None and not a.no_cpu_baseline:
