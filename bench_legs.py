@@ -11,6 +11,7 @@ sample with a bit-for-bit comparison of that sample:
   optimize_moves       C1: optimize() with all six moves on the trials of one design iteration
   design_iteration     C1: whole iterations of pcramp's main loop (candidates, index maintenance, optimize, screens, accept,
                        splits) through pcramp_gpu_design_iteration, next to the stock program
+  design_c2            C2: whole design iterations with backgrounds at config 2's size, next to the stock program on a sample of the trials
   large_genomes        C4: 1000 x 5 Mb genomes (5 x 10^9 positions: the text index in parts of < 2^31 positions) -- index build time /
                        bytes, one batch per step on the indexed scan
 
@@ -364,6 +365,74 @@ def design_leg(a, device):
                                    "seconds": per[str(streams)][0], "seconds_thread_1": per["1"][0],
                                    "sample": "the stock program (oracle/_ref/pcramp) on the same FASTA, --count 3, wall clock of the whole run "
                                              "(reading 1 MB of FASTA included) / 3"}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def design_c2_leg(a, device):
+    """C2: whole design iterations with backgrounds -- 10 000 x 5 kb targets at 2 %, 1 000 x 5 kb backgrounds from a sister ancestor 10 % away"""
+    from pcramp_b200 import BACKGROUND, MULTIPLEX, TARGET, PcrampGpu, synth
+    from pcramp_b200.api import DesignLoop
+    tg = synth.TargetFactory(2, 10000, 5000, n_clades=1, between=0.0, within=0.02).collection()
+    bg = synth.TargetFactory(2, 1000, 5000, n_clades=1, between=0.10, within=0.02).collection()
+    g = PcrampGpu(device)
+    its = []
+    try:
+        g.upload_sequences(TARGET, tg.nibbles, tg.byte_off, tg.length)
+        g.upload_sequences(BACKGROUND, bg.nibbles, bg.byte_off, bg.length)
+        g.upload_sequences(MULTIPLEX, np.zeros(16, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32))
+        g.multiplex_keys()
+        g.set_pool(np.zeros((0, 2), np.uint64), np.zeros((0, 2), np.uint64))
+        loop = DesignLoop(g, 42, num_trial=1000, n_streams=1000)
+        try:
+            t0 = time.perf_counter()
+            for _ in range(4):
+                res = loop.iteration()
+                its.append({"ms_total": res.ms_total, "ms_candidates": res.ms_candidates, "ms_background_database": res.ms_select_background,
+                            "ms_target_database": res.ms_select_target, "ms_optimize": res.ms_optimize, "ms_screen": res.ms_screen,
+                            "ms_accept_and_splits": res.ms_accept, "found": int(res.found), "target_coverage": float(res.target_coverage),
+                            "background_coverage": float(res.background_coverage), "targets_remaining": int(res.targets_remaining),
+                            "splits": int(res.n_splits), "target_entries": int(res.n_target_entries), "background_entries": int(res.n_background_entries)})
+                if not res.found:
+                    break
+            wall = time.perf_counter() - t0
+        finally:
+            loop.close()
+    finally:
+        g.close()
+    ms = wall * 1e3 / max(1, len(its))
+    out = {
+        "config": "C2 design run: 10 000 x 5 000 nt targets at 2 %, 1 000 x 5 000 nt backgrounds (sister clade 10 % away), --seed 42 --trial 1000, "
+                  "one seed stream per trial; step = one pcramp_gpu_design_iteration (candidates, background and target word databases, optimize, "
+                  "screens incl. find_background_match, accept + splits)",
+        "metric": "design_iterations_per_s", "value": 1e3 / ms, "unit": "iterations/s", "ms_per_iteration": ms,
+        "ms_fastest_iteration": min(i["ms_total"] for i in its), "iterations": its,
+        "roofline": {"kernel": "scan_full_kernel (background database) + score kernels on 1.8 x 10^7 database entries", "bound": "integer issue / latency",
+                     "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                     "note": "see configs.background_scan for the brute-force scan's roofline"},
+        "cpu_baseline": None, "parity": None}
+    stock = os.path.join(ROOT, "oracle", "_ref", "pcramp")
+    if os.path.exists(stock) and not a.no_cpu_baseline:
+        threads = max(1, os.cpu_count() or 1)
+        trials = 50
+        with tempfile.TemporaryDirectory() as d:
+            ft, fb = os.path.join(d, "t.fa"), os.path.join(d, "b.fa")
+            _write_fasta(ft, tg, "t")
+            _write_fasta(fb, bg, "b")
+            t0 = time.perf_counter()
+            try:
+                p = subprocess.run([stock, "-t", ft, "-b", fb, "--thread", str(threads), "--seed", "42", "--count", "1", "--trial", str(trials),
+                                    "-o", os.path.join(d, "o.txt"), "-v", "silent"], stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL, timeout=240)
+                dt = time.perf_counter() - t0
+                if p.returncode == 0:
+                    scale = 1000.0 / trials
+                    out["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": "iterations/s", "cores": threads, "kind": "reference", "seconds": dt,
+                                           "sample": "the stock program (oracle/_ref/pcramp) on the same FASTA files, ONE iteration of %d trials instead "
+                                                     "of 1000 (%.1f s incl. reading 55 MB of FASTA), scaled x %.0f: its word-database loops are candidates x "
+                                                     "words (select_words.cpp:93-117)" % (trials, dt, scale)}
+            except subprocess.TimeoutExpired:
+                out["cpu_baseline"] = {"value": None, "unit": "iterations/s", "cores": threads, "kind": "reference",
+                                       "sample": "the stock program did not finish one iteration of %d trials in 240 s" % trials}
     return out
 
 
