@@ -1071,23 +1071,30 @@ def run_b200(a):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_at_bench": parity}
         line.update(legs)
         # the driver keeps the last ~1500 characters of the line: the facts a reader needs first go last
+        def sig(x, n=4):
+            """n significant digits: the tail of the line has to hold the whole summary"""
+            if x is None or isinstance(x, (bool, str)):
+                return x
+            return float("%.*g" % (n, float(x)))
+
+        # the legs first, the headline LAST: what the driver keeps of a long line is its tail
         line["summary"] = {
-            "value": value, "e2e": e2e_value, "ms_per_step": ms_resident / a.steps, "ms_one_batch_at_a_time": ms_sequential / a.steps,
-            "launches_per_step": launches_resident / max(1, a.steps), "roofline_frac": roofline["frac"], "roofline_kernel": roofline["kernel"],
-            "index_build_ms": index_info["ms_build"], "index_gb": index_info["bytes"] / 1e9,
-            "parity_at_bench": None if parity is None else parity["ok"],
-            "cpu_reference_evals_per_s": None if cpu_baseline is None else cpu_baseline["value"],
-            "dp_gcups": None if dp is None else dp["value"], "dp_gcups_e2e": None if dp is None else dp["e2e"]["value"],
-            "dp_gcups_e2e_words": None if dp is None else dp["e2e_words"]["value"],
-            "sw_gcups": None if legs["sw_gcups"] is None else legs["sw_gcups"]["value"],
-            "sw_gcups_e2e": None if legs["sw_gcups"] is None else legs["sw_gcups"]["e2e"]["value"],
-            "configs": {k: {"value": v["value"], "unit": v["unit"], "ms": v.get("ms_per_step", v.get("ms_per_iteration")),
-                            "cpu": None if not v.get("cpu_baseline") else v["cpu_baseline"]["value"],
+            "configs": {k: {"value": sig(v["value"]), "unit": v["unit"], "ms": sig(v.get("ms_per_step", v.get("ms_per_iteration"))),
+                            "cpu": None if not v.get("cpu_baseline") else sig(v["cpu_baseline"]["value"]),
                             "parity": None if not v.get("parity") else v["parity"]["ok"],
-                            "roofline_frac": (v.get("roofline") or {}).get("frac")} for k, v in cfg.items()},
-            "target_sharded_evals_per_s": None if tsh is None else tsh["value"],
-            "target_sharded_ms_per_step": None if tsh is None else tsh["ms_per_step"],
-            "timed_seconds": ms_resident * reps_resident * 1e-3}
+                            "frac": sig((v.get("roofline") or {}).get("frac"))} for k, v in cfg.items()},
+            "index_build_ms": sig(index_info["ms_build"]), "index_gb": sig(index_info["bytes"] / 1e9),
+            "dp_gcups": None if dp is None else sig(dp["value"]), "dp_gcups_e2e": None if dp is None else sig(dp["e2e"]["value"]),
+            "dp_gcups_e2e_words": None if dp is None else sig(dp["e2e_words"]["value"]),
+            "sw_gcups": None if legs["sw_gcups"] is None else sig(legs["sw_gcups"]["value"]),
+            "sw_gcups_e2e": None if legs["sw_gcups"] is None else sig(legs["sw_gcups"]["e2e"]["value"]),
+            "target_sharded_evals_per_s": None if tsh is None else sig(tsh["value"]),
+            "target_sharded_ms_per_step": None if tsh is None else sig(tsh["ms_per_step"]),
+            "cpu_reference_evals_per_s": None if cpu_baseline is None else sig(cpu_baseline["value"]),
+            "parity_at_bench": None if parity is None else parity["ok"],
+            "launches_per_step": launches_resident / max(1, a.steps), "ms_one_batch_at_a_time": sig(ms_sequential / a.steps),
+            "roofline_kernel": roofline["kernel"], "roofline_frac": sig(roofline["frac"]),
+            "ms_per_step": sig(ms_resident / a.steps), "e2e": sig(e2e_value, 5), "value": sig(value, 5)}
         print(json.dumps(line))
     # teardown order matters: torch tensors that were used on the library's stream must die before the stream does
     sys.stdout.flush()
