@@ -159,7 +159,9 @@ PCR_HD Result align_score(const Query &q, const Target &t)
 }
 
 // With start coordinates (operands of at most 32 bases: Word against Word).  Every state is ONE 32-bit word
-//   [31:16] score   [13:12] state (M = 3, Iq = 1, It = 0: re-labelling a maximum is one OR / AND)   [11:6] 63 - start_i   [5:0] 63 - start_j
+//   [31:22] score   [21:16] row + 1   [13:12] state (M = 3, Iq = 1, It = 0: re-labelling a maximum is one OR / AND)   [11:6] 63 - start_i   [5:0] 63 - start_j
+// (the words that meet in a maximum belong to the same row, so the row field never decides there; it rides along -- the constants that
+// move a word one row down add 1 to it -- so that the winner, the largest (score, row) and among equals the latest, is one compare)
 // and the reference's propagation rules (:457-512) are what a plain signed maximum of such words does:
 //   * M takes the start of M when M is not beaten, else of Iq when Iq >= It, else of It: ties on the score fall to the
 //     larger state code;
@@ -171,8 +173,11 @@ PCR_HD Result align_score(const Query &q, const Target &t)
 //   * the fresh start (i, j) is taken when the incoming maximum is negative (`0 > amax` strictly, :502-512): a path
 //     that comes in with score 0 started at some i' < i, so its inverted start field is larger than the fresh one and a
 //     maximum against the word (0, M, i, j) keeps it.  The borders carry score 0 with the start the fresh rule would give.
-constexpr int SWP_ONE = 1 << 16, SWP_STATE_M = 3 << 12, SWP_STATE_IQ = 1 << 12;
-PCR_HD int swp_pack(int score, int state, int si, int sj) { return score * SWP_ONE + state + ((63 - si) << 6) + (63 - sj); }
+constexpr int SWP_ONE = 1 << 22, SWP_ROW = 1 << 16, SWP_STATE_M = 3 << 12, SWP_STATE_IQ = 1 << 12;
+PCR_HD int swp_pack(int score, int row_field, int state, int si, int sj)
+{
+	return score * SWP_ONE + row_field * SWP_ROW + state + ((63 - si) << 6) + (63 - sj);
+}
 
 template <int ROWS, class Target>
 PCR_HD Result align_start(const Query &q, const Target &t)
@@ -183,28 +188,29 @@ PCR_HD Result align_start(const Query &q, const Target &t)
 	r.any = false;
 	const int tlen = t.length();
 	int M[ROWS], Iq[ROWS], It[ROWS];
-	const int border_gap = swp_pack(SW_GAP_OPEN, 0, 63, 63), floor_gap = swp_pack(SW_GAP_EXTEND, 0, 63, 63);
+	const int border_gap = swp_pack(SW_GAP_OPEN, 0, 0, 63, 63), floor_gap = swp_pack(SW_GAP_EXTEND, 0, 0, 63, 63);
 #pragma unroll
 	for (int i = 0; i < ROWS; ++i) { // column -1 (:400-408): M = 0 with start (i + 1, 0)
-		M[i] = swp_pack(0, SWP_STATE_M, i + 1, 0);
-		Iq[i] = It[i] = border_gap;
+		M[i] = swp_pack(0, i + 1, SWP_STATE_M, i + 1, 0);
+		Iq[i] = It[i] = border_gap + (i + 1) * SWP_ROW;
 	}
-	int best_key = 0, best_j = -1, best_w = 0;
+	int best_w = 0, best_j = -1; // best_w: the winning M word -- its (score, row) decide, its start is the answer
 	for (int j = 0; j < tlen; ++j) {
 		const uint32_t m = match_mask(q, t.at(j));
-		// the top border (:381-389): M = 0 with start (0, j) on the diagonal side and (0, j + 1) above the column
-		int aM = swp_pack(0, SWP_STATE_M, 0, j), aIq = border_gap, aIt = border_gap;
-		int bM = swp_pack(0, SWP_STATE_M, 0, j + 1), bIt = border_gap;
-		const int fresh0 = swp_pack(0, SWP_STATE_M, 0, j);
+		// the top border (:381-389), row field 0: M = 0 with start (0, j) on the diagonal side and (0, j + 1) above the column
+		int aM = swp_pack(0, 0, SWP_STATE_M, 0, j), aIq = border_gap, aIt = border_gap;
+		int bM = swp_pack(0, 0, SWP_STATE_M, 0, j + 1), bIt = border_gap;
+		const int fresh0 = swp_pack(0, 0, SWP_STATE_M, 0, j);
 #pragma unroll
 		for (int i = 0; i < ROWS; ++i) {
 			const int cM = M[i], cIq = Iq[i], cIt = It[i];
-			const int in = max3i(aM, aIq, aIt) | SWP_STATE_M;
-			const int xM = max(in, fresh0 - (i << 6)) + (((m >> i) & 1u) ? SW_MATCH * SWP_ONE : SW_MISMATCH * SWP_ONE);
-			const int xIq = (addmaxi(cM, SW_GAP_OPEN * SWP_ONE, addmaxi(cIq, SW_GAP_EXTEND * SWP_ONE, floor_gap)) & ~(SWP_STATE_M ^ SWP_STATE_IQ));
-			const int xIt = addmaxi(bM, SW_GAP_OPEN * SWP_ONE, addmaxi(bIt, SW_GAP_EXTEND * SWP_ONE, floor_gap)) & ~SWP_STATE_M;
-			const int key = (xM >> 16) * 64 + i;
-			if (key >= best_key) { best_key = key; best_j = j; best_w = xM; }
+			const int in = max3i(aM, aIq, aIt) | SWP_STATE_M; // row field i (the cell above-left), as the fresh word's
+			const int xM = max(in, fresh0 + i * SWP_ROW - (i << 6)) +
+			               (((m >> i) & 1u) ? SW_MATCH * SWP_ONE + SWP_ROW : SW_MISMATCH * SWP_ONE + SWP_ROW);
+			const int floor_i = floor_gap + (i + 1) * SWP_ROW;
+			const int xIq = (addmaxi(cM, SW_GAP_OPEN * SWP_ONE, addmaxi(cIq, SW_GAP_EXTEND * SWP_ONE, floor_i)) & ~(SWP_STATE_M ^ SWP_STATE_IQ));
+			const int xIt = addmaxi(bM, SW_GAP_OPEN * SWP_ONE + SWP_ROW, addmaxi(bIt, SW_GAP_EXTEND * SWP_ONE + SWP_ROW, floor_i)) & ~SWP_STATE_M;
+			if ((xM | (SWP_ROW - 1)) >= best_w) { best_w = xM; best_j = j; } // (score, row) not smaller: a later cell replaces
 			aM = cM; aIq = cIq; aIt = cIt;
 			bM = xM; bIt = xIt;
 			M[i] = xM; Iq[i] = xIq; It[i] = xIt;
@@ -212,8 +218,8 @@ PCR_HD Result align_start(const Query &q, const Target &t)
 	}
 	if (best_j >= 0) {
 		r.any = true;
-		r.score = best_key >> 6;
-		r.q_stop = best_key & 63;
+		r.score = best_w >> 22;
+		r.q_stop = ((best_w >> 16) & 63) - 1;
 		r.t_stop = best_j;
 		r.q_start = 63 - ((best_w >> 6) & 63);
 		r.t_start = 63 - (best_w & 63);
