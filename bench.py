@@ -9,9 +9,10 @@ batches of --pairs (the reference's num_trial, default 1000) against --targets x
 targets (20 clades, 15 % between / 5 % within).  One step = one batch through the
 whole hot path: seed scan (Sequence::pack + select_words over every active target, sort, keys) and pair scoring
 (collect_candidates, identity, coverage, amplified-target bitsets).  One evaluation = one (pair, target)
-decision.  With N > 1 the targets are sharded over the ranks (strong scaling: the collection is fixed),
-every rank scores the same batch on its shard, and NCCL all-gathers the shard bitsets, which are spliced
-into global bitsets + coverages on every rank (include/pcramp_gpu.h: pcramp_gpu_merge_shards).
+decision.  With N > 1 (one rank per GPU under torchrun) the sweep is sharded by PAIRS -- every GPU holds every target and scores its own
+batches, nothing is exchanged on the data path ("scaling": "weak") -- and the target-sharded arrangement (every GPU scores the same batch
+on its shard of the targets, the shards' bitsets merged by peer stores over NVLink, xchg.cuh) is measured beside it (`target_sharded`).
+At N = 1 the line also carries one leg per other BASELINE configuration (bench_legs.py) and the DP / Smith-Waterman / ingest legs.
 
 Prints ONE JSON line (rank 0).
 """

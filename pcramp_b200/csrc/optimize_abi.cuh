@@ -309,6 +309,7 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 		if (pcramp_gpu_score_variants(ctx, PCRAMP_TARGET, pf.data(), pr.data(), pf.data(), pr.data(), na, t_search, o->target_threshold,
 				o->target_amplicon_min, o->target_amplicon_max, o->use_taq_mama, cov_t.data(), nullptr)) return 1;
 		launches += ctx->stats.kernel_launches;
+		lap(7);
 		if (have_bg) {
 			if (pcramp_gpu_score_variants(ctx, PCRAMP_BACKGROUND, pf.data(), pr.data(), pf.data(), pr.data(), na, b_search, o->background_threshold,
 					o->background_amplicon_min, o->background_amplicon_max, o->use_taq_mama, cov_b.data(), nullptr)) return 1;
@@ -589,9 +590,9 @@ extern "C" int pcramp_gpu_optimize(pcramp_gpu_ctx *ctx, uint64_t *f, uint64_t *r
 	}
 	if (trace_on)
 		fprintf(stderr, "[trace] optimize: %u rounds, %llu variants, %llu duplex + %llu hairpin problems, %llu variants scored; ms: score current %.1f, "
-			"variants + expansions %.1f, duplex Tm %.1f, hairpin replay %.1f, hairpin Tm %.1f, score variants %.1f, selection %.1f\n", rounds,
-			(unsigned long long)tr_vars, (unsigned long long)tr_exp, (unsigned long long)tr_hp, (unsigned long long)tr_scored, tr_acc[0], tr_acc[1],
-			tr_acc[2], tr_acc[3], tr_acc[4], tr_acc[5], tr_acc[6]);
+			"variants + expansions %.1f, duplex Tm %.1f, hairpin replay %.1f, hairpin Tm %.1f, score variants %.1f, selection %.1f (of score current: targets %.1f)\n", rounds,
+			(unsigned long long)tr_vars, (unsigned long long)tr_exp, (unsigned long long)tr_hp, (unsigned long long)tr_scored, tr_acc[0] + tr_acc[7], tr_acc[1],
+			tr_acc[2], tr_acc[3], tr_acc[4], tr_acc[5], tr_acc[6], tr_acc[7]);
 	for (uint32_t t = 0; t < n; ++t) {
 		f[2 * t] = bf[t].hi; f[2 * t + 1] = bf[t].lo;
 		r[2 * t] = br[t].hi; r[2 * t + 1] = br[t].lo;
