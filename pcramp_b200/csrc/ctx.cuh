@@ -27,6 +27,19 @@ int thermo_run_codes(pcramp_gpu_ctx *ctx, int op, uint32_t n, const uint8_t *cod
 
 namespace pcr {
 
+// device allocation bookkeeping for the stage trace (PCRAMP_TRACE): calls and host milliseconds spent in cudaMalloc / cudaFree
+struct AllocTrace {
+	static std::atomic<uint64_t> &calls() { static std::atomic<uint64_t> v{0}; return v; }
+	static std::atomic<uint64_t> &micros() { static std::atomic<uint64_t> v{0}; return v; }
+	static bool on() { static const bool v = getenv("PCRAMP_TRACE") != nullptr; return v; }
+	static uint64_t now_us()
+	{
+		struct timespec ts;
+		clock_gettime(CLOCK_MONOTONIC, &ts);
+		return (uint64_t)ts.tv_sec * 1000000ull + (uint64_t)ts.tv_nsec / 1000ull;
+	}
+};
+
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
@@ -37,7 +50,11 @@ struct DevBuf {
 	~DevBuf() { release(); }
 	void release()
 	{
-		if (p && owned) cudaFree(p);
+		if (p && owned) {
+			const uint64_t t0 = AllocTrace::on() ? AllocTrace::now_us() : 0;
+			cudaFree(p);
+			if (AllocTrace::on()) { AllocTrace::calls()++; AllocTrace::micros() += AllocTrace::now_us() - t0; }
+		}
 		p = nullptr;
 		cap = 0;
 		owned = true;
@@ -54,7 +71,9 @@ struct DevBuf {
 		if (bytes <= cap) return cudaSuccess;
 		release();
 		size_t want = bytes + bytes / 4 + 256;
+		const uint64_t t0 = AllocTrace::on() ? AllocTrace::now_us() : 0;
 		cudaError_t e = cudaMalloc(&p, want);
+		if (AllocTrace::on()) { AllocTrace::calls()++; AllocTrace::micros() += AllocTrace::now_us() - t0; }
 		if (e != cudaSuccess) { p = nullptr; return e; }
 		cap = want;
 		return cudaSuccess;

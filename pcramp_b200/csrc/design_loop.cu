@@ -396,6 +396,9 @@ int pcramp_gpu_design_iteration(pcramp_gpu_design *d, pcramp_gpu_design_result *
 	d->pool_background.push_back(d->background_match);
 	res->found = 1;
 	lap(res->ms_accept);
+	if (pcr::AllocTrace::on())
+		fprintf(stderr, "[trace] design iteration %u: %llu cudaMalloc / cudaFree calls so far, %.1f ms in them\n", res->iteration,
+			(unsigned long long)pcr::AllocTrace::calls().load(), pcr::AllocTrace::micros().load() * 1e-3);
 	res->ms_total = (float)(now_ms() - t_start);
 	return 0;
 }
