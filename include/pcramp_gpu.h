@@ -506,7 +506,9 @@ int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
  * "use_neighbours" = 0 makes pair scoring find the oligos of a database word by that table walk instead of through the
  * neighbour list of the candidate that produced the word (score.cuh); "use_entry_score" = 0 goes back from the entry-driven scoring
  * kernel (one thread per plus-strand entry looks for the partner among the minus-strand entries in amplicon range) to the
- * (sequence, strand, oligo) bit rows + work list + one warp per item; "use_async_scan" = 1 makes the indexed scan keep a ring of chunks in flight in shared memory
+ * (sequence, strand, oligo) bit rows + work list + one warp per item; "use_unit_score" = 0 sends pair scoring at thresholds where neither the neighbour bound nor a
+ * seed table excludes anybody (search below ~0.82: the background thresholds) through the key-matrix path instead of one thread per (sequence, pair)
+ * unit over the membership lists (sw_abi.cuh); "use_async_scan" = 1 makes the indexed scan keep a ring of chunks in flight in shared memory
  * through cp.async (scan_index_async_kernel, measured slower) instead of holding the entries of one range in registers (scan_index_kernel); "use_background_units" = 0 makes pcramp_gpu_background_match write
  * down every candidate amplicon and align four times per amplicon instead of aligning once per (pair, matching database entry) and
  * walking the (plus, minus) combinations of every (sequence, pair) in the reference's order (sw_abi.cuh); "use_variant_groups" = 0 scores the variants of pcramp_gpu_score_variants one

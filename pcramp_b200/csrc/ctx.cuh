@@ -11,6 +11,7 @@
 #include <memory>
 #include <string>
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 struct pcramp_gpu_ctx;
@@ -40,6 +41,61 @@ struct AllocTrace {
 	}
 };
 
+// A process-wide cache of released device blocks.  cudaMalloc / cudaFree are not cheap and not steady: under the stage trace single
+// calls of 100-400 ms show up now and then (a 1 MB buffer in pcramp_gpu_multiplex_keys: 380 ms), which is several design iterations.
+// Per-call scratch (candidate lists, sort buffers, bit rows) is therefore handed back here and re-used by the next request of a
+// similar size; blocks above 1 GB (index build scratch) and whatever would push the cache past 8 GB go back to the driver, and a
+// failed cudaMalloc empties the cache and tries again.  A release synchronises the device first, as cudaFree does, so a block never
+// changes hands under a kernel that still reads it.  PCRAMP_NO_ALLOC_CACHE=1 switches the cache off.
+struct AllocCache {
+	struct Block {
+		void *p;
+		size_t cap;
+		int dev;
+	};
+	static constexpr size_t MAX_BLOCK = 1ull << 30, MAX_TOTAL = 8ull << 30;
+	static std::mutex &mu() { static std::mutex m; return m; }
+	static std::vector<Block> &blocks() { static std::vector<Block> *v = new std::vector<Block>(); return *v; } // never destroyed: no CUDA call at exit
+	static size_t &bytes() { static size_t b = 0; return b; }
+	static bool enabled() { static const bool v = getenv("PCRAMP_NO_ALLOC_CACHE") == nullptr; return v; }
+	static void *take(size_t want, size_t &cap_out)
+	{
+		if (!enabled()) return nullptr;
+		int dev = 0;
+		cudaGetDevice(&dev);
+		std::lock_guard<std::mutex> lock(mu());
+		std::vector<Block> &b = blocks();
+		size_t best = b.size();
+		for (size_t i = 0; i < b.size(); ++i)
+			if (b[i].dev == dev && b[i].cap >= want && b[i].cap <= 2 * want + 65536 && (best == b.size() || b[i].cap < b[best].cap)) best = i;
+		if (best == b.size()) return nullptr;
+		void *p = b[best].p;
+		cap_out = b[best].cap;
+		bytes() -= b[best].cap;
+		b[best] = b.back();
+		b.pop_back();
+		return p;
+	}
+	static bool put(void *p, size_t cap)
+	{
+		if (!enabled() || cap > MAX_BLOCK) return false;
+		int dev = 0;
+		cudaGetDevice(&dev);
+		std::lock_guard<std::mutex> lock(mu());
+		if (bytes() + cap > MAX_TOTAL) return false;
+		blocks().push_back(Block{p, cap, dev});
+		bytes() += cap;
+		return true;
+	}
+	static void flush()
+	{
+		std::lock_guard<std::mutex> lock(mu());
+		for (const Block &k : blocks()) cudaFree(k.p);
+		blocks().clear();
+		bytes() = 0;
+	}
+};
+
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
@@ -52,8 +108,15 @@ struct DevBuf {
 	{
 		if (p && owned) {
 			const uint64_t t0 = AllocTrace::on() ? AllocTrace::now_us() : 0;
-			cudaFree(p);
-			if (AllocTrace::on()) { AllocTrace::calls()++; AllocTrace::micros() += AllocTrace::now_us() - t0; }
+			bool cached = false;
+			if (AllocCache::enabled() && cap <= AllocCache::MAX_BLOCK) {
+				cudaDeviceSynchronize(); // what cudaFree does implicitly: nobody still reads the block
+				cached = AllocCache::put(p, cap);
+			}
+			if (!cached) {
+				cudaFree(p);
+				if (AllocTrace::on()) { AllocTrace::calls()++; AllocTrace::micros() += AllocTrace::now_us() - t0; }
+			}
 		}
 		p = nullptr;
 		cap = 0;
@@ -71,8 +134,19 @@ struct DevBuf {
 		if (bytes <= cap) return cudaSuccess;
 		release();
 		size_t want = bytes + bytes / 4 + 256;
+		size_t got = 0;
+		if (void *q = AllocCache::take(want, got)) {
+			p = q;
+			cap = got;
+			return cudaSuccess;
+		}
 		const uint64_t t0 = AllocTrace::on() ? AllocTrace::now_us() : 0;
 		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) { // out of memory with blocks parked in the cache: give them back and try once more
+			(void)cudaGetLastError();
+			AllocCache::flush();
+			e = cudaMalloc(&p, want);
+		}
 		if (AllocTrace::on()) { AllocTrace::calls()++; AllocTrace::micros() += AllocTrace::now_us() - t0; }
 		if (e != cudaSuccess) { p = nullptr; return e; }
 		cap = want;
@@ -250,6 +324,7 @@ struct pcramp_gpu_ctx {
 	int use_variant_groups = 1;      // option "use_variant_groups"
 	DevBuf bg_cnt4, bg_off4, bg_entry, bg_res, bg_cnt2, bg_off2; // find_background_match by units (sw_abi.cuh)
 	int use_background_units = 1;    // option "use_background_units"
+	int use_unit_score = 1;          // option "use_unit_score": pair scoring by (sequence, pair) units at unselective thresholds
 	int use_async_scan = 0;          // option "use_async_scan" = 1: scan_index_async_kernel instead of scan_index_kernel (measured slower)
 	bool async_scan_ready = false;   // its dynamic shared memory size has been set on this context's device
 	float sw_ms_kernel = 0.0f;

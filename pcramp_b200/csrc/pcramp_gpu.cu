@@ -544,7 +544,8 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	w->use_fst = parent->use_fst; w->force_brute = parent->force_brute; w->use_index = parent->use_index; w->idx_part_cap = parent->idx_part_cap;
 	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
 	w->use_entry_score = parent->use_entry_score; w->use_seg_db = parent->use_seg_db; w->use_fast = parent->use_fast;
-	w->use_async_scan = parent->use_async_scan;
+	w->use_async_scan = parent->use_async_scan; w->use_unit_score = parent->use_unit_score; w->use_background_units = parent->use_background_units;
+	w->use_variant_groups = parent->use_variant_groups;
 	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
 		const SeqSet &p = parent->sets[kind];
 		SeqSet &s = w->sets[kind];
@@ -1922,6 +1923,10 @@ static int fst_build(pcramp_gpu_ctx *ctx, const uint4 *d_planes, const uint32_t 
 
 // K2 launch sequence shared by pair scoring and move-variant scoring.  d_f / d_r: the oligos whose identities are
 // computed; d_bf / d_br (variant scoring only, else null): the base assays whose candidate amplicon lists are used.
+// pair scoring by (sequence, pair) units for thresholds at which the filters exclude nobody (sw_abi.cuh)
+static int score_by_units(pcramp_gpu_ctx *ctx, SeqSet &s, const OligoDev *d_member, const OligoDev *d_oligos, uint32_t n_pairs, float detect_threshold,
+	int amp_min, int amp_max, int taq, uint32_t *d_bits_any, uint32_t *d_bits_pass1, uint32_t n_words);
+
 static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, const uint64_t *d_r, const uint64_t *d_bf, const uint64_t *d_br,
 	uint32_t n_pairs, float search_threshold, float detect_threshold, int amp_min, int amp_max, int taq)
 {
@@ -1973,7 +1978,14 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 			// is every candidate's neighbour, the slots overflow and every entry would be compared with every oligo
 			const bool neigh_selective = search_threshold * search_threshold + search_threshold >= 1.5f;
 			const bool use_neigh = ctx->use_neigh != 0 && neigh_selective && s.n_cand > 0 && (uint64_t)s.n_cand * 2ull * n_pairs <= (1ull << 28);
-			bool use_fst = ctx->use_fst != 0 && !use_neigh;
+			bool units_done = false;
+			if (!neigh_selective) { // nothing to filter with: membership lists per (sequence, pair) and one thread per unit
+				const int rc = score_by_units(ctx, s, d_member, ctx->d_oligos.as<OligoDev>(), n_pairs, detect_threshold, amp_min, amp_max, taq,
+					ctx->d_bits.as<uint32_t>(), ctx->d_bits1.as<uint32_t>(), n_words);
+				if (rc == 1) return 1;
+				units_done = rc == 0;
+			}
+			bool use_fst = ctx->use_fst != 0 && !use_neigh && !units_done;
 			if (use_fst) {
 				CK(ctx->d_fst_planes.ensure((size_t)n_pairs * 2 * 16));
 				CK(ctx->d_fst_thr.ensure((size_t)n_pairs * 2 * 4));
@@ -2007,7 +2019,7 @@ static int score_launch(pcramp_gpu_ctx *ctx, int kind, const uint64_t *d_f, cons
 				chunk_pairs = n_pairs;
 			}
 			if (use_fst || use_neigh) chunk_pairs = std::min(chunk_pairs, chunk_for(2ull * s.n)); // two bit rows per sequence
-			for (uint32_t p0 = (use_neigh && ctx->use_entry_score) ? n_pairs : 0u; p0 < n_pairs; p0 += chunk_pairs) {
+			for (uint32_t p0 = ((use_neigh && ctx->use_entry_score) || units_done) ? n_pairs : 0u; p0 < n_pairs; p0 += chunk_pairs) {
 				const uint32_t pc = std::min<uint32_t>(chunk_pairs, n_pairs - p0), nw = (2u * pc + 31u) / 32u;
 				bool chunk_fst = use_fst;
 				if (use_neigh) {
@@ -2460,6 +2472,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_variant_groups") == 0) { ctx->use_variant_groups = value; return 0; }
 	if (strcmp(name, "use_background_units") == 0) { ctx->use_background_units = value; return 0; }
 	if (strcmp(name, "use_async_scan") == 0) { ctx->use_async_scan = value; return 0; }
+	if (strcmp(name, "use_unit_score") == 0) { ctx->use_unit_score = value; return 0; }
 	if (strcmp(name, "use_segmented_db") == 0) { ctx->use_seg_db = value; return 0; }
 	if (strcmp(name, "use_fast_path") == 0) { ctx->use_fast = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }

@@ -669,6 +669,121 @@ int background_match_units(pcramp_gpu_ctx *ctx, SeqSet &s, const uint64_t *d_f, 
 	return 0;
 }
 
+// Pair scoring by units, for thresholds at which neither the neighbour bound nor a seed table can exclude anybody (the background
+// thresholds: search 0.72, oligos matched at 0.52).  The lists of find_background_match above are exactly collect_candidates'
+// membership -- the plus / minus entries of a sequence that F / R match at thr^2 -- so find_amplicon_match (pcr_assay.cpp:338-441) is
+// one thread per (sequence, pair) walking PF x MR and PR x MF: geometry, split test, the two identities, sqrtf(f * r) >= detect.
+// `member` decides the lists (the unmoved assay in variant mode), `oligos` gives the identities.
+__global__ void __launch_bounds__(128) unit_score_kernel(SeqDev sd, BgLists B, const uint4 *__restrict__ e_planes, const int32_t *__restrict__ e_loc,
+	const OligoDev *__restrict__ member, const OligoDev *__restrict__ oligos, uint32_t n_pairs, float detect, int amp_min, int amp_max, int taq,
+	uint32_t *bits_any, uint32_t *bits_pass1, uint32_t n_words)
+{
+	const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= (uint64_t)sd.n * n_pairs) return;
+	const uint32_t seq = (uint32_t)(u / n_pairs), pair = (uint32_t)(u % n_pairs);
+	uint32_t o[5];
+#pragma unroll
+	for (int l = 0; l < 5; ++l) o[l] = B.off4[4 * u + l];
+	if (o[4] == o[0]) return;
+	const int L = (int)sd.len[seq];
+	bool any = false, first = false;
+	for (uint32_t pass = 0; pass < 2u; ++pass) {
+		// pass 0: F on the plus entry (PF), R on the minus entry (MR); pass 1: R on plus (PR), F on minus (MF) (pcr_assay.cpp:37-59)
+		const uint32_t p0 = pass ? o[1] : o[0], p1 = pass ? o[2] : o[1], m0 = pass ? o[2] : o[3], m1 = pass ? o[3] : o[4];
+		if (p0 == p1 || m0 == m1) continue;
+		const OligoDev Pb = member[2 * pair + pass], Mb = member[2 * pair + (pass ^ 1u)];
+		const OligoDev P = oligos[2 * pair + pass], M = oligos[2 * pair + (pass ^ 1u)];
+		const int p_start = (int)((Pb.packed >> 8) & 255u), p_stop = (int)((Pb.packed >> 16) & 255u);
+		const int m_start = (int)((Mb.packed >> 8) & 255u), m_stop = (int)((Mb.packed >> 16) & 255u);
+		bool found = false;
+		for (uint32_t a = p0; a < p1 && !found; ++a) {
+			const uint32_t ea = B.entry[a];
+			ScoreEntry pe;
+			const uint4 w = __ldg(e_planes + ea);
+			pe.a = w.x; pe.c = w.y; pe.g = w.z; pe.t = w.w;
+			pe.loc = __ldg(e_loc + ea);
+			pe.strand = STRAND_PLUS;
+			const float ident_p = oligo_identity(P, oligo_count(P, pe), pe, taq);
+			const int plus_loc3 = pe.loc + p_stop;
+			for (uint32_t b = m0; b < m1; ++b) {
+				const uint32_t eb = B.entry[b];
+				const int mloc = __ldg(e_loc + eb);
+				if (!(plus_loc3 < mloc - m_stop)) continue; // pcr_assay.cpp:368-371
+				int amp_start = pe.loc + p_start;
+				const int amp_stop = min(mloc - m_start, L - 1);
+				int amp_len = amp_stop - amp_start + 1;
+				if (amp_len < amp_min || amp_len > amp_max) continue; // :383-392
+				if (amp_start < 0) { amp_len += amp_start; amp_start = 0; } // :412-416
+				if (amp_len < 0 || has_split_dev(sd, seq, amp_start, amp_len)) continue; // :418
+				ScoreEntry m2;
+				const uint4 v = __ldg(e_planes + eb);
+				m2.a = v.x; m2.c = v.y; m2.g = v.z; m2.t = v.w;
+				m2.loc = mloc;
+				m2.strand = STRAND_MINUS;
+				const float ident_m = oligo_identity(M, oligo_count(M, m2), m2, taq);
+				if (__fsqrt_rn(__fmul_rn(ident_p, ident_m)) >= detect) { found = true; break; } // :292-294
+			}
+		}
+		if (found) {
+			any = true;
+			if (pass == 0u) first = true;
+		}
+	}
+	if (any) {
+		const uint32_t bit = 1u << (seq & 31u);
+		atomicOr(bits_any + (size_t)pair * n_words + (seq >> 5), bit);
+		if (first) atomicOr(bits_pass1 + (size_t)pair * n_words + (seq >> 5), bit); // {F(+), R(-)}: pass 1
+	}
+}
+
+} // namespace
+
+// -> 0 done (bits_any / bits_pass1 hold the result), 1 error, 2 not applicable
+static int score_by_units(pcramp_gpu_ctx *ctx, SeqSet &s, const OligoDev *d_member, const OligoDev *d_oligos, uint32_t n_pairs, float detect_threshold,
+	int amp_min, int amp_max, int taq, uint32_t *d_bits_any, uint32_t *d_bits_pass1, uint32_t n_words)
+{
+	cudaStream_t st = ctx->stream;
+	const uint64_t U = (uint64_t)s.n * n_pairs;
+	if (!ctx->use_unit_score || U * 4 + 1 >= (1ull << 32)) return 2;
+	const uint32_t n_lists = (uint32_t)(U * 4);
+	DevBuf &d_cnt4 = ctx->bg_cnt4, &d_off4 = ctx->bg_off4, &d_entry = ctx->bg_entry;
+	CK(d_cnt4.ensure(((size_t)n_lists + 1) * 4));
+	CK(d_off4.ensure(((size_t)n_lists + 1) * 4));
+	CK(cudaMemsetAsync(d_cnt4.p, 0, ((size_t)n_lists + 1) * 4, st));
+	const unsigned grid = (unsigned)std::min<uint64_t>(s.n, (uint64_t)ctx->sm_count * 8);
+	bg_match_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+		s.seq_ent_off.as<uint32_t>(), d_member, n_pairs, d_cnt4.as<uint32_t>(), nullptr, nullptr);
+	CK(cudaGetLastError());
+	size_t tb = 0;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt4.as<uint32_t>(), d_off4.as<uint32_t>(), (int)(n_lists + 1), st));
+	CK(ctx->cub_tmp.ensure(tb));
+	tb = ctx->cub_tmp.cap;
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, d_cnt4.as<uint32_t>(), d_off4.as<uint32_t>(), (int)(n_lists + 1), st));
+	CK(ctx->d_item_count.ensure(16));
+	CK(cudaMemsetAsync(ctx->d_item_count.p, 0, 8, st));
+	bg_total_kernel<<<(unsigned)ctx->sm_count * 4u, 256, 0, st>>>(d_cnt4.as<uint32_t>(), n_lists, ctx->d_item_count.as<unsigned long long>());
+	uint32_t n_match = 0;
+	unsigned long long n_match64 = 0;
+	CK(cudaMemcpyAsync(&n_match, d_off4.as<uint32_t>() + n_lists, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&n_match64, ctx->d_item_count.p, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.kernel_launches += 4;
+	if (n_match64 >= (1ull << 32)) return 2; // more list elements than 32-bit offsets hold: the general path
+	if (!n_match) return 0;
+	CK(d_entry.ensure((size_t)n_match * 4));
+	BgLists B;
+	B.off4 = d_off4.as<uint32_t>();
+	B.entry = d_entry.as<uint32_t>();
+	bg_match_kernel<true><<<grid, SCORE_THREADS, 0, st>>>(s.dev(), s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), s.e_strand.as<uint32_t>(),
+		s.seq_ent_off.as<uint32_t>(), d_member, n_pairs, nullptr, d_off4.as<uint32_t>(), d_entry.as<uint32_t>());
+	unit_score_kernel<<<grid_for(U, 128), 128, 0, st>>>(s.dev(), B, s.e_planes.as<uint4>(), s.e_loc.as<int32_t>(), d_member, d_oligos, n_pairs,
+		detect_threshold, amp_min, amp_max, taq, d_bits_any, d_bits_pass1, n_words);
+	CK(cudaGetLastError());
+	ctx->stats.kernel_launches += 2;
+	return 0;
+}
+
+namespace {
 } // namespace
 
 extern "C" {
@@ -741,7 +856,7 @@ int pcramp_gpu_background_match(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f
 	prep_oligos_kernel<<<grid_for(2ull * n_pairs, 256), 256, 0, st>>>(d_f.as<uint64_t>(), d_r.as<uint64_t>(), n_pairs, thr2, d_ol.as<OligoDev>());
 	CK(cudaGetLastError());
 	ctx->stats.kernel_launches++;
-	if (ctx->use_background_units) {
+	if (ctx->use_background_units && (uint64_t)s.n * n_pairs * 4ull + 1ull < (1ull << 32)) { // (more units than 32-bit list offsets hold: the record form)
 		if (background_match_units(ctx, s, d_f.as<uint64_t>(), d_r.as<uint64_t>(), d_ol.as<OligoDev>(), n_pairs, detect_threshold, amp_min, amp_max, taq,
 				d_bits.as<uint32_t>(), n_words, n_amplicons)) return 1;
 		CK(cudaMemcpyAsync(bitsets, d_bits.p, (size_t)n_pairs * n_words * 4, cudaMemcpyDeviceToHost, st));

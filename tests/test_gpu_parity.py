@@ -616,3 +616,27 @@ def test_async_index_scan_equals_register_scan(gpu, name):
     for a, b in zip(out[0][0], out[1][0]):
         assert np.array_equal(a, b)
     assert out[0][1] == out[1][1]
+
+
+@pytest.mark.parametrize("name", ["lowthr", "taq_weights", "repeats"])
+def test_unit_scoring_equals_key_matrix(gpu, name):
+    """pair scoring by (sequence, pair) units (option use_unit_score; thresholds at which the filters exclude nobody) == the key-matrix path"""
+    sc = SCENARIOS[name]()
+    g = GpuChecker(gpu)
+    g.set_sequences(sc.coll, sc.active)
+    for (s, p) in sc.splits:
+        g.split_sequence(s, p)
+    g.select_words(sc.f, sc.r, float(sc.threshold), **sc.select_kwargs())
+    out = []
+    for use in (1, 0):
+        gpu.set_option("use_unit_score", use)
+        try:
+            res = []
+            for search, detect in ((sc.search_threshold, sc.target_threshold), (0.72, 0.8), (0.6, 0.7)):
+                res.append(g.score_pairs(sc.f, sc.r, float(search), float(detect), sc.amp[0], sc.amp[1], sc.taq))
+            out.append(res)
+        finally:
+            gpu.set_option("use_unit_score", 1)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert any(a[1].sum() > 0 for a in out[0])
