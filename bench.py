@@ -65,9 +65,9 @@ def parse_args():
     ap.add_argument("--fasta-targets", type=int, default=8000, help="sequences in the FASTA-ingest leg (0 = skip; rank 0 only)")
     ap.add_argument("--dp-problems", type=int, default=262144, help="NucCruc problems per step of the DP GCUPS leg (0 = skip the leg)")
     ap.add_argument("--dp-cpu-problems", type=int, default=60000, help="problems in the bounded CPU sample of the DP leg")
-    ap.add_argument("--config-legs", default="background,degenerate,optimize,design,design_c2,large",
+    ap.add_argument("--config-legs", default="background,degenerate,optimize,design,design_c2,design_c3,large",
                     help="legs for the other BASELINE configurations (bench_legs.py; rank 0, N = 1): any of background (C2), degenerate (C3), "
-                         "optimize (C1 moves), design (C1 iterations), design_c2 (C2 iterations with backgrounds), large (C4); 'none' skips them")
+                         "optimize (C1 moves), design (C1 iterations), design_c2 (C2 iterations with backgrounds), design_c3 (C3 iterations with -d 16), large (C4); 'none' skips them")
     ap.add_argument("--c4-targets", type=int, default=1000, help="genomes in the large-genome leg (1000 x 5 Mb = BASELINE config 4's targets)")
     ap.add_argument("--c4-length", type=int, default=5000000, help="bases per genome in the large-genome leg")
     return ap.parse_args()
@@ -1040,6 +1040,8 @@ def run_b200(a):
             cfg["design_iteration"] = bench_legs.design_leg(a, local)
         if "design_c2" in want:
             cfg["design_iteration_c2"] = bench_legs.design_c2_leg(a, local)
+        if "design_c3" in want:
+            cfg["design_iteration_c3"] = bench_legs.design_c3_leg(a, coll, local, None if cpu_baseline is None else cpu_baseline["value"])
         if "large" in want:
             cfg["large_genomes"] = bench_legs.large_genome_leg(a, local)
         legs = {

@@ -12,6 +12,7 @@ sample with a bit-for-bit comparison of that sample:
   design_iteration     C1: whole iterations of pcramp's main loop (candidates, index maintenance, optimize, screens, accept,
                        splits) through pcramp_gpu_design_iteration, next to the stock program
   design_c2            C2: whole design iterations with backgrounds at config 2's size, next to the stock program on a sample of the trials
+  design_c3            C3: whole design iterations with -d 16 on the headline's collection
   large_genomes        C4: 1000 x 5 Mb genomes (5 x 10^9 positions: the text index in parts of < 2^31 positions) -- index build time /
                        bytes, one batch per step on the indexed scan
 
@@ -433,6 +434,59 @@ def design_c2_leg(a, device):
             except subprocess.TimeoutExpired:
                 out["cpu_baseline"] = {"value": None, "unit": "iterations/s", "cores": threads, "kind": "reference",
                                        "sample": "the stock program did not finish one iteration of %d trials in 240 s" % trials}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def design_c3_leg(a, coll, device, cpu_evals_per_s):
+    """C3: whole design iterations on the headline's own collection (20 000 x 30 kb in 20 clades) with degenerate primers (-d 16)"""
+    from pcramp_b200 import BACKGROUND, MULTIPLEX, TARGET, PcrampGpu
+    from pcramp_b200.api import DesignLoop
+    g = PcrampGpu(device)
+    its = []
+    try:
+        g.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
+        for kind in (BACKGROUND, MULTIPLEX):
+            g.upload_sequences(kind, np.zeros(16, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32))
+        g.multiplex_keys()
+        g.set_pool(np.zeros((0, 2), np.uint64), np.zeros((0, 2), np.uint64))
+        loop = DesignLoop(g, 42, num_trial=1000, n_streams=1000, degen=16)
+        try:
+            t0 = time.perf_counter()
+            for _ in range(4):
+                res = loop.iteration()
+                its.append({"ms_total": res.ms_total, "ms_candidates": res.ms_candidates, "ms_target_database": res.ms_select_target,
+                            "ms_optimize": res.ms_optimize, "ms_screen": res.ms_screen, "ms_accept_and_splits": res.ms_accept, "found": int(res.found),
+                            "target_coverage": float(res.target_coverage), "targets_remaining": int(res.targets_remaining), "splits": int(res.n_splits),
+                            "target_entries": int(res.n_target_entries)})
+                if not res.found:
+                    break
+            wall = time.perf_counter() - t0
+        finally:
+            loop.close()
+        st = g.stats()
+    finally:
+        g.close()
+    ms = wall * 1e3 / max(1, len(its))
+    out = {
+        "config": "C3 design run: %d x %d nt targets in clades (the headline's collection), -d 16, --seed 42 --trial 1000, one seed stream per trial; "
+                  "step = one pcramp_gpu_design_iteration (candidates, target word database incl. the text index and its upkeep across splits, "
+                  "optimize() with the degeneracy moves, screens, accept + splits)" % (coll.n, int(coll.length[0])),
+        "metric": "design_iterations_per_s", "value": 1e3 / ms, "unit": "iterations/s", "ms_per_iteration": ms,
+        "ms_fastest_iteration": min(i["ms_total"] for i in its), "iterations": its,
+        "index": {"ms_build": float(st["ms_index_build"]), "builds": int(st["n_index_builds"]), "stale_sequences_last_call": int(st["n_index_stale"])},
+        "roofline": {"kernel": "thermo_kernel / score_entries_groups_kernel per move round + host replay of the accept rule", "bound": "latency",
+                     "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                     "note": "optimize() with -d 16 is 12-18 lock-step rounds over ~9 x 10^5 trial oligos: see configs.optimize_moves"},
+        "cpu_baseline": None, "parity": None}
+    if cpu_evals_per_s:
+        evals = 1000.0 * coll.n
+        out["cpu_baseline"] = {"value": cpu_evals_per_s / evals, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "reference",
+                               "seconds": evals / cpu_evals_per_s,
+                               "sample": "LOWER BOUND from this run's reference sample (cpu_baseline of the main line: %.3g (pair, target) evaluations/s "
+                                         "through the reference's select_words + scoring): one iteration's 1000 trials x %d targets need %.0f s for "
+                                         "the word database and first scores alone, before optimize()'s moves" % (cpu_evals_per_s, coll.n,
+                                                                                                                  evals / cpu_evals_per_s)}
     return out
 
 

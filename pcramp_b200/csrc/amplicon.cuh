@@ -287,8 +287,9 @@ int pcramp_gpu_unique_amplicons(pcramp_gpu_ctx *ctx, int kind, const uint64_t *f
 	less.R = R;
 	RegionEq eq;
 	eq.R = R;
-	thrust::sort(thrust::cuda::par.on(st), u, u + n, less); // sort(amplicons) (pcr_assay.cpp:806)
-	uint32_t *e = thrust::unique(thrust::cuda::par.on(st), u, u + n, eq); // :807
+	CachedScratch scratch;
+	thrust::sort(thrust::cuda::par(scratch).on(st), u, u + n, less); // sort(amplicons) (pcr_assay.cpp:806)
+	uint32_t *e = thrust::unique(thrust::cuda::par(scratch).on(st), u, u + n, eq); // :807
 	CK(cudaStreamSynchronize(st));
 	const uint64_t nu = (uint64_t)(e - u);
 	ctx->amp_n_uniq = nu;

@@ -12,6 +12,8 @@
 #include <string>
 #include <atomic>
 #include <mutex>
+#include <new>
+#include <utility>
 #include <vector>
 
 struct pcramp_gpu_ctx;
@@ -153,6 +155,35 @@ struct DevBuf {
 		return cudaSuccess;
 	}
 	template <class T> T *as() const { return (T *)p; }
+};
+
+// scratch allocator for the library algorithms that take one (thrust::cuda::par(alloc)): blocks come from and go back to the cache
+// above instead of one cudaMalloc + cudaFree per call
+struct CachedScratch {
+	typedef char value_type;
+	std::vector<std::pair<char *, size_t>> live;
+	char *allocate(std::ptrdiff_t n)
+	{
+		DevBuf b;
+		if (b.ensure((size_t)std::max<std::ptrdiff_t>(n, 1)) != cudaSuccess) throw std::bad_alloc();
+		char *p = (char *)b.p;
+		live.push_back(std::make_pair(p, b.cap));
+		b.p = nullptr; // ownership moves to `live`
+		b.cap = 0;
+		return p;
+	}
+	void deallocate(char *p, size_t)
+	{
+		for (size_t i = 0; i < live.size(); ++i)
+			if (live[i].first == p) {
+				DevBuf b;
+				b.p = p;
+				b.cap = live[i].second;
+				live[i] = live.back();
+				live.pop_back();
+				return; // b's destructor hands the block to the cache
+			}
+	}
 };
 
 struct SeqSet {

@@ -336,8 +336,9 @@ int pcramp_gpu_multiplex_keys(pcramp_gpu_ctx *ctx, uint32_t pack_max_degen, uint
 		if (n >= (1ull << 32)) return fail(ctx, "pcramp_gpu_multiplex_keys: more than 2^32 words");
 		if (n) {
 			WKey *p = raw.as<WKey>();
-			thrust::sort(thrust::cuda::par.on(st), p, p + n, WKeyLess());
-			WKey *e = thrust::unique(thrust::cuda::par.on(st), p, p + n, WKeyEq());
+			CachedScratch scratch;
+			thrust::sort(thrust::cuda::par(scratch).on(st), p, p + n, WKeyLess());
+			WKey *e = thrust::unique(thrust::cuda::par(scratch).on(st), p, p + n, WKeyEq());
 			CK(cudaStreamSynchronize(st));
 			const uint64_t nk = (uint64_t)(e - p);
 			CK(ctx->mpx_words.ensure(nk * sizeof(WKey)));
