@@ -46,7 +46,7 @@ struct AllocTrace {
 // A process-wide cache of released device blocks.  cudaMalloc / cudaFree are not cheap and not steady: under the stage trace single
 // calls of 100-400 ms show up now and then (a 1 MB buffer in pcramp_gpu_multiplex_keys: 380 ms), which is several design iterations.
 // Per-call scratch (candidate lists, sort buffers, bit rows) is therefore handed back here and re-used by the next request of a
-// similar size; blocks above 1 GB (index build scratch) and whatever would push the cache past 8 GB go back to the driver, and a
+// similar size; blocks above 1 GB (index build scratch) go back to the driver, a full cache (8 GB) gives up its oldest blocks, and a
 // failed cudaMalloc empties the cache and tries again.  A release synchronises the device first, as cudaFree does, so a block never
 // changes hands under a kernel that still reads it.  PCRAMP_NO_ALLOC_CACHE=1 switches the cache off.
 struct AllocCache {
@@ -74,8 +74,7 @@ struct AllocCache {
 		void *p = b[best].p;
 		cap_out = b[best].cap;
 		bytes() -= b[best].cap;
-		b[best] = b.back();
-		b.pop_back();
+		b.erase(b.begin() + (std::ptrdiff_t)best); // keeps the age order put() evicts by
 		return p;
 	}
 	static bool put(void *p, size_t cap)
@@ -84,7 +83,12 @@ struct AllocCache {
 		int dev = 0;
 		cudaGetDevice(&dev);
 		std::lock_guard<std::mutex> lock(mu());
-		if (bytes() + cap > MAX_TOTAL) return false;
+		std::vector<Block> &b = blocks();
+		while (bytes() + cap > MAX_TOTAL && !b.empty()) { // full: the oldest blocks go back to the driver (sizes nobody asked for again)
+			cudaFree(b.front().p);
+			bytes() -= b.front().cap;
+			b.erase(b.begin());
+		}
 		blocks().push_back(Block{p, cap, dev});
 		bytes() += cap;
 		return true;
