@@ -326,12 +326,21 @@ __device__ __forceinline__ void seed_hit(uint32_t en, uint32_t m, uint32_t xpos,
 	}
 	const uint32_t meta = __ldg(g_meta + pid), meta2 = __ldg(g_meta2 + pid);
 	const uint32_t n = (meta2 >> 10) & 63u, pieces = ((meta2 >> 16) & 63u) + 1u;
-	for (uint32_t i = 0; i < pieces; ++i) { // report through the leftmost exactly-matching piece only
+	// Report through the leftmost exactly-matching piece only -- and that piece must be THIS one.  A q = 7 bucket holds two seed
+	// codes, so an entry is also proposed at texts that carry the bucket's other code (base 0 and base 6 of the seed off by one
+	// code bit each).  With a degenerate base 0 (M, K) one of those two is no mismatch at all, the alignment can pass the count, and
+	// it used to be reported here AND through a later exact piece: the same hit twice (deduplicated downstream, but n_hits and the
+	// hit buffers carried it).  An alignment at or above threshold always has an exact piece (pigeonhole), so nothing is lost.
+	for (uint32_t i = 0; i < pieces; ++i) {
 		uint32_t o, pq;
 		seed_piece(n, pieces, i, o, pq);
-		if (o >= off) break;
 		const uint32_t pm = (1u << pq) - 1u;
-		if (((m >> o) & pm) == pm) return;
+		const bool exact = ((m >> o) & pm) == pm;
+		if (o >= off) {
+			if (!exact) return;
+			break;
+		}
+		if (exact) return;
 	}
 	emit_family(hs, seq, clen, cand_bits, meta, meta2, x, (uint32_t)__popc(m));
 }

@@ -597,6 +597,40 @@ def test_degenerate_primers_through_the_index(gpu, oracle):
     assert int(bits_o.sum()) > 0
 
 
+def test_seed_table_reports_a_site_once_when_the_bucket_partner_matches(gpu, oracle):
+    """A 7-base seed bucket holds two codes (base 0 and base 6 off by one code bit each).  Primer CTGAAT MGCGCTC ATTTGGG on the site
+    CTGAAA AGCGCTT ATTTGGG: piece 1's text is the bucket partner of the M = C expansion, M admits the A, and the alignment passes with
+    two mismatches -- the table scan used to report it through piece 1 AND through the exact piece 2 (found by scripts/stress_parity.py:
+    hits 747684 by the table against 747558 through the index, databases identical).  One site, one hit, by both scans."""
+    rng = np.random.default_rng(77)
+    site = [int(synth.CODE["ACGT".index(c)]) for c in "CTGAAAAGCGCTTATTTGGG"]
+    seqs = []
+    for k in range(4):
+        c = synth.CODE[rng.integers(0, 4, 700)].astype(np.uint8)
+        at = 100 + 37 * k
+        c[at:at + 20] = site if k % 2 == 0 else synth.revcomp_codes(site)
+        seqs.append(c)
+    coll = synth.Collection(seqs)
+    f = np.array([synth.word_from_string("CTGAATMGCGCTCATTTGGG")], np.uint64)
+    r = np.array([synth.word_from_codes(seqs[0][400:420])], np.uint64)
+    thr = float(np.float32(1.0) * np.float32(0.9))
+    g = GpuChecker(gpu)
+    g.set_sequences(coll)
+    oracle.set_sequences(coll)
+    no, nko = oracle.select_words(f, r, thr)
+    hits = []
+    for use in (0, 1):
+        gpu.set_option("use_index", use)
+        try:
+            assert g.select_words(f, r, thr) == (no, nko)
+            for a, c in zip(g.db(), oracle.db()):
+                assert np.array_equal(a, c)
+            hits.append(gpu.stats()["n_hits"])
+        finally:
+            gpu.set_option("use_index", 1)
+    assert no >= 5 and hits[0] == hits[1] == no  # four embedded sites + the plain primer's own, each seen by one pattern only
+
+
 @pytest.mark.parametrize("name", ["basic", "degenerate", "splits", "shift"])
 def test_async_index_scan_equals_register_scan(gpu, name):
     """scan_index_async_kernel (a cp.async ring of chunks in shared memory; option use_async_scan) == scan_index_kernel"""
