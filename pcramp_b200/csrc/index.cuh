@@ -227,16 +227,19 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 	uint32_t k = 0, o = 0, si = 0, wo = 0, x = 0, budget = 0, ext_pat = 0, n_combo = 1u, sub_letter = 0u, sub_at = 0xFFFFFFFFu;
 	uint4 seg_m = make_uint4(0u, 0u, 0u, 0u);
 	bool ext_left = false, ext = false;
+	uint64_t okm = 0ull; // extended seeds with x <= 3: bit c = extension code c is within the budget
 	if (p < n_pat) {
-		const uint4 m = mask[p];
 		const uint32_t m2 = meta2[p];
-		if (idx_indexable(m, m2)) {
+		const uint32_t n = (m2 >> 10) & 63u, e = (m2 >> 16) & 63u, segs = idx_segments(e);
+		const uint32_t per = 1u + 3u * IDX_K;
+		const uint32_t j = slot % per;
+		si = slot / per;
+		// (half of a pattern's slots belong to segments it does not have: they leave before the indexability test, which walks
+		// every prefix base; slot 0 always takes it -- it counts the pattern)
+		const uint4 m = (si < segs) ? mask[p] : make_uint4(0u, 0u, 0u, 0u);
+		if (si < segs && idx_indexable(m, m2)) {
 			counts = (slot == 0u);
-			const uint32_t n = (m2 >> 10) & 63u, e = (m2 >> 16) & 63u, segs = idx_segments(e);
-			const uint32_t per = 1u + 3u * IDX_K;
-			const uint32_t j = slot % per;
-			si = slot / per;
-			if (si < segs) {
+			{
 				idx_segment(n, segs, si, o, k);
 				uint32_t sub_pos = 0xFFFFFFFFu, sub_alt = 0u;
 				bool ok = true;
@@ -284,7 +287,14 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 							ext = true;
 							if (ext_left) wo = o - x;
 							n_emit = idx_ext_count(x, budget);
-							if (!ext_left) { // extension in the low digits of the code: runs of consecutive allowed codes are ONE range
+							if (x <= 3u) { // the allowed codes as one 64-bit mask: counted and emitted from its set bits, not by two walks over the codes
+								for (uint32_t c = 0; c < (1u << (2u * x)); ++c) {
+									const uint32_t d = c ^ ext_pat;
+									okm |= (uint64_t)((uint32_t)__popc((d | (d >> 1)) & 0x55u) <= budget ? 1u : 0u) << c;
+								}
+								// extension in the low digits of the code: runs of consecutive allowed codes are ONE range
+								if (!ext_left) n_emit = (uint32_t)__popcll(okm & ~(okm << 1));
+							} else if (!ext_left) {
 								n_emit = 0u;
 								bool prev = false;
 								for (uint32_t c = 0; c < (1u << (2u * x)); ++c) {
@@ -342,6 +352,26 @@ __global__ void index_query_kernel(const uint4 *__restrict__ mask, const uint32_
 				span += qy.hi - qy.lo;
 				if (at < q_cap) queries[at] = qy;
 				++at;
+			} else if (x <= 3u && ext_left) {
+				for (uint64_t rem = okm; rem; rem &= rem - 1ull) {
+					const uint32_t code = ((uint32_t)(__ffsll((long long)rem) - 1) << (2u * k)) | seg_code;
+					qy.lo = __ldg(off + code);
+					qy.hi = __ldg(off + code + 1u);
+					span += qy.hi - qy.lo;
+					if (at < q_cap) queries[at] = qy;
+					++at;
+				}
+			} else if (x <= 3u) {
+				const uint32_t code0 = seg_code << (2u * x);
+				for (uint64_t starts = okm & ~(okm << 1); starts; starts &= starts - 1ull) {
+					const uint32_t s0 = (uint32_t)(__ffsll((long long)starts) - 1);
+					const uint32_t len = (uint32_t)(__ffsll((long long)~(okm >> s0)) - 1); // the run's allowed codes (bit 63 set: >> leaves zeros above)
+					qy.lo = __ldg(off + code0 + s0);
+					qy.hi = __ldg(off + code0 + s0 + len);
+					span += qy.hi - qy.lo;
+					if (at < q_cap) queries[at] = qy;
+					++at;
+				}
 			} else if (ext_left) {
 				for (uint32_t c = 0; c < (1u << (2u * x)); ++c) {
 					const uint32_t d = c ^ ext_pat, bad = (d | (d >> 1)) & 0x55u;
@@ -644,7 +674,10 @@ scan_index_async_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, cons
 }
 
 // place each candidate in its sequence, drop what other kernels own, report once
-__global__ void __launch_bounds__(256)
+#ifndef IDX_HITS_BLOCKS
+#define IDX_HITS_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, IDX_HITS_BLOCKS)
 index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__restrict__ g_meta, const uint32_t *__restrict__ g_meta2,
 	const uint32_t *__restrict__ dirty_bits, const uint8_t *__restrict__ stale, uint32_t cand_bits, HitSink hs)
 {
@@ -661,6 +694,8 @@ index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__res
 			const IdxCand c = cs.buf[i];
 			if (c.gpos != IDX_INVALID) { // (else: the unused tail of a warp's block)
 				const uint32_t wo = c.seg >> 24, si = (c.seg >> 16) & 255u;
+				meta = __ldg(g_meta + c.pid); // independent of the chain of loads that places the candidate: issued beside it
+				meta2 = __ldg(g_meta2 + c.pid);
 				const uint32_t rel = idx_seq_of_fast(ix, ix.n_seq, c.gpos);
 				seq = ix.seq_lo + rel;
 				x = (int64_t)(c.gpos - __ldg(ix.cum + rel)) - (int64_t)wo; // text index of primer base 0
@@ -671,8 +706,6 @@ index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__res
 					if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) ok = false;
 				}
 				if (ok) {
-					meta = __ldg(g_meta + c.pid);
-					meta2 = __ldg(g_meta2 + c.pid);
 					const uint32_t n = (meta2 >> 10) & 63u, segs = idx_segments((meta2 >> 16) & 63u);
 					for (uint32_t k = 0; k < si; ++k) { // an earlier segment whose prefix is within one mismatch reports this alignment
 						uint32_t oo, kk;

@@ -79,5 +79,63 @@ print("index:", outs[0][:3], "indexed patterns", outs[0][5], "| table:", outs[1]
       "bits equal", np.array_equal(outs[0][4], outs[1][4]), flush=True)
 assert outs[0][:3] == outs[1][:3] and np.array_equal(outs[0][3], outs[1][3]) and np.array_equal(outs[0][4], outs[1][4]), "degenerate index vs table"
 print("degenerate primers: %d entries, %d keys, %d hits identical through the index and the table scan, %.1f s" % (outs[0][0], outs[0][1], outs[0][2], time.time() - t0))
+
+# 5'/3' shift families (optimize_5 / optimize_3) with the same degenerate primers: index against table scan
+t0 = time.time()
+outs = []
+for use in (1, 0):
+    g.set_option("use_index", use)
+    ne, nk = g.select_words(TARGET, f[:400], r[:400], thr9, optimize_5=True, optimize_3=True)
+    cov, bits = g.score_pairs(TARGET, f[:400], r[:400], thr9, 1.0)
+    outs.append((ne, nk, g.stats()["n_hits"], cov.copy(), bits.copy()))
+g.set_option("use_index", 1)
+print("families index:", outs[0][:3], "| table:", outs[1][:3], flush=True)
+assert outs[0][:3] == outs[1][:3] and np.array_equal(outs[0][3], outs[1][3]) and np.array_equal(outs[0][4], outs[1][4]), "families index vs table"
+print("shift families: %d entries, %d keys, %d hits identical, %.1f s" % (outs[0][0], outs[0][1], outs[0][2], time.time() - t0), flush=True)
+
+# the index through the design loop's lifecycle at this size: sequences split (some several times), a third switched off and on again;
+# after every stage index == table scan, and the first 150 sequences (all of them split) == the live reference fed the same splits
+t0 = time.time()
+srng = np.random.default_rng(11)
+sub = big.subset(np.arange(150))
+ref.set_sequences(sub)
+gs = PcrampGpu(0)   # the same 150 sequences alone: per-sequence independence (select_words.cpp:131-138) ties it to the big run
+gs.upload_sequences(TARGET, sub.nibbles, sub.byte_off, sub.length)
+for stage in range(3):
+    # stage 0 stays below 1/16 of the text (the split sequences keep their stale index entries and take the table scan), the later
+    # stages go past it (the index is rebuilt)
+    n_own, n_other = ((60, 40), (150, 400), (150, 1500))[stage]
+    seqs = np.concatenate([np.arange(n_own), srng.integers(150, big.n, n_other)]).astype(np.uint32)
+    pos = srng.integers(40, 7900, len(seqs)).astype(np.uint32)
+    g.split_sequences(TARGET, seqs, pos)
+    gs.split_sequences(TARGET, seqs[:n_own], pos[:n_own])
+    for s_, p_ in zip(seqs[:n_own], pos[:n_own]):
+        ref.split_sequence(int(s_), int(p_))
+    active = np.ones(big.n, np.uint8)
+    if stage == 1:
+        active[srng.integers(150, big.n, 600)] = 0
+    g.set_active(TARGET, active)
+    outs = []
+    for use in (1, 0):
+        g.set_option("use_index", use)
+        ne, nk = g.select_words(TARGET, f, r, thr9)
+        st = g.stats()
+        cov, bits = g.score_pairs(TARGET, f, r, thr9, 1.0)
+        outs.append((ne, nk, st["n_hits"], cov.copy(), unpack_bits(bits, big.n), st["n_index_builds"], st["n_index_stale"]))
+    g.set_option("use_index", 1)
+    assert outs[0][:3] == outs[1][:3] and np.array_equal(outs[0][3], outs[1][3]) and np.array_equal(outs[0][4], outs[1][4]), "split lifecycle index vs table"
+    # the reference's coverage is optimize()'s (search 0.9, detect 1.0), its bits find_target_match's (search = detect = 1.0)
+    g.select_words(TARGET, f, r, thr9)
+    bits_big = unpack_bits(g.score_pairs(TARGET, f, r, 1.0, 1.0)[1], big.n)
+    gs.select_words(TARGET, f, r, thr9)
+    cov_s = gs.score_pairs(TARGET, f, r, thr9, 1.0)[0].copy()
+    bits_s = unpack_bits(gs.score_pairs(TARGET, f, r, 1.0, 1.0)[1], sub.n)
+    ref.select_words(f, r, thr9)
+    cov_r, bits_r = ref.score_pairs(f, r, 1.0, 0.9)
+    assert np.array_equal(bits_s, bits_r) and np.array_equal(cov_s, cov_r), "split sequences vs reference"
+    assert np.array_equal(bits_big[:, :150], bits_r), "split sequences inside the big collection vs reference"
+    print("splits stage %d: %d entries, %d hits, index builds %d, stale sequences %d: index == table, 150 split sequences == reference (%d bits), %.1f s" % (
+        stage, outs[0][0], outs[0][2], outs[0][5], outs[0][6], int(bits_r.sum()), time.time() - t0), flush=True)
+gs.close()
 g.close()
 print("stress ok")
