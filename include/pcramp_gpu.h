@@ -497,6 +497,10 @@ typedef struct pcramp_gpu_stats {
 	uint64_t n_index_stale;   /* sequences split since the build and active again: covered by the table scan in this call */
 	uint64_t n_fast;          /* select_words batches of this ctx that ran in the fast form (no host round trip inside) so far */
 	uint64_t n_fast_redo;     /* ... of those, batches whose verification failed and that were run again in the general form */
+	uint64_t n_edge_words;    /* partial words (both strands) in the collection's table (edge.cuh) when this call used it, else 0 */
+	uint64_t edge_table_bytes;/* device memory of that table */
+	float ms_edge_table_build;/* host wall clock of its last build (one-time per upload / split and set of pack() parameters) */
+	uint32_t edge_table_used; /* 1: the partial words were matched through the table; 0: by the per-batch scan kernel */
 } pcramp_gpu_stats;
 int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
 /* Tuning / testing switches.  "force_brute_scan" = 1 sends every pattern through the brute-force scan kernel;

@@ -50,6 +50,10 @@ class Stats(ctypes.Structure):
         ("n_index_stale", ctypes.c_uint64),
         ("n_fast", ctypes.c_uint64),
         ("n_fast_redo", ctypes.c_uint64),
+        ("n_edge_words", ctypes.c_uint64),
+        ("edge_table_bytes", ctypes.c_uint64),
+        ("ms_edge_table_build", ctypes.c_float),
+        ("edge_table_used", ctypes.c_uint32),
     ]
 
     def as_dict(self):

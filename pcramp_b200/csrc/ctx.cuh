@@ -221,6 +221,17 @@ struct SeqSet {
 	DevBuf d_idx_stale;
 	uint64_t idx_bytes = 0, idx_builds = 0;
 	float idx_build_ms = 0.0f;
+	// the partial words of the collection as a table (edge.cuh): built on the first fast batch after an upload / split, for one set
+	// of pack() parameters; `failed` = not worth building (too large) until the text changes
+	struct EdgeTab {
+		DevBuf planes, meta, start, ids, degen;
+		uint32_t n_words = 0, n_degen = 0;
+		bool valid = false, failed = false;
+		PackParams pp = {};
+		uint64_t bytes = 0, builds = 0;
+		float build_ms = 0.0f;
+		void drop() { valid = failed = false; }
+	} edge;
 	void idx_drop()
 	{
 		idx_parts.clear();
@@ -228,6 +239,7 @@ struct SeqSet {
 		idx_stale.clear();
 		n_idx_stale = 0;
 		idx_bytes = 0;
+		edge.drop(); // (every caller has just changed the text)
 	}
 	// database (seq-grouped order = entry-id order) + canonical permutation
 	uint64_t n_entries = 0, n_keys = 0;
@@ -361,6 +373,8 @@ struct pcramp_gpu_ctx {
 	int use_background_units = 1;    // option "use_background_units"
 	int use_unit_score = 1;          // option "use_unit_score": pair scoring by (sequence, pair) units at unselective thresholds
 	int use_async_scan = 0;          // option "use_async_scan" = 1: scan_index_async_kernel instead of scan_index_kernel (measured slower)
+	int use_edge_table = 1;          // option "use_edge_table": fast batches look the candidates up in the collection's partial-word table (edge.cuh)
+	float edge_off_thr[PCRAMP_NUM_KINDS] = {-1.0f, -1.0f, -1.0f}; // a threshold whose candidates the table could not serve: the scan kernel keeps it
 	bool async_scan_ready = false;   // its dynamic shared memory size has been set on this context's device
 	float sw_ms_kernel = 0.0f;
 };

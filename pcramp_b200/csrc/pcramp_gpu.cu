@@ -8,6 +8,7 @@
 #include "ctx.cuh"
 #include "score.cuh"
 #include "index.cuh"
+#include "edge.cuh"
 
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
@@ -460,6 +461,63 @@ int build_index(pcramp_gpu_ctx *ctx, SeqSet &s)
 	return 0;
 }
 
+// The partial words of a collection as a table the candidates are looked up in (edge.cuh).  One-time per upload / split and set of
+// pack() parameters; synchronous (two small counts come back to size the buffers).  Leaves `failed` set when the table is not
+// worth its memory (the callers then keep scan_edge_fst_kernel).
+int edge_table_build(pcramp_gpu_ctx *ctx, SeqSet &s, const PackParams &pp)
+{
+	SeqSet::EdgeTab &t = s.edge;
+	t.valid = false;
+	t.failed = true;
+	t.pp = pp;
+	if (s.n == 0) return 0;
+	const auto t0 = std::chrono::steady_clock::now();
+	cudaStream_t st = ctx->stream;
+	const SeqDev sd = s.dev();
+	DevBuf counters, cnt;
+	CK(counters.ensure(16));
+	CK(cnt.ensure((size_t)(EDGE_BUCKETS + 1) * 4));
+	CK(t.start.ensure((size_t)(EDGE_BUCKETS + 1) * 4));
+	CK(cudaMemsetAsync(counters.p, 0, 16, st));
+	CK(cudaMemsetAsync(cnt.p, 0, (size_t)(EDGE_BUCKETS + 1) * 4, st));
+	const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)s.n + 3) / 4, (uint64_t)ctx->sm_count * 16);
+	edge_words_kernel<false><<<grid, 128, 0, st>>>(sd, pp, counters.as<unsigned int>(), cnt.as<uint32_t>(), nullptr, nullptr, nullptr, 0u, 0u);
+	CK(cudaGetLastError());
+	size_t tmp_bytes = 0;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.as<uint32_t>(), t.start.as<uint32_t>(), (int)(EDGE_BUCKETS + 1), st));
+	CK(ctx->cub_tmp.ensure(tmp_bytes));
+	CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, cnt.as<uint32_t>(), t.start.as<uint32_t>(), (int)(EDGE_BUCKETS + 1), st));
+	unsigned int h_cnt[2] = {0, 0};
+	uint32_t total = 0;
+	CK(cudaMemcpyAsync(h_cnt, counters.p, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&total, t.start.as<uint32_t>() + EDGE_BUCKETS, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const uint64_t bytes = (uint64_t)h_cnt[0] * 32ull + (uint64_t)total * 4ull + (uint64_t)h_cnt[1] * 4ull + (uint64_t)(EDGE_BUCKETS + 1) * 4ull;
+	if (h_cnt[0] >= (1u << 30) || bytes > (8ull << 30)) return 0; // (hundreds of millions of sequence ends: the scan kernel handles them)
+	CK(t.planes.ensure(std::max<size_t>(1, h_cnt[0]) * 16));
+	CK(t.meta.ensure(std::max<size_t>(1, h_cnt[0]) * 16));
+	CK(t.degen.ensure(std::max<size_t>(1, h_cnt[1]) * 4));
+	CK(t.ids.ensure(std::max<size_t>(1, total) * 4));
+	CK(cudaMemsetAsync(counters.p, 0, 16, st));
+	edge_words_kernel<true><<<grid, 128, 0, st>>>(sd, pp, counters.as<unsigned int>(), nullptr, t.planes.as<uint4>(), t.meta.as<uint4>(), t.degen.as<uint32_t>(),
+		h_cnt[0], h_cnt[1]);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(cnt.p, t.start.p, (size_t)(EDGE_BUCKETS + 1) * 4, cudaMemcpyDeviceToDevice, st));
+	if (h_cnt[0]) {
+		edge_fill_kernel<<<grid_for(h_cnt[0], 256), 256, 0, st>>>(t.planes.as<uint4>(), h_cnt[0], cnt.as<uint32_t>(), t.ids.as<uint32_t>(), total);
+		CK(cudaGetLastError());
+	}
+	CK(cudaStreamSynchronize(st));
+	t.n_words = h_cnt[0];
+	t.n_degen = h_cnt[1];
+	t.bytes = bytes;
+	t.builds++;
+	t.build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	t.valid = true;
+	t.failed = false;
+	return 0;
+}
+
 int fast_resolve(pcramp_gpu_ctx *ctx); // below: verify (and if need be re-run) a batch that select_words_fast left unverified
 
 int check_kind(pcramp_gpu_ctx *ctx, int kind)
@@ -515,6 +573,25 @@ int pcramp_gpu_create(pcramp_gpu_ctx **out, int device)
 	cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
 	cudaMallocHost((void **)&ctx->h_fast, 8 * sizeof(unsigned long long));
+	// PCRAMP_OPTIONS="name=value,name=value": pcramp_gpu_set_option for every context of the process (A/B runs of a host that has no
+	// switch of its own for an option; an unknown name fails the create -- a typo must not pass for a measurement)
+	if (const char *env = getenv("PCRAMP_OPTIONS")) {
+		std::string all(env);
+		size_t at = 0;
+		while (at < all.size()) {
+			size_t end = all.find(',', at);
+			if (end == std::string::npos) end = all.size();
+			const std::string item = all.substr(at, end - at);
+			at = end + 1;
+			if (item.empty()) continue;
+			const size_t eq = item.find('=');
+			if (eq == std::string::npos || pcramp_gpu_set_option(ctx, item.substr(0, eq).c_str(), atoi(item.c_str() + eq + 1))) {
+				fprintf(stderr, "pcramp_gpu_create: bad PCRAMP_OPTIONS item '%s'\n", item.c_str());
+				pcramp_gpu_destroy(ctx);
+				return 6;
+			}
+		}
+	}
 	*out = ctx;
 	return 0;
 }
@@ -545,7 +622,7 @@ int pcramp_gpu_create_worker(pcramp_gpu_ctx *parent, pcramp_gpu_ctx **out)
 	w->use_neigh = parent->use_neigh; w->use_tier_table = parent->use_tier_table; w->use_fused_score = parent->use_fused_score;
 	w->use_entry_score = parent->use_entry_score; w->use_seg_db = parent->use_seg_db; w->use_fast = parent->use_fast;
 	w->use_async_scan = parent->use_async_scan; w->use_unit_score = parent->use_unit_score; w->use_background_units = parent->use_background_units;
-	w->use_variant_groups = parent->use_variant_groups;
+	w->use_variant_groups = parent->use_variant_groups; w->use_edge_table = parent->use_edge_table;
 	for (int kind = 0; kind < PCRAMP_NUM_KINDS; ++kind) {
 		const SeqSet &p = parent->sets[kind];
 		SeqSet &s = w->sets[kind];
@@ -757,6 +834,7 @@ int pcramp_gpu_split_sequences(pcramp_gpu_ctx *ctx, int kind, uint32_t n, const 
 	std::sort(touched.begin(), touched.end());
 	touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
 	s.db_valid = false;
+	s.edge.drop(); // the split sequences have new partial words (EOS events): the table is rebuilt by the next fast batch
 	if (kind == PCRAMP_MULTIPLEX) ctx->mpx_valid = false;
 	if (s.idx_valid) { // the index stays: the split sequences' entries are ignored from now on (SeqSet::idx_stale)
 		for (uint32_t q : touched)
@@ -1587,6 +1665,16 @@ static int select_words_fast(pcramp_gpu_ctx *ctx, int kind, float threshold, con
 	hs.val = ctx->hit_val[0].as<uint32_t>();
 	hs.count = d_cnt;
 	hs.cap = cap;
+	// ---- the collection's partial words as a table (edge.cuh): built on the first fast batch after an upload / split ---------------
+	bool use_et = ctx->use_edge_table && ctx->edge_off_thr[kind] != threshold;
+	if (use_et) {
+		SeqSet::EdgeTab &t = s.edge;
+		if (t.pp.max_degen != pp.max_degen || t.pp.min_gc != pp.min_gc || t.pp.max_gc != pp.max_gc || t.pp.min_len != pp.min_len ||
+		    t.pp.gc_filter != pp.gc_filter)
+			t.drop();
+		if (!t.valid && !t.failed && edge_table_build(ctx, s, pp)) return 1;
+		use_et = t.valid;
+	}
 	// ---- candidates + patterns ------------------------------------------------------------------------------------------
 	CK(cudaEventRecord(ctx->ev[0], st));
 	CK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
@@ -1599,7 +1687,21 @@ static int select_words_fast(pcramp_gpu_ctx *ctx, int kind, float threshold, con
 	CK(cudaEventRecord(ctx->ev_fork, st));
 	// ---- second stream: the partial words through the seed table over the candidates ---------------------------------------
 	CK(cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
-	{
+	if (use_et) { // the candidates look themselves up in the table of partial words
+		EdgeTable et;
+		et.planes = s.edge.planes.as<uint4>();
+		et.meta = s.edge.meta.as<uint4>();
+		et.start = s.edge.start.as<uint32_t>();
+		et.ids = s.edge.ids.as<uint32_t>();
+		et.degen = s.edge.degen.as<uint32_t>();
+		et.n_words = s.edge.n_words;
+		et.n_degen = s.edge.n_degen;
+		const uint64_t tasks = std::max<uint64_t>((uint64_t)n_cand * EDGE_MAX_PIECES, std::min<uint64_t>(et.n_degen, (uint64_t)ctx->sm_count * 16));
+		edge_lookup_kernel<<<(unsigned)std::max<uint64_t>(1, tasks), EDGE_THREADS, 0, st2>>>(sd, et,
+			s.c_planes.as<uint4>(), s.c_thr.as<uint32_t>(), n_cand, cand_bits, hs, ctx->d_fst_nbrute.as<unsigned int>() + 1);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev_join, st2));
+	} else {
 		Fst fst;
 		CK(cudaMemsetAsync(ctx->d_fst_cnt.p, 0, (size_t)(FST_BUCKETS + 1) * 4, st2));
 		CK(cudaMemsetAsync(ctx->d_fst_combo.p, 0, FST_COMBOS * 4, st2));
@@ -1665,7 +1767,13 @@ static int select_words_fast(pcramp_gpu_ctx *ctx, int kind, float threshold, con
 	CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); // every hit is in the list from here on
 	CK(cudaEventRecord(ctx->ev[2], st));
 	CK(cudaEventRecord(ctx->ev[3], st));
-	stat.kernel_launches += 6;
+	stat.kernel_launches += use_et ? 1 : 6;
+	stat.edge_table_used = use_et ? 1u : 0u;
+	if (use_et) {
+		stat.n_edge_words = s.edge.n_words;
+		stat.edge_table_bytes = s.edge.bytes;
+		stat.ms_edge_table_build = s.edge.build_ms;
+	}
 	// ---- database (db.cuh, segmented form; the hit count stays on the device) -----------------------------------------------
 	if (pp.gc_filter || s.any_degenerate) {
 		validate_hits_kernel<<<grid_for(cap, 256), 256, 0, st>>>(sd, pp, hs.key, hs.val, cap, cand_bits, d_cnt);
@@ -1757,6 +1865,7 @@ int fast_resolve(pcramp_gpu_ctx *ctx)
 		return 0;
 	}
 	// an assumption did not hold (a buffer was too small, a pattern not indexable, a zero threshold): the general form decides
+	if (h[0] & (unsigned long long)EDGE_FLAG_UNSUITABLE) ctx->edge_off_thr[p.kind] = p.threshold; // pieces shorter than the table's runs
 	ctx->fast_hint[p.kind].ok = false;
 	ctx->n_fast_redo++;
 	return select_words_general(ctx, p.kind, 0, 0, p.threshold, p.pp.max_degen, p.pp.min_gc, p.pp.max_gc, p.pp.min_len, nullptr, nullptr);
@@ -2473,6 +2582,7 @@ int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value)
 	if (strcmp(name, "use_background_units") == 0) { ctx->use_background_units = value; return 0; }
 	if (strcmp(name, "use_async_scan") == 0) { ctx->use_async_scan = value; return 0; }
 	if (strcmp(name, "use_unit_score") == 0) { ctx->use_unit_score = value; return 0; }
+	if (strcmp(name, "use_edge_table") == 0) { ctx->use_edge_table = value; return 0; }
 	if (strcmp(name, "use_segmented_db") == 0) { ctx->use_seg_db = value; return 0; }
 	if (strcmp(name, "use_fast_path") == 0) { ctx->use_fast = value; return 0; }
 	if (strcmp(name, "tiny_buffers") == 0) { ctx->tiny_buffers = value; return 0; }

@@ -562,6 +562,107 @@ def test_fast_form_equals_general_form(oracle):
         g.close()
 
 
+def _end_primers(rng, coll, seqs, n_each):
+    """primers cut from the first and last ~35 bases of sequences: the ones partial words (FILL / TAIL / EOS events) can match"""
+    out = []
+    for s_ in seqs:
+        c = coll.codes(int(s_))
+        L = len(c)
+        for _ in range(n_each):
+            n = int(rng.integers(18, 26))
+            if L < n:
+                continue
+            a = int(rng.integers(0, min(10, L - n + 1)))
+            out.append(synth.word_from_codes(c[a:a + n]))
+            b = L - n - int(rng.integers(0, min(10, L - n + 1)))
+            out.append(synth.word_from_codes(synth.revcomp_codes(c[b:b + n])))
+    return np.array(out, np.uint64)
+
+
+def test_partial_word_table_equals_scan_and_oracle(oracle):
+    """edge.cuh: in the fast form the candidates look themselves up in the collection's table of partial words.  Primers cut from
+    sequence ends (so that FILL / TAIL / EOS-event words really match), short sequences, IUPAC codes inside the first and last 32
+    bases, splits and switched-off sequences: table == scan kernel == oracle, and the table follows splits.  (Every batch the fast
+    form accepts has pieces of five slots or more -- shorter pieces are not seedable, select_words takes the general form -- so the
+    table's runs of five serve all of them; the flag for a candidate it cannot serve is a guard.)"""
+    from pcramp_b200 import PcrampGpu
+    from bench_legs import widen
+    rng = np.random.default_rng(91)
+    base = synth.make_targets(141, 36, 420, n_clades=2, between=0.10, within=0.03)
+    seqs = [base.codes(i).copy() for i in range(base.n)]
+    for i in (3, 9, 20):                                            # degenerate bases near both ends: words without a seed code
+        seqs[i][int(rng.integers(2, 30))] = 15
+        seqs[i][len(seqs[i]) - int(rng.integers(2, 30))] = 5
+    for n in (17, 18, 24, 31, 32, 33):                              # shorter than / about one word
+        seqs.append(seqs[1][:n].copy())
+        seqs.append(seqs[2][-n:].copy())
+    coll = synth.Collection(seqs)
+    ends = _end_primers(rng, coll, range(0, 36, 3), 3)
+    inner_f, inner_r = synth.make_pairs(142, base, 40)
+    P = 48
+    f = np.concatenate([ends[0::2][:P - 16], inner_f[:16]])
+    r = np.concatenate([ends[1::2][:P - 16], inner_r[:16]])
+    f2, r2 = widen(f[::-1].copy(), rng), widen(r[::-1].copy(), rng)
+    assert len(f) == P and len(r) == P
+    active = np.ones(coll.n, np.uint8)
+    active[[5, 11, 40]] = 0
+    oracle.set_sequences(coll, active)
+    g = PcrampGpu(0)
+    try:
+        g.upload_sequences(TARGET, coll.nibbles, coll.byte_off, coll.length)
+        g.set_active(TARGET, active)
+        chk = GpuChecker(g)
+        chk.n_seq = coll.n
+
+        def batch(fb, rb, thr, table):
+            g.set_option("use_edge_table", table)
+            g.select_words(TARGET, fb, rb, thr, want_keys=False, want_entries=False)
+            cov, bits = g.score_pairs(TARGET, fb, rb, thr, 1.0)
+            no, nko = oracle.select_words(fb, rb, thr)
+            cov_o, bits_o = oracle.score_pairs(fb, rb, thr, 1.0, 80, 200, False)
+            assert g.db_size(TARGET) == (no, nko)
+            db_o = oracle.db()
+            for a, c in zip(chk.db(), db_o):
+                assert np.array_equal(a, c)
+            assert np.array_equal(cov, cov_o) and np.array_equal(unpack_bits(bits, coll.n), bits_o)
+            w = db_o[0]                                               # entries that are partial words: an empty first or last slot
+            partial = int((((w[:, 0] >> np.uint64(60)) == 0) | ((w[:, 1] & np.uint64(15)) == 0)).sum())
+            return g.stats(), partial
+        st, partial = batch(f, r, THR_09, 1)
+        assert st["n_fast"] == 0 and partial >= 20                  # general form; the end primers do find partial words
+        st, _ = batch(f2, r2, THR_09, 1)
+        assert st["n_fast"] == 1 and st["n_fast_redo"] == 0 and st["edge_table_used"] == 1 and st["n_edge_words"] > 1000
+        hits_table = st["n_hits"]
+        st, _ = batch(f2, r2, THR_09, 0)
+        assert st["n_fast"] == 2 and st["edge_table_used"] == 0 and st["n_hits"] == hits_table
+        # splits make new partial words (EOS events) and retire old ones: the table is rebuilt
+        for s_, p_ in ((0, 25), (0, 200), (6, 31), (6, 32), (12, 400), (12, 401), (37, 9), (21, 100)):
+            g.split_sequence(TARGET, s_, p_)
+            oracle.split_sequence(s_, p_)
+        active[[5, 40]] = 1
+        active[[0, 15]] = 0
+        g.set_active(TARGET, active)
+        oracle.set_active(active)
+        near = np.array([synth.word_from_codes(coll.codes(12)[401 + 1:401 + 21]), synth.word_from_codes(coll.codes(0)[26:26 + 22])], np.uint64)
+        f3, r3 = f.copy(), r.copy()
+        f3[:2] = near                                                # primers that start right behind a split
+        st, _ = batch(f3, r3, THR_09, 1)                             # (the split withdrew the hint: general form)
+        fast = st["n_fast"]
+        st, _ = batch(f3[::-1].copy(), r3[::-1].copy(), THR_09, 1)
+        assert st["n_fast"] == fast + 1 and st["edge_table_used"] == 1 and st["n_fast_redo"] == 0
+        hits_table = st["n_hits"]
+        st, _ = batch(f3[::-1].copy(), r3[::-1].copy(), THR_09, 0)
+        assert st["edge_table_used"] == 0 and st["n_hits"] == hits_table
+        # another threshold, same table (it belongs to the collection and the pack() parameters, not to the batch)
+        thr95 = float(np.float32(1.0) * np.float32(0.95))
+        st, _ = batch(f, r, thr95, 1)
+        fast = st["n_fast"]
+        st, _ = batch(f2, r2, thr95, 1)
+        assert st["n_fast"] == fast + 1 and st["edge_table_used"] == 1 and st["n_fast_redo"] == 0 and st["n_edge_words"] > 1000
+    finally:
+        g.close()
+
+
 def test_degenerate_primers_through_the_index(gpu, oracle):
     """primers as `-d 16` leaves them (up to four two-letter positions): the degenerate positions of a segment prefix are enumerated
     letter by letter in the index queries -- same database, keys, coverage and bits as the oracle and as the table scan, the same
