@@ -628,13 +628,25 @@ def test_partial_word_table_equals_scan_and_oracle(oracle):
             w = db_o[0]                                               # entries that are partial words: an empty first or last slot
             partial = int((((w[:, 0] >> np.uint64(60)) == 0) | ((w[:, 1] & np.uint64(15)) == 0)).sum())
             return g.stats(), partial
+        def fast_batch(fb, rb, thr, table):
+            """a batch that must run in the fast form; if its buffers (sized by the batch before) overflowed it was re-run in the
+            general form, which grew them: the same batch again is then fast and verified"""
+            before = g.stats()
+            st, _ = batch(fb, rb, thr, table)
+            assert st["n_fast"] == before["n_fast"] + 1
+            if st["n_fast_redo"] != before["n_fast_redo"]:
+                st2, _ = batch(fb, rb, thr, table)
+                assert st2["n_fast"] == st["n_fast"] + 1 and st2["n_fast_redo"] == st["n_fast_redo"]
+                st = st2
+            assert st["edge_table_used"] == table
+            return st
         st, partial = batch(f, r, THR_09, 1)
         assert st["n_fast"] == 0 and partial >= 20                  # general form; the end primers do find partial words
-        st, _ = batch(f2, r2, THR_09, 1)
-        assert st["n_fast"] == 1 and st["n_fast_redo"] == 0 and st["edge_table_used"] == 1 and st["n_edge_words"] > 1000
+        st = fast_batch(f2, r2, THR_09, 1)
+        assert st["n_edge_words"] > 1000
         hits_table = st["n_hits"]
-        st, _ = batch(f2, r2, THR_09, 0)
-        assert st["n_fast"] == 2 and st["edge_table_used"] == 0 and st["n_hits"] == hits_table
+        st = fast_batch(f2, r2, THR_09, 0)
+        assert st["n_hits"] == hits_table
         # splits make new partial words (EOS events) and retire old ones: the table is rebuilt
         for s_, p_ in ((0, 25), (0, 200), (6, 31), (6, 32), (12, 400), (12, 401), (37, 9), (21, 100)):
             g.split_sequence(TARGET, s_, p_)
@@ -646,19 +658,18 @@ def test_partial_word_table_equals_scan_and_oracle(oracle):
         near = np.array([synth.word_from_codes(coll.codes(12)[401 + 1:401 + 21]), synth.word_from_codes(coll.codes(0)[26:26 + 22])], np.uint64)
         f3, r3 = f.copy(), r.copy()
         f3[:2] = near                                                # primers that start right behind a split
+        fast = g.stats()["n_fast"]
         st, _ = batch(f3, r3, THR_09, 1)                             # (the split withdrew the hint: general form)
-        fast = st["n_fast"]
-        st, _ = batch(f3[::-1].copy(), r3[::-1].copy(), THR_09, 1)
-        assert st["n_fast"] == fast + 1 and st["edge_table_used"] == 1 and st["n_fast_redo"] == 0
+        assert st["n_fast"] == fast
+        st = fast_batch(f3[::-1].copy(), r3[::-1].copy(), THR_09, 1)
         hits_table = st["n_hits"]
-        st, _ = batch(f3[::-1].copy(), r3[::-1].copy(), THR_09, 0)
-        assert st["edge_table_used"] == 0 and st["n_hits"] == hits_table
+        st = fast_batch(f3[::-1].copy(), r3[::-1].copy(), THR_09, 0)
+        assert st["n_hits"] == hits_table
         # another threshold, same table (it belongs to the collection and the pack() parameters, not to the batch)
         thr95 = float(np.float32(1.0) * np.float32(0.95))
-        st, _ = batch(f, r, thr95, 1)
-        fast = st["n_fast"]
-        st, _ = batch(f2, r2, thr95, 1)
-        assert st["n_fast"] == fast + 1 and st["edge_table_used"] == 1 and st["n_fast_redo"] == 0 and st["n_edge_words"] > 1000
+        batch(f, r, thr95, 1)
+        st = fast_batch(f2, r2, thr95, 1)
+        assert st["n_edge_words"] > 1000
     finally:
         g.close()
 
