@@ -954,6 +954,11 @@ def run_b200(a):
         stats_acc.update(fast_acc)
         for _ in range(2):                                   # back in the fast form for the legs that follow
             step_resident(a.warmup, False, 0)
+        st_edge = g.stats()                                  # (settles the batch; the partial-word table is per context)
+        edge_info = {"used": bool(st_edge["edge_table_used"]), "words": int(st_edge["n_edge_words"]), "bytes": int(st_edge["edge_table_bytes"]),
+                     "ms_build": float(st_edge["ms_edge_table_build"]),
+                     "note": "the FILL / EOS-event / TAIL words of the collection, both strands, indexed by their runs of five slots (edge.cuh): "
+                             "one-time per upload / split and context, outside the timed region"}
         int_peak = g.measure_int_peak() if rank == 0 else 0.0
         dp = dp_leg(a, g, torch, ext, rank, world, dist if world > 1 else None) if a.dp_problems > 0 else None
 
@@ -1058,7 +1063,7 @@ def run_b200(a):
                        "exchange": ("none" if not by_targets else "peer stores over NVLink from the scoring stream + flag wait (xchg.cuh), no NCCL "
                                     "on the data path" if p2p else "NCCL all-gather + pcramp_gpu_merge_shards"),
                        "db_entries_per_step": stats_acc["n_entries"] / n_scan, "hits_per_step": stats_acc["n_hits"] / n_scan,
-                       "text_index": index_info},
+                       "text_index": index_info, "partial_word_table": edge_info},
             "timed_region": {"repeats_resident": reps_resident, "repeats_e2e": reps_e2e, "seconds_resident": ms_resident * reps_resident * 1e-3,
                              "seconds_e2e": ms_e2e * reps_e2e * 1e-3,
                              "note": "the region of --steps steps (barrier + synchronize on both sides, CUDA events) is repeated until "

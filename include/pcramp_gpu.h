@@ -521,8 +521,12 @@ int pcramp_gpu_get_stats(pcramp_gpu_ctx *ctx, pcramp_gpu_stats *out);
  * by sorting the hit list instead of through a (sequence, candidate) table of maxima (db.cuh); "tiny_buffers" = 1 makes every
  * growable device buffer (hits, index queries / candidates, neighbour list, work list) start far too small on a fresh context,
  * so that the overflow -> grow -> re-run paths are exercised; "index_part_positions" = the most positions one part of the text index
- * may hold (default 2^31; a small value cuts a test collection into several parts, as a collection above 2^31 bases is).
- * All paths are CUDA and give identical results; the tests compare them. */
+ * may hold (default 2^31; a small value cuts a test collection into several parts, as a collection above 2^31 bases is);
+ * "use_edge_table" = 0 makes the fast form of select_words match the partial words pack() emits at sequence ends by the per-batch scan
+ * kernel (scan_edge_fst_kernel) instead of looking the candidates up in the collection's table of partial words (edge.cuh).
+ * All paths are CUDA and give identical results; the tests compare them.
+ * The environment variable PCRAMP_OPTIONS="name=value,name=value" applies pcramp_gpu_set_option to every context the process
+ * creates (A/B runs of a host that has no switch of its own); an unknown name makes pcramp_gpu_create fail with 6. */
 int pcramp_gpu_set_option(pcramp_gpu_ctx *ctx, const char *name, int value);
 /* Issue-bound ceiling of the scan's own instruction mix on this GPU (alignments/s), measured live. */
 int pcramp_gpu_measure_int_peak(pcramp_gpu_ctx *ctx, double *alignments_per_s);

@@ -134,13 +134,16 @@ edge_lookup_kernel(SeqDev sd, EdgeTable et, const uint4 *__restrict__ cand_plane
 		bool usable;
 		fst_shape(p, need, first, len, pieces, usable);
 		if ((p.x | p.y | p.z | p.w) == 0u || need > len) continue; // can never match (fst_build_kernel leaves it out as well)
-		if (!edge_candidate_ok(p, first, len, pieces, usable)) {
-			if (k == 0u && threadIdx.x == 0u) atomicOr(flags, EDGE_FLAG_UNSUITABLE);
+		// (five of a candidate's eight CTAs have no piece: they leave here.  The CTA of piece 0 decides whether the table can serve the
+		// candidate at all; the others only look at their own piece -- if another piece is the problem the batch is re-run anyway)
+		if (k != 0u && (!usable || k >= pieces)) continue;
+		if (k == 0u && !edge_candidate_ok(p, first, len, pieces, usable)) {
+			if (threadIdx.x == 0u) atomicOr(flags, EDGE_FLAG_UNSUITABLE);
 			continue;
 		}
-		if (k >= pieces) continue;
 		uint32_t o, q;
 		fst_piece(len, pieces, k, o, q);
+		if (q < EDGE_Q) continue;
 		const uint32_t p0 = first + o;
 		uint32_t seed_earlier[EDGE_MAX_PIECES]; // seed masks of the pieces before this one
 		for (uint32_t j = 0; j < EDGE_MAX_PIECES; ++j) {

@@ -473,6 +473,7 @@ int edge_table_build(pcramp_gpu_ctx *ctx, SeqSet &s, const PackParams &pp)
 	if (s.n == 0) return 0;
 	const auto t0 = std::chrono::steady_clock::now();
 	cudaStream_t st = ctx->stream;
+	Trace tr("edge_table_build", st);
 	const SeqDev sd = s.dev();
 	DevBuf counters, cnt;
 	CK(counters.ensure(16));
@@ -492,6 +493,7 @@ int edge_table_build(pcramp_gpu_ctx *ctx, SeqSet &s, const PackParams &pp)
 	CK(cudaMemcpyAsync(h_cnt, counters.p, 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(&total, t.start.as<uint32_t>() + EDGE_BUCKETS, 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
+	tr.mark("count + prefix sum");
 	const uint64_t bytes = (uint64_t)h_cnt[0] * 32ull + (uint64_t)total * 4ull + (uint64_t)h_cnt[1] * 4ull + (uint64_t)(EDGE_BUCKETS + 1) * 4ull;
 	if (h_cnt[0] >= (1u << 30) || bytes > (8ull << 30)) return 0; // (hundreds of millions of sequence ends: the scan kernel handles them)
 	CK(t.planes.ensure(std::max<size_t>(1, h_cnt[0]) * 16));
@@ -508,6 +510,7 @@ int edge_table_build(pcramp_gpu_ctx *ctx, SeqSet &s, const PackParams &pp)
 		CK(cudaGetLastError());
 	}
 	CK(cudaStreamSynchronize(st));
+	tr.mark("words + ids");
 	t.n_words = h_cnt[0];
 	t.n_degen = h_cnt[1];
 	t.bytes = bytes;
