@@ -673,69 +673,122 @@ scan_index_async_kernel(TextIndex ix, const IdxQuery *__restrict__ queries, cons
 	if (wb.used < IDX_BLOCK) index_block_pad(cs, wb, lane);
 }
 
-// place each candidate in its sequence, drop what other kernels own, report once
+// place each candidate in its sequence, drop what other kernels own, report once.
+// A candidate is a chain of dependent loads (record -> block table -> sequence starts -> the sequence's flags and length) with a few
+// instructions in between: ncu had 13 warps per issue waiting on them.  The kernel can walk IDX_HITS_ROWS candidates per thread side
+// by side (the loads of a step issued for all of them before any is used); measured on the bench batch, 4 batches in flight / one at
+// a time: 1 row 0.850 / 1.145 ms per step, 2 rows 0.852 / 1.141, 4 rows 0.857 / 1.137 -- the latency a lone batch gains is lost again
+// when other batches' kernels fill the stalls anyway, so the default stays 1.  The lanes of a warp meet again before the hit list is
+// touched, so a row of 32 candidates costs one atomic on the list counter.
 #ifndef IDX_HITS_BLOCKS
 #define IDX_HITS_BLOCKS 1
+#endif
+#ifndef IDX_HITS_ROWS
+#define IDX_HITS_ROWS 1
 #endif
 __global__ void __launch_bounds__(256, IDX_HITS_BLOCKS)
 index_hits_kernel(SeqDev sd, TextIndex ix, IdxCandSink cs, const uint32_t *__restrict__ g_meta, const uint32_t *__restrict__ g_meta2,
 	const uint32_t *__restrict__ dirty_bits, const uint8_t *__restrict__ stale, uint32_t cand_bits, HitSink hs)
 {
+	constexpr int R = IDX_HITS_ROWS;
 	const uint32_t total = min(*cs.count, cs.cap);
 	const uint32_t lane = threadIdx.x & 31u;
-	// warp-uniform trip count: the lanes of a warp meet again before the hit list is touched, so a row of 32 candidates costs one
-	// atomic on the list counter instead of one per group of lanes that happened to survive the same branches
-	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += gridDim.x * blockDim.x) {
-		const uint32_t i = i0 + lane;
-		bool ok = false;
-		uint32_t seq = 0, meta = 0, meta2 = 0, cnt = 0;
-		int64_t x = 0;
-		if (i < total) {
-			const IdxCand c = cs.buf[i];
-			if (c.gpos != IDX_INVALID) { // (else: the unused tail of a warp's block)
-				const uint32_t wo = c.seg >> 24, si = (c.seg >> 16) & 255u;
-				meta = __ldg(g_meta + c.pid); // independent of the chain of loads that places the candidate: issued beside it
-				meta2 = __ldg(g_meta2 + c.pid);
-				const uint32_t rel = idx_seq_of_fast(ix, ix.n_seq, c.gpos);
-				seq = ix.seq_lo + rel;
-				x = (int64_t)(c.gpos - __ldg(ix.cum + rel)) - (int64_t)wo; // text index of primer base 0
-				// a sequence split since the build has moved under its entries: the table scan covers it (pcramp_gpu.cu)
-				ok = x >= 0 && sd.active[seq] && !(stale && stale[seq]);
-				if (ok && dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
-					const uint64_t G = sd.grp_off[seq] + (uint64_t)(x >> 5);
-					if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) ok = false;
-				}
-				if (ok) {
-					const uint32_t n = (meta2 >> 10) & 63u, segs = idx_segments((meta2 >> 16) & 63u);
-					for (uint32_t k = 0; k < si; ++k) { // an earlier segment whose prefix is within one mismatch reports this alignment
-						uint32_t oo, kk;
-						idx_segment(n, segs, k, oo, kk);
-						if ((uint32_t)__popc((c.m >> oo) & ((1u << kk) - 1u)) + 1u >= kk) ok = false;
-					}
-					cnt = (uint32_t)__popc(c.m);
-				}
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t r0 = warp * R; r0 * 32u < total; r0 += n_warps * R) { // rows r0 .. r0 + R - 1 of 32 candidates: warp-uniform trip count
+		IdxCand c[R];
+		bool live[R];
+		uint32_t meta[R], meta2[R], lo[R], hi[R];
+		#pragma unroll
+		for (int u = 0; u < R; ++u) {
+			const uint32_t i = (r0 + u) * 32u + lane;
+			live[u] = i < total;
+			c[u].gpos = IDX_INVALID;
+			c[u].m = c[u].pid = c[u].seg = 0u;
+			if (live[u]) c[u] = cs.buf[i];
+			live[u] = live[u] && c[u].gpos != IDX_INVALID; // (else: the unused tail of a warp's block)
+		}
+		#pragma unroll
+		for (int u = 0; u < R; ++u) { // independent of the chain that places the candidate: issued beside it
+			meta[u] = meta2[u] = lo[u] = 0u;
+			hi[u] = 1u;
+			if (live[u]) {
+				meta[u] = __ldg(g_meta + c[u].pid);
+				meta2[u] = __ldg(g_meta2 + c[u].pid);
+				const uint32_t b = c[u].gpos >> IDX_BLK_SHIFT; // idx_seq_of_fast, its probes taken in step with the other rows'
+				lo[u] = __ldg(ix.blk + b);
+				hi[u] = min(__ldg(ix.blk + b + 1u) + 1u, ix.n_seq);
 			}
 		}
-		const bool family = ok && (meta2 & 1023u) != 0u; // 5'/3' shift families fan out to several candidates: the general path
-		if (family) emit_family(hs, seq, sd.clen[seq], cand_bits, meta, meta2, x, cnt);
-		// the plain case (no shift family): at most one hit per candidate, appended with one atomic per warp
-		bool one = ok && !family;
-		uint32_t wstart = 0;
-		if (one) {
-			const int64_t ws = x - (int64_t)((meta >> 6) & 31u);
-			one = ws >= 0 && ws + 32 <= (int64_t)sd.clen[seq];
-			wstart = (uint32_t)ws;
+		for (;;) {
+			bool any = false;
+			uint32_t mid[R], at[R];
+			#pragma unroll
+			for (int u = 0; u < R; ++u) {
+				mid[u] = (lo[u] + hi[u]) >> 1;
+				at[u] = (live[u] && hi[u] - lo[u] > 1u) ? __ldg(ix.cum + mid[u]) : 0u;
+			}
+			#pragma unroll
+			for (int u = 0; u < R; ++u)
+				if (live[u] && hi[u] - lo[u] > 1u) {
+					if (at[u] <= c[u].gpos) lo[u] = mid[u]; else hi[u] = mid[u];
+					any = any || hi[u] - lo[u] > 1u;
+				}
+			if (!any) break;
 		}
-		const uint32_t bal = __ballot_sync(0xffffffffu, one);
-		if (bal) {
-			unsigned long long base = 0;
-			if (lane == 0u) base = atomicAdd(hs.count, (unsigned long long)__popc(bal));
-			base = __shfl_sync(0xffffffffu, base, 0);
+		uint32_t seq[R], first[R], clen[R];
+		bool ok[R];
+		#pragma unroll
+		for (int u = 0; u < R; ++u) {
+			seq[u] = ix.seq_lo + lo[u];
+			first[u] = clen[u] = 0u;
+			ok[u] = false;
+			if (live[u]) {
+				first[u] = __ldg(ix.cum + lo[u]);
+				clen[u] = sd.clen[seq[u]];
+				// a sequence split since the build has moved under its entries: the table scan covers it (pcramp_gpu.cu)
+				ok[u] = sd.active[seq[u]] && !(stale && stale[seq[u]]);
+			}
+		}
+		#pragma unroll
+		for (int u = 0; u < R; ++u) {
+			const uint32_t wo = c[u].seg >> 24, si = (c[u].seg >> 16) & 255u;
+			const int64_t x = (int64_t)(c[u].gpos - first[u]) - (int64_t)wo; // text index of primer base 0
+			bool good = ok[u] && x >= 0;
+			if (good && dirty_bits) { // alignments touching a degenerate text base belong to scan_groups_kernel
+				const uint64_t G = sd.grp_off[seq[u]] + (uint64_t)(x >> 5);
+				if ((dirty_bits[G >> 5] >> (G & 31u)) & 1u) good = false;
+			}
+			uint32_t cnt = 0;
+			if (good) {
+				const uint32_t n = (meta2[u] >> 10) & 63u, segs = idx_segments((meta2[u] >> 16) & 63u);
+				for (uint32_t k = 0; k < si; ++k) { // an earlier segment whose prefix is within one mismatch reports this alignment
+					uint32_t oo, kk;
+					idx_segment(n, segs, k, oo, kk);
+					if ((uint32_t)__popc((c[u].m >> oo) & ((1u << kk) - 1u)) + 1u >= kk) good = false;
+				}
+				cnt = (uint32_t)__popc(c[u].m);
+			}
+			const bool family = good && (meta2[u] & 1023u) != 0u; // 5'/3' shift families fan out to several candidates: the general path
+			if (family) emit_family(hs, seq[u], clen[u], cand_bits, meta[u], meta2[u], x, cnt);
+			// the plain case (no shift family): at most one hit per candidate, appended with one atomic per warp
+			bool one = good && !family;
+			uint32_t wstart = 0;
 			if (one) {
-				const unsigned long long at = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
-				if (at < hs.cap) {
-					hs.key[at] = hit_key_pack(seq, meta >> 12, cand_bits, cnt, ENT_FULL, (meta >> 11) & 1u);
-					hs.val[at] = wstart + 31u;
+				const int64_t ws = x - (int64_t)((meta[u] >> 6) & 31u);
+				one = ws >= 0 && ws + 32 <= (int64_t)clen[u];
+				wstart = (uint32_t)ws;
+			}
+			const uint32_t bal = __ballot_sync(0xffffffffu, one);
+			if (bal) {
+				unsigned long long base = 0;
+				if (lane == 0u) base = atomicAdd(hs.count, (unsigned long long)__popc(bal));
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (one) {
+					const unsigned long long at = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+					if (at < hs.cap) {
+						hs.key[at] = hit_key_pack(seq[u], meta[u] >> 12, cand_bits, cnt, ENT_FULL, (meta[u] >> 11) & 1u);
+						hs.val[at] = wstart + 31u;
+					}
 				}
 			}
 		}
