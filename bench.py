@@ -1090,7 +1090,9 @@ def run_b200(a):
             "configs": {k: {"value": sig(v["value"]), "unit": v["unit"], "ms": sig(v.get("ms_per_step", v.get("ms_per_iteration"))),
                             "cpu": None if not v.get("cpu_baseline") else sig(v["cpu_baseline"]["value"]),
                             "parity": None if not v.get("parity") else v["parity"]["ok"],
-                            "frac": sig((v.get("roofline") or {}).get("frac"))} for k, v in cfg.items()},
+                            "frac": sig((v.get("roofline") or {}).get("frac")),
+                            **({"ms_first": sig(v["ms_first_iteration"]), "ms_later": sig(v["ms_later_iterations"])} if v.get("ms_later_iterations") else {})}
+                        for k, v in cfg.items()},
             "index_build_ms": sig(index_info["ms_build"]), "index_gb": sig(index_info["bytes"] / 1e9),
             "dp_gcups": None if dp is None else sig(dp["value"]), "dp_gcups_e2e": None if dp is None else sig(dp["e2e"]["value"]),
             "dp_gcups_e2e_words": None if dp is None else sig(dp["e2e_words"]["value"]),
