@@ -495,7 +495,9 @@ int edge_table_build(pcramp_gpu_ctx *ctx, SeqSet &s, const PackParams &pp)
 	CK(cudaStreamSynchronize(st));
 	tr.mark("count + prefix sum");
 	const uint64_t bytes = (uint64_t)h_cnt[0] * 32ull + (uint64_t)total * 4ull + (uint64_t)h_cnt[1] * 4ull + (uint64_t)(EDGE_BUCKETS + 1) * 4ull;
-	if (h_cnt[0] >= (1u << 30) || bytes > (8ull << 30)) return 0; // (hundreds of millions of sequence ends: the scan kernel handles them)
+	// (tens of millions of sequence ends: the scan kernel handles them.  The first test also keeps the 32-bit bucket offsets exact:
+	// a word sits in at most EDGE_POS buckets)
+	if ((uint64_t)h_cnt[0] * EDGE_POS >= (1ull << 31) || bytes > (8ull << 30)) return 0;
 	CK(t.planes.ensure(std::max<size_t>(1, h_cnt[0]) * 16));
 	CK(t.meta.ensure(std::max<size_t>(1, h_cnt[0]) * 16));
 	CK(t.degen.ensure(std::max<size_t>(1, h_cnt[1]) * 4));
